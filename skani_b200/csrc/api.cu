@@ -1,0 +1,419 @@
+// api.cu -- C ABI glue of libskani_b200.so: context, sketch-set lifecycle, host->device staging.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "sk_core.cuh"
+#include "sk_internal.h"
+
+using namespace sk;
+
+namespace {
+constexpr size_t SUBBATCH_BYTES = 512ull << 20;  // bases staged per seeding sub-batch
+
+int check_sketch_params(sk_ctx* ctx, const sk_sketch_params* sp) {
+  if (!sp || sp->c == 0 || sp->marker_c == 0 || sp->k == 0) { ctx->err = "bad sketch params"; return SK_ERR_PARAM; }
+  if (sp->c > sp->marker_c) { ctx->err = "c > marker_c is not allowed (src/params.rs:183-185)"; return SK_ERR_PARAM; }
+  if (sp->k > 16) { ctx->err = "k > 16 is not allowed (src/seeding.rs:239-241)"; return SK_ERR_PARAM; }
+  return SK_OK;
+}
+
+void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t n) {
+  const size_t T = 8, chunk = (n + T - 1) / T;
+  if (n < (8u << 20)) { memcpy(dst, src, n); return; }
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < T; t++) {
+    size_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=] { memcpy(dst + b, src + b, e - b); });
+  }
+  for (auto& t : th) t.join();
+}
+
+template <typename T>
+int concat_dev(sk_ctx* ctx, const std::vector<const T*>& parts, const std::vector<size_t>& counts, T** out) {
+  size_t total = 0;
+  for (size_t c : counts) total += c;
+  T* p = nullptr;
+  SK_CUDA(cudaMalloc((void**)&p, std::max<size_t>(total, 1) * sizeof(T)));
+  size_t o = 0;
+  for (size_t i = 0; i < parts.size(); i++) {
+    if (counts[i]) SK_CUDA(cudaMemcpyAsync(p + o, parts[i], counts[i] * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    o += counts[i];
+  }
+  *out = p;
+  return SK_OK;
+}
+
+// concatenate sketch sets (genome-local indexing everywhere, so only the prefix offsets shift)
+int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_sketch_set** out) {
+  sk_sketch_set* s = new sk_sketch_set();
+  s->ctx = ctx;
+  s->sp = parts.empty() ? sk_sketch_params{125, 15, 1000} : parts[0]->sp;
+  struct Guard { sk_sketch_set* s; ~Guard() { if (s) { free_set_device(s); delete s; } } } guard{s};
+  s->seed_off = {0}; s->uk_off = {0}; s->mk_off = {0}; s->ctg_off = {0};
+  std::vector<size_t> nS, nU, nM, nC, nUG, nCG;
+  for (auto* p : parts) {
+    if (p->sp.c != s->sp.c || p->sp.k != s->sp.k || p->sp.marker_c != s->sp.marker_c) { ctx->err = "sketch parameter mismatch"; return SK_ERR_PARAM; }
+    for (uint32_t g = 0; g < p->G; g++) {
+      s->seed_off.push_back(s->seed_off.back() + (p->seed_off[g + 1] - p->seed_off[g]));
+      s->uk_off.push_back(s->uk_off.back() + (p->uk_off[g + 1] - p->uk_off[g]));
+      s->mk_off.push_back(s->mk_off.back() + (p->mk_off[g + 1] - p->mk_off[g]));
+      s->ctg_off.push_back(s->ctg_off.back() + (p->ctg_off[g + 1] - p->ctg_off[g]));
+      s->total_len.push_back(p->total_len[g]);
+      s->name_rank.push_back(s->G + g);
+    }
+    s->ctg_len.insert(s->ctg_len.end(), p->ctg_len.begin(), p->ctg_len.end());
+    s->G += p->G;
+    nS.push_back(p->S); nU.push_back(p->U); nM.push_back(p->M); nC.push_back(p->C);
+    nUG.push_back(p->U + p->G); nCG.push_back(p->C + p->G);
+  }
+  s->S = s->seed_off.back(); s->U = s->uk_off.back(); s->M = s->mk_off.back(); s->C = s->ctg_off.back();
+#define CAT(field, T, counts)                                         \
+  {                                                                   \
+    std::vector<const T*> v;                                          \
+    for (auto* p : parts) v.push_back(p->field);                      \
+    SK_TRY(concat_dev<T>(ctx, v, counts, &s->field));                 \
+  }
+  CAT(pv_kmer, uint32_t, nS) CAT(pv_pos, uint32_t, nS) CAT(pv_cc, uint32_t, nS) CAT(pv_mult, uint16_t, nS)
+  CAT(kv_pos, uint32_t, nS) CAT(kv_cc, uint32_t, nS) CAT(ukmer, uint32_t, nU) CAT(ustart, uint32_t, nUG)
+  CAT(markers, uint64_t, nM) CAT(ctg_rec_off, uint32_t, nCG) CAT(d_ctg_len, uint32_t, nC)
+#undef CAT
+  SK_CUDA(cudaStreamSynchronize(ctx->stream));
+  guard.s = nullptr;
+  *out = s;
+  return SK_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int sk_ctx_create(int device, sk_ctx** out) {
+  if (!out) return SK_ERR_PARAM;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return SK_ERR_CUDA;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return SK_ERR_CUDA;
+  sk_ctx* ctx = new sk_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return SK_ERR_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SK_ERR_CUDA; }
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&ctx->pinned_free[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->h2d_done[i], cudaEventDisableTiming);
+  }
+  // keep freed stream-ordered allocations cached in the pool
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return SK_OK;
+}
+
+int sk_ctx_destroy(sk_ctx* ctx) {
+  if (!ctx) return SK_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+    if (ctx->pinned_free[i]) cudaEventDestroy(ctx->pinned_free[i]);
+    if (ctx->h2d_done[i]) cudaEventDestroy(ctx->h2d_done[i]);
+  }
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return SK_OK;
+}
+
+const char* sk_last_error(const sk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t sk_ctx_launch_count(const sk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* sk_ctx_stream(const sk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void sk_free(void* p) { free(p); }
+
+int sk_sketch_set_free(sk_sketch_set* set) {
+  if (!set) return SK_OK;
+  cudaSetDevice(set->ctx->device);
+  free_set_device(set);
+  delete set;
+  return SK_OK;
+}
+
+uint32_t sk_sketch_set_n_genomes(const sk_sketch_set* set) { return set ? set->G : 0; }
+
+int sk_sketch_set_genome_info(const sk_sketch_set* s, uint32_t g, uint64_t* n_records, uint64_t* n_kmers,
+                              uint64_t* n_markers, uint64_t* n_contigs, uint64_t* total_len) {
+  if (!s || g >= s->G) return SK_ERR_PARAM;
+  if (n_records) *n_records = s->seed_off[g + 1] - s->seed_off[g];
+  if (n_kmers) *n_kmers = s->uk_off[g + 1] - s->uk_off[g];
+  if (n_markers) *n_markers = s->mk_off[g + 1] - s->mk_off[g];
+  if (n_contigs) *n_contigs = s->ctg_off[g + 1] - s->ctg_off[g];
+  if (total_len) *total_len = s->total_len[g];
+  return SK_OK;
+}
+
+int sk_sketch_set_export(const sk_sketch_set* s, uint32_t g, uint32_t* kmer, uint32_t* pos, uint32_t* contig_canon,
+                         uint64_t* markers, uint32_t* contig_lengths) {
+  if (!s || g >= s->G) return SK_ERR_PARAM;
+  sk_ctx* ctx = s->ctx;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  size_t b = s->seed_off[g], n = s->seed_off[g + 1] - b;
+  if (pos && n) SK_CUDA(cudaMemcpy(pos, s->kv_pos + b, n * 4, cudaMemcpyDeviceToHost));
+  if (contig_canon && n) SK_CUDA(cudaMemcpy(contig_canon, s->kv_cc + b, n * 4, cudaMemcpyDeviceToHost));
+  if (kmer && n) {
+    size_t ub = s->uk_off[g], un = s->uk_off[g + 1] - ub;
+    std::vector<uint32_t> uk(un), us(un + 1);
+    SK_CUDA(cudaMemcpy(uk.data(), s->ukmer + ub, un * 4, cudaMemcpyDeviceToHost));
+    SK_CUDA(cudaMemcpy(us.data(), s->ustart + ub + g, (un + 1) * 4, cudaMemcpyDeviceToHost));
+    for (size_t u = 0; u < un; u++)
+      for (uint32_t i = us[u]; i < us[u + 1]; i++) kmer[i] = uk[u];
+  }
+  size_t mb = s->mk_off[g], mn = s->mk_off[g + 1] - mb;
+  if (markers && mn) SK_CUDA(cudaMemcpy(markers, s->markers + mb, mn * 8, cudaMemcpyDeviceToHost));
+  if (contig_lengths) {
+    size_t cb = s->ctg_off[g], cn = s->ctg_off[g + 1] - cb;
+    for (size_t i = 0; i < cn; i++) contig_lengths[i] = s->ctg_len[cb + i];
+  }
+  return SK_OK;
+}
+
+int sk_sketch_set_set_name_ranks(sk_sketch_set* set, const uint64_t* ranks) {
+  if (!set || !ranks) return SK_ERR_PARAM;
+  for (uint32_t g = 0; g < set->G; g++) set->name_rank[g] = ranks[g];
+  return SK_OK;
+}
+
+int sk_sketch_set_append(sk_sketch_set* dst, const sk_sketch_set* src) {
+  if (!dst || !src) return SK_ERR_PARAM;
+  sk_ctx* ctx = dst->ctx;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  sk_sketch_set* merged = nullptr;
+  SK_TRY(concat_sets(ctx, {dst, src}, &merged));
+  free_set_device(dst);
+  std::vector<uint64_t> ranks = dst->name_rank;
+  uint64_t mx = 0;
+  for (uint64_t r : ranks) mx = std::max(mx, r + 1);
+  for (uint64_t r : src->name_rank) ranks.push_back(mx + r);
+  *dst = *merged;  // takes over device pointers + metadata
+  dst->name_rank = ranks;
+  merged->pv_kmer = nullptr;  // ownership moved
+  delete merged;
+  return SK_OK;
+}
+
+int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* contig_off, uint32_t n_contigs,
+                        const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
+                        sk_sketch_set** out) {
+  if (!ctx || !out || !contig_off || (!genome_of_contig && n_contigs)) return SK_ERR_PARAM;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  SK_TRY(check_sketch_params(ctx, sp));
+  // split into sub-batches of whole genomes (bounds the per-base temporaries)
+  std::vector<sk_sketch_set*> parts;
+  struct Guard { std::vector<sk_sketch_set*>& v; ~Guard() { for (auto* s : v) sk_sketch_set_free(s); } } guard{parts};
+  uint32_t c0 = 0;
+  std::vector<uint32_t> gl;
+  while (c0 < n_contigs) {
+    uint32_t g0 = genome_of_contig[c0];
+    uint32_t c1 = c0;
+    uint64_t bytes = 0;
+    while (c1 < n_contigs) {
+      // extend by one whole genome at a time
+      uint32_t g = genome_of_contig[c1];
+      uint32_t c2 = c1;
+      while (c2 < n_contigs && genome_of_contig[c2] == g) c2++;
+      uint64_t gb = contig_off[c2] - contig_off[c1];
+      if (c1 > c0 && bytes + gb > SUBBATCH_BYTES) break;
+      bytes += gb;
+      c1 = c2;
+    }
+    uint32_t g_last = genome_of_contig[c1 - 1];
+    uint32_t g_next = (c1 < n_contigs) ? genome_of_contig[c1] : n_genomes;
+    // genomes g0 .. g_next-1 belong to this part (empty genomes between are kept as empty sketches)
+    uint32_t g_begin = parts.empty() ? 0 : g0;
+    if (!parts.empty()) {
+      // empty genomes skipped between the previous part and g0 were already attributed to the previous part
+    }
+    (void)g_last;
+    gl.resize(c1 - c0);
+    for (uint32_t i = c0; i < c1; i++) gl[i - c0] = genome_of_contig[i] - g_begin;
+    sk_sketch_set* part = nullptr;
+    SK_TRY(sketch_batch_device(ctx, d_bases, 0, contig_off + c0, c1 - c0, gl.data(), g_next - g_begin, sp, &part));
+    parts.push_back(part);
+    c0 = c1;
+  }
+  if (parts.empty()) {  // no contigs at all: n_genomes empty sketches
+    sk_sketch_set* part = nullptr;
+    uint64_t z = 0;
+    SK_TRY(sketch_batch_device(ctx, d_bases, 0, contig_off ? contig_off : &z, 0, nullptr, n_genomes, sp, &part));
+    *out = part;
+    return SK_OK;
+  }
+  if (parts.size() == 1) {
+    *out = parts[0];
+    parts.clear();
+    return SK_OK;
+  }
+  std::vector<const sk_sketch_set*> cp(parts.begin(), parts.end());
+  SK_TRY(concat_sets(ctx, cp, out));
+  return SK_OK;
+}
+
+int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+                    const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out) {
+  if (!ctx || !out || !contig_off || (!genome_of_contig && n_contigs)) return SK_ERR_PARAM;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  SK_TRY(check_sketch_params(ctx, sp));
+  // is the caller's buffer page-locked? then DMA straight from it; otherwise stage through our pinned buffers
+  bool pinned_src = false;
+  if (bases) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, bases) == cudaSuccess) pinned_src = (attr.type == cudaMemoryTypeHost);
+    cudaGetLastError();
+  }
+  // sub-batch plan (whole genomes)
+  struct Part { uint32_t c0, c1, g_begin, g_end; uint64_t b0, b1; };
+  std::vector<Part> plan;
+  uint32_t c0 = 0;
+  uint64_t max_bytes = 0;
+  while (c0 < n_contigs) {
+    uint32_t c1 = c0;
+    uint64_t bytes = 0;
+    while (c1 < n_contigs) {
+      uint32_t g = genome_of_contig[c1], c2 = c1;
+      while (c2 < n_contigs && genome_of_contig[c2] == g) c2++;
+      uint64_t gb = contig_off[c2] - contig_off[c1];
+      if (c1 > c0 && bytes + gb > SUBBATCH_BYTES) break;
+      bytes += gb;
+      c1 = c2;
+    }
+    Part p;
+    p.c0 = c0; p.c1 = c1;
+    p.g_begin = plan.empty() ? 0 : genome_of_contig[c0];
+    p.g_end = (c1 < n_contigs) ? genome_of_contig[c1] : n_genomes;
+    p.b0 = contig_off[c0]; p.b1 = contig_off[c1];
+    max_bytes = std::max(max_bytes, p.b1 - p.b0);
+    plan.push_back(p);
+    c0 = c1;
+  }
+  if (plan.empty()) return sk_sketch_batch_dev(ctx, nullptr, contig_off, 0, genome_of_contig, n_genomes, sp, out);
+  // device double buffer
+  uint8_t* dbuf[2] = {nullptr, nullptr};
+  struct DGuard { uint8_t** b; ~DGuard() { for (int i = 0; i < 2; i++) if (b[i]) cudaFree(b[i]); } } dguard{dbuf};
+  for (int i = 0; i < 2; i++) SK_CUDA(cudaMalloc((void**)&dbuf[i], max_bytes + 64));
+  if (!pinned_src && ctx->pinned_bytes < max_bytes) {
+    for (int i = 0; i < 2; i++) {
+      if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+      ctx->pinned[i] = nullptr;
+      SK_CUDA(cudaHostAlloc((void**)&ctx->pinned[i], max_bytes, cudaHostAllocDefault));
+    }
+    ctx->pinned_bytes = max_bytes;
+  }
+  cudaEvent_t compute_done[2];
+  for (int i = 0; i < 2; i++) SK_CUDA(cudaEventCreateWithFlags(&compute_done[i], cudaEventDisableTiming));
+  struct EGuard { cudaEvent_t* e; ~EGuard() { for (int i = 0; i < 2; i++) cudaEventDestroy(e[i]); } } eguard{compute_done};
+  auto enqueue_copy = [&](size_t pi) -> int {
+    const Part& p = plan[pi];
+    int b = (int)(pi & 1);
+    size_t nbytes = p.b1 - p.b0;
+    if (pi >= 2) SK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, compute_done[b], 0));  // device buffer free again
+    if (pinned_src) {
+      SK_CUDA(cudaMemcpyAsync(dbuf[b], bases + p.b0, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+      if (pi >= 2) SK_CUDA(cudaEventSynchronize(ctx->pinned_free[b]));  // staging buffer drained
+      parallel_memcpy(ctx->pinned[b], bases + p.b0, nbytes);
+      SK_CUDA(cudaMemcpyAsync(dbuf[b], ctx->pinned[b], nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      SK_CUDA(cudaEventRecord(ctx->pinned_free[b], ctx->copy_stream));
+    }
+    SK_CUDA(cudaEventRecord(ctx->h2d_done[b], ctx->copy_stream));
+    return SK_OK;
+  };
+  std::vector<sk_sketch_set*> parts;
+  struct Guard { std::vector<sk_sketch_set*>& v; ~Guard() { for (auto* s : v) sk_sketch_set_free(s); } } guard{parts};
+  std::vector<uint32_t> gl;
+  SK_TRY(enqueue_copy(0));
+  for (size_t pi = 0; pi < plan.size(); pi++) {
+    const Part& p = plan[pi];
+    int b = (int)(pi & 1);
+    if (pi + 1 < plan.size()) SK_TRY(enqueue_copy(pi + 1));  // overlaps with this part's kernels
+    SK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->h2d_done[b], 0));
+    gl.resize(p.c1 - p.c0);
+    for (uint32_t i = p.c0; i < p.c1; i++) gl[i - p.c0] = genome_of_contig[i] - p.g_begin;
+    sk_sketch_set* part = nullptr;
+    SK_TRY(sketch_batch_device(ctx, dbuf[b], p.b0, contig_off + p.c0, p.c1 - p.c0, gl.data(), p.g_end - p.g_begin, sp, &part));
+    parts.push_back(part);
+    SK_CUDA(cudaEventRecord(compute_done[b], ctx->stream));
+  }
+  SK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  if (parts.size() == 1) {
+    *out = parts[0];
+    parts.clear();
+    return SK_OK;
+  }
+  std::vector<const sk_sketch_set*> cp(parts.begin(), parts.end());
+  SK_TRY(concat_sets(ctx, cp, out));
+  return SK_OK;
+}
+
+int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t* kmer, const uint32_t* pos,
+                         const uint32_t* cc, uint64_t n_records, const uint64_t* markers, uint64_t n_markers,
+                         const uint32_t* contig_lengths, uint32_t n_contigs, sk_sketch_set** out) {
+  if (!ctx || !out || (n_records && (!kmer || !pos || !cc)) || (n_markers && !markers) || (n_contigs && !contig_lengths)) return SK_ERR_PARAM;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  SK_TRY(check_sketch_params(ctx, sp));
+  if (n_records >= (1ull << 31) || n_markers >= (1ull << 31)) { ctx->err = "sketch too large"; return SK_ERR_PARAM; }
+  sk_sketch_set* s = new sk_sketch_set();
+  s->ctx = ctx; s->sp = *sp; s->G = 1;
+  struct Guard { sk_sketch_set* s; ~Guard() { if (s) { free_set_device(s); delete s; } } } guard{s};
+  // position view = records ordered by (contig, pos)
+  std::vector<uint32_t> order(n_records);
+  for (uint64_t i = 0; i < n_records; i++) order[i] = (uint32_t)i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    uint32_t ca = cc[a] >> 1, cb = cc[b] >> 1;
+    if (ca != cb) return ca < cb;
+    return pos[a] < pos[b];
+  });
+  std::vector<uint32_t> hk(n_records), hp(n_records), hc(n_records);
+  std::vector<uint32_t> crl(n_contigs + 2, 0);
+  for (uint64_t i = 0; i < n_records; i++) {
+    hk[i] = kmer[order[i]]; hp[i] = pos[order[i]]; hc[i] = cc[order[i]];
+    uint32_t ctg = hc[i] >> 1;
+    if (ctg >= n_contigs) { ctx->err = "record contig index out of range"; return SK_ERR_PARAM; }
+    crl[ctg + 1]++;
+  }
+  for (uint32_t c = 0; c < n_contigs; c++) crl[c + 1] += crl[c];
+  s->S = n_records; s->C = n_contigs;
+  s->seed_off = {0, n_records};
+  s->ctg_off = {0, n_contigs};
+  s->ctg_len.assign(contig_lengths, contig_lengths + n_contigs);
+  uint64_t tl = 0;
+  for (uint32_t c = 0; c < n_contigs; c++) tl += contig_lengths[c];
+  s->total_len = {tl};
+  s->name_rank = {0};
+  size_t S1 = std::max<size_t>(n_records, 1);
+  SK_CUDA(cudaMalloc((void**)&s->pv_kmer, S1 * 4)); SK_CUDA(cudaMalloc((void**)&s->pv_pos, S1 * 4)); SK_CUDA(cudaMalloc((void**)&s->pv_cc, S1 * 4));
+  SK_CUDA(cudaMalloc((void**)&s->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
+  SK_CUDA(cudaMalloc((void**)&s->ctg_rec_off, (size_t)(n_contigs + 2) * 4));
+  if (n_records) {
+    SK_CUDA(cudaMemcpy(s->pv_kmer, hk.data(), n_records * 4, cudaMemcpyHostToDevice));
+    SK_CUDA(cudaMemcpy(s->pv_pos, hp.data(), n_records * 4, cudaMemcpyHostToDevice));
+    SK_CUDA(cudaMemcpy(s->pv_cc, hc.data(), n_records * 4, cudaMemcpyHostToDevice));
+  }
+  if (n_contigs) SK_CUDA(cudaMemcpy(s->d_ctg_len, contig_lengths, n_contigs * 4, cudaMemcpyHostToDevice));
+  SK_CUDA(cudaMemcpy(s->ctg_rec_off, crl.data(), (size_t)(n_contigs + 1) * 4, cudaMemcpyHostToDevice));
+  DTmp<uint64_t> mraw;
+  SK_CUDA(mraw.alloc(n_markers, ctx->stream));
+  if (n_markers) SK_CUDA(cudaMemcpyAsync(mraw.p, markers, n_markers * 8, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<uint64_t> raw_off = {0, n_markers};
+  SK_TRY(build_views(ctx, s, mraw.p, raw_off));
+  SK_CUDA(cudaStreamSynchronize(ctx->stream));
+  guard.s = nullptr;
+  *out = s;
+  return SK_OK;
+}
+
+}  // extern "C"

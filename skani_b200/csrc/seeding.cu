@@ -1,0 +1,487 @@
+// seeding.cu -- FracMinHash seeding + sketch assembly on the device (sm_100a).
+//
+// Replaces avx2_seeding::avx2_fmh_seeds (reference src/avx2_seeding.rs:33-272), Sketch::add_seed_position
+// (src/types.rs:281-304) and the per-file assembly of file_io::fastx_to_sketches (src/file_io.rs:141-252).
+//
+// Pipeline for one sub-batch of contigs (all arrays device resident):
+//   pack_kernel     ASCII -> 2-bit units (u64 per 32 bases) + 'N' bitmask (u32 per 32 bases)        [HBM bound: 1.4 B/base]
+//   hashpass_kernel per unit: 32 windows -> seed k-mer -> mm_hash64 -> 32-bit pass mask + popcount  [integer-ALU bound]
+//   (cub) exclusive scan of popcounts -> record offsets in (genome, contig, pos) order
+//   expand_kernel   per set bit: (kmer, pos, contig<<1|canonical) record + canonical 21-mer marker for hash < T_marker
+//   build_views     k-mer-ordered view (segmented radix sort per genome), distinct k-mer groups, multiplicities,
+//                   marker sort + dedup per genome  (the flat-array equivalent of the reference's HashMap/HashSet)
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
+
+#include "sk_core.cuh"
+#include "sk_internal.h"
+
+namespace sk {
+
+uint64_t count_launch(sk_ctx* ctx, uint64_t n) {
+  ctx->launches += n;
+  return ctx->launches;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PACK_THREADS = 256;
+
+// contig lookup for a unit: block-level narrowed binary search over the unit prefix offsets
+__device__ __forceinline__ uint32_t find_contig(const uint32_t* __restrict__ cuoff, uint32_t n_contigs, uint32_t u,
+                                                uint32_t lo_hint, uint32_t hi_hint) {
+  uint32_t lo = lo_hint, hi = hi_hint;  // invariant: cuoff[lo] <= u < cuoff[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (cuoff[mid] <= u) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ coff, const uint32_t* __restrict__ cuoff,
+            const uint32_t* __restrict__ clen, uint32_t n_contigs, uint32_t n_units, uint64_t* __restrict__ P,
+            uint32_t* __restrict__ NM, uint32_t* __restrict__ ucontig) {
+  __shared__ uint8_t lut[256];
+  __shared__ uint32_t s_c0, s_c1;
+  lut[threadIdx.x] = (uint8_t)ascii_code(threadIdx.x);
+  uint32_t u0 = blockIdx.x * PACK_THREADS;
+  if (threadIdx.x == 0) {
+    uint32_t ulast = min(u0 + PACK_THREADS - 1, n_units - 1);
+    s_c0 = find_contig(cuoff, n_contigs, u0, 0, n_contigs);
+    s_c1 = find_contig(cuoff, n_contigs, ulast, 0, n_contigs);
+  }
+  __syncthreads();
+  uint32_t u = u0 + threadIdx.x;
+  if (u >= n_units) return;
+  uint32_t ci = find_contig(cuoff, n_contigs, u, s_c0, s_c1 + 1);
+  uint32_t ul = u - cuoff[ci];
+  uint32_t len = clen[ci];
+  uint32_t nvalid = min(32u, len - 32u * ul);
+  const uint8_t* src = ascii + coff[ci] + 32ull * ul;
+  // realign to 4-byte words: 9 aligned words cover any 32-byte span
+  uintptr_t addr = (uintptr_t)src;
+  const uint32_t* wp = (const uint32_t*)(addr & ~(uintptr_t)3);
+  uint32_t sh = (uint32_t)(addr & 3) * 8;
+  uint32_t nwords = (nvalid + (uint32_t)(addr & 3) + 3) >> 2;  // words overlapping the valid span
+  uint32_t w[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) w[i] = (i < (int)nwords) ? __ldg(wp + i) : 0u;
+  uint64_t packed = 0;
+  uint32_t nm = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t r = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      uint32_t j = i * 4 + b;
+      uint32_t v = lut[(r >> (8 * b)) & 0xFFu];
+      if (j >= nvalid) v = 0;
+      packed |= (uint64_t)(v & 3u) << (2 * j);
+      nm |= (v >> 2) << j;
+    }
+  }
+  P[u] = packed;
+  NM[u] = nm;
+  ucontig[u] = ci;
+}
+
+constexpr int HASH_THREADS = 128;
+
+__global__ void __launch_bounds__(HASH_THREADS)
+hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM, const uint32_t* __restrict__ ucontig,
+                const uint32_t* __restrict__ cuoff, const uint32_t* __restrict__ clen, uint32_t n_units,
+                uint64_t seed_mask, uint64_t threshold, uint32_t* __restrict__ PM, uint32_t* __restrict__ cnt) {
+  uint32_t u = blockIdx.x * HASH_THREADS + threadIdx.x;
+  if (u >= n_units) return;
+  uint32_t ci = ucontig[u];
+  uint32_t ul = u - cuoff[ci];
+  uint32_t n = clen[ci];
+  uint64_t hi = P[u];
+  uint64_t lo = ul ? P[u - 1] : 0ull;
+  uint32_t nhi = NM[u];
+  uint32_t nlo = ul ? NM[u - 1] : 0u;
+  uint32_t pass = unit_pass_mask(lo, hi, nlo, nhi, n, ul, seed_mask, threshold);
+  PM[u] = pass;
+  cnt[u] = __popc(pass);
+}
+
+// one thread per unit with a non-empty pass mask: regenerate the few passing windows and emit their records
+__global__ void __launch_bounds__(256)
+expand_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ ucontig, const uint32_t* __restrict__ cuoff,
+              const uint32_t* __restrict__ clocal, uint32_t n_units, const uint32_t* __restrict__ PM,
+              const uint32_t* __restrict__ uoff, uint64_t seed_mask, uint64_t threshold_marker,
+              uint32_t* __restrict__ pv_kmer, uint32_t* __restrict__ pv_pos, uint32_t* __restrict__ pv_cc,
+              uint64_t* __restrict__ mkv) {
+  uint32_t u = blockIdx.x * 256 + threadIdx.x;
+  if (u >= n_units) return;
+  uint32_t pass = PM[u];
+  if (pass == 0) return;
+  uint32_t ci = ucontig[u];
+  uint32_t ul = u - cuoff[ci];
+  uint64_t hi = P[u];
+  uint64_t lo = ul ? P[u - 1] : 0ull;
+  WindowCtx w = make_window_ctx(lo, hi);
+  uint32_t o = uoff[u];
+  uint32_t cl = clocal[ci];
+  while (pass) {
+    uint32_t j = __ffs(pass) - 1;
+    pass &= pass - 1;
+    bool canon;
+    uint32_t seed = window_seed(w, j, seed_mask, &canon);
+    pv_kmer[o] = seed;
+    pv_pos[o] = 32u * ul + j;                       // index of the window's last base (src/avx2_seeding.rs:184,207)
+    pv_cc[o] = (cl << 1) | (canon ? 1u : 0u);       // SeedPosition::new (src/types.rs:135-143)
+    // marker gated by the SEED's hash (src/avx2_seeding.rs:197)
+    mkv[o] = (mm_hash64(seed) < threshold_marker) ? window_marker(w, j) : ~0ull;
+    o++;
+  }
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n,
+                                  uint32_t src_len, uint32_t total, uint32_t* __restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = idx[i];
+  dst[i] = (k >= src_len) ? total : src[k];
+}
+
+__global__ void marker_flag_kernel(const uint64_t* __restrict__ mkv, uint32_t n, uint32_t* __restrict__ flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (mkv[i] != ~0ull) ? 1u : 0u;
+}
+__global__ void marker_scatter_kernel(const uint64_t* __restrict__ mkv, const uint32_t* __restrict__ scan, uint32_t n,
+                                      uint64_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && mkv[i] != ~0ull) out[scan[i]] = mkv[i];
+}
+
+// ---- view building (block per genome) ------------------------------------------------------------------
+__global__ void iota_local_kernel(const uint64_t* __restrict__ seg_off, uint32_t* __restrict__ vals) {
+  uint32_t g = blockIdx.x;
+  uint64_t b = seg_off[g], e = seg_off[g + 1];
+  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) vals[i] = (uint32_t)(i - b);
+}
+
+// after the per-genome sort by k-mer: gather the k-mer view and flag group heads
+__global__ void kview_gather_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ skmer,
+                                    const uint32_t* __restrict__ perm, const uint32_t* __restrict__ pv_pos,
+                                    const uint32_t* __restrict__ pv_cc, uint32_t* __restrict__ kv_pos,
+                                    uint32_t* __restrict__ kv_cc, uint32_t* __restrict__ head) {
+  uint32_t g = blockIdx.x;
+  uint64_t b = seg_off[g], e = seg_off[g + 1];
+  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+    uint32_t r = perm[i];
+    kv_pos[i] = pv_pos[b + r];
+    kv_cc[i] = pv_cc[b + r];
+    head[i] = (i == b || skmer[i] != skmer[i - 1]) ? 1u : 0u;
+  }
+}
+
+// hscan = exclusive scan of head flags (global).  Group id of sorted element i = hscan[i] + head[i] - 1 (global);
+// writes distinct k-mers and local group starts (+ one sentinel per genome), then multiplicities per pv record.
+__global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ skmer,
+                              const uint32_t* __restrict__ head, const uint32_t* __restrict__ hscan, uint32_t total_groups,
+                              uint32_t n_genomes, uint32_t* __restrict__ ukmer, uint32_t* __restrict__ ustart) {
+  uint32_t g = blockIdx.x;
+  uint64_t b = seg_off[g], e = seg_off[g + 1];
+  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+    if (head[i]) {
+      uint32_t gid = hscan[i];
+      ukmer[gid] = skmer[i];
+      ustart[gid + g] = (uint32_t)(i - b);
+    }
+  }
+  if (threadIdx.x == 0) {
+    // sentinel of genome g sits right after its last group: global group index of next genome's first group
+    uint64_t total = seg_off[n_genomes];
+    uint32_t next_gid = (e < total) ? hscan[e] : total_groups;  // head[e] is always 1, so hscan[e] = #groups before e
+    ustart[next_gid + g] = (uint32_t)(e - b);
+  }
+}
+
+__global__ void mult_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ head,
+                            const uint32_t* __restrict__ hscan, const uint32_t* __restrict__ perm,
+                            const uint32_t* __restrict__ ustart, uint16_t* __restrict__ pv_mult) {
+  uint32_t g = blockIdx.x;
+  uint64_t b = seg_off[g], e = seg_off[g + 1];
+  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+    uint32_t gid = hscan[i] + head[i] - 1;
+    uint32_t cntv = ustart[gid + g + 1] - ustart[gid + g];
+    pv_mult[b + perm[i]] = (uint16_t)min(cntv, 65535u);
+  }
+}
+
+// markers: flag distinct values inside each genome's sorted segment
+__global__ void marker_head_kernel(const uint64_t* __restrict__ seg_off, const uint64_t* __restrict__ mk,
+                                   uint32_t* __restrict__ head) {
+  uint32_t g = blockIdx.x;
+  uint64_t b = seg_off[g], e = seg_off[g + 1];
+  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) head[i] = (i == b || mk[i] != mk[i - 1]) ? 1u : 0u;
+}
+__global__ void marker_compact_kernel(const uint64_t* __restrict__ mk, const uint32_t* __restrict__ head,
+                                      const uint32_t* __restrict__ hscan, uint32_t n, uint64_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && head[i]) out[hscan[i]] = mk[i];
+}
+__global__ void gather_scan_at_kernel(const uint32_t* __restrict__ scan, const uint64_t* __restrict__ at, uint32_t n,
+                                      uint64_t len, uint32_t total, uint64_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (at[i] >= len) ? (uint64_t)total : (uint64_t)scan[at[i]];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static inline uint32_t div_up(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+template <typename T>
+static int scan_exclusive(sk_ctx* ctx, const T* in, T* out, size_t n) {
+  size_t tb = 0;
+  SK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, ctx->stream));
+  DTmp<uint8_t> tmp;
+  SK_CUDA(tmp.alloc(tb, ctx->stream));
+  SK_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n, ctx->stream));
+  return SK_OK;
+}
+
+void free_set_device(sk_sketch_set* s) {
+  void* ptrs[] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart,
+                  s->markers, s->ctg_rec_off, s->d_ctg_len};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  s->pv_kmer = s->pv_pos = s->pv_cc = s->kv_pos = s->kv_cc = s->ukmer = s->ustart = s->ctg_rec_off = s->d_ctg_len = nullptr;
+  s->pv_mult = nullptr;
+  s->markers = nullptr;
+}
+
+// Given the position view (pv_kmer/pv_pos/pv_cc filled, set->seed_off known) and the raw (unsorted, possibly
+// duplicated) markers per genome, build the k-mer view, groups, multiplicities and the sorted distinct marker arrays.
+int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const std::vector<uint64_t>& raw_mk_off) {
+  const uint32_t G = set->G;
+  const size_t S = set->S;
+  cudaStream_t st = ctx->stream;
+  DTmp<uint64_t> d_seed_off, d_rawmk_off;
+  SK_CUDA(d_seed_off.alloc(G + 1, st));
+  SK_CUDA(cudaMemcpyAsync(d_seed_off.p, set->seed_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  SK_CUDA(cudaMalloc((void**)&set->kv_pos, std::max<size_t>(S, 1) * 4));
+  SK_CUDA(cudaMalloc((void**)&set->kv_cc, std::max<size_t>(S, 1) * 4));
+  SK_CUDA(cudaMalloc((void**)&set->pv_mult, std::max<size_t>(S, 1) * 2));
+  set->uk_off.assign(G + 1, 0);
+  if (S > 0) {
+    if (S >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 seed records"; return SK_ERR_PARAM; }
+    DTmp<uint32_t> vals, skmer, perm, head, hscan;
+    SK_CUDA(vals.alloc(S, st)); SK_CUDA(skmer.alloc(S, st)); SK_CUDA(perm.alloc(S, st));
+    SK_CUDA(head.alloc(S + 1, st)); SK_CUDA(hscan.alloc(S + 1, st));
+    iota_local_kernel<<<G, 256, 0, st>>>(d_seed_off.p, vals.p); count_launch(ctx);
+    size_t tb = 0;
+    int end_bit = std::min(32, (int)(2 * set->sp.k));
+    SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tb, set->pv_kmer, skmer.p, vals.p, perm.p, (int)S, (int)G,
+                                                     d_seed_off.p, d_seed_off.p + 1, 0, end_bit, st));
+    DTmp<uint8_t> tmp;
+    SK_CUDA(tmp.alloc(tb, st));
+    SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp.p, tb, set->pv_kmer, skmer.p, vals.p, perm.p, (int)S, (int)G,
+                                                     d_seed_off.p, d_seed_off.p + 1, 0, end_bit, st));
+    kview_gather_kernel<<<G, 256, 0, st>>>(d_seed_off.p, skmer.p, perm.p, set->pv_pos, set->pv_cc, set->kv_pos,
+                                           set->kv_cc, head.p); count_launch(ctx);
+    SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, S));
+    // total groups and per-genome group offsets
+    DTmp<uint64_t> d_ukoff;
+    SK_CUDA(d_ukoff.alloc(G + 1, st));
+    uint32_t last_head = 0, last_scan = 0;
+    SK_CUDA(cudaMemcpyAsync(&last_head, head.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(cudaMemcpyAsync(&last_scan, hscan.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(cudaStreamSynchronize(st));
+    uint32_t U = last_head + last_scan;
+    gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_seed_off.p, G + 1, S, U, d_ukoff.p); count_launch(ctx);
+    SK_CUDA(cudaMemcpyAsync(set->uk_off.data(), d_ukoff.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    set->U = U;
+    SK_CUDA(cudaMalloc((void**)&set->ukmer, std::max<size_t>(U, 1) * 4));
+    SK_CUDA(cudaMalloc((void**)&set->ustart, (size_t)(U + G) * 4));
+    groups_kernel<<<G, 256, 0, st>>>(d_seed_off.p, skmer.p, head.p, hscan.p, U, G, set->ukmer, set->ustart); count_launch(ctx);
+    mult_kernel<<<G, 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult); count_launch(ctx);
+    SK_CUDA(cudaStreamSynchronize(st));
+  } else {
+    set->U = 0;
+    SK_CUDA(cudaMalloc((void**)&set->ukmer, 4));
+    SK_CUDA(cudaMalloc((void**)&set->ustart, (size_t)(G + 1) * 4));
+    SK_CUDA(cudaMemsetAsync(set->ustart, 0, (size_t)(G + 1) * 4, st));
+  }
+  // ---- markers: per-genome sort + dedup (HashSet semantics, reference src/types.rs:269)
+  const size_t MR = raw_mk_off[G];
+  set->mk_off.assign(G + 1, 0);
+  if (MR > 0) {
+    if (MR >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 markers"; return SK_ERR_PARAM; }
+    SK_CUDA(d_rawmk_off.alloc(G + 1, st));
+    SK_CUDA(cudaMemcpyAsync(d_rawmk_off.p, raw_mk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+    DTmp<uint64_t> sorted;
+    SK_CUDA(sorted.alloc(MR, st));
+    size_t tb = 0;
+    SK_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, d_marker_raw, sorted.p, (int)MR, (int)G, d_rawmk_off.p,
+                                                    d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
+    DTmp<uint8_t> tmp;
+    SK_CUDA(tmp.alloc(tb, st));
+    SK_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(tmp.p, tb, d_marker_raw, sorted.p, (int)MR, (int)G, d_rawmk_off.p,
+                                                    d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
+    DTmp<uint32_t> head, hscan;
+    SK_CUDA(head.alloc(MR, st)); SK_CUDA(hscan.alloc(MR, st));
+    marker_head_kernel<<<G, 256, 0, st>>>(d_rawmk_off.p, sorted.p, head.p); count_launch(ctx);
+    SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, MR));
+    uint32_t lh = 0, ls = 0;
+    SK_CUDA(cudaMemcpyAsync(&lh, head.p + (MR - 1), 4, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(cudaMemcpyAsync(&ls, hscan.p + (MR - 1), 4, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(cudaStreamSynchronize(st));
+    uint32_t M = lh + ls;
+    set->M = M;
+    SK_CUDA(cudaMalloc((void**)&set->markers, std::max<size_t>(M, 1) * 8));
+    marker_compact_kernel<<<div_up(MR, 256), 256, 0, st>>>(sorted.p, head.p, hscan.p, (uint32_t)MR, set->markers); count_launch(ctx);
+    DTmp<uint64_t> d_mkoff;
+    SK_CUDA(d_mkoff.alloc(G + 1, st));
+    gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_rawmk_off.p, G + 1, MR, M, d_mkoff.p); count_launch(ctx);
+    SK_CUDA(cudaMemcpyAsync(set->mk_off.data(), d_mkoff.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(cudaStreamSynchronize(st));
+  } else {
+    set->M = 0;
+    SK_CUDA(cudaMalloc((void**)&set->markers, 8));
+  }
+  return SK_OK;
+}
+
+// Seeds all contigs of one sub-batch whose ASCII bases are resident on the device.
+//   d_ascii + (contig_off[i] - ascii_base) is the first byte of contig i.
+int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base, const uint64_t* contig_off, uint32_t n_contigs,
+                        const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t G = n_genomes;
+  sk_sketch_set* set = new sk_sketch_set();
+  set->ctx = ctx; set->sp = *sp; set->G = G;
+  struct Guard { sk_sketch_set* s; ~Guard() { if (s) { free_set_device(s); delete s; } } } guard{set};
+
+  // ---- host-side layout
+  std::vector<uint64_t> coff(n_contigs + 1);
+  std::vector<uint32_t> cuoff(n_contigs + 1), clen(n_contigs), clocal(n_contigs);
+  set->ctg_off.assign(G + 1, 0);
+  set->total_len.assign(G, 0);
+  set->ctg_len.resize(n_contigs);
+  uint64_t units = 0;
+  uint32_t prev_g = 0, rank = 0;
+  for (uint32_t i = 0; i < n_contigs; i++) {
+    uint64_t len = contig_off[i + 1] - contig_off[i];
+    if (contig_off[i + 1] < contig_off[i] || len >= (1ull << 32)) { ctx->err = "contig length out of range (u32 positions, src/types.rs:52)"; return SK_ERR_PARAM; }
+    uint32_t g = genome_of_contig[i];
+    if (g >= G || g < prev_g) { ctx->err = "genome_of_contig must be non-decreasing and < n_genomes"; return SK_ERR_PARAM; }
+    if (g != prev_g || i == 0) rank = 0;
+    prev_g = g;
+    if (rank >= (1u << 30)) { ctx->err = "contig index exceeds 30 bits (src/types.rs:136)"; return SK_ERR_PARAM; }
+    coff[i] = contig_off[i] - ascii_base;
+    cuoff[i] = (uint32_t)units;
+    clen[i] = (uint32_t)len;
+    clocal[i] = rank++;
+    set->ctg_len[i] = (uint32_t)len;
+    set->ctg_off[g + 1]++;
+    set->total_len[g] += len;
+    units += (len + 31) / 32;
+    if (units >= (1ull << 31)) { ctx->err = "sub-batch too large (>= 2^31 units)"; return SK_ERR_PARAM; }
+  }
+  coff[n_contigs] = contig_off[n_contigs] - ascii_base;
+  cuoff[n_contigs] = (uint32_t)units;
+  for (uint32_t g = 0; g < G; g++) set->ctg_off[g + 1] += set->ctg_off[g];
+  set->C = n_contigs;
+  set->name_rank.resize(G);
+  for (uint32_t g = 0; g < G; g++) set->name_rank[g] = g;
+  const uint32_t NU = (uint32_t)units;
+
+  SK_CUDA(cudaMalloc((void**)&set->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
+  SK_CUDA(cudaMalloc((void**)&set->ctg_rec_off, (size_t)(n_contigs + G + 1) * 4));
+  set->seed_off.assign(G + 1, 0);
+
+  DTmp<uint64_t> d_coff, P;
+  DTmp<uint32_t> d_cuoff, d_clen, d_clocal, NM, ucontig, PM, cnt, uoff;
+  std::vector<uint64_t> raw_mk_off(G + 1, 0);
+  DTmp<uint64_t> mkv, mraw;
+  if (NU > 0) {
+    SK_CUDA(d_coff.alloc(n_contigs + 1, st)); SK_CUDA(d_cuoff.alloc(n_contigs + 1, st));
+    SK_CUDA(d_clen.alloc(n_contigs, st)); SK_CUDA(d_clocal.alloc(n_contigs, st));
+    SK_CUDA(cudaMemcpyAsync(d_coff.p, coff.data(), (n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
+    SK_CUDA(cudaMemcpyAsync(d_cuoff.p, cuoff.data(), (n_contigs + 1) * 4, cudaMemcpyHostToDevice, st));
+    SK_CUDA(cudaMemcpyAsync(d_clen.p, clen.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
+    SK_CUDA(cudaMemcpyAsync(d_clocal.p, clocal.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
+    SK_CUDA(cudaMemcpyAsync(set->d_ctg_len, clen.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
+    SK_CUDA(P.alloc(NU, st)); SK_CUDA(NM.alloc(NU, st)); SK_CUDA(ucontig.alloc(NU, st));
+    SK_CUDA(PM.alloc(NU, st)); SK_CUDA(cnt.alloc(NU, st)); SK_CUDA(uoff.alloc(NU, st));
+
+    pack_kernel<<<div_up(NU, PACK_THREADS), PACK_THREADS, 0, st>>>(d_ascii, d_coff.p, d_cuoff.p, d_clen.p, n_contigs, NU,
+                                                                  P.p, NM.p, ucontig.p); count_launch(ctx);
+    const uint64_t seed_mask = ~0ull >> (64 - 2 * sp->k);
+    const uint64_t thr = ~0ull / sp->c, thr_m = ~0ull / sp->marker_c;  // src/avx2_seeding.rs:93-94
+    hashpass_kernel<<<div_up(NU, HASH_THREADS), HASH_THREADS, 0, st>>>(P.p, NM.p, ucontig.p, d_cuoff.p, d_clen.p, NU, seed_mask,
+                                                                      thr, PM.p, cnt.p); count_launch(ctx);
+    SK_TRY(scan_exclusive<uint32_t>(ctx, cnt.p, uoff.p, NU));
+    uint32_t last_cnt = 0, last_off = 0;
+    SK_CUDA(cudaMemcpyAsync(&last_cnt, cnt.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(cudaMemcpyAsync(&last_off, uoff.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
+    // record offset of every contig's first unit (-> per-genome offsets and per-contig record offsets)
+    DTmp<uint32_t> d_crec;
+    SK_CUDA(d_crec.alloc(n_contigs + 1, st));
+    SK_CUDA(cudaStreamSynchronize(st));
+    const uint32_t S = last_cnt + last_off;
+    gather_u32_kernel<<<div_up(n_contigs + 1, 256), 256, 0, st>>>(uoff.p, d_cuoff.p, n_contigs + 1, NU, S, d_crec.p); count_launch(ctx);
+    std::vector<uint32_t> crec(n_contigs + 1);
+    SK_CUDA(cudaMemcpyAsync(crec.data(), d_crec.p, (n_contigs + 1) * 4, cudaMemcpyDeviceToHost, st));
+    set->S = S;
+    SK_CUDA(cudaMalloc((void**)&set->pv_kmer, std::max<size_t>(S, 1) * 4));
+    SK_CUDA(cudaMalloc((void**)&set->pv_pos, std::max<size_t>(S, 1) * 4));
+    SK_CUDA(cudaMalloc((void**)&set->pv_cc, std::max<size_t>(S, 1) * 4));
+    SK_CUDA(mkv.alloc(S, st));
+    expand_kernel<<<div_up(NU, 256), 256, 0, st>>>(P.p, ucontig.p, d_cuoff.p, d_clocal.p, NU, PM.p, uoff.p, seed_mask, thr_m,
+                                                   set->pv_kmer, set->pv_pos, set->pv_cc, mkv.p); count_launch(ctx);
+    SK_CUDA(cudaStreamSynchronize(st));
+    // per-genome record offsets + per-contig local record offsets (with one sentinel per genome)
+    std::vector<uint32_t> crl(n_contigs + G + 1, 0);
+    for (uint32_t g = 0; g < G; g++) {
+      uint64_t c0 = set->ctg_off[g], c1 = set->ctg_off[g + 1];
+      uint32_t base = (c0 < n_contigs) ? crec[c0] : S;
+      set->seed_off[g] = base;
+      for (uint64_t c = c0; c < c1; c++) crl[c + g] = crec[c] - base;
+      uint32_t endrec = (c1 < n_contigs) ? crec[c1] : S;
+      crl[c1 + g] = endrec - base;
+    }
+    set->seed_off[G] = S;
+    SK_CUDA(cudaMemcpyAsync(set->ctg_rec_off, crl.data(), (size_t)(n_contigs + G) * 4, cudaMemcpyHostToDevice, st));
+    // raw markers: compact the flagged values (order inside a genome is irrelevant: they are sorted + deduped next)
+    if (S > 0) {
+      DTmp<uint32_t> mflag, mscan;
+      SK_CUDA(mflag.alloc(S, st)); SK_CUDA(mscan.alloc(S, st));
+      marker_flag_kernel<<<div_up(S, 256), 256, 0, st>>>(mkv.p, S, mflag.p); count_launch(ctx);
+      SK_TRY(scan_exclusive<uint32_t>(ctx, mflag.p, mscan.p, S));
+      uint32_t lf = 0, ls = 0;
+      SK_CUDA(cudaMemcpyAsync(&lf, mflag.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
+      SK_CUDA(cudaMemcpyAsync(&ls, mscan.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
+      DTmp<uint64_t> d_so, d_mo;
+      SK_CUDA(d_so.alloc(G + 1, st)); SK_CUDA(d_mo.alloc(G + 1, st));
+      SK_CUDA(cudaMemcpyAsync(d_so.p, set->seed_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+      SK_CUDA(cudaStreamSynchronize(st));
+      uint32_t MR = lf + ls;
+      SK_CUDA(mraw.alloc(MR, st));
+      marker_scatter_kernel<<<div_up(S, 256), 256, 0, st>>>(mkv.p, mscan.p, S, mraw.p); count_launch(ctx);
+      gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(mscan.p, d_so.p, G + 1, S, MR, d_mo.p); count_launch(ctx);
+      SK_CUDA(cudaMemcpyAsync(raw_mk_off.data(), d_mo.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
+      SK_CUDA(cudaStreamSynchronize(st));
+    }
+  } else {
+    set->S = 0;
+    SK_CUDA(cudaMalloc((void**)&set->pv_kmer, 4)); SK_CUDA(cudaMalloc((void**)&set->pv_pos, 4)); SK_CUDA(cudaMalloc((void**)&set->pv_cc, 4));
+    SK_CUDA(cudaMemsetAsync(set->ctg_rec_off, 0, (size_t)(n_contigs + G + 1) * 4, st));
+  }
+  // free the big per-base temporaries before the sort temporaries are allocated
+  P.release(); NM.release(); ucontig.release(); PM.release(); cnt.release(); uoff.release(); mkv.release();
+  SK_TRY(build_views(ctx, set, mraw.p, raw_mk_off));
+  SK_CUDA(cudaStreamSynchronize(st));
+  guard.s = nullptr;
+  *out = set;
+  return SK_OK;
+}
+
+}  // namespace sk

@@ -1,0 +1,95 @@
+// sk_internal.h -- host-side structures shared by the translation units of libskani_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/skani_b200.h"
+
+struct sk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+  // pinned staging buffers for host->device pipelining (sk_sketch_batch)
+  uint8_t* pinned[2] = {nullptr, nullptr};
+  size_t pinned_bytes = 0;
+  cudaEvent_t pinned_free[2] = {nullptr, nullptr};
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+};
+
+struct sk_sketch_set {
+  sk_ctx* ctx = nullptr;
+  sk_sketch_params sp{};
+  uint32_t G = 0;
+  // ---- host metadata (prefix offsets have G+1 entries)
+  std::vector<uint64_t> seed_off, uk_off, mk_off, ctg_off;
+  std::vector<uint32_t> ctg_len;     // all contigs, genome-major
+  std::vector<uint64_t> total_len;   // per genome (Sketch.total_sequence_length)
+  std::vector<uint64_t> name_rank;   // per genome; order of file names (switch_qr tie-break)
+  // ---- device arrays
+  size_t S = 0, U = 0, M = 0, C = 0;
+  uint32_t *pv_kmer = nullptr, *pv_pos = nullptr, *pv_cc = nullptr;  // [S] position-ordered view (genome, contig, pos)
+  uint16_t* pv_mult = nullptr;                                        // [S] multiplicity of the record's k-mer in its genome (saturating)
+  uint32_t *kv_pos = nullptr, *kv_cc = nullptr;                       // [S] k-mer-ordered view (genome, kmer, contig, pos)
+  uint32_t* ukmer = nullptr;                                          // [U] distinct k-mers, ascending per genome
+  uint32_t* ustart = nullptr;                                         // [U+G] genome g, group u -> ustart[uk_off[g] + g + u] = local start in kv; +1 sentinel per genome
+  uint64_t* markers = nullptr;                                        // [M] sorted distinct per genome
+  uint32_t* ctg_rec_off = nullptr;                                    // [C+G] genome g, contig j -> ctg_rec_off[ctg_off[g] + g + j] = local first pv record; +1 sentinel
+  uint32_t* d_ctg_len = nullptr;                                      // [C]
+};
+
+#define SK_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                 std::to_string(__LINE__) + ")";                                              \
+      return SK_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define SK_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != SK_OK) return rc__; \
+  } while (0)
+
+// stream-ordered temporary allocation
+template <typename T>
+struct DTmp {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DTmp() {}
+  DTmp(const DTmp&) = delete;
+  DTmp& operator=(const DTmp&) = delete;
+  ~DTmp() { release(); }
+  cudaError_t alloc(size_t count, cudaStream_t stream) {
+    release();
+    s = stream;
+    n = count;
+    if (count == 0) count = 1;
+    return cudaMallocAsync((void**)&p, count * sizeof(T), stream);
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  T* take() { T* r = p; p = nullptr; return r; }  // ownership moves to the caller (free with cudaFreeAsync/cudaFree)
+};
+
+namespace sk {
+// seeding.cu
+int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base, const uint64_t* contig_off, uint32_t n_contigs,
+                        const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out);
+int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const std::vector<uint64_t>& raw_mk_off);
+void free_set_device(sk_sketch_set* s);
+// screen.cu / chain.cu
+uint64_t count_launch(sk_ctx* ctx, uint64_t n = 1);
+}  // namespace sk

@@ -1,0 +1,206 @@
+"""Thin Python host layer over the C ABI (ctypes).  Names follow the reference: Sketch sets, screen, chain."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import AniResult, ChainDebug, MapParams, SketchParams, TriangleStats
+
+MIN_LENGTH_CONTIG = 500  # reference src/params.rs:42, applied by file_io::fastx_to_sketches (src/file_io.rs:176)
+
+
+class SkaniError(RuntimeError):
+    pass
+
+
+def sketch_params(c=125, k=15, marker_c=1000):
+    return SketchParams(c, k, marker_c)
+
+
+def map_params(screen_val=0.0, min_af=0.15, both_min_af=-0.01, robust=False, median=False, learned_ani=True,
+               rescue_small=True):
+    return MapParams(screen_val, min_af, both_min_af, int(robust), int(median), int(learned_ani), int(rescue_small))
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        rc = self.L.sk_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise SkaniError("sk_ctx_create failed (rc=%d): a CUDA device is required, there is no CPU fallback" % rc)
+        self.h = h
+
+    def check(self, rc):
+        if rc != 0:
+            raise SkaniError("rc=%d: %s" % (rc, self.L.sk_last_error(self.h).decode()))
+
+    @property
+    def launches(self):
+        return self.L.sk_ctx_launch_count(self.h)
+
+    @property
+    def stream(self):
+        return self.L.sk_ctx_stream(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.sk_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SketchSet:
+    """Device-resident Vec<Sketch> (reference src/types.rs:253-277)."""
+
+    def __init__(self, ctx, handle, names=None):
+        self.ctx, self.h, self.names = ctx, handle, names
+
+    def __len__(self):
+        return self.ctx.L.sk_sketch_set_n_genomes(self.h)
+
+    def info(self, g):
+        v = [C.c_uint64() for _ in range(5)]
+        self.ctx.check(self.ctx.L.sk_sketch_set_genome_info(self.h, g, *[C.byref(x) for x in v]))
+        return dict(zip(("n_records", "n_kmers", "n_markers", "n_contigs", "total_len"), [x.value for x in v]))
+
+    def export(self, g):
+        i = self.info(g)
+        kmer = np.zeros(i["n_records"], np.uint32); pos = np.zeros_like(kmer); cc = np.zeros_like(kmer)
+        mk = np.zeros(i["n_markers"], np.uint64); cl = np.zeros(i["n_contigs"], np.uint32)
+        self.ctx.check(self.ctx.L.sk_sketch_set_export(self.h, g, kmer.ctypes.data, pos.ctypes.data, cc.ctypes.data,
+                                                       mk.ctypes.data, cl.ctypes.data))
+        return dict(kmer=kmer, pos=pos, cc=cc, markers=mk, contig_lengths=cl)
+
+    def append(self, other):
+        self.ctx.check(self.ctx.L.sk_sketch_set_append(self.h, other.h))
+
+    def free(self):
+        if self.h:
+            self.ctx.L.sk_sketch_set_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _as_u8(x):
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(x, np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+def sketch_contigs(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None, device_ptr=None):
+    """sk_sketch_batch on already-laid-out buffers (bases: uint8 array or None when device_ptr is given)."""
+    sp = sp or sketch_params()
+    contig_off = np.ascontiguousarray(contig_off, np.uint64)
+    goc = np.ascontiguousarray(genome_of_contig, np.uint32)
+    out = C.c_void_p()
+    if device_ptr is not None:
+        rc = ctx.L.sk_sketch_batch_dev(ctx.h, device_ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes,
+                                       C.byref(sp), C.byref(out))
+    else:
+        ptr = bases if isinstance(bases, int) else _as_u8(bases).ctypes.data
+        rc = ctx.L.sk_sketch_batch(ctx.h, ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes,
+                                   C.byref(sp), C.byref(out))
+    ctx.check(rc)
+    return SketchSet(ctx, out)
+
+
+def sketch_sequences(ctx, genomes, sp=None, individual_contig=False):
+    """genomes: list of genomes, each a list of contig byte strings (one file's records, in file order).
+    Applies the reference's record rules (file_io.rs:141-362): records < 500 bp are dropped, files without a
+    kept record yield no sketch; with individual_contig every kept record becomes its own sketch."""
+    arrs, goc, g = [], [], 0
+    kept_genomes = []
+    for gi, contigs in enumerate(genomes):
+        kept = [_as_u8(c) for c in contigs if len(c) >= MIN_LENGTH_CONTIG]
+        if not kept:
+            continue
+        if individual_contig:
+            for j, a in enumerate(kept):
+                arrs.append(a); goc.append(g); g += 1
+                kept_genomes.append((gi, j))
+        else:
+            for a in kept:
+                arrs.append(a); goc.append(g)
+            g += 1
+            kept_genomes.append((gi, 0))
+    off = np.zeros(len(arrs) + 1, np.uint64)
+    if arrs:
+        off[1:] = np.cumsum([len(a) for a in arrs])
+    bases = np.concatenate(arrs) if arrs else np.zeros(1, np.uint8)
+    s = sketch_contigs(ctx, bases, off, goc, g, sp)
+    s.names = kept_genomes
+    return s
+
+
+def _pairs_out(ctx, fn, *args):
+    pp = C.POINTER(C.c_uint64)(); n = C.c_uint64()
+    ctx.check(fn(*args, C.byref(pp), C.byref(n)))
+    arr = np.ctypeslib.as_array(pp, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
+    ctx.L.sk_free(pp)
+    return arr
+
+
+def screen_triangle(ctx, sset, mp=None):
+    mp = mp or map_params()
+    return _pairs_out(ctx, ctx.L.sk_screen_triangle, ctx.h, sset.h, C.byref(mp))
+
+
+def screen_query_ref(ctx, refs, queries, mp=None, mode=0):
+    mp = mp or map_params()
+    pp = C.POINTER(C.c_uint64)(); n = C.c_uint64()
+    ctx.check(ctx.L.sk_screen_query_ref(ctx.h, refs.h, queries.h, C.byref(mp), mode, C.byref(pp), C.byref(n)))
+    arr = np.ctypeslib.as_array(pp, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
+    ctx.L.sk_free(pp)
+    return arr
+
+
+def chain_pairs(ctx, refs, queries, pairs, mp=None):
+    mp = mp or map_params()
+    pairs = np.ascontiguousarray(pairs, np.uint64)
+    out = (AniResult * max(len(pairs), 1))()
+    ctx.check(ctx.L.sk_chain_pairs(ctx.h, refs.h, queries.h, pairs.ctypes.data, len(pairs), C.byref(mp), out))
+    return [out[i] for i in range(len(pairs))]
+
+
+def chain_pair_debug(ctx, refs, queries, ref_id, query_id, mp=None):
+    mp = mp or map_params()
+    d = ChainDebug()
+    ctx.check(ctx.L.sk_chain_pair_debug(ctx.h, refs.h, queries.h, (ref_id << 32) | query_id, C.byref(mp), C.byref(d)))
+
+    def arr(p, shape, dt):
+        n = int(np.prod(shape))
+        return np.ctypeslib.as_array(p, shape=(n,)).astype(dt).reshape(shape).copy() if n else np.zeros(shape, dt)
+    res = dict(result=AniResult.from_buffer_copy(d.result), switched=bool(d.switched),
+               anchors=arr(d.anchors, (d.n_anchors, 5), np.uint32), score=arr(d.score, (d.n_anchors,), np.int64),
+               pointer=arr(d.pointer, (d.n_anchors,), np.uint32),
+               chunk_first=arr(d.chunk_first, (d.n_chunks + 1,), np.uint32) if d.n_chunks else np.zeros(1, np.uint32),
+               chunk_nseeds=arr(d.chunk_nseeds, (d.n_chunks,), np.uint32),
+               intervals=arr(d.intervals, (d.n_intervals, 11), np.int64),
+               est=arr(d.est, (d.n_ests,), np.float64), weight=arr(d.weight, (d.n_ests,), np.uint64))
+    ctx.L.sk_chain_debug_free(C.byref(d))
+    return res
+
+
+def triangle(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=None):
+    """Whole `skani triangle` hot path from host buffers (reference src/triangle.rs:13-105)."""
+    sp = sp or sketch_params(); mp = mp or map_params()
+    contig_off = np.ascontiguousarray(contig_off, np.uint64)
+    goc = np.ascontiguousarray(genome_of_contig, np.uint32)
+    ptr = bases if isinstance(bases, int) else _as_u8(bases).ctypes.data
+    out = C.POINTER(AniResult)(); n = C.c_uint64(); st = TriangleStats()
+    ctx.check(ctx.L.sk_triangle(ctx.h, ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes, C.byref(sp),
+                                C.byref(mp), C.byref(out), C.byref(n), C.byref(st)))
+    res = [AniResult.from_buffer_copy(out[i]) for i in range(n.value)]
+    ctx.L.sk_free(out)
+    return res, st

@@ -68,6 +68,10 @@ const char* sk_last_error(const sk_ctx* ctx);
 uint64_t sk_ctx_launch_count(const sk_ctx* ctx);
 /* CUDA stream the context launches on (cudaStream_t), so callers can bracket it with events */
 void* sk_ctx_stream(const sk_ctx* ctx);
+/* per-kernel device timing for measurement runs: when on, every major kernel launch is bracketed with CUDA events on
+ * the launch stream.  sk_ctx_get_timing writes "kernel_name total_ms launches\n" lines into buf (NUL-terminated). */
+int sk_ctx_set_timing(sk_ctx* ctx, int on);
+int sk_ctx_get_timing(sk_ctx* ctx, char* buf, uint64_t cap, int reset);
 
 /* ---- seeding: replaces avx2_seeding::avx2_fmh_seeds (src/avx2_seeding.rs:33, the path x86-64 hosts run;
  *      bit-exact incl. its 4-lane split, dropped tail windows and 'N' rule) and the Sketch assembly of

@@ -47,6 +47,8 @@ SYMBOLS = [
     ("sk_last_error", C.c_char_p, [vp]),
     ("sk_ctx_launch_count", u64, [vp]),
     ("sk_ctx_stream", vp, [vp]),
+    ("sk_ctx_set_timing", i32, [vp, i32]),
+    ("sk_ctx_get_timing", i32, [vp, C.c_char_p, u64, i32]),
     ("sk_sketch_batch", i32, [vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(vp)]),
     ("sk_sketch_batch_dev", i32, [vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(vp)]),
     ("sk_sketch_set_free", i32, [vp]),

@@ -136,6 +136,34 @@ uint64_t sk_ctx_launch_count(const sk_ctx* ctx) { return ctx ? ctx->launches : 0
 void* sk_ctx_stream(const sk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 void sk_free(void* p) { free(p); }
 
+int sk_ctx_set_timing(sk_ctx* ctx, int on) {
+  if (!ctx) return SK_ERR_PARAM;
+  ctx->timing = on != 0;
+  return SK_OK;
+}
+
+// "name total_ms launches\n" per kernel, accumulated since the last call with reset != 0
+int sk_ctx_get_timing(sk_ctx* ctx, char* buf, uint64_t cap, int reset) {
+  if (!ctx || !buf || cap == 0) return SK_ERR_PARAM;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  SK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      auto& a = ctx->timing_acc[p.name];
+      a.first += ms; a.second += 1;
+    }
+    cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+  }
+  ctx->pending.clear();
+  std::string out;
+  for (auto& kv : ctx->timing_acc) out += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
+  if (out.size() + 1 > cap) return SK_ERR_NOMEM;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  if (reset) ctx->timing_acc.clear();
+  return SK_OK;
+}
+
 int sk_sketch_set_free(sk_sketch_set* set) {
   if (!set) return SK_OK;
   cudaSetDevice(set->ctx->device);
@@ -185,6 +213,7 @@ int sk_sketch_set_export(const sk_sketch_set* s, uint32_t g, uint32_t* kmer, uin
 int sk_sketch_set_set_name_ranks(sk_sketch_set* set, const uint64_t* ranks) {
   if (!set || !ranks) return SK_ERR_PARAM;
   for (uint32_t g = 0; g < set->G; g++) set->name_rank[g] = ranks[g];
+  set->ranks_user_set = true;
   return SK_OK;
 }
 

@@ -1,0 +1,1085 @@
+// chain.cu -- per-pair ANI estimation on the device: seed intersection -> anchors -> chunking -> banded chaining ->
+// chain intervals -> greedy non-overlap selection -> per-chunk identities -> ANI / AF / std / bootstrap CI -> GBDT.
+//
+// Replaces chain::chain_seeds (reference src/chain.rs:144-171) with its callees get_anchors (:608-836),
+// chain_anchors_ani (:838-896), get_chain_intervals (:939-1007), get_nonoverlapping_chains (:1008-1099),
+// calculate_ani (:173-555), bootstrap_interval (:57-86) and regression::predict_from_ani_res (src/regression.rs:30-64).
+//
+// Data layout (HBM): both genomes of a pair are flat sorted arrays (sk_internal.h).  The query-role genome is
+// streamed in (contig, pos) order and probed against the other genome's distinct k-mer array, so anchors come out
+// already in the reference's sorted order (query_contig, query_pos, ref_contig, ref_pos, reverse) with no per-pair sort.
+// Pairs are processed in batches; every stage is one kernel over the batch:
+//   probe_kernel   (block/pair)  k-mer lookup per query record, multiplicity filters, anchor offsets  [scan]
+//   chunk_kernel   (block/pair)  20 kb chunk assignment = two segmented scans (closed form of the sequential loop)
+//   anchor_kernel  (block/pair)  materialise anchors + chunk descriptors
+//   dp_kernel      (thread/chunk) banded DP, chain components, chain intervals
+//   select_kernel  (block/pair)  bitonic sort of intervals (descending derived order), greedy non-overlap filter
+//   chunkstat_kernel (thread/chunk) seeds inside the padded interval union -> per-chunk identity
+//   final_kernel   (block/pair)  sorted (est, weight) -> trimmed weighted mean, AF, std, bootstrap, cutoffs, GBDT
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include "chain_core.cuh"
+#include "sk_internal.h"
+
+namespace sk {
+
+namespace tables {
+#include "gbdt_tables.inc"
+}
+
+__constant__ unsigned char c_gbdt_feat[2][1365];
+__constant__ float c_gbdt_thr[2][1365];
+__constant__ float c_gbdt_leaf[2][1560];
+__constant__ float c_gbdt_shrink[2];
+__constant__ float c_gbdt_bias[2];
+
+struct SetView {
+  const uint32_t *pv_kmer, *pv_pos, *pv_cc;
+  const uint16_t* pv_mult;
+  const uint32_t *kv_pos, *kv_cc, *ukmer, *ustart, *ctg_rec_off;
+};
+struct GenomeMeta {
+  uint64_t seed_off, uk_off, ctg_off;  // bases into the set arrays (ustart base = uk_off + g, ctg_rec_off base = ctg_off + g)
+  uint32_t n_rec, n_uk, n_ctg, g;
+  uint64_t total_len;
+  uint32_t q10, q50, q90, pad;
+};
+struct PairDesc {
+  uint32_t qset, qg, rset, rg;  // query-role (iterated + chunked) and ref-role (probed) genome: set 0 = refs, 1 = queries
+  uint32_t ref_idx, query_idx;
+  uint32_t switched, valid;
+  uint64_t rec_off;             // offset of this pair's slice in the per-record / per-hit workspaces
+};
+struct ChainParams {
+  uint32_t c, k, band;
+  int32_t robust, median, model;  // model: -1 none, 0 C125, 1 C200
+  double frac_cover_cutoff, both_frac_cover_cutoff;
+};
+
+// per-batch workspace (device pointers)
+struct Workspace {
+  // per record of the query-role genome
+  uint32_t* rec_rstart;   // local start of the matching k-mer group in the ref-role k-mer view
+  uint16_t* rec_nh;       // bits 0..14 = number of anchors, bit 15 = "counted" (enters seeds_in_chunk)
+  // per hit record (compact, same slice offsets)
+  uint32_t *hit_rec, *hit_aoff;
+  uint32_t *hit_clfirst, *hit_need, *hit_p0, *hit_cid;  // hit_cid: pair-local chunk id of the first anchor; bit31 of hit_clfirst unused
+  // per pair
+  uint32_t *pairA, *pairH, *pairC;       // anchors, hit records, chunks
+  uint64_t *pairAbase, *pairCbase, *pairIbase;  // exclusive prefix sums over the batch (anchors, chunks, interval capacity)
+  uint32_t* pair_nint;
+  uint32_t *pair_sumlen, *pair_nchains, *pair_tqb_ns;
+  // per anchor
+  AnchorRec* anc;
+  int32_t* score;
+  uint32_t *ptr, *root, *depth, *cnt, *best;
+  // per chunk
+  uint64_t* chunk_first;   // batch-global anchor index (+ sentinel)
+  uint32_t *chunk_pair, *chunk_qctg;
+  int64_t *chunk_lo, *chunk_hi;  // seeds of the chunk: lo < pos <= hi
+  uint32_t *acc_total, *acc_rq0, *acc_rq1, *acc_tbcq, *acc_nint, *chunk_head;
+  double* chunk_est;
+  uint32_t* chunk_w;
+  uint8_t* chunk_valid;
+  uint32_t* chunk_nseeds;
+  // per interval (capacity floor(A/3) per pair)
+  IntervalKey* iv;
+  uint32_t* iv_order;   // sorted order (indices local to the pair's slice)
+  uint8_t* iv_kept;
+  uint32_t* iv_next;
+  uint32_t* acc_list;   // accepted interval indices (greedy)
+  // per pair estimates scratch (sorted est/weight), capacity = chunks
+  double* est_sorted;
+  uint32_t* w_sorted;
+};
+
+constexpr int CT = 256;       // threads per block for block-per-pair kernels
+constexpr int ITEMS = 4;
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: probe
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CT)
+probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const GenomeMeta* __restrict__ m0,
+             const GenomeMeta* __restrict__ m1, ChainParams prm, Workspace ws) {
+  using Scan = cub::BlockScan<uint64_t, CT>;
+  __shared__ typename Scan::TempStorage tmp;
+  const PairDesc pd = pairs[blockIdx.x];
+  if (!pd.valid) {
+    if (threadIdx.x == 0) { ws.pairA[blockIdx.x] = 0; ws.pairH[blockIdx.x] = 0; }
+    return;
+  }
+  const SetView& Q = pd.qset ? s1 : s0;
+  const SetView& R = pd.rset ? s1 : s0;
+  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
+  const GenomeMeta rm = (pd.rset ? m1 : m0)[pd.rg];
+  const uint32_t* __restrict__ ruk = R.ukmer + rm.uk_off;
+  const uint32_t* __restrict__ rus = R.ustart + rm.uk_off + rm.g;
+  const uint32_t nuk = rm.n_uk;
+  uint64_t carry = 0;  // low 32: anchors so far, high 32: hit records so far
+  for (uint32_t t0 = 0; t0 < qm.n_rec; t0 += CT * ITEMS) {
+    uint64_t item[ITEMS];
+    uint32_t rst[ITEMS], nh[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      uint32_t t = t0 + threadIdx.x * ITEMS + it;
+      nh[it] = 0; rst[it] = 0;
+      uint32_t counted = 0;
+      if (t < qm.n_rec) {
+        uint32_t kmer = Q.pv_kmer[qm.seed_off + t];
+        uint32_t mq = Q.pv_mult[qm.seed_off + t];
+        if (mq <= prm.band) {                          // query positions > band: dropped entirely (src/chain.rs:676-678)
+          // binary search the ref-role distinct k-mers
+          uint32_t lo = 0, hi = nuk;
+          while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (ruk[mid] < kmer) lo = mid + 1; else hi = mid;
+          }
+          if (lo < nuk && ruk[lo] == kmer) {
+            uint32_t s = rus[lo], cntr = rus[lo + 1] - s;
+            if (cntr <= prm.band) { counted = 1; nh[it] = cntr; rst[it] = s; }  // else dropped entirely (:695-697)
+          } else {
+            counted = 1;                               // no hit: position still counts (:684-687)
+          }
+        }
+        ws.rec_rstart[pd.rec_off + t] = rst[it];
+        ws.rec_nh[pd.rec_off + t] = (uint16_t)(nh[it] | (counted << 15));
+      }
+      item[it] = (uint64_t)nh[it] | ((uint64_t)(nh[it] ? 1u : 0u) << 32);
+    }
+    uint64_t agg;
+    Scan(tmp).ExclusiveSum(item, item, agg);
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      if (nh[it]) {
+        uint64_t pre = carry + item[it];
+        uint32_t hidx = (uint32_t)(pre >> 32);
+        ws.hit_rec[pd.rec_off + hidx] = t0 + threadIdx.x * ITEMS + it;
+        ws.hit_aoff[pd.rec_off + hidx] = (uint32_t)pre;
+      }
+    }
+    carry += agg;
+  }
+  if (threadIdx.x == 0) { ws.pairA[blockIdx.x] = (uint32_t)carry; ws.pairH[blockIdx.x] = (uint32_t)(carry >> 32); }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2: chunk assignment over the compact hit list
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CT)
+chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const GenomeMeta* __restrict__ m0,
+             const GenomeMeta* __restrict__ m1, Workspace ws) {
+  using ScanF = cub::BlockScan<FirstState, CT>;
+  using ScanM = cub::BlockScan<MinState, CT>;
+  using ScanU = cub::BlockScan<uint32_t, CT>;
+  __shared__ union { typename ScanF::TempStorage f; typename ScanM::TempStorage m; typename ScanU::TempStorage u; } tmp;
+  __shared__ uint32_t sh_ctg[CT], sh_cl[CT];
+  const PairDesc pd = pairs[blockIdx.x];
+  const uint32_t H = ws.pairH[blockIdx.x];
+  if (!pd.valid || H == 0) {
+    if (threadIdx.x == 0) ws.pairC[blockIdx.x] = 0;
+    return;
+  }
+  const SetView& Q = pd.qset ? s1 : s0;
+  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
+  FirstState carryF; carryF.valid = 0; carryF.ctg = 0; carryF.p0 = 0; carryF.a0 = 0;
+  MinState carryM; carryM.valid = 0; carryM.ctg = 0; carryM.v = 0;
+  uint32_t carry_ctg = 0xFFFFFFFFu, carry_cl = 0;  // contig / last chunk_local of the previous hit record
+  uint32_t carryC = 0;                              // chunk starts so far
+  for (uint32_t h0 = 0; h0 < H; h0 += CT * ITEMS) {
+    uint32_t ctg[ITEMS], pos[ITEMS], aoff[ITEMS], nh[ITEMS];
+    FirstState fs[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      uint32_t h = h0 + threadIdx.x * ITEMS + it;
+      fs[it].valid = 0; fs[it].ctg = 0; fs[it].p0 = 0; fs[it].a0 = 0;
+      ctg[it] = pos[it] = aoff[it] = nh[it] = 0;
+      if (h < H) {
+        uint32_t t = ws.hit_rec[pd.rec_off + h];
+        ctg[it] = Q.pv_cc[qm.seed_off + t] >> 1;
+        pos[it] = Q.pv_pos[qm.seed_off + t];
+        aoff[it] = ws.hit_aoff[pd.rec_off + h];
+        nh[it] = ws.rec_nh[pd.rec_off + t] & 0x7FFFu;
+        fs[it].valid = 1; fs[it].ctg = ctg[it]; fs[it].p0 = pos[it]; fs[it].a0 = aoff[it];
+      }
+    }
+    FirstState aggF;
+    ScanF(tmp.f).InclusiveScan(fs, fs, FirstOp(), aggF);
+    __syncthreads();
+    MinState ms[ITEMS];
+    uint32_t need[ITEMS], al[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      uint32_t h = h0 + threadIdx.x * ITEMS + it;
+      ms[it].valid = 0; ms[it].ctg = 0; ms[it].v = 0;
+      need[it] = al[it] = 0;
+      if (h < H) {
+        FirstState f = FirstOp()(carryF, fs[it]);
+        fs[it] = f;
+        need[it] = chunk_need(pos[it], f.p0);
+        al[it] = aoff[it] - f.a0;
+        ms[it].valid = 1; ms[it].ctg = ctg[it];
+        ms[it].v = (int64_t)need[it] - (int64_t)al[it] - (int64_t)(nh[it] - 1);
+      }
+    }
+    carryF = FirstOp()(carryF, aggF);
+    MinState aggM, identM; identM.valid = 0; identM.ctg = 0; identM.v = 0;
+    MinState ex[ITEMS];
+    ScanM(tmp.m).ExclusiveScan(ms, ex, identM, MinOp(), aggM);
+    __syncthreads();
+    uint32_t clf[ITEMS], cll[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      uint32_t h = h0 + threadIdx.x * ITEMS + it;
+      clf[it] = cll[it] = 0;
+      if (h < H) {
+        MinState e = MinOp()(carryM, ex[it]);           // state of everything before this hit
+        bool has_prev = e.valid && e.ctg == ctg[it];
+        clf[it] = chunk_local_of(al[it], has_prev, e.v, need[it]);
+        cll[it] = chunk_local_of((uint64_t)al[it] + nh[it] - 1, has_prev, e.v, need[it]);
+      }
+    }
+    carryM = MinOp()(carryM, aggM);
+    // previous hit's (contig, last chunk) for the chunk-start test of each hit's first anchor
+    sh_ctg[threadIdx.x] = ctg[ITEMS - 1];
+    sh_cl[threadIdx.x] = cll[ITEMS - 1];
+    __syncthreads();
+    uint32_t inc[ITEMS], start0[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      uint32_t h = h0 + threadIdx.x * ITEMS + it;
+      inc[it] = 0; start0[it] = 0;
+      if (h < H) {
+        uint32_t pc, pl;
+        if (it > 0) { pc = ctg[it - 1]; pl = cll[it - 1]; }
+        else if (threadIdx.x > 0) { pc = sh_ctg[threadIdx.x - 1]; pl = sh_cl[threadIdx.x - 1]; }
+        else { pc = carry_ctg; pl = carry_cl; }
+        start0[it] = (h == 0 || pc != ctg[it] || pl != clf[it]) ? 1u : 0u;
+        inc[it] = start0[it] + (cll[it] - clf[it]);
+      }
+    }
+    // last valid hit of the tile -> carry
+    uint32_t last_h = min(H, h0 + CT * ITEMS) - 1 - h0;
+    uint32_t new_ctg = 0, new_cl = 0;
+    __syncthreads();
+    if (threadIdx.x == last_h / ITEMS) { sh_ctg[0] = ctg[last_h % ITEMS]; sh_cl[0] = cll[last_h % ITEMS]; }
+    __syncthreads();
+    new_ctg = sh_ctg[0]; new_cl = sh_cl[0];
+    uint32_t aggU, exu[ITEMS];
+    ScanU(tmp.u).ExclusiveSum(inc, exu, aggU);
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      uint32_t h = h0 + threadIdx.x * ITEMS + it;
+      if (h < H) {
+        ws.hit_clfirst[pd.rec_off + h] = clf[it];
+        ws.hit_need[pd.rec_off + h] = need[it];
+        ws.hit_p0[pd.rec_off + h] = fs[it].p0;
+        ws.hit_cid[pd.rec_off + h] = carryC + exu[it] + start0[it] - 1;  // chunk id of the hit's first anchor
+      }
+    }
+    carryC += aggU;
+    carry_ctg = new_ctg; carry_cl = new_cl;
+  }
+  if (threadIdx.x == 0) ws.pairC[blockIdx.x] = carryC;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3: anchors + chunk descriptors
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CT)
+anchor_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const GenomeMeta* __restrict__ m0,
+              const GenomeMeta* __restrict__ m1, Workspace ws) {
+  const uint32_t p = blockIdx.x;
+  const PairDesc pd = pairs[p];
+  const uint32_t H = ws.pairH[p];
+  if (!pd.valid || H == 0) return;
+  const SetView& Q = pd.qset ? s1 : s0;
+  const SetView& R = pd.rset ? s1 : s0;
+  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
+  const GenomeMeta rm = (pd.rset ? m1 : m0)[pd.rg];
+  const uint64_t abase = ws.pairAbase[p], cbase = ws.pairCbase[p];
+  for (uint32_t h = threadIdx.x; h < H; h += CT) {
+    uint32_t t = ws.hit_rec[pd.rec_off + h];
+    uint32_t nh = ws.rec_nh[pd.rec_off + t] & 0x7FFFu;
+    uint32_t rs = ws.rec_rstart[pd.rec_off + t];
+    uint32_t qpos = Q.pv_pos[qm.seed_off + t];
+    uint32_t qcc = Q.pv_cc[qm.seed_off + t];
+    uint32_t clf = ws.hit_clfirst[pd.rec_off + h], need = ws.hit_need[pd.rec_off + h], p0 = ws.hit_p0[pd.rec_off + h];
+    uint32_t cid = ws.hit_cid[pd.rec_off + h];
+    uint64_t x = abase + ws.hit_aoff[pd.rec_off + h];
+    // is the first anchor a chunk start?  (cid of the previous anchor differs)  recompute from neighbours' ids:
+    // the hit's first anchor starts a chunk iff h == 0 or hit_cid[h] != chunk id of the previous hit's last anchor
+    uint32_t prev_last_cid = 0xFFFFFFFFu;
+    if (h > 0) {
+      uint32_t tp = ws.hit_rec[pd.rec_off + h - 1];
+      uint32_t nhp = ws.rec_nh[pd.rec_off + tp] & 0x7FFFu;
+      uint32_t clfp = ws.hit_clfirst[pd.rec_off + h - 1], needp = ws.hit_need[pd.rec_off + h - 1];
+      uint32_t cllp = min(clfp + nhp - 1, needp);
+      prev_last_cid = ws.hit_cid[pd.rec_off + h - 1] + (cllp - clfp);
+    }
+    uint32_t prev_cid = prev_last_cid, prev_cl = 0;
+    for (uint32_t u = 0; u < nh; u++) {
+      uint32_t cl = min(clf + u, need);                       // contig-local chunk of this anchor
+      uint32_t mycid = cid + (cl - clf);
+      uint32_t rpos = R.kv_pos[rm.seed_off + rs + u];
+      uint32_t rcc = R.kv_cc[rm.seed_off + rs + u];
+      AnchorRec a;
+      a.qpos = qpos; a.rpos = rpos;
+      a.rc = (rcc & ~1u) | ((rcc ^ qcc) & 1u);                // reverse_match = canonical differs (src/chain.rs:709)
+      ws.anc[x + u] = a;
+      if (mycid != prev_cid) {                                 // chunk start: write its descriptor
+        uint64_t c = cbase + mycid;
+        ws.chunk_first[c] = x + u;
+        ws.chunk_pair[c] = p;
+        ws.chunk_qctg[c] = qcc >> 1;
+        ws.chunk_lo[c] = (cl == 0) ? -1ll : (int64_t)p0 + (int64_t)cl * FRAGMENT_LENGTH;   // seeds with pos > lo
+        ws.chunk_hi[c] = (int64_t)p0 + (int64_t)(cl + 1) * FRAGMENT_LENGTH;                // and pos <= hi
+      }
+      prev_cid = mycid; prev_cl = cl;
+    }
+    (void)prev_cl;
+  }
+  // the pair's last chunk is never closed by the loop: it keeps seeds up to its last anchor (src/chain.rs:796-824).
+  // Patched after every descriptor of this pair has been written (same block).
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t h = H - 1;
+    uint32_t t = ws.hit_rec[pd.rec_off + h];
+    uint32_t nh = ws.rec_nh[pd.rec_off + t] & 0x7FFFu;
+    uint32_t clf = ws.hit_clfirst[pd.rec_off + h], need = ws.hit_need[pd.rec_off + h];
+    uint32_t cll = min(clf + nh - 1, need);
+    ws.chunk_hi[cbase + ws.hit_cid[pd.rec_off + h] + (cll - clf)] = (int64_t)Q.pv_pos[qm.seed_off + t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4: banded DP + chain extraction, one thread per chunk
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+dp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
+  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const uint64_t a0 = ws.chunk_first[c], a1 = ws.chunk_first[c + 1];
+  const uint32_t n = (uint32_t)(a1 - a0);
+  const uint32_t p = ws.chunk_pair[c];
+  const uint32_t qctg = ws.chunk_qctg[c];
+  const uint32_t chunk_local_id = (uint32_t)(c - ws.pairCbase[p]);
+  const AnchorRec* a = ws.anc + a0;
+  auto emit = [&](int32_t score, uint32_t num_anchors, uint32_t first, uint32_t bestidx) {
+    const AnchorRec f = a[first], l = a[bestidx];
+    uint32_t r0 = f.rpos < l.rpos ? f.rpos : l.rpos, r1 = f.rpos < l.rpos ? l.rpos : f.rpos;
+    IntervalKey key = make_interval(score, num_anchors, f.qpos, l.qpos, r0, r1, f.rc >> 1, qctg, chunk_local_id, f.rc & 1u);
+    uint32_t slot = atomicAdd(&ws.pair_nint[p], 1u);
+    ws.iv[ws.pairIbase[p] + slot] = key;
+  };
+  dp_chunk(a, n, prm.band, ws.score + a0, ws.ptr + a0, ws.root + a0, ws.depth + a0, ws.cnt + a0, ws.best + a0, emit);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: interval sort + greedy non-overlap selection, block per pair
+// ------------------------------------------------------------------------------------------------------------
+__device__ void block_bitonic_sort_intervals(uint32_t* idx, uint32_t npow2, const IntervalKey* iv) {
+  // idx holds interval indices (0xFFFFFFFF = padding, sorts last); order = interval_before
+  for (uint32_t k = 2; k <= npow2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < npow2; i += blockDim.x) {
+        uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          uint32_t a = idx[i], b = idx[ixj];
+          bool up = ((i & k) == 0);
+          bool a_before_b;
+          if (a == 0xFFFFFFFFu) a_before_b = false;
+          else if (b == 0xFFFFFFFFu) a_before_b = true;
+          else a_before_b = interval_before(iv[a], iv[b]);
+          bool swap = up ? !a_before_b : a_before_b;
+          if (a == b) swap = false;
+          if (swap) { idx[i] = b; idx[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr uint32_t SEL_SMEM_MAX = 4096;  // intervals sorted in shared memory up to this many (power of two)
+
+__global__ void __launch_bounds__(CT)
+select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws) {
+  __shared__ uint32_t s_idx[SEL_SMEM_MAX];
+  __shared__ uint32_t s_nacc;
+  __shared__ int s_dec;
+  const uint32_t p = blockIdx.x;
+  const uint32_t n = ws.pair_nint[p];
+  if (n == 0) return;
+  const uint64_t ib = ws.pairIbase[p];
+  const IntervalKey* iv = ws.iv + ib;
+  uint32_t npow2 = 1;
+  while (npow2 < n) npow2 <<= 1;
+  uint32_t* idx = (npow2 <= SEL_SMEM_MAX) ? s_idx : (ws.iv_order + 4 * ib);  // global fallback slice has >= 2n slots
+  for (uint32_t i = threadIdx.x; i < npow2; i += blockDim.x) idx[i] = i < n ? i : 0xFFFFFFFFu;
+  __syncthreads();
+  block_bitonic_sort_intervals(idx, npow2, iv);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { ws.iv_order[4 * ib + npow2 + i] = idx[i]; }
+  __syncthreads();
+  const uint32_t* order = ws.iv_order + 4 * ib + npow2;  // final sorted order lives after the sort scratch
+  // greedy selection by warp 0 (inherently ordered, src/chain.rs:1016-1095)
+  uint32_t* acc = ws.acc_list + ib;
+  if (threadIdx.x == 0) s_nacc = 0;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const uint32_t lane = threadIdx.x;
+    uint32_t nacc = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t ci = order[i];
+      const IntervalKey c = iv[ci];
+      uint32_t sum_r = 0, hit_r = 0, sum_q = 0, hit_q = 0;
+      for (uint32_t a = lane; a < nacc; a += 32) overlap_contrib(c, iv[acc[a]], &sum_r, &hit_r, &sum_q, &hit_q);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sum_r += __shfl_xor_sync(0xFFFFFFFFu, sum_r, o);
+        hit_r += __shfl_xor_sync(0xFFFFFFFFu, hit_r, o);
+        sum_q += __shfl_xor_sync(0xFFFFFFFFu, sum_q, o);
+        hit_q += __shfl_xor_sync(0xFFFFFFFFu, hit_q, o);
+      }
+      bool ok = overlap_accept(c, sum_r, hit_r, sum_q, hit_q);
+      if (lane == 0) {
+        ws.iv_kept[ib + ci] = ok ? 1 : 0;
+        if (ok) acc[nacc] = ci;
+      }
+      if (ok) nacc++;
+      __syncwarp();
+    }
+    if (lane == 0) s_nacc = nacc;
+  }
+  __syncthreads();
+  // accumulate the kept intervals into their chunks (src/chain.rs:204-251); all integer sums/min/max: order-free
+  const uint32_t nacc = s_nacc;
+  const uint64_t cbase = ws.pairCbase[p];
+  const PairDesc pd = pairs[p];
+  uint32_t my_sum = 0, my_cnt = 0;
+  for (uint32_t a = threadIdx.x; a < nacc; a += blockDim.x) {
+    const uint32_t ci = acc[a];
+    const IntervalKey x = iv[ci];
+    const uint64_t ch = cbase + iv_chunk(x);
+    atomicAdd(&ws.acc_total[ch], iv_num_anchors(x));
+    atomicMin(&ws.acc_rq0[ch], iv_q0(x));
+    atomicMax(&ws.acc_rq1[ch], iv_q1(x));
+    uint32_t span = pd.switched ? (iv_r1(x) - iv_r0(x)) : (iv_q1(x) - iv_q0(x));   // :223-237
+    atomicAdd(&ws.acc_tbcq[ch], span + prm.k + 2 * prm.c);
+    atomicAdd(&ws.acc_nint[ch], 1u);
+    ws.iv_next[ib + ci] = atomicExch(&ws.chunk_head[ch], ci);
+    my_sum += (iv_q1(x) - iv_q0(x)) + 2 * prm.c + prm.k;                            // :244-249 (overlap is always 0)
+    my_cnt += 1;
+  }
+  if (my_cnt) { atomicAdd(&ws.pair_sumlen[p], my_sum); atomicAdd(&ws.pair_nchains[p], my_cnt); }
+  (void)s_dec;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6: per-chunk identity, one thread per chunk
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+chunkstat_kernel(uint64_t n_chunks, const PairDesc* __restrict__ pairs, SetView s0, SetView s1,
+                 const GenomeMeta* __restrict__ m0, const GenomeMeta* __restrict__ m1, ChainParams prm, Workspace ws) {
+  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const uint32_t p = ws.chunk_pair[c];
+  const PairDesc pd = pairs[p];
+  const SetView& Q = pd.qset ? s1 : s0;
+  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
+  ChunkAcc acc;
+  acc.total_anchors = ws.acc_total[c]; acc.rq0 = ws.acc_rq0[c]; acc.rq1 = ws.acc_rq1[c];
+  acc.tbcq = ws.acc_tbcq[c]; acc.n_int = ws.acc_nint[c];
+  ws.chunk_valid[c] = 0;
+  // seeds_in_chunk: counted query records of the chunk's contig with lo < pos <= hi
+  const uint32_t ctg = ws.chunk_qctg[c];
+  const uint32_t* cro = Q.ctg_rec_off + qm.ctg_off + qm.g;
+  uint32_t r0 = cro[ctg], r1 = cro[ctg + 1];
+  const uint32_t* pos = Q.pv_pos + qm.seed_off;
+  const int64_t lo = ws.chunk_lo[c], hi = ws.chunk_hi[c];
+  // first record with pos > lo
+  uint32_t a = r0, b = r1;
+  while (a < b) { uint32_t m = (a + b) >> 1; if ((int64_t)pos[m] <= lo) a = m + 1; else b = m; }
+  uint32_t first = a;
+  b = r1;
+  while (a < b) { uint32_t m = (a + b) >> 1; if ((int64_t)pos[m] <= hi) a = m + 1; else b = m; }
+  uint32_t last = a;  // [first, last)
+  const uint16_t* nhv = ws.rec_nh + pd.rec_off;
+  const uint64_t ib = ws.pairIbase[p];
+  uint32_t n_seeds = 0, num_in = 0, upper_lower = 0;
+  const bool has_int = acc.n_int > 0;
+  for (uint32_t t = first; t < last; t++) {
+    if (!(nhv[t] & 0x8000u)) continue;
+    n_seeds++;
+    if (!has_int) continue;
+    uint32_t ps = pos[t];
+    bool in = false;
+    for (uint32_t i = ws.chunk_head[c]; i != 0xFFFFFFFFu; i = ws.iv_next[ib + i]) {
+      const IntervalKey x = ws.iv[ib + i];
+      uint32_t q0 = iv_q0(x), q1 = iv_q1(x);
+      uint32_t start = q0 > prm.c ? q0 - prm.c : 0;         // max(q0 - c, 0) in i32 (src/chain.rs:239-240)
+      uint32_t stop = q1 + prm.c;
+      if (start <= ps && ps <= stop) { in = true; break; }
+    }
+    if (in) num_in++;
+    if (ps >= acc.rq0 && ps <= acc.rq1) upper_lower++;      // :322-328 with both spacing estimates 0
+  }
+  ws.chunk_nseeds[c] = n_seeds;
+  double est; uint32_t w;
+  if (chunk_estimate(acc, prm.c, prm.k, n_seeds, num_in, upper_lower, &est, &w)) {
+    ws.chunk_est[c] = est; ws.chunk_w[c] = w; ws.chunk_valid[c] = 1;
+    if (prm.c >= 200) atomicAdd(&ws.pair_tqb_ns[p], acc.rq1 - acc.rq0 + 2 * prm.c + prm.k);  // !sensitive_af (:261-264)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K7: final statistics, block per pair
+// ------------------------------------------------------------------------------------------------------------
+struct EstKey { double e; uint32_t w; };
+__device__ __forceinline__ bool est_less(double ea, uint32_t wa, double eb, uint32_t wb) {  // (f64, usize) tuple order (:414)
+  if (ea != eb) return ea < eb;
+  return wa < wb;
+}
+
+constexpr int FT = 128;
+constexpr uint32_t FIN_SMEM_MAX = 2048;
+
+__global__ void __launch_bounds__(FT)
+final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ m0, const GenomeMeta* __restrict__ m1,
+             ChainParams prm, Workspace ws, sk_ani_result* __restrict__ out) {
+  __shared__ double s_e[FIN_SMEM_MAX];
+  __shared__ uint32_t s_w[FIN_SMEM_MAX];
+  __shared__ uint32_t s_n;
+  __shared__ double s_boot[128];
+  __shared__ uint32_t s_lower_i, s_upper_i, s_reject;
+  __shared__ double s_final, s_std;
+  const uint32_t p = blockIdx.x;
+  const PairDesc pd = pairs[p];
+  const GenomeMeta refm = m0[pd.ref_idx];     // the call's ref / query sketches (un-switched, src/chain.rs:477-484)
+  const GenomeMeta qrym = m1[pd.query_idx];
+  sk_ani_result r;
+  memset(&r, 0, sizeof(r));
+  r.ref_id = pd.ref_idx; r.query_id = pd.query_idx;
+  const uint64_t cb = ws.pairCbase[p];
+  const uint32_t nc = ws.pairC[p];
+  // compact valid chunk estimates
+  double* ge = (nc <= FIN_SMEM_MAX) ? s_e : ws.est_sorted + 4 * cb;
+  uint32_t* gw = (nc <= FIN_SMEM_MAX) ? s_w : ws.w_sorted + 4 * cb;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  uint32_t npow2 = 1;
+  while (npow2 < nc) npow2 <<= 1;
+  // deterministic compaction is unnecessary: the list is sorted next (ties are exact duplicates)
+  for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+    if (ws.chunk_valid[cb + i]) {
+      uint32_t slot = atomicAdd(&s_n, 1u);
+      ge[slot] = ws.chunk_est[cb + i]; gw[slot] = ws.chunk_w[cb + i];
+    }
+  }
+  __syncthreads();
+  const uint32_t n = s_n;
+  const uint32_t num_chains = ws.pair_nchains[p];
+  if (n == 0 || num_chains == 0) {                       // src/chain.rs:416-420: default result with ani = NaN
+    if (threadIdx.x == 0) { r.ani = nanf(""); out[p] = r; }
+    return;
+  }
+  uint32_t np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (uint32_t i = n + threadIdx.x; i < np2; i += blockDim.x) { ge[i] = INFINITY; gw[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  for (uint32_t k = 2; k <= np2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
+        uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          bool up = ((i & k) == 0);
+          bool a_lt_b = est_less(ge[i], gw[i], ge[ixj], gw[ixj]);
+          bool b_lt_a = est_less(ge[ixj], gw[ixj], ge[i], gw[i]);
+          bool swap = up ? b_lt_a : a_lt_b;
+          if (swap) { double te = ge[i]; ge[i] = ge[ixj]; ge[ixj] = te; uint32_t tw = gw[i]; gw[i] = gw[ixj]; gw[ixj] = tw; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // sequential part (exact left-to-right f64 sums as the reference): thread 0
+  if (threadIdx.x == 0) {
+    uint64_t total_mult = 0;
+    for (uint32_t i = 0; i < n; i++) total_mult += gw[i];
+    double lower, upper;
+    if (prm.median) { lower = 0.499; upper = 0.501; }
+    else if (prm.robust) { lower = 0.10; upper = 0.90; }
+    else { lower = 0.; upper = 1.; }
+    uint32_t lower_i = 0, upper_i = n - 1;
+    bool cl = false, cu = false;
+    uint64_t curr = 0;
+    const uint64_t tl = (uint64_t)((double)total_mult * lower), tu = (uint64_t)((double)total_mult * upper);
+    for (uint32_t i = 0; i < n; i++) {                   // src/chain.rs:448-460
+      curr += gw[i];
+      if (curr >= tl && !cl) { lower_i = i; cl = true; }
+      if (curr >= tu && !cu) { upper_i = i + 1; cu = true; break; }
+    }
+    double weighted = 0.;
+    uint64_t tm2 = 0;
+    for (uint32_t i = lower_i; i < upper_i; i++) { weighted += ge[i] * (double)gw[i]; tm2 += gw[i]; }
+    s_final = weighted / (double)tm2;
+    // population std of the unweighted estimates (src/chain.rs:28-55)
+    double sum = 0.;
+    for (uint32_t i = 0; i < n; i++) sum += ge[i];
+    double mean = sum / (double)n, var = 0.;
+    for (uint32_t i = 0; i < n; i++) { double d = mean - ge[i]; var += d * d; }
+    s_std = sqrt(var / (double)n);
+    s_lower_i = lower_i; s_upper_i = upper_i;
+    s_reject = 0;
+  }
+  __syncthreads();
+  // bootstrap (src/chain.rs:57-86): 100 replicates x n draws from the weight-expanded pool; replicate r uses draws
+  // [r*n, (r+1)*n) of the WyRand stream seeded with 7, each replicate summed sequentially by one thread.
+  double ci_lo = 0., ci_hi = 1.;
+  if (n >= 10) {
+    uint64_t pool = 0;
+    for (uint32_t i = 0; i < n; i++) pool += gw[i];      // every thread: cheap, avoids another broadcast
+    // prefix sums of weights for idx -> estimate lookup: reuse gw? keep separate: binary search over running sums
+    // (n <= a few thousand; compute cumulative on the fly per thread is O(n) per draw -> too slow; build once)
+    uint64_t* cum = (uint64_t*)(ws.est_sorted + 4 * cb + (nc <= FIN_SMEM_MAX ? 0 : npow2));  // scratch (8 B per chunk available)
+    if (threadIdx.x == 0) {
+      uint64_t run = 0;
+      for (uint32_t i = 0; i < n; i++) { run += gw[i]; cum[i] = run; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 100) {
+      const uint32_t rep = threadIdx.x;
+      double ssum = 0.;
+      bool rej = false;
+      for (uint32_t s = 0; s < n; s++) {
+        bool nr;
+        uint64_t idx = lemire_below(wyrand_at(7, (uint64_t)rep * n + s), pool, &nr);
+        rej |= nr;
+        uint32_t a = 0, b = n;                           // first i with cum[i] > idx
+        while (a < b) { uint32_t m = (a + b) >> 1; if (cum[m] <= idx) a = m + 1; else b = m; }
+        ssum += ge[a];
+      }
+      s_boot[rep] = ssum / (double)n;
+      if (rej) atomicOr(&s_reject, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_reject) {
+        // a Lemire rejection shifts the stream: redo sequentially (probability ~ n*100*pool / 2^64)
+        uint64_t draws = 0;
+        for (uint32_t rep = 0; rep < 100; rep++) {
+          double ssum = 0.;
+          // the reference draws all n indices first, then sums: same stream order
+          for (uint32_t s = 0; s < n; s++) {
+            uint64_t rr = wyrand_at(7, draws++);
+            uint64_t hi = __umul64hi(rr, pool), lo = rr * pool;
+            if (lo < pool) {
+              uint64_t thr = (0 - pool) % pool;
+              while (lo < thr) { rr = wyrand_at(7, draws++); hi = __umul64hi(rr, pool); lo = rr * pool; }
+            }
+            uint32_t a = 0, b = n;
+            while (a < b) { uint32_t m = (a + b) >> 1; if (cum[m] <= hi) a = m + 1; else b = m; }
+            ssum += ge[a];
+          }
+          s_boot[rep] = ssum / (double)n;
+        }
+      }
+      // sort the 100 replicate means, take [4] and [94]
+      for (int i = 1; i < 100; i++) { double v = s_boot[i]; int j = i - 1; while (j >= 0 && s_boot[j] > v) { s_boot[j + 1] = s_boot[j]; j--; } s_boot[j + 1] = v; }
+    }
+    __syncthreads();
+    ci_lo = s_boot[4]; ci_hi = s_boot[94];
+  }
+  if (threadIdx.x == 0) {
+    double final_ani = s_final;
+    const uint32_t sumlen = ws.pair_sumlen[p];
+    const uint32_t tqb = (prm.c < 200) ? sumlen : ws.pair_tqb_ns[p];      // sensitive_af (:183-190, 244-247, 261-264)
+    double covered_query = (double)tqb / (double)qrym.total_len; if (covered_query > 1.) covered_query = 1.;
+    double covered_ref = (double)tqb / (double)refm.total_len; if (covered_ref > 1.) covered_ref = 1.;
+    if (prm.both_frac_cover_cutoff > 0.0) {
+      if (covered_query < prm.both_frac_cover_cutoff || covered_ref < prm.both_frac_cover_cutoff) final_ani = -1.;
+    } else if (covered_query < prm.frac_cover_cutoff && covered_ref < prm.frac_cover_cutoff) {
+      final_ani = -1.;
+    }
+    r.ani = (float)final_ani;
+    r.af_query = (float)covered_query; r.af_ref = (float)covered_ref;
+    r.ci_lower = (float)ci_lo; r.ci_upper = (float)ci_hi; r.std = (float)s_std;
+    r.q10_q = (float)qrym.q10; r.q50_q = (float)qrym.q50; r.q90_q = (float)qrym.q90;
+    r.q10_r = (float)refm.q10; r.q50_r = (float)refm.q50; r.q90_r = (float)refm.q90;
+    r.num_contigs_q = qrym.n_ctg; r.num_contigs_r = refm.n_ctg;
+    r.avg_chain_int_len = sumlen / num_chains;            // u32 division (:421)
+    r.total_bases_covered = tqb;
+    // learned-ANI regression (src/regression.rs:30-64)
+    if (prm.model >= 0 && r.ani > 0.9f && r.total_bases_covered > REGRESS_CUTOFF) {
+      float x[5];
+      x[0] = r.ani * 100.f; x[1] = r.std;
+      if (r.q50_r > r.q50_q) { x[2] = r.q90_r; x[3] = r.q90_q; } else { x[2] = r.q90_q; x[3] = r.q90_r; }
+      x[4] = (float)r.avg_chain_int_len;
+      float pred = gbdt_eval(c_gbdt_feat[prm.model], c_gbdt_thr[prm.model], c_gbdt_leaf[prm.model], 195,
+                             c_gbdt_shrink[prm.model], c_gbdt_bias[prm.model], x);
+      if (pred < 100.f) {
+        r.ci_upper = (r.ci_upper - r.ani) + pred / 100.f;
+        r.ci_lower = (r.ci_lower - r.ani) + pred / 100.f;
+        r.ani = pred / 100.f;
+      }
+    }
+    out[p] = r;
+  }
+}
+
+__global__ void init_chunk_acc_kernel(uint64_t n, Workspace ws) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ws.acc_total[i] = 0; ws.acc_rq0[i] = 0xFFFFFFFFu; ws.acc_rq1[i] = 0; ws.acc_tbcq[i] = 0; ws.acc_nint[i] = 0;
+  ws.chunk_head[i] = 0xFFFFFFFFu;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------------------
+static bool g_tables_uploaded[64] = {false};
+
+static int upload_tables(sk_ctx* ctx) {
+  if (ctx->device < 64 && g_tables_uploaded[ctx->device]) return SK_OK;
+  static float thr[2][1365], leaf[2][1560], shrink[2], bias[2];
+  static unsigned char feat[2][1365];
+  auto b2f = [](uint32_t b) { float f; memcpy(&f, &b, 4); return f; };
+  for (int i = 0; i < 1365; i++) {
+    feat[0][i] = tables::SK_GBDT_C125_FEAT[i]; feat[1][i] = tables::SK_GBDT_C200_FEAT[i];
+    thr[0][i] = b2f(tables::SK_GBDT_C125_THR[i]); thr[1][i] = b2f(tables::SK_GBDT_C200_THR[i]);
+  }
+  for (int i = 0; i < 1560; i++) { leaf[0][i] = b2f(tables::SK_GBDT_C125_LEAF[i]); leaf[1][i] = b2f(tables::SK_GBDT_C200_LEAF[i]); }
+  shrink[0] = b2f(SK_GBDT_C125_SHRINK_BITS); shrink[1] = b2f(SK_GBDT_C200_SHRINK_BITS);
+  bias[0] = b2f(SK_GBDT_C125_BIAS_BITS); bias[1] = b2f(SK_GBDT_C200_BIAS_BITS);
+  SK_CUDA(cudaMemcpyToSymbol(c_gbdt_feat, feat, sizeof(feat)));
+  SK_CUDA(cudaMemcpyToSymbol(c_gbdt_thr, thr, sizeof(thr)));
+  SK_CUDA(cudaMemcpyToSymbol(c_gbdt_leaf, leaf, sizeof(leaf)));
+  SK_CUDA(cudaMemcpyToSymbol(c_gbdt_shrink, shrink, sizeof(shrink)));
+  SK_CUDA(cudaMemcpyToSymbol(c_gbdt_bias, bias, sizeof(bias)));
+  if (ctx->device < 64) g_tables_uploaded[ctx->device] = true;
+  return SK_OK;
+}
+
+static SetView view_of(const sk_sketch_set* s) {
+  SetView v;
+  v.pv_kmer = s->pv_kmer; v.pv_pos = s->pv_pos; v.pv_cc = s->pv_cc; v.pv_mult = s->pv_mult;
+  v.kv_pos = s->kv_pos; v.kv_cc = s->kv_cc; v.ukmer = s->ukmer; v.ustart = s->ustart; v.ctg_rec_off = s->ctg_rec_off;
+  return v;
+}
+
+static void build_meta(const sk_sketch_set* s, std::vector<GenomeMeta>& out) {
+  out.resize(s->G);
+  std::vector<uint32_t> tmp;
+  for (uint32_t g = 0; g < s->G; g++) {
+    GenomeMeta& m = out[g];
+    m.seed_off = s->seed_off[g]; m.uk_off = s->uk_off[g]; m.ctg_off = s->ctg_off[g];
+    m.n_rec = (uint32_t)(s->seed_off[g + 1] - s->seed_off[g]);
+    m.n_uk = (uint32_t)(s->uk_off[g + 1] - s->uk_off[g]);
+    m.n_ctg = (uint32_t)(s->ctg_off[g + 1] - s->ctg_off[g]);
+    m.g = g; m.total_len = s->total_len[g]; m.pad = 0;
+    tmp.assign(s->ctg_len.begin() + s->ctg_off[g], s->ctg_len.begin() + s->ctg_off[g + 1]);
+    std::sort(tmp.begin(), tmp.end());
+    size_t n = tmp.size();
+    m.q10 = n ? tmp[n * 10 / 100] : 0; m.q50 = n ? tmp[n * 50 / 100] : 0; m.q90 = n ? tmp[n * 90 / 100] : 0;  // src/chain.rs:519-526
+  }
+}
+
+// role selection of get_anchors (src/chain.rs:625-661) + switch_qr (:15-26), in f64 exactly as the reference
+static bool pair_switched(const sk_sketch_set* refs, uint32_t r, const sk_sketch_set* qs, uint32_t q, bool same_set) {
+  auto mean_len = [](const sk_sketch_set* s, uint32_t g) {
+    double sum = 0;
+    for (uint64_t c = s->ctg_off[g]; c < s->ctg_off[g + 1]; c++) sum += (double)s->ctg_len[c];
+    return sum / (double)(s->ctg_off[g + 1] - s->ctg_off[g]);
+  };
+  double mean_q = mean_len(qs, q), mean_r = mean_len(refs, r);
+  double qp, rp;
+  if (qs->total_len[q] > 100000 && refs->total_len[r] > 100000) {
+    qp = (double)(qs->mk_off[q + 1] - qs->mk_off[q]) * (double)qs->sp.c;
+    rp = (double)(refs->mk_off[r + 1] - refs->mk_off[r]) * (double)refs->sp.c;
+  } else {
+    qp = (double)qs->total_len[q]; rp = (double)refs->total_len[r];
+  }
+  double score_query = qp * std::min(mean_q, 300000.);
+  double score_ref = rp * std::min(mean_r, 300000.);
+  if (score_query == score_ref) {
+    uint64_t rq = qs->name_rank[q] + ((same_set || qs->ranks_user_set) ? 0 : refs->G), rr = refs->name_rank[r];
+    return rq > rr;  // query_file_name > ref_file_name
+  }
+  return score_query > score_ref;
+}
+
+struct BatchBuffers {  // grow-only device buffers reused across batches
+  std::vector<std::pair<void**, size_t>> reg;
+};
+
+template <typename T>
+static int ensure(sk_ctx* ctx, T** p, size_t* cap, size_t need) {
+  if (need <= *cap && *p) return SK_OK;
+  if (*p) SK_CUDA(cudaFree(*p));
+  *p = nullptr;
+  size_t n = std::max<size_t>(need + need / 4, 1024);
+  SK_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  *cap = n;
+  return SK_OK;
+}
+
+struct ChainScratch {
+  Workspace ws{};
+  size_t cap_rec = 0, cap_pair = 0, cap_anc = 0, cap_chunk = 0, cap_iv = 0;
+  size_t c_rec_rstart = 0, c_rec_nh = 0, c_hit_rec = 0, c_hit_aoff = 0, c_hit_clfirst = 0, c_hit_need = 0, c_hit_p0 = 0, c_hit_cid = 0;
+  size_t c_pairA = 0, c_pairH = 0, c_pairC = 0, c_pairAbase = 0, c_pairCbase = 0, c_pairIbase = 0, c_pair_nint = 0, c_pair_sumlen = 0,
+         c_pair_nchains = 0, c_pair_tqb = 0;
+  size_t c_anc = 0, c_score = 0, c_ptr = 0, c_root = 0, c_depth = 0, c_cnt = 0, c_best = 0;
+  size_t c_chunk_first = 0, c_chunk_pair = 0, c_chunk_qctg = 0, c_chunk_lo = 0, c_chunk_hi = 0, c_acc_total = 0, c_acc_rq0 = 0,
+         c_acc_rq1 = 0, c_acc_tbcq = 0, c_acc_nint = 0, c_chunk_head = 0, c_chunk_est = 0, c_chunk_w = 0, c_chunk_valid = 0, c_chunk_nseeds = 0;
+  size_t c_iv = 0, c_iv_order = 0, c_iv_kept = 0, c_iv_next = 0, c_acc_list = 0, c_est_sorted = 0, c_w_sorted = 0;
+  PairDesc* d_pairs = nullptr; size_t c_pairs = 0;
+  sk_ani_result* d_out = nullptr; size_t c_out = 0;
+  GenomeMeta *d_m0 = nullptr, *d_m1 = nullptr;
+  void free_all() {
+    void* ptrs[] = {ws.rec_rstart, ws.rec_nh, ws.hit_rec, ws.hit_aoff, ws.hit_clfirst, ws.hit_need, ws.hit_p0, ws.hit_cid, ws.pairA, ws.pairH,
+                    ws.pairC, ws.pairAbase, ws.pairCbase, ws.pairIbase, ws.pair_nint, ws.pair_sumlen, ws.pair_nchains, ws.pair_tqb_ns, ws.anc,
+                    ws.score, ws.ptr, ws.root, ws.depth, ws.cnt, ws.best, ws.chunk_first, ws.chunk_pair, ws.chunk_qctg, ws.chunk_lo, ws.chunk_hi,
+                    ws.acc_total, ws.acc_rq0, ws.acc_rq1, ws.acc_tbcq, ws.acc_nint, ws.chunk_head, ws.chunk_est, ws.chunk_w, ws.chunk_valid,
+                    ws.chunk_nseeds, ws.iv, ws.iv_order, ws.iv_kept, ws.iv_next, ws.acc_list, ws.est_sorted, ws.w_sorted, d_pairs, d_out, d_m0, d_m1};
+    for (void* p : ptrs) if (p) cudaFree(p);
+  }
+};
+
+struct HostPair { uint32_t ref, query; };
+
+// Runs one batch (pairs [b0, b1) of `hp`); results -> host_out[b0..b1).  If dbg != nullptr (single pair) the
+// intermediate products are copied out as well.
+static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, const sk_sketch_set* qs, const std::vector<PairDesc>& descs,
+                     size_t b0, size_t b1, uint64_t total_rec, const ChainParams& prm, const SetView& v0, const SetView& v1,
+                     sk_ani_result* host_out, sk_chain_debug* dbg) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t B = (uint32_t)(b1 - b0);
+  Workspace& ws = S.ws;
+  const size_t NR = std::max<uint64_t>(total_rec, 1);
+#define ENS(field, capf, n) SK_TRY(ensure(ctx, &ws.field, &S.capf, n))
+  ENS(rec_rstart, c_rec_rstart, NR); ENS(rec_nh, c_rec_nh, NR); ENS(hit_rec, c_hit_rec, NR); ENS(hit_aoff, c_hit_aoff, NR);
+  ENS(hit_clfirst, c_hit_clfirst, NR); ENS(hit_need, c_hit_need, NR); ENS(hit_p0, c_hit_p0, NR); ENS(hit_cid, c_hit_cid, NR);
+  ENS(pairA, c_pairA, B); ENS(pairH, c_pairH, B); ENS(pairC, c_pairC, B); ENS(pairAbase, c_pairAbase, B + 1); ENS(pairCbase, c_pairCbase, B + 1);
+  ENS(pairIbase, c_pairIbase, B + 1); ENS(pair_nint, c_pair_nint, B); ENS(pair_sumlen, c_pair_sumlen, B); ENS(pair_nchains, c_pair_nchains, B);
+  ENS(pair_tqb_ns, c_pair_tqb, B);
+  SK_TRY(ensure(ctx, &S.d_pairs, &S.c_pairs, B));
+  SK_TRY(ensure(ctx, &S.d_out, &S.c_out, B));
+  SK_CUDA(cudaMemcpyAsync(S.d_pairs, descs.data() + b0, B * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+  SK_CUDA(cudaMemsetAsync(ws.pair_nint, 0, B * 4, st));
+  SK_CUDA(cudaMemsetAsync(ws.pair_sumlen, 0, B * 4, st));
+  SK_CUDA(cudaMemsetAsync(ws.pair_nchains, 0, B * 4, st));
+  SK_CUDA(cudaMemsetAsync(ws.pair_tqb_ns, 0, B * 4, st));
+
+  SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+  SK_LAUNCH(ctx, "chunk_kernel", (chunk_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
+  std::vector<uint32_t> hA(B), hC(B);
+  SK_CUDA(cudaMemcpyAsync(hA.data(), ws.pairA, B * 4, cudaMemcpyDeviceToHost, st));
+  SK_CUDA(cudaMemcpyAsync(hC.data(), ws.pairC, B * 4, cudaMemcpyDeviceToHost, st));
+  SK_CUDA(cudaStreamSynchronize(st));
+  SK_CUDA(cudaGetLastError());
+  std::vector<uint64_t> abase(B + 1, 0), cbase(B + 1, 0), ibase(B + 1, 0);
+  for (uint32_t i = 0; i < B; i++) {
+    abase[i + 1] = abase[i] + hA[i];
+    cbase[i + 1] = cbase[i] + hC[i];
+    ibase[i + 1] = ibase[i] + hA[i] / 3;   // every chain interval owns >= 3 distinct anchors
+  }
+  const uint64_t TA = abase[B], TC = cbase[B], TI = ibase[B];
+  SK_CUDA(cudaMemcpyAsync(ws.pairAbase, abase.data(), (B + 1) * 8, cudaMemcpyHostToDevice, st));
+  SK_CUDA(cudaMemcpyAsync(ws.pairCbase, cbase.data(), (B + 1) * 8, cudaMemcpyHostToDevice, st));
+  SK_CUDA(cudaMemcpyAsync(ws.pairIbase, ibase.data(), (B + 1) * 8, cudaMemcpyHostToDevice, st));
+  const size_t NA = std::max<uint64_t>(TA, 1), NCH = std::max<uint64_t>(TC, 1), NI = std::max<uint64_t>(TI, 1);
+  ENS(anc, c_anc, NA); ENS(score, c_score, NA); ENS(ptr, c_ptr, NA); ENS(root, c_root, NA); ENS(depth, c_depth, NA); ENS(cnt, c_cnt, NA);
+  ENS(best, c_best, NA);
+  ENS(chunk_first, c_chunk_first, NCH + 1); ENS(chunk_pair, c_chunk_pair, NCH); ENS(chunk_qctg, c_chunk_qctg, NCH);
+  ENS(chunk_lo, c_chunk_lo, NCH); ENS(chunk_hi, c_chunk_hi, NCH); ENS(acc_total, c_acc_total, NCH); ENS(acc_rq0, c_acc_rq0, NCH);
+  ENS(acc_rq1, c_acc_rq1, NCH); ENS(acc_tbcq, c_acc_tbcq, NCH); ENS(acc_nint, c_acc_nint, NCH); ENS(chunk_head, c_chunk_head, NCH);
+  ENS(chunk_est, c_chunk_est, NCH); ENS(chunk_w, c_chunk_w, NCH); ENS(chunk_valid, c_chunk_valid, NCH); ENS(chunk_nseeds, c_chunk_nseeds, NCH);
+  ENS(iv, c_iv, NI); ENS(iv_order, c_iv_order, 4 * NI + 8); ENS(iv_kept, c_iv_kept, NI); ENS(iv_next, c_iv_next, NI); ENS(acc_list, c_acc_list, NI);
+  ENS(est_sorted, c_est_sorted, 4 * NCH + 8); ENS(w_sorted, c_w_sorted, 4 * NCH + 8);
+#undef ENS
+  if (TC > 0) {
+    SK_CUDA(cudaMemcpyAsync(ws.chunk_first + TC, &TA, 8, cudaMemcpyHostToDevice, st));
+    init_chunk_acc_kernel<<<(uint32_t)((TC + 255) / 256), 256, 0, st>>>(TC, ws); count_launch(ctx);
+    SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
+    SK_LAUNCH(ctx, "dp_kernel", (dp_kernel<<<(uint32_t)((TC + 127) / 128), 128, 0, st>>>(TC, prm, ws)));
+    SK_LAUNCH(ctx, "select_kernel", (select_kernel<<<B, CT, 0, st>>>(S.d_pairs, prm, ws)));
+    SK_LAUNCH(ctx, "chunkstat_kernel", (chunkstat_kernel<<<(uint32_t)((TC + 127) / 128), 128, 0, st>>>(TC, S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+  }
+  SK_LAUNCH(ctx, "final_kernel", (final_kernel<<<B, FT, 0, st>>>(S.d_pairs, S.d_m0, S.d_m1, prm, ws, S.d_out)));
+  SK_CUDA(cudaMemcpyAsync(host_out + b0, S.d_out, B * sizeof(sk_ani_result), cudaMemcpyDeviceToHost, st));
+  SK_CUDA(cudaStreamSynchronize(st));
+  SK_CUDA(cudaGetLastError());
+
+  if (dbg) {  // single pair: copy the intermediate products out
+    memset(dbg, 0, sizeof(*dbg));
+    dbg->result = host_out[b0];
+    dbg->switched = descs[b0].switched;
+    dbg->n_anchors = TA; dbg->n_chunks = TC;
+    std::vector<AnchorRec> anc(TA);
+    std::vector<int32_t> score(TA);
+    std::vector<uint32_t> ptr(TA), cq(TC), nseeds(TC);
+    std::vector<uint64_t> cf(TC + 1);
+    if (TA) {
+      SK_CUDA(cudaMemcpy(anc.data(), ws.anc, TA * sizeof(AnchorRec), cudaMemcpyDeviceToHost));
+      SK_CUDA(cudaMemcpy(score.data(), ws.score, TA * 4, cudaMemcpyDeviceToHost));
+      SK_CUDA(cudaMemcpy(ptr.data(), ws.ptr, TA * 4, cudaMemcpyDeviceToHost));
+    }
+    if (TC) {
+      SK_CUDA(cudaMemcpy(cf.data(), ws.chunk_first, (TC + 1) * 8, cudaMemcpyDeviceToHost));
+      SK_CUDA(cudaMemcpy(cq.data(), ws.chunk_qctg, TC * 4, cudaMemcpyDeviceToHost));
+      SK_CUDA(cudaMemcpy(nseeds.data(), ws.chunk_nseeds, TC * 4, cudaMemcpyDeviceToHost));
+    }
+    dbg->anchors = (uint32_t*)malloc(std::max<size_t>(TA, 1) * 20);
+    dbg->score = (int64_t*)malloc(std::max<size_t>(TA, 1) * 8);
+    dbg->pointer = (uint32_t*)malloc(std::max<size_t>(TA, 1) * 4);
+    dbg->chunk_first = (uint32_t*)malloc((TC + 1) * 4);
+    dbg->chunk_nseeds = (uint32_t*)malloc(std::max<size_t>(TC, 1) * 4);
+    for (uint64_t c = 0; c < TC; c++) {
+      dbg->chunk_first[c] = (uint32_t)cf[c]; dbg->chunk_nseeds[c] = nseeds[c];
+      for (uint64_t x = cf[c]; x < cf[c + 1]; x++) {
+        dbg->anchors[5 * x] = cq[c]; dbg->anchors[5 * x + 1] = anc[x].qpos; dbg->anchors[5 * x + 2] = anc[x].rc >> 1;
+        dbg->anchors[5 * x + 3] = anc[x].rpos; dbg->anchors[5 * x + 4] = anc[x].rc & 1u;
+        dbg->score[x] = score[x]; dbg->pointer[x] = ptr[x];
+      }
+    }
+    dbg->chunk_first[TC] = (uint32_t)TA;
+    uint32_t nint = 0;
+    SK_CUDA(cudaMemcpy(&nint, ws.pair_nint, 4, cudaMemcpyDeviceToHost));
+    dbg->n_intervals = nint;
+    std::vector<IntervalKey> iv(nint);
+    std::vector<uint32_t> order(nint);
+    std::vector<uint8_t> kept(nint);
+    uint32_t npow2 = 1;
+    while (npow2 < nint) npow2 <<= 1;
+    if (nint) {
+      SK_CUDA(cudaMemcpy(iv.data(), ws.iv, nint * sizeof(IntervalKey), cudaMemcpyDeviceToHost));
+      SK_CUDA(cudaMemcpy(order.data(), ws.iv_order + npow2, nint * 4, cudaMemcpyDeviceToHost));
+      SK_CUDA(cudaMemcpy(kept.data(), ws.iv_kept, nint, cudaMemcpyDeviceToHost));
+    }
+    dbg->intervals = (int64_t*)malloc(std::max<size_t>(nint, 1) * 11 * 8);
+    for (uint32_t i = 0; i < nint; i++) {
+      const IntervalKey& x = iv[order[i]];
+      int64_t* o = dbg->intervals + 11 * i;
+      o[0] = iv_score(x); o[1] = iv_num_anchors(x); o[2] = iv_q0(x); o[3] = iv_q1(x); o[4] = iv_r0(x); o[5] = iv_r1(x);
+      o[6] = iv_rctg(x); o[7] = iv_qctg(x); o[8] = iv_chunk(x); o[9] = iv_rev(x); o[10] = kept[order[i]];
+    }
+    std::vector<double> est(TC);
+    std::vector<uint32_t> w(TC);
+    std::vector<uint8_t> valid(TC);
+    if (TC) {
+      SK_CUDA(cudaMemcpy(est.data(), ws.chunk_est, TC * 8, cudaMemcpyDeviceToHost));
+      SK_CUDA(cudaMemcpy(w.data(), ws.chunk_w, TC * 4, cudaMemcpyDeviceToHost));
+      SK_CUDA(cudaMemcpy(valid.data(), ws.chunk_valid, TC, cudaMemcpyDeviceToHost));
+    }
+    std::vector<std::pair<double, uint64_t>> es;
+    for (uint64_t c = 0; c < TC; c++) if (valid[c]) es.push_back({est[c], w[c]});
+    std::sort(es.begin(), es.end());
+    dbg->n_ests = es.size();
+    dbg->est = (double*)malloc(std::max<size_t>(es.size(), 1) * 8);
+    dbg->weight = (uint64_t*)malloc(std::max<size_t>(es.size(), 1) * 8);
+    for (size_t i = 0; i < es.size(); i++) { dbg->est[i] = es[i].first; dbg->weight[i] = es[i].second; }
+  }
+  return SK_OK;
+}
+
+static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_set* qs, const uint64_t* pairs, uint64_t n_pairs,
+                      const sk_map_params* mp, sk_ani_result* out, sk_chain_debug* dbg) {
+  SK_CUDA(cudaSetDevice(ctx->device));
+  if (refs->sp.c != qs->sp.c || refs->sp.k != qs->sp.k) { ctx->err = "ref/query sketch parameters differ"; return SK_ERR_PARAM; }
+  if (n_pairs == 0) return SK_OK;
+  SK_TRY(upload_tables(ctx));
+  cudaStream_t st = ctx->stream;
+  ChainParams prm;
+  prm.c = refs->sp.c; prm.k = refs->sp.k;
+  prm.band = BP_CHAIN_BAND / refs->sp.c;                       // index_chain_band (src/chain.rs:111-112)
+  prm.robust = mp->robust; prm.median = mp->median;
+  double fcc = mp->min_aligned_frac;
+  if (fcc < 0.) fcc = 15.0 / 100.;                              // src/chain.rs:101-107
+  prm.frac_cover_cutoff = fcc;
+  prm.both_frac_cover_cutoff = mp->both_min_aligned_frac;
+  prm.model = -1;
+  if (mp->learned_ani) {                                        // regression::get_model (src/regression.rs:12-28)
+    long d125 = std::labs((long)refs->sp.c - 125), d200 = std::labs((long)refs->sp.c - 200);
+    prm.model = d125 < d200 ? 0 : 1;
+  }
+  if (prm.band >= 0x7FFF) { ctx->err = "band too large"; return SK_ERR_PARAM; }
+  const bool same = (refs == qs);
+  ChainScratch S;
+  struct Guard { ChainScratch& s; ~Guard() { s.free_all(); } } guard{S};
+  std::vector<GenomeMeta> m0, m1;
+  build_meta(refs, m0);
+  build_meta(qs, m1);
+  SK_CUDA(cudaMalloc((void**)&S.d_m0, std::max<size_t>(m0.size(), 1) * sizeof(GenomeMeta)));
+  SK_CUDA(cudaMalloc((void**)&S.d_m1, std::max<size_t>(m1.size(), 1) * sizeof(GenomeMeta)));
+  SK_CUDA(cudaMemcpyAsync(S.d_m0, m0.data(), m0.size() * sizeof(GenomeMeta), cudaMemcpyHostToDevice, st));
+  SK_CUDA(cudaMemcpyAsync(S.d_m1, m1.data(), m1.size() * sizeof(GenomeMeta), cudaMemcpyHostToDevice, st));
+  const SetView v0 = view_of(refs), v1 = view_of(qs);
+  // pair descriptors
+  std::vector<PairDesc> descs(n_pairs);
+  for (uint64_t i = 0; i < n_pairs; i++) {
+    uint32_t r = (uint32_t)(pairs[i] >> 32), q = (uint32_t)pairs[i];
+    if (r >= refs->G || q >= qs->G) { ctx->err = "pair index out of range"; return SK_ERR_PARAM; }
+    PairDesc& d = descs[i];
+    d.ref_idx = r; d.query_idx = q; d.rec_off = 0;
+    bool empty = (m0[r].n_ctg == 0 || m1[q].n_ctg == 0);      // src/chain.rs:618-620
+    d.valid = empty ? 0 : 1;
+    bool sw = empty ? true : pair_switched(refs, r, qs, q, same);
+    d.switched = sw ? 1 : 0;
+    if (sw) { d.qset = 0; d.qg = r; d.rset = 1; d.rg = q; }    // iterate + chunk the ref sketch, probe the query sketch
+    else { d.qset = 1; d.qg = q; d.rset = 0; d.rg = r; }
+  }
+  // batches bounded by the per-record workspace
+  const uint64_t REC_CAP = 64ull << 20;
+  size_t b0 = 0;
+  while (b0 < n_pairs) {
+    size_t b1 = b0;
+    uint64_t rec = 0;
+    while (b1 < n_pairs && b1 - b0 < 65535) {
+      const PairDesc& d = descs[b1];
+      uint64_t nr = d.valid ? (d.qset ? m1[d.qg].n_rec : m0[d.qg].n_rec) : 0;
+      if (b1 > b0 && rec + nr > REC_CAP) break;
+      descs[b1].rec_off = rec;
+      rec += nr;
+      b1++;
+    }
+    SK_TRY(run_batch(ctx, S, refs, qs, descs, b0, b1, rec, prm, v0, v1, out, dbg));
+    b0 = b1;
+  }
+  return SK_OK;
+}
+
+}  // namespace sk
+
+extern "C" {
+
+int sk_chain_pairs(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_set* queries, const uint64_t* pairs, uint64_t n_pairs,
+                   const sk_map_params* mp, sk_ani_result* out) {
+  if (!ctx || !refs || !queries || !mp || (n_pairs && (!pairs || !out))) return SK_ERR_PARAM;
+  return sk::chain_impl(ctx, refs, queries, pairs, n_pairs, mp, out, nullptr);
+}
+
+int sk_chain_pair_debug(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_set* queries, uint64_t pair, const sk_map_params* mp,
+                        sk_chain_debug* out) {
+  if (!ctx || !refs || !queries || !mp || !out) return SK_ERR_PARAM;
+  sk_ani_result r;
+  return sk::chain_impl(ctx, refs, queries, &pair, 1, mp, &r, out);
+}
+
+void sk_chain_debug_free(sk_chain_debug* d) {
+  if (!d) return;
+  free(d->anchors); free(d->chunk_first); free(d->chunk_nseeds); free(d->score); free(d->pointer); free(d->intervals);
+  free(d->est); free(d->weight);
+  memset(d, 0, sizeof(*d));
+}
+
+}  // extern "C"

@@ -412,12 +412,12 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     SK_CUDA(P.alloc(NU, st)); SK_CUDA(NM.alloc(NU, st)); SK_CUDA(ucontig.alloc(NU, st));
     SK_CUDA(PM.alloc(NU, st)); SK_CUDA(cnt.alloc(NU, st)); SK_CUDA(uoff.alloc(NU, st));
 
-    pack_kernel<<<div_up(NU, PACK_THREADS), PACK_THREADS, 0, st>>>(d_ascii, d_coff.p, d_cuoff.p, d_clen.p, n_contigs, NU,
-                                                                  P.p, NM.p, ucontig.p); count_launch(ctx);
+    SK_LAUNCH(ctx, "pack_kernel", (pack_kernel<<<div_up(NU, PACK_THREADS), PACK_THREADS, 0, st>>>(
+        d_ascii, d_coff.p, d_cuoff.p, d_clen.p, n_contigs, NU, P.p, NM.p, ucontig.p)));
     const uint64_t seed_mask = ~0ull >> (64 - 2 * sp->k);
     const uint64_t thr = ~0ull / sp->c, thr_m = ~0ull / sp->marker_c;  // src/avx2_seeding.rs:93-94
-    hashpass_kernel<<<div_up(NU, HASH_THREADS), HASH_THREADS, 0, st>>>(P.p, NM.p, ucontig.p, d_cuoff.p, d_clen.p, NU, seed_mask,
-                                                                      thr, PM.p, cnt.p); count_launch(ctx);
+    SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<<<div_up(NU, HASH_THREADS), HASH_THREADS, 0, st>>>(
+        P.p, NM.p, ucontig.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, cnt.p)));
     SK_TRY(scan_exclusive<uint32_t>(ctx, cnt.p, uoff.p, NU));
     uint32_t last_cnt = 0, last_off = 0;
     SK_CUDA(cudaMemcpyAsync(&last_cnt, cnt.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
@@ -435,8 +435,8 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     SK_CUDA(cudaMalloc((void**)&set->pv_pos, std::max<size_t>(S, 1) * 4));
     SK_CUDA(cudaMalloc((void**)&set->pv_cc, std::max<size_t>(S, 1) * 4));
     SK_CUDA(mkv.alloc(S, st));
-    expand_kernel<<<div_up(NU, 256), 256, 0, st>>>(P.p, ucontig.p, d_cuoff.p, d_clocal.p, NU, PM.p, uoff.p, seed_mask, thr_m,
-                                                   set->pv_kmer, set->pv_pos, set->pv_cc, mkv.p); count_launch(ctx);
+    SK_LAUNCH(ctx, "expand_kernel", (expand_kernel<<<div_up(NU, 256), 256, 0, st>>>(
+        P.p, ucontig.p, d_cuoff.p, d_clocal.p, NU, PM.p, uoff.p, seed_mask, thr_m, set->pv_kmer, set->pv_pos, set->pv_cc, mkv.p)));
     SK_CUDA(cudaStreamSynchronize(st));
     // per-genome record offsets + per-contig local record offsets (with one sentinel per genome)
     std::vector<uint32_t> crl(n_contigs + G + 1, 0);

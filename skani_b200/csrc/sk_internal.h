@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -20,7 +21,28 @@ struct sk_ctx {
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_free[2] = {nullptr, nullptr};
   cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+  // optional per-kernel timing (sk_ctx_set_timing): CUDA events on the launch stream around each major kernel
+  bool timing = false;
+  struct Pending { const char* name; cudaEvent_t e0, e1; };
+  std::vector<Pending> pending;
+  std::map<std::string, std::pair<double, uint64_t>> timing_acc;  // name -> (total ms, launches)
 };
+
+// launch wrapper: counts the launch and, when timing is on, brackets it with events on ctx->stream
+#define SK_LAUNCH(ctx, name, ...)                                     \
+  do {                                                                \
+    sk_ctx::Pending pe__{name, nullptr, nullptr};                     \
+    if ((ctx)->timing) {                                              \
+      cudaEventCreate(&pe__.e0); cudaEventCreate(&pe__.e1);           \
+      cudaEventRecord(pe__.e0, (ctx)->stream);                        \
+    }                                                                 \
+    __VA_ARGS__;                                                      \
+    (ctx)->launches++;                                                \
+    if ((ctx)->timing) {                                              \
+      cudaEventRecord(pe__.e1, (ctx)->stream);                        \
+      (ctx)->pending.push_back(pe__);                                 \
+    }                                                                 \
+  } while (0)
 
 struct sk_sketch_set {
   sk_ctx* ctx = nullptr;
@@ -31,6 +53,7 @@ struct sk_sketch_set {
   std::vector<uint32_t> ctg_len;     // all contigs, genome-major
   std::vector<uint64_t> total_len;   // per genome (Sketch.total_sequence_length)
   std::vector<uint64_t> name_rank;   // per genome; order of file names (switch_qr tie-break)
+  bool ranks_user_set = false;
   // ---- device arrays
   size_t S = 0, U = 0, M = 0, C = 0;
   uint32_t *pv_kmer = nullptr, *pv_pos = nullptr, *pv_cc = nullptr;  // [S] position-ordered view (genome, contig, pos)

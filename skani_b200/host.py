@@ -43,6 +43,19 @@ class Context:
     def stream(self):
         return self.L.sk_ctx_stream(self.h)
 
+    def set_timing(self, on=True):
+        self.check(self.L.sk_ctx_set_timing(self.h, int(on)))
+
+    def get_timing(self, reset=True):
+        """{kernel_name: (total_ms, launches)} measured with CUDA events on the launch stream."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.L.sk_ctx_get_timing(self.h, buf, len(buf), int(reset)))
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            name, ms, n = ln.split()
+            out[name] = (float(ms), int(n))
+        return out
+
     def close(self):
         if self.h:
             self.L.sk_ctx_destroy(self.h)

@@ -1,0 +1,179 @@
+"""GPU parity: screen + chain kernels vs the CPU oracle through the C ABI.  Integer stages (anchors, chunks, DP
+scores/pointers, chain intervals, greedy selection, per-chunk weights) must be bit-exact; ANI/AF floats within 1e-4
+(BASELINE.json north_star), in practice identical to the last f32 digit."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from bench_support import synth
+from fasta_py import read_fastx
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import skani_b200 as sk
+    c = sk.Context(0)
+    yield c
+    c.close()
+
+
+def f2(x):
+    return "%.2f" % float(np.float32(x) * np.float32(100.0))
+
+
+def assert_result_close(g, o, tol=TOL):
+    if np.isnan(o.ani):
+        assert np.isnan(g.ani)
+        return
+    for f in ("ani", "af_query", "af_ref", "std", "ci_lower", "ci_upper"):
+        assert abs(getattr(g, f) - getattr(o, f)) <= tol, (f, getattr(g, f), getattr(o, f))
+    for f in ("q90_q", "q90_r", "q50_q", "q50_r", "q10_q", "q10_r", "num_contigs_q", "num_contigs_r",
+              "avg_chain_int_len", "total_bases_covered"):
+        assert getattr(g, f) == getattr(o, f), (f, getattr(g, f), getattr(o, f))
+
+
+def assert_debug_equal(gd, od):
+    assert gd["switched"] == od["switched"]
+    assert np.array_equal(gd["anchors"], od["anchors"]), "anchors"
+    assert np.array_equal(gd["chunk_first"], od["chunk_first"]), "chunk_first"
+    assert np.array_equal(gd["chunk_nseeds"], od["chunk_nseeds"]), "chunk_nseeds"
+    assert np.array_equal(gd["score"], od["score"]), "score"
+    assert np.array_equal(gd["pointer"], od["pointer"]), "pointer"
+    assert np.array_equal(gd["intervals"], od["intervals"]), "intervals"
+    assert np.array_equal(gd["weight"], od["weight"]), "weights"
+    assert np.allclose(gd["est"], od["est"], rtol=0, atol=1e-12), "ests"
+    assert_result_close(gd["result"], od["result"])
+
+
+def make_sets(ctx, genomes, sp_kw, individual=False):
+    """genomes: list of lists of contig byte arrays -> (gpu set, [oracle sketches])"""
+    import skani_b200 as sk
+    gs = sk.sketch_sequences(ctx, genomes, sk.sketch_params(**sp_kw), individual_contig=individual)
+    osk = []
+    for gi, ctgs in enumerate(genomes):
+        kept = [c for c in ctgs if len(c) >= 500]
+        if not kept:
+            continue
+        if individual:
+            for j, c in enumerate(kept):
+                osk.append(O.sketch_from_contigs("g%06d" % gi, [c], **sp_kw))
+        else:
+            osk.append(O.sketch_from_contigs("g%06d" % gi, kept, **sp_kw))
+    assert len(gs) == len(osk)
+    return gs, osk
+
+
+def synth_genomes(n, L, G):
+    bases, off, goc = synth.generate(0, n, L, G=G)
+    out = []
+    for g in range(n):
+        idx = np.nonzero(goc == g)[0]
+        out.append([bases[int(off[i]):int(off[i + 1])] for i in idx])
+    return out
+
+
+@pytest.mark.parametrize("c,mc,learned", [(125, 1000, True), (30, 200, False), (200, 1000, True)])
+def test_chain_debug_parity_synthetic(ctx, c, mc, learned):
+    import skani_b200 as sk
+    genomes = synth_genomes(8, 700_000, 4)
+    kw = dict(c=c, k=15, marker_c=mc)
+    gs, osk = make_sets(ctx, genomes, kw)
+    mp = sk.map_params(learned_ani=learned)
+    ocp = O.cmd(learned_ani=learned)
+    for (r, q) in [(0, 1), (0, 2), (1, 3), (2, 3), (5, 6), (4, 7), (0, 5), (3, 3)]:
+        gd = sk.chain_pair_debug(ctx, gs, gs, r, q, mp)
+        od = O.chain_debug(osk[r], osk[q], ocp)
+        assert_debug_equal(gd, od)
+
+
+def test_triangle_parity_synthetic(ctx):
+    import skani_b200 as sk
+    n, L, G = 24, 400_000, 6
+    bases, off, goc = synth.generate(0, n, L, G=G)
+    res, st = sk.triangle(ctx, bases, off, goc, n)
+    genomes = [[bases[int(off[i]):int(off[i + 1])] for i in np.nonzero(goc == g)[0]] for g in range(n)]
+    osk = [O.sketch_from_contigs("g%06d" % g, genomes[g]) for g in range(n)]
+    ores, info = O.triangle(osk, O.cmd())
+    assert st.n_pairs_screened == info["n_chained"]
+    got = {(r.ref_id, r.query_id): r for r in res}
+    exp = {(r.ref_id, r.query_id): r for r in ores}
+    assert set(got) == set(exp) and len(got) == n // G * (G * (G - 1) // 2)
+    for key in exp:
+        assert_result_close(got[key], exp[key])
+    # screen alone
+    gs = sk.sketch_contigs(ctx, bases, off, goc, n)
+    pairs = sk.screen_triangle(ctx, gs)
+    ro, cols = O.screen_triangle(osk)
+    exp_pairs = [(i << 32) | int(j) for i in range(n) for j in cols[int(ro[i]):int(ro[i + 1])]]
+    assert pairs.tolist() == sorted(exp_pairs)
+
+
+def load_genome(name):
+    return [np.frombuffer(s, np.uint8) for _, s in read_fastx(os.path.join(GOLD, name))]
+
+
+def test_config1_ecoli_dist(ctx):
+    """BASELINE.json configs[0]: skani dist refs/e.coli-EC590.fasta refs/e.coli-K12.fasta (query = EC590, ref = K12)."""
+    import skani_b200 as sk
+    k12, ec = load_genome("e.coli-K12.fasta.gz"), load_genome("e.coli-EC590.fasta.gz")
+    for c, exp in [(125, ("99.39", "91.89", "92.46")), (200, ("99.42", "94.47", "95.06"))]:   # G13 / G4 goldens
+        kw = dict(c=c, k=15, marker_c=1000)
+        refs, oref = make_sets(ctx, [k12], kw)
+        qs, oq = make_sets(ctx, [ec], kw)
+        import ctypes
+        qs.ctx.check(qs.ctx.L.sk_sketch_set_set_name_ranks(qs.h, np.array([0], np.uint64).ctypes.data))
+        refs.ctx.check(refs.ctx.L.sk_sketch_set_set_name_ranks(refs.h, np.array([1], np.uint64).ctypes.data))
+        pairs = sk.host.screen_query_ref(ctx, refs, qs, sk.map_params(), mode=0)
+        assert pairs.tolist() == [0]
+        gd = sk.chain_pair_debug(ctx, refs, qs, 0, 0, sk.map_params())
+        oref[0]  # oracle names: ref "g000000" == query "g000000": tie-break not reached (scores differ)
+        od = O.chain_debug(oref[0], oq[0], O.cmd())
+        assert_debug_equal(gd, od)
+        r = gd["result"]
+        assert (f2(r.ani), f2(r.af_ref), f2(r.af_query)) == exp
+
+
+def test_reads_vs_genome_g8_golden(ctx):
+    """G8: dist --qi --robust, 364 ONT reads vs EC590 -> the reference's own 269 rows (test_results_versions/0.3.0:153-421)."""
+    import skani_b200 as sk
+    gold = {}
+    for ln in open(os.path.join(GOLD, "g8_dist_qi_robust.tsv")):
+        if not ln.startswith("#"):
+            ani, afr, afq, name = ln.rstrip("\n").split("\t")
+            gold[name] = (ani, afr, afq)
+    recs = [(n, s) for n, s in read_fastx(os.path.join(GOLD, "o157_reads.fa.gz")) if len(s) >= 500]
+    reads = [np.frombuffer(s, np.uint8) for _, s in recs]
+    kw = dict(c=125, k=15, marker_c=1000)
+    refs, _ = make_sets(ctx, [load_genome("e.coli-EC590.fasta.gz")], kw)
+    qs = sk.sketch_sequences(ctx, [reads], sk.sketch_params(**kw), individual_contig=True)
+    assert len(qs) == 364
+    mp = sk.map_params(robust=True, learned_ani=False)
+    pairs = sk.host.screen_query_ref(ctx, refs, qs, mp, mode=2)        # --qi => marker index on
+    res = sk.chain_pairs(ctx, refs, qs, pairs, mp)
+    got = {recs[r.query_id][0]: (f2(r.ani), f2(r.af_ref), f2(r.af_query)) for r in res if r.ani > 0.1}
+    assert len(got) == 269
+    assert got == gold
+
+
+def test_small_genomes_viruses(ctx):
+    import skani_b200 as sk
+    recs = read_fastx(os.path.join(GOLD, "viruses.fna"))
+    ctgs = [np.frombuffer(s, np.uint8) for _, s in recs]
+    for kw, rescue in [(dict(c=125, k=15, marker_c=1000), True), (dict(c=30, k=15, marker_c=200), False)]:
+        gs, osk = make_sets(ctx, [ctgs], kw, individual=True)
+        mp = sk.map_params(learned_ani=False, rescue_small=rescue)
+        pairs = sk.screen_triangle(ctx, gs, mp)
+        ro, cols = O.screen_triangle(osk, rescue_small=rescue)
+        assert pairs.tolist() == sorted((i << 32) | int(j) for i in range(3) for j in cols[int(ro[i]):int(ro[i + 1])])
+        res = sk.chain_pairs(ctx, gs, gs, pairs, mp)
+        for r in res:
+            o = O.chain(osk[r.ref_id], osk[r.query_id], O.cmd(learned_ani=False, rescue_small=rescue))
+            assert_result_close(r, o)
+            gd = sk.chain_pair_debug(ctx, gs, gs, r.ref_id, r.query_id, mp)
+            assert_debug_equal(gd, O.chain_debug(osk[r.ref_id], osk[r.query_id], O.cmd(learned_ani=False, rescue_small=rescue)))

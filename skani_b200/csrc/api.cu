@@ -36,7 +36,7 @@ int concat_dev(sk_ctx* ctx, const std::vector<const T*>& parts, const std::vecto
   size_t total = 0;
   for (size_t c : counts) total += c;
   T* p = nullptr;
-  SK_CUDA(cudaMalloc((void**)&p, std::max<size_t>(total, 1) * sizeof(T)));
+  SK_CUDA(cudaMallocAsync((void**)&p, std::max<size_t>(total, 1) * sizeof(T), ctx->stream));
   size_t o = 0;
   for (size_t i = 0; i < parts.size(); i++) {
     if (counts[i]) SK_CUDA(cudaMemcpyAsync(p + o, parts[i], counts[i] * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -53,7 +53,7 @@ int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_
   s->sp = parts.empty() ? sk_sketch_params{125, 15, 1000} : parts[0]->sp;
   struct Guard { sk_sketch_set* s; ~Guard() { if (s) { free_set_device(s); delete s; } } } guard{s};
   s->seed_off = {0}; s->uk_off = {0}; s->mk_off = {0}; s->ctg_off = {0};
-  std::vector<size_t> nS, nU, nM, nC, nUG, nCG;
+  std::vector<size_t> nS, nU, nM, nC, nUG, nCG, nB;
   for (auto* p : parts) {
     if (p->sp.c != s->sp.c || p->sp.k != s->sp.k || p->sp.marker_c != s->sp.marker_c) { ctx->err = "sketch parameter mismatch"; return SK_ERR_PARAM; }
     for (uint32_t g = 0; g < p->G; g++) {
@@ -67,7 +67,7 @@ int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_
     s->ctg_len.insert(s->ctg_len.end(), p->ctg_len.begin(), p->ctg_len.end());
     s->G += p->G;
     nS.push_back(p->S); nU.push_back(p->U); nM.push_back(p->M); nC.push_back(p->C);
-    nUG.push_back(p->U + p->G); nCG.push_back(p->C + p->G);
+    nUG.push_back(p->U + p->G); nCG.push_back(p->C + p->G); nB.push_back((size_t)p->G * (UBUCKETS + 1));
   }
   s->S = s->seed_off.back(); s->U = s->uk_off.back(); s->M = s->mk_off.back(); s->C = s->ctg_off.back();
 #define CAT(field, T, counts)                                         \
@@ -78,7 +78,7 @@ int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_
   }
   CAT(pv_kmer, uint32_t, nS) CAT(pv_pos, uint32_t, nS) CAT(pv_cc, uint32_t, nS) CAT(pv_mult, uint16_t, nS)
   CAT(kv_pos, uint32_t, nS) CAT(kv_cc, uint32_t, nS) CAT(ukmer, uint32_t, nU) CAT(ustart, uint32_t, nUG)
-  CAT(markers, uint64_t, nM) CAT(ctg_rec_off, uint32_t, nCG) CAT(d_ctg_len, uint32_t, nC)
+  CAT(markers, uint64_t, nM) CAT(ctg_rec_off, uint32_t, nCG) CAT(d_ctg_len, uint32_t, nC) CAT(ubucket, uint32_t, nB)
 #undef CAT
   SK_CUDA(cudaStreamSynchronize(ctx->stream));
   guard.s = nullptr;
@@ -120,6 +120,8 @@ int sk_ctx_destroy(sk_ctx* ctx) {
   if (!ctx) return SK_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
+  for (int i = 0; i < 2; i++) if (ctx->dbuf[i]) cudaFree(ctx->dbuf[i]);
   for (int i = 0; i < 2; i++) {
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
     if (ctx->pinned_free[i]) cudaEventDestroy(ctx->pinned_free[i]);
@@ -330,10 +332,16 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
     c0 = c1;
   }
   if (plan.empty()) return sk_sketch_batch_dev(ctx, nullptr, contig_off, 0, genome_of_contig, n_genomes, sp, out);
-  // device double buffer
-  uint8_t* dbuf[2] = {nullptr, nullptr};
-  struct DGuard { uint8_t** b; ~DGuard() { for (int i = 0; i < 2; i++) if (b[i]) cudaFree(b[i]); } } dguard{dbuf};
-  for (int i = 0; i < 2; i++) SK_CUDA(cudaMalloc((void**)&dbuf[i], max_bytes + 64));
+  // device double buffer (grow-only, kept in the context)
+  if (ctx->dbuf_bytes < max_bytes + 64) {
+    for (int i = 0; i < 2; i++) {
+      if (ctx->dbuf[i]) SK_CUDA(cudaFree(ctx->dbuf[i]));
+      ctx->dbuf[i] = nullptr;
+      SK_CUDA(cudaMalloc((void**)&ctx->dbuf[i], max_bytes + 64));
+    }
+    ctx->dbuf_bytes = max_bytes + 64;
+  }
+  uint8_t** dbuf = ctx->dbuf;
   if (!pinned_src && ctx->pinned_bytes < max_bytes) {
     for (int i = 0; i < 2; i++) {
       if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
@@ -424,9 +432,11 @@ int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t
   s->total_len = {tl};
   s->name_rank = {0};
   size_t S1 = std::max<size_t>(n_records, 1);
-  SK_CUDA(cudaMalloc((void**)&s->pv_kmer, S1 * 4)); SK_CUDA(cudaMalloc((void**)&s->pv_pos, S1 * 4)); SK_CUDA(cudaMalloc((void**)&s->pv_cc, S1 * 4));
-  SK_CUDA(cudaMalloc((void**)&s->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
-  SK_CUDA(cudaMalloc((void**)&s->ctg_rec_off, (size_t)(n_contigs + 2) * 4));
+  SK_CUDA(cudaMallocAsync((void**)&s->pv_kmer, S1 * 4, ctx->stream)); SK_CUDA(cudaMallocAsync((void**)&s->pv_pos, S1 * 4, ctx->stream));
+  SK_CUDA(cudaMallocAsync((void**)&s->pv_cc, S1 * 4, ctx->stream));
+  SK_CUDA(cudaMallocAsync((void**)&s->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4, ctx->stream));
+  SK_CUDA(cudaMallocAsync((void**)&s->ctg_rec_off, (size_t)(n_contigs + 2) * 4, ctx->stream));
+  SK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (n_records) {
     SK_CUDA(cudaMemcpy(s->pv_kmer, hk.data(), n_records * 4, cudaMemcpyHostToDevice));
     SK_CUDA(cudaMemcpy(s->pv_pos, hp.data(), n_records * 4, cudaMemcpyHostToDevice));

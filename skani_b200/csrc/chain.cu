@@ -43,7 +43,7 @@ __constant__ float c_gbdt_bias[2];
 struct SetView {
   const uint32_t *pv_kmer, *pv_pos, *pv_cc;
   const uint16_t* pv_mult;
-  const uint32_t *kv_pos, *kv_cc, *ukmer, *ustart, *ctg_rec_off;
+  const uint32_t *kv_pos, *kv_cc, *ukmer, *ustart, *ctg_rec_off, *ubucket;
 };
 struct GenomeMeta {
   uint64_t seed_off, uk_off, ctg_off;  // bases into the set arrays (ustart base = uk_off + g, ctg_rec_off base = ctg_off + g)
@@ -58,7 +58,7 @@ struct PairDesc {
   uint64_t rec_off;             // offset of this pair's slice in the per-record / per-hit workspaces
 };
 struct ChainParams {
-  uint32_t c, k, band;
+  uint32_t c, k, band, ushift;
   int32_t robust, median, model;  // model: -1 none, 0 C125, 1 C200
   double frac_cover_cutoff, both_frac_cover_cutoff;
 };
@@ -79,7 +79,8 @@ struct Workspace {
   // per anchor
   AnchorRec* anc;
   int32_t* score;
-  uint32_t *ptr, *root, *depth, *cnt, *best;
+  uint32_t *ptr, *depth;
+  unsigned long long* rootkey;
   // per chunk
   uint64_t* chunk_first;   // batch-global anchor index (+ sentinel)
   uint32_t *chunk_pair, *chunk_qctg;
@@ -111,6 +112,7 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
              const GenomeMeta* __restrict__ m1, ChainParams prm, Workspace ws) {
   using Scan = cub::BlockScan<uint64_t, CT>;
   __shared__ typename Scan::TempStorage tmp;
+  __shared__ uint32_t s_bucket[UBUCKETS + 1];
   const PairDesc pd = pairs[blockIdx.x];
   if (!pd.valid) {
     if (threadIdx.x == 0) { ws.pairA[blockIdx.x] = 0; ws.pairH[blockIdx.x] = 0; }
@@ -123,6 +125,11 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
   const uint32_t* __restrict__ ruk = R.ukmer + rm.uk_off;
   const uint32_t* __restrict__ rus = R.ustart + rm.uk_off + rm.g;
   const uint32_t nuk = rm.n_uk;
+  {  // every thread of the block probes the same ref-role genome: stage its bucket index (16 KB) in shared memory
+    const uint32_t* gb = R.ubucket + (size_t)rm.g * (UBUCKETS + 1);
+    for (uint32_t b = threadIdx.x; b <= UBUCKETS; b += CT) s_bucket[b] = gb[b];
+    __syncthreads();
+  }
   uint64_t carry = 0;  // low 32: anchors so far, high 32: hit records so far
   for (uint32_t t0 = 0; t0 < qm.n_rec; t0 += CT * ITEMS) {
     uint64_t item[ITEMS];
@@ -136,13 +143,14 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
         uint32_t kmer = Q.pv_kmer[qm.seed_off + t];
         uint32_t mq = Q.pv_mult[qm.seed_off + t];
         if (mq <= prm.band) {                          // query positions > band: dropped entirely (src/chain.rs:676-678)
-          // binary search the ref-role distinct k-mers
-          uint32_t lo = 0, hi = nuk;
+          // binary search the ref-role distinct k-mers inside the k-mer's top-bits bucket
+          const uint32_t bk = kmer >> prm.ushift;
+          uint32_t lo = s_bucket[bk], hi = s_bucket[bk + 1];
           while (lo < hi) {
             uint32_t mid = (lo + hi) >> 1;
             if (ruk[mid] < kmer) lo = mid + 1; else hi = mid;
           }
-          if (lo < nuk && ruk[lo] == kmer) {
+          if (lo < s_bucket[bk + 1] && lo < nuk && ruk[lo] == kmer) {
             uint32_t s = rus[lo], cntr = rus[lo + 1] - s;
             if (cntr <= prm.band) { counted = 1; nh[it] = cntr; rst[it] = s; }  // else dropped entirely (:695-697)
           } else {
@@ -362,26 +370,108 @@ anchor_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K4: banded DP + chain extraction, one thread per chunk
+// K4: banded DP + chain extraction, one WARP per chunk, anchors and DP state held in registers.
+//
+// Lane l owns the anchors whose chunk index is congruent to l mod 32: register set s holds the anchor of block
+// (current block - s).  For the anchor i = 32 b + m being scored, every lane tests its own candidates j = 32 (b - s) + l
+// (the reference's predecessor window j in [i - band, i), same ref contig, query gap <= 2500, src/chain.rs:853-880) against
+// the anchor's fields broadcast from lane m; two REDUX reductions pick the maximal score and, among those, the largest j
+// (the reference's strict `>` scanning j downward).  Chain components are tracked with the closed form of the union-find
+// (root / depth propagate through the winning predecessor); per-root statistics live in global memory at the root's slot.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-dp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
-  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+template <int NB, bool TAPS>
+__global__ void __launch_bounds__(32)
+dp_warp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x;
+  const uint64_t c = blockIdx.x;
   if (c >= n_chunks) return;
-  const uint64_t a0 = ws.chunk_first[c], a1 = ws.chunk_first[c + 1];
-  const uint32_t n = (uint32_t)(a1 - a0);
+  const uint64_t a0 = ws.chunk_first[c];
+  const uint32_t n = (uint32_t)(ws.chunk_first[c + 1] - a0);
+  const AnchorRec* __restrict__ a = ws.anc + a0;
+  // per-root "best chain end" key = score << 32 | index, maintained with atomicMax: the maximum is the largest index
+  // among the maximal scores, exactly the reference's pick.  depth = anchors on the path to the root.
+  unsigned long long* __restrict__ g_key = ws.rootkey + a0;
+  uint32_t* __restrict__ g_depth = ws.depth + a0;
+  const uint32_t band = prm.band;
+  uint32_t q[NB], r[NB], rc[NB], rt[NB], dpth[NB];
+  int32_t sc[NB];
+  uint32_t my_ptr = 0;
+#pragma unroll
+  for (int s = 0; s < NB; s++) { q[s] = r[s] = rc[s] = rt[s] = dpth[s] = 0; sc[s] = 0; }
+  for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+#pragma unroll
+    for (int s = NB - 1; s > 0; s--) { q[s] = q[s - 1]; r[s] = r[s - 1]; rc[s] = rc[s - 1]; rt[s] = rt[s - 1]; dpth[s] = dpth[s - 1]; sc[s] = sc[s - 1]; }
+    const uint32_t idx = b0 + lane;
+    {
+      AnchorRec x; x.qpos = 0; x.rpos = 0; x.rc = 0;
+      if (idx < n) { x = a[idx]; g_key[idx] = (unsigned long long)idx; }   // every anchor starts as its own root, score 0
+      q[0] = x.qpos; r[0] = x.rpos; rc[0] = x.rc; sc[0] = 0; rt[0] = idx; dpth[0] = 1;
+      my_ptr = idx;
+    }
+    __syncwarp();
+    const uint32_t mend = min(32u, n - b0);
+    for (uint32_t m = 0; m < mend; m++) {
+      const uint32_t i = b0 + m;
+      AnchorRec cur;
+      cur.qpos = __shfl_sync(FULL, q[0], m);
+      cur.rpos = __shfl_sync(FULL, r[0], m);
+      cur.rc = __shfl_sync(FULL, rc[0], m);
+      int32_t best_ns = 0;
+      uint32_t best_j1 = 0;  // j + 1 of this lane's best candidate
+#pragma unroll
+      for (int s = 0; s < NB; s++) {   // ascending s = descending j inside a lane: strict > keeps the largest j
+        if (b0 >= 32u * s) {
+          const uint32_t j = b0 - 32u * s + lane;
+          if (j < i && i - j <= band && (rc[s] >> 1) == (cur.rc >> 1) && cur.qpos - q[s] <= BP_CHAIN_BAND) {
+            AnchorRec past; past.qpos = q[s]; past.rpos = r[s]; past.rc = rc[s];
+            const int32_t ps = pair_score(cur, past);
+            if (ps != INT32_MIN) {
+              const int32_t ns = ps + sc[s];
+              if (ns > best_ns) { best_ns = ns; best_j1 = j + 1; }
+            }
+          }
+        }
+      }
+      const int32_t smax = __reduce_max_sync(FULL, best_ns);
+      if (smax > 0) {   // uniform branch
+        const uint32_t jw = __reduce_max_sync(FULL, (best_ns == smax) ? best_j1 : 0u) - 1;
+        const int sidx = (int)(b0 >> 5) - (int)(jw >> 5);
+        uint32_t rsel = rt[0], dsel = dpth[0];
+#pragma unroll
+        for (int s = 1; s < NB; s++) if (sidx == s) { rsel = rt[s]; dsel = dpth[s]; }
+        const uint32_t root_i = __shfl_sync(FULL, rsel, jw & 31u);
+        const uint32_t depth_i = __shfl_sync(FULL, dsel, jw & 31u) + 1;
+        if (lane == m) { sc[0] = smax; rt[0] = root_i; dpth[0] = depth_i; my_ptr = jw; }
+      }
+    }
+    // block epilogue: coalesced depth store; chained anchors push their (score, index) to their root
+    if (idx < n) {
+      g_depth[idx] = dpth[0];
+      if (rt[0] != idx) atomicMax(&g_key[rt[0]], ((unsigned long long)(uint32_t)sc[0] << 32) | idx);
+      if (TAPS) { ws.score[a0 + idx] = sc[0]; ws.ptr[a0 + idx] = my_ptr; }
+    }
+  }
+  __threadfence_block();
+  __syncwarp();
+  // emit one interval per surviving chain (src/chain.rs:954-1005).  The len_of_set >= 3 test (:954-957) is implied by
+  // num_anchors >= 3 (:974): a component has at least as many members as its best path.
   const uint32_t p = ws.chunk_pair[c];
   const uint32_t qctg = ws.chunk_qctg[c];
   const uint32_t chunk_local_id = (uint32_t)(c - ws.pairCbase[p]);
-  const AnchorRec* a = ws.anc + a0;
-  auto emit = [&](int32_t score, uint32_t num_anchors, uint32_t first, uint32_t bestidx) {
-    const AnchorRec f = a[first], l = a[bestidx];
+  for (uint32_t i = lane; i < n; i += 32) {
+    if (((volatile uint32_t*)g_depth)[i] != 1) continue;            // not a root
+    const unsigned long long key = ((volatile unsigned long long*)g_key)[i];
+    const uint32_t b = (uint32_t)key, score = (uint32_t)(key >> 32);
+    if (b == i) continue;                                            // singleton
+    const uint32_t num_anchors = ((volatile uint32_t*)g_depth)[b];
+    if (num_anchors < MIN_ANCHORS || (int32_t)score < MIN_SCORE) continue;
+    const AnchorRec f = a[i], l = a[b];
     uint32_t r0 = f.rpos < l.rpos ? f.rpos : l.rpos, r1 = f.rpos < l.rpos ? l.rpos : f.rpos;
-    IntervalKey key = make_interval(score, num_anchors, f.qpos, l.qpos, r0, r1, f.rc >> 1, qctg, chunk_local_id, f.rc & 1u);
+    IntervalKey key5 = make_interval((int32_t)score, num_anchors, f.qpos, l.qpos, r0, r1, f.rc >> 1, qctg, chunk_local_id, f.rc & 1u);
     uint32_t slot = atomicAdd(&ws.pair_nint[p], 1u);
-    ws.iv[ws.pairIbase[p] + slot] = key;
-  };
-  dp_chunk(a, n, prm.band, ws.score + a0, ws.ptr + a0, ws.root + a0, ws.depth + a0, ws.cnt + a0, ws.best + a0, emit);
+    ws.iv[ws.pairIbase[p] + slot] = key5;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -772,7 +862,7 @@ static int upload_tables(sk_ctx* ctx) {
 static SetView view_of(const sk_sketch_set* s) {
   SetView v;
   v.pv_kmer = s->pv_kmer; v.pv_pos = s->pv_pos; v.pv_cc = s->pv_cc; v.pv_mult = s->pv_mult;
-  v.kv_pos = s->kv_pos; v.kv_cc = s->kv_cc; v.ukmer = s->ukmer; v.ustart = s->ustart; v.ctg_rec_off = s->ctg_rec_off;
+  v.kv_pos = s->kv_pos; v.kv_cc = s->kv_cc; v.ukmer = s->ukmer; v.ustart = s->ustart; v.ctg_rec_off = s->ctg_rec_off; v.ubucket = s->ubucket;
   return v;
 }
 
@@ -838,17 +928,18 @@ struct ChainScratch {
   size_t c_rec_rstart = 0, c_rec_nh = 0, c_hit_rec = 0, c_hit_aoff = 0, c_hit_clfirst = 0, c_hit_need = 0, c_hit_p0 = 0, c_hit_cid = 0;
   size_t c_pairA = 0, c_pairH = 0, c_pairC = 0, c_pairAbase = 0, c_pairCbase = 0, c_pairIbase = 0, c_pair_nint = 0, c_pair_sumlen = 0,
          c_pair_nchains = 0, c_pair_tqb = 0;
-  size_t c_anc = 0, c_score = 0, c_ptr = 0, c_root = 0, c_depth = 0, c_cnt = 0, c_best = 0;
+  size_t c_anc = 0, c_score = 0, c_ptr = 0, c_rootkey = 0, c_depth = 0;
   size_t c_chunk_first = 0, c_chunk_pair = 0, c_chunk_qctg = 0, c_chunk_lo = 0, c_chunk_hi = 0, c_acc_total = 0, c_acc_rq0 = 0,
          c_acc_rq1 = 0, c_acc_tbcq = 0, c_acc_nint = 0, c_chunk_head = 0, c_chunk_est = 0, c_chunk_w = 0, c_chunk_valid = 0, c_chunk_nseeds = 0;
   size_t c_iv = 0, c_iv_order = 0, c_iv_kept = 0, c_iv_next = 0, c_acc_list = 0, c_est_sorted = 0, c_w_sorted = 0;
   PairDesc* d_pairs = nullptr; size_t c_pairs = 0;
   sk_ani_result* d_out = nullptr; size_t c_out = 0;
   GenomeMeta *d_m0 = nullptr, *d_m1 = nullptr;
+  size_t c_m0 = 0, c_m1 = 0;
   void free_all() {
     void* ptrs[] = {ws.rec_rstart, ws.rec_nh, ws.hit_rec, ws.hit_aoff, ws.hit_clfirst, ws.hit_need, ws.hit_p0, ws.hit_cid, ws.pairA, ws.pairH,
                     ws.pairC, ws.pairAbase, ws.pairCbase, ws.pairIbase, ws.pair_nint, ws.pair_sumlen, ws.pair_nchains, ws.pair_tqb_ns, ws.anc,
-                    ws.score, ws.ptr, ws.root, ws.depth, ws.cnt, ws.best, ws.chunk_first, ws.chunk_pair, ws.chunk_qctg, ws.chunk_lo, ws.chunk_hi,
+                    ws.score, ws.ptr, ws.rootkey, ws.depth, ws.chunk_first, ws.chunk_pair, ws.chunk_qctg, ws.chunk_lo, ws.chunk_hi,
                     ws.acc_total, ws.acc_rq0, ws.acc_rq1, ws.acc_tbcq, ws.acc_nint, ws.chunk_head, ws.chunk_est, ws.chunk_w, ws.chunk_valid,
                     ws.chunk_nseeds, ws.iv, ws.iv_order, ws.iv_kept, ws.iv_next, ws.acc_list, ws.est_sorted, ws.w_sorted, d_pairs, d_out, d_m0, d_m1};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -898,8 +989,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   SK_CUDA(cudaMemcpyAsync(ws.pairCbase, cbase.data(), (B + 1) * 8, cudaMemcpyHostToDevice, st));
   SK_CUDA(cudaMemcpyAsync(ws.pairIbase, ibase.data(), (B + 1) * 8, cudaMemcpyHostToDevice, st));
   const size_t NA = std::max<uint64_t>(TA, 1), NCH = std::max<uint64_t>(TC, 1), NI = std::max<uint64_t>(TI, 1);
-  ENS(anc, c_anc, NA); ENS(score, c_score, NA); ENS(ptr, c_ptr, NA); ENS(root, c_root, NA); ENS(depth, c_depth, NA); ENS(cnt, c_cnt, NA);
-  ENS(best, c_best, NA);
+  ENS(anc, c_anc, NA); ENS(score, c_score, dbg ? NA : 1); ENS(ptr, c_ptr, dbg ? NA : 1); ENS(rootkey, c_rootkey, NA); ENS(depth, c_depth, NA);
   ENS(chunk_first, c_chunk_first, NCH + 1); ENS(chunk_pair, c_chunk_pair, NCH); ENS(chunk_qctg, c_chunk_qctg, NCH);
   ENS(chunk_lo, c_chunk_lo, NCH); ENS(chunk_hi, c_chunk_hi, NCH); ENS(acc_total, c_acc_total, NCH); ENS(acc_rq0, c_acc_rq0, NCH);
   ENS(acc_rq1, c_acc_rq1, NCH); ENS(acc_tbcq, c_acc_tbcq, NCH); ENS(acc_nint, c_acc_nint, NCH); ENS(chunk_head, c_chunk_head, NCH);
@@ -911,7 +1001,16 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
     SK_CUDA(cudaMemcpyAsync(ws.chunk_first + TC, &TA, 8, cudaMemcpyHostToDevice, st));
     init_chunk_acc_kernel<<<(uint32_t)((TC + 255) / 256), 256, 0, st>>>(TC, ws); count_launch(ctx);
     SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
-    SK_LAUNCH(ctx, "dp_kernel", (dp_kernel<<<(uint32_t)((TC + 127) / 128), 128, 0, st>>>(TC, prm, ws)));
+    {
+      const uint32_t grid = (uint32_t)TC;
+      const uint32_t nb = prm.band / 32 + 2;   // register sets per lane: current block + ceil(band / 32) earlier ones
+#define DP_LAUNCH(NBV)                                                                                       \
+  if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, true><<<grid, 32, 0, st>>>(TC, prm, ws)));       \
+  else SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, false><<<grid, 32, 0, st>>>(TC, prm, ws)));
+      if (nb <= 2) { DP_LAUNCH(2) } else if (nb <= 4) { DP_LAUNCH(4) } else if (nb <= 8) { DP_LAUNCH(8) }
+      else if (nb <= 16) { DP_LAUNCH(16) } else { ctx->err = "c too small: chain band > 479 anchors is not supported"; return SK_ERR_PARAM; }
+#undef DP_LAUNCH
+    }
     SK_LAUNCH(ctx, "select_kernel", (select_kernel<<<B, CT, 0, st>>>(S.d_pairs, prm, ws)));
     SK_LAUNCH(ctx, "chunkstat_kernel", (chunkstat_kernel<<<(uint32_t)((TC + 127) / 128), 128, 0, st>>>(TC, S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
   }
@@ -1002,6 +1101,7 @@ static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_se
   ChainParams prm;
   prm.c = refs->sp.c; prm.k = refs->sp.k;
   prm.band = BP_CHAIN_BAND / refs->sp.c;                       // index_chain_band (src/chain.rs:111-112)
+  prm.ushift = 2 * refs->sp.k > UBUCKET_BITS ? 2 * refs->sp.k - UBUCKET_BITS : 0;
   prm.robust = mp->robust; prm.median = mp->median;
   double fcc = mp->min_aligned_frac;
   if (fcc < 0.) fcc = 15.0 / 100.;                              // src/chain.rs:101-107
@@ -1014,13 +1114,16 @@ static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_se
   }
   if (prm.band >= 0x7FFF) { ctx->err = "band too large"; return SK_ERR_PARAM; }
   const bool same = (refs == qs);
-  ChainScratch S;
-  struct Guard { ChainScratch& s; ~Guard() { s.free_all(); } } guard{S};
+  if (!ctx->chain_scratch) {
+    ctx->chain_scratch = new ChainScratch();
+    ctx->chain_scratch_free = [](void* p) { ((ChainScratch*)p)->free_all(); delete (ChainScratch*)p; };
+  }
+  ChainScratch& S = *(ChainScratch*)ctx->chain_scratch;   // grow-only device buffers, reused by every call on this context
   std::vector<GenomeMeta> m0, m1;
   build_meta(refs, m0);
   build_meta(qs, m1);
-  SK_CUDA(cudaMalloc((void**)&S.d_m0, std::max<size_t>(m0.size(), 1) * sizeof(GenomeMeta)));
-  SK_CUDA(cudaMalloc((void**)&S.d_m1, std::max<size_t>(m1.size(), 1) * sizeof(GenomeMeta)));
+  SK_TRY(ensure(ctx, &S.d_m0, &S.c_m0, m0.size()));
+  SK_TRY(ensure(ctx, &S.d_m1, &S.c_m1, m1.size()));
   SK_CUDA(cudaMemcpyAsync(S.d_m0, m0.data(), m0.size() * sizeof(GenomeMeta), cudaMemcpyHostToDevice, st));
   SK_CUDA(cudaMemcpyAsync(S.d_m1, m1.data(), m1.size() * sizeof(GenomeMeta), cudaMemcpyHostToDevice, st));
   const SetView v0 = view_of(refs), v1 = view_of(qs);

@@ -215,6 +215,22 @@ __global__ void mult_kernel(const uint64_t* __restrict__ seg_off, const uint32_t
   }
 }
 
+// bucket index over each genome's distinct k-mers: ubucket[g][b] = first index u with (ukmer[u] >> shift) >= b
+__global__ void bucket_kernel(const uint64_t* __restrict__ uk_off, const uint32_t* __restrict__ ukmer, uint32_t shift,
+                              uint32_t* __restrict__ ubucket) {
+  const uint32_t g = blockIdx.x;
+  const uint32_t* uk = ukmer + uk_off[g];
+  const uint32_t n = (uint32_t)(uk_off[g + 1] - uk_off[g]);
+  for (uint32_t b = threadIdx.x; b <= UBUCKETS; b += blockDim.x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if ((uk[mid] >> shift) < b) lo = mid + 1; else hi = mid;
+    }
+    ubucket[(size_t)g * (UBUCKETS + 1) + b] = lo;
+  }
+}
+
 // markers: flag distinct values inside each genome's sorted segment
 __global__ void marker_head_kernel(const uint64_t* __restrict__ seg_off, const uint64_t* __restrict__ mk,
                                    uint32_t* __restrict__ head) {
@@ -250,11 +266,13 @@ static int scan_exclusive(sk_ctx* ctx, const T* in, T* out, size_t n) {
 
 void free_set_device(sk_sketch_set* s) {
   void* ptrs[] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart,
-                  s->markers, s->ctg_rec_off, s->d_ctg_len};
-  for (void* p : ptrs) if (p) cudaFree(p);
+                  s->markers, s->ctg_rec_off, s->d_ctg_len, s->ubucket};
+  cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
+  for (void* p : ptrs) if (p) cudaFreeAsync(p, st);
   s->pv_kmer = s->pv_pos = s->pv_cc = s->kv_pos = s->kv_cc = s->ukmer = s->ustart = s->ctg_rec_off = s->d_ctg_len = nullptr;
   s->pv_mult = nullptr;
   s->markers = nullptr;
+  s->ubucket = nullptr;
 }
 
 // Given the position view (pv_kmer/pv_pos/pv_cc filled, set->seed_off known) and the raw (unsorted, possibly
@@ -266,9 +284,9 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
   DTmp<uint64_t> d_seed_off, d_rawmk_off;
   SK_CUDA(d_seed_off.alloc(G + 1, st));
   SK_CUDA(cudaMemcpyAsync(d_seed_off.p, set->seed_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
-  SK_CUDA(cudaMalloc((void**)&set->kv_pos, std::max<size_t>(S, 1) * 4));
-  SK_CUDA(cudaMalloc((void**)&set->kv_cc, std::max<size_t>(S, 1) * 4));
-  SK_CUDA(cudaMalloc((void**)&set->pv_mult, std::max<size_t>(S, 1) * 2));
+  SK_CUDA(cudaMallocAsync((void**)&set->kv_pos, std::max<size_t>(S, 1) * 4, ctx->stream));
+  SK_CUDA(cudaMallocAsync((void**)&set->kv_cc, std::max<size_t>(S, 1) * 4, ctx->stream));
+  SK_CUDA(cudaMallocAsync((void**)&set->pv_mult, std::max<size_t>(S, 1) * 2, ctx->stream));
   set->uk_off.assign(G + 1, 0);
   if (S > 0) {
     if (S >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 seed records"; return SK_ERR_PARAM; }
@@ -298,16 +316,26 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_seed_off.p, G + 1, S, U, d_ukoff.p); count_launch(ctx);
     SK_CUDA(cudaMemcpyAsync(set->uk_off.data(), d_ukoff.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
     set->U = U;
-    SK_CUDA(cudaMalloc((void**)&set->ukmer, std::max<size_t>(U, 1) * 4));
-    SK_CUDA(cudaMalloc((void**)&set->ustart, (size_t)(U + G) * 4));
+    SK_CUDA(cudaMallocAsync((void**)&set->ukmer, std::max<size_t>(U, 1) * 4, ctx->stream));
+    SK_CUDA(cudaMallocAsync((void**)&set->ustart, (size_t)(U + G) * 4, ctx->stream));
     groups_kernel<<<G, 256, 0, st>>>(d_seed_off.p, skmer.p, head.p, hscan.p, U, G, set->ukmer, set->ustart); count_launch(ctx);
     mult_kernel<<<G, 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult); count_launch(ctx);
     SK_CUDA(cudaStreamSynchronize(st));
   } else {
     set->U = 0;
-    SK_CUDA(cudaMalloc((void**)&set->ukmer, 4));
-    SK_CUDA(cudaMalloc((void**)&set->ustart, (size_t)(G + 1) * 4));
+    SK_CUDA(cudaMallocAsync((void**)&set->ukmer, 4, ctx->stream));
+    SK_CUDA(cudaMallocAsync((void**)&set->ustart, (size_t)(G + 1) * 4, ctx->stream));
     SK_CUDA(cudaMemsetAsync(set->ustart, 0, (size_t)(G + 1) * 4, st));
+  }
+  {  // bucket index for the probe kernel
+    DTmp<uint64_t> d_uk;
+    SK_CUDA(d_uk.alloc(G + 1, st));
+    SK_CUDA(cudaMemcpyAsync(d_uk.p, set->uk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+    SK_CUDA(cudaMallocAsync((void**)&set->ubucket, (size_t)std::max<uint32_t>(G, 1) * (UBUCKETS + 1) * 4, st));
+    const uint32_t kbits = 2 * set->sp.k;
+    const uint32_t shift = kbits > UBUCKET_BITS ? kbits - UBUCKET_BITS : 0;
+    if (G) { bucket_kernel<<<G, 256, 0, st>>>(d_uk.p, set->ukmer, shift, set->ubucket); count_launch(ctx); }
+    SK_CUDA(cudaStreamSynchronize(st));
   }
   // ---- markers: per-genome sort + dedup (HashSet semantics, reference src/types.rs:269)
   const size_t MR = raw_mk_off[G];
@@ -335,7 +363,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     SK_CUDA(cudaStreamSynchronize(st));
     uint32_t M = lh + ls;
     set->M = M;
-    SK_CUDA(cudaMalloc((void**)&set->markers, std::max<size_t>(M, 1) * 8));
+    SK_CUDA(cudaMallocAsync((void**)&set->markers, std::max<size_t>(M, 1) * 8, ctx->stream));
     marker_compact_kernel<<<div_up(MR, 256), 256, 0, st>>>(sorted.p, head.p, hscan.p, (uint32_t)MR, set->markers); count_launch(ctx);
     DTmp<uint64_t> d_mkoff;
     SK_CUDA(d_mkoff.alloc(G + 1, st));
@@ -344,7 +372,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     SK_CUDA(cudaStreamSynchronize(st));
   } else {
     set->M = 0;
-    SK_CUDA(cudaMalloc((void**)&set->markers, 8));
+    SK_CUDA(cudaMallocAsync((void**)&set->markers, 8, ctx->stream));
   }
   return SK_OK;
 }
@@ -393,8 +421,8 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
   for (uint32_t g = 0; g < G; g++) set->name_rank[g] = g;
   const uint32_t NU = (uint32_t)units;
 
-  SK_CUDA(cudaMalloc((void**)&set->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
-  SK_CUDA(cudaMalloc((void**)&set->ctg_rec_off, (size_t)(n_contigs + G + 1) * 4));
+  SK_CUDA(cudaMallocAsync((void**)&set->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4, ctx->stream));
+  SK_CUDA(cudaMallocAsync((void**)&set->ctg_rec_off, (size_t)(n_contigs + G + 1) * 4, ctx->stream));
   set->seed_off.assign(G + 1, 0);
 
   DTmp<uint64_t> d_coff, P;
@@ -431,9 +459,9 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     std::vector<uint32_t> crec(n_contigs + 1);
     SK_CUDA(cudaMemcpyAsync(crec.data(), d_crec.p, (n_contigs + 1) * 4, cudaMemcpyDeviceToHost, st));
     set->S = S;
-    SK_CUDA(cudaMalloc((void**)&set->pv_kmer, std::max<size_t>(S, 1) * 4));
-    SK_CUDA(cudaMalloc((void**)&set->pv_pos, std::max<size_t>(S, 1) * 4));
-    SK_CUDA(cudaMalloc((void**)&set->pv_cc, std::max<size_t>(S, 1) * 4));
+    SK_CUDA(cudaMallocAsync((void**)&set->pv_kmer, std::max<size_t>(S, 1) * 4, ctx->stream));
+    SK_CUDA(cudaMallocAsync((void**)&set->pv_pos, std::max<size_t>(S, 1) * 4, ctx->stream));
+    SK_CUDA(cudaMallocAsync((void**)&set->pv_cc, std::max<size_t>(S, 1) * 4, ctx->stream));
     SK_CUDA(mkv.alloc(S, st));
     SK_LAUNCH(ctx, "expand_kernel", (expand_kernel<<<div_up(NU, 256), 256, 0, st>>>(
         P.p, ucontig.p, d_cuoff.p, d_clocal.p, NU, PM.p, uoff.p, seed_mask, thr_m, set->pv_kmer, set->pv_pos, set->pv_cc, mkv.p)));
@@ -472,7 +500,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     }
   } else {
     set->S = 0;
-    SK_CUDA(cudaMalloc((void**)&set->pv_kmer, 4)); SK_CUDA(cudaMalloc((void**)&set->pv_pos, 4)); SK_CUDA(cudaMalloc((void**)&set->pv_cc, 4));
+    SK_CUDA(cudaMallocAsync((void**)&set->pv_kmer, 4, ctx->stream)); SK_CUDA(cudaMallocAsync((void**)&set->pv_pos, 4, ctx->stream)); SK_CUDA(cudaMallocAsync((void**)&set->pv_cc, 4, ctx->stream));
     SK_CUDA(cudaMemsetAsync(set->ctg_rec_off, 0, (size_t)(n_contigs + G + 1) * 4, st));
   }
   // free the big per-base temporaries before the sort temporaries are allocated

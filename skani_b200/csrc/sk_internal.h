@@ -21,6 +21,11 @@ struct sk_ctx {
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_free[2] = {nullptr, nullptr};
   cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+  uint8_t* dbuf[2] = {nullptr, nullptr};  // device staging double buffer (sk_sketch_batch)
+  size_t dbuf_bytes = 0;
+  // grow-only chaining workspace (chain.cu), kept for the life of the context
+  void* chain_scratch = nullptr;
+  void (*chain_scratch_free)(void*) = nullptr;
   // optional per-kernel timing (sk_ctx_set_timing): CUDA events on the launch stream around each major kernel
   bool timing = false;
   struct Pending { const char* name; cudaEvent_t e0, e1; };
@@ -64,6 +69,7 @@ struct sk_sketch_set {
   uint64_t* markers = nullptr;                                        // [M] sorted distinct per genome
   uint32_t* ctg_rec_off = nullptr;                                    // [C+G] genome g, contig j -> ctg_rec_off[ctg_off[g] + g + j] = local first pv record; +1 sentinel
   uint32_t* d_ctg_len = nullptr;                                      // [C]
+  uint32_t* ubucket = nullptr;                                        // [G * (UBUCKETS + 1)] first ukmer index of each top-bits bucket, per genome
 };
 
 #define SK_CUDA(call)                                                                         \
@@ -108,6 +114,8 @@ struct DTmp {
 };
 
 namespace sk {
+constexpr uint32_t UBUCKET_BITS = 12;
+constexpr uint32_t UBUCKETS = 1u << UBUCKET_BITS;
 // seeding.cu
 int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base, const uint64_t* contig_off, uint32_t n_contigs,
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out);

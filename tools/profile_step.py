@@ -52,3 +52,10 @@ t0 = time.perf_counter()
 res, st = sk.triangle(ctx, host, off, goc, n, sp, mp)
 print("e2e triangle %.1f ms (sketch %.1f screen %.1f chain %.1f)" % ((time.perf_counter() - t0) * 1e3, st.t_sketch * 1e3,
                                                                       st.t_screen * 1e3, st.t_chain * 1e3))
+# raw H2D bandwidth of the same pinned buffer (reference point for the e2e leg)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+dev.copy_(pinned, non_blocking=True)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+print("raw H2D %.1f GB/s (%.1f ms for %.2f GB)" % (n * L / dt / 1e9, dt * 1e3, n * L / 1e9))

@@ -419,19 +419,30 @@ dp_warp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
       cur.rc = __shfl_sync(FULL, rc[0], m);
       int32_t best_ns = 0;
       uint32_t best_j1 = 0;  // j + 1 of this lane's best candidate
+      // Exactly one of two adjacent register sets can hold a predecessor of i in this lane: set t when lane < m
+      // (j = 32 (b - t) + lane < i in the same residue class), set t + 1 otherwise.  32-bit arithmetic throughout:
+      // contig lengths are < 2^32 - 65536 (enforced at sketch time), so the unsigned range tests below are exact.
+      const bool lo_set = lane < m;
 #pragma unroll
-      for (int s = 0; s < NB; s++) {   // ascending s = descending j inside a lane: strict > keeps the largest j
-        if (b0 >= 32u * s) {
-          const uint32_t j = b0 - 32u * s + lane;
-          if (j < i && i - j <= band && (rc[s] >> 1) == (cur.rc >> 1) && cur.qpos - q[s] <= BP_CHAIN_BAND) {
-            AnchorRec past; past.qpos = q[s]; past.rpos = r[s]; past.rc = rc[s];
-            const int32_t ps = pair_score(cur, past);
-            if (ps != INT32_MIN) {
-              const int32_t ns = ps + sc[s];
-              if (ns > best_ns) { best_ns = ns; best_j1 = j + 1; }
-            }
-          }
-        }
+      for (int t = 0; t < NB - 1; t++) {   // ascending t = descending j inside a lane: strict > keeps the largest j
+        const uint32_t qs = lo_set ? q[t] : q[t + 1];
+        const uint32_t rs = lo_set ? r[t] : r[t + 1];
+        const uint32_t rcs = lo_set ? rc[t] : rc[t + 1];
+        const int32_t scs = lo_set ? sc[t] : sc[t + 1];
+        const uint32_t d = m + 32u * (uint32_t)t + (lo_set ? 0u : 32u) - lane;   // i - j >= 1
+        const uint32_t j = i - d;                                               // wraps when the set is not filled yet
+        const uint32_t dq = cur.qpos - qs;                                      // >= 0 inside a chunk (sorted)
+        const uint32_t tr = cur.rpos - rs;
+        const uint32_t dr = (cur.rc & 1u) ? (0u - tr) : tr;                     // src/chain.rs:580-584
+        const uint32_t g = dr - dq;
+        const bool ok = (d <= band) & (d <= i) &                                // window (:859-863) and j >= 0
+                        (rcs == cur.rc) &                                       // same ref contig (:856) and same strand (:564)
+                        (dq - 1u < BP_CHAIN_BAND) &                             // query_pos differs (:567) and dq <= 2500 (:859)
+                        (dr - 1u < (uint32_t)MAX_LIN) &                         // 0 < dr <= 5000 (:586-592), ref_pos differs (:567)
+                        (g + (uint32_t)MAX_GAP <= 2u * (uint32_t)MAX_GAP);      // |dr - dq| <= 300 (:594-597)
+        const int32_t gi = (int32_t)g;
+        const int32_t ns = scs + ANCHOR_SCORE - (gi < 0 ? -gi : gi);
+        if (ok && ns > best_ns) { best_ns = ns; best_j1 = j + 1; }
       }
       const int32_t smax = __reduce_max_sync(FULL, best_ns);
       if (smax > 0) {   // uniform branch

@@ -397,7 +397,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
   uint32_t prev_g = 0, rank = 0;
   for (uint32_t i = 0; i < n_contigs; i++) {
     uint64_t len = contig_off[i + 1] - contig_off[i];
-    if (contig_off[i + 1] < contig_off[i] || len >= (1ull << 32)) { ctx->err = "contig length out of range (u32 positions, src/types.rs:52)"; return SK_ERR_PARAM; }
+    if (contig_off[i + 1] < contig_off[i] || len >= (1ull << 32) - 65536) { ctx->err = "contig length out of range (u32 positions, src/types.rs:52; pos + 20000 must not wrap, src/chain.rs:743)"; return SK_ERR_PARAM; }
     uint32_t g = genome_of_contig[i];
     if (g >= G || g < prev_g) { ctx->err = "genome_of_contig must be non-decreasing and < n_genomes"; return SK_ERR_PARAM; }
     if (g != prev_g || i == 0) rank = 0;

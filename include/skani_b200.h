@@ -110,12 +110,26 @@ int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* params, const uint
                          const uint32_t* contig_canon, uint64_t n_records, const uint64_t* markers, uint64_t n_markers,
                          const uint32_t* contig_lengths, uint32_t n_contigs, sk_sketch_set** out);
 
+/* ---- multi-GPU plumbing (the reference is single-process): a sketch set is flattened into ONE
+ *      device buffer + a small host metadata vector so that ranks can exchange sketches with a single NCCL all-gather
+ *      over NVLink, then rebuilt (rank-major genome order) on every GPU.
+ * sk_sketch_set_blob_size: bytes of the device blob and number of u64 metadata words.
+ * sk_sketch_set_pack     : d_blob (device, >= bytes) and host_meta (host, >= words) are caller-allocated.
+ * sk_sketch_set_unpack   : builds ONE set from n_parts blobs (device pointers) + their metadata, concatenated in order. */
+int sk_sketch_set_blob_size(const sk_sketch_set* set, uint64_t* device_bytes, uint64_t* host_meta_words);
+int sk_sketch_set_pack(const sk_sketch_set* set, void* d_blob, uint64_t* host_meta);
+int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blobs, const uint64_t* const* host_metas,
+                         sk_sketch_set** out);
+
 /* ---- marker screen: replaces screen::kmer_to_sketch_from_refs + screen_refs / screen_refs_indices /
  *      check_markers_quickly (src/screen.rs:190, 148, 39, 84) -----------------------------------------------
  * Output pair lists are malloc'd by the library (free with sk_free), sorted ascending, each pair = (a << 32) | b. */
 /* triangle: pairs (i, j), i < j, such that j is in screen_refs(i) (src/triangle.rs:71-90; asymmetric rule) */
 int sk_screen_triangle(sk_ctx* ctx, const sk_sketch_set* set, const sk_map_params* mp, uint64_t** pairs_ij,
                        uint64_t* n_pairs);
+/* same, restricted to rows i with i % row_mod == row_rem: the partition of the pair set over ranks (no communication) */
+int sk_screen_triangle_rows(sk_ctx* ctx, const sk_sketch_set* set, const sk_map_params* mp, uint32_t row_mod, uint32_t row_rem,
+                            uint64_t** pairs_ij, uint64_t* n_pairs);
 /* dist / search: pairs (ref, query).  mode 0 = check_markers_quickly with rescue_small from mp (dist without index,
  * src/dist.rs:104), mode 1 = check_markers_quickly with rescue_small = false (search, src/search.rs:127),
  * mode 2 = screen_refs via the inverted index (dist with index, src/dist.rs:122), mode 3 = screen_refs_indices

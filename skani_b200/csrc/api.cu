@@ -237,6 +237,86 @@ int sk_sketch_set_append(sk_sketch_set* dst, const sk_sketch_set* src) {
   return SK_OK;
 }
 
+namespace {
+struct BlobLayout {
+  size_t off[12];
+  size_t bytes[12];
+  size_t total;
+};
+inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+BlobLayout blob_layout(size_t G, size_t S, size_t U, size_t M, size_t Cn) {
+  BlobLayout b;
+  const size_t n[12] = {S * 4, S * 4, S * 4, S * 2, S * 4, S * 4, U * 4, (U + G) * 4, M * 8, (Cn + G) * 4, Cn * 4, G * (UBUCKETS + 1) * 4};
+  size_t o = 0;
+  for (int i = 0; i < 12; i++) { b.off[i] = o; b.bytes[i] = n[i]; o += al256(n[i]); }
+  b.total = o ? o : 256;
+  return b;
+}
+inline const void* set_array(const sk_sketch_set* s, int i) {
+  const void* p[12] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart, s->markers, s->ctg_rec_off,
+                       s->d_ctg_len, s->ubucket};
+  return p[i];
+}
+}  // namespace
+
+int sk_sketch_set_blob_size(const sk_sketch_set* s, uint64_t* device_bytes, uint64_t* host_meta_words) {
+  if (!s || !device_bytes || !host_meta_words) return SK_ERR_PARAM;
+  *device_bytes = blob_layout(s->G, s->S, s->U, s->M, s->C).total;
+  *host_meta_words = 8 + 4 * ((uint64_t)s->G + 1) + s->G + s->C;
+  return SK_OK;
+}
+
+int sk_sketch_set_pack(const sk_sketch_set* s, void* d_blob, uint64_t* meta) {
+  if (!s || !d_blob || !meta) return SK_ERR_PARAM;
+  sk_ctx* ctx = s->ctx;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  BlobLayout b = blob_layout(s->G, s->S, s->U, s->M, s->C);
+  for (int i = 0; i < 12; i++)
+    if (b.bytes[i]) SK_CUDA(cudaMemcpyAsync((uint8_t*)d_blob + b.off[i], set_array(s, i), b.bytes[i], cudaMemcpyDeviceToDevice, ctx->stream));
+  uint64_t* m = meta;
+  *m++ = s->G; *m++ = s->S; *m++ = s->U; *m++ = s->M; *m++ = s->C; *m++ = s->sp.c; *m++ = s->sp.k; *m++ = s->sp.marker_c;
+  for (uint32_t g = 0; g <= s->G; g++) *m++ = s->seed_off[g];
+  for (uint32_t g = 0; g <= s->G; g++) *m++ = s->uk_off[g];
+  for (uint32_t g = 0; g <= s->G; g++) *m++ = s->mk_off[g];
+  for (uint32_t g = 0; g <= s->G; g++) *m++ = s->ctg_off[g];
+  for (uint32_t g = 0; g < s->G; g++) *m++ = s->total_len[g];
+  for (size_t c = 0; c < s->C; c++) *m++ = s->ctg_len[c];
+  SK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SK_OK;
+}
+
+int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blobs, const uint64_t* const* metas, sk_sketch_set** out) {
+  if (!ctx || !out || n_parts == 0 || !d_blobs || !metas) return SK_ERR_PARAM;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  // non-owning views over the blobs, then one concatenating copy
+  std::vector<sk_sketch_set> views(n_parts);
+  std::vector<const sk_sketch_set*> vp;
+  for (uint32_t i = 0; i < n_parts; i++) {
+    const uint64_t* m = metas[i];
+    sk_sketch_set& v = views[i];
+    v.ctx = ctx;
+    v.G = (uint32_t)m[0]; v.S = m[1]; v.U = m[2]; v.M = m[3]; v.C = m[4];
+    v.sp.c = (uint32_t)m[5]; v.sp.k = (uint32_t)m[6]; v.sp.marker_c = (uint32_t)m[7];
+    m += 8;
+    v.seed_off.assign(m, m + v.G + 1); m += v.G + 1;
+    v.uk_off.assign(m, m + v.G + 1); m += v.G + 1;
+    v.mk_off.assign(m, m + v.G + 1); m += v.G + 1;
+    v.ctg_off.assign(m, m + v.G + 1); m += v.G + 1;
+    v.total_len.assign(m, m + v.G); m += v.G;
+    v.ctg_len.resize(v.C);
+    for (size_t c = 0; c < v.C; c++) v.ctg_len[c] = (uint32_t)m[c];
+    v.name_rank.resize(v.G);
+    BlobLayout b = blob_layout(v.G, v.S, v.U, v.M, v.C);
+    uint8_t* base = (uint8_t*)d_blobs[i];
+    v.pv_kmer = (uint32_t*)(base + b.off[0]); v.pv_pos = (uint32_t*)(base + b.off[1]); v.pv_cc = (uint32_t*)(base + b.off[2]);
+    v.pv_mult = (uint16_t*)(base + b.off[3]); v.kv_pos = (uint32_t*)(base + b.off[4]); v.kv_cc = (uint32_t*)(base + b.off[5]);
+    v.ukmer = (uint32_t*)(base + b.off[6]); v.ustart = (uint32_t*)(base + b.off[7]); v.markers = (uint64_t*)(base + b.off[8]);
+    v.ctg_rec_off = (uint32_t*)(base + b.off[9]); v.d_ctg_len = (uint32_t*)(base + b.off[10]); v.ubucket = (uint32_t*)(base + b.off[11]);
+    vp.push_back(&v);
+  }
+  return concat_sets(ctx, vp, out);
+}
+
 int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* contig_off, uint32_t n_contigs,
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                         sk_sketch_set** out) {

@@ -103,9 +103,10 @@ screen_rows_kernel(const uint64_t* __restrict__ row_mk_off, const uint64_t* __re
                    uint32_t n_cols, const uint32_t* __restrict__ ra, const uint32_t* __restrict__ rb,
                    const uint32_t* __restrict__ scol, int mode, int rescue_small, double cutoff, int all_pass,
                    uint32_t tile, uint64_t* __restrict__ pairs, unsigned long long* __restrict__ n_pairs,
-                   unsigned long long cap) {
+                   unsigned long long cap, uint32_t row_mod, uint32_t row_rem) {
   extern __shared__ uint32_t counts[];
-  const uint32_t i = blockIdx.x;
+  const uint32_t i = blockIdx.x * row_mod + row_rem;
+  if (i >= n_rows) return;
   const uint64_t mb = row_mk_off[i], me = row_mk_off[i + 1];
   const uint64_t card_i = me - mb;
   const bool tri = (mode == MODE_TRIANGLE);
@@ -164,7 +165,7 @@ screen_rows_kernel(const uint64_t* __restrict__ row_mk_off, const uint64_t* __re
 }
 
 static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_set* cols, int mode, const sk_map_params* mp,
-                      uint64_t** out_pairs, uint64_t* out_n) {
+                      uint64_t** out_pairs, uint64_t* out_n, uint32_t row_mod = 1, uint32_t row_rem = 0) {
   cudaStream_t st = ctx->stream;
   const bool tri = (mode == MODE_TRIANGLE);
   const uint32_t NR = rows->G, NC = cols->G;
@@ -239,10 +240,12 @@ static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_se
   for (int attempt = 0; attempt < 2; attempt++) {
     SK_CUDA(d_pairs.alloc(cap, st));
     SK_CUDA(cudaMemsetAsync(d_n.p, 0, 8, st));
-    const uint32_t n_rows_launch = tri ? (NR > 0 ? NR - 1 : 0) : NR;  // src/triangle.rs:71: rows 0..N-2
+    const uint32_t n_rows_total = tri ? (NR > 0 ? NR - 1 : 0) : NR;  // src/triangle.rs:71: rows 0..N-2
+    const uint32_t n_rows_launch = n_rows_total > row_rem ? (n_rows_total - row_rem + row_mod - 1) / row_mod : 0;
     if (n_rows_launch) {
       SK_LAUNCH(ctx, "screen_rows_kernel", (screen_rows_kernel<<<n_rows_launch, 256, smem, st>>>(
-          d_row_off.p, d_col_off.p, NR, NC, ra.p, rb.p, scol.p, mode, mp->rescue_small, cutoff, all_pass, tile, d_pairs.p, d_n.p, cap)));
+          d_row_off.p, d_col_off.p, n_rows_total, NC, ra.p, rb.p, scol.p, mode, mp->rescue_small, cutoff, all_pass, tile, d_pairs.p, d_n.p, cap,
+          row_mod, row_rem)));
     }
     SK_CUDA(cudaMemcpyAsync(&n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaStreamSynchronize(st));
@@ -276,6 +279,13 @@ int sk_screen_triangle(sk_ctx* ctx, const sk_sketch_set* set, const sk_map_param
   if (!ctx || !set || !mp || !pairs || !n) return SK_ERR_PARAM;
   SK_CUDA(cudaSetDevice(ctx->device));
   return sk::run_screen(ctx, set, set, sk::MODE_TRIANGLE, mp, pairs, n);
+}
+
+int sk_screen_triangle_rows(sk_ctx* ctx, const sk_sketch_set* set, const sk_map_params* mp, uint32_t row_mod, uint32_t row_rem,
+                            uint64_t** pairs, uint64_t* n) {
+  if (!ctx || !set || !mp || !pairs || !n || row_mod == 0 || row_rem >= row_mod) return SK_ERR_PARAM;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  return sk::run_screen(ctx, set, set, sk::MODE_TRIANGLE, mp, pairs, n, row_mod, row_rem);
 }
 
 int sk_screen_query_ref(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_set* queries, const sk_map_params* mp, int mode,

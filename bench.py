@@ -212,7 +212,10 @@ def main():
             kept = sum(1 for r in res if r.ani > 0.1)
             gs.free()
             return kept, None
-        return tri.step(host if e2e else None, dev_bases.data_ptr(), off, goc, nloc, g0, N), None
+        kept = tri.step(host if e2e else None, dev_bases.data_ptr(), off, goc, nloc, g0, N)
+        if e2e:
+            result_bytes[0] = kept * C.sizeof(_lib.AniResult)
+        return kept, None
 
     def timed(e2e, n_steps):
         if world > 1:

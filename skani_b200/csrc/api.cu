@@ -225,6 +225,7 @@ int sk_sketch_set_append(sk_sketch_set* dst, const sk_sketch_set* src) {
   SK_CUDA(cudaSetDevice(ctx->device));
   sk_sketch_set* merged = nullptr;
   SK_TRY(concat_sets(ctx, {dst, src}, &merged));
+  SK_TRY(build_hash(ctx, merged));
   free_set_device(dst);
   std::vector<uint64_t> ranks = dst->name_rank;
   uint64_t mx = 0;
@@ -314,7 +315,8 @@ int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blo
     v.ctg_rec_off = (uint32_t*)(base + b.off[9]); v.d_ctg_len = (uint32_t*)(base + b.off[10]); v.ubucket = (uint32_t*)(base + b.off[11]);
     vp.push_back(&v);
   }
-  return concat_sets(ctx, vp, out);
+  SK_TRY(concat_sets(ctx, vp, out));
+  return build_hash(ctx, *out);
 }
 
 int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* contig_off, uint32_t n_contigs,
@@ -361,16 +363,19 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
     sk_sketch_set* part = nullptr;
     uint64_t z = 0;
     SK_TRY(sketch_batch_device(ctx, d_bases, 0, contig_off ? contig_off : &z, 0, nullptr, n_genomes, sp, &part));
+    SK_TRY(build_hash(ctx, part));
     *out = part;
     return SK_OK;
   }
   if (parts.size() == 1) {
+    SK_TRY(build_hash(ctx, parts[0]));
     *out = parts[0];
     parts.clear();
     return SK_OK;
   }
   std::vector<const sk_sketch_set*> cp(parts.begin(), parts.end());
   SK_TRY(concat_sets(ctx, cp, out));
+  SK_TRY(build_hash(ctx, *out));
   return SK_OK;
 }
 
@@ -467,12 +472,14 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
   }
   SK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   if (parts.size() == 1) {
+    SK_TRY(build_hash(ctx, parts[0]));
     *out = parts[0];
     parts.clear();
     return SK_OK;
   }
   std::vector<const sk_sketch_set*> cp(parts.begin(), parts.end());
   SK_TRY(concat_sets(ctx, cp, out));
+  SK_TRY(build_hash(ctx, *out));
   return SK_OK;
 }
 
@@ -529,6 +536,7 @@ int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t
   if (n_markers) SK_CUDA(cudaMemcpyAsync(mraw.p, markers, n_markers * 8, cudaMemcpyHostToDevice, ctx->stream));
   std::vector<uint64_t> raw_off = {0, n_markers};
   SK_TRY(build_views(ctx, s, mraw.p, raw_off));
+  SK_TRY(build_hash(ctx, s));
   SK_CUDA(cudaStreamSynchronize(ctx->stream));
   guard.s = nullptr;
   *out = s;

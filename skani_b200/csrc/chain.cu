@@ -44,12 +44,15 @@ struct SetView {
   const uint32_t *pv_kmer, *pv_pos, *pv_cc;
   const uint16_t* pv_mult;
   const uint32_t *kv_pos, *kv_cc, *ukmer, *ustart, *ctg_rec_off, *ubucket;
+  const unsigned long long* htab;
 };
 struct GenomeMeta {
   uint64_t seed_off, uk_off, ctg_off;  // bases into the set arrays (ustart base = uk_off + g, ctg_rec_off base = ctg_off + g)
   uint32_t n_rec, n_uk, n_ctg, g;
   uint64_t total_len;
   uint32_t q10, q50, q90, pad;
+  uint64_t ht_off;   // k-mer hash table of the genome (probe kernel); ht_cap == 0 => bucket search
+  uint32_t ht_cap, pad2;
 };
 struct PairDesc {
   uint32_t qset, qg, rset, rg;  // query-role (iterated + chunked) and ref-role (probed) genome: set 0 = refs, 1 = queries
@@ -93,6 +96,7 @@ struct Workspace {
   // per interval (capacity floor(A/3) per pair)
   IntervalKey* iv;
   uint32_t* iv_order;   // sorted order (indices local to the pair's slice)
+  unsigned long long* iv_keys;  // primary sort keys for the global-memory sort fallback
   uint8_t* iv_kept;
   uint32_t* iv_next;
   uint32_t* acc_list;   // accepted interval indices (greedy)
@@ -125,7 +129,11 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
   const uint32_t* __restrict__ ruk = R.ukmer + rm.uk_off;
   const uint32_t* __restrict__ rus = R.ustart + rm.uk_off + rm.g;
   const uint32_t nuk = rm.n_uk;
-  {  // every thread of the block probes the same ref-role genome: stage its bucket index (16 KB) in shared memory
+  const bool use_hash = rm.ht_cap != 0;
+  const unsigned long long* __restrict__ htab = R.htab + rm.ht_off;
+  const uint32_t ht_mask = rm.ht_cap - 1;
+  const uint32_t ht_shift = use_hash ? (32u - (uint32_t)__ffs((int)rm.ht_cap) + 1u) : 32u;
+  if (!use_hash) {  // fallback (genomes with >= 2^20 records): bucket index (16 KB) staged in shared memory
     const uint32_t* gb = R.ubucket + (size_t)rm.g * (UBUCKETS + 1);
     for (uint32_t b = threadIdx.x; b <= UBUCKETS; b += CT) s_bucket[b] = gb[b];
     __syncthreads();
@@ -134,33 +142,93 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
   for (uint32_t t0 = 0; t0 < qm.n_rec; t0 += CT * ITEMS) {
     uint64_t item[ITEMS];
     uint32_t rst[ITEMS], nh[ITEMS];
+    if (use_hash) {
+      // one 8-byte probe (plus rare linear-probing steps) per record; the ITEMS probes of a thread are independent
+      uint32_t kmer[ITEMS], hpos[ITEMS];
+      unsigned long long ent[ITEMS];
+      bool live[ITEMS];
 #pragma unroll
-    for (int it = 0; it < ITEMS; it++) {
-      uint32_t t = t0 + threadIdx.x * ITEMS + it;
-      nh[it] = 0; rst[it] = 0;
-      uint32_t counted = 0;
-      if (t < qm.n_rec) {
-        uint32_t kmer = Q.pv_kmer[qm.seed_off + t];
-        uint32_t mq = Q.pv_mult[qm.seed_off + t];
-        if (mq <= prm.band) {                          // query positions > band: dropped entirely (src/chain.rs:676-678)
-          // binary search the ref-role distinct k-mers inside the k-mer's top-bits bucket
-          const uint32_t bk = kmer >> prm.ushift;
-          uint32_t lo = s_bucket[bk], hi = s_bucket[bk + 1];
-          while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (ruk[mid] < kmer) lo = mid + 1; else hi = mid;
-          }
-          if (lo < s_bucket[bk + 1] && lo < nuk && ruk[lo] == kmer) {
-            uint32_t s = rus[lo], cntr = rus[lo + 1] - s;
-            if (cntr <= prm.band) { counted = 1; nh[it] = cntr; rst[it] = s; }  // else dropped entirely (:695-697)
+      for (int it = 0; it < ITEMS; it++) {
+        const uint32_t t = t0 + threadIdx.x * ITEMS + it;
+        live[it] = false; kmer[it] = 0; hpos[it] = 0; ent[it] = 0;
+        if (t < qm.n_rec) {
+          kmer[it] = Q.pv_kmer[qm.seed_off + t];
+          live[it] = Q.pv_mult[qm.seed_off + t] <= prm.band;   // query positions > band: dropped entirely (src/chain.rs:676-678)
+          hpos[it] = (ht_shift >= 32) ? 0u : ((kmer[it] * 0x9E3779B1u) >> ht_shift);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < ITEMS; it++) if (live[it]) ent[it] = htab[hpos[it]];
+#pragma unroll
+      for (int it = 0; it < ITEMS; it++) {
+        const uint32_t t = t0 + threadIdx.x * ITEMS + it;
+        nh[it] = 0; rst[it] = 0;
+        uint32_t counted = 0;
+        if (live[it]) {
+          unsigned long long e = ent[it];
+          uint32_t hp = hpos[it];
+          while (e != 0ull && (uint32_t)(e >> 32) != kmer[it]) { hp = (hp + 1) & ht_mask; e = htab[hp]; }
+          if (e != 0ull) {
+            const uint32_t cntr = (uint32_t)e & 0xFFFu;        // saturated at 4095 > any band
+            if (cntr <= prm.band) { counted = 1; nh[it] = cntr; rst[it] = (uint32_t)(e >> 12) & 0xFFFFFu; }  // else dropped (:695-697)
           } else {
-            counted = 1;                               // no hit: position still counts (:684-687)
+            counted = 1;                                       // no hit: position still counts (:684-687)
           }
         }
+        if (t < qm.n_rec) {
+          ws.rec_rstart[pd.rec_off + t] = rst[it];
+          ws.rec_nh[pd.rec_off + t] = (uint16_t)(nh[it] | (counted << 15));
+        }
+        item[it] = (uint64_t)nh[it] | ((uint64_t)(nh[it] ? 1u : 0u) << 32);
+      }
+    } else {
+    uint32_t kmer[ITEMS], lo[ITEMS], hi[ITEMS], bend[ITEMS];
+    bool live[ITEMS];
+    // the ITEMS searches of a thread advance in lock-step so that their (L2-latency) loads overlap
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const uint32_t t = t0 + threadIdx.x * ITEMS + it;
+      nh[it] = 0; rst[it] = 0; kmer[it] = 0; lo[it] = hi[it] = bend[it] = 0; live[it] = false;
+      if (t < qm.n_rec) {
+        kmer[it] = Q.pv_kmer[qm.seed_off + t];
+        const uint32_t mq = Q.pv_mult[qm.seed_off + t];
+        if (mq <= prm.band) {                          // query positions > band: dropped entirely (src/chain.rs:676-678)
+          const uint32_t bk = kmer[it] >> prm.ushift;
+          lo[it] = s_bucket[bk]; hi[it] = bend[it] = s_bucket[bk + 1];
+          live[it] = true;
+        }
+      }
+    }
+    bool any = true;
+    while (any) {
+      any = false;
+#pragma unroll
+      for (int it = 0; it < ITEMS; it++) {
+        if (live[it] && lo[it] < hi[it]) {
+          const uint32_t mid = (lo[it] + hi[it]) >> 1;
+          if (ruk[mid] < kmer[it]) lo[it] = mid + 1; else hi[it] = mid;
+          any = true;
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const uint32_t t = t0 + threadIdx.x * ITEMS + it;
+      uint32_t counted = 0;
+      if (live[it]) {
+        if (lo[it] < bend[it] && lo[it] < nuk && ruk[lo[it]] == kmer[it]) {
+          const uint32_t s = rus[lo[it]], cntr = rus[lo[it] + 1] - s;
+          if (cntr <= prm.band) { counted = 1; nh[it] = cntr; rst[it] = s; }  // else dropped entirely (:695-697)
+        } else {
+          counted = 1;                                 // no hit: position still counts (:684-687)
+        }
+      }
+      if (t < qm.n_rec) {
         ws.rec_rstart[pd.rec_off + t] = rst[it];
         ws.rec_nh[pd.rec_off + t] = (uint16_t)(nh[it] | (counted << 15));
       }
       item[it] = (uint64_t)nh[it] | ((uint64_t)(nh[it] ? 1u : 0u) << 32);
+    }
     }
     uint64_t agg;
     Scan(tmp).ExclusiveSum(item, item, agg);
@@ -488,22 +556,28 @@ dp_warp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
 // ------------------------------------------------------------------------------------------------------------
 // K5: interval sort + greedy non-overlap selection, block per pair
 // ------------------------------------------------------------------------------------------------------------
-__device__ void block_bitonic_sort_intervals(uint32_t* idx, uint32_t npow2, const IntervalKey* iv) {
-  // idx holds interval indices (0xFFFFFFFF = padding, sorts last); order = interval_before
+__device__ __forceinline__ bool interval_idx_before(uint32_t a, uint32_t b, unsigned long long ka, unsigned long long kb,
+                                                    const IntervalKey* iv) {
+  // a / b = interval indices (0xFFFFFFFF = padding, sorts last); ka / kb = their primary keys (score << 32 | num_anchors)
+  if (a == 0xFFFFFFFFu) return false;
+  if (b == 0xFFFFFFFFu) return true;
+  if (ka != kb) return ka > kb;
+  return interval_before(iv[a], iv[b]);   // rare: full derived-PartialOrd comparison on a primary-key tie
+}
+
+// bitonic sort of (primary key, index) pairs into the descending order of src/chain.rs:1012
+__device__ void block_bitonic_sort_intervals(unsigned long long* key, uint32_t* idx, uint32_t npow2, const IntervalKey* iv) {
   for (uint32_t k = 2; k <= npow2; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       for (uint32_t i = threadIdx.x; i < npow2; i += blockDim.x) {
         uint32_t ixj = i ^ j;
         if (ixj > i) {
           uint32_t a = idx[i], b = idx[ixj];
+          unsigned long long ka = key[i], kb = key[ixj];
           bool up = ((i & k) == 0);
-          bool a_before_b;
-          if (a == 0xFFFFFFFFu) a_before_b = false;
-          else if (b == 0xFFFFFFFFu) a_before_b = true;
-          else a_before_b = interval_before(iv[a], iv[b]);
-          bool swap = up ? !a_before_b : a_before_b;
-          if (a == b) swap = false;
-          if (swap) { idx[i] = b; idx[ixj] = a; }
+          bool a_before_b = interval_idx_before(a, b, ka, kb, iv);
+          bool swap = (a == b) ? false : (up ? !a_before_b : a_before_b);
+          if (swap) { idx[i] = b; idx[ixj] = a; key[i] = kb; key[ixj] = ka; }
         }
       }
       __syncthreads();
@@ -511,13 +585,22 @@ __device__ void block_bitonic_sort_intervals(uint32_t* idx, uint32_t npow2, cons
   }
 }
 
-constexpr uint32_t SEL_SMEM_MAX = 4096;  // intervals sorted in shared memory up to this many (power of two)
+constexpr uint32_t SEL_SMEM_MAX = 1024;   // intervals sorted / accepted in shared memory up to this many (power of two)
+constexpr uint32_t SEL_CELL_SHIFT = 14;   // occupancy-bitmap cell = 16 kb
+constexpr uint32_t SEL_MAP_BITS = 4096;
+
+struct AccRec { uint32_t q0, q1, r0, r1, qctg, rctg; };
+
+__device__ __forceinline__ uint32_t sel_cell_hash(uint32_t ctg, uint32_t cell) { return (cell + ctg * 0x9E37u) & (SEL_MAP_BITS - 1); }
 
 __global__ void __launch_bounds__(CT)
 select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws) {
+  __shared__ unsigned long long s_key[SEL_SMEM_MAX];
   __shared__ uint32_t s_idx[SEL_SMEM_MAX];
+  __shared__ AccRec s_acc[SEL_SMEM_MAX];
+  __shared__ uint32_t s_qmap[SEL_MAP_BITS / 32], s_rmap[SEL_MAP_BITS / 32];
   __shared__ uint32_t s_nacc;
-  __shared__ int s_dec;
+  const unsigned FULL = 0xFFFFFFFFu;
   const uint32_t p = blockIdx.x;
   const uint32_t n = ws.pair_nint[p];
   if (n == 0) return;
@@ -525,14 +608,23 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
   const IntervalKey* iv = ws.iv + ib;
   uint32_t npow2 = 1;
   while (npow2 < n) npow2 <<= 1;
-  uint32_t* idx = (npow2 <= SEL_SMEM_MAX) ? s_idx : (ws.iv_order + 4 * ib);  // global fallback slice has >= 2n slots
-  for (uint32_t i = threadIdx.x; i < npow2; i += blockDim.x) idx[i] = i < n ? i : 0xFFFFFFFFu;
+  const bool in_smem = npow2 <= SEL_SMEM_MAX;
+  // global fallback slices: iv_order has 4 slots per interval capacity, est_sorted-sized u64 scratch is not available here,
+  // so the fallback keeps its primary keys in the iv_keys array (2 x u64 per interval capacity)
+  uint32_t* idx = in_smem ? s_idx : (ws.iv_order + 4 * ib);
+  unsigned long long* key = in_smem ? s_key : (ws.iv_keys + 2 * ib);
+  for (uint32_t i = threadIdx.x; i < npow2; i += blockDim.x) {
+    idx[i] = i < n ? i : 0xFFFFFFFFu;
+    key[i] = i < n ? iv[i].k[0] : 0ull;
+  }
+  for (uint32_t i = threadIdx.x; i < SEL_MAP_BITS / 32; i += blockDim.x) { s_qmap[i] = 0; s_rmap[i] = 0; }
   __syncthreads();
-  block_bitonic_sort_intervals(idx, npow2, iv);
+  block_bitonic_sort_intervals(key, idx, npow2, iv);
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { ws.iv_order[4 * ib + npow2 + i] = idx[i]; }
   __syncthreads();
   const uint32_t* order = ws.iv_order + 4 * ib + npow2;  // final sorted order lives after the sort scratch
-  // greedy selection by warp 0 (inherently ordered, src/chain.rs:1016-1095)
+  // greedy selection by warp 0 (inherently ordered, src/chain.rs:1016-1095).  A 16 kb-cell occupancy bitmap per axis
+  // answers "cannot overlap anything accepted so far" in O(1); only candidates that touch an occupied cell scan the list.
   uint32_t* acc = ws.acc_list + ib;
   if (threadIdx.x == 0) s_nacc = 0;
   __syncthreads();
@@ -542,21 +634,46 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
     for (uint32_t i = 0; i < n; i++) {
       const uint32_t ci = order[i];
       const IntervalKey c = iv[ci];
-      uint32_t sum_r = 0, hit_r = 0, sum_q = 0, hit_q = 0;
-      for (uint32_t a = lane; a < nacc; a += 32) overlap_contrib(c, iv[acc[a]], &sum_r, &hit_r, &sum_q, &hit_q);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sum_r += __shfl_xor_sync(0xFFFFFFFFu, sum_r, o);
-        hit_r += __shfl_xor_sync(0xFFFFFFFFu, hit_r, o);
-        sum_q += __shfl_xor_sync(0xFFFFFFFFu, sum_q, o);
-        hit_q += __shfl_xor_sync(0xFFFFFFFFu, hit_q, o);
+      const uint32_t q0 = iv_q0(c), q1 = iv_q1(c), r0 = iv_r0(c), r1 = iv_r1(c), qc = iv_qctg(c), rcg = iv_rctg(c);
+      const uint32_t cq0 = q0 >> SEL_CELL_SHIFT, ncq = ((q1 - 1) >> SEL_CELL_SHIFT) - cq0 + 1;   // q0 < q1, r0 < r1 always
+      const uint32_t cr0 = r0 >> SEL_CELL_SHIFT, ncr = ((r1 - 1) >> SEL_CELL_SHIFT) - cr0 + 1;
+      bool need_scan = true;
+      if (ncq <= 32 && ncr <= 32) {
+        bool occ = false;
+        if (lane < ncq) { uint32_t h = sel_cell_hash(qc, cq0 + lane); occ |= (s_qmap[h >> 5] >> (h & 31)) & 1u; }
+        if (lane < ncr) { uint32_t h = sel_cell_hash(rcg, cr0 + lane); occ |= (s_rmap[h >> 5] >> (h & 31)) & 1u; }
+        need_scan = __any_sync(FULL, occ);
       }
-      bool ok = overlap_accept(c, sum_r, hit_r, sum_q, hit_q);
-      if (lane == 0) {
-        ws.iv_kept[ib + ci] = ok ? 1 : 0;
-        if (ok) acc[nacc] = ci;
+      bool ok = true;
+      if (need_scan) {
+        uint32_t sum_r = 0, hit_r = 0, sum_q = 0, hit_q = 0;
+        for (uint32_t a = lane; a < nacc; a += 32) {
+          if (a < SEL_SMEM_MAX) {
+            const AccRec x = s_acc[a];
+            if (x.rctg == rcg && x.r0 < r1 && r0 < x.r1) { uint32_t u = r1 - x.r0, v = x.r1 - r0; sum_r += u < v ? u : v; hit_r = 1; }
+            if (x.qctg == qc && x.q0 < q1 && q0 < x.q1) { uint32_t u = q1 - x.q0, v = x.q1 - q0; sum_q += u < v ? u : v; hit_q = 1; }
+          } else {
+            uint32_t hr = 0, hq = 0;
+            overlap_contrib(c, iv[acc[a]], &sum_r, &hr, &sum_q, &hq);
+            hit_r |= hr ? 1u : 0u; hit_q |= hq ? 1u : 0u;
+          }
+        }
+        sum_r = __reduce_add_sync(FULL, sum_r);
+        sum_q = __reduce_add_sync(FULL, sum_q);
+        hit_r = __any_sync(FULL, hit_r) ? 1u : 0u;
+        hit_q = __any_sync(FULL, hit_q) ? 1u : 0u;
+        ok = overlap_accept(c, sum_r, hit_r, sum_q, hit_q);
       }
-      if (ok) nacc++;
+      if (ok) {
+        if (lane == 0) {
+          acc[nacc] = ci;
+          if (nacc < SEL_SMEM_MAX) { AccRec x; x.q0 = q0; x.q1 = q1; x.r0 = r0; x.r1 = r1; x.qctg = qc; x.rctg = rcg; s_acc[nacc] = x; }
+        }
+        for (uint32_t t = lane; t < ncq; t += 32) { uint32_t h = sel_cell_hash(qc, cq0 + t); atomicOr(&s_qmap[h >> 5], 1u << (h & 31)); }
+        for (uint32_t t = lane; t < ncr; t += 32) { uint32_t h = sel_cell_hash(rcg, cr0 + t); atomicOr(&s_rmap[h >> 5], 1u << (h & 31)); }
+        nacc++;
+      }
+      if (lane == 0) ws.iv_kept[ib + ci] = ok ? 1 : 0;
       __syncwarp();
     }
     if (lane == 0) s_nacc = nacc;
@@ -582,7 +699,6 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
     my_cnt += 1;
   }
   if (my_cnt) { atomicAdd(&ws.pair_sumlen[p], my_sum); atomicAdd(&ws.pair_nchains[p], my_cnt); }
-  (void)s_dec;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -652,17 +768,19 @@ __device__ __forceinline__ bool est_less(double ea, uint32_t wa, double eb, uint
 }
 
 constexpr int FT = 128;
-constexpr uint32_t FIN_SMEM_MAX = 2048;
+constexpr uint32_t FIN_SMEM_MAX = 1024;
 
 __global__ void __launch_bounds__(FT)
 final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ m0, const GenomeMeta* __restrict__ m1,
              ChainParams prm, Workspace ws, sk_ani_result* __restrict__ out) {
   __shared__ double s_e[FIN_SMEM_MAX];
   __shared__ uint32_t s_w[FIN_SMEM_MAX];
+  __shared__ uint64_t s_cum[FIN_SMEM_MAX];
   __shared__ uint32_t s_n;
   __shared__ double s_boot[128];
   __shared__ uint32_t s_lower_i, s_upper_i, s_reject;
   __shared__ double s_final, s_std;
+  __shared__ uint64_t s_pool;
   const uint32_t p = blockIdx.x;
   const PairDesc pd = pairs[p];
   const GenomeMeta refm = m0[pd.ref_idx];     // the call's ref / query sketches (un-switched, src/chain.rs:477-484)
@@ -741,17 +859,17 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
     s_std = sqrt(var / (double)n);
     s_lower_i = lower_i; s_upper_i = upper_i;
     s_reject = 0;
+    s_pool = total_mult;
   }
   __syncthreads();
   // bootstrap (src/chain.rs:57-86): 100 replicates x n draws from the weight-expanded pool; replicate r uses draws
   // [r*n, (r+1)*n) of the WyRand stream seeded with 7, each replicate summed sequentially by one thread.
   double ci_lo = 0., ci_hi = 1.;
   if (n >= 10) {
-    uint64_t pool = 0;
-    for (uint32_t i = 0; i < n; i++) pool += gw[i];      // every thread: cheap, avoids another broadcast
+    const uint64_t pool = s_pool;
     // prefix sums of weights for idx -> estimate lookup: reuse gw? keep separate: binary search over running sums
     // (n <= a few thousand; compute cumulative on the fly per thread is O(n) per draw -> too slow; build once)
-    uint64_t* cum = (uint64_t*)(ws.est_sorted + 4 * cb + (nc <= FIN_SMEM_MAX ? 0 : npow2));  // scratch (8 B per chunk available)
+    uint64_t* cum = (nc <= FIN_SMEM_MAX) ? s_cum : (uint64_t*)(ws.est_sorted + 4 * cb + npow2);  // global scratch: 8 B per chunk available
     if (threadIdx.x == 0) {
       uint64_t run = 0;
       for (uint32_t i = 0; i < n; i++) { run += gw[i]; cum[i] = run; }
@@ -873,7 +991,7 @@ static int upload_tables(sk_ctx* ctx) {
 static SetView view_of(const sk_sketch_set* s) {
   SetView v;
   v.pv_kmer = s->pv_kmer; v.pv_pos = s->pv_pos; v.pv_cc = s->pv_cc; v.pv_mult = s->pv_mult;
-  v.kv_pos = s->kv_pos; v.kv_cc = s->kv_cc; v.ukmer = s->ukmer; v.ustart = s->ustart; v.ctg_rec_off = s->ctg_rec_off; v.ubucket = s->ubucket;
+  v.kv_pos = s->kv_pos; v.kv_cc = s->kv_cc; v.ukmer = s->ukmer; v.ustart = s->ustart; v.ctg_rec_off = s->ctg_rec_off; v.ubucket = s->ubucket; v.htab = s->htab;
   return v;
 }
 
@@ -886,7 +1004,9 @@ static void build_meta(const sk_sketch_set* s, std::vector<GenomeMeta>& out) {
     m.n_rec = (uint32_t)(s->seed_off[g + 1] - s->seed_off[g]);
     m.n_uk = (uint32_t)(s->uk_off[g + 1] - s->uk_off[g]);
     m.n_ctg = (uint32_t)(s->ctg_off[g + 1] - s->ctg_off[g]);
-    m.g = g; m.total_len = s->total_len[g]; m.pad = 0;
+    m.g = g; m.total_len = s->total_len[g]; m.pad = 0; m.pad2 = 0;
+    m.ht_off = s->ht_off.empty() ? 0 : s->ht_off[g];
+    m.ht_cap = s->ht_off.empty() ? 0 : (uint32_t)(s->ht_off[g + 1] - s->ht_off[g]);
     tmp.assign(s->ctg_len.begin() + s->ctg_off[g], s->ctg_len.begin() + s->ctg_off[g + 1]);
     std::sort(tmp.begin(), tmp.end());
     size_t n = tmp.size();
@@ -942,7 +1062,7 @@ struct ChainScratch {
   size_t c_anc = 0, c_score = 0, c_ptr = 0, c_rootkey = 0, c_depth = 0;
   size_t c_chunk_first = 0, c_chunk_pair = 0, c_chunk_qctg = 0, c_chunk_lo = 0, c_chunk_hi = 0, c_acc_total = 0, c_acc_rq0 = 0,
          c_acc_rq1 = 0, c_acc_tbcq = 0, c_acc_nint = 0, c_chunk_head = 0, c_chunk_est = 0, c_chunk_w = 0, c_chunk_valid = 0, c_chunk_nseeds = 0;
-  size_t c_iv = 0, c_iv_order = 0, c_iv_kept = 0, c_iv_next = 0, c_acc_list = 0, c_est_sorted = 0, c_w_sorted = 0;
+  size_t c_iv = 0, c_iv_keys = 0, c_iv_order = 0, c_iv_kept = 0, c_iv_next = 0, c_acc_list = 0, c_est_sorted = 0, c_w_sorted = 0;
   PairDesc* d_pairs = nullptr; size_t c_pairs = 0;
   sk_ani_result* d_out = nullptr; size_t c_out = 0;
   GenomeMeta *d_m0 = nullptr, *d_m1 = nullptr;
@@ -952,7 +1072,7 @@ struct ChainScratch {
                     ws.pairC, ws.pairAbase, ws.pairCbase, ws.pairIbase, ws.pair_nint, ws.pair_sumlen, ws.pair_nchains, ws.pair_tqb_ns, ws.anc,
                     ws.score, ws.ptr, ws.rootkey, ws.depth, ws.chunk_first, ws.chunk_pair, ws.chunk_qctg, ws.chunk_lo, ws.chunk_hi,
                     ws.acc_total, ws.acc_rq0, ws.acc_rq1, ws.acc_tbcq, ws.acc_nint, ws.chunk_head, ws.chunk_est, ws.chunk_w, ws.chunk_valid,
-                    ws.chunk_nseeds, ws.iv, ws.iv_order, ws.iv_kept, ws.iv_next, ws.acc_list, ws.est_sorted, ws.w_sorted, d_pairs, d_out, d_m0, d_m1};
+                    ws.chunk_nseeds, ws.iv, ws.iv_keys, ws.iv_order, ws.iv_kept, ws.iv_next, ws.acc_list, ws.est_sorted, ws.w_sorted, d_pairs, d_out, d_m0, d_m1};
     for (void* p : ptrs) if (p) cudaFree(p);
   }
 };
@@ -1005,7 +1125,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   ENS(chunk_lo, c_chunk_lo, NCH); ENS(chunk_hi, c_chunk_hi, NCH); ENS(acc_total, c_acc_total, NCH); ENS(acc_rq0, c_acc_rq0, NCH);
   ENS(acc_rq1, c_acc_rq1, NCH); ENS(acc_tbcq, c_acc_tbcq, NCH); ENS(acc_nint, c_acc_nint, NCH); ENS(chunk_head, c_chunk_head, NCH);
   ENS(chunk_est, c_chunk_est, NCH); ENS(chunk_w, c_chunk_w, NCH); ENS(chunk_valid, c_chunk_valid, NCH); ENS(chunk_nseeds, c_chunk_nseeds, NCH);
-  ENS(iv, c_iv, NI); ENS(iv_order, c_iv_order, 4 * NI + 8); ENS(iv_kept, c_iv_kept, NI); ENS(iv_next, c_iv_next, NI); ENS(acc_list, c_acc_list, NI);
+  ENS(iv, c_iv, NI); ENS(iv_keys, c_iv_keys, 2 * NI + 8); ENS(iv_order, c_iv_order, 4 * NI + 8); ENS(iv_kept, c_iv_kept, NI); ENS(iv_next, c_iv_next, NI); ENS(acc_list, c_acc_list, NI);
   ENS(est_sorted, c_est_sorted, 4 * NCH + 8); ENS(w_sorted, c_w_sorted, 4 * NCH + 8);
 #undef ENS
   if (TC > 0) {
@@ -1153,7 +1273,7 @@ static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_se
     else { d.qset = 1; d.qg = q; d.rset = 0; d.rg = r; }
   }
   // batches bounded by the per-record workspace
-  const uint64_t REC_CAP = 64ull << 20;
+  const uint64_t REC_CAP = 256ull << 20;
   size_t b0 = 0;
   while (b0 < n_pairs) {
     size_t b1 = b0;

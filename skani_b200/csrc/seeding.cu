@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "sk_core.cuh"
@@ -104,7 +105,7 @@ hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM,
   uint64_t lo = ul ? P[u - 1] : 0ull;
   uint32_t nhi = NM[u];
   uint32_t nlo = ul ? NM[u - 1] : 0u;
-  uint32_t pass = unit_pass_mask(lo, hi, nlo, nhi, n, ul, seed_mask, threshold);
+  uint32_t pass = unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold);
   PM[u] = pass;
   cnt[u] = __popc(pass);
 }
@@ -163,7 +164,7 @@ __global__ void marker_scatter_kernel(const uint64_t* __restrict__ mkv, const ui
 __global__ void iota_local_kernel(const uint64_t* __restrict__ seg_off, uint32_t* __restrict__ vals) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
-  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) vals[i] = (uint32_t)(i - b);
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) vals[i] = (uint32_t)(i - b);
 }
 
 // after the per-genome sort by k-mer: gather the k-mer view and flag group heads
@@ -173,7 +174,7 @@ __global__ void kview_gather_kernel(const uint64_t* __restrict__ seg_off, const 
                                     uint32_t* __restrict__ kv_cc, uint32_t* __restrict__ head) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
-  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
     uint32_t r = perm[i];
     kv_pos[i] = pv_pos[b + r];
     kv_cc[i] = pv_cc[b + r];
@@ -188,14 +189,14 @@ __global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint32
                               uint32_t n_genomes, uint32_t* __restrict__ ukmer, uint32_t* __restrict__ ustart) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
-  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
     if (head[i]) {
       uint32_t gid = hscan[i];
       ukmer[gid] = skmer[i];
       ustart[gid + g] = (uint32_t)(i - b);
     }
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && blockIdx.y == 0) {
     // sentinel of genome g sits right after its last group: global group index of next genome's first group
     uint64_t total = seg_off[n_genomes];
     uint32_t next_gid = (e < total) ? hscan[e] : total_groups;  // head[e] is always 1, so hscan[e] = #groups before e
@@ -208,7 +209,7 @@ __global__ void mult_kernel(const uint64_t* __restrict__ seg_off, const uint32_t
                             const uint32_t* __restrict__ ustart, uint16_t* __restrict__ pv_mult) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
-  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
     uint32_t gid = hscan[i] + head[i] - 1;
     uint32_t cntv = ustart[gid + g + 1] - ustart[gid + g];
     pv_mult[b + perm[i]] = (uint16_t)min(cntv, 65535u);
@@ -236,7 +237,7 @@ __global__ void marker_head_kernel(const uint64_t* __restrict__ seg_off, const u
                                    uint32_t* __restrict__ head) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
-  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) head[i] = (i == b || mk[i] != mk[i - 1]) ? 1u : 0u;
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) head[i] = (i == b || mk[i] != mk[i - 1]) ? 1u : 0u;
 }
 __global__ void marker_compact_kernel(const uint64_t* __restrict__ mk, const uint32_t* __restrict__ head,
                                       const uint32_t* __restrict__ hscan, uint32_t n, uint64_t* __restrict__ out) {
@@ -266,13 +267,61 @@ static int scan_exclusive(sk_ctx* ctx, const T* in, T* out, size_t n) {
 
 void free_set_device(sk_sketch_set* s) {
   void* ptrs[] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart,
-                  s->markers, s->ctg_rec_off, s->d_ctg_len, s->ubucket};
+                  s->markers, s->ctg_rec_off, s->d_ctg_len, s->ubucket, s->htab};
   cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
   for (void* p : ptrs) if (p) cudaFreeAsync(p, st);
   s->pv_kmer = s->pv_pos = s->pv_cc = s->kv_pos = s->kv_cc = s->ukmer = s->ustart = s->ctg_rec_off = s->d_ctg_len = nullptr;
   s->pv_mult = nullptr;
   s->markers = nullptr;
   s->ubucket = nullptr;
+  s->htab = nullptr;
+}
+
+// per-genome k-mer hash table for the probe kernel: one 8-byte entry holds key, group start and (saturated) group size,
+// so a probe costs ~1.2 divergent sector reads instead of a search + two ustart reads
+__global__ void hash_build_kernel(const uint64_t* __restrict__ uk_off, const uint64_t* __restrict__ ht_off,
+                                  const uint32_t* __restrict__ ukmer, const uint32_t* __restrict__ ustart,
+                                  unsigned long long* __restrict__ htab) {
+  const uint32_t g = blockIdx.x;
+  const uint64_t cap = ht_off[g + 1] - ht_off[g];
+  if (cap == 0) return;
+  const uint32_t mask = (uint32_t)cap - 1;
+  const uint32_t shift = 32 - (uint32_t)__ffsll((long long)cap) + 1;   // 32 - log2(cap)
+  const uint32_t* uk = ukmer + uk_off[g];
+  const uint32_t* us = ustart + uk_off[g] + g;
+  unsigned long long* tab = htab + ht_off[g];
+  const uint32_t n = (uint32_t)(uk_off[g + 1] - uk_off[g]);
+  for (uint32_t u = blockIdx.y * blockDim.x + threadIdx.x; u < n; u += blockDim.x * gridDim.y) {
+    const uint32_t key = uk[u], start = us[u], cntv = us[u + 1] - start;
+    const unsigned long long e = ((unsigned long long)key << 32) | ((unsigned long long)start << 12) | (cntv < 4095u ? cntv : 4095u);
+    uint32_t hpos = (shift >= 32) ? 0u : ((key * 0x9E3779B1u) >> shift);
+    while (atomicCAS(&tab[hpos], 0ull, e) != 0ull) hpos = (hpos + 1) & mask;
+  }
+}
+
+int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t G = set->G;
+  if (set->htab) { cudaFreeAsync(set->htab, st); set->htab = nullptr; }
+  set->ht_off.assign(G + 1, 0);
+  const bool force_bucket = getenv("SK_FORCE_BUCKET_PROBE") != nullptr;  // test hook: exercise the large-genome fallback
+  for (uint32_t g = 0; g < G && !force_bucket; g++) {
+    const uint64_t nuk = set->uk_off[g + 1] - set->uk_off[g], nrec = set->seed_off[g + 1] - set->seed_off[g];
+    uint64_t cap = 0;
+    if (nuk > 0 && nrec < (1ull << 20)) { cap = 16; while (cap < 2 * nuk) cap <<= 1; }   // start must fit 20 bits
+    set->ht_off[g + 1] = set->ht_off[g] + cap;
+  }
+  const uint64_t total = set->ht_off[G];
+  SK_CUDA(cudaMallocAsync((void**)&set->htab, std::max<uint64_t>(total, 1) * 8, st));
+  if (total == 0) return SK_OK;
+  SK_CUDA(cudaMemsetAsync(set->htab, 0, total * 8, st));
+  DTmp<uint64_t> d_uk, d_ht;
+  SK_CUDA(d_uk.alloc(G + 1, st)); SK_CUDA(d_ht.alloc(G + 1, st));
+  SK_CUDA(cudaMemcpyAsync(d_uk.p, set->uk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  SK_CUDA(cudaMemcpyAsync(d_ht.p, set->ht_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  hash_build_kernel<<<dim3(G, 8), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab); count_launch(ctx);
+  SK_CUDA(cudaStreamSynchronize(st));
+  return SK_OK;
 }
 
 // Given the position view (pv_kmer/pv_pos/pv_cc filled, set->seed_off known) and the raw (unsorted, possibly
@@ -293,7 +342,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     DTmp<uint32_t> vals, skmer, perm, head, hscan;
     SK_CUDA(vals.alloc(S, st)); SK_CUDA(skmer.alloc(S, st)); SK_CUDA(perm.alloc(S, st));
     SK_CUDA(head.alloc(S + 1, st)); SK_CUDA(hscan.alloc(S + 1, st));
-    iota_local_kernel<<<G, 256, 0, st>>>(d_seed_off.p, vals.p); count_launch(ctx);
+    iota_local_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, vals.p); count_launch(ctx);
     size_t tb = 0;
     int end_bit = std::min(32, (int)(2 * set->sp.k));
     SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tb, set->pv_kmer, skmer.p, vals.p, perm.p, (int)S, (int)G,
@@ -302,7 +351,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     SK_CUDA(tmp.alloc(tb, st));
     SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp.p, tb, set->pv_kmer, skmer.p, vals.p, perm.p, (int)S, (int)G,
                                                      d_seed_off.p, d_seed_off.p + 1, 0, end_bit, st));
-    kview_gather_kernel<<<G, 256, 0, st>>>(d_seed_off.p, skmer.p, perm.p, set->pv_pos, set->pv_cc, set->kv_pos,
+    kview_gather_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, perm.p, set->pv_pos, set->pv_cc, set->kv_pos,
                                            set->kv_cc, head.p); count_launch(ctx);
     SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, S));
     // total groups and per-genome group offsets
@@ -318,8 +367,8 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     set->U = U;
     SK_CUDA(cudaMallocAsync((void**)&set->ukmer, std::max<size_t>(U, 1) * 4, ctx->stream));
     SK_CUDA(cudaMallocAsync((void**)&set->ustart, (size_t)(U + G) * 4, ctx->stream));
-    groups_kernel<<<G, 256, 0, st>>>(d_seed_off.p, skmer.p, head.p, hscan.p, U, G, set->ukmer, set->ustart); count_launch(ctx);
-    mult_kernel<<<G, 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult); count_launch(ctx);
+    groups_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, head.p, hscan.p, U, G, set->ukmer, set->ustart); count_launch(ctx);
+    mult_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult); count_launch(ctx);
     SK_CUDA(cudaStreamSynchronize(st));
   } else {
     set->U = 0;
@@ -355,7 +404,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
                                                     d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
     DTmp<uint32_t> head, hscan;
     SK_CUDA(head.alloc(MR, st)); SK_CUDA(hscan.alloc(MR, st));
-    marker_head_kernel<<<G, 256, 0, st>>>(d_rawmk_off.p, sorted.p, head.p); count_launch(ctx);
+    marker_head_kernel<<<dim3(G, 8), 256, 0, st>>>(d_rawmk_off.p, sorted.p, head.p); count_launch(ctx);
     SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, MR));
     uint32_t lh = 0, ls = 0;
     SK_CUDA(cudaMemcpyAsync(&lh, head.p + (MR - 1), 4, cudaMemcpyDeviceToHost, st));

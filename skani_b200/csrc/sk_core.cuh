@@ -155,3 +155,54 @@ SK_HD uint32_t unit_pass_mask(uint64_t lo, uint64_t hi, uint32_t nm_lo, uint32_t
 }
 
 }  // namespace sk
+
+namespace sk {
+
+// ---- tuned variant of unit_pass_mask used by hashpass_kernel: 32-bit seed extraction, multiply-form hash ----------
+SK_HD uint32_t funnel_r32(uint32_t lo, uint32_t hi, uint32_t sh) {  // low 32 bits of (hi:lo) >> sh, 0 <= sh <= 31
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+// mm_hash64 with its shift-add steps written as multiplications (x + (x << s) == x * (2^s + 1) mod 2^64): on sm_100a
+// the 64-bit multiplies issue on the FMA pipe (IMAD) and relieve the ALU pipe (LOP3/SHF/IADD3) that bounds the kernel.
+SK_HD uint64_t mm_hash64_mul(uint64_t key) {
+  key = ~(key * 0x200001ull);
+  key = key ^ (key >> 24);
+  key = key * 265ull;
+  key = key ^ (key >> 14);
+  key = key * 21ull;
+  key = key ^ (key >> 28);
+  key = key * 0x80000001ull;
+  return key;
+}
+
+SK_HD uint32_t unit_pass_mask_fast(uint64_t lo, uint64_t hi, uint32_t nm_lo, uint32_t nm_hi, uint32_t n, uint32_t ul,
+                                   uint32_t seed_mask32, uint64_t threshold) {
+  const uint32_t valid = unit_valid_mask(n, ul);
+  if (valid == 0) return 0;
+  const uint64_t clo = ~lo, chi = ~hi;
+  const uint64_t tlo = pair_reverse64(hi), thi = pair_reverse64(lo);
+  const uint32_t c[4] = {(uint32_t)clo, (uint32_t)(clo >> 32), (uint32_t)chi, (uint32_t)(chi >> 32)};
+  const uint32_t t[4] = {(uint32_t)tlo, (uint32_t)(tlo >> 32), (uint32_t)thi, (uint32_t)(thi >> 32)};
+  uint32_t pass = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (uint32_t j = 0; j < 32; j++) {
+    const uint32_t orv = 24 + 2 * j;   // bit offset of the reverse seed in the complemented stream (<= 86; + 32 bits <= 118)
+    const uint32_t ofw = 62 - 2 * j;   // bit offset of the forward seed in the pair-reversed stream (<= 62)
+    const uint32_t rs = funnel_r32(c[orv >> 5], c[(orv >> 5) + 1], orv & 31) & seed_mask32;
+    const uint32_t fs = funnel_r32(t[ofw >> 5], t[(ofw >> 5) + 1], ofw & 31) & seed_mask32;
+    const uint32_t seed = fs < rs ? fs : rs;
+    if (mm_hash64_mul((uint64_t)seed) < threshold) pass |= 1u << j;
+  }
+  pass &= valid;
+  if ((nm_lo | nm_hi) != 0 && pass != 0) pass &= ~unit_n_suppress_mask(n, ul, nm_lo, nm_hi, pass);
+  return pass;
+}
+
+}  // namespace sk
+

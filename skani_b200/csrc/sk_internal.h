@@ -69,6 +69,8 @@ struct sk_sketch_set {
   uint64_t* markers = nullptr;                                        // [M] sorted distinct per genome
   uint32_t* ctg_rec_off = nullptr;                                    // [C+G] genome g, contig j -> ctg_rec_off[ctg_off[g] + g + j] = local first pv record; +1 sentinel
   uint32_t* d_ctg_len = nullptr;                                      // [C]
+  unsigned long long* htab = nullptr;                                 // [ht_off[G]] per-genome open-addressing table: kmer<<32 | start<<12 | min(count,4095); 0 = empty
+  std::vector<uint64_t> ht_off;                                       // [G+1] table offsets (capacity = power of two, >= 2 * distinct k-mers); capacity 0 => use ubucket search
   uint32_t* ubucket = nullptr;                                        // [G * (UBUCKETS + 1)] first ukmer index of each top-bits bucket, per genome
 };
 
@@ -121,6 +123,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out);
 int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const std::vector<uint64_t>& raw_mk_off);
 void free_set_device(sk_sketch_set* s);
+int build_hash(sk_ctx* ctx, sk_sketch_set* set);  // (re)builds set->htab from ukmer/ustart; call on every finished set
 // screen.cu / chain.cu
 uint64_t count_launch(sk_ctx* ctx, uint64_t n = 1);
 }  // namespace sk

@@ -30,6 +30,7 @@ static void emu_seed(const std::vector<uint8_t>& s, uint32_t c, uint32_t k, uint
     uint64_t lo = ul ? P[ul - 1] : 0, hi = P[ul];
     uint32_t nlo = ul ? NM[ul - 1] : 0, nhi = NM[ul];
     uint32_t pass = sk::unit_pass_mask(lo, hi, nlo, nhi, n, ul, seed_mask, thr);
+    if (pass != sk::unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, thr)) { fprintf(stderr, "fast/slow pass mask mismatch\n"); exit(2); }
     sk::WindowCtx w = sk::make_window_ctx(lo, hi);
     for (uint32_t j = 0; j < 32; j++) {
       if (!((pass >> j) & 1)) continue;

@@ -177,3 +177,15 @@ def test_small_genomes_viruses(ctx):
             assert_result_close(r, o)
             gd = sk.chain_pair_debug(ctx, gs, gs, r.ref_id, r.query_id, mp)
             assert_debug_equal(gd, O.chain_debug(osk[r.ref_id], osk[r.query_id], O.cmd(learned_ani=False, rescue_small=rescue)))
+
+
+def test_bucket_probe_fallback_path(ctx, monkeypatch):
+    """Genomes with >= 2^20 seed records use the bucket-index search instead of the per-genome hash table;
+    SK_FORCE_BUCKET_PROBE forces that path so it stays covered."""
+    import skani_b200 as sk
+    monkeypatch.setenv("SK_FORCE_BUCKET_PROBE", "1")
+    genomes = synth_genomes(4, 500_000, 4)
+    kw = dict(c=125, k=15, marker_c=1000)
+    gs, osk = make_sets(ctx, genomes, kw)
+    for (r, q) in [(0, 1), (2, 3), (1, 2)]:
+        assert_debug_equal(sk.chain_pair_debug(ctx, gs, gs, r, q, sk.map_params()), O.chain_debug(osk[r], osk[q], O.cmd()))

@@ -189,3 +189,53 @@ def test_bucket_probe_fallback_path(ctx, monkeypatch):
     gs, osk = make_sets(ctx, genomes, kw)
     for (r, q) in [(0, 1), (2, 3), (1, 2)]:
         assert_debug_equal(sk.chain_pair_debug(ctx, gs, gs, r, q, sk.map_params()), O.chain_debug(osk[r], osk[q], O.cmd()))
+
+
+def test_large_multicontig_pair_global_fallbacks(ctx):
+    """> 1024 chunks and > 1024 chain intervals per pair: the shared-memory sorts of select_kernel / final_kernel fall
+    back to their global-memory paths (the MAG-sized pairs of the reference's fast_eukaryote_test)."""
+    import skani_b200 as sk
+    genomes = synth_genomes(3, 24_000_000, 3)          # member 2 is cut into 50 contigs, member 1 carries an inversion
+    kw = dict(c=125, k=15, marker_c=1000)
+    gs, osk = make_sets(ctx, genomes, kw)
+    for (r, q) in [(0, 2), (1, 2), (0, 1)]:
+        gd = sk.chain_pair_debug(ctx, gs, gs, r, q, sk.map_params())
+        od = O.chain_debug(osk[r], osk[q], O.cmd())
+        assert len(od["chunk_first"]) - 1 > 1024 and len(od["intervals"]) > 1024
+        assert_debug_equal(gd, od)
+
+
+@pytest.mark.parametrize("kw", [dict(robust=True), dict(median=True, learned_ani=False), dict(min_af=0.999), dict(both_min_af=0.999),
+                                dict(min_af=-1.0), dict(learned_ani=False)])
+def test_map_param_variants(ctx, kw):
+    import skani_b200 as sk
+    genomes = synth_genomes(6, 400_000, 3)
+    gs, osk = make_sets(ctx, genomes, dict(c=125, k=15, marker_c=1000))
+    mp, ocp = sk.map_params(**kw), O.cmd(**kw)
+    pairs = [(0, 1), (0, 2), (1, 2), (3, 4), (0, 3), (2, 5)]      # incl. unrelated pairs (no anchors -> NaN)
+    res = sk.chain_pairs(ctx, gs, gs, np.array([(r << 32) | q for r, q in pairs], np.uint64), mp)
+    for (r, q), g in zip(pairs, res):
+        assert (g.ref_id, g.query_id) == (r, q)
+        assert_result_close(g, O.chain(osk[r], osk[q], ocp))
+
+
+def test_degenerate_sets(ctx):
+    import skani_b200 as sk
+    # no pairs
+    genomes = synth_genomes(2, 300_000, 1)               # two unrelated genomes: screen passes nothing
+    gs, osk = make_sets(ctx, genomes, dict(c=125, k=15, marker_c=1000))
+    assert len(sk.screen_triangle(ctx, gs)) == 0
+    assert sk.chain_pairs(ctx, gs, gs, np.zeros(0, np.uint64)) == []
+    r = sk.chain_pairs(ctx, gs, gs, np.array([1], np.uint64))[0]           # unrelated pair chained anyway: no anchors
+    assert np.isnan(r.ani) and np.isnan(O.chain(osk[0], osk[1]).ani)
+    # a single genome: triangle has no rows
+    one = sk.sketch_sequences(ctx, [genomes[0]])
+    assert len(sk.screen_triangle(ctx, one)) == 0
+    # genome made of N only: sketch exists but is empty (reference: all_ns.fa -> 0 rows)
+    ns = sk.sketch_sequences(ctx, [[np.full(2000, ord("N"), np.uint8)], genomes[0]])
+    assert ns.info(0)["n_records"] == 0 and ns.info(0)["n_markers"] == 0
+    assert len(sk.screen_triangle(ctx, ns, sk.map_params(rescue_small=False))) == 0
+    pr = sk.screen_triangle(ctx, ns)                                        # rescue_small: < 20 markers passes everything
+    assert pr.tolist() == [1]
+    rr = sk.chain_pairs(ctx, ns, ns, pr)[0]
+    assert np.isnan(rr.ani)

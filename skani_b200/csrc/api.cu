@@ -10,7 +10,9 @@
 using namespace sk;
 
 namespace {
-constexpr size_t SUBBATCH_BYTES = 512ull << 20;  // bases staged per seeding sub-batch
+constexpr size_t SUBBATCH_MAX = 2048ull << 20;  // bases per seeding sub-batch: bounds the per-base temporaries ...
+constexpr size_t SUBBATCH_MIN = 256ull << 20;   // ... while keeping >= ~8 sub-batches so H2D copies overlap the kernels
+inline size_t subbatch_bytes(uint64_t total) { return std::min<size_t>(SUBBATCH_MAX, std::max<size_t>(SUBBATCH_MIN, total / 8)); }
 
 int check_sketch_params(sk_ctx* ctx, const sk_sketch_params* sp) {
   if (!sp || sp->c == 0 || sp->marker_c == 0 || sp->k == 0) { ctx->err = "bad sketch params"; return SK_ERR_PARAM; }
@@ -78,7 +80,7 @@ int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_
   }
   CAT(pv_kmer, uint32_t, nS) CAT(pv_pos, uint32_t, nS) CAT(pv_cc, uint32_t, nS) CAT(pv_mult, uint16_t, nS)
   CAT(kv_pos, uint32_t, nS) CAT(kv_cc, uint32_t, nS) CAT(ukmer, uint32_t, nU) CAT(ustart, uint32_t, nUG)
-  CAT(markers, uint64_t, nM) CAT(ctg_rec_off, uint32_t, nCG) CAT(d_ctg_len, uint32_t, nC) CAT(ubucket, uint32_t, nB)
+  CAT(markers, uint64_t, nM) CAT(ctg_rec_off, uint32_t, nCG) CAT(d_ctg_len, uint32_t, nC)
 #undef CAT
   SK_CUDA(cudaStreamSynchronize(ctx->stream));
   guard.s = nullptr;
@@ -240,22 +242,22 @@ int sk_sketch_set_append(sk_sketch_set* dst, const sk_sketch_set* src) {
 
 namespace {
 struct BlobLayout {
-  size_t off[12];
-  size_t bytes[12];
+  size_t off[11];
+  size_t bytes[11];
   size_t total;
 };
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 BlobLayout blob_layout(size_t G, size_t S, size_t U, size_t M, size_t Cn) {
   BlobLayout b;
-  const size_t n[12] = {S * 4, S * 4, S * 4, S * 2, S * 4, S * 4, U * 4, (U + G) * 4, M * 8, (Cn + G) * 4, Cn * 4, G * (UBUCKETS + 1) * 4};
+  const size_t n[11] = {S * 4, S * 4, S * 4, S * 2, S * 4, S * 4, U * 4, (U + G) * 4, M * 8, (Cn + G) * 4, Cn * 4};
   size_t o = 0;
-  for (int i = 0; i < 12; i++) { b.off[i] = o; b.bytes[i] = n[i]; o += al256(n[i]); }
+  for (int i = 0; i < 11; i++) { b.off[i] = o; b.bytes[i] = n[i]; o += al256(n[i]); }
   b.total = o ? o : 256;
   return b;
 }
 inline const void* set_array(const sk_sketch_set* s, int i) {
-  const void* p[12] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart, s->markers, s->ctg_rec_off,
-                       s->d_ctg_len, s->ubucket};
+  const void* p[11] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart, s->markers, s->ctg_rec_off,
+                       s->d_ctg_len};
   return p[i];
 }
 }  // namespace
@@ -272,7 +274,7 @@ int sk_sketch_set_pack(const sk_sketch_set* s, void* d_blob, uint64_t* meta) {
   sk_ctx* ctx = s->ctx;
   SK_CUDA(cudaSetDevice(ctx->device));
   BlobLayout b = blob_layout(s->G, s->S, s->U, s->M, s->C);
-  for (int i = 0; i < 12; i++)
+  for (int i = 0; i < 11; i++)
     if (b.bytes[i]) SK_CUDA(cudaMemcpyAsync((uint8_t*)d_blob + b.off[i], set_array(s, i), b.bytes[i], cudaMemcpyDeviceToDevice, ctx->stream));
   uint64_t* m = meta;
   *m++ = s->G; *m++ = s->S; *m++ = s->U; *m++ = s->M; *m++ = s->C; *m++ = s->sp.c; *m++ = s->sp.k; *m++ = s->sp.marker_c;
@@ -312,7 +314,7 @@ int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blo
     v.pv_kmer = (uint32_t*)(base + b.off[0]); v.pv_pos = (uint32_t*)(base + b.off[1]); v.pv_cc = (uint32_t*)(base + b.off[2]);
     v.pv_mult = (uint16_t*)(base + b.off[3]); v.kv_pos = (uint32_t*)(base + b.off[4]); v.kv_cc = (uint32_t*)(base + b.off[5]);
     v.ukmer = (uint32_t*)(base + b.off[6]); v.ustart = (uint32_t*)(base + b.off[7]); v.markers = (uint64_t*)(base + b.off[8]);
-    v.ctg_rec_off = (uint32_t*)(base + b.off[9]); v.d_ctg_len = (uint32_t*)(base + b.off[10]); v.ubucket = (uint32_t*)(base + b.off[11]);
+    v.ctg_rec_off = (uint32_t*)(base + b.off[9]); v.d_ctg_len = (uint32_t*)(base + b.off[10]);
     vp.push_back(&v);
   }
   SK_TRY(concat_sets(ctx, vp, out));
@@ -330,6 +332,7 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
   struct Guard { std::vector<sk_sketch_set*>& v; ~Guard() { for (auto* s : v) sk_sketch_set_free(s); } } guard{parts};
   uint32_t c0 = 0;
   std::vector<uint32_t> gl;
+  const size_t SUBBATCH = subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
   while (c0 < n_contigs) {
     uint32_t g0 = genome_of_contig[c0];
     uint32_t c1 = c0;
@@ -340,7 +343,7 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
       uint32_t c2 = c1;
       while (c2 < n_contigs && genome_of_contig[c2] == g) c2++;
       uint64_t gb = contig_off[c2] - contig_off[c1];
-      if (c1 > c0 && bytes + gb > SUBBATCH_BYTES) break;
+      if (c1 > c0 && bytes + gb > SUBBATCH) break;
       bytes += gb;
       c1 = c2;
     }
@@ -396,6 +399,7 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
   std::vector<Part> plan;
   uint32_t c0 = 0;
   uint64_t max_bytes = 0;
+  const size_t SUBBATCH = subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
   while (c0 < n_contigs) {
     uint32_t c1 = c0;
     uint64_t bytes = 0;
@@ -403,7 +407,7 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
       uint32_t g = genome_of_contig[c1], c2 = c1;
       while (c2 < n_contigs && genome_of_contig[c2] == g) c2++;
       uint64_t gb = contig_off[c2] - contig_off[c1];
-      if (c1 > c0 && bytes + gb > SUBBATCH_BYTES) break;
+      if (c1 > c0 && bytes + gb > SUBBATCH) break;
       bytes += gb;
       c1 = c2;
     }

@@ -59,6 +59,7 @@ struct PairDesc {
   uint32_t ref_idx, query_idx;
   uint32_t switched, valid;
   uint64_t rec_off;             // offset of this pair's slice in the per-record / per-hit workspaces
+  uint64_t ctab_off;            // offset of this pair's slice in the per-query-contig tables
 };
 struct ChainParams {
   uint32_t c, k, band, ushift;
@@ -75,6 +76,8 @@ struct Workspace {
   uint32_t *hit_rec, *hit_aoff;
   uint32_t *hit_clfirst, *hit_need, *hit_p0, *hit_cid;  // hit_cid: pair-local chunk id of the first anchor; bit31 of hit_clfirst unused
   // per pair
+  uint32_t *ctab_p0, *ctab_a0;           // per query contig: position / anchor offset of its first hit record
+  uint32_t* pair_slow;                   // 1 = the pair needs the general (prefix-min) chunk assignment
   uint32_t *pairA, *pairH, *pairC;       // anchors, hit records, chunks
   uint64_t *pairAbase, *pairCbase, *pairIbase;  // exclusive prefix sums over the batch (anchors, chunks, interval capacity)
   uint32_t* pair_nint;
@@ -248,6 +251,97 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K2a: chunk assignment, fast path.  When the chunk index never has to "catch up" (no two consecutive hit records of a
+// contig whose `need` differs by >= 2, i.e. no anchor-free stretch longer than a fragment) every anchor's chunk is simply
+// need = ceil((pos - P0)/F) - 1 (SURVEY App. A.6 with the prefix minimum attained at the anchor itself), so one u32
+// block scan per tile suffices.  Pairs that violate the condition are flagged and redone by the general kernel below.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CT)
+chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const GenomeMeta* __restrict__ m0,
+                  const GenomeMeta* __restrict__ m1, Workspace ws) {
+  using ScanU = cub::BlockScan<uint32_t, CT>;
+  __shared__ typename ScanU::TempStorage tmp;
+  __shared__ uint32_t sh_ctg[CT], sh_need[CT];
+  __shared__ uint32_t s_slow;
+  const PairDesc pd = pairs[blockIdx.x];
+  const uint32_t H = ws.pairH[blockIdx.x];
+  if (threadIdx.x == 0) { s_slow = 0; ws.pair_slow[blockIdx.x] = 0; }
+  if (!pd.valid || H == 0) {
+    if (threadIdx.x == 0) ws.pairC[blockIdx.x] = 0;
+    return;
+  }
+  const SetView& Q = pd.qset ? s1 : s0;
+  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
+  uint32_t* __restrict__ tp0 = ws.ctab_p0 + pd.ctab_off;
+  uint32_t* __restrict__ ta0 = ws.ctab_a0 + pd.ctab_off;
+  // phase A: the first hit record of every query contig publishes (P0, A0)
+  for (uint32_t h = threadIdx.x; h < H; h += CT) {
+    const uint32_t t = ws.hit_rec[pd.rec_off + h];
+    const uint32_t ctg = Q.pv_cc[qm.seed_off + t] >> 1;
+    bool head = (h == 0);
+    if (!head) { const uint32_t tp = ws.hit_rec[pd.rec_off + h - 1]; head = (Q.pv_cc[qm.seed_off + tp] >> 1) != ctg; }
+    if (head) { tp0[ctg] = Q.pv_pos[qm.seed_off + t]; ta0[ctg] = ws.hit_aoff[pd.rec_off + h]; }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // phase B: need per hit, chunk starts, chunk ids
+  uint32_t carry_ctg = 0xFFFFFFFFu, carry_need = 0, carryC = 0, slow = 0;
+  for (uint32_t h0 = 0; h0 < H; h0 += CT * ITEMS) {
+    uint32_t ctg[ITEMS], need[ITEMS], p0[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const uint32_t h = h0 + threadIdx.x * ITEMS + it;
+      ctg[it] = 0xFFFFFFFFu; need[it] = 0; p0[it] = 0;
+      if (h < H) {
+        const uint32_t t = ws.hit_rec[pd.rec_off + h];
+        ctg[it] = Q.pv_cc[qm.seed_off + t] >> 1;
+        p0[it] = tp0[ctg[it]];
+        need[it] = chunk_need(Q.pv_pos[qm.seed_off + t], p0[it]);
+      }
+    }
+    __syncthreads();                       // sh_* of the previous tile fully consumed
+    sh_ctg[threadIdx.x] = ctg[ITEMS - 1];
+    sh_need[threadIdx.x] = need[ITEMS - 1];
+    __syncthreads();
+    uint32_t st[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const uint32_t h = h0 + threadIdx.x * ITEMS + it;
+      st[it] = 0;
+      if (h < H) {
+        uint32_t pc, pn;
+        if (it > 0) { pc = ctg[it - 1]; pn = need[it - 1]; }
+        else if (threadIdx.x > 0) { pc = sh_ctg[threadIdx.x - 1]; pn = sh_need[threadIdx.x - 1]; }
+        else { pc = carry_ctg; pn = carry_need; }
+        const bool same = (h != 0) && (pc == ctg[it]);
+        if (same && need[it] > pn + 1) slow = 1;           // the chunk index would lag behind `need`: general path
+        st[it] = (!same || need[it] != pn) ? 1u : 0u;
+      }
+    }
+    const uint32_t last_h = min(H, h0 + CT * ITEMS) - 1 - h0;   // carry = last valid hit of the tile
+    uint32_t agg, ex[ITEMS];
+    ScanU(tmp).ExclusiveSum(st, ex, agg);
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const uint32_t h = h0 + threadIdx.x * ITEMS + it;
+      if (h < H) {
+        ws.hit_clfirst[pd.rec_off + h] = need[it];
+        ws.hit_need[pd.rec_off + h] = need[it];
+        ws.hit_p0[pd.rec_off + h] = p0[it];
+        ws.hit_cid[pd.rec_off + h] = carryC + ex[it] + st[it] - 1;
+      }
+      if (h0 + threadIdx.x * ITEMS + it == h0 + last_h) { sh_ctg[0] = ctg[it]; sh_need[0] = need[it]; }  // written after the reads above (guarded by the next sync)
+    }
+    __syncthreads();
+    carry_ctg = sh_ctg[0]; carry_need = sh_need[0];
+    carryC += agg;
+  }
+  if (slow) atomicOr(&s_slow, 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) { ws.pairC[blockIdx.x] = carryC; ws.pair_slow[blockIdx.x] = s_slow; }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K2: chunk assignment over the compact hit list
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CT)
@@ -260,6 +354,7 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
   __shared__ uint32_t sh_ctg[CT], sh_cl[CT];
   const PairDesc pd = pairs[blockIdx.x];
   const uint32_t H = ws.pairH[blockIdx.x];
+  if (!ws.pair_slow[blockIdx.x]) return;      // the fast path already produced this pair's chunks
   if (!pd.valid || H == 0) {
     if (threadIdx.x == 0) ws.pairC[blockIdx.x] = 0;
     return;
@@ -1057,6 +1152,7 @@ struct ChainScratch {
   Workspace ws{};
   size_t cap_rec = 0, cap_pair = 0, cap_anc = 0, cap_chunk = 0, cap_iv = 0;
   size_t c_rec_rstart = 0, c_rec_nh = 0, c_hit_rec = 0, c_hit_aoff = 0, c_hit_clfirst = 0, c_hit_need = 0, c_hit_p0 = 0, c_hit_cid = 0;
+  size_t c_ctab_p0 = 0, c_ctab_a0 = 0, c_pair_slow = 0;
   size_t c_pairA = 0, c_pairH = 0, c_pairC = 0, c_pairAbase = 0, c_pairCbase = 0, c_pairIbase = 0, c_pair_nint = 0, c_pair_sumlen = 0,
          c_pair_nchains = 0, c_pair_tqb = 0;
   size_t c_anc = 0, c_score = 0, c_ptr = 0, c_rootkey = 0, c_depth = 0;
@@ -1068,7 +1164,7 @@ struct ChainScratch {
   GenomeMeta *d_m0 = nullptr, *d_m1 = nullptr;
   size_t c_m0 = 0, c_m1 = 0;
   void free_all() {
-    void* ptrs[] = {ws.rec_rstart, ws.rec_nh, ws.hit_rec, ws.hit_aoff, ws.hit_clfirst, ws.hit_need, ws.hit_p0, ws.hit_cid, ws.pairA, ws.pairH,
+    void* ptrs[] = {ws.ctab_p0, ws.ctab_a0, ws.pair_slow, ws.rec_rstart, ws.rec_nh, ws.hit_rec, ws.hit_aoff, ws.hit_clfirst, ws.hit_need, ws.hit_p0, ws.hit_cid, ws.pairA, ws.pairH,
                     ws.pairC, ws.pairAbase, ws.pairCbase, ws.pairIbase, ws.pair_nint, ws.pair_sumlen, ws.pair_nchains, ws.pair_tqb_ns, ws.anc,
                     ws.score, ws.ptr, ws.rootkey, ws.depth, ws.chunk_first, ws.chunk_pair, ws.chunk_qctg, ws.chunk_lo, ws.chunk_hi,
                     ws.acc_total, ws.acc_rq0, ws.acc_rq1, ws.acc_tbcq, ws.acc_nint, ws.chunk_head, ws.chunk_est, ws.chunk_w, ws.chunk_valid,
@@ -1082,7 +1178,7 @@ struct HostPair { uint32_t ref, query; };
 // Runs one batch (pairs [b0, b1) of `hp`); results -> host_out[b0..b1).  If dbg != nullptr (single pair) the
 // intermediate products are copied out as well.
 static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, const sk_sketch_set* qs, const std::vector<PairDesc>& descs,
-                     size_t b0, size_t b1, uint64_t total_rec, const ChainParams& prm, const SetView& v0, const SetView& v1,
+                     size_t b0, size_t b1, uint64_t total_rec, uint64_t total_ctab, const ChainParams& prm, const SetView& v0, const SetView& v1,
                      sk_ani_result* host_out, sk_chain_debug* dbg) {
   cudaStream_t st = ctx->stream;
   const uint32_t B = (uint32_t)(b1 - b0);
@@ -1093,7 +1189,8 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   ENS(hit_clfirst, c_hit_clfirst, NR); ENS(hit_need, c_hit_need, NR); ENS(hit_p0, c_hit_p0, NR); ENS(hit_cid, c_hit_cid, NR);
   ENS(pairA, c_pairA, B); ENS(pairH, c_pairH, B); ENS(pairC, c_pairC, B); ENS(pairAbase, c_pairAbase, B + 1); ENS(pairCbase, c_pairCbase, B + 1);
   ENS(pairIbase, c_pairIbase, B + 1); ENS(pair_nint, c_pair_nint, B); ENS(pair_sumlen, c_pair_sumlen, B); ENS(pair_nchains, c_pair_nchains, B);
-  ENS(pair_tqb_ns, c_pair_tqb, B);
+  ENS(pair_tqb_ns, c_pair_tqb, B); ENS(pair_slow, c_pair_slow, B);
+  ENS(ctab_p0, c_ctab_p0, std::max<uint64_t>(total_ctab, 1)); ENS(ctab_a0, c_ctab_a0, std::max<uint64_t>(total_ctab, 1));
   SK_TRY(ensure(ctx, &S.d_pairs, &S.c_pairs, B));
   SK_TRY(ensure(ctx, &S.d_out, &S.c_out, B));
   SK_CUDA(cudaMemcpyAsync(S.d_pairs, descs.data() + b0, B * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
@@ -1103,6 +1200,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   SK_CUDA(cudaMemsetAsync(ws.pair_tqb_ns, 0, B * 4, st));
 
   SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+  SK_LAUNCH(ctx, "chunk_fast_kernel", (chunk_fast_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
   SK_LAUNCH(ctx, "chunk_kernel", (chunk_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
   std::vector<uint32_t> hA(B), hC(B);
   SK_CUDA(cudaMemcpyAsync(hA.data(), ws.pairA, B * 4, cudaMemcpyDeviceToHost, st));
@@ -1264,7 +1362,7 @@ static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_se
     uint32_t r = (uint32_t)(pairs[i] >> 32), q = (uint32_t)pairs[i];
     if (r >= refs->G || q >= qs->G) { ctx->err = "pair index out of range"; return SK_ERR_PARAM; }
     PairDesc& d = descs[i];
-    d.ref_idx = r; d.query_idx = q; d.rec_off = 0;
+    d.ref_idx = r; d.query_idx = q; d.rec_off = 0; d.ctab_off = 0;
     bool empty = (m0[r].n_ctg == 0 || m1[q].n_ctg == 0);      // src/chain.rs:618-620
     d.valid = empty ? 0 : 1;
     bool sw = empty ? true : pair_switched(refs, r, qs, q, same);
@@ -1277,16 +1375,18 @@ static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_se
   size_t b0 = 0;
   while (b0 < n_pairs) {
     size_t b1 = b0;
-    uint64_t rec = 0;
+    uint64_t rec = 0, ctab = 0;
     while (b1 < n_pairs && b1 - b0 < 65535) {
       const PairDesc& d = descs[b1];
       uint64_t nr = d.valid ? (d.qset ? m1[d.qg].n_rec : m0[d.qg].n_rec) : 0;
+      uint64_t nc = d.valid ? (d.qset ? m1[d.qg].n_ctg : m0[d.qg].n_ctg) : 0;
       if (b1 > b0 && rec + nr > REC_CAP) break;
       descs[b1].rec_off = rec;
-      rec += nr;
+      descs[b1].ctab_off = ctab;
+      rec += nr; ctab += nc;
       b1++;
     }
-    SK_TRY(run_batch(ctx, S, refs, qs, descs, b0, b1, rec, prm, v0, v1, out, dbg));
+    SK_TRY(run_batch(ctx, S, refs, qs, descs, b0, b1, rec, ctab, prm, v0, v1, out, dbg));
     b0 = b1;
   }
   return SK_OK;

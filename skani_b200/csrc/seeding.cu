@@ -313,6 +313,20 @@ int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
   }
   const uint64_t total = set->ht_off[G];
   SK_CUDA(cudaMallocAsync((void**)&set->htab, std::max<uint64_t>(total, 1) * 8, st));
+  // genomes without a table (>= 2^20 records, or the test hook) use the bucket-index search: build that index only then
+  bool need_bucket = false;
+  for (uint32_t g = 0; g < G; g++) if (set->ht_off[g + 1] == set->ht_off[g] && set->uk_off[g + 1] > set->uk_off[g]) need_bucket = true;
+  if (set->ubucket) { cudaFreeAsync(set->ubucket, st); set->ubucket = nullptr; }
+  if (need_bucket) {
+    DTmp<uint64_t> d_uk2;
+    SK_CUDA(d_uk2.alloc(G + 1, st));
+    SK_CUDA(cudaMemcpyAsync(d_uk2.p, set->uk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+    SK_CUDA(cudaMallocAsync((void**)&set->ubucket, (size_t)G * (UBUCKETS + 1) * 4, st));
+    const uint32_t kbits = 2 * set->sp.k;
+    const uint32_t shift = kbits > UBUCKET_BITS ? kbits - UBUCKET_BITS : 0;
+    bucket_kernel<<<G, 256, 0, st>>>(d_uk2.p, set->ukmer, shift, set->ubucket); count_launch(ctx);
+    SK_CUDA(cudaStreamSynchronize(st));
+  }
   if (total == 0) return SK_OK;
   SK_CUDA(cudaMemsetAsync(set->htab, 0, total * 8, st));
   DTmp<uint64_t> d_uk, d_ht;
@@ -375,16 +389,6 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     SK_CUDA(cudaMallocAsync((void**)&set->ukmer, 4, ctx->stream));
     SK_CUDA(cudaMallocAsync((void**)&set->ustart, (size_t)(G + 1) * 4, ctx->stream));
     SK_CUDA(cudaMemsetAsync(set->ustart, 0, (size_t)(G + 1) * 4, st));
-  }
-  {  // bucket index for the probe kernel
-    DTmp<uint64_t> d_uk;
-    SK_CUDA(d_uk.alloc(G + 1, st));
-    SK_CUDA(cudaMemcpyAsync(d_uk.p, set->uk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
-    SK_CUDA(cudaMallocAsync((void**)&set->ubucket, (size_t)std::max<uint32_t>(G, 1) * (UBUCKETS + 1) * 4, st));
-    const uint32_t kbits = 2 * set->sp.k;
-    const uint32_t shift = kbits > UBUCKET_BITS ? kbits - UBUCKET_BITS : 0;
-    if (G) { bucket_kernel<<<G, 256, 0, st>>>(d_uk.p, set->ukmer, shift, set->ubucket); count_launch(ctx); }
-    SK_CUDA(cudaStreamSynchronize(st));
   }
   // ---- markers: per-genome sort + dedup (HashSet semantics, reference src/types.rs:269)
   const size_t MR = raw_mk_off[G];

@@ -239,3 +239,27 @@ def test_degenerate_sets(ctx):
     assert pr.tolist() == [1]
     rr = sk.chain_pairs(ctx, ns, ns, pr)[0]
     assert np.isnan(rr.ani)
+
+
+def test_chunk_catchup_after_long_gap(ctx):
+    """Anchor-free stretches longer than a fragment (20 kb) make the reference's chunk loop emit singleton 'catch-up'
+    chunks (src/chain.rs:744-793); those pairs take the general prefix-min kernel instead of the fast path."""
+    import skani_b200 as sk
+    rng = np.random.default_rng(7)
+    base = synth_genomes(1, 900_000, 1)[0][0].copy()
+    other = base.copy()
+    for a, b in [(100_000, 190_000), (400_000, 465_000), (700_000, 724_000)]:     # 90 kb, 65 kb, 24 kb of unrelated sequence
+        other[a:b] = rng.choice(np.frombuffer(b"ACGT", np.uint8), b - a)
+    mut = rng.random(len(other)) < 0.01
+    other[mut] = rng.choice(np.frombuffer(b"ACGT", np.uint8), int(mut.sum()))
+    # a multi-contig variant as well: contig boundaries inside and outside the gaps
+    cuts = [0, 150_000, 420_000, 430_000, 900_000]
+    multi = [other[cuts[i]:cuts[i + 1]] for i in range(4)]
+    kw = dict(c=125, k=15, marker_c=1000)
+    gs, osk = make_sets(ctx, [[base], [other], multi], kw)
+    for (r, q) in [(0, 1), (1, 0), (0, 2), (2, 0), (1, 2)]:
+        gd = sk.chain_pair_debug(ctx, gs, gs, r, q, sk.map_params())
+        od = O.chain_debug(osk[r], osk[q], O.cmd())
+        assert_debug_equal(gd, od)
+    sizes = np.diff(O.chain_debug(osk[0], osk[1], O.cmd())["chunk_first"])
+    assert (sizes == 1).sum() >= 2          # the oracle really produced catch-up singleton chunks

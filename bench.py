@@ -203,16 +203,16 @@ def main():
     def step(e2e):
         if world == 1:
             if e2e:
-                res, st = sk.triangle(ctx, host, off, goc, nloc, sp, mp)
+                res, st = sk.triangle(ctx, host, off, goc, nloc, sp, mp, as_array=True)
                 result_bytes[0] = len(res) * C.sizeof(_lib.AniResult)
                 return len(res), st
             gs = sk.sketch_contigs(ctx, None, off, goc, nloc, sp, device_ptr=dev_bases.data_ptr())
             pairs = sk.screen_triangle(ctx, gs, mp)
-            res = sk.chain_pairs(ctx, gs, gs, pairs, mp)
-            kept = sum(1 for r in res if r.ani > 0.1)
+            res = sk.chain_pairs(ctx, gs, gs, pairs, mp, as_array=True)
+            kept = int((res["ani"] > 0.1).sum())
             gs.free()
             return kept, None
-        kept = tri.step(host if e2e else None, dev_bases.data_ptr(), off, goc, nloc, g0, N)
+        kept = tri.step(host if e2e else None, dev_bases.data_ptr() if dev_bases is not None else 0, off, goc, nloc, g0, N)
         if e2e:
             result_bytes[0] = kept * C.sizeof(_lib.AniResult)
         return kept, None
@@ -241,19 +241,24 @@ def main():
             ms = float(t.item())
         return ms / n_steps, kept, ctx.launches - l0
 
+    # value leg first (needs the device-resident copy of the bases), then the roofline probe, then drop the 50 GB device
+    # copy before the end-to-end leg so that both legs run with comfortable HBM headroom
     for _ in range(max(args.warmup, 0)):
-        step(True)
+        step(False)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms_e2e, kept, _ = timed(True, args.steps)
     ms_val, _, launches = timed(False, args.steps)
-    clk = clocks.stop() if rank == 0 else None
-
-    # roofline of the dominant kernel (hashpass: one launch per seeding sub-batch), timed live with CUDA events
     roof = None
     if rank == 0:
         roof = measure_hashpass(ctx, stream, dev_bases, off, goc, nloc, sp, L)
+    dev_bases = None
+    torch.cuda.empty_cache()
+    for _ in range(max(args.warmup, 0)):
+        step(True)
+    ms_e2e, kept, _ = timed(True, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu, _d = cpu_baseline(args, os.cpu_count() or 1)

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <thread>
 
 #include "sk_core.cuh"
@@ -122,6 +123,7 @@ int sk_ctx_destroy(sk_ctx* ctx) {
   if (!ctx) return SK_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->child) { sk_ctx_destroy(ctx->child); ctx->child = nullptr; }
   if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
   for (int i = 0; i < 2; i++) if (ctx->dbuf[i]) cudaFree(ctx->dbuf[i]);
   for (int i = 0; i < 2; i++) {
@@ -382,9 +384,16 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
   return SK_OK;
 }
 
-int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
-                    const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out) {
-  if (!ctx || !out || !contig_off || (!genome_of_contig && n_contigs)) return SK_ERR_PARAM;
+}  // extern "C"
+
+namespace sk {
+// sk_sketch_batch with an optional per-part hand-off: when on_part is set, every finished sub-batch (a sketch set of the
+// genomes [g_begin, g_end), without hash tables) is passed to it as soon as it is ready and nothing is concatenated;
+// *out stays null.  Used by the pipelined sk_triangle so that the H2D stream never drains between waves.
+int sketch_batch_host(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+                      const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out,
+                      const std::function<int(sk_sketch_set*, uint32_t, uint32_t)>* on_part, size_t subbatch_override) {
+  if (!ctx || (!out && !on_part) || !contig_off || (!genome_of_contig && n_contigs)) return SK_ERR_PARAM;
   SK_CUDA(cudaSetDevice(ctx->device));
   SK_TRY(check_sketch_params(ctx, sp));
   // is the caller's buffer page-locked? then DMA straight from it; otherwise stage through our pinned buffers
@@ -399,7 +408,7 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
   std::vector<Part> plan;
   uint32_t c0 = 0;
   uint64_t max_bytes = 0;
-  const size_t SUBBATCH = subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
+  const size_t SUBBATCH = subbatch_override ? subbatch_override : subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
   while (c0 < n_contigs) {
     uint32_t c1 = c0;
     uint64_t bytes = 0;
@@ -471,10 +480,12 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
     for (uint32_t i = p.c0; i < p.c1; i++) gl[i - p.c0] = genome_of_contig[i] - p.g_begin;
     sk_sketch_set* part = nullptr;
     SK_TRY(sketch_batch_device(ctx, dbuf[b], p.b0, contig_off + p.c0, p.c1 - p.c0, gl.data(), p.g_end - p.g_begin, sp, &part));
-    parts.push_back(part);
     SK_CUDA(cudaEventRecord(compute_done[b], ctx->stream));
+    if (on_part) SK_TRY((*on_part)(part, p.g_begin, p.g_end));   // ownership moves to the callee
+    else parts.push_back(part);
   }
   SK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  if (on_part) return SK_OK;
   if (parts.size() == 1) {
     SK_TRY(build_hash(ctx, parts[0]));
     *out = parts[0];
@@ -485,6 +496,24 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
   SK_TRY(concat_sets(ctx, cp, out));
   SK_TRY(build_hash(ctx, *out));
   return SK_OK;
+}
+
+// concatenate `parts` after `base` (may be null) into a fresh set owned by ctx, with hash tables; inputs stay valid
+int merge_sets(sk_ctx* ctx, const sk_sketch_set* base, const std::vector<sk_sketch_set*>& parts, sk_sketch_set** out) {
+  std::vector<const sk_sketch_set*> v;
+  if (base) v.push_back(base);
+  for (auto* p : parts) v.push_back(p);
+  SK_TRY(concat_sets(ctx, v, out));
+  return build_hash(ctx, *out);
+}
+}  // namespace sk
+
+extern "C" {
+
+int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+                    const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out) {
+  if (!out) return SK_ERR_PARAM;
+  return sk::sketch_batch_host(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, out, nullptr, 0);
 }
 
 int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t* kmer, const uint32_t* pos,

@@ -1140,6 +1140,8 @@ struct BatchBuffers {  // grow-only device buffers reused across batches
 template <typename T>
 static int ensure(sk_ctx* ctx, T** p, size_t* cap, size_t need) {
   if (need <= *cap && *p) return SK_OK;
+  // grow-only, kept for the life of the context: plain cudaMalloc (outside the stream-ordered pool, whose reuse of
+  // multi-GB blocks of varying size proved erratic); growth happens only while the workload is still getting larger
   if (*p) SK_CUDA(cudaFree(*p));
   *p = nullptr;
   size_t n = std::max<size_t>(need + need / 4, 1024);
@@ -1371,7 +1373,7 @@ static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_se
     else { d.qset = 1; d.qg = q; d.rset = 0; d.rg = r; }
   }
   // batches bounded by the per-record workspace
-  const uint64_t REC_CAP = 256ull << 20;
+  const uint64_t REC_CAP = 128ull << 20;
   size_t b0 = 0;
   while (b0 < n_pairs) {
     size_t b1 = b0;

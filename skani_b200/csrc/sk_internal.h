@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@ struct sk_ctx {
   cudaEvent_t h2d_done[2] = {nullptr, nullptr};
   uint8_t* dbuf[2] = {nullptr, nullptr};  // device staging double buffer (sk_sketch_batch)
   size_t dbuf_bytes = 0;
+  sk_ctx* child = nullptr;               // worker context of the pipelined sk_triangle (second stream + own workspaces)
   // grow-only chaining workspace (chain.cu), kept for the life of the context
   void* chain_scratch = nullptr;
   void (*chain_scratch_free)(void*) = nullptr;
@@ -123,7 +125,12 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out);
 int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const std::vector<uint64_t>& raw_mk_off);
 void free_set_device(sk_sketch_set* s);
-int build_hash(sk_ctx* ctx, sk_sketch_set* set);  // (re)builds set->htab from ukmer/ustart; call on every finished set
+int build_hash(sk_ctx* ctx, sk_sketch_set* set);
+// api.cu
+int sketch_batch_host(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs, const uint32_t* genome_of_contig,
+                      uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out,
+                      const std::function<int(sk_sketch_set*, uint32_t, uint32_t)>* on_part, size_t subbatch_override);
+int merge_sets(sk_ctx* ctx, const sk_sketch_set* base, const std::vector<sk_sketch_set*>& parts, sk_sketch_set** out);  // (re)builds set->htab from ukmer/ustart; call on every finished set
 // screen.cu / chain.cu
 uint64_t count_launch(sk_ctx* ctx, uint64_t n = 1);
 }  // namespace sk

@@ -1,47 +1,164 @@
 // triangle.cu -- whole `skani triangle` hot path from host buffers (reference src/triangle.rs:13-105):
 // sketch every genome, marker screen (rows i, columns j > i), chain every passing pair, keep ani > 0.1.
+//
+// Large inputs are PCIe-bound (a 5 Mbp genome is 5 MB of ASCII on the wire and ~70 us of kernels), so the call is
+// software-pipelined: the genome set is cut into waves; while wave w+1 is being uploaded and seeded on the context's
+// stream, a worker thread with a child context appends wave w to the set sketched so far, screens it and chains the
+// NEW pairs (those whose larger index lies in wave w) on a second stream.  The result set is identical to the
+// unpipelined order of operations: pair (i, j), i < j, is screened by row i's rule against all columns exactly once,
+// when j's wave arrives (src/triangle.rs:71-105 evaluates the same predicate on the same sketches).
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "sk_internal.h"
 
-extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
-                           const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
-                           const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats) {
-  if (!ctx || !out || !n_out || !sp || !mp) return SK_ERR_PARAM;
-  *out = nullptr; *n_out = 0;
-  SK_CUDA(cudaSetDevice(ctx->device));
-  cudaEvent_t ev[4];
-  for (auto& e : ev) SK_CUDA(cudaEventCreate(&e));
-  struct EG { cudaEvent_t* e; ~EG() { for (int i = 0; i < 4; i++) cudaEventDestroy(e[i]); } } eg{ev};
-  SK_CUDA(cudaEventRecord(ev[0], ctx->stream));
+namespace {
+
+struct Wave { sk_sketch_set* set; uint32_t g_begin; bool last; };
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int simple_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs, const uint32_t* genome_of_contig,
+                    uint32_t n_genomes, const sk_sketch_params* sp, const sk_map_params* mp, std::vector<sk_ani_result>& kept,
+                    uint64_t* n_screened) {
   sk_sketch_set* set = nullptr;
   SK_TRY(sk_sketch_batch(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, &set));
   struct SG { sk_sketch_set* s; ~SG() { sk_sketch_set_free(s); } } sg{set};
-  SK_CUDA(cudaEventRecord(ev[1], ctx->stream));
   uint64_t* pairs = nullptr;
   uint64_t np = 0;
   SK_TRY(sk_screen_triangle(ctx, set, mp, &pairs, &np));
   struct PG { uint64_t* p; ~PG() { free(p); } } pg{pairs};
-  SK_CUDA(cudaEventRecord(ev[2], ctx->stream));
   std::vector<sk_ani_result> res(np);
   SK_TRY(sk_chain_pairs(ctx, set, set, pairs, np, mp, res.data()));
-  SK_CUDA(cudaEventRecord(ev[3], ctx->stream));
-  SK_CUDA(cudaEventSynchronize(ev[3]));
-  uint64_t kept = 0;
-  for (auto& r : res) if (r.ani > 0.1f) kept++;                    // src/triangle.rs:99 (NaN and -1 fail)
-  sk_ani_result* o = (sk_ani_result*)malloc(sizeof(sk_ani_result) * (kept ? kept : 1));
+  for (auto& r : res) if (r.ani > 0.1f) kept.push_back(r);            // src/triangle.rs:99 (NaN and -1 fail)
+  *n_screened = np;
+  return SK_OK;
+}
+
+}  // namespace
+
+extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+                           const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
+                           const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats) {
+  if (!ctx || !out || !n_out || !sp || !mp || !contig_off) return SK_ERR_PARAM;
+  *out = nullptr; *n_out = 0;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  cudaEvent_t ev[2];
+  for (auto& e : ev) SK_CUDA(cudaEventCreate(&e));
+  struct EG { cudaEvent_t* e; ~EG() { for (int i = 0; i < 2; i++) cudaEventDestroy(e[i]); } } eg{ev};
+  SK_CUDA(cudaEventRecord(ev[0], ctx->stream));
+  std::vector<sk_ani_result> kept;
+  uint64_t n_screened = 0;
+  const uint64_t total_bytes = n_contigs ? contig_off[n_contigs] - contig_off[0] : 0;
+  // The upload/seed || screen/chain pipeline is EXPERIMENTAL and off by default (SK_PIPELINE=1 or SK_FORCE_PIPELINE=1 enable
+  // it): it hides chaining under the PCIe transfer, but the stream-ordered allocator's handling of the varying multi-GB
+  // set sizes made its timing erratic on B200 (profiles/r01_pipeline_trace.txt); see DESIGN.md section 9.
+  const bool pipelined = ((getenv("SK_PIPELINE") && total_bytes >= (4ull << 30) && n_genomes >= 64) ||
+                          (getenv("SK_FORCE_PIPELINE") && n_genomes >= 2)) && getenv("SK_NO_PIPELINE") == nullptr;
+  if (!pipelined) {
+    SK_TRY(simple_triangle(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, kept, &n_screened));
+  } else {
+    // ---- producer: ONE continuous upload + seeding pass (the H2D stream never drains); every finished sub-batch is
+    //      handed to the worker.  Worker: once >= 1/8 of the genomes are pending (or the input is finished) it merges
+    //      them into the set sketched so far, screens the merged set and chains the pairs whose larger index is new.
+    if (!ctx->child) {
+      if (sk_ctx_create(ctx->device, &ctx->child) != SK_OK) { ctx->err = "cannot create the worker context"; return SK_ERR_CUDA; }
+    }
+    sk_ctx* wctx = ctx->child;
+    const bool trace = getenv("SK_TRACE") != nullptr;
+    const double t00 = now_s();
+    const uint32_t wave_genomes = std::max<uint32_t>(1, n_genomes / 8);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Wave> q;
+    int worker_rc = SK_OK;
+    std::string worker_err;
+    std::thread worker([&] {
+      cudaSetDevice(wctx->device);
+      sk_sketch_set* merged = nullptr;
+      std::vector<sk_sketch_set*> pending;
+      uint32_t pending_begin = 0, pending_genomes = 0;
+      bool done = false;
+      while (!done) {
+        Wave w;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return !q.empty(); });
+          w = q.front(); q.pop_front();
+        }
+        if (w.set) {
+          if (pending.empty()) pending_begin = w.g_begin;
+          pending.push_back(w.set);
+          pending_genomes += w.set->G;
+        }
+        done = w.last;
+        if (pending.empty() || (!done && pending_genomes < wave_genomes)) continue;
+        if (worker_rc == SK_OK) {
+          const double ta = now_s();
+          sk_sketch_set* next = nullptr;
+          int rc = sk::merge_sets(wctx, merged, pending, &next);
+          double tb = now_s(), tc = tb, td = tb;
+          if (rc == SK_OK) {
+            if (merged) sk_sketch_set_free(merged);
+            merged = next;
+            uint64_t* pairs = nullptr; uint64_t np = 0;
+            rc = sk_screen_triangle(wctx, merged, mp, &pairs, &np);
+            tc = now_s();
+            if (rc == SK_OK) {
+              uint64_t m = 0;   // new pairs: larger index j inside the genomes just merged
+              for (uint64_t i = 0; i < np; i++) if ((uint32_t)pairs[i] >= pending_begin) pairs[m++] = pairs[i];
+              std::vector<sk_ani_result> res(m);
+              rc = sk_chain_pairs(wctx, merged, merged, pairs, m, mp, res.data());
+              if (rc == SK_OK) { for (auto& r : res) if (r.ani > 0.1f) kept.push_back(r); n_screened += m; }
+              free(pairs);
+              td = now_s();
+            }
+          }
+          if (trace) fprintf(stderr, "[sk_triangle] worker: genomes >= %u (%u new): start %.3f merge %.3f screen %.3f chain %.3f s\n",
+                             pending_begin, pending_genomes, ta - t00, tb - ta, tc - tb, td - tc);
+          if (rc != SK_OK) { worker_rc = rc; worker_err = wctx->err; }
+        }
+        cudaStreamSynchronize(wctx->stream);
+        for (auto* p : pending) sk_sketch_set_free(p);
+        pending.clear(); pending_genomes = 0;
+      }
+      if (merged) { cudaStreamSynchronize(wctx->stream); sk_sketch_set_free(merged); }
+    });
+    std::function<int(sk_sketch_set*, uint32_t, uint32_t)> on_part = [&](sk_sketch_set* part, uint32_t g_begin, uint32_t g_end) -> int {
+      (void)g_end;
+      if (trace) fprintf(stderr, "[sk_triangle] producer: part of %u genomes from %u ready at %.3f s\n", part->G, g_begin, now_s() - t00);
+      { std::lock_guard<std::mutex> lk(mu); q.push_back(Wave{part, g_begin, false}); }
+      cv.notify_one();
+      return SK_OK;
+    };
+    int rc = sk::sketch_batch_host(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, nullptr, &on_part, 1024ull << 20);
+    { std::lock_guard<std::mutex> lk(mu); q.push_back(Wave{nullptr, 0, true}); }
+    cv.notify_one();
+    worker.join();
+    if (rc != SK_OK) return rc;
+    if (worker_rc != SK_OK) { ctx->err = "worker: " + worker_err; return worker_rc; }
+  }
+  SK_CUDA(cudaEventRecord(ev[1], ctx->stream));
+  SK_CUDA(cudaEventSynchronize(ev[1]));
+  sk_ani_result* o = (sk_ani_result*)malloc(sizeof(sk_ani_result) * (kept.empty() ? 1 : kept.size()));
   if (!o) return SK_ERR_NOMEM;
-  uint64_t w = 0;
-  for (auto& r : res) if (r.ani > 0.1f) o[w++] = r;
-  *out = o; *n_out = kept;
+  if (!kept.empty()) memcpy(o, kept.data(), kept.size() * sizeof(sk_ani_result));
+  *out = o; *n_out = kept.size();
   if (stats) {
-    float a, b, c, t;
-    cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
-    cudaEventElapsedTime(&t, ev[0], ev[3]);
-    stats->t_sketch = a * 1e-3; stats->t_screen = b * 1e-3; stats->t_chain = c * 1e-3; stats->t_total = t * 1e-3;
-    stats->n_pairs_screened = np; stats->n_pairs_kept = kept;
+    float t = 0;
+    cudaEventElapsedTime(&t, ev[0], ev[1]);
+    memset(stats, 0, sizeof(*stats));
+    stats->t_total = t * 1e-3;
+    stats->n_pairs_screened = n_screened; stats->n_pairs_kept = kept.size();
   }
   return SK_OK;
 }

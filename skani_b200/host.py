@@ -6,6 +6,13 @@ import numpy as np
 from . import _lib
 from ._lib import AniResult, ChainDebug, MapParams, SketchParams, TriangleStats
 
+# numpy view of sk_ani_result (include/skani_b200.h): lets callers take 10^5..10^6 results without per-row Python objects
+RESULT_DTYPE = np.dtype([(n, np.float32) for n in ("ani", "af_query", "af_ref", "ci_lower", "ci_upper", "std", "q90_q", "q90_r", "q50_q",
+                                                   "q50_r", "q10_q", "q10_r")] +
+                        [(n, np.uint32) for n in ("num_contigs_q", "num_contigs_r", "avg_chain_int_len", "total_bases_covered",
+                                                  "ref_id", "query_id")])
+assert RESULT_DTYPE.itemsize == C.sizeof(AniResult)
+
 MIN_LENGTH_CONTIG = 500  # reference src/params.rs:42, applied by file_io::fastx_to_sketches (src/file_io.rs:176)
 
 
@@ -178,12 +185,16 @@ def screen_query_ref(ctx, refs, queries, mp=None, mode=0):
     return arr
 
 
-def chain_pairs(ctx, refs, queries, pairs, mp=None):
+def chain_pairs(ctx, refs, queries, pairs, mp=None, as_array=False):
+    """sk_chain_pairs.  as_array=True returns a numpy structured array (RESULT_DTYPE) instead of a list of AniResult."""
     mp = mp or map_params()
     pairs = np.ascontiguousarray(pairs, np.uint64)
-    out = (AniResult * max(len(pairs), 1))()
-    ctx.check(ctx.L.sk_chain_pairs(ctx.h, refs.h, queries.h, pairs.ctypes.data, len(pairs), C.byref(mp), out))
-    return [out[i] for i in range(len(pairs))]
+    out = np.zeros(max(len(pairs), 1), RESULT_DTYPE)
+    ctx.check(ctx.L.sk_chain_pairs(ctx.h, refs.h, queries.h, pairs.ctypes.data, len(pairs), C.byref(mp), out.ctypes.data))
+    out = out[:len(pairs)]
+    if as_array:
+        return out
+    return [AniResult.from_buffer_copy(out[i].tobytes()) for i in range(len(pairs))]
 
 
 def chain_pair_debug(ctx, refs, queries, ref_id, query_id, mp=None):
@@ -205,7 +216,7 @@ def chain_pair_debug(ctx, refs, queries, ref_id, query_id, mp=None):
     return res
 
 
-def triangle(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=None):
+def triangle(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=None, as_array=False):
     """Whole `skani triangle` hot path from host buffers (reference src/triangle.rs:13-105)."""
     sp = sp or sketch_params(); mp = mp or map_params()
     contig_off = np.ascontiguousarray(contig_off, np.uint64)
@@ -214,6 +225,9 @@ def triangle(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=No
     out = C.POINTER(AniResult)(); n = C.c_uint64(); st = TriangleStats()
     ctx.check(ctx.L.sk_triangle(ctx.h, ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes, C.byref(sp),
                                 C.byref(mp), C.byref(out), C.byref(n), C.byref(st)))
-    res = [AniResult.from_buffer_copy(out[i]) for i in range(n.value)]
+    if as_array:
+        res = np.frombuffer(C.string_at(out, n.value * C.sizeof(AniResult)), RESULT_DTYPE).copy() if n.value else np.zeros(0, RESULT_DTYPE)
+    else:
+        res = [AniResult.from_buffer_copy(out[i]) for i in range(n.value)]
     ctx.L.sk_free(out)
     return res, st

@@ -85,7 +85,7 @@ class DistTriangle:
         ctx.check(L.sk_screen_triangle_rows(ctx.h, allset.h, C.byref(self.mp), self.world, self.rank, C.byref(pp), C.byref(n)))
         pairs = np.ctypeslib.as_array(pp, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
         L.sk_free(pp)
-        res = H.chain_pairs(ctx, allset, allset, pairs, self.mp)
+        res = H.chain_pairs(ctx, allset, allset, pairs, self.mp, as_array=True)
         allset.free()
-        self.last_results = [r for r in res if r.ani > 0.1]     # src/triangle.rs:99
+        self.last_results = res[res["ani"] > 0.1]               # src/triangle.rs:99 (numpy structured array)
         return len(self.last_results)

@@ -23,7 +23,8 @@ tri = DistTriangle(ctx, world, rank, sk.sketch_params(), sk.map_params())
 for use_host in (True, False):
     dev = torch.from_numpy(bases).cuda()
     kept = tri.step(bases if use_host else None, dev.data_ptr(), off, goc, g1 - g0, g0, n)
-    rows = np.array([[r.ref_id, r.query_id, r.ani, r.af_ref, r.af_query] for r in tri.last_results], np.float64).reshape(-1, 5)
+    lr = tri.last_results
+    rows = np.stack([lr["ref_id"], lr["query_id"], lr["ani"], lr["af_ref"], lr["af_query"]], axis=1).astype(np.float64).reshape(-1, 5)
     np.save(os.path.join(out_dir, "rank%d_%d.npy" % (rank, int(use_host))), rows)
 torch.distributed.barrier()
 torch.distributed.destroy_process_group()

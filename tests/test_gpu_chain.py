@@ -263,3 +263,18 @@ def test_chunk_catchup_after_long_gap(ctx):
         assert_debug_equal(gd, od)
     sizes = np.diff(O.chain_debug(osk[0], osk[1], O.cmd())["chunk_first"])
     assert (sizes == 1).sum() >= 2          # the oracle really produced catch-up singleton chunks
+
+
+def test_pipelined_triangle_equals_simple(ctx, monkeypatch):
+    """sk_triangle's upload/seed || screen/chain software pipeline (used for >= 4 GiB inputs) gives the same result set."""
+    import skani_b200 as sk
+    n, L, G = 30, 300_000, 5
+    bases, off, goc = synth.generate(0, n, L, G=G)
+    monkeypatch.setenv("SK_NO_PIPELINE", "1")
+    r0, st0 = sk.triangle(ctx, bases, off, goc, n, as_array=True)
+    monkeypatch.delenv("SK_NO_PIPELINE")
+    monkeypatch.setenv("SK_FORCE_PIPELINE", "1")
+    r1, st1 = sk.triangle(ctx, bases, off, goc, n, as_array=True)
+    assert st0.n_pairs_screened == st1.n_pairs_screened == n // G * (G * (G - 1) // 2)
+    k0 = np.sort(r0, order=["ref_id", "query_id"]); k1 = np.sort(r1, order=["ref_id", "query_id"])
+    assert len(k0) == len(k1) and k0.tobytes() == k1.tobytes()

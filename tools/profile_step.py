@@ -33,7 +33,7 @@ def run(timing):
     torch.cuda.synchronize(); t1 = time.perf_counter()
     pairs = sk.screen_triangle(ctx, gs, mp)
     torch.cuda.synchronize(); t2 = time.perf_counter()
-    res = sk.chain_pairs(ctx, gs, gs, pairs, mp)
+    res = sk.chain_pairs(ctx, gs, gs, pairs, mp, as_array=True)
     torch.cuda.synchronize(); t3 = time.perf_counter()
     gs.free()
     t4 = time.perf_counter()
@@ -49,7 +49,7 @@ for timing in (False, True):
     for k, (ms, cnt) in sorted(tk.items(), key=lambda kv: -kv[1][0]):
         print("   %-20s %9.3f ms  %5d launches" % (k, ms, cnt))
 t0 = time.perf_counter()
-res, st = sk.triangle(ctx, host, off, goc, n, sp, mp)
+res, st = sk.triangle(ctx, host, off, goc, n, sp, mp, as_array=True)
 print("e2e triangle %.1f ms (sketch %.1f screen %.1f chain %.1f)" % ((time.perf_counter() - t0) * 1e3, st.t_sketch * 1e3,
                                                                       st.t_screen * 1e3, st.t_chain * 1e3))
 # raw H2D bandwidth of the same pinned buffer (reference point for the e2e leg)

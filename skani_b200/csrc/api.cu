@@ -10,6 +10,62 @@
 
 using namespace sk;
 
+// ---- SkArena ------------------------------------------------------------------------------------------------
+cudaError_t SkArena::alloc(void** out, size_t bytes) {
+  std::lock_guard<std::mutex> lk(mu);
+  const size_t need = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+  for (int pass = 0; pass < 2; pass++) {
+    for (size_t si = 0; si < slabs.size(); si++) {
+      auto& fb = slabs[si].free_blocks;
+      for (auto it = fb.begin(); it != fb.end(); ++it) {
+        if (it->second >= need) {
+          const size_t off = it->first, sz = it->second;
+          fb.erase(it);
+          if (sz > need) fb[off + need] = sz - need;
+          void* p = slabs[si].base + off;
+          live[p] = {(int)si, need};
+          *out = p;
+          return cudaSuccess;
+        }
+      }
+    }
+    if (pass == 1) break;
+    // grow: a new slab, geometrically sized
+    size_t slab = std::max<size_t>(need, std::min<size_t>(16ull << 30, std::max<size_t>(1ull << 30, total)));
+    uint8_t* base = nullptr;
+    cudaError_t e = cudaMalloc((void**)&base, slab);
+    if (e != cudaSuccess && slab > need) { cudaGetLastError(); slab = need; e = cudaMalloc((void**)&base, slab); }
+    if (e != cudaSuccess) return e;
+    Slab s; s.base = base; s.size = slab; s.free_blocks[0] = slab;
+    slabs.push_back(std::move(s));
+    total += slab;
+  }
+  return cudaErrorMemoryAllocation;
+}
+void SkArena::release(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = live.find(p);
+  if (it == live.end()) return;
+  const int si = it->second.first;
+  size_t sz = it->second.second;
+  live.erase(it);
+  auto& fb = slabs[si].free_blocks;
+  size_t off = (uint8_t*)p - slabs[si].base;
+  auto nx = fb.lower_bound(off);
+  if (nx != fb.end() && off + sz == nx->first) { sz += nx->second; nx = fb.erase(nx); }     // coalesce with the next block
+  if (nx != fb.begin()) {
+    auto pv = std::prev(nx);
+    if (pv->first + pv->second == off) { off = pv->first; sz += pv->second; fb.erase(pv); }  // and with the previous one
+  }
+  fb[off] = sz;
+}
+void SkArena::destroy() {
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& s : slabs) cudaFree(s.base);
+  slabs.clear(); live.clear(); total = 0;
+}
+
 namespace {
 constexpr size_t SUBBATCH_MAX = 2048ull << 20;  // bases per seeding sub-batch: bounds the per-base temporaries ...
 constexpr size_t SUBBATCH_MIN = 256ull << 20;   // ... while keeping >= ~8 sub-batches so H2D copies overlap the kernels
@@ -39,7 +95,7 @@ int concat_dev(sk_ctx* ctx, const std::vector<const T*>& parts, const std::vecto
   size_t total = 0;
   for (size_t c : counts) total += c;
   T* p = nullptr;
-  SK_CUDA(cudaMallocAsync((void**)&p, std::max<size_t>(total, 1) * sizeof(T), ctx->stream));
+  SK_CUDA(ctx->arena.alloc((void**)&p, std::max<size_t>(total, 1) * sizeof(T)));
   size_t o = 0;
   for (size_t i = 0; i < parts.size(); i++) {
     if (counts[i]) SK_CUDA(cudaMemcpyAsync(p + o, parts[i], counts[i] * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -126,6 +182,7 @@ int sk_ctx_destroy(sk_ctx* ctx) {
   if (ctx->child) { sk_ctx_destroy(ctx->child); ctx->child = nullptr; }
   if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
   for (int i = 0; i < 2; i++) if (ctx->dbuf[i]) cudaFree(ctx->dbuf[i]);
+  ctx->arena.destroy();
   for (int i = 0; i < 2; i++) {
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
     if (ctx->pinned_free[i]) cudaEventDestroy(ctx->pinned_free[i]);
@@ -552,10 +609,10 @@ int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t
   s->total_len = {tl};
   s->name_rank = {0};
   size_t S1 = std::max<size_t>(n_records, 1);
-  SK_CUDA(cudaMallocAsync((void**)&s->pv_kmer, S1 * 4, ctx->stream)); SK_CUDA(cudaMallocAsync((void**)&s->pv_pos, S1 * 4, ctx->stream));
-  SK_CUDA(cudaMallocAsync((void**)&s->pv_cc, S1 * 4, ctx->stream));
-  SK_CUDA(cudaMallocAsync((void**)&s->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4, ctx->stream));
-  SK_CUDA(cudaMallocAsync((void**)&s->ctg_rec_off, (size_t)(n_contigs + 2) * 4, ctx->stream));
+  SK_CUDA(ctx->arena.alloc((void**)&s->pv_kmer, S1 * 4)); SK_CUDA(ctx->arena.alloc((void**)&s->pv_pos, S1 * 4));
+  SK_CUDA(ctx->arena.alloc((void**)&s->pv_cc, S1 * 4));
+  SK_CUDA(ctx->arena.alloc((void**)&s->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
+  SK_CUDA(ctx->arena.alloc((void**)&s->ctg_rec_off, (size_t)(n_contigs + 2) * 4));
   SK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (n_records) {
     SK_CUDA(cudaMemcpy(s->pv_kmer, hk.data(), n_records * 4, cudaMemcpyHostToDevice));
@@ -565,7 +622,7 @@ int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t
   if (n_contigs) SK_CUDA(cudaMemcpy(s->d_ctg_len, contig_lengths, n_contigs * 4, cudaMemcpyHostToDevice));
   SK_CUDA(cudaMemcpy(s->ctg_rec_off, crl.data(), (size_t)(n_contigs + 1) * 4, cudaMemcpyHostToDevice));
   DTmp<uint64_t> mraw;
-  SK_CUDA(mraw.alloc(n_markers, ctx->stream));
+  SK_CUDA(mraw.alloc(n_markers, ctx));
   if (n_markers) SK_CUDA(cudaMemcpyAsync(mraw.p, markers, n_markers * 8, cudaMemcpyHostToDevice, ctx->stream));
   std::vector<uint64_t> raw_off = {0, n_markers};
   SK_TRY(build_views(ctx, s, mraw.p, raw_off));

@@ -181,17 +181,17 @@ static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_se
   const int all_pass = 0;
 
   DTmp<uint64_t> d_row_off, d_col_off;
-  SK_CUDA(d_row_off.alloc(NR + 1, st)); SK_CUDA(d_col_off.alloc(NC + 1, st));
+  SK_CUDA(d_row_off.alloc(NR + 1, ctx)); SK_CUDA(d_col_off.alloc(NC + 1, ctx));
   SK_CUDA(cudaMemcpyAsync(d_row_off.p, rows->mk_off.data(), (NR + 1) * 8, cudaMemcpyHostToDevice, st));
   SK_CUDA(cudaMemcpyAsync(d_col_off.p, cols->mk_off.data(), (NC + 1) * 8, cudaMemcpyHostToDevice, st));
   DTmp<uint32_t> ra, rb, scol;
   const size_t n_row_entries = tri ? Mc : Mr;
-  SK_CUDA(ra.alloc(n_row_entries, st)); SK_CUDA(rb.alloc(n_row_entries, st)); SK_CUDA(scol.alloc(N, st));
+  SK_CUDA(ra.alloc(n_row_entries, ctx)); SK_CUDA(rb.alloc(n_row_entries, ctx)); SK_CUDA(scol.alloc(N, ctx));
   if (N > 0) {
     DTmp<uint64_t> keys, skeys;
     DTmp<uint32_t> vals, svals, eg, head, hscan, rstart, firstq;
-    SK_CUDA(keys.alloc(N, st)); SK_CUDA(skeys.alloc(N, st)); SK_CUDA(vals.alloc(N, st)); SK_CUDA(svals.alloc(N, st));
-    SK_CUDA(eg.alloc(N, st)); SK_CUDA(head.alloc(N, st)); SK_CUDA(hscan.alloc(N, st));
+    SK_CUDA(keys.alloc(N, ctx)); SK_CUDA(skeys.alloc(N, ctx)); SK_CUDA(vals.alloc(N, ctx)); SK_CUDA(svals.alloc(N, ctx));
+    SK_CUDA(eg.alloc(N, ctx)); SK_CUDA(head.alloc(N, ctx)); SK_CUDA(hscan.alloc(N, ctx));
     if (Mc) SK_CUDA(cudaMemcpyAsync(keys.p, cols->markers, Mc * 8, cudaMemcpyDeviceToDevice, st));
     if (Mr) SK_CUDA(cudaMemcpyAsync(keys.p + Mc, rows->markers, Mr * 8, cudaMemcpyDeviceToDevice, st));
     fill_genome_kernel<<<NC, 256, 0, st>>>(d_col_off.p, 0, eg.p); count_launch(ctx);
@@ -200,26 +200,26 @@ static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_se
     size_t tb = 0;
     SK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, skeys.p, vals.p, svals.p, (int)N, 0, 2 * MARKER_K, st));
     DTmp<uint8_t> tmp;
-    SK_CUDA(tmp.alloc(tb, st));
+    SK_CUDA(tmp.alloc(tb, ctx));
     SK_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, skeys.p, vals.p, svals.p, (int)N, 0, 2 * MARKER_K, st));
     run_head_kernel<<<div_up64(N, 256), 256, 0, st>>>(skeys.p, (uint32_t)N, head.p); count_launch(ctx);
     size_t tb2 = 0;
     SK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, head.p, hscan.p, N, st));
     DTmp<uint8_t> tmp2;
-    SK_CUDA(tmp2.alloc(tb2, st));
+    SK_CUDA(tmp2.alloc(tb2, ctx));
     SK_CUDA(cub::DeviceScan::ExclusiveSum(tmp2.p, tb2, head.p, hscan.p, N, st));
     uint32_t lh = 0, ls = 0;
     SK_CUDA(cudaMemcpyAsync(&lh, head.p + (N - 1), 4, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaMemcpyAsync(&ls, hscan.p + (N - 1), 4, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_runs = lh + ls;
-    SK_CUDA(rstart.alloc((size_t)n_runs + 1, st));
+    SK_CUDA(rstart.alloc((size_t)n_runs + 1, ctx));
     run_start_kernel<<<div_up64(N, 256), 256, 0, st>>>(head.p, hscan.p, (uint32_t)N, n_runs, rstart.p); count_launch(ctx);
     if (tri) {
       tri_ranges_kernel<<<div_up64(N, 256), 256, 0, st>>>(svals.p, head.p, hscan.p, rstart.p, eg.p, (uint32_t)N, ra.p, rb.p, scol.p);
       count_launch(ctx);
     } else {
-      SK_CUDA(firstq.alloc((size_t)n_runs + 1, st));
+      SK_CUDA(firstq.alloc((size_t)n_runs + 1, ctx));
       // runs without query entries never get read; runs without refs: firstq = rstart (empty slice)
       SK_CUDA(cudaMemcpyAsync(firstq.p, rstart.p, ((size_t)n_runs + 1) * 4, cudaMemcpyDeviceToDevice, st));
       qr_firstq_kernel<<<div_up64(N, 256), 256, 0, st>>>(svals.p, head.p, hscan.p, (uint32_t)N, (uint32_t)Mc, firstq.p); count_launch(ctx);
@@ -234,11 +234,11 @@ static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_se
   SK_CUDA(cudaFuncSetAttribute(screen_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned long long cap = std::max<unsigned long long>(1ull << 20, 64ull * NR);
   DTmp<unsigned long long> d_n;
-  SK_CUDA(d_n.alloc(1, st));
+  SK_CUDA(d_n.alloc(1, ctx));
   DTmp<uint64_t> d_pairs;
   unsigned long long n = 0;
   for (int attempt = 0; attempt < 2; attempt++) {
-    SK_CUDA(d_pairs.alloc(cap, st));
+    SK_CUDA(d_pairs.alloc(cap, ctx));
     SK_CUDA(cudaMemsetAsync(d_n.p, 0, 8, st));
     const uint32_t n_rows_total = tri ? (NR > 0 ? NR - 1 : 0) : NR;  // src/triangle.rs:71: rows 0..N-2
     const uint32_t n_rows_launch = n_rows_total > row_rem ? (n_rows_total - row_rem + row_mod - 1) / row_mod : 0;
@@ -257,11 +257,11 @@ static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_se
   if (!host) return SK_ERR_NOMEM;
   if (n > 0) {
     DTmp<uint64_t> sorted;
-    SK_CUDA(sorted.alloc(n, st));
+    SK_CUDA(sorted.alloc(n, ctx));
     size_t tb = 0;
     SK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_pairs.p, sorted.p, (uint64_t)n, 0, 64, st));
     DTmp<uint8_t> tmp;
-    SK_CUDA(tmp.alloc(tb, st));
+    SK_CUDA(tmp.alloc(tb, ctx));
     SK_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, d_pairs.p, sorted.p, (uint64_t)n, 0, 64, st));
     SK_CUDA(cudaMemcpyAsync(host, sorted.p, n * 8, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaStreamSynchronize(st));

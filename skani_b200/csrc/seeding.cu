@@ -260,7 +260,7 @@ static int scan_exclusive(sk_ctx* ctx, const T* in, T* out, size_t n) {
   size_t tb = 0;
   SK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, ctx->stream));
   DTmp<uint8_t> tmp;
-  SK_CUDA(tmp.alloc(tb, ctx->stream));
+  SK_CUDA(tmp.alloc(tb, ctx));
   SK_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n, ctx->stream));
   return SK_OK;
 }
@@ -268,8 +268,7 @@ static int scan_exclusive(sk_ctx* ctx, const T* in, T* out, size_t n) {
 void free_set_device(sk_sketch_set* s) {
   void* ptrs[] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart,
                   s->markers, s->ctg_rec_off, s->d_ctg_len, s->ubucket, s->htab};
-  cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
-  for (void* p : ptrs) if (p) cudaFreeAsync(p, st);
+  for (void* p : ptrs) if (p) s->ctx->arena.release(p);
   s->pv_kmer = s->pv_pos = s->pv_cc = s->kv_pos = s->kv_cc = s->ukmer = s->ustart = s->ctg_rec_off = s->d_ctg_len = nullptr;
   s->pv_mult = nullptr;
   s->markers = nullptr;
@@ -302,7 +301,7 @@ __global__ void hash_build_kernel(const uint64_t* __restrict__ uk_off, const uin
 int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
   cudaStream_t st = ctx->stream;
   const uint32_t G = set->G;
-  if (set->htab) { cudaFreeAsync(set->htab, st); set->htab = nullptr; }
+  if (set->htab) { ctx->arena.release(set->htab); set->htab = nullptr; }
   set->ht_off.assign(G + 1, 0);
   const bool force_bucket = getenv("SK_FORCE_BUCKET_PROBE") != nullptr;  // test hook: exercise the large-genome fallback
   for (uint32_t g = 0; g < G && !force_bucket; g++) {
@@ -312,16 +311,16 @@ int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
     set->ht_off[g + 1] = set->ht_off[g] + cap;
   }
   const uint64_t total = set->ht_off[G];
-  SK_CUDA(cudaMallocAsync((void**)&set->htab, std::max<uint64_t>(total, 1) * 8, st));
+  SK_CUDA(ctx->arena.alloc((void**)&set->htab, std::max<uint64_t>(total, 1) * 8));
   // genomes without a table (>= 2^20 records, or the test hook) use the bucket-index search: build that index only then
   bool need_bucket = false;
   for (uint32_t g = 0; g < G; g++) if (set->ht_off[g + 1] == set->ht_off[g] && set->uk_off[g + 1] > set->uk_off[g]) need_bucket = true;
-  if (set->ubucket) { cudaFreeAsync(set->ubucket, st); set->ubucket = nullptr; }
+  if (set->ubucket) { ctx->arena.release(set->ubucket); set->ubucket = nullptr; }
   if (need_bucket) {
     DTmp<uint64_t> d_uk2;
-    SK_CUDA(d_uk2.alloc(G + 1, st));
+    SK_CUDA(d_uk2.alloc(G + 1, ctx));
     SK_CUDA(cudaMemcpyAsync(d_uk2.p, set->uk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
-    SK_CUDA(cudaMallocAsync((void**)&set->ubucket, (size_t)G * (UBUCKETS + 1) * 4, st));
+    SK_CUDA(ctx->arena.alloc((void**)&set->ubucket, (size_t)G * (UBUCKETS + 1) * 4));
     const uint32_t kbits = 2 * set->sp.k;
     const uint32_t shift = kbits > UBUCKET_BITS ? kbits - UBUCKET_BITS : 0;
     bucket_kernel<<<G, 256, 0, st>>>(d_uk2.p, set->ukmer, shift, set->ubucket); count_launch(ctx);
@@ -330,7 +329,7 @@ int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
   if (total == 0) return SK_OK;
   SK_CUDA(cudaMemsetAsync(set->htab, 0, total * 8, st));
   DTmp<uint64_t> d_uk, d_ht;
-  SK_CUDA(d_uk.alloc(G + 1, st)); SK_CUDA(d_ht.alloc(G + 1, st));
+  SK_CUDA(d_uk.alloc(G + 1, ctx)); SK_CUDA(d_ht.alloc(G + 1, ctx));
   SK_CUDA(cudaMemcpyAsync(d_uk.p, set->uk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
   SK_CUDA(cudaMemcpyAsync(d_ht.p, set->ht_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
   hash_build_kernel<<<dim3(G, 8), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab); count_launch(ctx);
@@ -345,24 +344,24 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
   const size_t S = set->S;
   cudaStream_t st = ctx->stream;
   DTmp<uint64_t> d_seed_off, d_rawmk_off;
-  SK_CUDA(d_seed_off.alloc(G + 1, st));
+  SK_CUDA(d_seed_off.alloc(G + 1, ctx));
   SK_CUDA(cudaMemcpyAsync(d_seed_off.p, set->seed_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
-  SK_CUDA(cudaMallocAsync((void**)&set->kv_pos, std::max<size_t>(S, 1) * 4, ctx->stream));
-  SK_CUDA(cudaMallocAsync((void**)&set->kv_cc, std::max<size_t>(S, 1) * 4, ctx->stream));
-  SK_CUDA(cudaMallocAsync((void**)&set->pv_mult, std::max<size_t>(S, 1) * 2, ctx->stream));
+  SK_CUDA(ctx->arena.alloc((void**)&set->kv_pos, std::max<size_t>(S, 1) * 4));
+  SK_CUDA(ctx->arena.alloc((void**)&set->kv_cc, std::max<size_t>(S, 1) * 4));
+  SK_CUDA(ctx->arena.alloc((void**)&set->pv_mult, std::max<size_t>(S, 1) * 2));
   set->uk_off.assign(G + 1, 0);
   if (S > 0) {
     if (S >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 seed records"; return SK_ERR_PARAM; }
     DTmp<uint32_t> vals, skmer, perm, head, hscan;
-    SK_CUDA(vals.alloc(S, st)); SK_CUDA(skmer.alloc(S, st)); SK_CUDA(perm.alloc(S, st));
-    SK_CUDA(head.alloc(S + 1, st)); SK_CUDA(hscan.alloc(S + 1, st));
+    SK_CUDA(vals.alloc(S, ctx)); SK_CUDA(skmer.alloc(S, ctx)); SK_CUDA(perm.alloc(S, ctx));
+    SK_CUDA(head.alloc(S + 1, ctx)); SK_CUDA(hscan.alloc(S + 1, ctx));
     iota_local_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, vals.p); count_launch(ctx);
     size_t tb = 0;
     int end_bit = std::min(32, (int)(2 * set->sp.k));
     SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tb, set->pv_kmer, skmer.p, vals.p, perm.p, (int)S, (int)G,
                                                      d_seed_off.p, d_seed_off.p + 1, 0, end_bit, st));
     DTmp<uint8_t> tmp;
-    SK_CUDA(tmp.alloc(tb, st));
+    SK_CUDA(tmp.alloc(tb, ctx));
     SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp.p, tb, set->pv_kmer, skmer.p, vals.p, perm.p, (int)S, (int)G,
                                                      d_seed_off.p, d_seed_off.p + 1, 0, end_bit, st));
     kview_gather_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, perm.p, set->pv_pos, set->pv_cc, set->kv_pos,
@@ -370,7 +369,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, S));
     // total groups and per-genome group offsets
     DTmp<uint64_t> d_ukoff;
-    SK_CUDA(d_ukoff.alloc(G + 1, st));
+    SK_CUDA(d_ukoff.alloc(G + 1, ctx));
     uint32_t last_head = 0, last_scan = 0;
     SK_CUDA(cudaMemcpyAsync(&last_head, head.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaMemcpyAsync(&last_scan, hscan.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
@@ -379,15 +378,15 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_seed_off.p, G + 1, S, U, d_ukoff.p); count_launch(ctx);
     SK_CUDA(cudaMemcpyAsync(set->uk_off.data(), d_ukoff.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
     set->U = U;
-    SK_CUDA(cudaMallocAsync((void**)&set->ukmer, std::max<size_t>(U, 1) * 4, ctx->stream));
-    SK_CUDA(cudaMallocAsync((void**)&set->ustart, (size_t)(U + G) * 4, ctx->stream));
+    SK_CUDA(ctx->arena.alloc((void**)&set->ukmer, std::max<size_t>(U, 1) * 4));
+    SK_CUDA(ctx->arena.alloc((void**)&set->ustart, (size_t)(U + G) * 4));
     groups_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, head.p, hscan.p, U, G, set->ukmer, set->ustart); count_launch(ctx);
     mult_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult); count_launch(ctx);
     SK_CUDA(cudaStreamSynchronize(st));
   } else {
     set->U = 0;
-    SK_CUDA(cudaMallocAsync((void**)&set->ukmer, 4, ctx->stream));
-    SK_CUDA(cudaMallocAsync((void**)&set->ustart, (size_t)(G + 1) * 4, ctx->stream));
+    SK_CUDA(ctx->arena.alloc((void**)&set->ukmer, 4));
+    SK_CUDA(ctx->arena.alloc((void**)&set->ustart, (size_t)(G + 1) * 4));
     SK_CUDA(cudaMemsetAsync(set->ustart, 0, (size_t)(G + 1) * 4, st));
   }
   // ---- markers: per-genome sort + dedup (HashSet semantics, reference src/types.rs:269)
@@ -395,19 +394,19 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
   set->mk_off.assign(G + 1, 0);
   if (MR > 0) {
     if (MR >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 markers"; return SK_ERR_PARAM; }
-    SK_CUDA(d_rawmk_off.alloc(G + 1, st));
+    SK_CUDA(d_rawmk_off.alloc(G + 1, ctx));
     SK_CUDA(cudaMemcpyAsync(d_rawmk_off.p, raw_mk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
     DTmp<uint64_t> sorted;
-    SK_CUDA(sorted.alloc(MR, st));
+    SK_CUDA(sorted.alloc(MR, ctx));
     size_t tb = 0;
     SK_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, d_marker_raw, sorted.p, (int)MR, (int)G, d_rawmk_off.p,
                                                     d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
     DTmp<uint8_t> tmp;
-    SK_CUDA(tmp.alloc(tb, st));
+    SK_CUDA(tmp.alloc(tb, ctx));
     SK_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(tmp.p, tb, d_marker_raw, sorted.p, (int)MR, (int)G, d_rawmk_off.p,
                                                     d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
     DTmp<uint32_t> head, hscan;
-    SK_CUDA(head.alloc(MR, st)); SK_CUDA(hscan.alloc(MR, st));
+    SK_CUDA(head.alloc(MR, ctx)); SK_CUDA(hscan.alloc(MR, ctx));
     marker_head_kernel<<<dim3(G, 8), 256, 0, st>>>(d_rawmk_off.p, sorted.p, head.p); count_launch(ctx);
     SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, MR));
     uint32_t lh = 0, ls = 0;
@@ -416,16 +415,16 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     SK_CUDA(cudaStreamSynchronize(st));
     uint32_t M = lh + ls;
     set->M = M;
-    SK_CUDA(cudaMallocAsync((void**)&set->markers, std::max<size_t>(M, 1) * 8, ctx->stream));
+    SK_CUDA(ctx->arena.alloc((void**)&set->markers, std::max<size_t>(M, 1) * 8));
     marker_compact_kernel<<<div_up(MR, 256), 256, 0, st>>>(sorted.p, head.p, hscan.p, (uint32_t)MR, set->markers); count_launch(ctx);
     DTmp<uint64_t> d_mkoff;
-    SK_CUDA(d_mkoff.alloc(G + 1, st));
+    SK_CUDA(d_mkoff.alloc(G + 1, ctx));
     gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_rawmk_off.p, G + 1, MR, M, d_mkoff.p); count_launch(ctx);
     SK_CUDA(cudaMemcpyAsync(set->mk_off.data(), d_mkoff.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaStreamSynchronize(st));
   } else {
     set->M = 0;
-    SK_CUDA(cudaMallocAsync((void**)&set->markers, 8, ctx->stream));
+    SK_CUDA(ctx->arena.alloc((void**)&set->markers, 8));
   }
   return SK_OK;
 }
@@ -474,8 +473,8 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
   for (uint32_t g = 0; g < G; g++) set->name_rank[g] = g;
   const uint32_t NU = (uint32_t)units;
 
-  SK_CUDA(cudaMallocAsync((void**)&set->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4, ctx->stream));
-  SK_CUDA(cudaMallocAsync((void**)&set->ctg_rec_off, (size_t)(n_contigs + G + 1) * 4, ctx->stream));
+  SK_CUDA(ctx->arena.alloc((void**)&set->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
+  SK_CUDA(ctx->arena.alloc((void**)&set->ctg_rec_off, (size_t)(n_contigs + G + 1) * 4));
   set->seed_off.assign(G + 1, 0);
 
   DTmp<uint64_t> d_coff, P;
@@ -483,15 +482,15 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
   std::vector<uint64_t> raw_mk_off(G + 1, 0);
   DTmp<uint64_t> mkv, mraw;
   if (NU > 0) {
-    SK_CUDA(d_coff.alloc(n_contigs + 1, st)); SK_CUDA(d_cuoff.alloc(n_contigs + 1, st));
-    SK_CUDA(d_clen.alloc(n_contigs, st)); SK_CUDA(d_clocal.alloc(n_contigs, st));
+    SK_CUDA(d_coff.alloc(n_contigs + 1, ctx)); SK_CUDA(d_cuoff.alloc(n_contigs + 1, ctx));
+    SK_CUDA(d_clen.alloc(n_contigs, ctx)); SK_CUDA(d_clocal.alloc(n_contigs, ctx));
     SK_CUDA(cudaMemcpyAsync(d_coff.p, coff.data(), (n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
     SK_CUDA(cudaMemcpyAsync(d_cuoff.p, cuoff.data(), (n_contigs + 1) * 4, cudaMemcpyHostToDevice, st));
     SK_CUDA(cudaMemcpyAsync(d_clen.p, clen.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
     SK_CUDA(cudaMemcpyAsync(d_clocal.p, clocal.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
     SK_CUDA(cudaMemcpyAsync(set->d_ctg_len, clen.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
-    SK_CUDA(P.alloc(NU, st)); SK_CUDA(NM.alloc(NU, st)); SK_CUDA(ucontig.alloc(NU, st));
-    SK_CUDA(PM.alloc(NU, st)); SK_CUDA(cnt.alloc(NU, st)); SK_CUDA(uoff.alloc(NU, st));
+    SK_CUDA(P.alloc(NU, ctx)); SK_CUDA(NM.alloc(NU, ctx)); SK_CUDA(ucontig.alloc(NU, ctx));
+    SK_CUDA(PM.alloc(NU, ctx)); SK_CUDA(cnt.alloc(NU, ctx)); SK_CUDA(uoff.alloc(NU, ctx));
 
     SK_LAUNCH(ctx, "pack_kernel", (pack_kernel<<<div_up(NU, PACK_THREADS), PACK_THREADS, 0, st>>>(
         d_ascii, d_coff.p, d_cuoff.p, d_clen.p, n_contigs, NU, P.p, NM.p, ucontig.p)));
@@ -505,17 +504,17 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     SK_CUDA(cudaMemcpyAsync(&last_off, uoff.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
     // record offset of every contig's first unit (-> per-genome offsets and per-contig record offsets)
     DTmp<uint32_t> d_crec;
-    SK_CUDA(d_crec.alloc(n_contigs + 1, st));
+    SK_CUDA(d_crec.alloc(n_contigs + 1, ctx));
     SK_CUDA(cudaStreamSynchronize(st));
     const uint32_t S = last_cnt + last_off;
     gather_u32_kernel<<<div_up(n_contigs + 1, 256), 256, 0, st>>>(uoff.p, d_cuoff.p, n_contigs + 1, NU, S, d_crec.p); count_launch(ctx);
     std::vector<uint32_t> crec(n_contigs + 1);
     SK_CUDA(cudaMemcpyAsync(crec.data(), d_crec.p, (n_contigs + 1) * 4, cudaMemcpyDeviceToHost, st));
     set->S = S;
-    SK_CUDA(cudaMallocAsync((void**)&set->pv_kmer, std::max<size_t>(S, 1) * 4, ctx->stream));
-    SK_CUDA(cudaMallocAsync((void**)&set->pv_pos, std::max<size_t>(S, 1) * 4, ctx->stream));
-    SK_CUDA(cudaMallocAsync((void**)&set->pv_cc, std::max<size_t>(S, 1) * 4, ctx->stream));
-    SK_CUDA(mkv.alloc(S, st));
+    SK_CUDA(ctx->arena.alloc((void**)&set->pv_kmer, std::max<size_t>(S, 1) * 4));
+    SK_CUDA(ctx->arena.alloc((void**)&set->pv_pos, std::max<size_t>(S, 1) * 4));
+    SK_CUDA(ctx->arena.alloc((void**)&set->pv_cc, std::max<size_t>(S, 1) * 4));
+    SK_CUDA(mkv.alloc(S, ctx));
     SK_LAUNCH(ctx, "expand_kernel", (expand_kernel<<<div_up(NU, 256), 256, 0, st>>>(
         P.p, ucontig.p, d_cuoff.p, d_clocal.p, NU, PM.p, uoff.p, seed_mask, thr_m, set->pv_kmer, set->pv_pos, set->pv_cc, mkv.p)));
     SK_CUDA(cudaStreamSynchronize(st));
@@ -534,18 +533,18 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     // raw markers: compact the flagged values (order inside a genome is irrelevant: they are sorted + deduped next)
     if (S > 0) {
       DTmp<uint32_t> mflag, mscan;
-      SK_CUDA(mflag.alloc(S, st)); SK_CUDA(mscan.alloc(S, st));
+      SK_CUDA(mflag.alloc(S, ctx)); SK_CUDA(mscan.alloc(S, ctx));
       marker_flag_kernel<<<div_up(S, 256), 256, 0, st>>>(mkv.p, S, mflag.p); count_launch(ctx);
       SK_TRY(scan_exclusive<uint32_t>(ctx, mflag.p, mscan.p, S));
       uint32_t lf = 0, ls = 0;
       SK_CUDA(cudaMemcpyAsync(&lf, mflag.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
       SK_CUDA(cudaMemcpyAsync(&ls, mscan.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
       DTmp<uint64_t> d_so, d_mo;
-      SK_CUDA(d_so.alloc(G + 1, st)); SK_CUDA(d_mo.alloc(G + 1, st));
+      SK_CUDA(d_so.alloc(G + 1, ctx)); SK_CUDA(d_mo.alloc(G + 1, ctx));
       SK_CUDA(cudaMemcpyAsync(d_so.p, set->seed_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
       SK_CUDA(cudaStreamSynchronize(st));
       uint32_t MR = lf + ls;
-      SK_CUDA(mraw.alloc(MR, st));
+      SK_CUDA(mraw.alloc(MR, ctx));
       marker_scatter_kernel<<<div_up(S, 256), 256, 0, st>>>(mkv.p, mscan.p, S, mraw.p); count_launch(ctx);
       gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(mscan.p, d_so.p, G + 1, S, MR, d_mo.p); count_launch(ctx);
       SK_CUDA(cudaMemcpyAsync(raw_mk_off.data(), d_mo.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -553,7 +552,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     }
   } else {
     set->S = 0;
-    SK_CUDA(cudaMallocAsync((void**)&set->pv_kmer, 4, ctx->stream)); SK_CUDA(cudaMallocAsync((void**)&set->pv_pos, 4, ctx->stream)); SK_CUDA(cudaMallocAsync((void**)&set->pv_cc, 4, ctx->stream));
+    SK_CUDA(ctx->arena.alloc((void**)&set->pv_kmer, 4)); SK_CUDA(ctx->arena.alloc((void**)&set->pv_pos, 4)); SK_CUDA(ctx->arena.alloc((void**)&set->pv_cc, 4));
     SK_CUDA(cudaMemsetAsync(set->ctg_rec_off, 0, (size_t)(n_contigs + G + 1) * 4, st));
   }
   // free the big per-base temporaries before the sort temporaries are allocated

@@ -5,12 +5,30 @@
 
 #include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/skani_b200.h"
 
+// Context-owned device arena: every sketch-set array and every temporary of this library is sub-allocated from a few
+// large cudaMalloc'd slabs with host-side first-fit bookkeeping.  All users run on the context's single stream, so a
+// block may be handed out again as soon as the host has released it (stream order serialises the accesses).  This keeps
+// the steady state free of driver allocation calls: cudaMallocAsync's pool showed multi-100 ms stalls when multi-GB
+// blocks of changing size were recycled (profiles/r01_pipeline_trace.txt).
+struct SkArena {
+  struct Slab { uint8_t* base; size_t size; std::map<size_t, size_t> free_blocks; };  // offset -> size
+  std::vector<Slab> slabs;
+  std::map<void*, std::pair<int, size_t>> live;   // ptr -> (slab, size)
+  std::mutex mu;
+  size_t total = 0;
+  cudaError_t alloc(void** out, size_t bytes);
+  void release(void* p);
+  void destroy();
+};
+
 struct sk_ctx {
+  SkArena arena;
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
@@ -92,29 +110,28 @@ struct sk_sketch_set {
     if (rc__ != SK_OK) return rc__; \
   } while (0)
 
-// stream-ordered temporary allocation
+// temporary device allocation from the context's arena (released at scope exit)
 template <typename T>
 struct DTmp {
   T* p = nullptr;
   size_t n = 0;
-  cudaStream_t s = nullptr;
+  sk_ctx* c = nullptr;
   DTmp() {}
   DTmp(const DTmp&) = delete;
   DTmp& operator=(const DTmp&) = delete;
   ~DTmp() { release(); }
-  cudaError_t alloc(size_t count, cudaStream_t stream) {
+  cudaError_t alloc(size_t count, sk_ctx* ctx) {
     release();
-    s = stream;
+    c = ctx;
     n = count;
     if (count == 0) count = 1;
-    return cudaMallocAsync((void**)&p, count * sizeof(T), stream);
+    return ctx->arena.alloc((void**)&p, count * sizeof(T));
   }
   void release() {
-    if (p) cudaFreeAsync(p, s);
+    if (p) c->arena.release(p);
     p = nullptr;
     n = 0;
   }
-  T* take() { T* r = p; p = nullptr; return r; }  // ownership moves to the caller (free with cudaFreeAsync/cudaFree)
 };
 
 namespace sk {

@@ -101,9 +101,9 @@ class SketchSet:
         self.ctx.check(self.ctx.L.sk_sketch_set_append(self.h, other.h))
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:      # the set's storage lives in its context's arena
             self.ctx.L.sk_sketch_set_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

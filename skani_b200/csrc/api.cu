@@ -66,6 +66,35 @@ void SkArena::destroy() {
   slabs.clear(); live.clear(); total = 0;
 }
 
+namespace sk {
+__global__ void stage_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n_words) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_words) dst[i] = src[i];
+}
+// host -> device upload of a small parameter block, ordered on ctx->stream, without touching the H2D copy engine
+cudaError_t h2d_small(sk_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  const size_t CAP = 64ull << 20;
+  if ((bytes & 3) || ((uintptr_t)dst & 3) || bytes > CAP / 4) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (!ctx->stage) {
+    cudaError_t e = cudaHostAlloc((void**)&ctx->stage, CAP, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) return e;
+    ctx->stage_cap = CAP; ctx->stage_pos = 0;
+  }
+  size_t pos = (ctx->stage_pos + 15) & ~(size_t)15;
+  if (pos + bytes > ctx->stage_cap) {          // ring wrap: everything queued so far must have been consumed
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return e;
+    pos = 0;
+  }
+  memcpy(ctx->stage + pos, src, bytes);
+  const size_t nw = bytes / 4;
+  stage_copy_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, ctx->stream>>>((uint32_t*)dst, (const uint32_t*)(ctx->stage + pos), nw);
+  ctx->stage_pos = pos + bytes;
+  return cudaGetLastError();
+}
+}  // namespace sk
+
 namespace {
 constexpr size_t SUBBATCH_MAX = 2048ull << 20;  // bases per seeding sub-batch: bounds the per-base temporaries ...
 constexpr size_t SUBBATCH_MIN = 256ull << 20;   // ... while keeping >= ~8 sub-batches so H2D copies overlap the kernels
@@ -183,6 +212,7 @@ int sk_ctx_destroy(sk_ctx* ctx) {
   if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
   for (int i = 0; i < 2; i++) if (ctx->dbuf[i]) cudaFree(ctx->dbuf[i]);
   ctx->arena.destroy();
+  if (ctx->stage) cudaFreeHost(ctx->stage);
   for (int i = 0; i < 2; i++) {
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
     if (ctx->pinned_free[i]) cudaEventDestroy(ctx->pinned_free[i]);
@@ -623,7 +653,7 @@ int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t
   SK_CUDA(cudaMemcpy(s->ctg_rec_off, crl.data(), (size_t)(n_contigs + 1) * 4, cudaMemcpyHostToDevice));
   DTmp<uint64_t> mraw;
   SK_CUDA(mraw.alloc(n_markers, ctx));
-  if (n_markers) SK_CUDA(cudaMemcpyAsync(mraw.p, markers, n_markers * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_markers) SK_CUDA(cudaMemcpyAsync(mraw.p, markers, n_markers * 8, cudaMemcpyHostToDevice, ctx->stream));  // bulk
   std::vector<uint64_t> raw_off = {0, n_markers};
   SK_TRY(build_views(ctx, s, mraw.p, raw_off));
   SK_TRY(build_hash(ctx, s));

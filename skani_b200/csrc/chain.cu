@@ -1195,7 +1195,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   ENS(ctab_p0, c_ctab_p0, std::max<uint64_t>(total_ctab, 1)); ENS(ctab_a0, c_ctab_a0, std::max<uint64_t>(total_ctab, 1));
   SK_TRY(ensure(ctx, &S.d_pairs, &S.c_pairs, B));
   SK_TRY(ensure(ctx, &S.d_out, &S.c_out, B));
-  SK_CUDA(cudaMemcpyAsync(S.d_pairs, descs.data() + b0, B * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+  SK_CUDA(h2d_small(ctx, S.d_pairs, descs.data() + b0, B * sizeof(PairDesc)));
   SK_CUDA(cudaMemsetAsync(ws.pair_nint, 0, B * 4, st));
   SK_CUDA(cudaMemsetAsync(ws.pair_sumlen, 0, B * 4, st));
   SK_CUDA(cudaMemsetAsync(ws.pair_nchains, 0, B * 4, st));
@@ -1216,9 +1216,9 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
     ibase[i + 1] = ibase[i] + hA[i] / 3;   // every chain interval owns >= 3 distinct anchors
   }
   const uint64_t TA = abase[B], TC = cbase[B], TI = ibase[B];
-  SK_CUDA(cudaMemcpyAsync(ws.pairAbase, abase.data(), (B + 1) * 8, cudaMemcpyHostToDevice, st));
-  SK_CUDA(cudaMemcpyAsync(ws.pairCbase, cbase.data(), (B + 1) * 8, cudaMemcpyHostToDevice, st));
-  SK_CUDA(cudaMemcpyAsync(ws.pairIbase, ibase.data(), (B + 1) * 8, cudaMemcpyHostToDevice, st));
+  SK_CUDA(h2d_small(ctx, ws.pairAbase, abase.data(), (B + 1) * 8));
+  SK_CUDA(h2d_small(ctx, ws.pairCbase, cbase.data(), (B + 1) * 8));
+  SK_CUDA(h2d_small(ctx, ws.pairIbase, ibase.data(), (B + 1) * 8));
   const size_t NA = std::max<uint64_t>(TA, 1), NCH = std::max<uint64_t>(TC, 1), NI = std::max<uint64_t>(TI, 1);
   ENS(anc, c_anc, NA); ENS(score, c_score, dbg ? NA : 1); ENS(ptr, c_ptr, dbg ? NA : 1); ENS(rootkey, c_rootkey, NA); ENS(depth, c_depth, NA);
   ENS(chunk_first, c_chunk_first, NCH + 1); ENS(chunk_pair, c_chunk_pair, NCH); ENS(chunk_qctg, c_chunk_qctg, NCH);
@@ -1229,7 +1229,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   ENS(est_sorted, c_est_sorted, 4 * NCH + 8); ENS(w_sorted, c_w_sorted, 4 * NCH + 8);
 #undef ENS
   if (TC > 0) {
-    SK_CUDA(cudaMemcpyAsync(ws.chunk_first + TC, &TA, 8, cudaMemcpyHostToDevice, st));
+    SK_CUDA(h2d_small(ctx, ws.chunk_first + TC, &TA, 8));
     init_chunk_acc_kernel<<<(uint32_t)((TC + 255) / 256), 256, 0, st>>>(TC, ws); count_launch(ctx);
     SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
     {
@@ -1355,8 +1355,8 @@ static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_se
   build_meta(qs, m1);
   SK_TRY(ensure(ctx, &S.d_m0, &S.c_m0, m0.size()));
   SK_TRY(ensure(ctx, &S.d_m1, &S.c_m1, m1.size()));
-  SK_CUDA(cudaMemcpyAsync(S.d_m0, m0.data(), m0.size() * sizeof(GenomeMeta), cudaMemcpyHostToDevice, st));
-  SK_CUDA(cudaMemcpyAsync(S.d_m1, m1.data(), m1.size() * sizeof(GenomeMeta), cudaMemcpyHostToDevice, st));
+  SK_CUDA(h2d_small(ctx, S.d_m0, m0.data(), m0.size() * sizeof(GenomeMeta)));
+  SK_CUDA(h2d_small(ctx, S.d_m1, m1.data(), m1.size() * sizeof(GenomeMeta)));
   const SetView v0 = view_of(refs), v1 = view_of(qs);
   // pair descriptors
   std::vector<PairDesc> descs(n_pairs);

@@ -182,8 +182,8 @@ static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_se
 
   DTmp<uint64_t> d_row_off, d_col_off;
   SK_CUDA(d_row_off.alloc(NR + 1, ctx)); SK_CUDA(d_col_off.alloc(NC + 1, ctx));
-  SK_CUDA(cudaMemcpyAsync(d_row_off.p, rows->mk_off.data(), (NR + 1) * 8, cudaMemcpyHostToDevice, st));
-  SK_CUDA(cudaMemcpyAsync(d_col_off.p, cols->mk_off.data(), (NC + 1) * 8, cudaMemcpyHostToDevice, st));
+  SK_CUDA(h2d_small(ctx, d_row_off.p, rows->mk_off.data(), (NR + 1) * 8));
+  SK_CUDA(h2d_small(ctx, d_col_off.p, cols->mk_off.data(), (NC + 1) * 8));
   DTmp<uint32_t> ra, rb, scol;
   const size_t n_row_entries = tri ? Mc : Mr;
   SK_CUDA(ra.alloc(n_row_entries, ctx)); SK_CUDA(rb.alloc(n_row_entries, ctx)); SK_CUDA(scol.alloc(N, ctx));

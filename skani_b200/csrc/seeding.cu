@@ -319,7 +319,7 @@ int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
   if (need_bucket) {
     DTmp<uint64_t> d_uk2;
     SK_CUDA(d_uk2.alloc(G + 1, ctx));
-    SK_CUDA(cudaMemcpyAsync(d_uk2.p, set->uk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+    SK_CUDA(h2d_small(ctx, d_uk2.p, set->uk_off.data(), (G + 1) * 8));
     SK_CUDA(ctx->arena.alloc((void**)&set->ubucket, (size_t)G * (UBUCKETS + 1) * 4));
     const uint32_t kbits = 2 * set->sp.k;
     const uint32_t shift = kbits > UBUCKET_BITS ? kbits - UBUCKET_BITS : 0;
@@ -330,8 +330,8 @@ int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
   SK_CUDA(cudaMemsetAsync(set->htab, 0, total * 8, st));
   DTmp<uint64_t> d_uk, d_ht;
   SK_CUDA(d_uk.alloc(G + 1, ctx)); SK_CUDA(d_ht.alloc(G + 1, ctx));
-  SK_CUDA(cudaMemcpyAsync(d_uk.p, set->uk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
-  SK_CUDA(cudaMemcpyAsync(d_ht.p, set->ht_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  SK_CUDA(h2d_small(ctx, d_uk.p, set->uk_off.data(), (G + 1) * 8));
+  SK_CUDA(h2d_small(ctx, d_ht.p, set->ht_off.data(), (G + 1) * 8));
   hash_build_kernel<<<dim3(G, 8), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab); count_launch(ctx);
   SK_CUDA(cudaStreamSynchronize(st));
   return SK_OK;
@@ -345,7 +345,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
   cudaStream_t st = ctx->stream;
   DTmp<uint64_t> d_seed_off, d_rawmk_off;
   SK_CUDA(d_seed_off.alloc(G + 1, ctx));
-  SK_CUDA(cudaMemcpyAsync(d_seed_off.p, set->seed_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  SK_CUDA(h2d_small(ctx, d_seed_off.p, set->seed_off.data(), (G + 1) * 8));
   SK_CUDA(ctx->arena.alloc((void**)&set->kv_pos, std::max<size_t>(S, 1) * 4));
   SK_CUDA(ctx->arena.alloc((void**)&set->kv_cc, std::max<size_t>(S, 1) * 4));
   SK_CUDA(ctx->arena.alloc((void**)&set->pv_mult, std::max<size_t>(S, 1) * 2));
@@ -395,7 +395,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
   if (MR > 0) {
     if (MR >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 markers"; return SK_ERR_PARAM; }
     SK_CUDA(d_rawmk_off.alloc(G + 1, ctx));
-    SK_CUDA(cudaMemcpyAsync(d_rawmk_off.p, raw_mk_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+    SK_CUDA(h2d_small(ctx, d_rawmk_off.p, raw_mk_off.data(), (G + 1) * 8));
     DTmp<uint64_t> sorted;
     SK_CUDA(sorted.alloc(MR, ctx));
     size_t tb = 0;
@@ -484,11 +484,11 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
   if (NU > 0) {
     SK_CUDA(d_coff.alloc(n_contigs + 1, ctx)); SK_CUDA(d_cuoff.alloc(n_contigs + 1, ctx));
     SK_CUDA(d_clen.alloc(n_contigs, ctx)); SK_CUDA(d_clocal.alloc(n_contigs, ctx));
-    SK_CUDA(cudaMemcpyAsync(d_coff.p, coff.data(), (n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
-    SK_CUDA(cudaMemcpyAsync(d_cuoff.p, cuoff.data(), (n_contigs + 1) * 4, cudaMemcpyHostToDevice, st));
-    SK_CUDA(cudaMemcpyAsync(d_clen.p, clen.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
-    SK_CUDA(cudaMemcpyAsync(d_clocal.p, clocal.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
-    SK_CUDA(cudaMemcpyAsync(set->d_ctg_len, clen.data(), n_contigs * 4, cudaMemcpyHostToDevice, st));
+    SK_CUDA(h2d_small(ctx, d_coff.p, coff.data(), (n_contigs + 1) * 8));
+    SK_CUDA(h2d_small(ctx, d_cuoff.p, cuoff.data(), (n_contigs + 1) * 4));
+    SK_CUDA(h2d_small(ctx, d_clen.p, clen.data(), n_contigs * 4));
+    SK_CUDA(h2d_small(ctx, d_clocal.p, clocal.data(), n_contigs * 4));
+    SK_CUDA(h2d_small(ctx, set->d_ctg_len, clen.data(), n_contigs * 4));
     SK_CUDA(P.alloc(NU, ctx)); SK_CUDA(NM.alloc(NU, ctx)); SK_CUDA(ucontig.alloc(NU, ctx));
     SK_CUDA(PM.alloc(NU, ctx)); SK_CUDA(cnt.alloc(NU, ctx)); SK_CUDA(uoff.alloc(NU, ctx));
 
@@ -529,7 +529,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
       crl[c1 + g] = endrec - base;
     }
     set->seed_off[G] = S;
-    SK_CUDA(cudaMemcpyAsync(set->ctg_rec_off, crl.data(), (size_t)(n_contigs + G) * 4, cudaMemcpyHostToDevice, st));
+    SK_CUDA(h2d_small(ctx, set->ctg_rec_off, crl.data(), (size_t)(n_contigs + G) * 4));
     // raw markers: compact the flagged values (order inside a genome is irrelevant: they are sorted + deduped next)
     if (S > 0) {
       DTmp<uint32_t> mflag, mscan;
@@ -541,7 +541,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
       SK_CUDA(cudaMemcpyAsync(&ls, mscan.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
       DTmp<uint64_t> d_so, d_mo;
       SK_CUDA(d_so.alloc(G + 1, ctx)); SK_CUDA(d_mo.alloc(G + 1, ctx));
-      SK_CUDA(cudaMemcpyAsync(d_so.p, set->seed_off.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+      SK_CUDA(h2d_small(ctx, d_so.p, set->seed_off.data(), (G + 1) * 8));
       SK_CUDA(cudaStreamSynchronize(st));
       uint32_t MR = lf + ls;
       SK_CUDA(mraw.alloc(MR, ctx));

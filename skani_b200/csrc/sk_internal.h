@@ -42,6 +42,10 @@ struct sk_ctx {
   cudaEvent_t h2d_done[2] = {nullptr, nullptr};
   uint8_t* dbuf[2] = {nullptr, nullptr};  // device staging double buffer (sk_sketch_batch)
   size_t dbuf_bytes = 0;
+  // small host->device parameter uploads go through a pinned, device-mapped ring + a copy kernel on the context's
+  // stream instead of the H2D copy engine, which may be busy for tens of ms with bulk sequence uploads
+  uint8_t* stage = nullptr;
+  size_t stage_cap = 0, stage_pos = 0;
   sk_ctx* child = nullptr;               // worker context of the pipelined sk_triangle (second stream + own workspaces)
   // grow-only chaining workspace (chain.cu), kept for the life of the context
   void* chain_scratch = nullptr;
@@ -150,4 +154,5 @@ int sketch_batch_host(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_
 int merge_sets(sk_ctx* ctx, const sk_sketch_set* base, const std::vector<sk_sketch_set*>& parts, sk_sketch_set** out);  // (re)builds set->htab from ukmer/ustart; call on every finished set
 // screen.cu / chain.cu
 uint64_t count_launch(sk_ctx* ctx, uint64_t n = 1);
+cudaError_t h2d_small(sk_ctx* ctx, void* dst, const void* src, size_t bytes);  // api.cu
 }  // namespace sk

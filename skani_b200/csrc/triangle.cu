@@ -59,11 +59,12 @@ extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* co
   std::vector<sk_ani_result> kept;
   uint64_t n_screened = 0;
   const uint64_t total_bytes = n_contigs ? contig_off[n_contigs] - contig_off[0] : 0;
-  // The upload/seed || screen/chain pipeline is EXPERIMENTAL and off by default (SK_PIPELINE=1 or SK_FORCE_PIPELINE=1 enable
-  // it): it hides chaining under the PCIe transfer, but the stream-ordered allocator's handling of the varying multi-GB
-  // set sizes made its timing erratic on B200 (profiles/r01_pipeline_trace.txt); see DESIGN.md section 9.
-  const bool pipelined = ((getenv("SK_PIPELINE") && total_bytes >= (4ull << 30) && n_genomes >= 64) ||
-                          (getenv("SK_FORCE_PIPELINE") && n_genomes >= 2)) && getenv("SK_NO_PIPELINE") == nullptr;
+  // Inputs of >= 4 GiB use the upload/seed || merge/screen/chain pipeline (SK_NO_PIPELINE=1 disables it, SK_FORCE_PIPELINE=1
+  // forces it for small inputs in tests).  Two things made it work: the context arena (no driver allocations in steady
+  // state) and h2d_small (parameter uploads bypass the H2D copy engine that is saturated by the sequence upload);
+  // see profiles/r01_pipeline_trace.txt.
+  const bool pipelined = ((total_bytes >= (4ull << 30) && n_genomes >= 64) || (getenv("SK_FORCE_PIPELINE") && n_genomes >= 2)) &&
+                         getenv("SK_NO_PIPELINE") == nullptr;
   if (!pipelined) {
     SK_TRY(simple_triangle(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, kept, &n_screened));
   } else {

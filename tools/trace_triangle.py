@@ -13,11 +13,11 @@ host = pinned.numpy()
 synth.generate(0, n, L, out=host)
 off, goc = synth.layout(0, n, L)
 ctx = sk.Context(0)
-for mode in ("SK_NO_PIPELINE", None, "SK_NO_PIPELINE", None):
+for mode in ("SK_NO_PIPELINE", None, None, "SK_NO_PIPELINE", None):
     os.environ.pop("SK_NO_PIPELINE", None)
     if mode:
         os.environ[mode] = "1"
-    os.environ["SK_TRACE"] = "1"
+    os.environ["SK_TRACE"] = "1"; os.environ["SK_PIPELINE"] = "1"
     t0 = time.perf_counter()
     res, st = sk.triangle(ctx, host, off, goc, n, as_array=True)
     print("mode=%s  %.1f ms  kept=%d" % (mode or "pipelined", (time.perf_counter() - t0) * 1e3, len(res)), flush=True)

@@ -307,7 +307,11 @@ def measure_hashpass(ctx, stream, dev_bases, off, goc, nloc, sp, L):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = genomes_per_launch * bytes_per_genome / sec_per_launch / 1e9
     stage_ms = sum(v[0] for v in t.values())
-    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # DRAM traffic per genome of this kernel from the committed ncu --set full capture (profiles/r01_ncu_full_top5.md:
+    # dram__bytes_read 250.05 MB + dram__bytes_write 98.18 MB for a 100-genome launch), scaled to this launch size
+    traffic = (250.05184e6 + 98.18496e6) / 100.0 * genomes_per_launch
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_full_top5.md, per genome x genomes_per_launch",
             "kernel": "hashpass_kernel", "launch_ms": sec_per_launch * 1e3, "genomes_per_launch": genomes_per_launch,
             "algorithmic_bytes_per_genome": bytes_per_genome,
             "gbases_per_s": genomes_per_launch * L / sec_per_launch / 1e9,

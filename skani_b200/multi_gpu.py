@@ -4,7 +4,8 @@ The reference is a single process (rayon threads); the pair loop of src/triangle
   1. every rank sketches a contiguous block of genomes (seeding is independent per genome);
   2. ONE exchange step: the ranks' sketch blocks are all-gathered (NCCL over NVLink/NVSwitch) so every GPU holds all
      N sketches in rank-major = global genome order (10k genomes ~ 12 GB; 4.4 GB of seeds + views);
-  3. rows i with i % world == rank are screened and chained locally, no further communication;
+  3. every rank screens the triangle (cheap) and chains every world-th passing pair, no further communication
+     (sk_screen_triangle_rows offers a row-cyclic partition of the screen itself for sets where screening dominates);
   4. results stay on their rank (the reference's sparse output order is nondeterministic anyway).
 """
 import ctypes as C
@@ -22,6 +23,11 @@ def shard_range(n_items, world, rank):
 def rows_of_rank(n_rows, world, rank):
     """Row-cyclic partition of the triangle's rows (row i has N-1-i columns: cyclic interleave balances to < 1/N)."""
     return range(rank, n_rows, world)
+
+
+def pairs_of_rank(sorted_pairs, world, rank):
+    """Cyclic split of the sorted passing-pair list: every rank gets the same number of pairs (+-1)."""
+    return np.ascontiguousarray(sorted_pairs[rank::world])
 
 
 def gather_variable(dist, local, world, device):
@@ -73,19 +79,29 @@ class DistTriangle:
 
     def step(self, host_bases, dev_ptr, off, goc, nloc, g0, n_total):
         """One whole triangle over all ranks; returns this rank's number of kept pairs."""
+        import os
+        import time
         ctx, L = self.ctx, self.ctx.L
+        trace = os.environ.get("SK_TRACE") and self.rank == 0
+        t0 = time.perf_counter()
         if host_bases is not None:
             local = H.sketch_contigs(ctx, host_bases, off, goc, nloc, self.sp)
         else:
             local = H.sketch_contigs(ctx, None, off, goc, nloc, self.sp, device_ptr=dev_ptr)
+        t1 = time.perf_counter()
         allset = self.exchange(local)
         local.free()
         assert len(allset) == n_total
-        pp = C.POINTER(C.c_uint64)(); n = C.c_uint64()
-        ctx.check(L.sk_screen_triangle_rows(ctx.h, allset.h, C.byref(self.mp), self.world, self.rank, C.byref(pp), C.byref(n)))
-        pairs = np.ctypeslib.as_array(pp, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
-        L.sk_free(pp)
+        t2 = time.perf_counter()
+        # every rank screens the whole triangle (a few ms: one sort of all markers) and takes every world-th passing pair of
+        # the sorted list: an even split of the CHAINING work, which a row partition does not give when related genomes are
+        # adjacent (rows i mod 8 of a 20-genome cluster carry 33 vs 16 pairs)
+        pairs = pairs_of_rank(H.screen_triangle(ctx, allset, self.mp), self.world, self.rank)
+        t3 = time.perf_counter()
         res = H.chain_pairs(ctx, allset, allset, pairs, self.mp, as_array=True)
         allset.free()
+        if trace:
+            print("[multi_gpu rank0] sketch %.1f ms  exchange %.1f ms  screen %.1f ms  chain %.1f ms (%d pairs)" %
+                  ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (time.perf_counter() - t3) * 1e3, len(pairs)), flush=True)
         self.last_results = res[res["ani"] > 0.1]               # src/triangle.rs:99 (numpy structured array)
         return len(self.last_results)

@@ -15,7 +15,11 @@ sys.path.insert(0, ROOT)
 
 
 def test_partitions_cover_everything():
-    from skani_b200.multi_gpu import shard_range, rows_of_rank
+    from skani_b200.multi_gpu import shard_range, rows_of_rank, pairs_of_rank
+    import numpy as np
+    pl = np.arange(95000, dtype=np.uint64)
+    parts = [pairs_of_rank(pl, 8, r) for r in range(8)]
+    assert sorted(np.concatenate(parts).tolist()) == pl.tolist() and max(map(len, parts)) - min(map(len, parts)) <= 1
     for n in (0, 1, 7, 10000):
         for world in (1, 2, 4, 8):
             blocks = [shard_range(n, world, r) for r in range(world)]

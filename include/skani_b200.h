@@ -141,9 +141,10 @@ void sk_free(void* p);
 /* ---- chaining: replaces chain::map_params_from_sketch + chain::chain_seeds (src/chain.rs:88, 144) and
  *      regression::get_model / predict_from_ani_res (src/regression.rs:12, 30) for every listed pair ---------
  * pairs[i] = (ref_index << 32) | query_index; out[i] is the AniEstResult of chain_seeds(refs[ref], queries[query]).
- * file-name tie-break of switch_qr (src/chain.rs:19-21) uses genome order: name(x) > name(y) iff its
- * `name_rank` is larger; by default rank = index in the set (sets built in sorted file order, src/file_io.rs:250);
- * for two different sets the query set ranks after the ref set unless sk_sketch_set_set_name_ranks is used. */
+ * file-name tie-break of switch_qr (src/chain.rs:19-21): name(x) > name(y) iff its `name_rank` is larger, equal ranks =
+ * equal file names.  Default rank = index in the set (one file per sketch, sets built in sorted file order,
+ * src/file_io.rs:250); callers sketching individual records (-i / --qi / --ri) MUST give the records of one file equal
+ * ranks with sk_sketch_set_set_name_ranks; for two different sets the query set ranks after the ref set by default. */
 int sk_chain_pairs(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_set* queries, const uint64_t* pairs,
                    uint64_t n_pairs, const sk_map_params* mp, sk_ani_result* out);
 int sk_sketch_set_set_name_ranks(sk_sketch_set* set, const uint64_t* ranks /* n_genomes */);

@@ -247,6 +247,15 @@ int run_triangle(Opts& op) {
   mp.learned_ani = !op.no_learned && op.c >= 70 && !op.individual && !op.median;   // regression::use_learned_ani (src/regression.rs:8-10)
   if (mp.learned_ani) fprintf(stderr, "INFO Learned ANI mode detected. ANI may be adjusted according to a regression model trained on MAGs.\n");
   sk_sketch_set* set = sketch(ctx, in, sp);
+  {  // file-name order for the switch_qr tie-break (src/chain.rs:19-21): with -i all records of a file share its name
+    std::vector<uint64_t> ranks(in.genomes.size());
+    uint64_t rank = 0;
+    for (size_t i = 0; i < in.genomes.size(); i++) {
+      if (i && in.genomes[i].file_name != in.genomes[i - 1].file_name) rank++;
+      ranks[i] = rank;
+    }
+    sk_sketch_set_set_name_ranks(set, ranks.data());
+  }
   uint64_t* pairs = nullptr; uint64_t np = 0;
   CK(ctx, sk_screen_triangle(ctx, set, &mp, &pairs, &np));
   std::vector<sk_ani_result> res(np);

@@ -97,6 +97,13 @@ class SketchSet:
                                                        mk.ctypes.data, cl.ctypes.data))
         return dict(kmer=kmer, pos=pos, cc=cc, markers=mk, contig_lengths=cl)
 
+    def set_name_ranks(self, ranks):
+        """Order of the sketches' FILE names (equal names -> equal ranks): the tie-break of switch_qr
+        (reference src/chain.rs:19-21) compares file names, and with -i / --qi / --ri all records of one file share a name."""
+        r = np.ascontiguousarray(ranks, np.uint64)
+        assert len(r) == len(self)
+        self.ctx.check(self.ctx.L.sk_sketch_set_set_name_ranks(self.h, r.ctypes.data))
+
     def append(self, other):
         self.ctx.check(self.ctx.L.sk_sketch_set_append(self.h, other.h))
 
@@ -160,6 +167,8 @@ def sketch_sequences(ctx, genomes, sp=None, individual_contig=False):
     bases = np.concatenate(arrs) if arrs else np.zeros(1, np.uint8)
     s = sketch_contigs(ctx, bases, off, goc, g, sp)
     s.names = kept_genomes
+    if individual_contig and g:
+        s.set_name_ranks([gi for gi, _ in kept_genomes])   # records of one file share its name
     return s
 
 

@@ -113,6 +113,20 @@ def cpu_triangle_sample(n_sample, L, G, threads):
                 t_screen=info["t_screen"], t_chain=info["t_chain"])
 
 
+def cpu_single_thread(L, G):
+    """Per-thread rates of the oracle (1 thread): ms per genome seeded, ms per chained pair."""
+    import oracle_py as O
+    from bench_support import synth
+    n = min(G, 8)
+    bases, off, goc = synth.generate(0, n, L, G=G, threads=1)
+    t0 = time.perf_counter()
+    sk = [O.sketch_from_contigs("g%06d" % g, [bases[int(off[i]):int(off[i + 1])] for i in np.nonzero(goc == g)[0]]) for g in range(n)]
+    t1 = time.perf_counter()
+    res, info = O.triangle(sk, O.cmd(), threads=1)
+    t2 = time.perf_counter()
+    return {"seed_ms_per_genome": (t1 - t0) * 1e3 / n, "chain_ms_per_pair": (t2 - t1) * 1e3 / max(info["n_chained"], 1)}
+
+
 def cpu_baseline(args, threads):
     S = min(args.cpu_sample, args.genomes)
     S = max(args.cluster, (S // args.cluster) * args.cluster)
@@ -120,7 +134,8 @@ def cpu_baseline(args, threads):
     N = args.genomes
     t_full = d["t_total"] * (N / S)   # every stage is linear in N for the clustered set (fixed cluster size)
     value = (N * (N - 1) / 2) / t_full
-    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+    one = cpu_single_thread(args.genome_len, args.cluster)
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "single_thread": one,
             "sample": "oracle (C++ restatement of skani 0.3.0; Rust reference not buildable here) triangle on %d of the %d genomes "
                       "(%d clusters): %.2f s (seeding %.2f s, screen+chain %.2f s, %d chained pairs) scaled x%.1f to the full set "
                       "(all stages linear in N at fixed cluster size)" % (S, N, S // args.cluster, d["t_total"], d["t_seed"],

@@ -436,14 +436,12 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
       bytes += gb;
       c1 = c2;
     }
-    uint32_t g_last = genome_of_contig[c1 - 1];
     uint32_t g_next = (c1 < n_contigs) ? genome_of_contig[c1] : n_genomes;
     // genomes g0 .. g_next-1 belong to this part (empty genomes between are kept as empty sketches)
     uint32_t g_begin = parts.empty() ? 0 : g0;
     if (!parts.empty()) {
       // empty genomes skipped between the previous part and g0 were already attributed to the previous part
     }
-    (void)g_last;
     gl.resize(c1 - c0);
     for (uint32_t i = c0; i < c1; i++) gl[i - c0] = genome_of_contig[i] - g_begin;
     sk_sketch_set* part = nullptr;

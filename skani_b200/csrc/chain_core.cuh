@@ -68,63 +68,6 @@ SK_HD uint32_t chunk_local_of(uint64_t al, bool has_prev, int64_t m_prev, uint32
   return (uint32_t)(c < (int64_t)need ? c : (int64_t)need);
 }
 
-// ---- banded DP + chain extraction for ONE chunk (src/chain.rs:838-896 scoring :557-603, extraction :939-1007) ----
-// `a` = the chunk's anchors in sorted order; score/ptr/root/depth/cnt/best are n-element scratch arrays.
-// Emits one interval per surviving chain through `emit(score, num_anchors, first_idx, best_idx)`.
-SK_HD int32_t pair_score(const AnchorRec& cur, const AnchorRec& past) {  // score_anchors; INT32_MIN = f64::MIN (skip)
-  if ((cur.rc ^ past.rc) & 1u) return INT32_MIN;                          // reverse_match differs (:564)
-  if (cur.rpos == past.rpos || cur.qpos == past.qpos) return INT32_MIN;   // :567-570
-  int64_t dq = (int64_t)cur.qpos - (int64_t)past.qpos;
-  if (dq < 0) dq = -dq;
-  int64_t dr = (cur.rc & 1u) ? (int64_t)past.rpos - (int64_t)cur.rpos : (int64_t)cur.rpos - (int64_t)past.rpos;
-  if (dq > MAX_LIN || dr > MAX_LIN) return INT32_MIN;                     // :586-588
-  if (dr <= 0) return INT32_MIN;                                          // :590-592
-  int64_t gap = dr - dq;
-  if (gap < 0) gap = -gap;
-  if (gap > MAX_GAP) return INT32_MIN;                                    // :594-597
-  return ANCHOR_SCORE - (int32_t)gap;
-}
-
-template <typename Emit>
-SK_HD void dp_chunk(const AnchorRec* a, uint32_t n, uint32_t band, int32_t* score, uint32_t* ptr, uint32_t* root,
-                    uint32_t* depth, uint32_t* cnt, uint32_t* best, Emit emit) {
-  for (uint32_t i = 0; i < n; i++) {
-    const AnchorRec cur = a[i];
-    int32_t best_score = 0;
-    uint32_t best_prev = i;
-    for (uint32_t j = i; j-- > 0;) {
-      const AnchorRec past = a[j];
-      if ((cur.rc >> 1) != (past.rc >> 1)) continue;                          // other ref contig: skipped BEFORE the break test (:856-858)
-      if (cur.qpos - past.qpos > BP_CHAIN_BAND || i - j > band) break;        // :859-863
-      int32_t s = pair_score(cur, past);
-      if (s == INT32_MIN) continue;
-      int32_t ns = s + score[j];
-      if (ns > best_score) { best_score = ns; best_prev = j; }                // strict >: the largest j wins ties
-    }
-    score[i] = best_score;
-    ptr[i] = best_prev;
-    // union-find replaced by its closed form: component = tree under the pointer forest
-    if (best_prev == i) { root[i] = i; depth[i] = 1; cnt[i] = 1; best[i] = i; }
-    else {
-      uint32_t r = root[best_prev];
-      root[i] = r;
-      depth[i] = depth[best_prev] + 1;
-      cnt[r] += 1;
-      // best end of a chain = largest index among the maximal scores (PartitionVec iteration order root, newest..oldest
-      // with strict >, src/chain.rs:960-963): scanning i upward, >= keeps the latest
-      if (best_score >= score[best[r]]) best[r] = i;
-    }
-  }
-  for (uint32_t i = 0; i < n; i++) {
-    if (root[i] != i) continue;
-    if (cnt[i] < MIN_ANCHORS) continue;                                       // len_of_set < min_anchors (:954-957)
-    uint32_t b = best[i];
-    uint32_t num_anchors = depth[b];                                          // backtrack count (:969-973)
-    if (num_anchors < MIN_ANCHORS || score[b] < MIN_SCORE) continue;          // :974-977
-    emit(score[b], num_anchors, i, b);
-  }
-}
-
 // ---- chain intervals: 5 x u64 keys whose lexicographic order is the derived PartialOrd of ChainInterval
 // (score, num_anchors, interval_on_query, interval_on_ref, ref_contig, query_contig, chunk_id, reverse_chain, overlap=0)
 // src/types.rs:508-519.  Scores are small non-negative integers so the integer order equals the f64 order.

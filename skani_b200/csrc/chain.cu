@@ -90,6 +90,7 @@ struct Workspace {
   // per chunk
   uint64_t* chunk_first;   // batch-global anchor index (+ sentinel)
   uint32_t *chunk_pair, *chunk_qctg;
+  uint32_t *chunk_size, *chunk_size_sorted, *chunk_id, *chunk_perm;   // DP load balance: chunks sorted by size
   int64_t *chunk_lo, *chunk_hi;  // seeds of the chunk: lo < pos <= hi
   uint32_t *acc_total, *acc_rq0, *acc_rq1, *acc_tbcq, *acc_nint, *chunk_head;
   double* chunk_est;
@@ -649,6 +650,125 @@ dp_warp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K4b: the same DP with FOUR chunks per warp (8 lanes each), used when the band fits 3 candidates per lane (band <= 24,
+// i.e. c >= 105).  With band = 20 a full warp per chunk leaves 12 lanes idle and spends most of its issue slots on the
+// per-step bookkeeping; 8-lane groups evaluate 3 candidates per lane and amortise the bookkeeping over 4 anchors.
+// Lane gl of a group owns the anchors congruent to gl mod 8; register set s holds the anchor of block (current - s).
+// Group-wide arg-max = two 3-step xor-butterflies (max score, then largest j among the maxima).
+// ------------------------------------------------------------------------------------------------------------
+template <bool TAPS>
+__global__ void __launch_bounds__(32)
+dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
+  constexpr int NB = 4;                       // sets: current block + 3 earlier (covers band <= 24)
+  const unsigned FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x, gl = lane & 7u, gbase = lane & 24u;
+  const uint64_t slot = (uint64_t)blockIdx.x * 4 + (lane >> 3);
+  const bool live = slot < n_chunks;
+  const uint64_t c = live ? (uint64_t)ws.chunk_perm[slot] : 0;   // chunks sorted by size: the 4 chunks of a warp are alike
+  uint64_t a0 = 0;
+  uint32_t n = 0;
+  if (live) { a0 = ws.chunk_first[c]; n = (uint32_t)(ws.chunk_first[c + 1] - a0); }
+  const AnchorRec* __restrict__ a = ws.anc + a0;
+  unsigned long long* __restrict__ g_key = ws.rootkey + a0;
+  uint32_t* __restrict__ g_depth = ws.depth + a0;
+  const uint32_t band = prm.band;
+  // longest chunk of the warp bounds the common loop
+  uint32_t nmax = n;
+#pragma unroll
+  for (int o = 16; o >= 8; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+  uint32_t q[NB], r[NB], rc[NB], rt[NB], dpth[NB];
+  int32_t sc[NB];
+  uint32_t my_ptr = 0;
+#pragma unroll
+  for (int s = 0; s < NB; s++) { q[s] = r[s] = rc[s] = rt[s] = dpth[s] = 0; sc[s] = 0; }
+  for (uint32_t b0 = 0; b0 < nmax; b0 += 8) {
+#pragma unroll
+    for (int s = NB - 1; s > 0; s--) { q[s] = q[s - 1]; r[s] = r[s - 1]; rc[s] = rc[s - 1]; rt[s] = rt[s - 1]; dpth[s] = dpth[s - 1]; sc[s] = sc[s - 1]; }
+    const uint32_t idx = b0 + gl;
+    {
+      AnchorRec x; x.qpos = 0; x.rpos = 0; x.rc = 0xFFFFFFFEu;            // impossible contig: never matches
+      if (idx < n) { x = a[idx]; g_key[idx] = (unsigned long long)idx; }
+      q[0] = x.qpos; r[0] = x.rpos; rc[0] = x.rc; sc[0] = 0; rt[0] = idx; dpth[0] = 1;
+      my_ptr = idx;
+    }
+    __syncwarp();
+#pragma unroll
+    for (uint32_t m = 0; m < 8; m++) {
+      const uint32_t i = b0 + m;
+      const uint32_t src = gbase | m;
+      AnchorRec cur;
+      cur.qpos = __shfl_sync(FULL, q[0], src);
+      cur.rpos = __shfl_sync(FULL, r[0], src);
+      cur.rc = __shfl_sync(FULL, rc[0], src);
+      const bool active = i < n;                                           // uniform inside a group
+      int32_t best_ns = 0;
+      uint32_t best_d = 0;                                                 // i - j of the lane's best candidate (0 = none)
+      const bool lo_set = gl < m;
+#pragma unroll
+      for (int t = 0; t < NB - 1; t++) {                                   // ascending t = descending j: strict > keeps the largest j
+        const uint32_t qs = lo_set ? q[t] : q[t + 1];
+        const uint32_t rs = lo_set ? r[t] : r[t + 1];
+        const uint32_t rcs = lo_set ? rc[t] : rc[t + 1];
+        const int32_t scs = lo_set ? sc[t] : sc[t + 1];
+        const uint32_t d = m + 8u * (uint32_t)t + (lo_set ? 0u : 8u) - gl; // i - j >= 1
+        const uint32_t dq = cur.qpos - qs;
+        const uint32_t tr = cur.rpos - rs;
+        const uint32_t dr = (cur.rc & 1u) ? (0u - tr) : tr;
+        const uint32_t g = dr - dq;
+        const bool ok = active & (d <= band) & (d <= i) & (rcs == cur.rc) & (dq - 1u < BP_CHAIN_BAND) & (dr - 1u < (uint32_t)MAX_LIN) &
+                        (g + (uint32_t)MAX_GAP <= 2u * (uint32_t)MAX_GAP);
+        const int32_t gi = (int32_t)g;
+        const int32_t ns = scs + ANCHOR_SCORE - (gi < 0 ? -gi : gi);
+        if (ok && ns > best_ns) { best_ns = ns; best_d = d; }
+      }
+      // group arg-max: maximal score, then the smallest distance d (= largest j) among the maxima
+      int32_t smax = best_ns;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) smax = max(smax, __shfl_xor_sync(FULL, smax, o));
+      uint32_t dkey = (best_ns == smax && smax > 0) ? (64u - best_d) : 0u;   // d <= 31, so 64 - d > 0
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) dkey = max(dkey, __shfl_xor_sync(FULL, dkey, o));
+      const bool has = dkey != 0u;
+      const uint32_t dwin = 64u - dkey;
+      const uint32_t jw = i - dwin;                                          // only meaningful when has
+      // winner's root / depth: owner lane = jw mod 8, set = block distance
+      const int sidx = (int)(b0 >> 3) - (int)(jw >> 3);
+      uint32_t rsel = rt[0], dsel = dpth[0];
+#pragma unroll
+      for (int s = 1; s < NB; s++) if (sidx == s) { rsel = rt[s]; dsel = dpth[s]; }
+      const uint32_t wsrc = gbase | (jw & 7u);
+      const uint32_t root_w = __shfl_sync(FULL, rsel, wsrc);
+      const uint32_t depth_w = __shfl_sync(FULL, dsel, wsrc);
+      if (has && gl == m) { sc[0] = smax; rt[0] = root_w; dpth[0] = depth_w + 1; my_ptr = jw; }
+    }
+    if (idx < n) {
+      g_depth[idx] = dpth[0];
+      if (rt[0] != idx) atomicMax(&g_key[rt[0]], ((unsigned long long)(uint32_t)sc[0] << 32) | idx);
+      if (TAPS) { ws.score[a0 + idx] = sc[0]; ws.ptr[a0 + idx] = my_ptr; }
+    }
+  }
+  __threadfence_block();
+  __syncwarp();
+  if (!live) return;
+  const uint32_t p = ws.chunk_pair[c];
+  const uint32_t qctg = ws.chunk_qctg[c];
+  const uint32_t chunk_local_id = (uint32_t)(c - ws.pairCbase[p]);
+  for (uint32_t i = gl; i < n; i += 8) {
+    if (((volatile uint32_t*)g_depth)[i] != 1) continue;            // not a root
+    const unsigned long long key = ((volatile unsigned long long*)g_key)[i];
+    const uint32_t b = (uint32_t)key, score = (uint32_t)(key >> 32);
+    if (b == i) continue;                                            // singleton
+    const uint32_t num_anchors = ((volatile uint32_t*)g_depth)[b];
+    if (num_anchors < MIN_ANCHORS || (int32_t)score < MIN_SCORE) continue;
+    const AnchorRec f = a[i], l = a[b];
+    uint32_t r0 = f.rpos < l.rpos ? f.rpos : l.rpos, r1 = f.rpos < l.rpos ? l.rpos : f.rpos;
+    IntervalKey key5 = make_interval((int32_t)score, num_anchors, f.qpos, l.qpos, r0, r1, f.rc >> 1, qctg, chunk_local_id, f.rc & 1u);
+    uint32_t slot = atomicAdd(&ws.pair_nint[p], 1u);
+    ws.iv[ws.pairIbase[p] + slot] = key5;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K5: interval sort + greedy non-overlap selection, block per pair
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool interval_idx_before(uint32_t a, uint32_t b, unsigned long long ka, unsigned long long kb,
@@ -1050,6 +1170,13 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
   }
 }
 
+__global__ void chunk_size_kernel(uint64_t n, Workspace ws) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ws.chunk_size[i] = (uint32_t)(ws.chunk_first[i + 1] - ws.chunk_first[i]);
+  ws.chunk_id[i] = (uint32_t)i;
+}
+
 __global__ void init_chunk_acc_kernel(uint64_t n, Workspace ws) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1158,6 +1285,8 @@ struct ChainScratch {
   size_t c_pairA = 0, c_pairH = 0, c_pairC = 0, c_pairAbase = 0, c_pairCbase = 0, c_pairIbase = 0, c_pair_nint = 0, c_pair_sumlen = 0,
          c_pair_nchains = 0, c_pair_tqb = 0;
   size_t c_anc = 0, c_score = 0, c_ptr = 0, c_rootkey = 0, c_depth = 0;
+  size_t c_chunk_size = 0, c_chunk_size_sorted = 0, c_chunk_id = 0, c_chunk_perm = 0, c_sort_tmp = 0;
+  uint8_t* sort_tmp = nullptr;
   size_t c_chunk_first = 0, c_chunk_pair = 0, c_chunk_qctg = 0, c_chunk_lo = 0, c_chunk_hi = 0, c_acc_total = 0, c_acc_rq0 = 0,
          c_acc_rq1 = 0, c_acc_tbcq = 0, c_acc_nint = 0, c_chunk_head = 0, c_chunk_est = 0, c_chunk_w = 0, c_chunk_valid = 0, c_chunk_nseeds = 0;
   size_t c_iv = 0, c_iv_keys = 0, c_iv_order = 0, c_iv_kept = 0, c_iv_next = 0, c_acc_list = 0, c_est_sorted = 0, c_w_sorted = 0;
@@ -1166,7 +1295,7 @@ struct ChainScratch {
   GenomeMeta *d_m0 = nullptr, *d_m1 = nullptr;
   size_t c_m0 = 0, c_m1 = 0;
   void free_all() {
-    void* ptrs[] = {ws.ctab_p0, ws.ctab_a0, ws.pair_slow, ws.rec_rstart, ws.rec_nh, ws.hit_rec, ws.hit_aoff, ws.hit_clfirst, ws.hit_need, ws.hit_p0, ws.hit_cid, ws.pairA, ws.pairH,
+    void* ptrs[] = {ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, sort_tmp, ws.ctab_p0, ws.ctab_a0, ws.pair_slow, ws.rec_rstart, ws.rec_nh, ws.hit_rec, ws.hit_aoff, ws.hit_clfirst, ws.hit_need, ws.hit_p0, ws.hit_cid, ws.pairA, ws.pairH,
                     ws.pairC, ws.pairAbase, ws.pairCbase, ws.pairIbase, ws.pair_nint, ws.pair_sumlen, ws.pair_nchains, ws.pair_tqb_ns, ws.anc,
                     ws.score, ws.ptr, ws.rootkey, ws.depth, ws.chunk_first, ws.chunk_pair, ws.chunk_qctg, ws.chunk_lo, ws.chunk_hi,
                     ws.acc_total, ws.acc_rq0, ws.acc_rq1, ws.acc_tbcq, ws.acc_nint, ws.chunk_head, ws.chunk_est, ws.chunk_w, ws.chunk_valid,
@@ -1238,7 +1367,19 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
 #define DP_LAUNCH(NBV)                                                                                       \
   if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, true><<<grid, 32, 0, st>>>(TC, prm, ws)));       \
   else SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, false><<<grid, 32, 0, st>>>(TC, prm, ws)));
-      if (nb <= 2) { DP_LAUNCH(2) } else if (nb <= 4) { DP_LAUNCH(4) } else if (nb <= 8) { DP_LAUNCH(8) }
+      if (prm.band <= 24 && getenv("SK_DP_WARP") == nullptr) {   // 4 chunks per warp, 8 lanes each
+        const uint32_t g4 = (uint32_t)((TC + 3) / 4);
+        // group chunks of similar size: sort chunk ids by descending anchor count (cub radix sort, ~0.1 ms per batch)
+        SK_TRY(ensure(ctx, &ws.chunk_size, &S.c_chunk_size, TC)); SK_TRY(ensure(ctx, &ws.chunk_size_sorted, &S.c_chunk_size_sorted, TC));
+        SK_TRY(ensure(ctx, &ws.chunk_id, &S.c_chunk_id, TC)); SK_TRY(ensure(ctx, &ws.chunk_perm, &S.c_chunk_perm, TC));
+        chunk_size_kernel<<<(uint32_t)((TC + 255) / 256), 256, 0, st>>>(TC, ws); count_launch(ctx);
+        size_t tb = 0;
+        SK_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, (int)TC, 0, 32, st));
+        SK_TRY(ensure(ctx, &S.sort_tmp, &S.c_sort_tmp, tb));
+        SK_CUDA(cub::DeviceRadixSort::SortPairsDescending(S.sort_tmp, tb, ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, (int)TC, 0, 32, st));
+        if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true><<<g4, 32, 0, st>>>(TC, prm, ws)));
+        else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false><<<g4, 32, 0, st>>>(TC, prm, ws)));
+      } else if (nb <= 2) { DP_LAUNCH(2) } else if (nb <= 4) { DP_LAUNCH(4) } else if (nb <= 8) { DP_LAUNCH(8) }
       else if (nb <= 16) { DP_LAUNCH(16) } else { ctx->err = "c too small: chain band > 479 anchors is not supported"; return SK_ERR_PARAM; }
 #undef DP_LAUNCH
     }

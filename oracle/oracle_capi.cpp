@@ -6,8 +6,21 @@
 #include <cstdlib>
 #include <chrono>
 #include <algorithm>
+#include <malloc.h>
 
 #include "skani_oracle.hpp"
+
+// The CPU baseline should not be handicapped by glibc malloc defaults under 100+ threads: multi-100 KB vectors would be
+// mmap'ed/munmap'ed on every pair (serialising on the process' mm lock).  Keep them on the per-thread arenas instead.
+namespace {
+struct MallocTuning {
+  MallocTuning() {
+    mallopt(M_MMAP_THRESHOLD, 512 << 20);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_ARENA_MAX, 512);
+  }
+} g_malloc_tuning;
+}  // namespace
 
 using namespace orc;
 
@@ -266,4 +279,23 @@ extern "C" void* orc_seed_one_contig(const uint8_t* s, uint64_t n, uint64_t c, u
   if (avx2sem) orc::fmh_seeds_avx2sem(s, n, sp, 0, *sk);
   else orc::fmh_seeds_scalar(s, n, sp, 0, *sk);
   return sk;
+}
+
+// sketch n_genomes genomes laid out like sk_sketch_batch's input, threads over genomes (the reference's own parallel
+// structure, src/file_io.rs:149); handles are written to out[0..n_genomes)
+extern "C" int orc_sketch_many(const uint8_t* bases, const uint64_t* contig_off, const uint32_t* genome_of_contig, uint32_t n_contigs,
+                               uint32_t n_genomes, uint64_t c, uint64_t k, uint64_t marker_c, int threads, void** out) {
+  orc::SketchParams sp; sp.c = c; sp.k = k; sp.marker_c = marker_c;
+  std::vector<uint32_t> first(n_genomes + 1, n_contigs);
+  for (uint32_t i = n_contigs; i-- > 0;) first[genome_of_contig[i]] = i;
+  for (uint32_t g = n_genomes; g-- > 0;) if (first[g] == n_contigs && g + 1 <= n_genomes) first[g] = first[g + 1];
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1)
+  for (long g = 0; g < (long)n_genomes; g++) {
+    std::vector<std::pair<const uint8_t*, size_t>> ctgs;
+    for (uint32_t i = first[g]; i < first[g + 1]; i++) ctgs.push_back({bases + contig_off[i], (size_t)(contig_off[i + 1] - contig_off[i])});
+    char name[32];
+    snprintf(name, sizeof(name), "g%06ld", g);
+    out[g] = new orc::Sketch(orc::sketch_from_contigs(name, ctgs, nullptr, sp, true));
+  }
+  return 0;
 }

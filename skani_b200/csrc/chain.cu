@@ -719,7 +719,9 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
                         (g + (uint32_t)MAX_GAP <= 2u * (uint32_t)MAX_GAP);
         const int32_t gi = (int32_t)g;
         const int32_t ns = scs + ANCHOR_SCORE - (gi < 0 ? -gi : gi);
-        if (ok && ns > best_ns) { best_ns = ns; best_d = d; }
+        const bool take = ok & (ns > best_ns);                               // branch-free: keeps the warp converged
+        best_ns = take ? ns : best_ns;
+        best_d = take ? d : best_d;
       }
       // group arg-max: maximal score, then the smallest distance d (= largest j) among the maxima
       int32_t smax = best_ns;
@@ -739,7 +741,11 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
       const uint32_t wsrc = gbase | (jw & 7u);
       const uint32_t root_w = __shfl_sync(FULL, rsel, wsrc);
       const uint32_t depth_w = __shfl_sync(FULL, dsel, wsrc);
-      if (has && gl == m) { sc[0] = smax; rt[0] = root_w; dpth[0] = depth_w + 1; my_ptr = jw; }
+      const bool mine = has & (gl == m);
+      sc[0] = mine ? smax : sc[0];
+      rt[0] = mine ? root_w : rt[0];
+      dpth[0] = mine ? depth_w + 1 : dpth[0];
+      my_ptr = mine ? jw : my_ptr;
     }
     if (idx < n) {
       g_depth[idx] = dpth[0];

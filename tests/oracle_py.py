@@ -50,6 +50,8 @@ def lib():
     L.orc_sketch_from_contigs.restype = vp
     L.orc_sketch_from_contigs.argtypes = [C.c_char_p, vp, vp, u32, u64, u64, u64, i32]
     L.orc_sketch_free.argtypes = [vp]
+    L.orc_sketch_many.restype = i32
+    L.orc_sketch_many.argtypes = [vp, vp, vp, u32, u32, u64, u64, u64, i32, C.POINTER(vp)]
     L.orc_seed_one_contig.restype = vp
     L.orc_seed_one_contig.argtypes = [vp, u64, u64, u64, u64, i32]
     L.orc_time_seeding.restype = dbl
@@ -139,6 +141,15 @@ def sketch_from_contigs(name, seqs, c=125, k=15, marker_c=1000, avx2sem=True):
     buf = np.ascontiguousarray(buf)
     h = lib().orc_sketch_from_contigs(name.encode(), buf.ctypes.data, off.ctypes.data, len(arrs), c, k, marker_c, int(avx2sem))
     return Sketch(h)
+
+
+def sketch_many(bases, contig_off, genome_of_contig, n_genomes, c=125, k=15, marker_c=1000, threads=4):
+    """Oracle sketches of genomes laid out like sk_sketch_batch's input; OpenMP threads over genomes."""
+    bases = np.ascontiguousarray(bases, np.uint8)
+    off = np.ascontiguousarray(contig_off, np.uint64); goc = np.ascontiguousarray(genome_of_contig, np.uint32)
+    out = (C.c_void_p * n_genomes)()
+    lib().orc_sketch_many(bases.ctypes.data, off.ctypes.data, goc.ctypes.data, len(goc), n_genomes, c, k, marker_c, threads, out)
+    return [Sketch(out[i]) for i in range(n_genomes)]
 
 
 def chain(ref, query, cp=None):

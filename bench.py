@@ -90,6 +90,25 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU baseline (oracle = C++ restatement of the reference algorithm; "port")
 # ------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Threads for the CPU arm: all host CPUs this process may actually use.  The GPU boxes expose 128 logical CPUs but the
+    container's cgroup grants a CPU-time quota (cpu.max, 16 CPUs on the round-1 boxes); running 128 threads under that quota
+    is SLOWER than 32 (measured: seeding speed-up 15.9x at 16 threads, 18.7x at 32, 9.2x at 128), so use 2 threads per
+    granted CPU, capped by the visible CPUs."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        pass
+    if quota:
+        n = max(1, min(n, int(round(2 * quota))))
+    return n, quota
+
+
+
 def cpu_triangle_sample(n_sample, L, G, threads):
     """Times seeding + screen + chain of the oracle on n_sample synthetic genomes. Returns seconds and details."""
     import oracle_py as O
@@ -128,6 +147,7 @@ def cpu_baseline(args, threads):
     value = (N * (N - 1) / 2) / t_full
     one = cpu_single_thread(args.genome_len, args.cluster)
     return {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "single_thread": one,
+            "cgroup_cpu_quota": host_threads()[1],
             "sample": "oracle (C++ restatement of skani 0.3.0; Rust reference not buildable here) triangle on %d of the %d genomes "
                       "(%d clusters): %.2f s (seeding %.2f s; serial marker index + screen %.2f s; chain %.2f s for %d pairs) scaled "
                       "x%.1f to the full set (all stages linear in N at fixed cluster size)" % (S, N, S // args.cluster, d["t_total"],
@@ -142,7 +162,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads, _quota = host_threads()
     vals, last = [], None
     for i in range(args.warmup + args.steps):
         cb, d = cpu_baseline(args, threads)
@@ -269,7 +289,7 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu, _d = cpu_baseline(args, os.cpu_count() or 1)
+        cpu, _d = cpu_baseline(args, host_threads()[0])
     if rank == 0:
         line = {"metric": METRIC, "value": total_pairs / (ms_val * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_val, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

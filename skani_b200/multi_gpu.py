@@ -61,21 +61,42 @@ class DistTriangle:
 
     def exchange(self, local_set):
         """All-gather the ranks' sketch sets -> one set holding every genome, on this GPU."""
+        import os
+        import time
         torch, L, ctx = self.torch, self.ctx.L, self.ctx
+        trace = os.environ.get("SK_TRACE") and self.rank == 0
+        t0 = time.perf_counter()
         nbytes, nwords = C.c_uint64(), C.c_uint64()
         ctx.check(L.sk_sketch_set_blob_size(local_set.h, C.byref(nbytes), C.byref(nwords)))
-        blob = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
         meta = np.zeros(nwords.value, np.uint64)
-        ctx.check(L.sk_sketch_set_pack(local_set.h, blob.data_ptr(), meta.ctypes.data))
-        torch.cuda.synchronize()
-        blobs = gather_variable(self.dist, blob, self.world, self.device)
-        metas = gather_variable(self.dist, torch.from_numpy(meta.view(np.int64)).to(self.device), self.world, self.device)
-        metas = [m.cpu().numpy().view(np.uint64).copy() for m in metas]
-        bp = (C.c_void_p * self.world)(*[b.data_ptr() for b in blobs])
+        # sizes first (tiny), so the blob can be packed straight into its slot of the gathered buffer (no padded copy)
+        sz = torch.tensor([nbytes.value, nwords.value], dtype=torch.int64, device=self.device)
+        allsz = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(allsz, sz)
+        allsz = allsz.cpu().numpy().reshape(self.world, 2)
+        mx = int(allsz[:, 0].max())
+        mx = (mx + 255) & ~255
+        out = torch.empty(self.world * mx, dtype=torch.uint8, device=self.device)
+        mine = out[self.rank * mx:(self.rank + 1) * mx]
+        ctx.check(L.sk_sketch_set_pack(local_set.h, mine.data_ptr(), meta.ctypes.data))
+        t1 = time.perf_counter()
+        self.dist.all_gather_into_tensor(out, mine)              # in place: rank r's slice is already at offset r * mx
+        mw = int(allsz[:, 1].max())
+        mloc = torch.zeros(mw, dtype=torch.int64, device=self.device)
+        mloc[:nwords.value] = torch.from_numpy(meta.view(np.int64)).to(self.device)
+        mall = torch.empty(self.world * mw, dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(mall, mloc)
+        mall = mall.cpu().numpy().view(np.uint64).reshape(self.world, mw)
+        t2 = time.perf_counter()
+        metas = [np.ascontiguousarray(mall[r, :int(allsz[r, 1])]) for r in range(self.world)]
+        bp = (C.c_void_p * self.world)(*[out.data_ptr() + r * mx for r in range(self.world)])
         mp_ = (C.c_void_p * self.world)(*[m.ctypes.data for m in metas])
-        out = C.c_void_p()
-        ctx.check(L.sk_sketch_set_unpack(ctx.h, self.world, bp, mp_, C.byref(out)))
-        return H.SketchSet(ctx, out)
+        res = C.c_void_p()
+        ctx.check(L.sk_sketch_set_unpack(ctx.h, self.world, bp, mp_, C.byref(res)))
+        if trace:
+            print("[multi_gpu rank0] exchange: sizes+pack %.1f ms, all-gather (%.2f GB) %.1f ms, unpack+tables %.1f ms" %
+                  ((t1 - t0) * 1e3, self.world * mx / 1e9, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3), flush=True)
+        return H.SketchSet(ctx, res)
 
     def step(self, host_bases, dev_ptr, off, goc, nloc, g0, n_total):
         """One whole triangle over all ranks; returns this rank's number of kept pairs."""

@@ -120,6 +120,16 @@ int sk_sketch_set_blob_size(const sk_sketch_set* set, uint64_t* device_bytes, ui
 int sk_sketch_set_pack(const sk_sketch_set* set, void* d_blob, uint64_t* host_meta);
 int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blobs, const uint64_t* const* host_metas,
                          sk_sketch_set** out);
+/* Subset variants for exchanges that move only what a rank needs (skani_b200/multi_gpu.py: markers of every genome are
+ * all-gathered for the screen, then each rank fetches the full sketches of just the genomes its pairs touch):
+ * genomes[0..n) index `set` (NULL = all genomes, in order); the blob holds them in that order.  With
+ * SK_PACK_MARKERS_ONLY the blob carries the marker arrays only (enough for sk_screen_*; such a set chains to
+ * "no anchors", ani = NaN).  Same blob / metadata format as sk_sketch_set_pack, so sk_sketch_set_unpack reads both. */
+#define SK_PACK_MARKERS_ONLY 1
+int sk_sketch_set_subset_blob_size(const sk_sketch_set* set, const uint32_t* genomes, uint32_t n, int flags,
+                                   uint64_t* device_bytes, uint64_t* host_meta_words);
+int sk_sketch_set_pack_subset(const sk_sketch_set* set, const uint32_t* genomes, uint32_t n, int flags, void* d_blob,
+                              uint64_t* host_meta);
 
 /* ---- marker screen: replaces screen::kmer_to_sketch_from_refs + screen_refs / screen_refs_indices /
  *      check_markers_quickly (src/screen.rs:190, 148, 39, 84) -----------------------------------------------

@@ -60,6 +60,8 @@ SYMBOLS = [
     ("sk_sketch_set_blob_size", i32, [vp, PP(u64), PP(u64)]),
     ("sk_sketch_set_pack", i32, [vp, vp, vp]),
     ("sk_sketch_set_unpack", i32, [vp, u32, vp, vp, PP(vp)]),
+    ("sk_sketch_set_subset_blob_size", i32, [vp, vp, u32, i32, PP(u64), PP(u64)]),
+    ("sk_sketch_set_pack_subset", i32, [vp, vp, u32, i32, vp, vp]),
     ("sk_screen_triangle", i32, [vp, vp, PP(MapParams), PP(PP(u64)), PP(u64)]),
     ("sk_screen_triangle_rows", i32, [vp, vp, PP(MapParams), u32, u32, PP(PP(u64)), PP(u64)]),
     ("sk_screen_query_ref", i32, [vp, vp, vp, PP(MapParams), i32, PP(PP(u64)), PP(u64)]),

@@ -377,6 +377,93 @@ int sk_sketch_set_pack(const sk_sketch_set* s, void* d_blob, uint64_t* meta) {
   return SK_OK;
 }
 
+namespace {
+// host-side plan of a subset blob: maximal runs of consecutive genomes are copied with one memcpy per array
+struct SubsetPlan {
+  std::vector<uint32_t> idx;                        // selected genomes, in output order
+  std::vector<uint64_t> seed_off, uk_off, mk_off, ctg_off;
+  size_t S = 0, U = 0, M = 0, C = 0;
+};
+int plan_subset(const sk_sketch_set* s, const uint32_t* genomes, uint32_t n, int flags, SubsetPlan& pl) {
+  const bool mo = (flags & SK_PACK_MARKERS_ONLY) != 0;
+  if (!genomes) { n = s->G; pl.idx.resize(n); for (uint32_t i = 0; i < n; i++) pl.idx[i] = i; }
+  else pl.idx.assign(genomes, genomes + n);
+  pl.seed_off.assign(n + 1, 0); pl.uk_off.assign(n + 1, 0); pl.mk_off.assign(n + 1, 0); pl.ctg_off.assign(n + 1, 0);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t g = pl.idx[i];
+    if (g >= s->G) { s->ctx->err = "subset genome index out of range"; return SK_ERR_PARAM; }
+    pl.seed_off[i + 1] = pl.seed_off[i] + (mo ? 0 : s->seed_off[g + 1] - s->seed_off[g]);
+    pl.uk_off[i + 1] = pl.uk_off[i] + (mo ? 0 : s->uk_off[g + 1] - s->uk_off[g]);
+    pl.ctg_off[i + 1] = pl.ctg_off[i] + (mo ? 0 : s->ctg_off[g + 1] - s->ctg_off[g]);
+    pl.mk_off[i + 1] = pl.mk_off[i] + (s->mk_off[g + 1] - s->mk_off[g]);
+  }
+  pl.S = pl.seed_off[n]; pl.U = pl.uk_off[n]; pl.M = pl.mk_off[n]; pl.C = pl.ctg_off[n];
+  return SK_OK;
+}
+}  // namespace
+
+int sk_sketch_set_subset_blob_size(const sk_sketch_set* s, const uint32_t* genomes, uint32_t n, int flags, uint64_t* device_bytes,
+                                   uint64_t* host_meta_words) {
+  if (!s || !device_bytes || !host_meta_words) return SK_ERR_PARAM;
+  SubsetPlan pl;
+  SK_TRY(plan_subset(s, genomes, n, flags, pl));
+  const size_t G = pl.idx.size();
+  *device_bytes = blob_layout(G, pl.S, pl.U, pl.M, pl.C).total;
+  *host_meta_words = 8 + 4 * ((uint64_t)G + 1) + G + pl.C;
+  return SK_OK;
+}
+
+int sk_sketch_set_pack_subset(const sk_sketch_set* s, const uint32_t* genomes, uint32_t n, int flags, void* d_blob, uint64_t* meta) {
+  if (!s || !d_blob || !meta) return SK_ERR_PARAM;
+  sk_ctx* ctx = s->ctx;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  SubsetPlan pl;
+  SK_TRY(plan_subset(s, genomes, n, flags, pl));
+  const bool mo = (flags & SK_PACK_MARKERS_ONLY) != 0;
+  const uint32_t G = (uint32_t)pl.idx.size();
+  const BlobLayout b = blob_layout(G, pl.S, pl.U, pl.M, pl.C);
+  uint8_t* base = (uint8_t*)d_blob;
+  cudaStream_t st = ctx->stream;
+  auto cp = [&](int arr, size_t dst_elem, const void* src, size_t src_elem, size_t count, size_t esz) -> cudaError_t {
+    if (count == 0) return cudaSuccess;
+    return cudaMemcpyAsync(base + b.off[arr] + dst_elem * esz, (const uint8_t*)src + src_elem * esz, count * esz, cudaMemcpyDeviceToDevice, st);
+  };
+  if (mo) {   // one zero sentinel per genome in the group-start and contig-record tables
+    if (G) SK_CUDA(cudaMemsetAsync(base + b.off[7], 0, (size_t)G * 4, st));
+    if (G) SK_CUDA(cudaMemsetAsync(base + b.off[9], 0, (size_t)G * 4, st));
+  }
+  for (uint32_t i = 0; i < G;) {
+    uint32_t j = i + 1;
+    while (j < G && pl.idx[j] == pl.idx[j - 1] + 1) j++;       // run [i, j) = source genomes [a, e)
+    const uint32_t a = pl.idx[i], e = pl.idx[j - 1] + 1;
+    if (!mo) {
+      const size_t so = s->seed_off[a], ns = s->seed_off[e] - so, uo = s->uk_off[a], nu = s->uk_off[e] - uo;
+      const size_t co = s->ctg_off[a], nc = s->ctg_off[e] - co;
+      SK_CUDA(cp(0, pl.seed_off[i], s->pv_kmer, so, ns, 4)); SK_CUDA(cp(1, pl.seed_off[i], s->pv_pos, so, ns, 4));
+      SK_CUDA(cp(2, pl.seed_off[i], s->pv_cc, so, ns, 4));   SK_CUDA(cp(3, pl.seed_off[i], s->pv_mult, so, ns, 2));
+      SK_CUDA(cp(4, pl.seed_off[i], s->kv_pos, so, ns, 4));  SK_CUDA(cp(5, pl.seed_off[i], s->kv_cc, so, ns, 4));
+      SK_CUDA(cp(6, pl.uk_off[i], s->ukmer, uo, nu, 4));
+      SK_CUDA(cp(7, pl.uk_off[i] + i, s->ustart, uo + a, nu + (e - a), 4));          // + one sentinel per genome
+      SK_CUDA(cp(9, pl.ctg_off[i] + i, s->ctg_rec_off, co + a, nc + (e - a), 4));
+      SK_CUDA(cp(10, pl.ctg_off[i], s->d_ctg_len, co, nc, 4));
+    }
+    SK_CUDA(cp(8, pl.mk_off[i], s->markers, s->mk_off[a], s->mk_off[e] - s->mk_off[a], 8));
+    i = j;
+  }
+  uint64_t* m = meta;
+  *m++ = G; *m++ = pl.S; *m++ = pl.U; *m++ = pl.M; *m++ = pl.C; *m++ = s->sp.c; *m++ = s->sp.k; *m++ = s->sp.marker_c;
+  for (uint32_t g = 0; g <= G; g++) *m++ = pl.seed_off[g];
+  for (uint32_t g = 0; g <= G; g++) *m++ = pl.uk_off[g];
+  for (uint32_t g = 0; g <= G; g++) *m++ = pl.mk_off[g];
+  for (uint32_t g = 0; g <= G; g++) *m++ = pl.ctg_off[g];
+  for (uint32_t g = 0; g < G; g++) *m++ = s->total_len[pl.idx[g]];
+  if (!mo)
+    for (uint32_t g = 0; g < G; g++)
+      for (uint64_t c = s->ctg_off[pl.idx[g]]; c < s->ctg_off[pl.idx[g] + 1]; c++) *m++ = s->ctg_len[c];
+  SK_CUDA(cudaStreamSynchronize(st));
+  return SK_OK;
+}
+
 int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blobs, const uint64_t* const* metas, sk_sketch_set** out) {
   if (!ctx || !out || n_parts == 0 || !d_blobs || !metas) return SK_ERR_PARAM;
   SK_CUDA(cudaSetDevice(ctx->device));

@@ -104,6 +104,27 @@ class SketchSet:
         assert len(r) == len(self)
         self.ctx.check(self.ctx.L.sk_sketch_set_set_name_ranks(self.h, r.ctypes.data))
 
+    def _genome_arg(self, genomes):
+        if genomes is None:
+            return None, 0, None
+        g = np.ascontiguousarray(genomes, np.uint32)
+        keep = g if len(g) else np.zeros(1, np.uint32)      # never hand the library a NULL pointer for "no genomes"
+        return keep.ctypes.data, len(g), keep
+
+    def subset_blob_size(self, genomes=None, flags=0):
+        """(device bytes, metadata words) of the blob sk_sketch_set_pack_subset would write; genomes=None -> all."""
+        ptr, n, _keep = self._genome_arg(genomes)
+        nb, nw = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx.L.sk_sketch_set_subset_blob_size(self.h, ptr, n, flags, C.byref(nb), C.byref(nw)))
+        return nb.value, nw.value
+
+    def pack_subset(self, genomes, flags, device_ptr, n_words):
+        """Pack the chosen genomes into caller-owned device memory; returns the host metadata vector (uint64)."""
+        ptr, n, _keep = self._genome_arg(genomes)
+        meta = np.zeros(n_words, np.uint64)
+        self.ctx.check(self.ctx.L.sk_sketch_set_pack_subset(self.h, ptr, n, flags, device_ptr, meta.ctypes.data))
+        return meta
+
     def append(self, other):
         self.ctx.check(self.ctx.L.sk_sketch_set_append(self.h, other.h))
 

@@ -2,21 +2,31 @@
 
 The reference is a single process (rayon threads); the pair loop of src/triangle.rs:71-105 shards naturally:
   1. every rank sketches a contiguous block of genomes (seeding is independent per genome);
-  2. ONE exchange step: the ranks' sketch blocks are all-gathered (NCCL over NVLink/NVSwitch) so every GPU holds all
-     N sketches in rank-major = global genome order (10k genomes ~ 12 GB; 4.4 GB of seeds + views);
-  3. every rank screens the triangle (cheap) and chains every world-th passing pair, no further communication
-     (sk_screen_triangle_rows offers a row-cyclic partition of the screen itself for sets where screening dominates);
-  4. results stay on their rank (the reference's sparse output order is nondeterministic anyway).
+  2. the MARKERS of every genome (8 B x L/1000 per genome: 0.4 GB for 10k genomes) are all-gathered and every rank
+     screens the whole triangle (a few ms) -> the same sorted list of passing pairs on every rank;
+  3. the sorted pair list is cut into `world` contiguous slices (equal chaining work by construction); a rank needs the
+     full sketches of just the genomes its slice touches.  Because the list is sorted by (i, j) and related genomes
+     tend to be neighbours, most of them are the rank's own block; the rest arrive in ONE variable all-to-all (NCCL
+     over NVLink/NVSwitch) of per-destination sub-blobs (sk_sketch_set_pack_subset).  Worst case (relatedness unrelated
+     to the input order) this degenerates to the volume of a full all-gather, never more;
+  4. each rank rebuilds a working set from what it received (rank-major = ascending global genome order), chains its
+     slice, maps the ids back to global ones.  Results stay on their rank (the reference's sparse output order is
+     nondeterministic anyway).
+`exchange()` (full all-gather of the sketches) is kept for callers that want every sketch everywhere (search/dist DBs).
 """
 import ctypes as C
+import os
+import time
 
 import numpy as np
 
 from . import host as H
 
+PACK_MARKERS_ONLY = 1        # include/skani_b200.h SK_PACK_MARKERS_ONLY
+
 
 def shard_range(n_items, world, rank):
-    """Contiguous block partition used for the seeding stage."""
+    """Contiguous block partition used for the seeding stage (and for the slices of the sorted pair list)."""
     return (n_items * rank) // world, (n_items * (rank + 1)) // world
 
 
@@ -28,6 +38,46 @@ def rows_of_rank(n_rows, world, rank):
 def pairs_of_rank(sorted_pairs, world, rank):
     """Cyclic split of the sorted passing-pair list: every rank gets the same number of pairs (+-1)."""
     return np.ascontiguousarray(sorted_pairs[rank::world])
+
+
+def pair_slice_of_rank(sorted_pairs, world, rank):
+    """Contiguous slice of the sorted passing-pair list (same count +-1 on every rank, neighbouring genomes together)."""
+    lo, hi = shard_range(len(sorted_pairs), world, rank)
+    return np.ascontiguousarray(sorted_pairs[lo:hi])
+
+
+def genomes_of_pairs(pairs):
+    """Ascending distinct genome ids that appear in a list of (i << 32 | j) pairs."""
+    p = np.asarray(pairs, np.uint64)
+    if len(p) == 0:
+        return np.zeros(0, np.uint32)
+    return np.unique(np.concatenate([(p >> np.uint64(32)).astype(np.uint32), (p & np.uint64(0xFFFFFFFF)).astype(np.uint32)]))
+
+
+def fetch_plan(sorted_pairs, world, rank, bounds):
+    """Who needs what.  bounds[r] .. bounds[r+1] = the genome block sketched by rank r.
+    Returns (need, send, recv_counts): need = ascending global ids this rank chains; send[d] = LOCAL indices (into this
+    rank's block) of the genomes rank d needs from here; recv_counts[r] = how many genomes arrive from rank r."""
+    bounds = np.asarray(bounds, np.int64)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    send, need = [], None
+    for d in range(world):
+        nd = genomes_of_pairs(pair_slice_of_rank(sorted_pairs, world, d))
+        if d == rank:
+            need = nd
+        a, b = np.searchsorted(nd, [lo, hi])
+        send.append((nd[a:b] - lo).astype(np.uint32))
+    cut = np.searchsorted(need, bounds)
+    recv_counts = np.diff(cut).astype(np.int64)
+    return need, send, recv_counts
+
+
+def remap_pairs(pairs, need):
+    """(i << 32 | j) in global ids -> the same pairs in indices of the ascending id list `need`."""
+    p = np.asarray(pairs, np.uint64)
+    i = np.searchsorted(need, (p >> np.uint64(32)).astype(np.uint32)).astype(np.uint64)
+    j = np.searchsorted(need, (p & np.uint64(0xFFFFFFFF)).astype(np.uint32)).astype(np.uint64)
+    return np.ascontiguousarray((i << np.uint64(32)) | j)
 
 
 def gather_variable(dist, local, world, device):
@@ -50,27 +100,49 @@ def gather_variable(dist, local, world, device):
     return [out[r * mx:r * mx + sizes[r]] for r in range(world)]
 
 
+def alltoall_variable(dist, send_parts, world, device, src=None):
+    """Variable all-to-all of 1-D tensors (send_parts[d] goes to rank d); returns the list of tensors received, by source
+    rank.  One tiny all-to-all for the sizes, one for the payload.  Any backend (gloo on CPU for tests, nccl on GPUs).
+    src: the buffer the parts are consecutive views of, if they are (saves the concatenating copy)."""
+    import torch
+    dtype = send_parts[0].dtype
+    n_in = torch.tensor([p.numel() for p in send_parts], dtype=torch.int64, device=device)
+    n_out = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(n_out, n_in)
+    in_split = [int(p.numel()) for p in send_parts]
+    out_split = [int(x) for x in n_out.cpu().tolist()]
+    if src is None:
+        src = torch.cat(send_parts) if sum(in_split) else torch.empty(0, dtype=dtype, device=device)
+    dst = torch.empty(sum(out_split), dtype=dtype, device=device)
+    dist.all_to_all_single(dst, src, output_split_sizes=out_split, input_split_sizes=in_split)
+    outs, o = [], 0
+    for r in range(world):
+        outs.append(dst[o:o + out_split[r]])
+        o += out_split[r]
+    return outs
+
+
 class DistTriangle:
-    def __init__(self, ctx, world, rank, sp, mp):
+    def __init__(self, ctx, world, rank, sp, mp, name_ranks=None):
+        """name_ranks: optional per-GLOBAL-genome order of the file names (see SketchSet.set_name_ranks); default = index."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.ctx, self.world, self.rank, self.sp, self.mp = ctx, world, rank, sp, mp
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self.name_ranks = None if name_ranks is None else np.ascontiguousarray(name_ranks, np.uint64)
         self.last_results = []
+        self.last_need = None
 
-    def exchange(self, local_set):
-        """All-gather the ranks' sketch sets -> one set holding every genome, on this GPU."""
-        import os
-        import time
+    # ---- full exchange: every rank ends up with every genome (markers only, or whole sketches) -------------------
+    def exchange(self, local_set, flags=0):
+        """All-gather the ranks' sketch sets -> one set holding every genome (rank-major order), on this GPU."""
         torch, L, ctx = self.torch, self.ctx.L, self.ctx
         trace = os.environ.get("SK_TRACE") and self.rank == 0
         t0 = time.perf_counter()
-        nbytes, nwords = C.c_uint64(), C.c_uint64()
-        ctx.check(L.sk_sketch_set_blob_size(local_set.h, C.byref(nbytes), C.byref(nwords)))
-        meta = np.zeros(nwords.value, np.uint64)
+        nbytes, nwords = local_set.subset_blob_size(None, flags)
         # sizes first (tiny), so the blob can be packed straight into its slot of the gathered buffer (no padded copy)
-        sz = torch.tensor([nbytes.value, nwords.value], dtype=torch.int64, device=self.device)
+        sz = torch.tensor([nbytes, nwords], dtype=torch.int64, device=self.device)
         allsz = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
         self.dist.all_gather_into_tensor(allsz, sz)
         allsz = allsz.cpu().numpy().reshape(self.world, 2)
@@ -78,31 +150,59 @@ class DistTriangle:
         mx = (mx + 255) & ~255
         out = torch.empty(self.world * mx, dtype=torch.uint8, device=self.device)
         mine = out[self.rank * mx:(self.rank + 1) * mx]
-        ctx.check(L.sk_sketch_set_pack(local_set.h, mine.data_ptr(), meta.ctypes.data))
+        meta = local_set.pack_subset(None, flags, mine.data_ptr(), nwords)
         t1 = time.perf_counter()
         self.dist.all_gather_into_tensor(out, mine)              # in place: rank r's slice is already at offset r * mx
         mw = int(allsz[:, 1].max())
         mloc = torch.zeros(mw, dtype=torch.int64, device=self.device)
-        mloc[:nwords.value] = torch.from_numpy(meta.view(np.int64)).to(self.device)
+        mloc[:nwords] = torch.from_numpy(meta.view(np.int64)).to(self.device)
         mall = torch.empty(self.world * mw, dtype=torch.int64, device=self.device)
         self.dist.all_gather_into_tensor(mall, mloc)
         mall = mall.cpu().numpy().view(np.uint64).reshape(self.world, mw)
         t2 = time.perf_counter()
         metas = [np.ascontiguousarray(mall[r, :int(allsz[r, 1])]) for r in range(self.world)]
-        bp = (C.c_void_p * self.world)(*[out.data_ptr() + r * mx for r in range(self.world)])
-        mp_ = (C.c_void_p * self.world)(*[m.ctypes.data for m in metas])
-        res = C.c_void_p()
-        ctx.check(L.sk_sketch_set_unpack(ctx.h, self.world, bp, mp_, C.byref(res)))
+        res = self._unpack([out.data_ptr() + r * mx for r in range(self.world)], metas)
         if trace:
-            print("[multi_gpu rank0] exchange: sizes+pack %.1f ms, all-gather (%.2f GB) %.1f ms, unpack+tables %.1f ms" %
-                  ((t1 - t0) * 1e3, self.world * mx / 1e9, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3), flush=True)
+            print("[multi_gpu rank0] exchange(flags=%d): sizes+pack %.1f ms, all-gather (%.2f GB) %.1f ms, unpack+tables %.1f ms" %
+                  (flags, (t1 - t0) * 1e3, self.world * mx / 1e9, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3), flush=True)
+        return res
+
+    def _unpack(self, blob_ptrs, metas):
+        ctx, L = self.ctx, self.ctx.L
+        n = len(blob_ptrs)
+        bp = (C.c_void_p * n)(*blob_ptrs)
+        mp_ = (C.c_void_p * n)(*[m.ctypes.data for m in metas])
+        res = C.c_void_p()
+        ctx.check(L.sk_sketch_set_unpack(ctx.h, n, bp, mp_, C.byref(res)))
         return H.SketchSet(ctx, res)
 
+    # ---- partial exchange: every rank receives the sketches of the genomes its pair slice touches ----------------
+    def fetch(self, local_set, send, recv_counts):
+        """send[d] = local genome indices for rank d (ascending).  Returns the working set: the received genomes in
+        source-rank order (= ascending global order)."""
+        torch = self.torch
+        sizes = [local_set.subset_blob_size(send[d], 0) for d in range(self.world)]
+        blobs = torch.empty(sum(s[0] for s in sizes), dtype=torch.uint8, device=self.device)
+        parts, metas, o = [], [], 0
+        for d in range(self.world):
+            part = blobs[o:o + sizes[d][0]]
+            metas.append(local_set.pack_subset(send[d], 0, part.data_ptr(), sizes[d][1]))
+            parts.append(part)
+            o += sizes[d][0]
+        got = alltoall_variable(self.dist, parts, self.world, self.device, src=blobs)
+        mparts = [torch.from_numpy(m.view(np.int64)).to(self.device) for m in metas]
+        gmeta = [g.cpu().numpy().view(np.uint64) for g in alltoall_variable(self.dist, mparts, self.world, self.device)]
+        for r in range(self.world):
+            assert int(gmeta[r][0]) == int(recv_counts[r]), "fetch plan mismatch between ranks"
+        # all_to_all_single's output is one contiguous tensor; sub-blob sizes are multiples of 256 bytes, so alignment holds
+        work = self._unpack([g.data_ptr() for g in got], [np.ascontiguousarray(m) for m in gmeta])
+        return work, sum(int(g.numel()) for r, g in enumerate(got) if r != self.rank)
+
     def step(self, host_bases, dev_ptr, off, goc, nloc, g0, n_total):
-        """One whole triangle over all ranks; returns this rank's number of kept pairs."""
-        import os
-        import time
-        ctx, L = self.ctx, self.ctx.L
+        """One whole triangle over all ranks; returns this rank's number of kept pairs (results in self.last_results,
+        ref_id / query_id = GLOBAL genome indices)."""
+        ctx = self.ctx
+        torch = self.torch
         trace = os.environ.get("SK_TRACE") and self.rank == 0
         t0 = time.perf_counter()
         if host_bases is not None:
@@ -110,19 +210,34 @@ class DistTriangle:
         else:
             local = H.sketch_contigs(ctx, None, off, goc, nloc, self.sp, device_ptr=dev_ptr)
         t1 = time.perf_counter()
-        allset = self.exchange(local)
-        local.free()
-        assert len(allset) == n_total
+        # genome blocks of all ranks
+        blk = torch.tensor([g0, nloc], dtype=torch.int64, device=self.device)
+        allblk = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(allblk, blk)
+        allblk = allblk.cpu().numpy().reshape(self.world, 2)
+        bounds = np.concatenate([allblk[:, 0], [allblk[-1, 0] + allblk[-1, 1]]])
+        assert bounds[0] == 0 and bounds[-1] == n_total and np.all(np.diff(bounds) == allblk[:, 1]), "ranks must hold consecutive blocks"
+        # markers everywhere -> every rank screens the whole triangle
+        mk = self.exchange(local, PACK_MARKERS_ONLY)
+        assert len(mk) == n_total
+        pairs = H.screen_triangle(ctx, mk, self.mp)
+        mk.free()
         t2 = time.perf_counter()
-        # every rank screens the whole triangle (a few ms: one sort of all markers) and takes every world-th passing pair of
-        # the sorted list: an even split of the CHAINING work, which a row partition does not give when related genomes are
-        # adjacent (rows i mod 8 of a 20-genome cluster carry 33 vs 16 pairs)
-        pairs = pairs_of_rank(H.screen_triangle(ctx, allset, self.mp), self.world, self.rank)
+        need, send, recv_counts = fetch_plan(pairs, self.world, self.rank, bounds)
+        mine = pair_slice_of_rank(pairs, self.world, self.rank)
+        work, remote_bytes = self.fetch(local, send, recv_counts)
+        local.free()
+        assert len(work) == len(need)
+        work.set_name_ranks(need.astype(np.uint64) if self.name_ranks is None else self.name_ranks[need])
         t3 = time.perf_counter()
-        res = H.chain_pairs(ctx, allset, allset, pairs, self.mp, as_array=True)
-        allset.free()
+        res = H.chain_pairs(ctx, work, work, remap_pairs(mine, need), self.mp, as_array=True)
+        work.free()
+        res["ref_id"] = need[res["ref_id"]]
+        res["query_id"] = need[res["query_id"]]
         if trace:
-            print("[multi_gpu rank0] sketch %.1f ms  exchange %.1f ms  screen %.1f ms  chain %.1f ms (%d pairs)" %
-                  ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (time.perf_counter() - t3) * 1e3, len(pairs)), flush=True)
+            print("[multi_gpu rank0] sketch %.1f ms  markers+screen %.1f ms  fetch %.1f ms (%d genomes, %.1f MB remote)  "
+                  "chain %.1f ms (%d pairs)" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, len(need), remote_bytes / 1e6,
+                                                (time.perf_counter() - t3) * 1e3, len(mine)), flush=True)
         self.last_results = res[res["ani"] > 0.1]               # src/triangle.rs:99 (numpy structured array)
+        self.last_need = need
         return len(self.last_results)

@@ -35,6 +35,40 @@ def test_partitions_cover_everything():
     assert (max(loads) - min(loads)) / (sum(loads) / world) < 2e-3
 
 
+def test_fetch_plan_is_consistent_across_ranks():
+    """Every rank computes the plan from the same sorted pair list: what rank r plans to send to d must be exactly what
+    d expects from r, the union over r must be d's need list, and the remapped pairs must point back at the same ids."""
+    from skani_b200.multi_gpu import fetch_plan, pair_slice_of_rank, remap_pairs, genomes_of_pairs, shard_range
+    rng = np.random.default_rng(7)
+    for n, world, clustered in ((200, 2, True), (1000, 4, True), (333, 8, False), (50, 3, True), (10, 4, False)):
+        if clustered:      # clusters of 20 consecutive genomes (the bench workload), all pairs inside a cluster
+            pl = [(i << 32) | j for i in range(n) for j in range(i + 1, min(n, (i // 20 + 1) * 20))]
+        else:              # relatedness unrelated to the input order
+            ii = rng.integers(0, n - 1, 400); jj = rng.integers(1, n, 400)
+            pl = sorted({(int(min(a, b)) << 32) | int(max(a, b)) for a, b in zip(ii, jj) if a != b})
+        pairs = np.array(pl, np.uint64)
+        bounds = [shard_range(n, world, r)[0] for r in range(world)] + [n]
+        plans = [fetch_plan(pairs, world, r, bounds) for r in range(world)]
+        covered = []
+        for d in range(world):
+            need, _send, recv_counts = plans[d]
+            mine = pair_slice_of_rank(pairs, world, d)
+            covered.append(mine)
+            assert np.array_equal(need, genomes_of_pairs(mine))
+            got = np.concatenate([plans[r][1][d].astype(np.int64) + bounds[r] for r in range(world)]) if world else []
+            assert np.array_equal(got, need.astype(np.int64))                       # rank-major == ascending global order
+            assert [len(plans[r][1][d]) for r in range(world)] == recv_counts.tolist()
+            rp = remap_pairs(mine, need)
+            back = (need[(rp >> np.uint64(32)).astype(np.int64)].astype(np.uint64) << np.uint64(32)) | need[(rp & np.uint64(0xFFFFFFFF)).astype(np.int64)].astype(np.uint64)
+            assert np.array_equal(back, mine)
+        assert np.array_equal(np.concatenate(covered), pairs)
+        sizes = [len(c) for c in covered]
+        assert max(sizes) - min(sizes) <= 1
+    # no pairs at all
+    need, send, rc = fetch_plan(np.zeros(0, np.uint64), 2, 1, [0, 5, 10])
+    assert len(need) == 0 and all(len(x) == 0 for x in send) and rc.tolist() == [0, 0]
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,6 +79,17 @@ def _worker(rank, world, port, q):
     b = torch.full((7 - 7 * rank,), rank + 1, dtype=torch.uint8)   # rank 1 contributes an empty blob
     pb = gather_variable(dist, b, world, "cpu")
     ok = ok and pb[0].numel() == 7 and pb[1].numel() == 0 and int(pb[0].sum()) == 7
+    # variable all-to-all (the sketch fetch): rank r sends 3r+d bytes of value 10r+d to rank d, including nothing at all
+    from skani_b200.multi_gpu import alltoall_variable
+    parts = [torch.full((3 * rank + d,), 10 * rank + d, dtype=torch.uint8) for d in range(world)]
+    got = alltoall_variable(dist, parts, world, "cpu")
+    ok = ok and all(got[r].tolist() == [10 * r + rank] * (3 * r + rank) for r in range(world))
+    buf = torch.cat(parts)
+    views, o = [], 0
+    for p_ in parts:
+        views.append(buf[o:o + p_.numel()]); o += p_.numel()
+    got2 = alltoall_variable(dist, views, world, "cpu", src=buf)
+    ok = ok and all(torch.equal(a, b) for a, b in zip(got, got2))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

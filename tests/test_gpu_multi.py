@@ -1,4 +1,5 @@
-"""Multi-GPU triangle (NCCL all-gather of sketch blocks + row-cyclic pair partition) == single-process oracle."""
+"""Multi-GPU triangle (markers all-gather + screen everywhere, contiguous pair slices, variable all-to-all fetch of the
+sketches a rank chains; n=18, G=6 puts a cluster across the block boundary) == single-process oracle."""
 import os
 import subprocess
 import sys

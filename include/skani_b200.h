@@ -109,6 +109,16 @@ int sk_sketch_set_export(const sk_sketch_set* set, uint32_t genome, uint32_t* km
 int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* params, const uint32_t* kmer, const uint32_t* pos,
                          const uint32_t* contig_canon, uint64_t n_records, const uint64_t* markers, uint64_t n_markers,
                          const uint32_t* contig_lengths, uint32_t n_contigs, sk_sketch_set** out);
+/* Batched form (e.g. every entry of a skani database decoded on the host: src/sketch_db.rs:104-121 get_sketch,
+ * src/file_io.rs:719 marker_sketches_from_marker_file): genome g owns records [rec_off[g], rec_off[g+1]), markers
+ * [mk_off[g], mk_off[g+1]) and contigs [ctg_off[g], ctg_off[g+1]) of the concatenated arrays (offset arrays have
+ * n_genomes + 1 entries, n_genomes >= 1).  total_len: Sketch.total_sequence_length per genome, or NULL = sum of the
+ * genome's contig lengths (marker-only sketches carry no contig lengths).  A batch is limited to < 2^31 records and
+ * markers; larger databases are imported in several batches joined with sk_sketch_set_append. */
+int sk_sketch_set_import_batch(sk_ctx* ctx, const sk_sketch_params* params, uint32_t n_genomes, const uint64_t* rec_off,
+                               const uint32_t* kmer, const uint32_t* pos, const uint32_t* contig_canon,
+                               const uint64_t* mk_off, const uint64_t* markers, const uint64_t* ctg_off,
+                               const uint32_t* contig_lengths, const uint64_t* total_len, sk_sketch_set** out);
 
 /* ---- multi-GPU plumbing (the reference is single-process): a sketch set is flattened into ONE
  *      device buffer + a small host metadata vector so that ranks can exchange sketches with a single NCCL all-gather

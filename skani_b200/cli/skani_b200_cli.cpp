@@ -1,12 +1,21 @@
-// skani_b200_cli.cpp -- `skani-b200 triangle|dist`: host driver over the C ABI (include/skani_b200.h).
+// skani_b200_cli.cpp -- `skani-b200 triangle|dist|sketch|search`: host driver over the C ABI (include/skani_b200.h).
 //
-// Mirrors the reference's command drivers for the two commands whose pair loops are the hot path:
+// Mirrors the reference's command drivers:
 //   triangle  src/triangle.rs:13-169  (flags src/cli.rs:236-330, defaults src/parse.rs:790-921)
 //   dist      src/dist.rs:12-190      (flags src/cli.rs:100-232, defaults src/parse.rs:628-788)
+//   sketch    src/sketch.rs:15-201    (consolidated sketches.db / index.db / markers.bin, or --separate-sketches)
+//   search    src/search.rs:16-300    (flags src/cli.rs:332-448, defaults src/parse.rs:380-500)
 // and their writers (TSV src/file_io.rs:15-139,608-678; phylip + .af matrices src/file_io.rs:364-539).
 // FASTA/FASTQ(.gz) record rules follow needletail as skani uses it (ids = whole header line, sequences with line
-// breaks removed, records < 500 bp dropped, src/file_io.rs:141-362).  `sketch` / `search` (on-disk sketch DB formats,
-// src/sketch_db.rs) are not implemented yet.  All heavy work happens on the GPU through libskani_b200.so.
+// breaks removed, records < 500 bp dropped, src/file_io.rs:141-362).  On-disk formats: sketch_db.hpp.
+// All heavy work happens on the GPU through libskani_b200.so.  search keeps the reference's structure but not its memory
+// model: instead of deserialising a reference sketch from the mmap'd database for every passing pair
+// (src/search.rs:142-166) it screens ALL queries against ALL marker sketches in one GPU pass, loads each reference sketch
+// that passed for some query exactly once, imports them to the device in one batch and chains every pair there.
+#include <dirent.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -21,6 +30,7 @@
 #include <vector>
 
 #include "../../include/skani_b200.h"
+#include "sketch_db.hpp"
 
 namespace {
 
@@ -179,6 +189,8 @@ struct Opts {
        small_genomes = false, fast = false, medium = false, slow = false, no_marker_index = false;
   uint64_t n = 1000000000000ull;
   int threads = 3, device = 0;
+  std::string db_dir;               // search -d
+  bool separate_sketches = false;   // sketch --separate-sketches
 };
 
 void write_header(FILE* o, bool ci, bool detailed) {   // src/file_io.rs:15-23
@@ -366,11 +378,290 @@ int run_dist(Opts& op) {
   return 0;
 }
 
+// ---- sketch / search (src/sketch.rs, src/search.rs) --------------------------------------------------------------
+std::string base_name(const std::string& p) { size_t i = p.find_last_of('/'); return i == std::string::npos ? p : p.substr(i + 1); }
+bool path_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+void make_dirs(const std::string& p) {
+  for (size_t i = 1; i <= p.size(); i++)
+    if (i == p.size() || p[i] == '/') mkdir(p.substr(0, i).c_str(), 0777);
+}
+
+// device sketch g -> the host form the database writer takes (records grouped by k-mer, src/types.rs:253-277)
+skdb::HostSketch export_sketch(sk_ctx* ctx, const sk_sketch_set* set, uint32_t g, const Genome& meta, const sk_sketch_params& sp) {
+  uint64_t nr = 0, nk = 0, nm = 0, nc = 0, tl = 0;
+  CK(ctx, sk_sketch_set_genome_info(set, g, &nr, &nk, &nm, &nc, &tl));
+  skdb::HostSketch h;
+  h.file_name = meta.file_name; h.contigs = meta.contigs; h.contig_order = meta.contig_order; h.total_len = tl;
+  h.kmer.resize(nr); h.pos.resize(nr); h.cc.resize(nr); h.markers.resize(nm); h.contig_lengths.resize(nc);
+  CK(ctx, sk_sketch_set_export(set, g, h.kmer.data(), h.pos.data(), h.cc.data(), h.markers.data(), h.contig_lengths.data()));
+  h.c = sp.c; h.k = sp.k; h.marker_c = sp.c;     // the sketch's marker_c field holds c (Sketch::new, src/types.rs:347)
+  return h;
+}
+
+int run_sketch(Opts& op) {
+  resolve_presets(op);
+  if (op.files.empty()) { fprintf(stderr, "ERROR No reference inputs found.\n"); return 1; }
+  if (op.out.empty()) { fprintf(stderr, "ERROR an output folder is required (-o)\n"); return 1; }
+  if (path_exists(op.out)) { fprintf(stderr, "ERROR Output directory exists; output directory must not be an existing directory. Exiting.\n"); return 1; }   // src/sketch.rs:19-22
+  make_dirs(op.out);
+  if (op.separate_sketches && op.individual)
+    fprintf(stderr, "WARN --separate-sketches combined with -i (individual contigs) is NOT compatible with `skani search`.\n");
+  sk_ctx* ctx = nullptr;
+  if (sk_ctx_create(op.device, &ctx) != 0) { fprintf(stderr, "ERROR a CUDA device is required (no CPU fallback)\n"); return 1; }
+  sk_sketch_params sp{op.c, op.k, op.m};
+  skdb::DiskParams dp;
+  dp.c = op.c; dp.k = op.k; dp.marker_c = op.m;
+  skdb::DbWriter w;
+  std::vector<skdb::HostSketch> sep_markers;
+  if (!op.separate_sketches && !w.open(op.out, dp)) { fprintf(stderr, "ERROR Failed to create consolidated database writer\n"); return 1; }
+  std::vector<std::string> files = op.files;
+  std::sort(files.begin(), files.end());
+  size_t total = 0;
+  // files go through the GPU in groups (bounds the host copy of the sequences); database order = (file_name, contig_order)
+  for (size_t f0 = 0; f0 < files.size();) {
+    size_t f1 = f0;
+    uint64_t bytes = 0;
+    while (f1 < files.size() && (f1 == f0 || (f1 - f0 < 4096 && bytes < (8ull << 30)))) {
+      struct stat st;
+      bytes += stat(files[f1].c_str(), &st) == 0 ? (uint64_t)st.st_size * 4 : 0;   // gz inflates ~4x
+      f1++;
+    }
+    Inputs in;
+    load_inputs(std::vector<std::string>(files.begin() + f0, files.begin() + f1), op.individual, std::max(op.threads, 1), in);
+    f0 = f1;
+    if (in.genomes.empty()) continue;
+    sk_sketch_set* set = sketch(ctx, in, sp);
+    size_t j_in_file = 0;
+    for (size_t g = 0; g < in.genomes.size(); g++) {
+      skdb::HostSketch h = export_sketch(ctx, set, (uint32_t)g, in.genomes[g], sp);
+      j_in_file = (g && in.genomes[g].file_name == in.genomes[g - 1].file_name) ? j_in_file + 1 : 0;
+      if (op.separate_sketches) {      // src/sketch.rs:38-101: <basename>.sketch, or <j>_<basename>.sketch with -i
+        std::string name = op.out + "/" + (op.individual ? std::to_string(j_in_file) + "_" : std::string()) + base_name(h.file_name) + ".sketch";
+        skdb::Out o;
+        skdb::put_params(o, dp);
+        skdb::put_sketch(o, h);
+        if (!skdb::write_file(name, o.b)) { fprintf(stderr, "ERROR cannot write %s\n", name.c_str()); return 1; }
+        sep_markers.push_back(skdb::markers_only(h));
+      } else if (!w.add(h)) { fprintf(stderr, "ERROR Failed to add sketch to database\n"); return 1; }
+      if (++total % 100 == 0) fprintf(stderr, "INFO %zu sequences sketched.\n", total);
+    }
+    sk_sketch_set_free(set);
+  }
+  if (op.separate_sketches) {
+    skdb::Out mk;
+    skdb::put_params(mk, dp);
+    mk.u64(sep_markers.size());
+    for (auto& m : sep_markers) skdb::put_sketch(mk, m);
+    if (!skdb::write_file(op.out + "/markers.bin", mk.b)) { fprintf(stderr, "ERROR cannot write markers.bin\n"); return 1; }
+  } else if (!w.finalize()) { fprintf(stderr, "ERROR Failed to finalize consolidated database\n"); return 1; }
+  fprintf(stderr, "INFO Successfully wrote %zu sketches to %s\n", total, op.out.c_str());
+  sk_ctx_destroy(ctx);
+  return 0;
+}
+
+// flatten host sketches for sk_sketch_set_import_batch
+struct Flat {
+  std::vector<uint64_t> rec_off{0}, mk_off{0}, ctg_off{0}, total_len;
+  std::vector<uint32_t> kmer, pos, cc, ctg_len;
+  std::vector<uint64_t> markers;
+  void add(const skdb::HostSketch& h, bool seeds) {
+    if (seeds) {
+      kmer.insert(kmer.end(), h.kmer.begin(), h.kmer.end()); pos.insert(pos.end(), h.pos.begin(), h.pos.end());
+      cc.insert(cc.end(), h.cc.begin(), h.cc.end()); ctg_len.insert(ctg_len.end(), h.contig_lengths.begin(), h.contig_lengths.end());
+    }
+    markers.insert(markers.end(), h.markers.begin(), h.markers.end());
+    rec_off.push_back(kmer.size()); mk_off.push_back(markers.size()); ctg_off.push_back(ctg_len.size());
+    total_len.push_back(h.total_len);
+  }
+  sk_sketch_set* import(sk_ctx* ctx, const sk_sketch_params& sp) {
+    sk_sketch_set* set = nullptr;
+    CK(ctx, sk_sketch_set_import_batch(ctx, &sp, (uint32_t)total_len.size(), rec_off.data(), kmer.data(), pos.data(), cc.data(), mk_off.data(),
+                                       markers.data(), ctg_off.data(), ctg_len.data(), total_len.data(), &set));
+    return set;
+  }
+};
+
+int run_search(Opts& op) {
+  if (op.db_dir.empty()) { fprintf(stderr, "ERROR search needs -d <sketched database folder>\n"); return 1; }
+  if (op.queries.empty()) { fprintf(stderr, "ERROR No query files found.\n"); return 1; }
+  const std::string marker_file = op.db_dir + "/markers.bin";
+  if (!path_exists(marker_file)) { fprintf(stderr, "ERROR markers.bin not found in the folder. Ensure that the folder was generated by `skani sketch`.\n"); return 1; }
+  skdb::DiskParams dp;
+  std::vector<skdb::HostSketch> ref_mk;
+  try { skdb::read_markers_bin(marker_file, dp, ref_mk); }
+  catch (const std::exception& e) { fprintf(stderr, "ERROR Problem reading %s. Exiting. (%s)\n", marker_file.c_str(), e.what()); return 1; }
+  if (dp.use_aa) { fprintf(stderr, "ERROR amino-acid databases are not supported\n"); return 1; }
+  if (ref_mk.empty()) { fprintf(stderr, "ERROR No valid reference fastas or sketches found.\n"); return 1; }
+  const bool consolidated = path_exists(op.db_dir + "/sketches.db") && path_exists(op.db_dir + "/index.db");   // src/sketch_db.rs:142-146
+  std::vector<skdb::IndexEntry> index;
+  int db_fd = -1;
+  if (consolidated) {
+    try { skdb::read_index_db(op.db_dir + "/index.db", index); }
+    catch (const std::exception& e) { fprintf(stderr, "ERROR Failed to load consolidated database: %s\n", e.what()); return 1; }
+    if (index.size() != ref_mk.size()) { fprintf(stderr, "ERROR index.db and markers.bin disagree on the number of sketches\n"); return 1; }
+    db_fd = open((op.db_dir + "/sketches.db").c_str(), O_RDONLY);
+    if (db_fd < 0) { fprintf(stderr, "ERROR Failed to load consolidated database\n"); return 1; }
+  }
+  sk_sketch_params sp{(uint32_t)dp.c, (uint32_t)dp.k, (uint32_t)dp.marker_c};
+  sk_ctx* ctx = nullptr;
+  if (sk_ctx_create(op.device, &ctx) != 0) { fprintf(stderr, "ERROR a CUDA device is required (no CPU fallback)\n"); return 1; }
+  // ---- queries: FASTA/FASTQ sketched with the DATABASE's parameters (src/search.rs:112-123), or .sketch files
+  bool queries_are_sketch = true;
+  for (auto& q : op.queries) if (q.find(".sketch") == std::string::npos && q.find("markers.bin") == std::string::npos) { queries_are_sketch = false; break; }
+  std::vector<Genome> qmeta;
+  sk_sketch_set* qset = nullptr;
+  if (queries_are_sketch) {
+    std::vector<skdb::HostSketch> qs;
+    for (auto& q : op.queries) {
+      if (q.find("markers.bin") != std::string::npos) continue;
+      std::vector<uint8_t> b;
+      if (!skdb::read_file(q, b)) { fprintf(stderr, "ERROR Problem reading sketch file %s. Perhaps your file path is wrong? Exiting.\n", q.c_str()); return 1; }
+      skdb::DiskParams qp;
+      try { qs.push_back(skdb::read_blob(b.data(), b.size(), &qp)); }
+      catch (const std::exception&) { fprintf(stderr, "ERROR %s is not a valid .sketch file or is corrupted.\n", q.c_str()); continue; }
+      if (!(qp == dp)) fprintf(stderr, "WARN Query sketch parameters for %s not equal to reference sketch parameters; no ANI calculated\n", q.c_str());
+    }
+    std::stable_sort(qs.begin(), qs.end(), [](const skdb::HostSketch& a, const skdb::HostSketch& b) { return a.file_name < b.file_name; });   // src/file_io.rs:715
+    if (qs.empty()) { fprintf(stderr, "ERROR No query sketches found.\n"); return 1; }
+    Flat f;
+    for (auto& h : qs) {
+      f.add(h, true);
+      Genome g; g.file_name = h.file_name; g.contigs = h.contigs; g.contig_order = h.contig_order; g.total_len = h.total_len;
+      qmeta.push_back(std::move(g));
+    }
+    qset = f.import(ctx, sp);
+  } else {
+    Inputs qin;
+    load_inputs(op.queries, op.qi, std::max(op.threads, 1), qin);
+    if (qin.genomes.empty()) { fprintf(stderr, "ERROR No query sequences found.\n"); return 1; }
+    qset = sketch(ctx, qin, sp);
+    qmeta = std::move(qin.genomes);
+  }
+  sk_map_params mp{};
+  mp.screen_val = op.s == 0.0 ? 0.80 : op.s / 100.0;              // SEARCH_ANI_CUTOFF_DEFAULT (src/search.rs:40-49)
+  mp.min_aligned_frac = (op.min_af > -1e8 ? op.min_af : -100.0) / 100.0;   // src/parse.rs:444-449; < 0 -> 15 % (src/chain.rs:101-107)
+  mp.both_min_aligned_frac = -0.01;
+  mp.robust = op.robust; mp.median = op.median;
+  mp.rescue_small = 0;
+  mp.learned_ani = !op.no_learned && dp.c >= 70 && !op.qi && !op.median;   // use_learned_ani(c, individual_contig_q, false, median)
+  if (mp.learned_ani) fprintf(stderr, "INFO Learned ANI mode detected. ANI may be adjusted according to a regression model trained on MAGs.\n");
+  const bool use_index = (op.queries.size() > 50 || op.qi) && !op.no_marker_index;   // src/parse.rs:436-442
+  // ---- marker sketches of every reference -> device, one screen of all queries against all references
+  sk_sketch_set* rmk = nullptr;
+  {
+    Flat f;
+    for (auto& h : ref_mk) f.add(h, false);
+    rmk = f.import(ctx, sp);
+  }
+  uint64_t* pairs = nullptr; uint64_t np = 0;
+  CK(ctx, sk_screen_query_ref(ctx, rmk, qset, &mp, use_index ? 3 : 1, &pairs, &np));
+  sk_sketch_set_free(rmk);
+  // file-name order for the switch_qr tie-break (src/chain.rs:19-21): rank all names together
+  std::vector<uint64_t> rrank(ref_mk.size()), qrank(qmeta.size());
+  {
+    std::vector<std::pair<const std::string*, std::pair<int, size_t>>> names;
+    for (size_t i = 0; i < ref_mk.size(); i++) names.push_back({&ref_mk[i].file_name, {0, i}});
+    for (size_t i = 0; i < qmeta.size(); i++) names.push_back({&qmeta[i].file_name, {1, i}});
+    std::sort(names.begin(), names.end(), [](auto& a, auto& b) { return *a.first < *b.first; });
+    uint64_t rank = 0;
+    for (size_t i = 0; i < names.size(); i++) {
+      if (i && *names[i].first != *names[i - 1].first) rank++;
+      (names[i].second.first ? qrank : rrank)[names[i].second.second] = rank;
+    }
+    sk_sketch_set_set_name_ranks(qset, qrank.data());
+  }
+  // ---- references that passed for at least one query: load each ONCE, import in batches, chain their pairs
+  std::vector<uint32_t> hits;
+  for (uint64_t i = 0; i < np; i++) hits.push_back((uint32_t)(pairs[i] >> 32));   // pairs are sorted by (ref, query)
+  hits.erase(std::unique(hits.begin(), hits.end()), hits.end());
+  std::vector<sk_ani_result> kept;
+  size_t pi = 0;
+  for (size_t h0 = 0; h0 < hits.size();) {
+    size_t h1 = h0;
+    std::vector<skdb::HostSketch> loaded;
+    uint64_t recs = 0;
+    while (h1 < hits.size() && h1 - h0 < 60000 && recs < (1ull << 30)) h1++, recs += 45000;   // provisional bound, refined below
+    loaded.resize(h1 - h0);
+    std::vector<int> ok(h1 - h0, 1);
+    {
+      const int T = std::max(op.threads, 1);
+      std::vector<std::thread> pool;
+      for (int t = 0; t < T; t++) pool.emplace_back([&, t] {
+        for (size_t i = h0 + t; i < h1; i += T) {
+          const uint32_t r = hits[i];
+          std::vector<uint8_t> b;
+          bool good;
+          if (consolidated) {
+            b.resize(index[r].length);
+            good = pread(db_fd, b.data(), b.size(), (off_t)index[r].offset) == (ssize_t)b.size();
+          } else {                     // <dir>/<basename(file_name)>.sketch (src/search.rs:157-166)
+            good = skdb::read_file(op.db_dir + "/" + base_name(ref_mk[r].file_name) + ".sketch", b);
+          }
+          try { if (good) loaded[i - h0] = skdb::read_blob(b.data(), b.size()); }
+          catch (const std::exception&) { good = false; }
+          if (!good) { ok[i - h0] = 0; fprintf(stderr, "ERROR Failed to load sketch %s\n", ref_mk[r].file_name.c_str()); }
+        }
+      });
+      for (auto& th : pool) th.join();
+    }
+    // keep the batch under 2^31 records: shrink it if the real sizes exceed the estimate
+    uint64_t real = 0;
+    size_t cut = h0;
+    while (cut < h1 && real + loaded[cut - h0].kmer.size() < (1ull << 31) - 1) real += loaded[cut - h0].kmer.size(), cut++;
+    if (cut == h0) { fprintf(stderr, "ERROR reference sketch too large\n"); return 1; }
+    h1 = cut;
+    Flat f;
+    std::vector<uint64_t> ranks;
+    for (size_t i = h0; i < h1; i++) {
+      if (!ok[i - h0]) loaded[i - h0] = skdb::HostSketch();     // unreadable reference: chains to "no anchors", dropped below
+      f.add(loaded[i - h0], true);
+      ranks.push_back(rrank[hits[i]]);
+    }
+    sk_sketch_set* rset = f.import(ctx, sp);
+    sk_sketch_set_set_name_ranks(rset, ranks.data());
+    std::vector<uint64_t> local;
+    while (pi < np && (uint32_t)(pairs[pi] >> 32) <= hits[h1 - 1]) {
+      const uint32_t r = (uint32_t)(pairs[pi] >> 32);
+      const size_t li = std::lower_bound(hits.begin() + h0, hits.begin() + h1, r) - (hits.begin() + h0);
+      local.push_back(((uint64_t)li << 32) | (uint32_t)pairs[pi]);
+      pi++;
+    }
+    std::vector<sk_ani_result> res(local.size());
+    CK(ctx, sk_chain_pairs(ctx, rset, qset, local.data(), local.size(), &mp, res.data()));
+    for (auto& r : res) if (r.ani > 0.5f) { r.ref_id = hits[h0 + r.ref_id]; kept.push_back(r); }   // src/search.rs:174
+    sk_sketch_set_free(rset);
+    h0 = h1;
+  }
+  sk_free(pairs);
+  if (db_fd >= 0) close(db_fd);
+  // write_query_ref_list (src/file_io.rs:608-678): group by the query's first contig name, ANI descending, top n
+  std::map<std::string, std::vector<const sk_ani_result*>> groups;
+  for (auto& r : kept) groups[qmeta[r.query_id].contigs[0]].push_back(&r);
+  FILE* o = op.out.empty() ? stdout : fopen(op.out.c_str(), "w");
+  if (!o) { fprintf(stderr, "ERROR cannot open %s\n", op.out.c_str()); return 1; }
+  write_header(o, op.ci, op.detailed);
+  for (auto& kv : groups) {
+    auto v = kv.second;
+    std::stable_sort(v.begin(), v.end(), [](const sk_ani_result* a, const sk_ani_result* b) { return a->ani > b->ani; });
+    for (size_t i = 0; i < v.size() && i < op.n; i++) {
+      Genome ref; ref.file_name = ref_mk[v[i]->ref_id].file_name; ref.contigs = ref_mk[v[i]->ref_id].contigs;
+      if (ref.contigs.empty()) ref.contigs.push_back("");
+      write_row(o, *v[i], ref, qmeta[v[i]->query_id], op);
+    }
+  }
+  if (o != stdout) fclose(o);
+  sk_sketch_set_free(qset);
+  sk_ctx_destroy(ctx);
+  return 0;
+}
+
 void usage() {
   fprintf(stderr,
           "skani-b200 (Blackwell implementation of skani v0.3.0's ANI hot path)\n"
           "  skani-b200 triangle [fasta ... | -l list] [-i] [-E|--sparse] [-o out] [--full-matrix] [--diagonal] [--distance]\n"
           "  skani-b200 dist [query] [refs ...] [-q ...] [-r ...] [--ql list] [--rl list] [--qi] [--ri] [-n N] [-o out]\n"
+          "  skani-b200 sketch [fasta ... | -l list] -o new_folder [-i] [--separate-sketches]\n"
+          "  skani-b200 search -d sketch_folder [query ... | -q ... | --ql list] [--qi] [-n N] [-o out]\n"
           "  common: -c C -m M -k K -s SCREEN%% --min-af P --both-min-af P --robust --median --no-learned-ani --faster-small\n"
           "          --small-genomes --fast --medium --slow --ci --detailed --short-header --no-marker-index -t THREADS --device D\n");
 }
@@ -381,7 +672,7 @@ int main(int argc, char** argv) {
   if (argc < 2) { usage(); return 2; }
   Opts op;
   op.cmd = argv[1];
-  if (op.cmd != "triangle" && op.cmd != "dist") { usage(); return 2; }
+  if (op.cmd != "triangle" && op.cmd != "dist" && op.cmd != "sketch" && op.cmd != "search") { usage(); return 2; }
   std::vector<std::string> positional;
   enum { NONE, QS, RS } multi = NONE;
   for (int i = 2; i < argc; i++) {
@@ -426,12 +717,19 @@ int main(int argc, char** argv) {
     else if (a == "--slow") op.slow = true;
     else if (a == "--no-marker-index") op.no_marker_index = true;
     else if (a == "--device") op.device = atoi(val().c_str());
+    else if (a == "-d") op.db_dir = val();
+    else if (a == "--separate-sketches") op.separate_sketches = true;
+    else if (a == "--keep-refs") {}   // search already loads every passing reference exactly once
     else if (a == "-v" || a == "--debug" || a == "--trace") {}
     else { fprintf(stderr, "ERROR unknown option %s\n", a.c_str()); usage(); return 2; }
   }
-  if (op.cmd == "triangle") {
+  if (op.cmd == "triangle" || op.cmd == "sketch") {
     op.files.insert(op.files.end(), positional.begin(), positional.end());
-    return run_triangle(op);
+    return op.cmd == "triangle" ? run_triangle(op) : run_sketch(op);
+  }
+  if (op.cmd == "search") {
+    op.queries.insert(op.queries.end(), positional.begin(), positional.end());
+    return run_search(op);
   }
   // dist: first positional is the query, the rest are references (src/cli.rs:115-121)
   if (!positional.empty()) {

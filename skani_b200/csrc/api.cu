@@ -688,64 +688,101 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
   return sk::sketch_batch_host(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, out, nullptr, 0);
 }
 
-int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t* kmer, const uint32_t* pos,
-                         const uint32_t* cc, uint64_t n_records, const uint64_t* markers, uint64_t n_markers,
-                         const uint32_t* contig_lengths, uint32_t n_contigs, sk_sketch_set** out) {
-  if (!ctx || !out || (n_records && (!kmer || !pos || !cc)) || (n_markers && !markers) || (n_contigs && !contig_lengths)) return SK_ERR_PARAM;
+int sk_sketch_set_import_batch(sk_ctx* ctx, const sk_sketch_params* sp, uint32_t n_genomes, const uint64_t* rec_off,
+                               const uint32_t* kmer, const uint32_t* pos, const uint32_t* cc, const uint64_t* mk_off,
+                               const uint64_t* markers, const uint64_t* ctg_off, const uint32_t* contig_lengths,
+                               const uint64_t* total_len, sk_sketch_set** out) {
+  if (!ctx || !out || n_genomes == 0 || !rec_off || !mk_off || !ctg_off) return SK_ERR_PARAM;
+  const uint32_t G = n_genomes;
+  const uint64_t r0 = rec_off[0], m0 = mk_off[0], c0 = ctg_off[0];
+  const uint64_t n_records = rec_off[G] - r0, n_markers = mk_off[G] - m0, n_contigs = ctg_off[G] - c0;
+  if ((n_records && (!kmer || !pos || !cc)) || (n_markers && !markers) || (n_contigs && !contig_lengths)) return SK_ERR_PARAM;
   SK_CUDA(cudaSetDevice(ctx->device));
   SK_TRY(check_sketch_params(ctx, sp));
-  if (n_records >= (1ull << 31) || n_markers >= (1ull << 31)) { ctx->err = "sketch too large"; return SK_ERR_PARAM; }
-  sk_sketch_set* s = new sk_sketch_set();
-  s->ctx = ctx; s->sp = *sp; s->G = 1;
-  struct Guard { sk_sketch_set* s; ~Guard() { if (s) { free_set_device(s); delete s; } } } guard{s};
-  // position view = records ordered by (contig, pos)
-  std::vector<uint32_t> order(n_records);
-  for (uint64_t i = 0; i < n_records; i++) order[i] = (uint32_t)i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-    uint32_t ca = cc[a] >> 1, cb = cc[b] >> 1;
-    if (ca != cb) return ca < cb;
-    return pos[a] < pos[b];
-  });
-  std::vector<uint32_t> hk(n_records), hp(n_records), hc(n_records);
-  std::vector<uint32_t> crl(n_contigs + 2, 0);
-  for (uint64_t i = 0; i < n_records; i++) {
-    hk[i] = kmer[order[i]]; hp[i] = pos[order[i]]; hc[i] = cc[order[i]];
-    uint32_t ctg = hc[i] >> 1;
-    if (ctg >= n_contigs) { ctx->err = "record contig index out of range"; return SK_ERR_PARAM; }
-    crl[ctg + 1]++;
+  if (n_records >= (1ull << 31) || n_markers >= (1ull << 31) || n_contigs >= (1ull << 31)) {
+    ctx->err = "import batch too large (>= 2^31 records, markers or contigs): import in several batches and sk_sketch_set_append";
+    return SK_ERR_PARAM;
   }
-  for (uint32_t c = 0; c < n_contigs; c++) crl[c + 1] += crl[c];
+  for (uint32_t g = 0; g < G; g++)
+    if (rec_off[g + 1] < rec_off[g] || mk_off[g + 1] < mk_off[g] || ctg_off[g + 1] < ctg_off[g]) { ctx->err = "offsets must be non-decreasing"; return SK_ERR_PARAM; }
+  sk_sketch_set* s = new sk_sketch_set();
+  s->ctx = ctx; s->sp = *sp; s->G = G;
+  struct Guard { sk_sketch_set* s; ~Guard() { if (s) { free_set_device(s); delete s; } } } guard{s};
+  // position view = each genome's records ordered by (contig, pos); per-contig first-record table with one sentinel per genome
+  std::vector<uint32_t> hk(n_records), hp(n_records), hc(n_records);
+  std::vector<uint32_t> crl(n_contigs + G + 1, 0);
+  std::vector<int> bad(G, 0);
+  auto do_genome = [&](uint32_t g) {
+    const uint64_t a = rec_off[g], e = rec_off[g + 1], n = e - a;
+    const uint32_t nc = (uint32_t)(ctg_off[g + 1] - ctg_off[g]);
+    std::vector<uint32_t> order(n);
+    for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+      const uint32_t cx = cc[a + x] >> 1, cy = cc[a + y] >> 1;
+      if (cx != cy) return cx < cy;
+      return pos[a + x] < pos[a + y];
+    });
+    uint32_t* tab = crl.data() + (ctg_off[g] - c0) + g;          // nc + 1 entries
+    for (uint64_t i = 0; i < n; i++) {
+      const uint64_t src = a + order[i], dst = a - r0 + i;
+      hk[dst] = kmer[src]; hp[dst] = pos[src]; hc[dst] = cc[src];
+      const uint32_t ctg = hc[dst] >> 1;
+      if (ctg >= nc) { bad[g] = 1; return; }
+      if (ctg + 1 < nc + 1) tab[ctg + 1]++;
+    }
+    for (uint32_t c = 0; c < nc; c++) tab[c + 1] += tab[c];
+  };
+  {
+    const unsigned T = std::max(1u, std::min(8u, std::min((unsigned)G, std::thread::hardware_concurrency())));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; t++) pool.emplace_back([&, t] { for (uint32_t g = t; g < G; g += T) do_genome(g); });
+    for (auto& th : pool) th.join();
+  }
+  for (uint32_t g = 0; g < G; g++) if (bad[g]) { ctx->err = "record contig index out of range"; return SK_ERR_PARAM; }
   s->S = n_records; s->C = n_contigs;
-  s->seed_off = {0, n_records};
-  s->ctg_off = {0, n_contigs};
-  s->ctg_len.assign(contig_lengths, contig_lengths + n_contigs);
-  uint64_t tl = 0;
-  for (uint32_t c = 0; c < n_contigs; c++) tl += contig_lengths[c];
-  s->total_len = {tl};
-  s->name_rank = {0};
-  size_t S1 = std::max<size_t>(n_records, 1);
+  s->seed_off.resize(G + 1); s->ctg_off.resize(G + 1);
+  for (uint32_t g = 0; g <= G; g++) { s->seed_off[g] = rec_off[g] - r0; s->ctg_off[g] = ctg_off[g] - c0; }
+  if (n_contigs) s->ctg_len.assign(contig_lengths + c0, contig_lengths + c0 + n_contigs);
+  s->total_len.resize(G);
+  s->name_rank.resize(G);
+  for (uint32_t g = 0; g < G; g++) {
+    uint64_t tl = 0;
+    if (total_len) tl = total_len[g];
+    else for (uint64_t c = ctg_off[g]; c < ctg_off[g + 1]; c++) tl += contig_lengths[c];
+    s->total_len[g] = tl;
+    s->name_rank[g] = g;
+  }
+  const size_t S1 = std::max<size_t>(n_records, 1);
   SK_CUDA(ctx->arena.alloc((void**)&s->pv_kmer, S1 * 4)); SK_CUDA(ctx->arena.alloc((void**)&s->pv_pos, S1 * 4));
   SK_CUDA(ctx->arena.alloc((void**)&s->pv_cc, S1 * 4));
   SK_CUDA(ctx->arena.alloc((void**)&s->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
-  SK_CUDA(ctx->arena.alloc((void**)&s->ctg_rec_off, (size_t)(n_contigs + 2) * 4));
+  SK_CUDA(ctx->arena.alloc((void**)&s->ctg_rec_off, (size_t)(n_contigs + G + 1) * 4));
   SK_CUDA(cudaStreamSynchronize(ctx->stream));
   if (n_records) {
     SK_CUDA(cudaMemcpy(s->pv_kmer, hk.data(), n_records * 4, cudaMemcpyHostToDevice));
     SK_CUDA(cudaMemcpy(s->pv_pos, hp.data(), n_records * 4, cudaMemcpyHostToDevice));
     SK_CUDA(cudaMemcpy(s->pv_cc, hc.data(), n_records * 4, cudaMemcpyHostToDevice));
   }
-  if (n_contigs) SK_CUDA(cudaMemcpy(s->d_ctg_len, contig_lengths, n_contigs * 4, cudaMemcpyHostToDevice));
-  SK_CUDA(cudaMemcpy(s->ctg_rec_off, crl.data(), (size_t)(n_contigs + 1) * 4, cudaMemcpyHostToDevice));
+  if (n_contigs) SK_CUDA(cudaMemcpy(s->d_ctg_len, contig_lengths + c0, n_contigs * 4, cudaMemcpyHostToDevice));
+  SK_CUDA(cudaMemcpy(s->ctg_rec_off, crl.data(), (size_t)(n_contigs + G) * 4, cudaMemcpyHostToDevice));
   DTmp<uint64_t> mraw;
   SK_CUDA(mraw.alloc(n_markers, ctx));
-  if (n_markers) SK_CUDA(cudaMemcpyAsync(mraw.p, markers, n_markers * 8, cudaMemcpyHostToDevice, ctx->stream));  // bulk
-  std::vector<uint64_t> raw_off = {0, n_markers};
+  if (n_markers) SK_CUDA(cudaMemcpy(mraw.p, markers + m0, n_markers * 8, cudaMemcpyHostToDevice));
+  std::vector<uint64_t> raw_off(G + 1);
+  for (uint32_t g = 0; g <= G; g++) raw_off[g] = mk_off[g] - m0;
   SK_TRY(build_views(ctx, s, mraw.p, raw_off));
   SK_TRY(build_hash(ctx, s));
   SK_CUDA(cudaStreamSynchronize(ctx->stream));
   guard.s = nullptr;
   *out = s;
   return SK_OK;
+}
+
+int sk_sketch_set_import(sk_ctx* ctx, const sk_sketch_params* sp, const uint32_t* kmer, const uint32_t* pos,
+                         const uint32_t* cc, uint64_t n_records, const uint64_t* markers, uint64_t n_markers,
+                         const uint32_t* contig_lengths, uint32_t n_contigs, sk_sketch_set** out) {
+  const uint64_t ro[2] = {0, n_records}, mo[2] = {0, n_markers}, co[2] = {0, n_contigs};
+  return sk_sketch_set_import_batch(ctx, sp, 1, ro, kmer, pos, cc, mo, markers, co, contig_lengths, nullptr, out);
 }
 
 }  // extern "C"

@@ -193,6 +193,32 @@ def sketch_sequences(ctx, genomes, sp=None, individual_contig=False):
     return s
 
 
+def import_sketches(ctx, sketches, sp=None, seeds=True):
+    """Device sketch set from host-side sketches (e.g. decoded from a skani database; reference
+    file_io::sketches_from_sketch src/file_io.rs:680, sketch_db::get_sketch src/sketch_db.rs:104).  sketches: list of dicts
+    with kmer / pos / cc (seed records, any order), markers (distinct), contig_lengths and optionally total_len, i.e. what
+    SketchSet.export returns.  seeds=False imports the markers only (the markers.bin form, Sketch::get_markers_only)."""
+    sp = sp or sketch_params()
+    n = len(sketches)
+    z32, z64 = np.zeros(0, np.uint32), np.zeros(0, np.uint64)
+    cat = lambda key, z: np.ascontiguousarray(np.concatenate([np.asarray(s[key], z.dtype) for s in sketches] + [z]))
+    off = lambda key: np.ascontiguousarray(np.concatenate([[0], np.cumsum([len(s[key]) for s in sketches])]).astype(np.uint64))
+    if seeds:
+        kmer, pos, cc, cl = cat("kmer", z32), cat("pos", z32), cat("cc", z32), cat("contig_lengths", z32)
+        rec_off, ctg_off = off("kmer"), off("contig_lengths")
+    else:
+        kmer = pos = cc = cl = np.zeros(1, np.uint32)
+        rec_off = ctg_off = np.zeros(n + 1, np.uint64)
+    mk, mk_off = cat("markers", z64), off("markers")
+    tl = np.ascontiguousarray([int(s["total_len"]) if "total_len" in s else int(np.sum(s["contig_lengths"], dtype=np.uint64)) for s in sketches],
+                              np.uint64)
+    h = C.c_void_p()
+    ctx.check(ctx.L.sk_sketch_set_import_batch(ctx.h, C.byref(sp), n, rec_off.ctypes.data, kmer.ctypes.data, pos.ctypes.data, cc.ctypes.data,
+                                               mk_off.ctypes.data, mk.ctypes.data, ctg_off.ctypes.data, cl.ctypes.data, tl.ctypes.data,
+                                               C.byref(h)))
+    return SketchSet(ctx, h)
+
+
 def _pairs_out(ctx, fn, *args):
     pp = C.POINTER(C.c_uint64)(); n = C.c_uint64()
     ctx.check(fn(*args, C.byref(pp), C.byref(n)))

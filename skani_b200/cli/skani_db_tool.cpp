@@ -3,6 +3,8 @@
 //   skani-db-tool write <dir> <c> <k> <marker_c>   < sketches in the text form below  -> sketches.db, index.db, markers.bin
 //   skani-db-tool dump  <dir>                       -> the same text form, read back through index.db / sketches.db /
 //                                                      markers.bin (records sorted by (kmer, contig, pos), markers ascending)
+//   skani-db-tool fastx <file>                      -> the CLI's FASTA/FASTQ(.gz) reader (fastx.hpp): "OK n" then one line per
+//                                                      record "<length> <fnv1a64 of the sequence> <id>", or "ERR"
 // Text form, one sketch = the lines
 //   S <contig_order> <total_len> <file name>
 //   C <contig header>            (one line per contig)
@@ -15,6 +17,7 @@
 #include <numeric>
 #include <sstream>
 
+#include "fastx.hpp"
 #include "sketch_db.hpp"
 
 using namespace skdb;
@@ -92,6 +95,17 @@ int main(int argc, char** argv) {
         print_sketch(s, "S");
       }
       for (auto& m : mk) print_sketch(m, "K");
+      return 0;
+    }
+    if (argc >= 3 && std::string(argv[1]) == "fastx") {
+      std::vector<fastx::Record> recs;
+      if (!fastx::read_fastx(argv[2], recs)) { printf("ERR\n"); return 0; }
+      printf("OK %zu\n", recs.size());
+      for (auto& r : recs) {
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (unsigned char ch : r.seq) { h ^= ch; h *= 0x100000001b3ull; }
+        printf("%zu %llu %s\n", r.seq.size(), (unsigned long long)h, r.id.c_str());
+      }
       return 0;
     }
   } catch (const std::exception& e) {

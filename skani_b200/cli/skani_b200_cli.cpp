@@ -186,16 +186,87 @@ void resolve_presets(Opts& op) {   // src/parse.rs:829-853 / 680-710
   if (op.c > op.m) { fprintf(stderr, "ERROR We currently don't allow c (%u) > m (%u). -m should be larger than c.\n", op.c, op.m); exit(1); }  // src/params.rs:183
 }
 
+// flatten host sketches for sk_sketch_set_import_batch
+struct Flat {
+  std::vector<uint64_t> rec_off{0}, mk_off{0}, ctg_off{0}, total_len;
+  std::vector<uint32_t> kmer, pos, cc, ctg_len;
+  std::vector<uint64_t> markers;
+  void add(const skdb::HostSketch& h, bool seeds) {
+    if (seeds) {
+      kmer.insert(kmer.end(), h.kmer.begin(), h.kmer.end()); pos.insert(pos.end(), h.pos.begin(), h.pos.end());
+      cc.insert(cc.end(), h.cc.begin(), h.cc.end()); ctg_len.insert(ctg_len.end(), h.contig_lengths.begin(), h.contig_lengths.end());
+    }
+    markers.insert(markers.end(), h.markers.begin(), h.markers.end());
+    rec_off.push_back(kmer.size()); mk_off.push_back(markers.size()); ctg_off.push_back(ctg_len.size());
+    total_len.push_back(h.total_len);
+  }
+  sk_sketch_set* import(sk_ctx* ctx, const sk_sketch_params& sp) {
+    sk_sketch_set* set = nullptr;
+    CK(ctx, sk_sketch_set_import_batch(ctx, &sp, (uint32_t)total_len.size(), rec_off.data(), kmer.data(), pos.data(), cc.data(), mk_off.data(),
+                                       markers.data(), ctg_off.data(), ctg_len.data(), total_len.data(), &set));
+    return set;
+  }
+};
+
+// inputs given as .sketch files (refs_are_sketch / queries_are_sketch, src/parse.rs:264-275): every file name contains
+// ".sketch" or "markers.bin"
+bool all_sketch_files(const std::vector<std::string>& files) {
+  if (files.empty()) return false;
+  for (auto& f : files) if (f.find(".sketch") == std::string::npos && f.find("markers.bin") == std::string::npos) return false;
+  return true;
+}
+
+// file_io::sketches_from_sketch (src/file_io.rs:680-717): one (SketchParams, Sketch) blob per file, markers.bin skipped,
+// result sorted by file name; the sketches' parameters replace the command line's.  Then straight to the device.
+sk_sketch_set* load_sketch_files(sk_ctx* ctx, const std::vector<std::string>& files, skdb::DiskParams& dp, std::vector<Genome>& meta) {
+  std::vector<skdb::HostSketch> hs;
+  for (auto& f : files) {
+    if (f.find("markers.bin") != std::string::npos) continue;
+    std::vector<uint8_t> b;
+    if (!skdb::read_file(f, b)) { fprintf(stderr, "ERROR Problem reading sketch file %s. Perhaps your file path is wrong? Exiting.\n", f.c_str()); exit(1); }
+    try { hs.push_back(skdb::read_blob(b.data(), b.size(), &dp)); }
+    catch (const std::exception&) {
+      fprintf(stderr, "ERROR %s is not a valid .sketch file or is corrupted. Skani v0.3+ is not compatible with older sketch files.\n", f.c_str());
+    }
+  }
+  if (hs.empty()) return nullptr;
+  if (dp.use_aa) { fprintf(stderr, "ERROR amino-acid sketches are not supported\n"); exit(1); }
+  std::stable_sort(hs.begin(), hs.end(), [](const skdb::HostSketch& x, const skdb::HostSketch& y) { return x.file_name < y.file_name; });
+  Flat f;
+  for (auto& h : hs) {
+    f.add(h, true);
+    Genome g; g.file_name = h.file_name; g.contigs = h.contigs; g.contig_order = h.contig_order; g.total_len = h.total_len;
+    if (g.contigs.empty()) g.contigs.push_back("");
+    meta.push_back(std::move(g));
+  }
+  sk_sketch_params sp{(uint32_t)dp.c, (uint32_t)dp.k, (uint32_t)dp.marker_c};
+  return f.import(ctx, sp);
+}
+
 int run_triangle(Opts& op) {
   resolve_presets(op);
   if (op.files.empty()) { fprintf(stderr, "ERROR No reference inputs found.\n"); return 1; }
   Inputs in;
-  load_inputs(op.files, op.individual, std::max(op.threads, 1), in);
-  if (in.genomes.empty()) { fprintf(stderr, "ERROR No genomes/sketches found.\n"); return 1; }   // src/triangle.rs:46-49
-  if (in.genomes.size() > 500 && !op.sparse) fprintf(stderr, "WARN > 500 genomes detected. The output matrix will be large. Consider using -E or --sparse for a tsv output instead.\n");
+  const bool refs_are_sketch = all_sketch_files(op.files);
+  if (!refs_are_sketch) {
+    load_inputs(op.files, op.individual, std::max(op.threads, 1), in);
+    if (in.genomes.empty()) { fprintf(stderr, "ERROR No genomes/sketches found.\n"); return 1; }   // src/triangle.rs:46-49
+  }
   sk_ctx* ctx = nullptr;
   if (sk_ctx_create(op.device, &ctx) != 0) { fprintf(stderr, "ERROR a CUDA device is required (no CPU fallback)\n"); return 1; }
   sk_sketch_params sp{op.c, op.k, op.m};
+  sk_sketch_set* loaded = nullptr;
+  if (refs_are_sketch) {      // src/triangle.rs:16-24
+    fprintf(stderr, "INFO Sketches detected.\n");
+    skdb::DiskParams dp;
+    loaded = load_sketch_files(ctx, op.files, dp, in.genomes);
+    if (!loaded) { fprintf(stderr, "ERROR No genomes/sketches found.\n"); return 1; }
+    if (dp.c != op.c || dp.marker_c != op.m)
+      fprintf(stderr, "WARN Input parameter c = %u, m = %u is not equal to the sketch parameter c = %llu,m = %llu. Using sketch parameters.\n", op.c, op.m,
+              (unsigned long long)dp.c, (unsigned long long)dp.marker_c);
+    sp = sk_sketch_params{(uint32_t)dp.c, (uint32_t)dp.k, (uint32_t)dp.marker_c};
+  }
+  if (in.genomes.size() > 500 && !op.sparse) fprintf(stderr, "WARN > 500 genomes detected. The output matrix will be large. Consider using -E or --sparse for a tsv output instead.\n");
   sk_map_params mp{};
   mp.screen_val = op.s / 100.0;
   mp.min_aligned_frac = (op.min_af > -1e8 ? op.min_af : 15.0) / 100.0;
@@ -204,7 +275,7 @@ int run_triangle(Opts& op) {
   mp.rescue_small = !op.faster_small && !op.small_genomes;
   mp.learned_ani = !op.no_learned && op.c >= 70 && !op.individual && !op.median;   // regression::use_learned_ani (src/regression.rs:8-10)
   if (mp.learned_ani) fprintf(stderr, "INFO Learned ANI mode detected. ANI may be adjusted according to a regression model trained on MAGs.\n");
-  sk_sketch_set* set = sketch(ctx, in, sp);
+  sk_sketch_set* set = loaded ? loaded : sketch(ctx, in, sp);
   {  // file-name order for the switch_qr tie-break (src/chain.rs:19-21): with -i all records of a file share its name
     std::vector<uint64_t> ranks(in.genomes.size());
     uint64_t rank = 0;
@@ -270,12 +341,34 @@ int run_dist(Opts& op) {
   resolve_presets(op);
   if (op.refs.empty() || op.queries.empty()) { fprintf(stderr, "ERROR No reference sketches/genomes or query sketches/genomes found.\n"); return 1; }
   Inputs rin, qin;
-  load_inputs(op.refs, op.ri, std::max(op.threads, 1), rin);
-  load_inputs(op.queries, op.qi, std::max(op.threads, 1), qin);
-  if (rin.genomes.empty() || qin.genomes.empty()) { fprintf(stderr, "ERROR No reference sketches/genomes or query sketches/genomes found.\n"); return 1; }
+  const bool refs_are_sketch = all_sketch_files(op.refs), queries_are_sketch = all_sketch_files(op.queries);
   sk_ctx* ctx = nullptr;
   if (sk_ctx_create(op.device, &ctx) != 0) { fprintf(stderr, "ERROR a CUDA device is required (no CPU fallback)\n"); return 1; }
   sk_sketch_params sp{op.c, op.k, op.m};
+  sk_sketch_set *rset = nullptr, *qset = nullptr;
+  // .sketch inputs carry their own parameters, which then also apply to FASTA inputs on the other side (src/dist.rs:17-50)
+  if (refs_are_sketch) {
+    fprintf(stderr, "INFO Sketches detected.\n");
+    skdb::DiskParams dp;
+    rset = load_sketch_files(ctx, op.refs, dp, rin.genomes);
+    if (rset) {
+      if (dp.c != sp.c || dp.k != sp.k || dp.marker_c != sp.marker_c)
+        fprintf(stderr, "WARN Parameters from .sketch files not equal to the input parameters. Using parameters from .sketch files.\n");
+      sp = sk_sketch_params{(uint32_t)dp.c, (uint32_t)dp.k, (uint32_t)dp.marker_c};
+    }
+  }
+  if (queries_are_sketch) {
+    skdb::DiskParams dp;
+    qset = load_sketch_files(ctx, op.queries, dp, qin.genomes);
+    if (qset && (dp.c != sp.c || dp.k != sp.k || dp.marker_c != sp.marker_c)) {
+      if (refs_are_sketch) { fprintf(stderr, "ERROR Query sketch parameters were not equal to reference sketch parameters. Exiting.\n"); return 1; }
+      fprintf(stderr, "WARN Parameters from .sketch files not equal to the input parameters. Using parameters from .sketch files.\n");
+      sp = sk_sketch_params{(uint32_t)dp.c, (uint32_t)dp.k, (uint32_t)dp.marker_c};
+    }
+  }
+  if (!refs_are_sketch) load_inputs(op.refs, op.ri, std::max(op.threads, 1), rin);
+  if (!queries_are_sketch) load_inputs(op.queries, op.qi, std::max(op.threads, 1), qin);
+  if (rin.genomes.empty() || qin.genomes.empty()) { fprintf(stderr, "ERROR No reference sketches/genomes or query sketches/genomes found.\n"); return 1; }
   sk_map_params mp{};
   mp.screen_val = op.s / 100.0;
   mp.min_aligned_frac = (op.min_af > -1e8 ? op.min_af : 15.0) / 100.0;
@@ -285,8 +378,8 @@ int run_dist(Opts& op) {
   mp.learned_ani = !op.no_learned && op.c >= 70 && !op.qi && !op.ri && !op.median;
   if (mp.learned_ani) fprintf(stderr, "INFO Learned ANI mode detected. ANI may be adjusted according to a regression model trained on MAGs.\n");
   const bool use_index = (op.queries.size() > 50 || op.qi) && !op.no_marker_index;   // FULL_INDEX_THRESH (src/parse.rs:750)
-  sk_sketch_set* rset = sketch(ctx, rin, sp);
-  sk_sketch_set* qset = sketch(ctx, qin, sp);
+  if (!rset) rset = sketch(ctx, rin, sp);
+  if (!qset) qset = sketch(ctx, qin, sp);
   // file-name order for the switch_qr tie-break (src/chain.rs:19-21): rank all names together
   {
     std::vector<std::pair<std::string, std::pair<int, size_t>>> names;
@@ -404,28 +497,6 @@ int run_sketch(Opts& op) {
   sk_ctx_destroy(ctx);
   return 0;
 }
-
-// flatten host sketches for sk_sketch_set_import_batch
-struct Flat {
-  std::vector<uint64_t> rec_off{0}, mk_off{0}, ctg_off{0}, total_len;
-  std::vector<uint32_t> kmer, pos, cc, ctg_len;
-  std::vector<uint64_t> markers;
-  void add(const skdb::HostSketch& h, bool seeds) {
-    if (seeds) {
-      kmer.insert(kmer.end(), h.kmer.begin(), h.kmer.end()); pos.insert(pos.end(), h.pos.begin(), h.pos.end());
-      cc.insert(cc.end(), h.cc.begin(), h.cc.end()); ctg_len.insert(ctg_len.end(), h.contig_lengths.begin(), h.contig_lengths.end());
-    }
-    markers.insert(markers.end(), h.markers.begin(), h.markers.end());
-    rec_off.push_back(kmer.size()); mk_off.push_back(markers.size()); ctg_off.push_back(ctg_len.size());
-    total_len.push_back(h.total_len);
-  }
-  sk_sketch_set* import(sk_ctx* ctx, const sk_sketch_params& sp) {
-    sk_sketch_set* set = nullptr;
-    CK(ctx, sk_sketch_set_import_batch(ctx, &sp, (uint32_t)total_len.size(), rec_off.data(), kmer.data(), pos.data(), cc.data(), mk_off.data(),
-                                       markers.data(), ctg_off.data(), ctg_len.data(), total_len.data(), &set));
-    return set;
-  }
-};
 
 int run_search(Opts& op) {
   if (op.db_dir.empty()) { fprintf(stderr, "ERROR search needs -d <sketched database folder>\n"); return 1; }

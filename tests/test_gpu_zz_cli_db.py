@@ -94,3 +94,25 @@ def test_sketch_then_search(tmp_path):
     want_i = sorted((osk[r.ref_id].file_name, qi[r.query_id].file_name, f2(r.ani), f2(r.af_ref), f2(r.af_query),
                      osk[r.ref_id].contig_name(0), qi[r.query_id].contig_name(0)) for r in exp_i)
     assert rows_of(run(["search", "-d", db, FILES[1], "--qi"])) == want_i
+
+
+def test_sketch_files_as_dist_and_triangle_inputs(tmp_path):
+    """.sketch files instead of FASTA (refs_are_sketch / queries_are_sketch, src/dist.rs:17-50, src/triangle.rs:16-24): the
+    reference's golden G8 with its literal argument shape `dist -r EC590.sketch markers.bin -q reads --qi --robust`
+    (test_results_versions/0.3.0:153-421), and triangle over a sketch folder == triangle over the FASTA files."""
+    sep = str(tmp_path / "sep")
+    run(["sketch"] + FILES + ["-o", sep, "--separate-sketches"])
+    gold = {}
+    for ln in open(os.path.join(GOLD, "g8_dist_qi_robust.tsv")):
+        if not ln.startswith("#"):
+            ani, afr, afq, name = ln.rstrip("\n").split("\t")
+            gold[name] = (ani, afr, afq)
+    out = run(["dist", "-r", os.path.join(sep, "e.coli-EC590.fasta.gz.sketch"), os.path.join(sep, "markers.bin"),
+               "-q", os.path.join(GOLD, "o157_reads.fa.gz"), "--qi", "--robust"])
+    rows = [ln.split("\t") for ln in out.strip().split("\n")[1:]]
+    assert len(rows) == 269 and {r[6]: (r[2], r[3], r[4]) for r in rows} == gold
+    assert all(r[0] == sorted(FILES)[0] for r in rows)            # Ref_file = the name stored in the sketch
+    sk_files = [os.path.join(sep, os.path.basename(f) + ".sketch") for f in FILES]
+    assert rows_of(run(["triangle", "-E"] + sk_files + [os.path.join(sep, "markers.bin")])) == rows_of(run(["triangle", "-E"] + FILES))
+    both = rows_of(run(["dist", "-q", sk_files[2], "-r", sk_files[0]]))           # query EC590, ref K12: README pair (G13)
+    assert [b[2:5] for b in both] == [("99.39", "91.89", "92.46")]

@@ -1475,7 +1475,6 @@ static int chain_impl(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_se
   if (refs->sp.c != qs->sp.c || refs->sp.k != qs->sp.k) { ctx->err = "ref/query sketch parameters differ"; return SK_ERR_PARAM; }
   if (n_pairs == 0) return SK_OK;
   SK_TRY(upload_tables(ctx));
-  cudaStream_t st = ctx->stream;
   ChainParams prm;
   prm.c = refs->sp.c; prm.k = refs->sp.k;
   prm.band = BP_CHAIN_BAND / refs->sp.c;                       // index_chain_band (src/chain.rs:111-112)

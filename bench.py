@@ -155,6 +155,12 @@ def cpu_baseline(args, threads):
                                                                                               d["n_chained"], N / S)}, d
 
 
+def workload_name(N, L, G):
+    """config.workload, identical for both arms (same synthetic set, same sketch parameters)"""
+    return ("triangle %d x %d bp synthetic clustered (G=%d, subst 0.1-5%%, inversions, 50-contig members), c=125 k=15 m=1000; "
+            "inputs %.1f GB >> L2 (no flush needed)" % (N, L, G, N * L / 1e9))
+
+
 # ------------------------------------------------------------------------------------------------------------
 # reference arm
 # ------------------------------------------------------------------------------------------------------------
@@ -178,7 +184,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
             "ms_per_step": float(np.mean([x[1] for x in vals])) * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "triangle %d x %d bp synthetic clustered (G=%d), c=125 k=15 m=1000" % (args.genomes, args.genome_len, args.cluster)},
+            "config": {"workload": workload_name(args.genomes, args.genome_len, args.cluster), "genomes": args.genomes,
+                       "genome_len": args.genome_len, "pairs": args.genomes * (args.genomes - 1) // 2},
             "cpu_baseline": last, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -294,9 +301,7 @@ def main():
         line = {"metric": METRIC, "value": total_pairs / (ms_val * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_val, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic",
-                "config": {"workload": "triangle %d x %d bp synthetic clustered (G=%d, subst 0.1-5%%, inversions, 50-contig members), "
-                                       "c=125 k=15 m=1000; inputs %.1f GB >> L2 (no flush needed)" % (N, L, G, N * L / 1e9),
-                           "genomes": N, "genome_len": L, "pairs": total_pairs, "kept_pairs_rank0": kept,
+                "config": {"workload": workload_name(N, L, G), "genomes": N, "genome_len": L, "pairs": total_pairs, "kept_pairs_rank0": kept,
                            "host_gen_s": round(t_gen, 2)},
                 "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(N * L), "d2h_bytes_per_step": int(result_bytes[0])},

@@ -20,3 +20,14 @@ def have_reference():
 
 needs_reference = pytest.mark.skipif(not have_reference(),
                                      reason="/root/reference fixtures not present (GPU box)")
+
+
+def db_tool():
+    """Path of the host-only database / FASTX helper (skani_b200/cli/skani_db_tool.cpp); built on demand (g++, no CUDA)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "skani_b200", "skani-db-tool")
+    src = [os.path.join(root, "skani_b200", "cli", f) for f in ("skani_db_tool.cpp", "sketch_db.hpp", "fastx.hpp")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(f) for f in src):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, src[0], "-lz"])
+    return exe

@@ -11,7 +11,9 @@ import pytest
 from fasta_py import read_fastx
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TOOL = os.path.join(ROOT, "skani_b200", "skani-db-tool")
+from conftest import db_tool
+
+TOOL = db_tool()
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 

@@ -13,7 +13,9 @@ import skani_db_py as D
 from fasta_py import read_fastx as read_fasta
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TOOL = os.path.join(ROOT, "skani_b200", "skani-db-tool")
+from conftest import db_tool
+
+TOOL = db_tool()
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
@@ -30,7 +32,6 @@ def text_of(name, order, sk, contig_names):
 
 
 def test_db_roundtrip_against_python_decoder(tmp_path):
-    assert os.path.exists(TOOL), "run ./build.sh (or __graft_entry__.build()) first"
     rng = np.random.default_rng(3)
     sketches = []
     # a multi-contig genome with repeated k-mers (multi-position entries), a one-contig genome, and a genome with no seeds

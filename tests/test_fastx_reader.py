@@ -12,8 +12,6 @@ from fasta_py import read_fastx
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from conftest import db_tool
-
-TOOL = db_tool()
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
@@ -25,7 +23,7 @@ def fnv(b):
 
 
 def tool(path):
-    out = subprocess.run([TOOL, "fastx", str(path)], check=True, capture_output=True).stdout.decode().split("\n")
+    out = subprocess.run([db_tool(), "fastx", str(path)], check=True, capture_output=True).stdout.decode().split("\n")
     if out[0] == "ERR":
         return None
     n = int(out[0].split()[1])

@@ -14,8 +14,6 @@ from fasta_py import read_fastx as read_fasta
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from conftest import db_tool
-
-TOOL = db_tool()
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
@@ -49,7 +47,7 @@ def test_db_roundtrip_against_python_decoder(tmp_path):
         exports.append(e)
     d = str(tmp_path / "db")
     os.makedirs(d)
-    subprocess.run([TOOL, "write", d, "30", "15", "200"], input=text.encode(), check=True)
+    subprocess.run([db_tool(), "write", d, "30", "15", "200"], input=text.encode(), check=True)
     par, sk, mk, index = D.read_db(d)
     # SketchParams blob: all 626 bytes as SketchParams::new(200, 30, 15, false, false) serialises them
     assert open(os.path.join(d, "markers.bin"), "rb").read(626) == D.expected_params_bytes(30, 15, 200)
@@ -68,7 +66,7 @@ def test_db_roundtrip_against_python_decoder(tmp_path):
         assert (s["marker_c"], s["c"], s["k"]) == (30, 30, 15)           # marker_c field = c (src/types.rs:347)
         assert s["repetitive_kmers"] == 0 and s["individual_contig"] == 0 and s["amino_acid"] == 0
     # the C++ reader returns what was written
-    dump = subprocess.run([TOOL, "dump", d], check=True, capture_output=True).stdout.decode().splitlines()
+    dump = subprocess.run([db_tool(), "dump", d], check=True, capture_output=True).stdout.decode().splitlines()
     assert dump[0] == "PARAMS 30 15 200 0 0 30" and dump[1] == "N 3 3"
     want = [l for l in text.splitlines()]
     got_full = [l for l in dump[2:] if not l.startswith("P ")]
@@ -86,15 +84,15 @@ def test_db_of_real_genome_roundtrips(tmp_path):
     text, e = text_of("refs/e.coli-EC590.fasta.gz", 0, osk, [n for n, s in recs if len(s) >= 500])
     d = str(tmp_path / "db")
     os.makedirs(d)
-    subprocess.run([TOOL, "write", d, "125", "15", "1000"], input=text.encode(), check=True)
+    subprocess.run([db_tool(), "write", d, "125", "15", "1000"], input=text.encode(), check=True)
     par, sk, mk, index = D.read_db(d)
     assert sk[0]["records"] == list(zip(e["kmer"].tolist(), e["pos"].tolist(), e["cc"].tolist()))
     assert sk[0]["markers"] == e["markers"].tolist() and sk[0]["n_keys"] == osk.n_kmers
-    dump = subprocess.run([TOOL, "dump", d], check=True, capture_output=True).stdout.decode().splitlines()
+    dump = subprocess.run([db_tool(), "dump", d], check=True, capture_output=True).stdout.decode().splitlines()
     assert [l.rstrip() for l in dump[2:] if not l.startswith("P ")][:len(text.splitlines())] == [l.rstrip() for l in text.splitlines()]
     # a corrupted length prefix is reported, not followed
     raw = bytearray(open(os.path.join(d, "sketches.db"), "rb").read())
     raw[626:634] = (2 ** 60).to_bytes(8, "little")
     open(os.path.join(d, "sketches.db"), "wb").write(bytes(raw))
-    r = subprocess.run([TOOL, "dump", d], capture_output=True)
+    r = subprocess.run([db_tool(), "dump", d], capture_output=True)
     assert r.returncode == 1 and b"ERROR" in r.stderr

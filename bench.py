@@ -302,6 +302,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_val, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic",
                 "config": {"workload": workload_name(N, L, G), "genomes": N, "genome_len": L, "pairs": total_pairs, "kept_pairs_rank0": kept,
+                           "kept_pairs_expected_all_ranks": N // G * (G * (G - 1) // 2),
                            "host_gen_s": round(t_gen, 2)},
                 "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(N * L), "d2h_bytes_per_step": int(result_bytes[0])},

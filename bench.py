@@ -1,14 +1,21 @@
 #!/usr/bin/env python3
 """bench.py -- genome-pairs/sec of the `skani triangle` hot path on synthetic 5 Mbp bacterial genomes.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--genomes G] ...
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config north|c2|dense|c5] [--shuffle-order] ...
   (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
 
 A "step" is one full pass of the hot path (FracMinHash seeding -> marker screen -> chaining/ANI) over the whole
 synthetic genome set.  `value` = genome pairs / second with the ASCII genomes already resident in HBM; `e2e` is the same
-metric through the C ABI with HOST (pinned) buffers: H2D of every base and D2H of every result inside the timed region.
+metric through the C ABI with HOST (pinned) buffers: H2D of every base and D2H of every result inside the timed region
+(the call converts a share of every sub-batch to 2-bit on the host cores while the previous one is uploaded: that
+packing is inside the timed region too).
+After the timed legs the run VERIFIES itself (outside the timed regions): the kept-pair count and an order-independent
+checksum of (ref, query, ani, af_ref, af_query) are all-reduced over the ranks (identical for every N), and a random
+sample of kept pairs is re-chained by the CPU oracle (1e-4).  With N > 1 (or --shuffle-order) the whole measurement is
+repeated on a seeded random permutation of the genome order (input order unrelated to relatedness: the worst case of the
+multi-GPU exchange) and reported under "shuffled".
 `--impl reference` times the reference's CPU algorithm (the C++ restatement in oracle/: the Rust crate cannot be built
-in this image) on all host cores over a bounded sample of the same workload, scaled as stated in `cpu_baseline.sample`.
+in this image) on all host cores on the SAME configuration (full genome set).
 """
 import argparse
 import ctypes as C
@@ -25,8 +32,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "genome-pairs/sec, skani triangle 10k x 5 Mbp synthetic"
 UNIT = "genome-pairs/s"
+CONFIGS = {   # BASELINE.json configs that are a triangle on one box (c3 = search, see tools/bench_search.py)
+    "north": dict(genomes=10000, genome_len=5_000_000, cluster=20, c=125, marker_c=1000, rescue_small=True,
+                  metric="genome-pairs/sec, skani triangle 10k x 5 Mbp synthetic"),
+    "c2": dict(genomes=1000, genome_len=5_000_000, cluster=20, c=125, marker_c=1000, rescue_small=True,
+               metric="genome-pairs/sec, skani triangle 1k x 5 Mbp synthetic (BASELINE.json configs[1])"),
+    "dense": dict(genomes=2000, genome_len=5_000_000, cluster=2000, c=125, marker_c=1000, rescue_small=True,
+                  metric="genome-pairs/sec, skani triangle 2000 x 5 Mbp synthetic, ONE cluster (every pair is chained)"),
+    "c5": dict(genomes=200000, genome_len=30_000, cluster=10, c=30, marker_c=200, rescue_small=False,
+               metric="genome-pairs/sec, skani triangle --small-genomes on 200k x 30 kb synthetic contigs (BASELINE.json configs[4] shape)"),
+}
 
 
 def parse():
@@ -35,12 +51,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--genomes", type=int, default=10000)
-    ap.add_argument("--genome-len", type=int, default=5_000_000)
-    ap.add_argument("--cluster", type=int, default=20)
-    ap.add_argument("--cpu-sample", type=int, default=400, help="genomes in the CPU-baseline sample")
+    ap.add_argument("--config", default="north", choices=sorted(CONFIGS))
+    ap.add_argument("--genomes", type=int, default=None)
+    ap.add_argument("--genome-len", type=int, default=None)
+    ap.add_argument("--cluster", type=int, default=None)
+    ap.add_argument("--cpu-sample", type=int, default=400, help="genomes in the bounded CPU-baseline sample of the b200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--shuffle-order", action="store_true", help="also measure a seeded random permutation of the genome order (always on for N > 1)")
+    ap.add_argument("--perm-seed", type=int, default=12345)
+    ap.add_argument("--spot-check", type=int, default=200, help="kept pairs re-chained by the CPU oracle after the timed legs")
+    a = ap.parse_args()
+    cfg = dict(CONFIGS[a.config])
+    for k in ("genomes", "genome_len", "cluster"):
+        if getattr(a, k) is not None:
+            cfg[k] = getattr(a, k)
+    a.cfg = cfg
+    a.genomes, a.genome_len, a.cluster = cfg["genomes"], cfg["genome_len"], cfg["cluster"]
+    if a.genomes != CONFIGS[a.config]["genomes"]:
+        cfg["metric"] = cfg["metric"] + " [--genomes %d]" % a.genomes
+    return a
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -108,87 +137,187 @@ def host_threads():
     return n, quota
 
 
-
-def cpu_triangle_sample(n_sample, L, G, threads):
-    """Times seeding + screen + chain of the oracle on n_sample synthetic genomes. Returns seconds and details."""
+def oracle_setup(native):
+    """Bind the oracle for baseline timing: -march=native build (made on this box) when possible, 4-lane AVX2 seeder on."""
     import oracle_py as O
+    how = "-march=x86-64-v3 (portable build)"
+    if native:
+        path = O.build_native()
+        if path and os.path.exists(path):
+            O.use_library(path)
+            how = "-march=native (built on this box)"
+    simd = O.set_avx2_intrinsics(True)
+    return O, how + (", AVX2 4-lane seeder (src/avx2_seeding.rs instruction mix)" if simd else ", scalar lane-by-lane seeder (no AVX2)")
+
+
+def cpu_triangle(O, cfg, n_genomes, threads, ids=None):
+    """Times seeding + screen + chain of the oracle on the first n_genomes synthetic genomes. Returns seconds and details."""
     from bench_support import synth
-    bases, off, goc = synth.generate(0, n_sample, L, G=G)
+    L, G = cfg["genome_len"], cfg["cluster"]
+    if ids is None:
+        bases, off, goc = synth.generate(0, n_genomes, L, G=G)
+    else:
+        bases, off, goc = synth.generate_ids(ids, L, G=G)
     t0 = time.perf_counter()
     # seeding: OpenMP threads over genomes inside the oracle, the reference's own parallel structure (src/file_io.rs:149)
-    sk = O.sketch_many(bases, off, goc, n_sample, threads=threads)
+    sk = O.sketch_many(bases, off, goc, n_genomes, c=cfg["c"], marker_c=cfg["marker_c"], threads=threads)
     t1 = time.perf_counter()
-    res, info = O.triangle(sk, O.cmd(), threads=threads)
+    del bases
+    res, info = O.triangle(sk, O.cmd(rescue_small=cfg["rescue_small"]), threads=threads)
     t2 = time.perf_counter()
     return dict(t_seed=t1 - t0, t_pairs=t2 - t1, t_total=t2 - t0, n_kept=len(res), n_chained=info["n_chained"],
                 t_screen=info["t_screen"], t_chain=info["t_chain"])
 
 
-def cpu_single_thread(L, G):
+def cpu_single_thread(O, cfg):
     """Per-thread rates of the oracle (1 thread): ms per genome seeded, ms per chained pair."""
-    import oracle_py as O
     from bench_support import synth
+    L, G = cfg["genome_len"], cfg["cluster"]
     n = min(G, 8)
     bases, off, goc = synth.generate(0, n, L, G=G, threads=1)
     t0 = time.perf_counter()
-    sk = [O.sketch_from_contigs("g%06d" % g, [bases[int(off[i]):int(off[i + 1])] for i in np.nonzero(goc == g)[0]]) for g in range(n)]
+    sk = O.sketch_many(bases, off, goc, n, c=cfg["c"], marker_c=cfg["marker_c"], threads=1)
     t1 = time.perf_counter()
-    res, info = O.triangle(sk, O.cmd(), threads=1)
+    res, info = O.triangle(sk, O.cmd(rescue_small=cfg["rescue_small"]), threads=1)
     t2 = time.perf_counter()
     return {"seed_ms_per_genome": (t1 - t0) * 1e3 / n, "chain_ms_per_pair": (t2 - t1) * 1e3 / max(info["n_chained"], 1)}
 
 
-def cpu_baseline(args, threads):
+def expected_pairs(n, G):
+    """chained pairs of the clustered set: every pair inside a cluster"""
+    return (n // G) * (G * (G - 1) // 2) + ((n % G) * (n % G - 1) // 2)
+
+
+def scale_sample(d, S, N, G):
+    """sample -> full set: seeding and the marker index are linear in the genomes, chaining in the chained pairs"""
+    return (d["t_seed"] + d["t_screen"]) * (N / S) + (d["t_total"] - d["t_seed"] - d["t_screen"]) * (expected_pairs(N, G) / max(expected_pairs(S, G), 1))
+
+
+def cpu_sample_baseline(O, how, args, threads):
+    """Bounded sample (b200 arm, rank 0): the first S genomes, scaled linearly to the full set (extrapolation, labelled)."""
+    cfg = args.cfg
     S = min(args.cpu_sample, args.genomes)
-    S = max(args.cluster, (S // args.cluster) * args.cluster)
-    d = cpu_triangle_sample(S, args.genome_len, args.cluster, threads)
+    if args.cluster <= S:
+        S = max(args.cluster, (S // args.cluster) * args.cluster)
+    d = cpu_triangle(O, cfg, S, threads)
     N = args.genomes
-    t_full = d["t_total"] * (N / S)   # every stage is linear in N for the clustered set (fixed cluster size)
+    t_full = scale_sample(d, S, N, args.cluster)
     value = (N * (N - 1) / 2) / t_full
-    one = cpu_single_thread(args.genome_len, args.cluster)
-    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "single_thread": one,
-            "cgroup_cpu_quota": host_threads()[1],
+    one = cpu_single_thread(O, cfg)
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "single_thread": one, "extrapolated": S != N,
+            "cgroup_cpu_quota": host_threads()[1], "build": how,
             "sample": "oracle (C++ restatement of skani 0.3.0; Rust reference not buildable here) triangle on %d of the %d genomes "
                       "(%d clusters): %.2f s (seeding %.2f s; serial marker index + screen %.2f s; chain %.2f s for %d pairs) scaled "
-                      "x%.1f to the full set (all stages linear in N at fixed cluster size)" % (S, N, S // args.cluster, d["t_total"],
-                                                                                              d["t_seed"], d["t_screen"], d["t_chain"],
-                                                                                              d["n_chained"], N / S)}, d
+                      "to the full set (seeding + index x%.1f, chaining by the number of chained pairs); the full-size measurement is "
+                      "`bench.py --impl reference`" % (S, N, max(S // args.cluster, 1), d["t_total"], d["t_seed"], d["t_screen"],
+                                                      d["t_chain"], d["n_chained"], N / S)}, d
 
 
-def workload_name(N, L, G):
+def workload_name(cfg):
     """config.workload, identical for both arms (same synthetic set, same sketch parameters)"""
-    return ("triangle %d x %d bp synthetic clustered (G=%d, subst 0.1-5%%, inversions, 50-contig members), c=125 k=15 m=1000; "
-            "inputs %.1f GB >> L2 (no flush needed)" % (N, L, G, N * L / 1e9))
+    return ("triangle %d x %d bp synthetic clustered (G=%d, subst 0.1-5%%, inversions, 50-contig members), c=%d k=15 m=%d%s; "
+            "inputs %.1f GB >> L2 (no flush needed)" % (cfg["genomes"], cfg["genome_len"], cfg["cluster"], cfg["c"], cfg["marker_c"],
+                                                        "" if cfg["rescue_small"] else " --faster-small",
+                                                        cfg["genomes"] * cfg["genome_len"] / 1e9))
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference arm
+# reference arm: the CPU algorithm on the SAME configuration (all genomes), all host threads
 # ------------------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads, _quota = host_threads()
-    vals, last = [], None
-    for i in range(args.warmup + args.steps):
-        cb, d = cpu_baseline(args, threads)
-        if i >= args.warmup:
-            vals.append((cb["value"], d["t_total"]))
-        last = cb
-        if i == 0 and d["t_total"] > 30:   # keep the whole run within a few minutes
-            args.warmup, args.steps = 0, min(args.steps, 2)
-            vals.append((cb["value"], d["t_total"]))
-            break
-    v = float(np.mean([x[0] for x in vals]))
-    last["value"] = v
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-            "ms_per_step": float(np.mean([x[1] for x in vals])) * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(args.genomes, args.genome_len, args.cluster), "genomes": args.genomes,
-                       "genome_len": args.genome_len, "pairs": args.genomes * (args.genomes - 1) // 2},
-            "cpu_baseline": last, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cfg = args.cfg
+    threads, quota = host_threads()
+    O, how = oracle_setup(native=True)
+    N = args.genomes
+    total_pairs = N * (N - 1) // 2
+    runs = []
+    warm, steps = args.warmup, args.steps
+    i = 0
+    while i < warm + steps:
+        d = cpu_triangle(O, cfg, N, threads)
+        if i == 0 and d["t_total"] > 30:   # one step already takes longer than the 30 s budget: no warm-up, at most 2 steps
+            warm, steps = 0, min(steps, 2)
+        if i >= warm:
+            runs.append(d)
+        i += 1
+    t = float(np.mean([r["t_total"] for r in runs]))
+    v = total_pairs / t
+    last = runs[-1]
+    # the b200 arm's bounded sample, measured here as well, to say how good the linear extrapolation is
+    S = min(args.cpu_sample, N)
+    if args.cluster <= S:
+        S = max(args.cluster, (S // args.cluster) * args.cluster)
+    extrap = None
+    if S < N:
+        ds = cpu_triangle(O, cfg, S, threads)
+        ve = total_pairs / scale_sample(ds, S, N, args.cluster)
+        extrap = {"sample_genomes": S, "extrapolated_value": ve, "measured_over_extrapolated": v / ve}
+    cb = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "cgroup_cpu_quota": quota, "build": how, "extrapolated": False,
+          "sample_extrapolation_check": extrap,
+          "sample": "oracle (C++ restatement of skani 0.3.0; Rust reference not buildable here) triangle on ALL %d genomes: %.2f s "
+                    "(seeding %.2f s; serial marker index + screen %.2f s; chain %.2f s for %d pairs; %d kept), %d step(s), no scaling"
+                    % (N, last["t_total"], last["t_seed"], last["t_screen"], last["t_chain"], last["n_chained"], last["n_kept"], len(runs))}
+    line = {"impl": "reference", "metric": cfg["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(runs), "warmup": warm,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "genomes": N, "genome_len": args.genome_len, "pairs": total_pairs,
+                       "kept_pairs": last["n_kept"]},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# verification helpers (outside every timed region)
+# ------------------------------------------------------------------------------------------------------------
+def result_checksum(res):
+    """Order-independent 64-bit checksum of the kept results: sum over rows of a mix of (ref, query, ani, af_ref, af_query) bits."""
+    if len(res) == 0:
+        return 0
+    u64 = np.uint64
+    a = (res["ref_id"].astype(u64) << u64(32)) | res["query_id"].astype(u64)
+    b = (res["ani"].view(np.uint32).astype(u64) << u64(32)) | res["af_ref"].view(np.uint32).astype(u64)
+    c = res["af_query"].view(np.uint32).astype(u64)
+    with np.errstate(over="ignore"):
+        x = a * u64(0x9E3779B97F4A7C15) ^ b * u64(0xBF58476D1CE4E5B9) ^ c * u64(0x94D049BB133111EB)
+        x ^= x >> u64(31)
+        x = x * u64(0xD6E8FEB86659FD93)
+        x ^= x >> u64(29)
+        return int(np.sum(x, dtype=u64))
+
+
+def allreduce_count_checksum(count, cks, world):
+    if world == 1:
+        return count, cks
+    import torch
+    t = torch.tensor([count, cks & 0xFFFFFFFF, cks >> 32], dtype=torch.int64, device="cuda")
+    torch.distributed.all_reduce(t)
+    c, lo, hi = [int(x) for x in t.cpu().tolist()]
+    return c, (lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
+
+
+def oracle_spot_check(res, ids, cfg, n_sample, seed):
+    """Re-chain a random sample of the kept pairs with the CPU oracle: |d ani|, |d af| <= 1e-4 (north_star's tolerance)."""
+    import oracle_py as O
+    from bench_support import synth
+    if len(res) == 0 or n_sample <= 0:
+        return {"pairs": 0}
+    rng = np.random.default_rng(seed)
+    pick = res[np.sort(rng.choice(len(res), min(n_sample, len(res)), replace=False))]
+    slots = np.unique(np.concatenate([pick["ref_id"], pick["query_id"]]))
+    bases, off, goc = synth.generate_ids(ids[slots], cfg["genome_len"], G=cfg["cluster"])
+    threads = host_threads()[0]
+    osk = O.sketch_many(bases, off, goc, len(slots), c=cfg["c"], marker_c=cfg["marker_c"], threads=threads)   # named by rank = slot order
+    del bases
+    worst = 0.0
+    cp = O.cmd(rescue_small=cfg["rescue_small"])
+    for r in pick:
+        o = O.chain(osk[int(np.searchsorted(slots, r["ref_id"]))], osk[int(np.searchsorted(slots, r["query_id"]))], cp)
+        for f in ("ani", "af_ref", "af_query"):
+            worst = max(worst, abs(float(r[f]) - float(getattr(o, f))))
+    return {"pairs": int(len(pick)), "max_abs_diff": worst, "tolerance": 1e-4, "ok": bool(worst <= 1e-4)}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -203,6 +332,7 @@ def main():
     from skani_b200 import _lib
     from bench_support import synth
 
+    cfg = args.cfg
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,110 +345,167 @@ def main():
         print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
 
     N, L, G = args.genomes, args.genome_len, args.cluster
-    # genome shard of this rank (contiguous block; global genome order = rank-major)
+    # genome shard of this rank (contiguous block of slots; global genome order = rank-major)
     g0, g1 = (N * rank) // world, (N * (rank + 1)) // world
     nloc = g1 - g0
     pinned = torch.empty(nloc * L, dtype=torch.uint8, pin_memory=True)
     host = pinned.numpy()
-    t_gen0 = time.perf_counter()
-    synth.generate(g0, g1, L, G=G, out=host)
-    off, goc = synth.layout(g0, g1, L, G)
-    t_gen = time.perf_counter() - t_gen0
     ctx = sk.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    sp, mp = sk.sketch_params(), sk.map_params()
-    dev_bases = pinned.to("cuda", non_blocking=False)
+    sp = sk.sketch_params(cfg["c"], 15, cfg["marker_c"])
+    mp = sk.map_params(rescue_small=cfg["rescue_small"])
     total_pairs = N * (N - 1) // 2
-    result_bytes = [0]
     tri = None
     if world > 1:
         from skani_b200.multi_gpu import DistTriangle
         tri = DistTriangle(ctx, world, rank, sp, mp)
-
-    def step(e2e):
-        if world == 1:
-            if e2e:
-                res, st = sk.triangle(ctx, host, off, goc, nloc, sp, mp, as_array=True)
-                result_bytes[0] = len(res) * C.sizeof(_lib.AniResult)
-                return len(res), st
-            gs = sk.sketch_contigs(ctx, None, off, goc, nloc, sp, device_ptr=dev_bases.data_ptr())
-            pairs = sk.screen_triangle(ctx, gs, mp)
-            res = sk.chain_pairs(ctx, gs, gs, pairs, mp, as_array=True)
-            kept = int((res["ani"] > 0.1).sum())
-            gs.free()
-            return kept, None
-        kept = tri.step(host if e2e else None, dev_bases.data_ptr() if dev_bases is not None else 0, off, goc, nloc, g0, N)
-        if e2e:
-            result_bytes[0] = kept * C.sizeof(_lib.AniResult)
-        return kept, None
-
-    def timed(e2e, n_steps):
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ctx.launches
-        t0 = time.perf_counter()
-        ev0.record(stream)
-        kept = 0
-        for _ in range(n_steps):
-            kept, _st = step(e2e)
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-        wall = time.perf_counter() - t0
-        dev_ms = ev0.elapsed_time(ev1)
-        ms = max(dev_ms, wall * 1e3)  # the step blocks on its own D2H copies; wall >= device span. report the larger
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / n_steps, kept, ctx.launches - l0
-
-    # value leg first (needs the device-resident copy of the bases), then the roofline probe, then drop the 50 GB device
-    # copy before the end-to-end leg so that both legs run with comfortable HBM headroom
-    for _ in range(max(args.warmup, 0)):
-        step(False)
     clocks = ClockSampler(local_rank)
+
+    def measure(order):
+        """value leg + e2e leg + verification on one genome order; returns a dict (rank 0) / None."""
+        ids = np.arange(N, dtype=np.uint64) if order == "contiguous" else synth.shuffled_ids(N, args.perm_seed)
+        t_gen0 = time.perf_counter()
+        synth.generate_ids(ids[g0:g1], L, G=G, out=host)
+        off, goc = synth.layout_ids(ids[g0:g1], L, G)
+        t_gen = time.perf_counter() - t_gen0
+        dev_bases = pinned.to("cuda", non_blocking=False)
+        last = {}
+
+        def step(e2e):
+            if world == 1:
+                if e2e:
+                    res, st = sk.triangle(ctx, host, off, goc, nloc, sp, mp, as_array=True)
+                    last["res"] = res
+                    return len(res)
+                gs = sk.sketch_contigs(ctx, None, off, goc, nloc, sp, device_ptr=dev_bases.data_ptr())
+                pairs = sk.screen_triangle(ctx, gs, mp)
+                res = sk.chain_pairs(ctx, gs, gs, pairs, mp, as_array=True)
+                res = res[res["ani"] > 0.1]
+                gs.free()
+                last["res"] = res
+                return len(res)
+            kept = tri.step(host if e2e else None, dev_bases.data_ptr() if dev_bases is not None else 0, off, goc, nloc, g0, N)
+            last["res"] = tri.last_results
+            return kept
+
+        def timed(e2e, n_steps):
+            if world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ctx.launches
+            t0 = time.perf_counter()
+            ev0.record(stream)
+            kept = 0
+            for _ in range(n_steps):
+                kept = step(e2e)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            wall = time.perf_counter() - t0
+            dev_ms = ev0.elapsed_time(ev1)
+            ms = max(dev_ms, wall * 1e3)  # the step blocks on its own D2H copies; wall >= device span. report the larger
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms / n_steps, kept, ctx.launches - l0
+
+        # value leg first (needs the device-resident copy of the bases), then the roofline probes, then drop the device copy
+        # before the end-to-end leg so that both legs run with comfortable HBM headroom
+        for _ in range(max(args.warmup, 0)):
+            step(False)
+        ms_val, _, launches = timed(False, args.steps)
+        ck_val = allreduce_count_checksum(len(last["res"]), result_checksum(last["res"]), world)
+        roof = roof_chain = None
+        if rank == 0 and order == "contiguous":
+            roof = measure_hashpass(ctx, dev_bases, off, goc, nloc, sp, L)
+            roof_chain = measure_chain(ctx, dev_bases, off, goc, nloc, sp, mp, L, G)
+        dev_bases = None
+        torch.cuda.empty_cache()
+        for _ in range(max(args.warmup, 0)):
+            step(True)
+        ms_e2e, kept, _ = timed(True, args.steps)
+        res = last["res"]
+        pack_share = ctx.last_pack_share
+        d2h = len(res) * C.sizeof(_lib.AniResult)
+        ck_e2e = allreduce_count_checksum(len(res), result_checksum(res), world)
+        if world > 1:
+            t = torch.tensor([d2h], dtype=torch.int64, device="cuda")
+            torch.distributed.all_reduce(t)
+            d2h = int(t.item())
+        spot = None
+        if rank == 0:
+            spot = oracle_spot_check(res, ids, cfg, args.spot_check, 99)
+        if rank != 0:
+            return None
+        expected = expected_pairs(N, G)
+        return {"order": order, "value": total_pairs / (ms_val * 1e-3), "ms_per_step": ms_val, "launches": int(launches),
+                "e2e_value": total_pairs / (ms_e2e * 1e-3), "e2e_ms_per_step": ms_e2e, "d2h": int(d2h), "host_gen_s": round(t_gen, 2),
+                "host_pack_share": round(pack_share, 3),
+                "verify": {"kept_pairs_all_ranks": ck_e2e[0], "kept_pairs_expected": expected, "kept_ok": ck_e2e[0] == expected == ck_val[0],
+                           "checksum_e2e": "%016x" % ck_e2e[1], "checksum_value_leg": "%016x" % ck_val[1],
+                           "legs_agree": ck_e2e == ck_val, "oracle_spot_check": spot},
+                "roof": roof, "roof_chain": roof_chain}
+
     if rank == 0:
         clocks.start()
-    ms_val, _, launches = timed(False, args.steps)
-    roof = None
-    if rank == 0:
-        roof = measure_hashpass(ctx, stream, dev_bases, off, goc, nloc, sp, L)
-    dev_bases = None
-    torch.cuda.empty_cache()
-    for _ in range(max(args.warmup, 0)):
-        step(True)
-    ms_e2e, kept, _ = timed(True, args.steps)
+    m = measure("contiguous")
+    shuf = None
+    if world > 1 or args.shuffle_order:
+        shuf = measure("shuffled")
     clk = clocks.stop() if rank == 0 else None
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu, _d = cpu_baseline(args, host_threads()[0])
+        O, how = oracle_setup(native=True)
+        cpu, _d = cpu_sample_baseline(O, how, args, host_threads()[0])
     if rank == 0:
-        line = {"metric": METRIC, "value": total_pairs / (ms_val * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_val, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        line = {"metric": cfg["metric"], "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic",
-                "config": {"workload": workload_name(N, L, G), "genomes": N, "genome_len": L, "pairs": total_pairs, "kept_pairs_rank0": kept,
-                           "kept_pairs_expected_all_ranks": N // G * (G * (G - 1) // 2),
-                           "host_gen_s": round(t_gen, 2)},
-                "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": int(N * L), "d2h_bytes_per_step": int(result_bytes[0])},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+                "config": {"workload": workload_name(cfg), "genomes": N, "genome_len": L, "pairs": total_pairs, "order": "contiguous (clusters adjacent)",
+                           "host_gen_s": m["host_gen_s"], "verify": m["verify"]},
+                "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms_per_step"],
+                        "h2d_bytes_per_step": int(N * L * (1.0 - 0.75 * m["host_pack_share"])), "d2h_bytes_per_step": m["d2h"],
+                        "host_bytes_per_step": int(N * L), "host_pack_share": m["host_pack_share"],
+                        "note": "inputs = ASCII in pinned host memory; host_pack_share of the bases is converted to 2-bit on the host "
+                                "cores inside the timed call (0.25 B/base on the wire), the rest crosses PCIe as ASCII"},
+                "gpu_launches": m["launches"], "clocks": clk, "roofline": m["roof"], "roofline_chain": m["roof_chain"], "cpu_baseline": cpu}
+        if shuf:
+            line["shuffled"] = {"what": "same genomes, seeded random permutation of the genome order (perm seed %d): input order unrelated "
+                                        "to relatedness" % args.perm_seed,
+                                "value": shuf["value"], "ms_per_step": shuf["ms_per_step"], "e2e_value": shuf["e2e_value"],
+                                "e2e_ms_per_step": shuf["e2e_ms_per_step"], "host_pack_share": shuf["host_pack_share"], "verify": shuf["verify"]}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
 
 
-def measure_hashpass(ctx, stream, dev_bases, off, goc, nloc, sp, L):
-    """Roofline of the dominant kernel (hashpass_kernel), timed live with CUDA events on the launch stream
+def _peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def _ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per unit of work from THIS round's ncu --set full capture
+    (profiles/r02_traffic.json, written by tools/profile_step.py + tools/summarize_ncu.py); None if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel]
+    except Exception:
+        return None
+
+
+def measure_hashpass(ctx, dev_bases, off, goc, nloc, sp, L):
+    """Roofline of the dominant seeding kernel (hashpass_kernel), timed live with CUDA events on the launch stream
     (sk_ctx_set_timing brackets every launch).  Algorithmic bytes: SURVEY.md section 8(d) seeding figure
     L/4 + L/8 + 12 L/c + 8 L/m per genome (2.395 MB at L = 5 Mbp), times the genomes one launch processes."""
     import skani_b200 as sk
-    n = min(nloc, 200)
+    n = min(nloc, max(1, int(1.0e9 // L)))
     n_contigs = int(np.searchsorted(goc, n))
     o, g = off[:n_contigs + 1], goc[:n_contigs]
     sk.sketch_contigs(ctx, None, o, g, n, sp, device_ptr=dev_bases.data_ptr()).free()   # warm
@@ -333,25 +520,55 @@ def measure_hashpass(ctx, stream, dev_bases, off, goc, nloc, sp, L):
     bytes_per_genome = L / 4.0 + L / 8.0 + 12.0 * L / sp.c + 8.0 * L / sp.marker_c
     genomes_per_launch = n * reps / launches
     sec_per_launch = ms * 1e-3 / launches
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak, peak_src = _peak()
     ach = genomes_per_launch * bytes_per_genome / sec_per_launch / 1e9
     stage_ms = sum(v[0] for v in t.values())
-    # DRAM traffic per genome of this kernel from the committed ncu --set full capture (profiles/r01_ncu_full_top5.md:
-    # dram__bytes_read 250.05 MB + dram__bytes_write 98.18 MB for a 100-genome launch), scaled to this launch size
-    traffic = (250.05184e6 + 98.18496e6) / 100.0 * genomes_per_launch
+    tr = _ncu_traffic("hashpass_kernel")      # {"dram_bytes_per_base": ..., "issue_active_pct": ..., "inst_per_window": ..., "source": ...}
+    traffic = tr["dram_bytes_per_base"] * L * genomes_per_launch if tr else None
+    alu = None
+    if tr and tr.get("inst_per_window"):
+        # issue roofline: one warp instruction per cycle per SM sub-partition (4 per SM); windows/s at that rate
+        sm, mhz = 148, 1965.0
+        peak_windows = sm * 4 * 32 * mhz * 1e6 / tr["inst_per_window"]
+        alu = {"inst_per_window": tr["inst_per_window"], "issue_active_pct": tr.get("issue_active_pct"),
+               "windows_per_s": genomes_per_launch * L / sec_per_launch, "issue_peak_windows_per_s": peak_windows,
+               "frac_of_issue_peak": genomes_per_launch * L / sec_per_launch / peak_windows}
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_full_top5.md, per genome x genomes_per_launch",
+            "traffic_source": tr["source"] if tr else None, "alu": alu,
             "kernel": "hashpass_kernel", "launch_ms": sec_per_launch * 1e3, "genomes_per_launch": genomes_per_launch,
             "algorithmic_bytes_per_genome": bytes_per_genome,
             "gbases_per_s": genomes_per_launch * L / sec_per_launch / 1e9,
             "kernel_ms": {k: round(v[0] / reps, 3) for k, v in t.items()}, "timed_kernels_ms_per_rep": round(stage_ms / reps, 3),
-            "note": "hashpass is integer-ALU bound (64-bit hash per base at 0.375 B/base), not HBM bound: see DESIGN.md",
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+            "note": "nominal bound = HBM (north_star); the kernel is integer-issue bound (64-bit hash per base at 0.375 B/base), see `alu` and DESIGN.md",
+            "peak_source": peak_src}
+
+
+def measure_chain(ctx, dev_bases, off, goc, nloc, sp, mp, L, G):
+    """Roofline block of the chaining stage: 0.96 MB algorithmic bytes per chained pair (12 B x (S_q + S_r) + 64) over
+    the CUDA-event time of the chain kernels of one batch."""
+    import skani_b200 as sk
+    n = min(nloc, max(G, int(2.0e9 // L) // G * G))
+    n_contigs = int(np.searchsorted(goc, n))
+    gs = sk.sketch_contigs(ctx, None, off[:n_contigs + 1], goc[:n_contigs], n, sp, device_ptr=dev_bases.data_ptr())
+    pairs = sk.screen_triangle(ctx, gs, mp)
+    sk.chain_pairs(ctx, gs, gs, pairs, mp, as_array=True)    # warm
+    ctx.get_timing(reset=True)
+    ctx.set_timing(True)
+    sk.chain_pairs(ctx, gs, gs, pairs, mp, as_array=True)
+    t = ctx.get_timing(reset=True)
+    ctx.set_timing(False)
+    recs = sum(gs.info(g)["n_records"] for g in range(n)) / n
+    gs.free()
+    ms = sum(v[0] for v in t.values())
+    if len(pairs) == 0 or ms <= 0:
+        return None
+    bpp = 12.0 * 2 * recs + 64
+    peak, peak_src = _peak()
+    ach = bpp * len(pairs) / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "pairs": int(len(pairs)),
+            "us_per_pair": ms * 1e3 / len(pairs), "algorithmic_bytes_per_pair": bpp,
+            "kernel_ms": {k: round(v[0], 3) for k, v in t.items()}, "peak_source": peak_src,
+            "note": "chaining is latency / issue bound integer work (hash probes, banded DP, greedy selection), far from the HBM roofline"}
 
 
 if __name__ == "__main__":

@@ -91,6 +91,35 @@ uint64_t synth_layout(uint64_t seed, uint64_t g_begin, uint64_t g_end, uint64_t 
   return nc;
 }
 
+// member g of its cluster, derived from the cluster ancestor `anc`
+static void gen_member(uint64_t seed, uint64_t g, uint64_t L, uint32_t G, double dmin, double dmax, const uint8_t* anc, uint8_t* dst) {
+  const uint32_t m = (uint32_t)(g % G);
+  memcpy(dst, anc, L);
+  Rng r(seed ^ (0x3C3Cull << 32) ^ (g * 0x9E3779B97F4A7C15ull));
+  double d = dmin + (dmax - dmin) * r.uniform();
+  if (m == 0) d = 0.0 + dmin * 0.0;  // member 0 is the ancestor itself
+  if (d > 0) {
+    double lg = std::log1p(-d);
+    uint64_t i = 0;
+    while (true) {
+      double u = r.uniform();
+      if (u <= 0) u = 1e-300;
+      uint64_t skip = (uint64_t)(std::log(u) / lg);  // geometric gap
+      i += skip;
+      if (i >= L) break;
+      int b = code(dst[i]);
+      dst[i] = ACGT[(b + 1 + r.below(3)) & 3];
+      i++;
+    }
+  }
+  if (m % 4 == 1 && L >= 1000000) {  // one inversion of 100-500 kb
+    uint64_t len = 100000 + r.below(400001);
+    uint64_t a = r.below(L - len);
+    std::reverse(dst + a, dst + a + len);
+    for (uint64_t i = a; i < a + len; i++) dst[i] = ACGT[3 - code(dst[i])];
+  }
+}
+
 // ASCII bases of genomes [g_begin, g_end) into out (size (g_end - g_begin) * L)
 void synth_generate(uint64_t seed, uint64_t g_begin, uint64_t g_end, uint64_t L, uint32_t G, double dmin, double dmax,
                     uint8_t* out, int threads) {
@@ -106,32 +135,49 @@ void synth_generate(uint64_t seed, uint64_t g_begin, uint64_t g_end, uint64_t L,
       for (uint32_t m = 0; m < G; m++) {
         uint64_t g = (uint64_t)c * G + m;
         if (g < g_begin || g >= g_end) continue;
-        uint8_t* dst = out + (g - g_begin) * L;
-        memcpy(dst, anc.data(), L);
-        Rng r(seed ^ (0x3C3Cull << 32) ^ (g * 0x9E3779B97F4A7C15ull));
-        double d = dmin + (dmax - dmin) * r.uniform();
-        if (m == 0) d = 0.0 + dmin * 0.0;  // member 0 is the ancestor itself
-        if (d > 0) {
-          double lg = std::log1p(-d);
-          uint64_t i = 0;
-          while (true) {
-            double u = r.uniform();
-            if (u <= 0) u = 1e-300;
-            uint64_t skip = (uint64_t)(std::log(u) / lg);  // geometric gap
-            i += skip;
-            if (i >= L) break;
-            int b = code(dst[i]);
-            dst[i] = ACGT[(b + 1 + r.below(3)) & 3];
-            i++;
-          }
-        }
-        if (m % 4 == 1 && L >= 1000000) {  // one inversion of 100-500 kb
-          uint64_t len = 100000 + r.below(400001);
-          uint64_t a = r.below(L - len);
-          std::reverse(dst + a, dst + a + len);
-          for (uint64_t i = a; i < a + len; i++) dst[i] = ACGT[3 - code(dst[i])];
-        }
+        gen_member(seed, g, L, G, dmin, dmax, anc.data(), out + (g - g_begin) * L);
       }
+    }
+  }
+}
+
+// Arbitrary genome order (bench.py --shuffle-order: file order unrelated to relatedness): slot p of the output holds
+// synthetic genome ids[p].  Same bytes per genome as synth_generate; the ancestor of a cluster is generated once per call.
+uint64_t synth_layout_ids(uint64_t seed, const uint64_t* ids, uint64_t n, uint64_t L, uint32_t G, uint64_t* contig_off,
+                          uint32_t* genome_of_contig) {
+  uint64_t nc = 0;
+  std::vector<uint64_t> cuts;
+  for (uint64_t p = 0; p < n; p++) {
+    const uint64_t g = ids[p];
+    uint32_t k = synth_n_contigs(g, L, G);
+    uint64_t base = p * L;
+    if (k == 1) { if (contig_off) { contig_off[nc] = base; genome_of_contig[nc] = (uint32_t)p; } nc++; }
+    else {
+      cut_points(seed, g, L, (int)k, cuts);
+      for (uint32_t i = 0; i < k; i++) { if (contig_off) { contig_off[nc] = base + cuts[i]; genome_of_contig[nc] = (uint32_t)p; } nc++; }
+    }
+  }
+  if (contig_off) contig_off[nc] = n * L;
+  return nc;
+}
+
+void synth_generate_ids(uint64_t seed, const uint64_t* ids, uint64_t n, uint64_t L, uint32_t G, double dmin, double dmax,
+                        uint8_t* out, int threads) {
+  if (n == 0) return;
+  std::vector<std::pair<uint64_t, uint64_t>> byc(n);   // (genome id, slot), sorted => grouped by cluster
+  for (uint64_t p = 0; p < n; p++) byc[p] = {ids[p], p};
+  std::sort(byc.begin(), byc.end());
+  std::vector<uint64_t> starts;
+  for (uint64_t i = 0; i < n; i++) if (i == 0 || byc[i].first / G != byc[i - 1].first / G) starts.push_back(i);
+  starts.push_back(n);
+  if (threads < 1) threads = 1;
+#pragma omp parallel num_threads(threads)
+  {
+    std::vector<uint8_t> anc(L);
+#pragma omp for schedule(dynamic, 1)
+    for (long ci = 0; ci < (long)starts.size() - 1; ci++) {
+      gen_ancestor(seed, byc[starts[ci]].first / G, L, anc.data());
+      for (uint64_t i = starts[ci]; i < starts[ci + 1]; i++) gen_member(seed, byc[i].first, L, G, dmin, dmax, anc.data(), out + byc[i].second * L);
     }
   }
 }

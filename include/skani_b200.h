@@ -82,10 +82,25 @@ int sk_ctx_get_timing(sk_ctx* ctx, char* buf, uint64_t cap, int reset);
  *               share one genome; -i / --qi / --ri mode: one genome per contig).  Contig index inside a
  *               genome = rank among that genome's contigs, as src/file_io.rs:167,188,230.
  *               The >= 500 bp record filter (src/file_io.rs:176) is applied by the caller.
- * Input buffers are HOST memory; the call stages them to the device itself.                                  */
+ * Input buffers are HOST memory (pinned or not); the call stages them to the device itself in sub-batches, converting
+ * a share of every sub-batch to 2-bit on the host while the previous one is uploaded and seeded.                */
 int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases_ascii, const uint64_t* contig_off, uint32_t n_contigs,
                     const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* params,
                     sk_sketch_set** out);
+/* Packed input (SURVEY.md section 8b `bases_ascii_or_2bit`): the caller already holds the sequences as 2-bit codes, the
+ * reference's own in-register encoding (src/types.rs:40-49 BYTE_TO_SEQ; A 0, C 1, G 2, T/U 3, anything else 0).
+ * units : contig i owns the u64 words [U_i, U_i + ceil(len_i / 32)), U_i = sum_{j<i} ceil(len_j / 32); base b of a word sits in
+ *         bits 2b..2b+1 (bases past the contig end must be 0)
+ * nmask : same indexing with u32 words, bit b = base b is the byte 'N' (the only byte the AVX2 seeder treats as a
+ *         break, src/avx2_seeding.rs:115-126); NULL = no 'N' anywhere
+ * HOST memory (pinned or not); 0.25 B/base cross PCIe instead of 1 (+ the mask words of contigs that contain 'N').
+ * sk_pack_contig converts one contig's ASCII to this layout on the host (AVX-512 / AVX2 / scalar). */
+int sk_pack_contig(const uint8_t* ascii, uint64_t n_bases, uint64_t* units, uint32_t* nmask);
+int sk_sketch_batch_2bit(sk_ctx* ctx, const uint64_t* units, const uint32_t* nmask, const uint32_t* contig_len, uint32_t n_contigs,
+                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* params, sk_sketch_set** out);
+/* share of the bases that the last sk_sketch_batch / sk_triangle on this context converted to 2-bit on the host before the
+ * upload (the call adapts it to the measured packing and PCIe rates; the rest is converted by a kernel) */
+double sk_ctx_last_pack_share(const sk_ctx* ctx);
 /* Same, with bases_ascii already resident in DEVICE memory (bench "value" leg). contig_off / genome_of_contig stay host. */
 int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases_ascii, const uint64_t* contig_off, uint32_t n_contigs,
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* params,

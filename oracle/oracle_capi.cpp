@@ -58,6 +58,7 @@ static void to_res(const AniEstResult& a, uint32_t rid, uint32_t qid, orc_result
 }
 
 uint64_t orc_mm_hash64(uint64_t x) { return mm_hash64(x); }
+int orc_set_avx2_intrinsics(int on) { set_avx2_intrinsics(on != 0); return avx2_intrinsics() ? 1 : 0; }
 
 // ---- sketching ------------------------------------------------------------------------------------
 // Sketch every file; returns a malloc'd array of handles in (file_name, contig_order) order.

@@ -4,6 +4,9 @@
 // (bluenote-1577/skani @ c57dbe7, crate v0.3.0).
 // ============================================================================
 #include "skani_oracle.hpp"
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <zlib.h>
 
@@ -212,7 +215,84 @@ void fmh_seeds_scalar(const uint8_t* s, size_t n, const SketchParams& sp, uint32
 // ------------------------------------------------------------------------------------------------
 // avx2_seeding.rs:33-272  the 4-lane path, restated lane by lane (what x86-64+AVX2 hosts execute)
 // ------------------------------------------------------------------------------------------------
+// The same function with the reference's actual instruction mix: one __m256i holds the four lanes, mm_hash256 runs on
+// all four per step and the hits are taken out with per-lane extracts (avx2_seeding.rs:7-30, 108-272).  Selected with
+// set_avx2_intrinsics(true) for the CPU BASELINE (bench.py); parity tests keep the lane-by-lane form above as the
+// definition and check that both produce identical sketches (tests/test_oracle_goldens.py).
+static bool g_avx2_intrinsics = false;
+void set_avx2_intrinsics(bool on) { g_avx2_intrinsics = on && __builtin_cpu_supports("avx2"); }
+bool avx2_intrinsics() { return g_avx2_intrinsics; }
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static inline __m256i mm_hash256(__m256i key) {  // avx2_seeding.rs:7-30
+  key = _mm256_add_epi64(key, _mm256_slli_epi64(key, 21));
+  key = _mm256_xor_si256(key, _mm256_cmpeq_epi64(key, key));
+  key = _mm256_xor_si256(key, _mm256_srli_epi64(key, 24));
+  key = _mm256_add_epi64(_mm256_add_epi64(key, _mm256_slli_epi64(key, 3)), _mm256_slli_epi64(key, 8));
+  key = _mm256_xor_si256(key, _mm256_srli_epi64(key, 14));
+  key = _mm256_add_epi64(_mm256_add_epi64(key, _mm256_slli_epi64(key, 2)), _mm256_slli_epi64(key, 4));
+  key = _mm256_xor_si256(key, _mm256_srli_epi64(key, 28));
+  key = _mm256_add_epi64(key, _mm256_slli_epi64(key, 31));
+  return key;
+}
+
+__attribute__((target("avx2"))) static void fmh_seeds_avx2_intrin(const uint8_t* s, size_t n, const SketchParams& sp, uint32_t contig_index, Sketch& sk) {
+  sk.has_seeds = true;
+  const size_t marker_k = K_MARKER_DNA;
+  const size_t k = sp.k;
+  if (k > 16) return;
+  if (n < 2 * marker_k) return;
+  const size_t len = (n - marker_k + 1) / 4;
+  const uint8_t* str[4] = {s, s + len, s + 2 * len, s + 3 * len};
+  const int64_t seed_mask = (int64_t)(~0ull >> (64 - 2 * k));
+  const int64_t marker_mask = (int64_t)(~0ull >> (64 - 2 * marker_k));
+  const int64_t rev_marker_mask = (int64_t)~(3ull << (2 * marker_k - 2));
+  const uint64_t threshold = ~0ull / sp.c, threshold_marker = ~0ull / sp.marker_c;
+  const __m256i rev_sub = _mm256_set1_epi64x(3), m_seed = _mm256_set1_epi64x(seed_mask), m_marker = _mm256_set1_epi64x(marker_mask),
+                m_rev = _mm256_set1_epi64x(rev_marker_mask);
+  __m256i f = _mm256_setzero_si256(), r = _mm256_setzero_si256();
+  for (size_t i = 0; i < marker_k - 1; i++) {  // :63-81
+    const __m256i fn = _mm256_set_epi64x(BYTE_TO_SEQ[str[3][i]], BYTE_TO_SEQ[str[2][i]], BYTE_TO_SEQ[str[1][i]], BYTE_TO_SEQ[str[0][i]]);
+    const __m256i rn = _mm256_sub_epi64(rev_sub, fn);
+    f = _mm256_or_si256(_mm256_slli_epi64(f, 2), fn);
+    r = _mm256_or_si256(_mm256_srli_epi64(r, 2), _mm256_slli_epi64(rn, 40));
+  }
+  size_t resume[4] = {0, 0, 0, 0};
+  for (size_t i = marker_k - 1; i < len + marker_k - 1; i++) {  // :108
+    const uint8_t b0 = str[0][i], b1 = str[1][i], b2 = str[2][i], b3 = str[3][i];
+    if (b0 == 78) resume[0] = i + marker_k;
+    if (b1 == 78) resume[1] = i + marker_k;
+    if (b2 == 78) resume[2] = i + marker_k;
+    if (b3 == 78) resume[3] = i + marker_k;
+    const __m256i fn = _mm256_set_epi64x(BYTE_TO_SEQ[b3], BYTE_TO_SEQ[b2], BYTE_TO_SEQ[b1], BYTE_TO_SEQ[b0]);
+    const __m256i rn = _mm256_sub_epi64(rev_sub, fn);
+    f = _mm256_and_si256(_mm256_or_si256(_mm256_slli_epi64(f, 2), fn), m_marker);
+    r = _mm256_or_si256(_mm256_and_si256(_mm256_srli_epi64(r, 2), m_rev), _mm256_slli_epi64(rn, 40));
+    const __m256i fs = _mm256_and_si256(f, m_seed), rs = _mm256_and_si256(r, m_seed);
+    const __m256i cmp = _mm256_cmpgt_epi64(rs, fs), cmp_marker = _mm256_cmpgt_epi64(r, f);
+    const __m256i seeds = _mm256_blendv_epi8(rs, fs, cmp);
+    alignas(32) uint64_t hv[4], sv[4], cv[4];
+    _mm256_store_si256((__m256i*)hv, mm_hash256(seeds));
+    _mm256_store_si256((__m256i*)sv, seeds);
+    _mm256_store_si256((__m256i*)cv, cmp);
+    for (int lane = 0; lane < 4; lane++) {   // the four unrolled blocks of :179-269
+      if (hv[lane] < threshold && resume[lane] <= i) {
+        sk.add_seed_position((uint32_t)sv[lane], SeedPosition{(uint32_t)(i + len * lane), (contig_index << 1) | (cv[lane] ? 1u : 0u)});
+        if (hv[lane] < threshold_marker) {
+          alignas(32) uint64_t fv[4], rv[4], mv[4];
+          _mm256_store_si256((__m256i*)fv, f); _mm256_store_si256((__m256i*)rv, r); _mm256_store_si256((__m256i*)mv, cmp_marker);
+          sk.marker_seeds.insert(mv[lane] ? fv[lane] : rv[lane]);
+        }
+      }
+    }
+  }
+}
+#endif
+
 void fmh_seeds_avx2sem(const uint8_t* s, size_t n, const SketchParams& sp, uint32_t contig_index, Sketch& sk) {
+#if defined(__x86_64__)
+  if (g_avx2_intrinsics) { fmh_seeds_avx2_intrin(s, n, sp, contig_index, sk); return; }
+#endif
   sk.has_seeds = true;  // avx2_seeding.rs:40-42
   const size_t marker_k = K_MARKER_DNA;
   const size_t k = sp.k;

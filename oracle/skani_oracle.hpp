@@ -111,6 +111,8 @@ struct Sketch {  // types.rs:253-277
 // seeding.rs:225-323 (scalar) and avx2_seeding.rs:33-272 (the path taken on x86-64 with AVX2; authoritative)
 void fmh_seeds_scalar(const uint8_t* s, size_t n, const SketchParams& sp, uint32_t contig_index, Sketch& sk);
 void fmh_seeds_avx2sem(const uint8_t* s, size_t n, const SketchParams& sp, uint32_t contig_index, Sketch& sk);
+void set_avx2_intrinsics(bool on);   // baseline only: run the 4-lane AVX2 instruction mix of avx2_seeding.rs instead of the lane-by-lane form
+bool avx2_intrinsics();
 
 // file_io.rs:141-252 / 253-362.  Returns sketches sorted by (file_name, contig_order).
 // warnings (one per skipped file) are appended to *warn if non-null.

@@ -544,6 +544,7 @@ int run_search(Opts& op) {
     for (auto& h : qs) {
       f.add(h, true);
       Genome g; g.file_name = h.file_name; g.contigs = h.contigs; g.contig_order = h.contig_order; g.total_len = h.total_len;
+      if (g.contigs.empty()) g.contigs.push_back("");   // a .sketch without contig names still prints (as load_sketch_files does)
       qmeta.push_back(std::move(g));
     }
     qset = f.import(ctx, sp);
@@ -560,7 +561,9 @@ int run_search(Opts& op) {
   mp.both_min_aligned_frac = -0.01;
   mp.robust = op.robust; mp.median = op.median;
   mp.rescue_small = 0;
-  mp.learned_ani = !op.no_learned && dp.c >= 70 && !op.qi && !op.median;   // use_learned_ani(c, individual_contig_q, false, median)
+  // use_learned_ani(c, individual_contig_q, false, median) alone picks the model in search (src/search.rs:52-53);
+  // --no-learned-ani never reaches map_params_from_sketch there, so the reference ignores the flag: so do we
+  mp.learned_ani = dp.c >= 70 && !op.qi && !op.median;
   if (mp.learned_ani) fprintf(stderr, "INFO Learned ANI mode detected. ANI may be adjusted according to a regression model trained on MAGs.\n");
   const bool use_index = (op.queries.size() > 50 || op.qi) && !op.no_marker_index;   // src/parse.rs:436-442
   // ---- marker sketches of every reference -> device, one screen of all queries against all references

@@ -1,10 +1,16 @@
 // api.cu -- C ABI glue of libskani_b200.so: context, sketch-set lifecycle, host->device staging.
+#include <sched.h>
+
 #include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <thread>
 
+#include "host_pack.hpp"
 #include "sk_core.cuh"
 #include "sk_internal.h"
 
@@ -66,7 +72,63 @@ void SkArena::destroy() {
   slabs.clear(); live.clear(); total = 0;
 }
 
+// ---- SkPool ---------------------------------------------------------------------------------------------------
+SkPool::SkPool(int n_threads) {
+  for (int t = 1; t < n_threads; t++)
+    th.emplace_back([this] {
+      uint64_t seen = 0;
+      for (;;) {
+        const std::function<void(size_t)>* f;
+        size_t n;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return stop || gen != seen; });
+          if (stop) return;
+          seen = gen; f = fn; n = n_tasks;
+        }
+        for (size_t i; (i = next.fetch_add(1)) < n;) (*f)(i);
+        { std::lock_guard<std::mutex> lk(mu); if (--working == 0) cv_done.notify_all(); }
+      }
+    });
+}
+SkPool::~SkPool() {
+  { std::lock_guard<std::mutex> lk(mu); stop = true; }
+  cv.notify_all();
+  for (auto& t : th) t.join();
+}
+void SkPool::run(size_t n, const std::function<void(size_t)>& f) {
+  if (n == 0) return;
+  if (th.empty() || n == 1) { for (size_t i = 0; i < n; i++) f(i); return; }
+  { std::lock_guard<std::mutex> lk(mu); fn = &f; n_tasks = n; next.store(0); working = th.size(); gen++; }
+  cv.notify_all();
+  for (size_t i; (i = next.fetch_add(1)) < n;) f(i);
+  std::unique_lock<std::mutex> lk(mu);
+  cv_done.wait(lk, [&] { return working == 0; });
+}
+
 namespace sk {
+// host threads this context may use for packing: the CPUs the process can run on, capped by the container's CPU quota,
+// divided among the ranks of one box (torchrun's LOCAL_WORLD_SIZE) / the contexts of one process; SK_PACK_THREADS overrides
+static int host_pack_threads(const sk_ctx* ctx) {
+  if (const char* e = getenv("SK_PACK_THREADS")) return std::max(1, atoi(e));
+  int n = (int)std::thread::hardware_concurrency();
+  cpu_set_t cs;
+  if (sched_getaffinity(0, sizeof(cs), &cs) == 0) n = CPU_COUNT(&cs);
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char q[64] = {0};
+    long per = 0;
+    if (fscanf(f, "%63s %ld", q, &per) == 2 && strcmp(q, "max") != 0 && per > 0) n = std::min(n, (int)std::ceil(atof(q) / (double)per));
+    fclose(f);
+  }
+  int share = std::max(1, ctx->cpu_share);
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) share *= std::max(1, atoi(e));
+  return std::max(1, std::min(64, n / share - 1));
+}
+SkPool* ctx_pool(sk_ctx* ctx) {
+  if (!ctx->pool) ctx->pool = new SkPool(host_pack_threads(ctx));
+  return ctx->pool;
+}
+
 __global__ void stage_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n_words) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_words) dst[i] = src[i];
@@ -107,16 +169,10 @@ int check_sketch_params(sk_ctx* ctx, const sk_sketch_params* sp) {
   return SK_OK;
 }
 
-void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t n) {
-  const size_t T = 8, chunk = (n + T - 1) / T;
+void parallel_memcpy(sk_ctx* ctx, void* dst, const void* src, size_t n) {
   if (n < (8u << 20)) { memcpy(dst, src, n); return; }
-  std::vector<std::thread> th;
-  for (size_t t = 0; t < T; t++) {
-    size_t b = t * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back([=] { memcpy(dst + b, src + b, e - b); });
-  }
-  for (auto& t : th) t.join();
+  const size_t chunk = 4u << 20, nt = (n + chunk - 1) / chunk;
+  ctx_pool(ctx)->run(nt, [&](size_t t) { const size_t b = t * chunk; memcpy((uint8_t*)dst + b, (const uint8_t*)src + b, std::min(chunk, n - b)); });
 }
 
 template <typename T>
@@ -210,7 +266,16 @@ int sk_ctx_destroy(sk_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->child) { sk_ctx_destroy(ctx->child); ctx->child = nullptr; }
   if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
-  for (int i = 0; i < 2; i++) if (ctx->dbuf[i]) cudaFree(ctx->dbuf[i]);
+  if (ctx->pool) { delete ctx->pool; ctx->pool = nullptr; }
+  for (int i = 0; i < 2; i++) {
+    if (ctx->dbuf[i]) cudaFree(ctx->dbuf[i]);
+    if (ctx->dP[i]) cudaFree(ctx->dP[i]);
+    if (ctx->dNM[i]) cudaFree(ctx->dNM[i]);
+    if (ctx->hP[i]) cudaFreeHost(ctx->hP[i]);
+    if (ctx->hNM[i]) cudaFreeHost(ctx->hNM[i]);
+    if (ctx->x0[i]) cudaEventDestroy(ctx->x0[i]);
+    if (ctx->x1[i]) cudaEventDestroy(ctx->x1[i]);
+  }
   ctx->arena.destroy();
   if (ctx->stage) cudaFreeHost(ctx->stage);
   for (int i = 0; i < 2; i++) {
@@ -316,7 +381,10 @@ int sk_sketch_set_append(sk_sketch_set* dst, const sk_sketch_set* src) {
   SK_CUDA(cudaSetDevice(ctx->device));
   sk_sketch_set* merged = nullptr;
   SK_TRY(concat_sets(ctx, {dst, src}, &merged));
+  struct MG { sk_sketch_set* s; ~MG() { if (s) { free_set_device(s); delete s; } } } mg{merged};
   SK_TRY(build_hash(ctx, merged));
+  mg.s = nullptr;
+  const bool user_ranks = dst->ranks_user_set || src->ranks_user_set;
   free_set_device(dst);
   std::vector<uint64_t> ranks = dst->name_rank;
   uint64_t mx = 0;
@@ -324,6 +392,7 @@ int sk_sketch_set_append(sk_sketch_set* dst, const sk_sketch_set* src) {
   for (uint64_t r : src->name_rank) ranks.push_back(mx + r);
   *dst = *merged;  // takes over device pointers + metadata
   dst->name_rank = ranks;
+  dst->ranks_user_set = user_ranks;
   merged->pv_kmer = nullptr;  // ownership moved
   delete merged;
   return SK_OK;
@@ -532,14 +601,16 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
     gl.resize(c1 - c0);
     for (uint32_t i = c0; i < c1; i++) gl[i - c0] = genome_of_contig[i] - g_begin;
     sk_sketch_set* part = nullptr;
-    SK_TRY(sketch_batch_device(ctx, d_bases, 0, contig_off + c0, c1 - c0, gl.data(), g_next - g_begin, sp, &part));
+    SeedSrc src; src.d_ascii = d_bases;
+    SK_TRY(sketch_batch_device(ctx, src, contig_off + c0, c1 - c0, gl.data(), g_next - g_begin, sp, &part));
     parts.push_back(part);
     c0 = c1;
   }
   if (parts.empty()) {  // no contigs at all: n_genomes empty sketches
     sk_sketch_set* part = nullptr;
     uint64_t z = 0;
-    SK_TRY(sketch_batch_device(ctx, d_bases, 0, contig_off ? contig_off : &z, 0, nullptr, n_genomes, sp, &part));
+    SeedSrc src; src.d_ascii = d_bases;
+    SK_TRY(sketch_batch_device(ctx, src, contig_off ? contig_off : &z, 0, nullptr, n_genomes, sp, &part));
     SK_TRY(build_hash(ctx, part));
     *out = part;
     return SK_OK;
@@ -559,28 +630,47 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
 }  // extern "C"
 
 namespace sk {
-// sk_sketch_batch with an optional per-part hand-off: when on_part is set, every finished sub-batch (a sketch set of the
-// genomes [g_begin, g_end), without hash tables) is passed to it as soon as it is ready and nothing is concatenated;
-// *out stays null.  Used by the pipelined sk_triangle so that the H2D stream never drains between waves.
-int sketch_batch_host(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+static double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Host -> device seeding pipeline behind sk_sketch_batch / sk_sketch_batch_2bit / sk_triangle.
+//
+// The input is cut into sub-batches of whole genomes.  Three stages run concurrently on double-buffered slots:
+//   pack    (stager thread + the context's worker pool) a leading share of the sub-batch's contigs is converted to 2-bit
+//           units + N mask on the HOST (host_pack.hpp) into pinned staging: 0.25 B/base on the wire instead of 1
+//   upload  (copy stream) packed units -> dP/dNM, the remaining contigs as ASCII -> dbuf; N-mask words travel only for
+//           contigs that contain 'N', the others get a device memset
+//   seed    (caller thread, context stream) pack_kernel for the ASCII share + the seeding kernels (seeding.cu)
+// The packed share adapts to the measured packing and PCIe rates so that packing and upload take equally long:
+//   t_pack = f B / Rp  ==  t_up = B (1 - 0.75 f) / Rx   =>   f = Rp / (Rx + 0.75 Rp)        (clamped to [0, 1])
+// SK_HOST_PACK=<fraction> pins the share (0 = everything as ASCII, 1 = everything packed on the host); tests use it.
+// When on_part is set every finished sub-batch (a sketch set of the genomes [g_begin, g_end), without hash tables) is
+// handed over as soon as it is ready and nothing is concatenated (*out stays null): the pipelined sk_triangle.
+int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_off, uint32_t n_contigs,
                       const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out,
                       const std::function<int(sk_sketch_set*, uint32_t, uint32_t)>* on_part, size_t subbatch_override) {
   if (!ctx || (!out && !on_part) || !contig_off || (!genome_of_contig && n_contigs)) return SK_ERR_PARAM;
   SK_CUDA(cudaSetDevice(ctx->device));
   SK_TRY(check_sketch_params(ctx, sp));
-  // is the caller's buffer page-locked? then DMA straight from it; otherwise stage through our pinned buffers
-  bool pinned_src = false;
-  if (bases) {
+  const bool prepacked = seq.units != nullptr;
+  if (!prepacked && !seq.ascii && n_contigs && contig_off[n_contigs] > contig_off[0]) { ctx->err = "null sequence buffer"; return SK_ERR_PARAM; }
+  auto is_pinned = [](const void* p) {
+    if (!p) return false;
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, bases) == cudaSuccess) pinned_src = (attr.type == cudaMemoryTypeHost);
+    const bool pin = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-  }
-  // sub-batch plan (whole genomes)
-  struct Part { uint32_t c0, c1, g_begin, g_end; uint64_t b0, b1; };
+    return pin;
+  };
+  // is the caller's buffer page-locked? then DMA straight from it; otherwise stage through our pinned buffers
+  const bool pinned_src = prepacked ? (is_pinned(seq.units) && (!seq.nmask || is_pinned(seq.nmask))) : is_pinned(seq.ascii);
+  // sub-batch plan (whole genomes) + unit offset of every contig in the caller's packed layout
+  struct Part { uint32_t c0, c1, g_begin, g_end; uint64_t b0, b1, units; };
   std::vector<Part> plan;
+  std::vector<uint64_t> gunit(prepacked ? (size_t)n_contigs + 1 : 0, 0);
+  if (prepacked) for (uint32_t i = 0; i < n_contigs; i++) gunit[i + 1] = gunit[i] + (contig_off[i + 1] - contig_off[i] + 31) / 32;
   uint32_t c0 = 0;
-  uint64_t max_bytes = 0;
-  const size_t SUBBATCH = subbatch_override ? subbatch_override : subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
+  uint64_t max_bytes = 0, max_units = 0;
+  size_t SUBBATCH = subbatch_override ? subbatch_override : subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
+  if (const char* e = getenv("SK_SUBBATCH_BYTES")) SUBBATCH = std::max<size_t>(1, (size_t)atoll(e));   // test hook: many small sub-batches
   while (c0 < n_contigs) {
     uint32_t c1 = c0;
     uint64_t bytes = 0;
@@ -597,13 +687,26 @@ int sketch_batch_host(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_
     p.g_begin = plan.empty() ? 0 : genome_of_contig[c0];
     p.g_end = (c1 < n_contigs) ? genome_of_contig[c1] : n_genomes;
     p.b0 = contig_off[c0]; p.b1 = contig_off[c1];
+    p.units = 0;
+    for (uint32_t i = c0; i < c1; i++) {
+      if (contig_off[i + 1] < contig_off[i]) { ctx->err = "contig offsets must be non-decreasing"; return SK_ERR_PARAM; }
+      p.units += (contig_off[i + 1] - contig_off[i] + 31) / 32;
+    }
     max_bytes = std::max(max_bytes, p.b1 - p.b0);
+    max_units = std::max(max_units, p.units);
     plan.push_back(p);
     c0 = c1;
   }
   if (plan.empty()) return sk_sketch_batch_dev(ctx, nullptr, contig_off, 0, genome_of_contig, n_genomes, sp, out);
-  // device double buffer (grow-only, kept in the context)
-  if (ctx->dbuf_bytes < max_bytes + 64) {
+  if (max_units >= (1ull << 31)) { ctx->err = "sub-batch too large (>= 2^31 units)"; return SK_ERR_PARAM; }
+  // ---- pinned share: fixed by SK_HOST_PACK, else adaptive
+  double fixed_share = -1.0;
+  if (const char* e = getenv("SK_HOST_PACK")) fixed_share = std::min(1.0, std::max(0.0, atof(e)));
+  if (prepacked) fixed_share = 1.0;
+  SkPool* pool = ctx_pool(ctx);
+  // ---- buffers (grow-only, kept in the context)
+  const bool want_ascii = !prepacked && fixed_share < 1.0;
+  if (want_ascii && ctx->dbuf_bytes < max_bytes + 64) {
     for (int i = 0; i < 2; i++) {
       if (ctx->dbuf[i]) SK_CUDA(cudaFree(ctx->dbuf[i]));
       ctx->dbuf[i] = nullptr;
@@ -611,8 +714,28 @@ int sketch_batch_host(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_
     }
     ctx->dbuf_bytes = max_bytes + 64;
   }
-  uint8_t** dbuf = ctx->dbuf;
-  if (!pinned_src && ctx->pinned_bytes < max_bytes) {
+  if (ctx->dunits < max_units) {
+    for (int i = 0; i < 2; i++) {
+      if (ctx->dP[i]) SK_CUDA(cudaFree(ctx->dP[i]));
+      if (ctx->dNM[i]) SK_CUDA(cudaFree(ctx->dNM[i]));
+      ctx->dP[i] = nullptr; ctx->dNM[i] = nullptr;
+      SK_CUDA(cudaMalloc((void**)&ctx->dP[i], (max_units + 8) * 8));
+      SK_CUDA(cudaMalloc((void**)&ctx->dNM[i], (max_units + 8) * 4));
+    }
+    ctx->dunits = max_units;
+  }
+  const bool need_hstage = !(prepacked && pinned_src) && fixed_share != 0.0;
+  if (need_hstage && ctx->hunits < max_units) {
+    for (int i = 0; i < 2; i++) {
+      if (ctx->hP[i]) cudaFreeHost(ctx->hP[i]);
+      if (ctx->hNM[i]) cudaFreeHost(ctx->hNM[i]);
+      ctx->hP[i] = nullptr; ctx->hNM[i] = nullptr;
+      SK_CUDA(cudaHostAlloc((void**)&ctx->hP[i], (max_units + 8) * 8, cudaHostAllocDefault));
+      SK_CUDA(cudaHostAlloc((void**)&ctx->hNM[i], (max_units + 8) * 4, cudaHostAllocDefault));
+    }
+    ctx->hunits = max_units;
+  }
+  if (want_ascii && !pinned_src && ctx->pinned_bytes < max_bytes) {
     for (int i = 0; i < 2; i++) {
       if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
       ctx->pinned[i] = nullptr;
@@ -620,43 +743,190 @@ int sketch_batch_host(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_
     }
     ctx->pinned_bytes = max_bytes;
   }
-  cudaEvent_t compute_done[2];
-  for (int i = 0; i < 2; i++) SK_CUDA(cudaEventCreateWithFlags(&compute_done[i], cudaEventDisableTiming));
-  struct EGuard { cudaEvent_t* e; ~EGuard() { for (int i = 0; i < 2; i++) cudaEventDestroy(e[i]); } } eguard{compute_done};
-  auto enqueue_copy = [&](size_t pi) -> int {
-    const Part& p = plan[pi];
-    int b = (int)(pi & 1);
-    size_t nbytes = p.b1 - p.b0;
-    if (pi >= 2) SK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, compute_done[b], 0));  // device buffer free again
-    if (pinned_src) {
-      SK_CUDA(cudaMemcpyAsync(dbuf[b], bases + p.b0, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-    } else {
-      if (pi >= 2) SK_CUDA(cudaEventSynchronize(ctx->pinned_free[b]));  // staging buffer drained
-      parallel_memcpy(ctx->pinned[b], bases + p.b0, nbytes);
-      SK_CUDA(cudaMemcpyAsync(dbuf[b], ctx->pinned[b], nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-      SK_CUDA(cudaEventRecord(ctx->pinned_free[b], ctx->copy_stream));
+  for (int i = 0; i < 2; i++) {
+    if (!ctx->x0[i]) { SK_CUDA(cudaEventCreate(&ctx->x0[i])); SK_CUDA(cudaEventCreate(&ctx->x1[i])); }
+  }
+  if (ctx->pack_rate <= 0) ctx->pack_rate = 3.0e9 * pool->size();
+  if (ctx->h2d_rate <= 0) ctx->h2d_rate = 50.0e9;
+
+  // ---- stager thread: pack + enqueue the copies of part k; the caller seeds part k as soon as its copies are queued
+  const size_t NP = plan.size();
+  std::vector<uint32_t> n_packed(NP, 0);
+  std::mutex mu;
+  std::condition_variable cv;
+  long enqueued = -1, computed = -1;
+  int stager_rc = SK_OK;
+  std::string stager_err;
+  bool abort_all = false;
+  uint64_t bases_packed = 0, bases_total = 0;
+  const bool trace = getenv("SK_TRACE") != nullptr;
+  std::thread stager([&] {
+    cudaSetDevice(ctx->device);
+    std::vector<uint64_t> cu;           // unit offset of every contig of the part (+ total)
+    std::vector<uint8_t> has_n;
+    std::vector<uint64_t> xbytes(2, 0);
+    auto fail = [&](const char* what, cudaError_t e) {
+      std::lock_guard<std::mutex> lk(mu);
+      stager_rc = SK_ERR_CUDA; stager_err = std::string(what) + ": " + cudaGetErrorString(e); abort_all = true;
+      cv.notify_all();
+    };
+    for (size_t k = 0; k < NP; k++) {
+      const Part& p = plan[k];
+      const int b = (int)(k & 1);
+      const uint32_t nc = p.c1 - p.c0;
+      cudaError_t e;
+      // (1) staging slot free again: the copies of part k-2 have completed; their duration gives the PCIe rate
+      if (k >= 2) {
+        if ((e = cudaEventSynchronize(ctx->x1[b])) != cudaSuccess) return fail("cudaEventSynchronize", e);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->x0[b], ctx->x1[b]) == cudaSuccess && ms > 0.05f && xbytes[b] > (8u << 20))
+          ctx->h2d_rate = 0.5 * ctx->h2d_rate + 0.5 * ((double)xbytes[b] / (ms * 1e-3));
+      }
+      // (2) how many leading contigs are packed on the host
+      cu.assign(nc + 1, 0);
+      for (uint32_t i = 0; i < nc; i++) cu[i + 1] = cu[i] + (contig_off[p.c0 + i + 1] - contig_off[p.c0 + i] + 31) / 32;
+      const uint64_t B = p.b1 - p.b0;
+      double share = fixed_share >= 0 ? fixed_share : ctx->pack_rate / (ctx->h2d_rate + 0.75 * ctx->pack_rate);
+      share = std::min(1.0, std::max(0.0, share));
+      uint32_t np = 0;
+      if (share >= 1.0) np = nc;
+      else if (share > 0.0) {
+        const uint64_t target = p.b0 + (uint64_t)((double)B * share);
+        while (np < nc && contig_off[p.c0 + np + 1] <= target) np++;      // whole contigs
+      }
+      n_packed[k] = np;
+      const uint64_t pk_bases = contig_off[p.c0 + np] - p.b0, pk_units = cu[np];
+      // (3) pack (or stage the caller's packed units) into the pinned slot
+      has_n.assign(nc, 0);
+      const uint64_t* src_units = nullptr; const uint32_t* src_nm = nullptr;
+      const double tp0 = wall_s();
+      if (prepacked) {
+        const uint64_t u0 = gunit[p.c0];
+        if (pinned_src) { src_units = seq.units + u0; src_nm = seq.nmask ? seq.nmask + u0 : nullptr; }
+        else {
+          parallel_memcpy(ctx, ctx->hP[b], seq.units + u0, pk_units * 8);
+          if (seq.nmask) parallel_memcpy(ctx, ctx->hNM[b], seq.nmask + u0, pk_units * 4);
+          src_units = ctx->hP[b]; src_nm = seq.nmask ? ctx->hNM[b] : nullptr;
+        }
+        if (seq.nmask) {   // which contigs carry an N at all (the others get a memset instead of a copy)
+          pool->run(np, [&](size_t i) {
+            const uint32_t* m = seq.nmask + u0 + cu[i];
+            uint32_t any = 0;
+            for (uint64_t j = 0, n = cu[i + 1] - cu[i]; j < n; j++) any |= m[j];
+            has_n[i] = any != 0;
+          });
+        }
+      } else if (np) {
+        struct Task { uint32_t ci; uint64_t ub, ue; };
+        std::vector<Task> tasks;
+        const uint64_t TU = 32768;   // 1 Mbase per task
+        for (uint32_t i = 0; i < np; i++)
+          for (uint64_t ub = 0, n = cu[i + 1] - cu[i]; ub < n; ub += TU) tasks.push_back(Task{i, ub, std::min(n, ub + TU)});
+        std::vector<std::atomic<uint8_t>> flag(np);
+        for (auto& f : flag) f.store(0, std::memory_order_relaxed);
+        uint64_t* hP = ctx->hP[b]; uint32_t* hNM = ctx->hNM[b];
+        pool->run(tasks.size(), [&](size_t t) {
+          const Task& tk = tasks[t];
+          const uint64_t len = contig_off[p.c0 + tk.ci + 1] - contig_off[p.c0 + tk.ci];
+          const uint8_t* s0 = seq.ascii + contig_off[p.c0 + tk.ci] + 32 * tk.ub;
+          const uint64_t nb = std::min<uint64_t>(len - 32 * tk.ub, 32 * (tk.ue - tk.ub));
+          uint64_t* P = hP + cu[tk.ci] + tk.ub;
+          uint32_t* M = hNM + cu[tk.ci] + tk.ub;
+          sk_host::pack_contig(s0, nb, P, M);
+          uint32_t any = 0;
+          for (uint64_t j = 0, n = tk.ue - tk.ub; j < n; j++) any |= M[j];
+          if (any) flag[tk.ci].store(1, std::memory_order_relaxed);
+        });
+        for (uint32_t i = 0; i < np; i++) has_n[i] = flag[i].load(std::memory_order_relaxed);
+        src_units = hP; src_nm = hNM;
+        const double tp = wall_s() - tp0;
+        if (tp > 1e-4 && pk_bases > (8u << 20)) ctx->pack_rate = 0.5 * ctx->pack_rate + 0.5 * ((double)pk_bases / tp);
+      }
+      // staging of an unpinned ASCII tail
+      const uint8_t* ascii_src = nullptr;
+      const uint64_t ascii_bytes = prepacked ? 0 : (p.b1 - contig_off[p.c0 + np]);
+      if (ascii_bytes) {
+        if (pinned_src) ascii_src = seq.ascii + contig_off[p.c0 + np];
+        else {
+          if (k >= 2 && (e = cudaEventSynchronize(ctx->pinned_free[b])) != cudaSuccess) return fail("cudaEventSynchronize", e);
+          parallel_memcpy(ctx, ctx->pinned[b], seq.ascii + contig_off[p.c0 + np], ascii_bytes);
+          ascii_src = ctx->pinned[b];
+        }
+      }
+      // (4) device slot free again: part k-2 has been seeded (its kernels read dP/dNM/dbuf of this slot)
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return abort_all || computed >= (long)k - 2; });
+        if (abort_all) return;
+      }
+      // (5) copies
+      cudaStream_t cs = ctx->copy_stream;
+      uint64_t wire = 0;
+      if ((e = cudaEventRecord(ctx->x0[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
+      if (pk_units) {
+        if ((e = cudaMemcpyAsync(ctx->dP[b], src_units, pk_units * 8, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return fail("H2D units", e);
+        wire += pk_units * 8;
+        for (uint32_t i = 0; i < np;) {      // runs of contigs with / without 'N'
+          uint32_t j = i + 1;
+          while (j < np && (has_n[j] != 0) == (has_n[i] != 0)) j++;
+          const uint64_t u0 = cu[i], nu = cu[j] - cu[i];
+          if (nu) {
+            if (has_n[i] && src_nm) { e = cudaMemcpyAsync(ctx->dNM[b] + u0, src_nm + u0, nu * 4, cudaMemcpyHostToDevice, cs); wire += nu * 4; }
+            else e = cudaMemsetAsync(ctx->dNM[b] + u0, 0, nu * 4, cs);
+            if (e != cudaSuccess) return fail("H2D N mask", e);
+          }
+          i = j;
+        }
+      }
+      if (ascii_bytes) {
+        if ((e = cudaMemcpyAsync(ctx->dbuf[b] + (contig_off[p.c0 + np] - p.b0), ascii_src, ascii_bytes, cudaMemcpyHostToDevice, cs)) != cudaSuccess)
+          return fail("H2D ASCII", e);
+        wire += ascii_bytes;
+        if (!pinned_src && (e = cudaEventRecord(ctx->pinned_free[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
+      }
+      xbytes[b] = wire;
+      if ((e = cudaEventRecord(ctx->x1[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
+      if ((e = cudaEventRecord(ctx->h2d_done[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
+      if (trace) fprintf(stderr, "[sk_sketch_batch] part %zu: %.0f%% of %.1f MB packed on the host (%d threads, %.1f GB/s; PCIe %.1f GB/s), %.1f MB on the wire\n",
+                         k, B ? 100.0 * pk_bases / B : 0.0, B / 1e6, pool->size(), ctx->pack_rate / 1e9, ctx->h2d_rate / 1e9, wire / 1e6);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        enqueued = (long)k; bases_packed += pk_bases; bases_total += B;
+      }
+      cv.notify_all();
     }
-    SK_CUDA(cudaEventRecord(ctx->h2d_done[b], ctx->copy_stream));
-    return SK_OK;
-  };
+  });
+  struct StagerJoin {
+    std::thread& t; std::mutex& mu; std::condition_variable& cv; bool& abort_all;
+    ~StagerJoin() { { std::lock_guard<std::mutex> lk(mu); abort_all = true; } cv.notify_all(); if (t.joinable()) t.join(); }
+  } sj{stager, mu, cv, abort_all};
+
   std::vector<sk_sketch_set*> parts;
   struct Guard { std::vector<sk_sketch_set*>& v; ~Guard() { for (auto* s : v) sk_sketch_set_free(s); } } guard{parts};
   std::vector<uint32_t> gl;
-  SK_TRY(enqueue_copy(0));
-  for (size_t pi = 0; pi < plan.size(); pi++) {
+  for (size_t pi = 0; pi < NP; pi++) {
     const Part& p = plan[pi];
-    int b = (int)(pi & 1);
-    if (pi + 1 < plan.size()) SK_TRY(enqueue_copy(pi + 1));  // overlaps with this part's kernels
+    const int b = (int)(pi & 1);
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return abort_all || enqueued >= (long)pi; });
+      if (abort_all) { ctx->err = "staging thread: " + stager_err; return stager_rc != SK_OK ? stager_rc : SK_ERR_STATE; }
+    }
     SK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->h2d_done[b], 0));
     gl.resize(p.c1 - p.c0);
     for (uint32_t i = p.c0; i < p.c1; i++) gl[i - p.c0] = genome_of_contig[i] - p.g_begin;
+    SeedSrc src;
+    src.d_ascii = ctx->dbuf[b]; src.ascii_base = p.b0; src.d_P = ctx->dP[b]; src.d_NM = ctx->dNM[b]; src.n_packed = n_packed[pi];
     sk_sketch_set* part = nullptr;
-    SK_TRY(sketch_batch_device(ctx, dbuf[b], p.b0, contig_off + p.c0, p.c1 - p.c0, gl.data(), p.g_end - p.g_begin, sp, &part));
-    SK_CUDA(cudaEventRecord(compute_done[b], ctx->stream));
+    SK_TRY(sketch_batch_device(ctx, src, contig_off + p.c0, p.c1 - p.c0, gl.data(), p.g_end - p.g_begin, sp, &part));   // ends synchronised
+    { std::lock_guard<std::mutex> lk(mu); computed = (long)pi; }
+    cv.notify_all();
     if (on_part) SK_TRY((*on_part)(part, p.g_begin, p.g_end));   // ownership moves to the callee
     else parts.push_back(part);
   }
+  stager.join();
   SK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  ctx->last_pack_share = bases_total ? (double)bases_packed / (double)bases_total : 0.0;
   if (on_part) return SK_OK;
   if (parts.size() == 1) {
     SK_TRY(build_hash(ctx, parts[0]));
@@ -685,8 +955,28 @@ extern "C" {
 int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
                     const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out) {
   if (!out) return SK_ERR_PARAM;
-  return sk::sketch_batch_host(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, out, nullptr, 0);
+  sk::HostSeq seq; seq.ascii = bases;
+  return sk::sketch_batch_host(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, out, nullptr, 0);
 }
+
+int sk_pack_contig(const uint8_t* ascii, uint64_t n_bases, uint64_t* units, uint32_t* nmask) {
+  if ((!ascii && n_bases) || !units || !nmask) return SK_ERR_PARAM;
+  sk_host::pack_contig(ascii, n_bases, units, nmask);
+  return SK_OK;
+}
+
+int sk_sketch_batch_2bit(sk_ctx* ctx, const uint64_t* units, const uint32_t* nmask, const uint32_t* contig_len, uint32_t n_contigs,
+                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out) {
+  if (!ctx || !out || (n_contigs && (!units || !contig_len || !genome_of_contig))) return SK_ERR_PARAM;
+  std::vector<uint64_t> off((size_t)n_contigs + 1, 0);
+  for (uint32_t i = 0; i < n_contigs; i++) off[i + 1] = off[i] + contig_len[i];
+  sk::HostSeq seq; seq.units = units; seq.nmask = nmask;
+  if (n_contigs == 0 || off[n_contigs] == 0) { seq.units = nullptr; }   // nothing to stage: falls through to the empty-set path
+  if (!seq.units) return sk_sketch_batch(ctx, (const uint8_t*)"", off.data(), n_contigs, genome_of_contig, n_genomes, sp, out);
+  return sk::sketch_batch_host(ctx, seq, off.data(), n_contigs, genome_of_contig, n_genomes, sp, out, nullptr, 0);
+}
+
+double sk_ctx_last_pack_share(const sk_ctx* ctx) { return ctx ? ctx->last_pack_share : 0.0; }
 
 int sk_sketch_set_import_batch(sk_ctx* ctx, const sk_sketch_params* sp, uint32_t n_genomes, const uint64_t* rec_off,
                                const uint32_t* kmer, const uint32_t* pos, const uint32_t* cc, const uint64_t* mk_off,

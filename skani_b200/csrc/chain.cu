@@ -1194,8 +1194,13 @@ __global__ void init_chunk_acc_kernel(uint64_t n, Workspace ws) {
 // host
 // ------------------------------------------------------------------------------------------------------------
 static bool g_tables_uploaded[64] = {false};
+static std::mutex g_tables_mu;
 
+// constant-memory GBDT tables, once per device.  Several contexts (the pipelined worker, sk_triangle_multi's per-device
+// threads) may get here concurrently: serialised, and the device is synchronised before the flag is published so that
+// no kernel on a non-blocking stream can run ahead of the upload.
 static int upload_tables(sk_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_tables_mu);
   if (ctx->device < 64 && g_tables_uploaded[ctx->device]) return SK_OK;
   static float thr[2][1365], leaf[2][1560], shrink[2], bias[2];
   static unsigned char feat[2][1365];
@@ -1212,6 +1217,7 @@ static int upload_tables(sk_ctx* ctx) {
   SK_CUDA(cudaMemcpyToSymbol(c_gbdt_leaf, leaf, sizeof(leaf)));
   SK_CUDA(cudaMemcpyToSymbol(c_gbdt_shrink, shrink, sizeof(shrink)));
   SK_CUDA(cudaMemcpyToSymbol(c_gbdt_bias, bias, sizeof(bias)));
+  SK_CUDA(cudaDeviceSynchronize());
   if (ctx->device < 64) g_tables_uploaded[ctx->device] = true;
   return SK_OK;
 }

@@ -4,10 +4,10 @@
 // the 'N' test of src/avx2_seeding.rs:115-126).
 //
 // Why: the end-to-end triangle is PCIe-bound (50 GB of ASCII = 903 ms at the measured 55 GB/s); the
-// same genomes are 12.5 GB as 2-bit units + 6.25 GB of N-mask (or a sparse exception list).  Packing on the host while
-// the previous sub-batch is in flight cuts the bytes on the wire 2.7-4x.  NOT wired into sk_sketch_batch yet: the device
-// entry that consumes pre-packed units needs a GPU run to validate; this header is
-// exercised on the CPU by tests/emu/emu_pack.cpp against sk::ascii_code.
+// same genomes are 12.5 GB as 2-bit units (+ an N mask only for contigs that contain 'N').  sk_sketch_batch packs a share
+// of every sub-batch on the host while the previous one is in flight (api.cu, the share adapts to the measured packing and
+// PCIe rates) and sk_sketch_batch_2bit takes sequences that are already packed.  Checked on the CPU by tests/emu/emu_pack.cpp
+// against sk::ascii_code, on the GPU by tests/test_gpu_twobit.py (bit-exact sketches through both entries).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -69,12 +69,36 @@ __attribute__((target("avx2,bmi2"))) inline void pack_contig_avx2(const uint8_t*
   }
   if (n % 32) pack_unit_scalar(s + 32 * full, (uint32_t)(n % 32), P + full, NM + full);
 }
+// 64 bases per iteration with AVX-512BW: the byte compares produce the bit planes directly as 64-bit masks.
+__attribute__((target("avx512f,avx512bw,bmi2"))) inline void pack_contig_avx512(const uint8_t* s, size_t n, uint64_t* P, uint32_t* NM) {
+  const size_t full = n / 64;
+  const __m512i fold = _mm512_set1_epi8((char)0xDF), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'), cT = _mm512_set1_epi8('T'),
+                cU = _mm512_set1_epi8('U'), cN = _mm512_set1_epi8('N'), four = _mm512_set1_epi8(4);
+  for (size_t j = 0; j < full; j++) {
+    const __m512i x = _mm512_loadu_si512((const void*)(s + 64 * j));
+    if (__builtin_expect(_mm512_cmplt_epu8_mask(x, four) != 0, 0)) {            // table rows 0..3: scalar path
+      pack_unit_scalar(s + 64 * j, 32, P + 2 * j, NM + 2 * j);
+      pack_unit_scalar(s + 64 * j + 32, 32, P + 2 * j + 1, NM + 2 * j + 1);
+      continue;
+    }
+    const __m512i u = _mm512_and_si512(x, fold);
+    const uint64_t tu = _mm512_cmpeq_epi8_mask(u, cT) | _mm512_cmpeq_epi8_mask(u, cU);
+    const uint64_t b0 = _mm512_cmpeq_epi8_mask(u, cC) | tu, b1 = _mm512_cmpeq_epi8_mask(u, cG) | tu;
+    const uint64_t nn = _mm512_cmpeq_epi8_mask(x, cN);
+    P[2 * j] = _pdep_u64(b0 & 0xFFFFFFFFull, 0x5555555555555555ull) | _pdep_u64(b1 & 0xFFFFFFFFull, 0xAAAAAAAAAAAAAAAAull);
+    P[2 * j + 1] = _pdep_u64(b0 >> 32, 0x5555555555555555ull) | _pdep_u64(b1 >> 32, 0xAAAAAAAAAAAAAAAAull);
+    NM[2 * j] = (uint32_t)nn; NM[2 * j + 1] = (uint32_t)(nn >> 32);
+  }
+  if (n % 64) pack_contig_avx2(s + 64 * full, n % 64, P + 2 * full, NM + 2 * full);
+}
 #endif
 
 // P and NM must hold (n + 31) / 32 entries
 inline void pack_contig(const uint8_t* s, size_t n, uint64_t* P, uint32_t* NM) {
 #if defined(__x86_64__)
   static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+  static const bool fast512 = fast && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f");
+  if (fast512) { pack_contig_avx512(s, n, P, NM); return; }
   if (fast) { pack_contig_avx2(s, n, P, NM); return; }
 #endif
   pack_contig_scalar(s, n, P, NM);

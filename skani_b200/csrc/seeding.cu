@@ -11,6 +11,7 @@
 //   build_views     k-mer-ordered view (segmented radix sort per genome), distinct k-mer groups, multiplicities,
 //                   marker sort + dedup per genome  (the flat-array equivalent of the reference's HashMap/HashSet)
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -30,10 +31,10 @@ uint64_t count_launch(sk_ctx* ctx, uint64_t n) {
 // kernels
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PACK_THREADS = 256;
+constexpr uint32_t UCOARSE_SHIFT = 8;   // host-built index: contig of every 256th unit (4 B per 8 KB of sequence)
 
-// contig lookup for a unit: block-level narrowed binary search over the unit prefix offsets
-__device__ __forceinline__ uint32_t find_contig(const uint32_t* __restrict__ cuoff, uint32_t n_contigs, uint32_t u,
-                                                uint32_t lo_hint, uint32_t hi_hint) {
+// contig lookup for a unit: narrowed binary search over the unit prefix offsets
+__device__ __forceinline__ uint32_t find_contig(const uint32_t* __restrict__ cuoff, uint32_t u, uint32_t lo_hint, uint32_t hi_hint) {
   uint32_t lo = lo_hint, hi = hi_hint;  // invariant: cuoff[lo] <= u < cuoff[hi]
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
@@ -41,33 +42,31 @@ __device__ __forceinline__ uint32_t find_contig(const uint32_t* __restrict__ cuo
   }
   return lo;
 }
+// contig of unit u through the coarse index (ucoarse has (n_units >> 8) + 2 entries, the last = n_contigs - 1): at most a
+// handful of contig starts fall inside one 256-unit stretch, so the search is 0-3 steps on cached data
+__device__ __forceinline__ uint32_t contig_of_unit(const uint32_t* __restrict__ ucoarse, const uint32_t* __restrict__ cuoff, uint32_t u) {
+  const uint32_t lo = __ldg(ucoarse + (u >> UCOARSE_SHIFT)), hi = __ldg(ucoarse + (u >> UCOARSE_SHIFT) + 1) + 1;
+  return find_contig(cuoff, u, lo, hi);
+}
 
+// ASCII -> 2-bit units + N mask for the units [u_begin, n_units) of a sub-batch (the units before u_begin arrived packed
+// from the host).  Thread per unit, nine aligned 32-bit loads realigned with funnel shifts (contig starts are arbitrary
+// byte offsets), then SIMD-in-register conversion: no shared-memory table.
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ coff, const uint32_t* __restrict__ cuoff,
-            const uint32_t* __restrict__ clen, uint32_t n_contigs, uint32_t n_units, uint64_t* __restrict__ P,
-            uint32_t* __restrict__ NM, uint32_t* __restrict__ ucontig) {
-  __shared__ uint8_t lut[256];
-  __shared__ uint32_t s_c0, s_c1;
-  lut[threadIdx.x] = (uint8_t)ascii_code(threadIdx.x);
-  uint32_t u0 = blockIdx.x * PACK_THREADS;
-  if (threadIdx.x == 0) {
-    uint32_t ulast = min(u0 + PACK_THREADS - 1, n_units - 1);
-    s_c0 = find_contig(cuoff, n_contigs, u0, 0, n_contigs);
-    s_c1 = find_contig(cuoff, n_contigs, ulast, 0, n_contigs);
-  }
-  __syncthreads();
-  uint32_t u = u0 + threadIdx.x;
+            const uint32_t* __restrict__ clen, const uint32_t* __restrict__ ucoarse, uint32_t u_begin, uint32_t n_units,
+            uint64_t* __restrict__ P, uint32_t* __restrict__ NM) {
+  const uint32_t u = u_begin + blockIdx.x * PACK_THREADS + threadIdx.x;
   if (u >= n_units) return;
-  uint32_t ci = find_contig(cuoff, n_contigs, u, s_c0, s_c1 + 1);
-  uint32_t ul = u - cuoff[ci];
-  uint32_t len = clen[ci];
-  uint32_t nvalid = min(32u, len - 32u * ul);
+  const uint32_t ci = contig_of_unit(ucoarse, cuoff, u);
+  const uint32_t ul = u - cuoff[ci];
+  const uint32_t len = clen[ci];
+  const uint32_t nvalid = min(32u, len - 32u * ul);
   const uint8_t* src = ascii + coff[ci] + 32ull * ul;
-  // realign to 4-byte words: 9 aligned words cover any 32-byte span
-  uintptr_t addr = (uintptr_t)src;
+  const uintptr_t addr = (uintptr_t)src;
   const uint32_t* wp = (const uint32_t*)(addr & ~(uintptr_t)3);
-  uint32_t sh = (uint32_t)(addr & 3) * 8;
-  uint32_t nwords = (nvalid + (uint32_t)(addr & 3) + 3) >> 2;  // words overlapping the valid span
+  const uint32_t sh = (uint32_t)(addr & 3) * 8;
+  const uint32_t nwords = (nvalid + (uint32_t)(addr & 3) + 3) >> 2;  // words overlapping the valid span
   uint32_t w[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) w[i] = (i < (int)nwords) ? __ldg(wp + i) : 0u;
@@ -75,44 +74,38 @@ pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ coff
   uint32_t nm = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    uint32_t r = __funnelshift_r(w[i], w[i + 1], sh);
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      uint32_t j = i * 4 + b;
-      uint32_t v = lut[(r >> (8 * b)) & 0xFFu];
-      if (j >= nvalid) v = 0;
-      packed |= (uint64_t)(v & 3u) << (2 * j);
-      nm |= (v >> 2) << j;
-    }
+    const uint32_t r = __funnelshift_r(w[i], w[i + 1], sh);
+    uint32_t c8, n4;
+    pack_word(r, c8, n4);
+    packed |= (uint64_t)c8 << (8 * i);
+    nm |= n4 << (4 * i);
   }
+  if (nvalid < 32u) { packed &= (1ull << (2 * nvalid)) - 1ull; nm &= (1u << nvalid) - 1u; }   // bases past the contig end read as 0
   P[u] = packed;
   NM[u] = nm;
-  ucontig[u] = ci;
 }
 
 constexpr int HASH_THREADS = 128;
 
 __global__ void __launch_bounds__(HASH_THREADS)
-hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM, const uint32_t* __restrict__ ucontig,
+hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM, const uint32_t* __restrict__ ucoarse,
                 const uint32_t* __restrict__ cuoff, const uint32_t* __restrict__ clen, uint32_t n_units,
-                uint64_t seed_mask, uint64_t threshold, uint32_t* __restrict__ PM, uint32_t* __restrict__ cnt) {
+                uint64_t seed_mask, uint64_t threshold, uint32_t* __restrict__ PM) {
   uint32_t u = blockIdx.x * HASH_THREADS + threadIdx.x;
   if (u >= n_units) return;
-  uint32_t ci = ucontig[u];
+  uint32_t ci = contig_of_unit(ucoarse, cuoff, u);
   uint32_t ul = u - cuoff[ci];
   uint32_t n = clen[ci];
   uint64_t hi = P[u];
   uint64_t lo = ul ? P[u - 1] : 0ull;
   uint32_t nhi = NM[u];
   uint32_t nlo = ul ? NM[u - 1] : 0u;
-  uint32_t pass = unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold);
-  PM[u] = pass;
-  cnt[u] = __popc(pass);
+  PM[u] = unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold);
 }
 
 // one thread per unit with a non-empty pass mask: regenerate the few passing windows and emit their records
 __global__ void __launch_bounds__(256)
-expand_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ ucontig, const uint32_t* __restrict__ cuoff,
+expand_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ ucoarse, const uint32_t* __restrict__ cuoff,
               const uint32_t* __restrict__ clocal, uint32_t n_units, const uint32_t* __restrict__ PM,
               const uint32_t* __restrict__ uoff, uint64_t seed_mask, uint64_t threshold_marker,
               uint32_t* __restrict__ pv_kmer, uint32_t* __restrict__ pv_pos, uint32_t* __restrict__ pv_cc,
@@ -121,7 +114,7 @@ expand_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ ucont
   if (u >= n_units) return;
   uint32_t pass = PM[u];
   if (pass == 0) return;
-  uint32_t ci = ucontig[u];
+  uint32_t ci = contig_of_unit(ucoarse, cuoff, u);
   uint32_t ul = u - cuoff[ci];
   uint64_t hi = P[u];
   uint64_t lo = ul ? P[u - 1] : 0ull;
@@ -429,9 +422,13 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
   return SK_OK;
 }
 
-// Seeds all contigs of one sub-batch whose ASCII bases are resident on the device.
-//   d_ascii + (contig_off[i] - ascii_base) is the first byte of contig i.
-int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base, const uint64_t* contig_off, uint32_t n_contigs,
+struct PopcOp { using result_type = uint32_t; __device__ __forceinline__ uint32_t operator()(uint32_t m) const { return (uint32_t)__popc(m); } };
+
+// Seeds all contigs of one sub-batch.  The sequence arrives either as ASCII resident on the device (contig i at
+// src.d_ascii + contig_off[i] - src.ascii_base; converted by pack_kernel) or, for the first src.n_packed contigs, already
+// as 2-bit units + N mask inside src.d_P / src.d_NM (packed on the host, api.cu, or handed over by sk_sketch_batch_2bit).
+// Unit layout: contig i owns units [cuoff[i], cuoff[i+1]), cuoff = prefix sum of ceil(len / 32).
+int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_off, uint32_t n_contigs,
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out) {
   cudaStream_t st = ctx->stream;
   const uint32_t G = n_genomes;
@@ -455,7 +452,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     if (g != prev_g || i == 0) rank = 0;
     prev_g = g;
     if (rank >= (1u << 30)) { ctx->err = "contig index exceeds 30 bits (src/types.rs:136)"; return SK_ERR_PARAM; }
-    coff[i] = contig_off[i] - ascii_base;
+    coff[i] = contig_off[i] - src.ascii_base;
     cuoff[i] = (uint32_t)units;
     clen[i] = (uint32_t)len;
     clocal[i] = rank++;
@@ -465,48 +462,74 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     units += (len + 31) / 32;
     if (units >= (1ull << 31)) { ctx->err = "sub-batch too large (>= 2^31 units)"; return SK_ERR_PARAM; }
   }
-  coff[n_contigs] = contig_off[n_contigs] - ascii_base;
+  coff[n_contigs] = contig_off[n_contigs] - src.ascii_base;
   cuoff[n_contigs] = (uint32_t)units;
   for (uint32_t g = 0; g < G; g++) set->ctg_off[g + 1] += set->ctg_off[g];
   set->C = n_contigs;
   set->name_rank.resize(G);
   for (uint32_t g = 0; g < G; g++) set->name_rank[g] = g;
   const uint32_t NU = (uint32_t)units;
+  const uint32_t n_packed = std::min(src.n_packed, n_contigs);
+  if (n_packed && (!src.d_P || !src.d_NM)) { ctx->err = "packed contigs without unit arrays"; return SK_ERR_PARAM; }
+  // coarse unit -> contig index: contig of every 256th unit (= the last contig starting at or before it)
+  std::vector<uint32_t> ucoarse(((size_t)NU >> UCOARSE_SHIFT) + 2, n_contigs ? n_contigs - 1 : 0);
+  {
+    uint32_t ci = 0;
+    for (size_t j = 0; ((uint64_t)j << UCOARSE_SHIFT) < NU; j++) {
+      const uint32_t u = (uint32_t)(j << UCOARSE_SHIFT);
+      while (ci + 1 < n_contigs && cuoff[ci + 1] <= u) ci++;
+      ucoarse[j] = ci;
+    }
+  }
 
   SK_CUDA(ctx->arena.alloc((void**)&set->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
   SK_CUDA(ctx->arena.alloc((void**)&set->ctg_rec_off, (size_t)(n_contigs + G + 1) * 4));
   set->seed_off.assign(G + 1, 0);
 
-  DTmp<uint64_t> d_coff, P;
-  DTmp<uint32_t> d_cuoff, d_clen, d_clocal, NM, ucontig, PM, cnt, uoff;
+  DTmp<uint64_t> d_coff, Pown;
+  DTmp<uint32_t> d_cuoff, d_clen, d_clocal, d_ucoarse, NMown, PM, uoff;
   std::vector<uint64_t> raw_mk_off(G + 1, 0);
   DTmp<uint64_t> mkv, mraw;
   if (NU > 0) {
     SK_CUDA(d_coff.alloc(n_contigs + 1, ctx)); SK_CUDA(d_cuoff.alloc(n_contigs + 1, ctx));
-    SK_CUDA(d_clen.alloc(n_contigs, ctx)); SK_CUDA(d_clocal.alloc(n_contigs, ctx));
+    SK_CUDA(d_clen.alloc(n_contigs, ctx)); SK_CUDA(d_clocal.alloc(n_contigs, ctx)); SK_CUDA(d_ucoarse.alloc(ucoarse.size(), ctx));
     SK_CUDA(h2d_small(ctx, d_coff.p, coff.data(), (n_contigs + 1) * 8));
     SK_CUDA(h2d_small(ctx, d_cuoff.p, cuoff.data(), (n_contigs + 1) * 4));
     SK_CUDA(h2d_small(ctx, d_clen.p, clen.data(), n_contigs * 4));
     SK_CUDA(h2d_small(ctx, d_clocal.p, clocal.data(), n_contigs * 4));
+    SK_CUDA(h2d_small(ctx, d_ucoarse.p, ucoarse.data(), ucoarse.size() * 4));
     SK_CUDA(h2d_small(ctx, set->d_ctg_len, clen.data(), n_contigs * 4));
-    SK_CUDA(P.alloc(NU, ctx)); SK_CUDA(NM.alloc(NU, ctx)); SK_CUDA(ucontig.alloc(NU, ctx));
-    SK_CUDA(PM.alloc(NU, ctx)); SK_CUDA(cnt.alloc(NU, ctx)); SK_CUDA(uoff.alloc(NU, ctx));
+    uint64_t* P = src.d_P; uint32_t* NM = src.d_NM;
+    if (!P) { SK_CUDA(Pown.alloc(NU, ctx)); SK_CUDA(NMown.alloc(NU, ctx)); P = Pown.p; NM = NMown.p; }
+    SK_CUDA(PM.alloc(NU, ctx)); SK_CUDA(uoff.alloc(NU, ctx));
 
-    SK_LAUNCH(ctx, "pack_kernel", (pack_kernel<<<div_up(NU, PACK_THREADS), PACK_THREADS, 0, st>>>(
-        d_ascii, d_coff.p, d_cuoff.p, d_clen.p, n_contigs, NU, P.p, NM.p, ucontig.p)));
+    const uint32_t u_ascii = cuoff[n_packed];            // first unit that still has to be converted on the device
+    if (u_ascii < NU) {
+      if (!src.d_ascii) { ctx->err = "ASCII contigs without a device buffer"; return SK_ERR_PARAM; }
+      SK_LAUNCH(ctx, "pack_kernel", (pack_kernel<<<div_up(NU - u_ascii, PACK_THREADS), PACK_THREADS, 0, st>>>(
+          src.d_ascii, d_coff.p, d_cuoff.p, d_clen.p, d_ucoarse.p, u_ascii, NU, P, NM)));
+    }
     const uint64_t seed_mask = ~0ull >> (64 - 2 * sp->k);
     const uint64_t thr = ~0ull / sp->c, thr_m = ~0ull / sp->marker_c;  // src/avx2_seeding.rs:93-94
     SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<<<div_up(NU, HASH_THREADS), HASH_THREADS, 0, st>>>(
-        P.p, NM.p, ucontig.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, cnt.p)));
-    SK_TRY(scan_exclusive<uint32_t>(ctx, cnt.p, uoff.p, NU));
-    uint32_t last_cnt = 0, last_off = 0;
-    SK_CUDA(cudaMemcpyAsync(&last_cnt, cnt.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
+        P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p)));
+    {   // record offset of every unit = exclusive scan of the pass-mask popcounts (no separate count array)
+      auto cnt_it = thrust::make_transform_iterator((const uint32_t*)PM.p, PopcOp());
+      size_t tb = 0;
+      SK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt_it, uoff.p, (int)NU, st));
+      DTmp<uint8_t> tmp;
+      SK_CUDA(tmp.alloc(tb, ctx));
+      SK_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_it, uoff.p, (int)NU, st));
+      count_launch(ctx, 2);
+    }
+    uint32_t last_pm = 0, last_off = 0;
+    SK_CUDA(cudaMemcpyAsync(&last_pm, PM.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaMemcpyAsync(&last_off, uoff.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
     // record offset of every contig's first unit (-> per-genome offsets and per-contig record offsets)
     DTmp<uint32_t> d_crec;
     SK_CUDA(d_crec.alloc(n_contigs + 1, ctx));
     SK_CUDA(cudaStreamSynchronize(st));
-    const uint32_t S = last_cnt + last_off;
+    const uint32_t S = (uint32_t)__builtin_popcount(last_pm) + last_off;
     gather_u32_kernel<<<div_up(n_contigs + 1, 256), 256, 0, st>>>(uoff.p, d_cuoff.p, n_contigs + 1, NU, S, d_crec.p); count_launch(ctx);
     std::vector<uint32_t> crec(n_contigs + 1);
     SK_CUDA(cudaMemcpyAsync(crec.data(), d_crec.p, (n_contigs + 1) * 4, cudaMemcpyDeviceToHost, st));
@@ -516,7 +539,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     SK_CUDA(ctx->arena.alloc((void**)&set->pv_cc, std::max<size_t>(S, 1) * 4));
     SK_CUDA(mkv.alloc(S, ctx));
     SK_LAUNCH(ctx, "expand_kernel", (expand_kernel<<<div_up(NU, 256), 256, 0, st>>>(
-        P.p, ucontig.p, d_cuoff.p, d_clocal.p, NU, PM.p, uoff.p, seed_mask, thr_m, set->pv_kmer, set->pv_pos, set->pv_cc, mkv.p)));
+        P, d_ucoarse.p, d_cuoff.p, d_clocal.p, NU, PM.p, uoff.p, seed_mask, thr_m, set->pv_kmer, set->pv_pos, set->pv_cc, mkv.p)));
     SK_CUDA(cudaStreamSynchronize(st));
     // per-genome record offsets + per-contig local record offsets (with one sentinel per genome)
     std::vector<uint32_t> crl(n_contigs + G + 1, 0);
@@ -556,7 +579,7 @@ int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base
     SK_CUDA(cudaMemsetAsync(set->ctg_rec_off, 0, (size_t)(n_contigs + G + 1) * 4, st));
   }
   // free the big per-base temporaries before the sort temporaries are allocated
-  P.release(); NM.release(); ucontig.release(); PM.release(); cnt.release(); uoff.release(); mkv.release();
+  Pown.release(); NMown.release(); PM.release(); uoff.release(); mkv.release();
   SK_TRY(build_views(ctx, set, mraw.p, raw_mk_off));
   SK_CUDA(cudaStreamSynchronize(st));
   guard.s = nullptr;

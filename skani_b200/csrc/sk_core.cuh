@@ -42,6 +42,30 @@ SK_HD uint32_t ascii_code(uint32_t b) {
   return v;
 }
 
+// Four ASCII bytes -> four 2-bit codes (bits 2i..2i+1 = byte i) + four 'N' flags, SIMD-in-register.
+// Letters ACGTU in either case: code = ((b >> 1) ^ (b >> 2)) & 3 (A 0, C 1, G 2, T/U 3 = BYTE_TO_SEQ, src/types.rs:40-49).
+// The word takes the arithmetic path only if all four bytes are such letters (checked by rebuilding the expected
+// upper-case byte from the code); anything else (N, IUPAC, table rows 0..3, padding) goes through ascii_code per byte.
+SK_HD void pack_word(uint32_t x, uint32_t& code8, uint32_t& n4) {
+  const uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+  const uint32_t lo = t & 0x01010101u, hi = (t >> 1) & 0x01010101u, lh = lo & hi;
+  const uint32_t expect = 0x41414141u + 2u * lo + 6u * hi + 11u * lh;     // 'A' 'C' 'G' 'T' per byte (no carries: max 0x54)
+  const uint32_t u = x & 0xDFDFDFDFu;                                     // fold case
+  if ((((u ^ expect) & ~lh)) == 0u) {                                     // T/U differ in bit 0 only
+    code8 = (t * 0x00041041u) >> 18 & 0xFFu;                              // gather the four 2-bit fields (disjoint partial products)
+    n4 = 0;
+    return;
+  }
+  uint32_t c = 0, n = 0;
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    const uint32_t v = ascii_code((x >> (8 * b)) & 0xFFu);
+    c |= (v & 3u) << (2 * b);
+    n |= (v >> 2) << b;
+  }
+  code8 = c; n4 = n;
+}
+
 // reverse the order of the 32 2-bit fields of a u64 (base j <-> base 31-j)
 SK_HD uint64_t pair_reverse64(uint64_t x) {
   x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);

@@ -3,10 +3,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <functional>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/skani_b200.h"
@@ -27,6 +30,23 @@ struct SkArena {
   void destroy();
 };
 
+// Host worker pool of a context (ASCII -> 2-bit packing and staging copies of sk_sketch_batch).  run() is blocking and
+// the caller works too; one run() at a time.
+struct SkPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv, cv_done;
+  const std::function<void(size_t)>* fn = nullptr;
+  size_t n_tasks = 0, working = 0;
+  std::atomic<size_t> next{0};
+  uint64_t gen = 0;
+  bool stop = false;
+  explicit SkPool(int n_threads);
+  ~SkPool();
+  void run(size_t n, const std::function<void(size_t)>& f);
+  int size() const { return (int)th.size() + 1; }
+};
+
 struct sk_ctx {
   SkArena arena;
   int device = 0;
@@ -40,8 +60,19 @@ struct sk_ctx {
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_free[2] = {nullptr, nullptr};
   cudaEvent_t h2d_done[2] = {nullptr, nullptr};
-  uint8_t* dbuf[2] = {nullptr, nullptr};  // device staging double buffer (sk_sketch_batch)
+  uint8_t* dbuf[2] = {nullptr, nullptr};  // device staging double buffer (sk_sketch_batch): ASCII ...
   size_t dbuf_bytes = 0;
+  uint64_t* dP[2] = {nullptr, nullptr};   // ... and 2-bit units + N mask of a sub-batch (host-packed contigs land here directly)
+  uint32_t* dNM[2] = {nullptr, nullptr};
+  size_t dunits = 0;
+  uint64_t* hP[2] = {nullptr, nullptr};   // pinned staging of the host-packed share
+  uint32_t* hNM[2] = {nullptr, nullptr};
+  size_t hunits = 0;
+  cudaEvent_t x0[2] = {nullptr, nullptr}, x1[2] = {nullptr, nullptr};   // timing events around a sub-batch's H2D copies
+  SkPool* pool = nullptr;
+  int cpu_share = 1;                      // contexts of one process sharing the host cores (sk_triangle_multi)
+  double pack_rate = 0, h2d_rate = 0;     // measured: bases/s packed by the pool, bytes/s over PCIe (adapt the host-packed share)
+  double last_pack_share = 0;             // share of the bases packed on the host in the last sk_sketch_batch (stats)
   // small host->device parameter uploads go through a pinned, device-mapped ring + a copy kernel on the context's
   // stream instead of the H2D copy engine, which may be busy for tens of ms with bulk sequence uploads
   uint8_t* stage = nullptr;
@@ -142,15 +173,28 @@ namespace sk {
 constexpr uint32_t UBUCKET_BITS = 12;
 constexpr uint32_t UBUCKETS = 1u << UBUCKET_BITS;
 // seeding.cu
-int sketch_batch_device(sk_ctx* ctx, const uint8_t* d_ascii, uint64_t ascii_base, const uint64_t* contig_off, uint32_t n_contigs,
+struct SeedSrc {                 // where a sub-batch's sequence comes from
+  const uint8_t* d_ascii = nullptr;  // device ASCII of the contigs [n_packed, n_contigs): contig i at d_ascii + contig_off[i] - ascii_base
+  uint64_t ascii_base = 0;
+  uint64_t* d_P = nullptr;           // caller-owned unit arrays of the whole sub-batch with the units of the contigs
+  uint32_t* d_NM = nullptr;          //   [0, n_packed) already filled (2-bit codes / N mask); null = allocated by the callee
+  uint32_t n_packed = 0;
+};
+int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_off, uint32_t n_contigs,
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out);
 int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const std::vector<uint64_t>& raw_mk_off);
 void free_set_device(sk_sketch_set* s);
 int build_hash(sk_ctx* ctx, sk_sketch_set* set);
 // api.cu
-int sketch_batch_host(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs, const uint32_t* genome_of_contig,
+struct HostSeq {                 // host-resident sequence of a sketch batch: ASCII, or 2-bit units (+ optional N mask)
+  const uint8_t* ascii = nullptr;    // contig i at ascii + contig_off[i]
+  const uint64_t* units = nullptr;   // contig i at units + sum_{j<i} ceil(len_j / 32); base b of a unit in bits 2b..2b+1
+  const uint32_t* nmask = nullptr;   // same indexing, bit b = base b is 'N'; null = no 'N' anywhere
+};
+int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_off, uint32_t n_contigs, const uint32_t* genome_of_contig,
                       uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out,
                       const std::function<int(sk_sketch_set*, uint32_t, uint32_t)>* on_part, size_t subbatch_override);
+SkPool* ctx_pool(sk_ctx* ctx);
 int merge_sets(sk_ctx* ctx, const sk_sketch_set* base, const std::vector<sk_sketch_set*>& parts, sk_sketch_set** out);  // (re)builds set->htab from ukmer/ustart; call on every finished set
 // screen.cu / chain.cu
 uint64_t count_launch(sk_ctx* ctx, uint64_t n = 1);

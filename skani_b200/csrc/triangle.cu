@@ -141,7 +141,8 @@ extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* co
       cv.notify_one();
       return SK_OK;
     };
-    int rc = sk::sketch_batch_host(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, nullptr, &on_part, 1024ull << 20);
+    sk::HostSeq seq; seq.ascii = bases;
+    int rc = sk::sketch_batch_host(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, nullptr, &on_part, 1024ull << 20);
     { std::lock_guard<std::mutex> lk(mu); q.push_back(Wave{nullptr, 0, true}); }
     cv.notify_one();
     worker.join();

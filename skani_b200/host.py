@@ -47,6 +47,10 @@ class Context:
         return self.L.sk_ctx_launch_count(self.h)
 
     @property
+    def last_pack_share(self):
+        return self.L.sk_ctx_last_pack_share(self.h)
+
+    @property
     def stream(self):
         return self.L.sk_ctx_stream(self.h)
 
@@ -156,10 +160,37 @@ def sketch_contigs(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None,
         rc = ctx.L.sk_sketch_batch_dev(ctx.h, device_ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes,
                                        C.byref(sp), C.byref(out))
     else:
-        ptr = bases if isinstance(bases, int) else _as_u8(bases).ctypes.data
+        arr = None if isinstance(bases, int) else _as_u8(bases)   # keep the (possibly copied) array alive across the call
+        ptr = bases if arr is None else arr.ctypes.data
         rc = ctx.L.sk_sketch_batch(ctx.h, ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes,
                                    C.byref(sp), C.byref(out))
     ctx.check(rc)
+    return SketchSet(ctx, out)
+
+
+def pack_contigs(L, bases, contig_off):
+    """ASCII contigs -> (units uint64, nmask uint32, contig_len uint32) in sk_sketch_batch_2bit's layout (host side, sk_pack_contig)."""
+    bases = _as_u8(bases)
+    off = np.ascontiguousarray(contig_off, np.uint64)
+    lens = np.diff(off).astype(np.uint32)
+    uoff = np.concatenate([[0], np.cumsum((lens.astype(np.uint64) + 31) // 32)]).astype(np.uint64)
+    units = np.zeros(max(int(uoff[-1]), 1), np.uint64); nmask = np.zeros(max(int(uoff[-1]), 1), np.uint32)
+    for i in range(len(lens)):
+        rc = L.sk_pack_contig(bases.ctypes.data + int(off[i]), int(lens[i]), units.ctypes.data + 8 * int(uoff[i]), nmask.ctypes.data + 4 * int(uoff[i]))
+        assert rc == 0
+    return units, nmask, lens
+
+
+def sketch_contigs_2bit(ctx, units, nmask, contig_len, genome_of_contig, n_genomes, sp=None):
+    """sk_sketch_batch_2bit: sequences already packed as 2-bit units (+ optional N mask, None = no 'N')."""
+    sp = sp or sketch_params()
+    units = np.ascontiguousarray(units, np.uint64)
+    nm = None if nmask is None else np.ascontiguousarray(nmask, np.uint32)
+    cl = np.ascontiguousarray(contig_len, np.uint32)
+    goc = np.ascontiguousarray(genome_of_contig, np.uint32)
+    out = C.c_void_p()
+    ctx.check(ctx.L.sk_sketch_batch_2bit(ctx.h, units.ctypes.data, None if nm is None else nm.ctypes.data, cl.ctypes.data, len(cl),
+                                         goc.ctypes.data, n_genomes, C.byref(sp), C.byref(out)))
     return SketchSet(ctx, out)
 
 
@@ -277,7 +308,8 @@ def triangle(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=No
     sp = sp or sketch_params(); mp = mp or map_params()
     contig_off = np.ascontiguousarray(contig_off, np.uint64)
     goc = np.ascontiguousarray(genome_of_contig, np.uint32)
-    ptr = bases if isinstance(bases, int) else _as_u8(bases).ctypes.data
+    arr = None if isinstance(bases, int) else _as_u8(bases)       # keep the (possibly copied) array alive across the call
+    ptr = bases if arr is None else arr.ctypes.data
     out = C.POINTER(AniResult)(); n = C.c_uint64(); st = TriangleStats()
     ctx.check(ctx.L.sk_triangle(ctx.h, ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes, C.byref(sp),
                                 C.byref(mp), C.byref(out), C.byref(n), C.byref(st)))

@@ -44,6 +44,19 @@ int main() {
     if (P[nu] != 0xDEADBEEFull || M[nu] != 0xABCDu) { failures++; fprintf(stderr, "case %d wrote past the end\n", t); }
     cases++;
   }
+  // device-side SIMD-in-register conversion (sk::pack_word, used by pack_kernel) against ascii_code per byte
+  for (int t = 0; t < 2000000; t++) {
+    uint32_t x = 0;
+    const int mode = t % 3;
+    for (int b = 0; b < 4; b++) {
+      uint8_t c = mode == 0 ? (uint8_t)"ACGTacgtUu"[rng() % 10] : mode == 1 ? (uint8_t)alphabet[rng() % 25] : (uint8_t)(rng() & 0xFF);
+      x |= (uint32_t)c << (8 * b);
+    }
+    uint32_t c8, n4, rc = 0, rn = 0;
+    sk::pack_word(x, c8, n4);
+    for (int b = 0; b < 4; b++) { const uint32_t v = sk::ascii_code((x >> (8 * b)) & 0xFF); rc |= (v & 3) << (2 * b); rn |= (v >> 2) << b; }
+    if (c8 != rc || n4 != rn) { failures++; if (failures < 10) fprintf(stderr, "pack_word(%08x): %x/%x vs %x/%x\n", x, c8, n4, rc, rn); }
+  }
   // rate: 256 MB of ACGT, single thread
   {
     const size_t n = 256u << 20;

@@ -34,6 +34,26 @@ def build():
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
 
 
+def build_native():
+    """-march=native build for the CPU baseline (oracle/_native/liboracle.so); returns its path or None."""
+    try:
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "native"])
+        return os.path.join(ORACLE_DIR, "_native", "liboracle.so")
+    except Exception:
+        return None
+
+
+def use_library(path):
+    """Bind a specific build of the oracle (bench.py --impl reference: the -march=native one). Call before lib()."""
+    global LIB_PATH, _lib
+    LIB_PATH, _lib = path, None
+
+
+def set_avx2_intrinsics(on=True):
+    """Seeding with the reference's 4-lane AVX2 instruction mix (baseline timing); returns whether it is active."""
+    return bool(lib().orc_set_avx2_intrinsics(int(on)))
+
+
 def lib():
     global _lib
     if _lib is not None:
@@ -43,6 +63,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
     L.orc_mm_hash64.restype = u64; L.orc_mm_hash64.argtypes = [u64]
+    L.orc_set_avx2_intrinsics.restype = i32; L.orc_set_avx2_intrinsics.argtypes = [i32]
     L.orc_sketch_files.restype = i32
     L.orc_sketch_files.argtypes = [C.POINTER(C.c_char_p), i32, u64, u64, u64, i32, i32, i32,
                                    C.POINTER(C.POINTER(vp)), C.POINTER(i32), C.POINTER(i32)]

@@ -278,3 +278,61 @@ def test_pipelined_triangle_equals_simple(ctx, monkeypatch):
     assert st0.n_pairs_screened == st1.n_pairs_screened == n // G * (G * (G - 1) // 2)
     k0 = np.sort(r0, order=["ref_id", "query_id"]); k1 = np.sort(r1, order=["ref_id", "query_id"])
     assert len(k0) == len(k1) and k0.tobytes() == k1.tobytes()
+
+
+@pytest.mark.parametrize("subbatch", ["350000", "1300000", "2500000"])
+def test_pipelined_triangle_many_uneven_waves_vs_oracle(ctx, monkeypatch, subbatch):
+    """The pipelined path with several waves of uneven size (sub-batches of 1 / 4 / 8 genomes, wave threshold n/8), genomes
+    WITHOUT sequence in the middle and at the end (empty sketches), a cluster cut by every wave boundary, shuffled genome
+    order: the kept (ref, query, ANI, AF) set must equal the unpipelined result byte for byte AND the oracle within 1e-4."""
+    import skani_b200 as sk
+    n_real, L, G = 22, 300_000, 4
+    ids = synth.shuffled_ids(n_real, 3)
+    b0, off0, goc0 = synth.generate_ids(ids, L, G=G)
+    # genome slots: real genomes 0..9, an empty genome (no contigs), real 10..21, two empty genomes at the end
+    slot = np.concatenate([np.arange(10), np.arange(11, 23)])
+    goc = slot[goc0].astype(np.uint32)
+    n = 25
+    monkeypatch.setenv("SK_NO_PIPELINE", "1")
+    r0, _ = sk.triangle(ctx, b0, off0, goc, n, as_array=True)
+    monkeypatch.delenv("SK_NO_PIPELINE")
+    monkeypatch.setenv("SK_FORCE_PIPELINE", "1")
+    monkeypatch.setenv("SK_SUBBATCH_BYTES", subbatch)
+    r1, _ = sk.triangle(ctx, b0, off0, goc, n, as_array=True)
+    k0 = np.sort(r0, order=["ref_id", "query_id"]); k1 = np.sort(r1, order=["ref_id", "query_id"])
+    assert len(k0) == len(k1) > 0 and k0.tobytes() == k1.tobytes()
+    osk = []
+    for g in range(n):
+        idx = np.nonzero(goc == g)[0]
+        osk.append(O.sketch_from_contigs("g%06d" % g, [b0[int(off0[i]):int(off0[i + 1])] for i in idx]))
+    ores, _ = O.triangle(osk, O.cmd())
+    exp = {(r.ref_id, r.query_id): r for r in ores}
+    got = {(int(r["ref_id"]), int(r["query_id"])): r for r in k1}
+    assert set(got) == set(exp)
+    for k, e in exp.items():
+        for f in ("ani", "af_ref", "af_query"):
+            assert abs(float(got[k][f]) - getattr(e, f)) <= TOL, (k, f)
+
+
+def test_append_then_chain_parity(ctx):
+    """sk_sketch_set_append (the merge the pipelined worker and database loaders rely on): chaining across the appended
+    boundary gives the oracle's results, and user-set name ranks survive the append."""
+    import skani_b200 as sk
+    n, L, G = 8, 300_000, 4
+    bases, off, goc = synth.generate(0, n, L, G=G)
+    n3 = int(np.searchsorted(goc, 3))
+    a = sk.sketch_contigs(ctx, bases[:3 * L], off[:n3 + 1], goc[:n3], 3)
+    b = sk.sketch_contigs(ctx, bases[3 * L:], off[n3:] - off[n3], goc[n3:] - 3, n - 3)
+    a.set_name_ranks(np.arange(3))
+    a.append(b)
+    assert len(a) == n
+    pairs = sk.screen_triangle(ctx, a)
+    res = sk.chain_pairs(ctx, a, a, pairs, as_array=True)
+    osk = [O.sketch_from_contigs("g%06d" % g, [bases[int(off[i]):int(off[i + 1])] for i in np.nonzero(goc == g)[0]]) for g in range(n)]
+    ores, _ = O.triangle(osk, O.cmd())
+    exp = {(r.ref_id, r.query_id): r for r in ores}
+    got = {(int(r["ref_id"]), int(r["query_id"])): r for r in res if r["ani"] > 0.1}
+    assert set(got) == set(exp) and len(exp) == 2 * (G * (G - 1) // 2)
+    for k, e in exp.items():
+        for f in ("ani", "af_ref", "af_query"):
+            assert abs(float(got[k][f]) - getattr(e, f)) <= TOL, (k, f)

@@ -61,6 +61,7 @@ typedef struct {
 } sk_ani_result;
 
 /* ---- context ------------------------------------------------------------------------------- */
+int sk_device_count(void);   /* usable CUDA devices (0 = none: nothing in this library can run) */
 int sk_ctx_create(int device, sk_ctx** out);
 int sk_ctx_destroy(sk_ctx* ctx);
 const char* sk_last_error(const sk_ctx* ctx);
@@ -151,6 +152,7 @@ int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blo
  * SK_PACK_MARKERS_ONLY the blob carries the marker arrays only (enough for sk_screen_*; such a set chains to
  * "no anchors", ani = NaN).  Same blob / metadata format as sk_sketch_set_pack, so sk_sketch_set_unpack reads both. */
 #define SK_PACK_MARKERS_ONLY 1
+#define SK_PACK_TABLES 2   /* also carry the per-genome k-mer hash tables, so sk_sketch_set_unpack does not rebuild them */
 int sk_sketch_set_subset_blob_size(const sk_sketch_set* set, const uint32_t* genomes, uint32_t n, int flags,
                                    uint64_t* device_bytes, uint64_t* host_meta_words);
 int sk_sketch_set_pack_subset(const sk_sketch_set* set, const uint32_t* genomes, uint32_t n, int flags, void* d_blob,
@@ -215,6 +217,26 @@ typedef struct {
 int sk_triangle(sk_ctx* ctx, const uint8_t* bases_ascii, const uint64_t* contig_off, uint32_t n_contigs,
                 const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                 const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats);
+
+/* Same, and additionally hands back the device-resident sketch set of all n_genomes genomes (with their k-mer tables), e.g.
+ * to chain further pairs against it (the cross-block pairs of a multi-GPU run).  name_ranks: optional file-name order per
+ * genome for the switch_qr tie-break (see sk_sketch_set_set_name_ranks), NULL = index order.  Free with sk_sketch_set_free. */
+int sk_triangle_local(sk_ctx* ctx, const uint8_t* bases_ascii, const uint64_t* contig_off, uint32_t n_contigs,
+                      const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
+                      const sk_map_params* mp, const uint64_t* name_ranks, sk_ani_result** out, uint64_t* n_out,
+                      sk_triangle_stats* stats, sk_sketch_set** set_out);
+
+/* ---- multi-GPU triangle from ONE host process (north_star: host -> C-ABI shim -> one exchange of the
+ *      per-GPU sketch blocks over NVLink).  ctxs[0..n_ctx): one context per GPU (created with sk_ctx_create(device)); a
+ *      device may appear more than once (the exchange then stays on that device: how a 1-GPU box tests this path).
+ *      Genomes are split into contiguous blocks balanced by bases; every GPU runs the pipelined triangle on its block,
+ *      the MARKERS of all blocks are exchanged GPU-to-GPU and screened everywhere, and the cross-block pairs are cut into
+ *      equal slices whose sketches (with k-mer tables) are fetched from the owning GPUs.  Same result SET as sk_triangle
+ *      (row order differs; the reference's own sparse output order is arbitrary).  results: malloc'd (sk_free). */
+int sk_triangle_multi(sk_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* bases_ascii, const uint64_t* contig_off, uint32_t n_contigs,
+                      const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
+                      const sk_map_params* mp, const uint64_t* name_ranks, sk_ani_result** out, uint64_t* n_out,
+                      sk_triangle_stats* stats);
 
 #ifdef __cplusplus
 }

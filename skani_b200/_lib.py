@@ -42,6 +42,7 @@ class TriangleStats(C.Structure):
 vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 PP = C.POINTER
 SYMBOLS = [
+    ("sk_device_count", i32, []),
     ("sk_ctx_create", i32, [i32, PP(vp)]),
     ("sk_ctx_destroy", i32, [vp]),
     ("sk_last_error", C.c_char_p, [vp]),
@@ -76,6 +77,10 @@ SYMBOLS = [
     ("sk_chain_debug_free", None, [PP(ChainDebug)]),
     ("sk_triangle", i32, [vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(MapParams), PP(PP(AniResult)), PP(u64),
                           PP(TriangleStats)]),
+    ("sk_triangle_local", i32, [vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(MapParams), vp, PP(PP(AniResult)), PP(u64),
+                                PP(TriangleStats), PP(vp)]),
+    ("sk_triangle_multi", i32, [vp, u32, vp, vp, u32, vp, u32, PP(SketchParams), PP(MapParams), vp, PP(PP(AniResult)), PP(u64),
+                                PP(TriangleStats)]),
 ]
 
 _lib = None

@@ -134,7 +134,7 @@ struct Opts {
        short_header = false, distance = false, robust = false, median = false, no_learned = false, faster_small = false,
        small_genomes = false, fast = false, medium = false, slow = false, no_marker_index = false;
   uint64_t n = 1000000000000ull;
-  int threads = 3, device = 0;
+  int threads = 3, device = 0, gpus = 1;
   std::string db_dir;               // search -d
   bool separate_sketches = false;   // sketch --separate-sketches
 };
@@ -275,21 +275,44 @@ int run_triangle(Opts& op) {
   mp.rescue_small = !op.faster_small && !op.small_genomes;
   mp.learned_ani = !op.no_learned && op.c >= 70 && !op.individual && !op.median;   // regression::use_learned_ani (src/regression.rs:8-10)
   if (mp.learned_ani) fprintf(stderr, "INFO Learned ANI mode detected. ANI may be adjusted according to a regression model trained on MAGs.\n");
-  sk_sketch_set* set = loaded ? loaded : sketch(ctx, in, sp);
-  {  // file-name order for the switch_qr tie-break (src/chain.rs:19-21): with -i all records of a file share its name
-    std::vector<uint64_t> ranks(in.genomes.size());
+  // file-name order for the switch_qr tie-break (src/chain.rs:19-21): with -i all records of a file share its name
+  std::vector<uint64_t> ranks(in.genomes.size());
+  {
     uint64_t rank = 0;
     for (size_t i = 0; i < in.genomes.size(); i++) {
       if (i && in.genomes[i].file_name != in.genomes[i - 1].file_name) rank++;
       ranks[i] = rank;
     }
-    sk_sketch_set_set_name_ranks(set, ranks.data());
   }
-  uint64_t* pairs = nullptr; uint64_t np = 0;
-  CK(ctx, sk_screen_triangle(ctx, set, &mp, &pairs, &np));
-  std::vector<sk_ani_result> res(np);
-  CK(ctx, sk_chain_pairs(ctx, set, set, pairs, np, &mp, res.data()));
-  sk_free(pairs);
+  std::vector<sk_ani_result> res;
+  sk_sketch_set* set = nullptr;
+  if (op.gpus > 1 && !loaded) {
+    // --gpus N: one context per GPU, genome blocks + marker exchange + cross-block slices (sk_triangle_multi).  With fewer
+    // physical devices than N the contexts share devices (same code path; the exchange then stays on the device).
+    const int ndev = sk_device_count();
+    if (ndev < op.gpus) fprintf(stderr, "WARN --gpus %d but %d CUDA device(s) visible: contexts share devices.\n", op.gpus, ndev);
+    std::vector<sk_ctx*> ctxs(1, ctx);
+    for (int d = 1; d < op.gpus; d++) {
+      sk_ctx* c = nullptr;
+      if (sk_ctx_create((op.device + d) % std::max(ndev, 1), &c) != 0) { fprintf(stderr, "ERROR cannot create a context on GPU %d\n", (op.device + d) % std::max(ndev, 1)); return 1; }
+      ctxs.push_back(c);
+    }
+    sk_ani_result* r = nullptr; uint64_t nr = 0;
+    CK(ctx, sk_triangle_multi(ctxs.data(), (uint32_t)ctxs.size(), in.bases.data(), in.contig_off.data(), (uint32_t)in.genome_of_contig.size(),
+                              in.genome_of_contig.data(), (uint32_t)in.genomes.size(), &sp, &mp, ranks.data(), &r, &nr, nullptr));
+    res.assign(r, r + nr);
+    sk_free(r);
+    std::sort(res.begin(), res.end(), [](const sk_ani_result& a, const sk_ani_result& b) { return a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.query_id < b.query_id; });
+    for (size_t d = 1; d < ctxs.size(); d++) sk_ctx_destroy(ctxs[d]);
+  } else {
+    set = loaded ? loaded : sketch(ctx, in, sp);
+    sk_sketch_set_set_name_ranks(set, ranks.data());
+    uint64_t* pairs = nullptr; uint64_t np = 0;
+    CK(ctx, sk_screen_triangle(ctx, set, &mp, &pairs, &np));
+    res.resize(np);
+    CK(ctx, sk_chain_pairs(ctx, set, set, pairs, np, &mp, res.data()));
+    sk_free(pairs);
+  }
   const size_t N = in.genomes.size();
   FILE* o = op.out.empty() ? stdout : fopen(op.out.c_str(), "w");
   if (!o) { fprintf(stderr, "ERROR cannot open %s\n", op.out.c_str()); return 1; }
@@ -332,7 +355,7 @@ int run_triangle(Opts& op) {
     fprintf(stderr, "INFO Aligned fraction matrix written to %s\n", af_name.c_str());
   }
   if (o != stdout) fclose(o);
-  sk_sketch_set_free(set);
+  if (set) sk_sketch_set_free(set);
   sk_ctx_destroy(ctx);
   return 0;
 }
@@ -730,6 +753,7 @@ int main(int argc, char** argv) {
     else if (a == "--robust") op.robust = true;
     else if (a == "--median") op.median = true;
     else if (a == "--no-learned-ani") op.no_learned = true;
+    else if (a == "--gpus") op.gpus = std::max(1, atoi(val().c_str()));
     else if (a == "--faster-small") op.faster_small = true;
     else if (a == "--small-genomes") op.small_genomes = true;
     else if (a == "--fast") op.fast = true;

@@ -190,8 +190,9 @@ int concat_dev(sk_ctx* ctx, const std::vector<const T*>& parts, const std::vecto
   return SK_OK;
 }
 
-// concatenate sketch sets (genome-local indexing everywhere, so only the prefix offsets shift)
-int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_sketch_set** out) {
+// concatenate sketch sets (genome-local indexing everywhere, so only the prefix offsets shift).  with_tables: the parts
+// carry their k-mer hash tables (ht_off / htab) and the result takes them over by copy instead of rebuilding them.
+int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_sketch_set** out, bool with_tables = false) {
   sk_sketch_set* s = new sk_sketch_set();
   s->ctx = ctx;
   s->sp = parts.empty() ? sk_sketch_params{125, 15, 1000} : parts[0]->sp;
@@ -223,6 +224,15 @@ int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_
   CAT(pv_kmer, uint32_t, nS) CAT(pv_pos, uint32_t, nS) CAT(pv_cc, uint32_t, nS) CAT(pv_mult, uint16_t, nS)
   CAT(kv_pos, uint32_t, nS) CAT(kv_cc, uint32_t, nS) CAT(ukmer, uint32_t, nU) CAT(ustart, uint32_t, nUG)
   CAT(markers, uint64_t, nM) CAT(ctg_rec_off, uint32_t, nCG) CAT(d_ctg_len, uint32_t, nC)
+  if (with_tables) {
+    std::vector<size_t> nH;
+    s->ht_off = {0};
+    for (auto* p : parts) {
+      for (uint32_t g = 0; g < p->G; g++) s->ht_off.push_back(s->ht_off.back() + (p->ht_off[g + 1] - p->ht_off[g]));
+      nH.push_back(p->ht_off[p->G]);
+    }
+    CAT(htab, unsigned long long, nH)
+  }
 #undef CAT
   SK_CUDA(cudaStreamSynchronize(ctx->stream));
   guard.s = nullptr;
@@ -287,6 +297,12 @@ int sk_ctx_destroy(sk_ctx* ctx) {
   cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return SK_OK;
+}
+
+int sk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
 }
 
 const char* sk_last_error(const sk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -399,23 +415,26 @@ int sk_sketch_set_append(sk_sketch_set* dst, const sk_sketch_set* src) {
 }
 
 namespace {
+constexpr int BLOB_ARRAYS = 12;     // 11 set arrays + the k-mer hash tables (present only with SK_PACK_TABLES)
+constexpr int META_HEADER = 10;     // G S U M C c k marker_c HT flags
 struct BlobLayout {
-  size_t off[11];
-  size_t bytes[11];
+  size_t off[BLOB_ARRAYS];
+  size_t bytes[BLOB_ARRAYS];
   size_t total;
 };
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
-BlobLayout blob_layout(size_t G, size_t S, size_t U, size_t M, size_t Cn) {
+BlobLayout blob_layout(size_t G, size_t S, size_t U, size_t M, size_t Cn, size_t HT = 0) {
   BlobLayout b;
-  const size_t n[11] = {S * 4, S * 4, S * 4, S * 2, S * 4, S * 4, U * 4, (U + G) * 4, M * 8, (Cn + G) * 4, Cn * 4};
+  const size_t n[BLOB_ARRAYS] = {S * 4, S * 4, S * 4, S * 2, S * 4, S * 4, U * 4, (U + G) * 4, M * 8, (Cn + G) * 4, Cn * 4, HT * 8};
   size_t o = 0;
-  for (int i = 0; i < 11; i++) { b.off[i] = o; b.bytes[i] = n[i]; o += al256(n[i]); }
+  for (int i = 0; i < BLOB_ARRAYS; i++) { b.off[i] = o; b.bytes[i] = n[i]; o += al256(n[i]); }
   b.total = o ? o : 256;
   return b;
 }
+inline uint64_t meta_words(uint64_t G, uint64_t C, bool tables) { return META_HEADER + 4 * (G + 1) + G + C + (tables ? G + 1 : 0); }
 inline const void* set_array(const sk_sketch_set* s, int i) {
-  const void* p[11] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart, s->markers, s->ctg_rec_off,
-                       s->d_ctg_len};
+  const void* p[BLOB_ARRAYS] = {s->pv_kmer, s->pv_pos, s->pv_cc, s->pv_mult, s->kv_pos, s->kv_cc, s->ukmer, s->ustart, s->markers, s->ctg_rec_off,
+                                 s->d_ctg_len, s->htab};
   return p[i];
 }
 }  // namespace
@@ -423,7 +442,7 @@ inline const void* set_array(const sk_sketch_set* s, int i) {
 int sk_sketch_set_blob_size(const sk_sketch_set* s, uint64_t* device_bytes, uint64_t* host_meta_words) {
   if (!s || !device_bytes || !host_meta_words) return SK_ERR_PARAM;
   *device_bytes = blob_layout(s->G, s->S, s->U, s->M, s->C).total;
-  *host_meta_words = 8 + 4 * ((uint64_t)s->G + 1) + s->G + s->C;
+  *host_meta_words = meta_words(s->G, s->C, false);
   return SK_OK;
 }
 
@@ -435,7 +454,7 @@ int sk_sketch_set_pack(const sk_sketch_set* s, void* d_blob, uint64_t* meta) {
   for (int i = 0; i < 11; i++)
     if (b.bytes[i]) SK_CUDA(cudaMemcpyAsync((uint8_t*)d_blob + b.off[i], set_array(s, i), b.bytes[i], cudaMemcpyDeviceToDevice, ctx->stream));
   uint64_t* m = meta;
-  *m++ = s->G; *m++ = s->S; *m++ = s->U; *m++ = s->M; *m++ = s->C; *m++ = s->sp.c; *m++ = s->sp.k; *m++ = s->sp.marker_c;
+  *m++ = s->G; *m++ = s->S; *m++ = s->U; *m++ = s->M; *m++ = s->C; *m++ = s->sp.c; *m++ = s->sp.k; *m++ = s->sp.marker_c; *m++ = 0; *m++ = 0;
   for (uint32_t g = 0; g <= s->G; g++) *m++ = s->seed_off[g];
   for (uint32_t g = 0; g <= s->G; g++) *m++ = s->uk_off[g];
   for (uint32_t g = 0; g <= s->G; g++) *m++ = s->mk_off[g];
@@ -450,23 +469,26 @@ namespace {
 // host-side plan of a subset blob: maximal runs of consecutive genomes are copied with one memcpy per array
 struct SubsetPlan {
   std::vector<uint32_t> idx;                        // selected genomes, in output order
-  std::vector<uint64_t> seed_off, uk_off, mk_off, ctg_off;
-  size_t S = 0, U = 0, M = 0, C = 0;
+  std::vector<uint64_t> seed_off, uk_off, mk_off, ctg_off, ht_off;
+  size_t S = 0, U = 0, M = 0, C = 0, HT = 0;
+  bool tables = false;
 };
 int plan_subset(const sk_sketch_set* s, const uint32_t* genomes, uint32_t n, int flags, SubsetPlan& pl) {
   const bool mo = (flags & SK_PACK_MARKERS_ONLY) != 0;
   if (!genomes) { n = s->G; pl.idx.resize(n); for (uint32_t i = 0; i < n; i++) pl.idx[i] = i; }
   else pl.idx.assign(genomes, genomes + n);
-  pl.seed_off.assign(n + 1, 0); pl.uk_off.assign(n + 1, 0); pl.mk_off.assign(n + 1, 0); pl.ctg_off.assign(n + 1, 0);
+  pl.seed_off.assign(n + 1, 0); pl.uk_off.assign(n + 1, 0); pl.mk_off.assign(n + 1, 0); pl.ctg_off.assign(n + 1, 0); pl.ht_off.assign(n + 1, 0);
+  pl.tables = !mo && (flags & SK_PACK_TABLES) != 0 && s->htab != nullptr && s->ht_off.size() == (size_t)s->G + 1;
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t g = pl.idx[i];
     if (g >= s->G) { s->ctx->err = "subset genome index out of range"; return SK_ERR_PARAM; }
+    pl.ht_off[i + 1] = pl.ht_off[i] + (pl.tables ? s->ht_off[g + 1] - s->ht_off[g] : 0);
     pl.seed_off[i + 1] = pl.seed_off[i] + (mo ? 0 : s->seed_off[g + 1] - s->seed_off[g]);
     pl.uk_off[i + 1] = pl.uk_off[i] + (mo ? 0 : s->uk_off[g + 1] - s->uk_off[g]);
     pl.ctg_off[i + 1] = pl.ctg_off[i] + (mo ? 0 : s->ctg_off[g + 1] - s->ctg_off[g]);
     pl.mk_off[i + 1] = pl.mk_off[i] + (s->mk_off[g + 1] - s->mk_off[g]);
   }
-  pl.S = pl.seed_off[n]; pl.U = pl.uk_off[n]; pl.M = pl.mk_off[n]; pl.C = pl.ctg_off[n];
+  pl.S = pl.seed_off[n]; pl.U = pl.uk_off[n]; pl.M = pl.mk_off[n]; pl.C = pl.ctg_off[n]; pl.HT = pl.ht_off[n];
   return SK_OK;
 }
 }  // namespace
@@ -477,8 +499,8 @@ int sk_sketch_set_subset_blob_size(const sk_sketch_set* s, const uint32_t* genom
   SubsetPlan pl;
   SK_TRY(plan_subset(s, genomes, n, flags, pl));
   const size_t G = pl.idx.size();
-  *device_bytes = blob_layout(G, pl.S, pl.U, pl.M, pl.C).total;
-  *host_meta_words = 8 + 4 * ((uint64_t)G + 1) + G + pl.C;
+  *device_bytes = blob_layout(G, pl.S, pl.U, pl.M, pl.C, pl.HT).total;
+  *host_meta_words = meta_words(G, pl.C, pl.tables);
   return SK_OK;
 }
 
@@ -490,7 +512,7 @@ int sk_sketch_set_pack_subset(const sk_sketch_set* s, const uint32_t* genomes, u
   SK_TRY(plan_subset(s, genomes, n, flags, pl));
   const bool mo = (flags & SK_PACK_MARKERS_ONLY) != 0;
   const uint32_t G = (uint32_t)pl.idx.size();
-  const BlobLayout b = blob_layout(G, pl.S, pl.U, pl.M, pl.C);
+  const BlobLayout b = blob_layout(G, pl.S, pl.U, pl.M, pl.C, pl.HT);
   uint8_t* base = (uint8_t*)d_blob;
   cudaStream_t st = ctx->stream;
   auto cp = [&](int arr, size_t dst_elem, const void* src, size_t src_elem, size_t count, size_t esz) -> cudaError_t {
@@ -515,12 +537,14 @@ int sk_sketch_set_pack_subset(const sk_sketch_set* s, const uint32_t* genomes, u
       SK_CUDA(cp(7, pl.uk_off[i] + i, s->ustart, uo + a, nu + (e - a), 4));          // + one sentinel per genome
       SK_CUDA(cp(9, pl.ctg_off[i] + i, s->ctg_rec_off, co + a, nc + (e - a), 4));
       SK_CUDA(cp(10, pl.ctg_off[i], s->d_ctg_len, co, nc, 4));
+      if (pl.tables) SK_CUDA(cp(11, pl.ht_off[i], s->htab, s->ht_off[a], s->ht_off[e] - s->ht_off[a], 8));
     }
     SK_CUDA(cp(8, pl.mk_off[i], s->markers, s->mk_off[a], s->mk_off[e] - s->mk_off[a], 8));
     i = j;
   }
   uint64_t* m = meta;
   *m++ = G; *m++ = pl.S; *m++ = pl.U; *m++ = pl.M; *m++ = pl.C; *m++ = s->sp.c; *m++ = s->sp.k; *m++ = s->sp.marker_c;
+  *m++ = pl.HT; *m++ = pl.tables ? 1 : 0;
   for (uint32_t g = 0; g <= G; g++) *m++ = pl.seed_off[g];
   for (uint32_t g = 0; g <= G; g++) *m++ = pl.uk_off[g];
   for (uint32_t g = 0; g <= G; g++) *m++ = pl.mk_off[g];
@@ -529,6 +553,7 @@ int sk_sketch_set_pack_subset(const sk_sketch_set* s, const uint32_t* genomes, u
   if (!mo)
     for (uint32_t g = 0; g < G; g++)
       for (uint64_t c = s->ctg_off[pl.idx[g]]; c < s->ctg_off[pl.idx[g] + 1]; c++) *m++ = s->ctg_len[c];
+  if (pl.tables) for (uint32_t g = 0; g <= G; g++) *m++ = pl.ht_off[g];
   SK_CUDA(cudaStreamSynchronize(st));
   return SK_OK;
 }
@@ -537,6 +562,7 @@ int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blo
   if (!ctx || !out || n_parts == 0 || !d_blobs || !metas) return SK_ERR_PARAM;
   SK_CUDA(cudaSetDevice(ctx->device));
   // non-owning views over the blobs, then one concatenating copy
+  bool all_tables = true;
   std::vector<sk_sketch_set> views(n_parts);
   std::vector<const sk_sketch_set*> vp;
   for (uint32_t i = 0; i < n_parts; i++) {
@@ -545,7 +571,10 @@ int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blo
     v.ctx = ctx;
     v.G = (uint32_t)m[0]; v.S = m[1]; v.U = m[2]; v.M = m[3]; v.C = m[4];
     v.sp.c = (uint32_t)m[5]; v.sp.k = (uint32_t)m[6]; v.sp.marker_c = (uint32_t)m[7];
-    m += 8;
+    const uint64_t HT = m[8];
+    const bool tables = m[9] != 0;
+    all_tables = all_tables && (tables || v.U == 0);
+    m += META_HEADER;
     v.seed_off.assign(m, m + v.G + 1); m += v.G + 1;
     v.uk_off.assign(m, m + v.G + 1); m += v.G + 1;
     v.mk_off.assign(m, m + v.G + 1); m += v.G + 1;
@@ -554,15 +583,27 @@ int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blo
     v.ctg_len.resize(v.C);
     for (size_t c = 0; c < v.C; c++) v.ctg_len[c] = (uint32_t)m[c];
     v.name_rank.resize(v.G);
-    BlobLayout b = blob_layout(v.G, v.S, v.U, v.M, v.C);
+    if (tables) { v.ht_off.assign(m + v.C, m + v.C + v.G + 1); }
+    else v.ht_off.assign((size_t)v.G + 1, 0);
+    BlobLayout b = blob_layout(v.G, v.S, v.U, v.M, v.C, HT);
     uint8_t* base = (uint8_t*)d_blobs[i];
+    v.htab = (unsigned long long*)(base + b.off[11]);
     v.pv_kmer = (uint32_t*)(base + b.off[0]); v.pv_pos = (uint32_t*)(base + b.off[1]); v.pv_cc = (uint32_t*)(base + b.off[2]);
     v.pv_mult = (uint16_t*)(base + b.off[3]); v.kv_pos = (uint32_t*)(base + b.off[4]); v.kv_cc = (uint32_t*)(base + b.off[5]);
     v.ukmer = (uint32_t*)(base + b.off[6]); v.ustart = (uint32_t*)(base + b.off[7]); v.markers = (uint64_t*)(base + b.off[8]);
     v.ctg_rec_off = (uint32_t*)(base + b.off[9]); v.d_ctg_len = (uint32_t*)(base + b.off[10]);
     vp.push_back(&v);
   }
-  SK_TRY(concat_sets(ctx, vp, out));
+  // blobs packed with SK_PACK_TABLES bring their k-mer hash tables along: no rebuild (genomes too large for a table, which
+  // use the bucket index instead, fall back to the rebuild)
+  if (all_tables) {
+    for (auto& v : views)
+      for (uint32_t g = 0; g < v.G && all_tables; g++)
+        if (v.uk_off[g + 1] > v.uk_off[g] && v.ht_off[g + 1] == v.ht_off[g]) all_tables = false;
+  }
+  SK_TRY(concat_sets(ctx, vp, out, all_tables));
+  for (auto& v : views) v.htab = nullptr;
+  if (all_tables) return SK_OK;
   return build_hash(ctx, *out);
 }
 

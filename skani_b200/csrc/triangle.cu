@@ -29,10 +29,12 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 
 int simple_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs, const uint32_t* genome_of_contig,
                     uint32_t n_genomes, const sk_sketch_params* sp, const sk_map_params* mp, std::vector<sk_ani_result>& kept,
-                    uint64_t* n_screened) {
+                    uint64_t* n_screened, sk_sketch_set** keep, const uint64_t* name_ranks) {
   sk_sketch_set* set = nullptr;
   SK_TRY(sk_sketch_batch(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, &set));
-  struct SG { sk_sketch_set* s; ~SG() { sk_sketch_set_free(s); } } sg{set};
+  if (name_ranks) sk_sketch_set_set_name_ranks(set, name_ranks);
+  struct SG { sk_sketch_set* s; sk_sketch_set** keep; ~SG() { if (keep && s) *keep = s; else sk_sketch_set_free(s); } } sg{set, keep};
+  if (keep) *keep = nullptr;
   uint64_t* pairs = nullptr;
   uint64_t np = 0;
   SK_TRY(sk_screen_triangle(ctx, set, mp, &pairs, &np));
@@ -44,13 +46,35 @@ int simple_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
   return SK_OK;
 }
 
+int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+                  const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
+                  const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats, sk_sketch_set** keep,
+                  const uint64_t* name_ranks);
+
 }  // namespace
 
 extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
                            const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                            const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats) {
+  return triangle_impl(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, out, n_out, stats, nullptr, nullptr);
+}
+
+extern "C" int sk_triangle_local(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+                                 const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
+                                 const sk_map_params* mp, const uint64_t* name_ranks, sk_ani_result** out, uint64_t* n_out,
+                                 sk_triangle_stats* stats, sk_sketch_set** set_out) {
+  if (!set_out) return SK_ERR_PARAM;
+  return triangle_impl(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, out, n_out, stats, set_out, name_ranks);
+}
+
+namespace {
+int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+                  const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
+                  const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats, sk_sketch_set** keep,
+                  const uint64_t* name_ranks) {
   if (!ctx || !out || !n_out || !sp || !mp || !contig_off) return SK_ERR_PARAM;
   *out = nullptr; *n_out = 0;
+  if (keep) *keep = nullptr;
   SK_CUDA(cudaSetDevice(ctx->device));
   cudaEvent_t ev[2];
   for (auto& e : ev) SK_CUDA(cudaEventCreate(&e));
@@ -64,9 +88,10 @@ extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* co
   // state) and h2d_small (parameter uploads bypass the H2D copy engine that is saturated by the sequence upload);
   // see profiles/r01_pipeline_trace.txt.
   const bool pipelined = ((total_bytes >= (4ull << 30) && n_genomes >= 64) || (getenv("SK_FORCE_PIPELINE") && n_genomes >= 2)) &&
-                         getenv("SK_NO_PIPELINE") == nullptr;
+                         getenv("SK_NO_PIPELINE") == nullptr && n_contigs > 0;
   if (!pipelined) {
-    SK_TRY(simple_triangle(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, kept, &n_screened));
+    int rc = simple_triangle(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, kept, &n_screened, keep, name_ranks);
+    if (rc != SK_OK) { if (keep && *keep) { sk_sketch_set_free(*keep); *keep = nullptr; } return rc; }
   } else {
     // ---- producer: ONE continuous upload + seeding pass (the H2D stream never drains); every finished sub-batch is
     //      handed to the worker.  Worker: once >= 1/8 of the genomes are pending (or the input is finished) it merges
@@ -83,9 +108,9 @@ extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* co
     std::deque<Wave> q;
     int worker_rc = SK_OK;
     std::string worker_err;
+    sk_sketch_set* merged = nullptr;        // the set sketched so far (owned by the worker context's arena)
     std::thread worker([&] {
       cudaSetDevice(wctx->device);
-      sk_sketch_set* merged = nullptr;
       std::vector<sk_sketch_set*> pending;
       uint32_t pending_begin = 0, pending_genomes = 0;
       bool done = false;
@@ -111,6 +136,10 @@ extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* co
           if (rc == SK_OK) {
             if (merged) sk_sketch_set_free(merged);
             merged = next;
+            if (name_ranks) {   // file-name order of the caller (switch_qr tie-break); the merged set covers genomes [0, merged->G)
+              for (uint32_t g = 0; g < merged->G; g++) merged->name_rank[g] = name_ranks[g];
+              merged->ranks_user_set = true;
+            }
             uint64_t* pairs = nullptr; uint64_t np = 0;
             rc = sk_screen_triangle(wctx, merged, mp, &pairs, &np);
             tc = now_s();
@@ -132,7 +161,7 @@ extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* co
         for (auto* p : pending) sk_sketch_set_free(p);
         pending.clear(); pending_genomes = 0;
       }
-      if (merged) { cudaStreamSynchronize(wctx->stream); sk_sketch_set_free(merged); }
+      cudaStreamSynchronize(wctx->stream);
     });
     std::function<int(sk_sketch_set*, uint32_t, uint32_t)> on_part = [&](sk_sketch_set* part, uint32_t g_begin, uint32_t g_end) -> int {
       (void)g_end;
@@ -146,8 +175,16 @@ extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* co
     { std::lock_guard<std::mutex> lk(mu); q.push_back(Wave{nullptr, 0, true}); }
     cv.notify_one();
     worker.join();
+    if (rc != SK_OK || worker_rc != SK_OK || !keep) { if (merged) sk_sketch_set_free(merged); merged = nullptr; }
     if (rc != SK_OK) return rc;
     if (worker_rc != SK_OK) { ctx->err = "worker: " + worker_err; return worker_rc; }
+    if (keep) {
+      if (!merged) {   // no genome carried sequence: an empty set of n_genomes sketches
+        uint64_t z = 0;
+        SK_TRY(sk_sketch_batch(ctx, (const uint8_t*)"", &z, 0, nullptr, n_genomes, sp, &merged));
+      }
+      *keep = merged;
+    }
   }
   SK_CUDA(cudaEventRecord(ev[1], ctx->stream));
   SK_CUDA(cudaEventSynchronize(ev[1]));
@@ -164,3 +201,4 @@ extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* co
   }
   return SK_OK;
 }
+}  // namespace

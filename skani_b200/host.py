@@ -319,3 +319,42 @@ def triangle(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=No
         res = [AniResult.from_buffer_copy(out[i]) for i in range(n.value)]
     ctx.L.sk_free(out)
     return res, st
+
+
+def _take_results(ctx, out, n, as_array):
+    if as_array:
+        res = np.frombuffer(C.string_at(out, n.value * C.sizeof(AniResult)), RESULT_DTYPE).copy() if n.value else np.zeros(0, RESULT_DTYPE)
+    else:
+        res = [AniResult.from_buffer_copy(out[i]) for i in range(n.value)]
+    ctx.L.sk_free(out)
+    return res
+
+
+def triangle_local(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=None, name_ranks=None, as_array=True):
+    """sk_triangle_local: the whole triangle of one genome block + the block's device-resident sketch set (with k-mer tables)."""
+    sp = sp or sketch_params(); mp = mp or map_params()
+    contig_off = np.ascontiguousarray(contig_off, np.uint64)
+    goc = np.ascontiguousarray(genome_of_contig, np.uint32)
+    arr = None if isinstance(bases, int) else _as_u8(bases)
+    ptr = bases if arr is None else arr.ctypes.data
+    nr = None if name_ranks is None else np.ascontiguousarray(name_ranks, np.uint64)
+    out = C.POINTER(AniResult)(); n = C.c_uint64(); st = TriangleStats(); h = C.c_void_p()
+    ctx.check(ctx.L.sk_triangle_local(ctx.h, ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes, C.byref(sp), C.byref(mp),
+                                      None if nr is None else nr.ctypes.data, C.byref(out), C.byref(n), C.byref(st), C.byref(h)))
+    return _take_results(ctx, out, n, as_array), SketchSet(ctx, h), st
+
+
+def triangle_multi(ctxs, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=None, name_ranks=None, as_array=True):
+    """sk_triangle_multi: one host process, one context per GPU (a device may repeat: the exchange then stays on it)."""
+    sp = sp or sketch_params(); mp = mp or map_params()
+    contig_off = np.ascontiguousarray(contig_off, np.uint64)
+    goc = np.ascontiguousarray(genome_of_contig, np.uint32)
+    arr = None if isinstance(bases, int) else _as_u8(bases)
+    ptr = bases if arr is None else arr.ctypes.data
+    nr = None if name_ranks is None else np.ascontiguousarray(name_ranks, np.uint64)
+    hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    out = C.POINTER(AniResult)(); n = C.c_uint64(); st = TriangleStats()
+    c0 = ctxs[0]
+    c0.check(c0.L.sk_triangle_multi(hs, len(ctxs), ptr, contig_off.ctypes.data, len(goc), goc.ctypes.data, n_genomes, C.byref(sp), C.byref(mp),
+                                    None if nr is None else nr.ctypes.data, C.byref(out), C.byref(n), C.byref(st)))
+    return _take_results(c0, out, n, as_array), st

@@ -1,14 +1,18 @@
-"""Multi-GPU `triangle` (one process per GPU, torch.distributed for the plumbing).
+"""Multi-GPU `triangle` (one process per GPU, torch.distributed for the plumbing; the one-process form of the same
+scheme is sk_triangle_multi, skani_b200/csrc/multi.cu).
 
 The reference is a single process (rayon threads); the pair loop of src/triangle.rs:71-105 shards naturally:
-  1. every rank sketches a contiguous block of genomes (seeding is independent per genome);
+  1. every rank owns a contiguous block of genomes and runs the pipelined single-GPU triangle on it (sk_triangle_local:
+     upload || seed || screen || chain of the pairs INSIDE the block) and keeps the block's sketch set;
   2. the MARKERS of every genome (8 B x L/1000 per genome: 0.4 GB for 10k genomes) are all-gathered and every rank
-     screens the whole triangle (a few ms) -> the same sorted list of passing pairs on every rank;
-  3. the sorted pair list is cut into `world` contiguous slices (equal chaining work by construction); a rank needs the
-     full sketches of just the genomes its slice touches.  Because the list is sorted by (i, j) and related genomes
-     tend to be neighbours, most of them are the rank's own block; the rest arrive in ONE variable all-to-all (NCCL
-     over NVLink/NVSwitch) of per-destination sub-blobs (sk_sketch_set_pack_subset).  Worst case (relatedness unrelated
-     to the input order) this degenerates to the volume of a full all-gather, never more;
+     screens the whole triangle (a few ms) -> the same sorted list of passing pairs on every rank; pairs inside one
+     block are dropped (done in step 1);
+  3. the remaining CROSS-BLOCK pairs are cut into `world` contiguous slices (equal chaining work by construction); a rank
+     needs the full sketches of just the genomes its slice touches; they arrive in ONE variable all-to-all (NCCL over
+     NVLink/NVSwitch) of per-destination sub-blobs that carry the k-mer hash tables along (sk_sketch_set_pack_subset,
+     SK_PACK_TABLES: nothing is rebuilt on arrival).  With related genomes adjacent in the input there are hardly any
+     cross-block pairs; with a random input order (1 - 1/world) of all pairs are cross-block and the exchange approaches
+     the volume of a full all-gather, never more;
   4. each rank rebuilds a working set from what it received (rank-major = ascending global genome order), chains its
      slice, maps the ids back to global ones.  Results stay on their rank (the reference's sparse output order is
      nondeterministic anyway).
@@ -23,6 +27,7 @@ import numpy as np
 from . import host as H
 
 PACK_MARKERS_ONLY = 1        # include/skani_b200.h SK_PACK_MARKERS_ONLY
+PACK_TABLES = 2              # include/skani_b200.h SK_PACK_TABLES
 
 
 def shard_range(n_items, world, rank):
@@ -70,6 +75,17 @@ def fetch_plan(sorted_pairs, world, rank, bounds):
     cut = np.searchsorted(need, bounds)
     recv_counts = np.diff(cut).astype(np.int64)
     return need, send, recv_counts
+
+
+def cross_block_pairs(sorted_pairs, bounds):
+    """The pairs whose two genomes live in different blocks (bounds[r] .. bounds[r+1] = block of rank r)."""
+    p = np.asarray(sorted_pairs, np.uint64)
+    if len(p) == 0:
+        return p
+    b = np.asarray(bounds, np.int64)[1:]
+    bi = np.searchsorted(b, (p >> np.uint64(32)).astype(np.int64), side="right")
+    bj = np.searchsorted(b, (p & np.uint64(0xFFFFFFFF)).astype(np.int64), side="right")
+    return np.ascontiguousarray(p[bi != bj])
 
 
 def remap_pairs(pairs, need):
@@ -179,14 +195,14 @@ class DistTriangle:
     # ---- partial exchange: every rank receives the sketches of the genomes its pair slice touches ----------------
     def fetch(self, local_set, send, recv_counts):
         """send[d] = local genome indices for rank d (ascending).  Returns the working set: the received genomes in
-        source-rank order (= ascending global order)."""
+        source-rank order (= ascending global order).  Sub-blobs carry the k-mer tables (no rebuild on arrival)."""
         torch = self.torch
-        sizes = [local_set.subset_blob_size(send[d], 0) for d in range(self.world)]
+        sizes = [local_set.subset_blob_size(send[d], PACK_TABLES) for d in range(self.world)]
         blobs = torch.empty(sum(s[0] for s in sizes), dtype=torch.uint8, device=self.device)
         parts, metas, o = [], [], 0
         for d in range(self.world):
             part = blobs[o:o + sizes[d][0]]
-            metas.append(local_set.pack_subset(send[d], 0, part.data_ptr(), sizes[d][1]))
+            metas.append(local_set.pack_subset(send[d], PACK_TABLES, part.data_ptr(), sizes[d][1]))
             parts.append(part)
             o += sizes[d][0]
         got = alltoall_variable(self.dist, parts, self.world, self.device, src=blobs)
@@ -205,10 +221,18 @@ class DistTriangle:
         torch = self.torch
         trace = os.environ.get("SK_TRACE") and self.rank == 0
         t0 = time.perf_counter()
-        if host_bases is not None:
-            local = H.sketch_contigs(ctx, host_bases, off, goc, nloc, self.sp)
-        else:
+        ranks_local = None if self.name_ranks is None else self.name_ranks[g0:g0 + nloc]
+        if host_bases is not None:      # pipelined: upload || seed || screen || chain inside the block
+            res_local, local, _st = H.triangle_local(ctx, host_bases, off, goc, nloc, self.sp, self.mp, name_ranks=ranks_local)
+        else:                           # sequences already resident on the device
             local = H.sketch_contigs(ctx, None, off, goc, nloc, self.sp, device_ptr=dev_ptr)
+            if ranks_local is not None:
+                local.set_name_ranks(ranks_local)
+            lp = H.screen_triangle(ctx, local, self.mp)
+            res_local = H.chain_pairs(ctx, local, local, lp, self.mp, as_array=True)
+            res_local = res_local[res_local["ani"] > 0.1]               # src/triangle.rs:99
+        res_local["ref_id"] += np.uint32(g0)
+        res_local["query_id"] += np.uint32(g0)
         t1 = time.perf_counter()
         # genome blocks of all ranks
         blk = torch.tensor([g0, nloc], dtype=torch.int64, device=self.device)
@@ -217,10 +241,10 @@ class DistTriangle:
         allblk = allblk.cpu().numpy().reshape(self.world, 2)
         bounds = np.concatenate([allblk[:, 0], [allblk[-1, 0] + allblk[-1, 1]]])
         assert bounds[0] == 0 and bounds[-1] == n_total and np.all(np.diff(bounds) == allblk[:, 1]), "ranks must hold consecutive blocks"
-        # markers everywhere -> every rank screens the whole triangle
+        # markers everywhere -> every rank screens the whole triangle; pairs inside a block are already done
         mk = self.exchange(local, PACK_MARKERS_ONLY)
         assert len(mk) == n_total
-        pairs = H.screen_triangle(ctx, mk, self.mp)
+        pairs = cross_block_pairs(H.screen_triangle(ctx, mk, self.mp), bounds)
         mk.free()
         t2 = time.perf_counter()
         need, send, recv_counts = fetch_plan(pairs, self.world, self.rank, bounds)
@@ -228,16 +252,20 @@ class DistTriangle:
         work, remote_bytes = self.fetch(local, send, recv_counts)
         local.free()
         assert len(work) == len(need)
-        work.set_name_ranks(need.astype(np.uint64) if self.name_ranks is None else self.name_ranks[need])
         t3 = time.perf_counter()
-        res = H.chain_pairs(ctx, work, work, remap_pairs(mine, need), self.mp, as_array=True)
+        if len(mine):
+            work.set_name_ranks(need.astype(np.uint64) if self.name_ranks is None else self.name_ranks[need])
+            res = H.chain_pairs(ctx, work, work, remap_pairs(mine, need), self.mp, as_array=True)
+            res["ref_id"] = need[res["ref_id"]]
+            res["query_id"] = need[res["query_id"]]
+            res = np.concatenate([res_local, res[res["ani"] > 0.1]])
+        else:
+            res = res_local
         work.free()
-        res["ref_id"] = need[res["ref_id"]]
-        res["query_id"] = need[res["query_id"]]
         if trace:
-            print("[multi_gpu rank0] sketch %.1f ms  markers+screen %.1f ms  fetch %.1f ms (%d genomes, %.1f MB remote)  "
-                  "chain %.1f ms (%d pairs)" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, len(need), remote_bytes / 1e6,
-                                                (time.perf_counter() - t3) * 1e3, len(mine)), flush=True)
-        self.last_results = res[res["ani"] > 0.1]               # src/triangle.rs:99 (numpy structured array)
+            print("[multi_gpu rank0] block triangle %.1f ms (%d pairs kept)  markers+screen %.1f ms  fetch %.1f ms (%d genomes, %.1f MB remote)  "
+                  "chain %.1f ms (%d cross-block pairs)" % ((t1 - t0) * 1e3, len(res_local), (t2 - t1) * 1e3, (t3 - t2) * 1e3, len(need),
+                                                            remote_bytes / 1e6, (time.perf_counter() - t3) * 1e3, len(mine)), flush=True)
+        self.last_results = res
         self.last_need = need
         return len(self.last_results)

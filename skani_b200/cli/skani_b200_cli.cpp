@@ -177,6 +177,13 @@ sk_sketch_set* sketch(sk_ctx* ctx, const Inputs& in, const sk_sketch_params& sp)
   return set;
 }
 
+// INTERMEDIATE_WRITE_COUNT (src/params.rs:9): results are appended to the output every this many processed rows / queries
+// (src/triangle.rs:113-138, src/dist.rs:151-175, src/search.rs:255-279).  SK_INTERMEDIATE_WRITE_COUNT overrides it (tests).
+size_t intermediate_write_count() {
+  if (const char* e = getenv("SK_INTERMEDIATE_WRITE_COUNT")) return (size_t)std::max(1ll, atoll(e));
+  return 5000;
+}
+
 void resolve_presets(Opts& op) {   // src/parse.rs:829-853 / 680-710
   if (op.fast && op.slow) { fprintf(stderr, "ERROR Both --slow and --fast were set. This is not allowed.\n"); exit(1); }
   if (op.fast) op.c = 200;
@@ -309,6 +316,31 @@ int run_triangle(Opts& op) {
     sk_sketch_set_set_name_ranks(set, ranks.data());
     uint64_t* pairs = nullptr; uint64_t np = 0;
     CK(ctx, sk_screen_triangle(ctx, set, &mp, &pairs, &np));
+    if (op.sparse) {
+      // sparse output: rows are chained and APPENDED in blocks of INTERMEDIATE_WRITE_COUNT rows (src/triangle.rs:113-138),
+      // so a long run leaves its finished rows on disk and holds at most one block of results in memory
+      FILE* o = op.out.empty() ? stdout : fopen(op.out.c_str(), "w");
+      if (!o) { fprintf(stderr, "ERROR cannot open %s\n", op.out.c_str()); return 1; }
+      write_header(o, op.ci, op.detailed);
+      if (op.diagonal) for (auto& g : in.genomes) write_perfect(o, g, op);
+      const size_t FL = intermediate_write_count(), Nrows = in.genomes.size();
+      uint64_t p0 = 0;
+      for (size_t r0 = 0; r0 < Nrows; r0 += FL) {
+        uint64_t p1 = p0;
+        while (p1 < np && (uint32_t)(pairs[p1] >> 32) < r0 + FL) p1++;      // pairs are sorted by (i, j)
+        res.resize(p1 - p0);
+        CK(ctx, sk_chain_pairs(ctx, set, set, pairs + p0, p1 - p0, &mp, res.data()));
+        for (auto& r : res) if (r.ani > 0.1f) write_row(o, r, in.genomes[r.ref_id], in.genomes[r.query_id], op);
+        fflush(o);
+        if (r0 + FL < Nrows) fprintf(stderr, "INFO Writing results for %zu query sequences.\n", FL);
+        p0 = p1;
+      }
+      sk_free(pairs);
+      if (o != stdout) fclose(o);
+      sk_sketch_set_free(set);
+      sk_ctx_destroy(ctx);
+      return 0;
+    }
     res.resize(np);
     CK(ctx, sk_chain_pairs(ctx, set, set, pairs, np, &mp, res.data()));
     sk_free(pairs);
@@ -420,19 +452,32 @@ int run_dist(Opts& op) {
   }
   uint64_t* pairs = nullptr; uint64_t np = 0;
   CK(ctx, sk_screen_query_ref(ctx, rset, qset, &mp, use_index ? 2 : 0, &pairs, &np));
-  std::vector<sk_ani_result> res(np);
-  CK(ctx, sk_chain_pairs(ctx, rset, qset, pairs, np, &mp, res.data()));
+  // queries are processed, and their results appended, in blocks of INTERMEDIATE_WRITE_COUNT (src/dist.rs:151-175)
+  std::vector<uint64_t> byq(pairs, pairs + np);
   sk_free(pairs);
-  // write_query_ref_list (src/file_io.rs:608-678): group by the query's first contig name, sort each group by ANI desc, top n
-  std::map<std::string, std::vector<const sk_ani_result*>> groups;
-  for (auto& r : res) if (r.ani > 0.1f) groups[qin.genomes[r.query_id].contigs[0]].push_back(&r);
+  std::sort(byq.begin(), byq.end(), [](uint64_t a, uint64_t b) { return (uint32_t)a != (uint32_t)b ? (uint32_t)a < (uint32_t)b : a < b; });
   FILE* o = op.out.empty() ? stdout : fopen(op.out.c_str(), "w");
   if (!o) { fprintf(stderr, "ERROR cannot open %s\n", op.out.c_str()); return 1; }
   write_header(o, op.ci, op.detailed);
-  for (auto& kv : groups) {
-    auto v = kv.second;
-    std::stable_sort(v.begin(), v.end(), [](const sk_ani_result* a, const sk_ani_result* b) { return a->ani > b->ani; });
-    for (size_t i = 0; i < v.size() && i < op.n; i++) write_row(o, *v[i], rin.genomes[v[i]->ref_id], qin.genomes[v[i]->query_id], op);
+  const size_t FL = intermediate_write_count(), NQ = qin.genomes.size();
+  size_t p0 = 0;
+  std::vector<sk_ani_result> res;
+  for (size_t q0 = 0; q0 < NQ; q0 += FL) {
+    size_t p1 = p0;
+    while (p1 < byq.size() && (uint32_t)byq[p1] < q0 + FL) p1++;
+    res.resize(p1 - p0);
+    CK(ctx, sk_chain_pairs(ctx, rset, qset, byq.data() + p0, p1 - p0, &mp, res.data()));
+    // write_query_ref_list (src/file_io.rs:608-678): group by the query's first contig name, sort each group by ANI desc, top n
+    std::map<std::string, std::vector<const sk_ani_result*>> groups;
+    for (auto& r : res) if (r.ani > 0.1f) groups[qin.genomes[r.query_id].contigs[0]].push_back(&r);
+    for (auto& kv : groups) {
+      auto v = kv.second;
+      std::stable_sort(v.begin(), v.end(), [](const sk_ani_result* a, const sk_ani_result* b) { return a->ani > b->ani; });
+      for (size_t i = 0; i < v.size() && i < op.n; i++) write_row(o, *v[i], rin.genomes[v[i]->ref_id], qin.genomes[v[i]->query_id], op);
+    }
+    fflush(o);
+    if (q0 + FL < NQ) fprintf(stderr, "INFO Writing results for %zu query sequences.\n", FL);
+    p0 = p1;
   }
   if (o != stdout) fclose(o);
   sk_sketch_set_free(rset); sk_sketch_set_free(qset);
@@ -613,7 +658,20 @@ int run_search(Opts& op) {
     }
     sk_sketch_set_set_name_ranks(qset, qrank.data());
   }
-  // ---- references that passed for at least one query: load each ONCE, import in batches, chain their pairs
+  // ---- queries are processed, and their results appended, in blocks of INTERMEDIATE_WRITE_COUNT (src/search.rs:255-279).
+  //      Inside a block: the references that passed for at least one of its queries are loaded ONCE each, imported in
+  //      batches, and their pairs chained (the reference deserialises a sketch per passing PAIR, src/search.rs:142-166)
+  FILE* o = op.out.empty() ? stdout : fopen(op.out.c_str(), "w");
+  if (!o) { fprintf(stderr, "ERROR cannot open %s\n", op.out.c_str()); return 1; }
+  write_header(o, op.ci, op.detailed);
+  std::vector<uint64_t> all_pairs(pairs, pairs + np);
+  sk_free(pairs);
+  const size_t FL = intermediate_write_count(), NQ = qmeta.size();
+  for (size_t q0 = 0; q0 < NQ; q0 += FL) {
+  std::vector<uint64_t> blockp;
+  for (uint64_t x : all_pairs) if ((uint32_t)x >= q0 && (uint32_t)x < q0 + FL) blockp.push_back(x);   // stays sorted by (ref, query)
+  const uint64_t* pairs = blockp.data();
+  const uint64_t np = blockp.size();
   std::vector<uint32_t> hits;
   for (uint64_t i = 0; i < np; i++) hits.push_back((uint32_t)(pairs[i] >> 32));   // pairs are sorted by (ref, query)
   hits.erase(std::unique(hits.begin(), hits.end()), hits.end());
@@ -675,14 +733,9 @@ int run_search(Opts& op) {
     sk_sketch_set_free(rset);
     h0 = h1;
   }
-  sk_free(pairs);
-  if (db_fd >= 0) close(db_fd);
   // write_query_ref_list (src/file_io.rs:608-678): group by the query's first contig name, ANI descending, top n
   std::map<std::string, std::vector<const sk_ani_result*>> groups;
   for (auto& r : kept) groups[qmeta[r.query_id].contigs[0]].push_back(&r);
-  FILE* o = op.out.empty() ? stdout : fopen(op.out.c_str(), "w");
-  if (!o) { fprintf(stderr, "ERROR cannot open %s\n", op.out.c_str()); return 1; }
-  write_header(o, op.ci, op.detailed);
   for (auto& kv : groups) {
     auto v = kv.second;
     std::stable_sort(v.begin(), v.end(), [](const sk_ani_result* a, const sk_ani_result* b) { return a->ani > b->ani; });
@@ -692,6 +745,10 @@ int run_search(Opts& op) {
       write_row(o, *v[i], ref, qmeta[v[i]->query_id], op);
     }
   }
+  fflush(o);
+  if (q0 + FL < NQ) fprintf(stderr, "INFO Writing results for %zu query sequences.\n", FL);
+  }
+  if (db_fd >= 0) close(db_fd);
   if (o != stdout) fclose(o);
   sk_sketch_set_free(qset);
   sk_ctx_destroy(ctx);

@@ -981,6 +981,77 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
   return SK_OK;
 }
 
+namespace {
+template <typename T>
+int grow_append(sk_ctx* ctx, T** arr, size_t* cap, size_t used_alloc, size_t used, const T* src, size_t add) {
+  // *cap == 0: the array was allocated at exactly `used_alloc` elements
+  const size_t have = *cap ? *cap : std::max<size_t>(used_alloc, 1);
+  if (used + add > have) {
+    const size_t ncap = std::max<size_t>(used + add, have + have / 2);
+    T* n = nullptr;
+    SK_CUDA(ctx->arena.alloc((void**)&n, ncap * sizeof(T)));
+    if (used) SK_CUDA(cudaMemcpyAsync(n, *arr, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    SK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*arr) ctx->arena.release(*arr);
+    *arr = n; *cap = ncap;
+  }
+  if (add) SK_CUDA(cudaMemcpyAsync(*arr + used, src, add * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+  return SK_OK;
+}
+}  // namespace
+
+int append_sets_inplace(sk_ctx* ctx, sk_sketch_set** dstp, const std::vector<sk_sketch_set*>& parts, const SetReserve& hint) {
+  if (parts.empty()) return SK_OK;
+  sk_sketch_set* d = *dstp;
+  if (!d) {   // first wave: an empty set with room for everything that is expected (estimates; arrays grow if they fall short)
+    d = new sk_sketch_set();
+    d->ctx = ctx; d->sp = parts[0]->sp;
+    d->seed_off = {0}; d->uk_off = {0}; d->mk_off = {0}; d->ctg_off = {0}; d->ht_off = {0};
+    const uint64_t S = (uint64_t)((double)hint.bases / d->sp.c * 1.06) + 64 * hint.genomes + 1024;
+    const uint64_t M = (uint64_t)((double)hint.bases / d->sp.marker_c * 1.10) + 16 * hint.genomes + 1024;
+    d->capS = S; d->capU = S; d->capUG = S + hint.genomes + 1; d->capM = M; d->capC = hint.contigs + 1; d->capCG = hint.contigs + hint.genomes + 1;
+    d->capHT = 4 * S + 16 * hint.genomes;   // table capacity = power of two >= 2 x distinct k-mers: between 2 and 4 entries per k-mer
+    struct G0 { sk_sketch_set* s; ~G0() { if (s) { free_set_device(s); delete s; } } } g0{d};
+    SK_CUDA(ctx->arena.alloc((void**)&d->pv_kmer, d->capS * 4)); SK_CUDA(ctx->arena.alloc((void**)&d->pv_pos, d->capS * 4));
+    SK_CUDA(ctx->arena.alloc((void**)&d->pv_cc, d->capS * 4));   SK_CUDA(ctx->arena.alloc((void**)&d->pv_mult, d->capS * 2));
+    SK_CUDA(ctx->arena.alloc((void**)&d->kv_pos, d->capS * 4));  SK_CUDA(ctx->arena.alloc((void**)&d->kv_cc, d->capS * 4));
+    SK_CUDA(ctx->arena.alloc((void**)&d->ukmer, d->capU * 4));   SK_CUDA(ctx->arena.alloc((void**)&d->ustart, d->capUG * 4));
+    SK_CUDA(ctx->arena.alloc((void**)&d->markers, d->capM * 8)); SK_CUDA(ctx->arena.alloc((void**)&d->ctg_rec_off, d->capCG * 4));
+    SK_CUDA(ctx->arena.alloc((void**)&d->d_ctg_len, d->capC * 4)); SK_CUDA(ctx->arena.alloc((void**)&d->htab, d->capHT * 8));
+    g0.s = nullptr;
+    *dstp = d;
+  }
+  const uint32_t g_begin = d->G;
+  for (auto* p : parts) {
+    if (p->sp.c != d->sp.c || p->sp.k != d->sp.k || p->sp.marker_c != d->sp.marker_c) { ctx->err = "sketch parameter mismatch"; return SK_ERR_PARAM; }
+    size_t cS;   // the six record arrays share one capacity
+    cS = d->capS; SK_TRY(grow_append(ctx, &d->pv_kmer, &cS, d->S, d->S, p->pv_kmer, p->S));
+    cS = d->capS; SK_TRY(grow_append(ctx, &d->pv_pos, &cS, d->S, d->S, p->pv_pos, p->S));
+    cS = d->capS; SK_TRY(grow_append(ctx, &d->pv_cc, &cS, d->S, d->S, p->pv_cc, p->S));
+    cS = d->capS; SK_TRY(grow_append(ctx, &d->pv_mult, &cS, d->S, d->S, p->pv_mult, p->S));
+    cS = d->capS; SK_TRY(grow_append(ctx, &d->kv_pos, &cS, d->S, d->S, p->kv_pos, p->S));
+    cS = d->capS; SK_TRY(grow_append(ctx, &d->kv_cc, &cS, d->S, d->S, p->kv_cc, p->S));
+    d->capS = cS;
+    SK_TRY(grow_append(ctx, &d->ukmer, &d->capU, d->U, d->U, p->ukmer, p->U));
+    SK_TRY(grow_append(ctx, &d->ustart, &d->capUG, d->U + d->G, d->U + d->G, p->ustart, p->U + p->G));
+    SK_TRY(grow_append(ctx, &d->markers, &d->capM, d->M, d->M, p->markers, p->M));
+    SK_TRY(grow_append(ctx, &d->ctg_rec_off, &d->capCG, d->C + d->G, d->C + d->G, p->ctg_rec_off, p->C + p->G));
+    SK_TRY(grow_append(ctx, &d->d_ctg_len, &d->capC, d->C, d->C, p->d_ctg_len, p->C));
+    for (uint32_t g = 0; g < p->G; g++) {
+      d->seed_off.push_back(d->seed_off.back() + (p->seed_off[g + 1] - p->seed_off[g]));
+      d->uk_off.push_back(d->uk_off.back() + (p->uk_off[g + 1] - p->uk_off[g]));
+      d->mk_off.push_back(d->mk_off.back() + (p->mk_off[g + 1] - p->mk_off[g]));
+      d->ctg_off.push_back(d->ctg_off.back() + (p->ctg_off[g + 1] - p->ctg_off[g]));
+      d->total_len.push_back(p->total_len[g]);
+      d->name_rank.push_back(d->G + g);
+    }
+    d->ctg_len.insert(d->ctg_len.end(), p->ctg_len.begin(), p->ctg_len.end());
+    d->G += p->G; d->S += p->S; d->U += p->U; d->M += p->M; d->C += p->C;
+  }
+  SK_CUDA(cudaStreamSynchronize(ctx->stream));   // the parts may be released by the caller now
+  return build_hash_range(ctx, d, g_begin);
+}
+
 // concatenate `parts` after `base` (may be null) into a fresh set owned by ctx, with hash tables; inputs stay valid
 int merge_sets(sk_ctx* ctx, const sk_sketch_set* base, const std::vector<sk_sketch_set*>& parts, sk_sketch_set** out) {
   std::vector<const sk_sketch_set*> v;

@@ -273,8 +273,8 @@ void free_set_device(sk_sketch_set* s) {
 // so a probe costs ~1.2 divergent sector reads instead of a search + two ustart reads
 __global__ void hash_build_kernel(const uint64_t* __restrict__ uk_off, const uint64_t* __restrict__ ht_off,
                                   const uint32_t* __restrict__ ukmer, const uint32_t* __restrict__ ustart,
-                                  unsigned long long* __restrict__ htab) {
-  const uint32_t g = blockIdx.x;
+                                  unsigned long long* __restrict__ htab, uint32_t g_base) {
+  const uint32_t g = g_base + blockIdx.x;
   const uint64_t cap = ht_off[g + 1] - ht_off[g];
   if (cap == 0) return;
   const uint32_t mask = (uint32_t)cap - 1;
@@ -325,7 +325,47 @@ int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
   SK_CUDA(d_uk.alloc(G + 1, ctx)); SK_CUDA(d_ht.alloc(G + 1, ctx));
   SK_CUDA(h2d_small(ctx, d_uk.p, set->uk_off.data(), (G + 1) * 8));
   SK_CUDA(h2d_small(ctx, d_ht.p, set->ht_off.data(), (G + 1) * 8));
-  hash_build_kernel<<<dim3(G, 8), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab); count_launch(ctx);
+  hash_build_kernel<<<dim3(G, 8), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab, 0); count_launch(ctx);
+  SK_CUDA(cudaStreamSynchronize(st));
+  return SK_OK;
+}
+
+// Tables of the genomes [g_begin, G) of a set whose earlier genomes already have theirs (in-place growth): the new
+// tables are appended to set->htab (grown if its capacity is exceeded).  Falls back to the full rebuild when a new genome
+// is too large for a table (needs the bucket index).
+int build_hash_range(sk_ctx* ctx, sk_sketch_set* set, uint32_t g_begin) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t G = set->G;
+  if (set->ht_off.size() != (size_t)g_begin + 1 || set->ubucket || getenv("SK_FORCE_BUCKET_PROBE")) { set->capHT = 0; return build_hash(ctx, set); }
+  std::vector<uint64_t> ht(set->ht_off);
+  for (uint32_t g = g_begin; g < G; g++) {
+    const uint64_t nuk = set->uk_off[g + 1] - set->uk_off[g], nrec = set->seed_off[g + 1] - set->seed_off[g];
+    uint64_t cap = 0;
+    if (nuk > 0) {
+      if (nrec >= (1ull << 20)) { set->capHT = 0; return build_hash(ctx, set); }
+      cap = 16; while (cap < 2 * nuk) cap <<= 1;
+    }
+    ht.push_back(ht.back() + cap);
+  }
+  const uint64_t old_total = ht[g_begin], total = ht[G];
+  const size_t have = set->capHT ? set->capHT : std::max<uint64_t>(old_total, 1);
+  if (total > have) {
+    const size_t ncap = std::max<size_t>(total, have + have / 2);
+    unsigned long long* nt = nullptr;
+    SK_CUDA(ctx->arena.alloc((void**)&nt, ncap * 8));
+    if (old_total) SK_CUDA(cudaMemcpyAsync(nt, set->htab, old_total * 8, cudaMemcpyDeviceToDevice, st));
+    SK_CUDA(cudaStreamSynchronize(st));
+    ctx->arena.release(set->htab);
+    set->htab = nt; set->capHT = ncap;
+  }
+  set->ht_off = ht;
+  if (total == old_total) return SK_OK;
+  SK_CUDA(cudaMemsetAsync(set->htab + old_total, 0, (total - old_total) * 8, st));
+  DTmp<uint64_t> d_uk, d_ht;
+  SK_CUDA(d_uk.alloc(G + 1, ctx)); SK_CUDA(d_ht.alloc(G + 1, ctx));
+  SK_CUDA(h2d_small(ctx, d_uk.p, set->uk_off.data(), (G + 1) * 8));
+  SK_CUDA(h2d_small(ctx, d_ht.p, set->ht_off.data(), (G + 1) * 8));
+  hash_build_kernel<<<dim3(G - g_begin, 8), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab, g_begin); count_launch(ctx);
   SK_CUDA(cudaStreamSynchronize(st));
   return SK_OK;
 }

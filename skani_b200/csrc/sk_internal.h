@@ -126,6 +126,8 @@ struct sk_sketch_set {
   uint32_t* d_ctg_len = nullptr;                                      // [C]
   unsigned long long* htab = nullptr;                                 // [ht_off[G]] per-genome open-addressing table: kmer<<32 | start<<12 | min(count,4095); 0 = empty
   std::vector<uint64_t> ht_off;                                       // [G+1] table offsets (capacity = power of two, >= 2 * distinct k-mers); capacity 0 => use ubucket search
+  // element capacities of the device arrays when the set grows in place (append_sets_inplace); 0 = allocated at exact size
+  size_t capS = 0, capU = 0, capUG = 0, capM = 0, capC = 0, capCG = 0, capHT = 0;
   uint32_t* ubucket = nullptr;                                        // [G * (UBUCKETS + 1)] first ukmer index of each top-bits bucket, per genome
 };
 
@@ -195,6 +197,11 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
                       uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out,
                       const std::function<int(sk_sketch_set*, uint32_t, uint32_t)>* on_part, size_t subbatch_override);
 SkPool* ctx_pool(sk_ctx* ctx);
+// grows `*dst` (created on first use, with capacities reserved for the expected totals) by the genomes of `parts` IN PLACE:
+// only the new genomes' arrays are copied and only their k-mer tables are built (the pipelined sk_triangle's merged set)
+struct SetReserve { uint64_t bases = 0, contigs = 0, genomes = 0; };
+int append_sets_inplace(sk_ctx* ctx, sk_sketch_set** dst, const std::vector<sk_sketch_set*>& parts, const SetReserve& hint);
+int build_hash_range(sk_ctx* ctx, sk_sketch_set* set, uint32_t g_begin);   // tables of the genomes [g_begin, G) appended to set->htab
 int merge_sets(sk_ctx* ctx, const sk_sketch_set* base, const std::vector<sk_sketch_set*>& parts, sk_sketch_set** out);  // (re)builds set->htab from ukmer/ustart; call on every finished set
 // screen.cu / chain.cu
 uint64_t count_launch(sk_ctx* ctx, uint64_t n = 1);

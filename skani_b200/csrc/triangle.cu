@@ -103,6 +103,8 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
     const bool trace = getenv("SK_TRACE") != nullptr;
     const double t00 = now_s();
     const uint32_t wave_genomes = std::max<uint32_t>(1, n_genomes / 8);
+    sk::SetReserve reserve;
+    reserve.bases = total_bytes; reserve.contigs = n_contigs; reserve.genomes = n_genomes;
     std::mutex mu;
     std::condition_variable cv;
     std::deque<Wave> q;
@@ -130,12 +132,10 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
         if (pending.empty() || (!done && pending_genomes < wave_genomes)) continue;
         if (worker_rc == SK_OK) {
           const double ta = now_s();
-          sk_sketch_set* next = nullptr;
-          int rc = sk::merge_sets(wctx, merged, pending, &next);
+          // the merged set grows in place: only the new genomes are copied and only their k-mer tables are built
+          int rc = sk::append_sets_inplace(wctx, &merged, pending, reserve);
           double tb = now_s(), tc = tb, td = tb;
           if (rc == SK_OK) {
-            if (merged) sk_sketch_set_free(merged);
-            merged = next;
             if (name_ranks) {   // file-name order of the caller (switch_qr tie-break); the merged set covers genomes [0, merged->G)
               for (uint32_t g = 0; g < merged->G; g++) merged->name_rank[g] = name_ranks[g];
               merged->ranks_user_set = true;

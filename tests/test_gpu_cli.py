@@ -62,3 +62,31 @@ def test_degenerate_inputs(tmp_path):
     bad.write_text("this is not fasta\n")
     p = subprocess.run([BIN, "triangle", str(bad), str(tmp_path / "missing.fa")], capture_output=True, text=True)
     assert p.returncode == 1 and "WARN" in p.stderr and "ERROR" in p.stderr   # tests/int_test_new.rs:135-163
+
+
+def _rowset(out):
+    return sorted(ln for ln in out.strip().split("\n")[1:])
+
+
+def test_intermediate_flushes_and_multi_gpu_flag(tmp_path):
+    """Results are appended in blocks of INTERMEDIATE_WRITE_COUNT rows / queries (src/params.rs:9, src/triangle.rs:113-138,
+    src/dist.rs:151-175): with a tiny block size the row SET is unchanged and the flush is announced.  `triangle --gpus N`
+    (sk_triangle_multi; contexts share the device on a 1-GPU box) prints the same rows."""
+    reads = os.path.join(GOLD, "o157_reads.fa.gz")
+    vir = os.path.join(GOLD, "viruses.fna")
+    base, _ = run(["triangle", "-i", "-E", reads], cwd=str(tmp_path))
+    env = dict(os.environ, SK_INTERMEDIATE_WRITE_COUNT="37")
+    p = subprocess.run([BIN, "triangle", "-i", "-E", reads], capture_output=True, text=True, cwd=str(tmp_path), timeout=600, env=env)
+    assert p.returncode == 0, p.stderr
+    assert _rowset(p.stdout) == _rowset(base) and len(_rowset(base)) == 270          # test_results_versions/0.3.0:60 (G10)
+    assert "INFO Writing results for 37 query sequences." in p.stderr
+    multi, err = run(["triangle", "-i", "-E", "--gpus", "3", reads], cwd=str(tmp_path))
+    assert _rowset(multi) == _rowset(base)
+    ec = os.path.join(GOLD, "e.coli-EC590.fasta.gz")
+    d0, _ = run(["dist", "-r", ec, "-q", reads, "--qi"])
+    p = subprocess.run([BIN, "dist", "-r", ec, "-q", reads, "--qi"], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0 and _rowset(p.stdout) == _rowset(d0) and len(_rowset(d0)) == 269
+    assert "INFO Writing results for 37 query sequences." in p.stderr
+    v0, _ = run(["triangle", "-E", "--gpus", "2", vir, ec, os.path.join(GOLD, "e.coli-K12.fasta.gz")], cwd=str(tmp_path))
+    v1, _ = run(["triangle", "-E", vir, ec, os.path.join(GOLD, "e.coli-K12.fasta.gz")], cwd=str(tmp_path))
+    assert _rowset(v0) == _rowset(v1) and len(_rowset(v1)) == 1

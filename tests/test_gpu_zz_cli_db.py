@@ -94,6 +94,10 @@ def test_sketch_then_search(tmp_path):
     want_i = sorted((osk[r.ref_id].file_name, qi[r.query_id].file_name, f2(r.ani), f2(r.af_ref), f2(r.af_query),
                      osk[r.ref_id].contig_name(0), qi[r.query_id].contig_name(0)) for r in exp_i)
     assert rows_of(run(["search", "-d", db, FILES[1], "--qi"])) == want_i
+    # results appended in query blocks (INTERMEDIATE_WRITE_COUNT, src/search.rs:255-279): same rows with a block size of 1
+    env = dict(os.environ, SK_INTERMEDIATE_WRITE_COUNT="1")
+    p = subprocess.run([BIN, "search", "-d", db, FILES[1], "--qi"], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0 and rows_of(p.stdout) == want_i and "INFO Writing results for 1 query sequences." in p.stderr
 
 
 def test_sketch_files_as_dist_and_triangle_inputs(tmp_path):

@@ -65,5 +65,37 @@ def full(src, dst, title):
     print("wrote", dst)
 
 
+def traffic(src, dst, bases_per_launch, source_note):
+    """profiles/r02_traffic.json for bench.py's roofline.traffic / roofline.alu: DRAM bytes per base, issue-active and thread
+    instructions per window of the FIRST captured launch of each seeding kernel (bases_per_launch = bases one launch processes)."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader([ln for ln in out.splitlines() if ln.startswith('"')]))
+    hdr = rows[0]
+    ix = {h: i for i, h in enumerate(hdr)}
+    units = rows[1]
+
+    def num(r, k):
+        v = float(r[ix[k]].replace(",", ""))
+        u = units[ix[k]]
+        return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
+    res = {}
+    for r in rows[2:]:
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("sk::", "")
+        if name in res or name not in ("hashpass_kernel", "pack_kernel", "expand_kernel"):
+            continue
+        b = float(bases_per_launch)
+        d = {"dram_bytes_per_base": (num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")) / b,
+             "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+             "inst_per_window": num(r, "smsp__inst_executed.sum") * num(r, "smsp__thread_inst_executed_per_inst_executed.ratio") / b,
+             "bases_per_launch": b, "source": source_note}
+        res[name] = d
+    json.dump(res, open(dst, "w"), indent=1)
+    print("wrote", dst, res)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4])

@@ -3,70 +3,204 @@
 // first byte ('>' FASTA, '@' FASTQ), transparent gzip (zlib; multi-member streams), FASTA sequences with line breaks
 // ("\n" / "\r\n") removed, id = the whole header line without the leading symbol, 4-line FASTQ records; an empty or
 // non-FASTX file is an error (the caller warns and skips it, src/file_io.rs:159-166).
+//
+// Ingestion speed: a file is read whole, inflated into one buffer and split into lines with
+// memchr (no per-byte state machine).  Block-gzipped files (BGZF: bgzip / htslib, every member carries its compressed
+// size in a 'BC' extra field) are inflated member-parallel with `inflate_threads` threads; ordinary single-member gzip has
+// no block index and is inflated by one zlib stream (the caller runs files in parallel).
 #pragma once
 #include <zlib.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace fastx {
 
 struct Record { std::string id; std::string seq; };
 
-// ---- FASTA / FASTQ reader (streaming over zlib; plain files pass through gzread unchanged) -----------------
-inline bool read_fastx(const std::string& path, std::vector<Record>& out) {
-  gzFile f = gzopen(path.c_str(), "rb");
-  if (!f) return false;
-  gzbuffer(f, 1 << 20);
-  std::vector<char> buf(1 << 22);
-  std::string line, pending;
+// read-only view of a whole file (mmap; empty files map to a null view)
+struct FileView {
+  const unsigned char* p = nullptr;
+  size_t n = 0;
+  bool ok = false;
+  explicit FileView(const std::string& path) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); return; }
+    n = (size_t)st.st_size;
+    ok = true;
+    if (n) {
+      void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) { ok = false; n = 0; }
+      else { p = (const unsigned char*)m; madvise(m, n, MADV_SEQUENTIAL); }
+    }
+    close(fd);
+  }
+  ~FileView() { if (p) munmap((void*)p, n); }
+  FileView(const FileView&) = delete;
+  FileView& operator=(const FileView&) = delete;
+};
+
+// BGZF member at `p` (n bytes available)?  returns the member's total compressed size (BSIZE + 1), or 0
+inline size_t bgzf_member_size(const unsigned char* p, size_t n) {
+  if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+  const size_t xlen = p[10] | (p[11] << 8);
+  if (12 + xlen > n) return 0;
+  for (size_t o = 12; o + 4 <= 12 + xlen;) {
+    const size_t slen = p[o + 2] | (p[o + 3] << 8);
+    if (p[o] == 'B' && p[o + 1] == 'C' && slen == 2 && o + 6 <= 12 + xlen) return (size_t)(p[o + 4] | (p[o + 5] << 8)) + 1;
+    o += 4 + slen;
+  }
+  return 0;
+}
+
+// gzip bytes -> decompressed text: multi-member streams via zlib; BGZF member-parallel.
+struct RawSpan { const unsigned char* p; size_t n; const unsigned char* data() const { return p; } size_t size() const { return n; } const unsigned char& operator[](size_t i) const { return p[i]; } };
+inline bool inflate_gzip(const RawSpan raw, std::string& out, int inflate_threads = 1) {
+  out.clear();
+  // ---- BGZF: every member announces its size, so the members can be located without inflating and inflated in parallel
+  if (bgzf_member_size(raw.data(), raw.size())) {
+    struct Mem { size_t off, csize, isize, out_off; };
+    std::vector<Mem> mem;
+    size_t o = 0, total = 0;
+    bool all = true;
+    while (o < raw.size()) {
+      const size_t cs = bgzf_member_size(raw.data() + o, raw.size() - o);
+      if (!cs || o + cs > raw.size() || cs < 26) { all = false; break; }
+      const unsigned char* t = raw.data() + o + cs - 4;
+      const size_t isz = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+      mem.push_back(Mem{o, cs, isz, total});
+      total += isz;
+      o += cs;
+    }
+    if (all && !mem.empty()) {
+      out.resize(total);
+      std::atomic<size_t> next{0};
+      std::atomic<bool> ok{true};
+      auto work = [&] {
+        for (size_t i; (i = next.fetch_add(1)) < mem.size();) {
+          const Mem& m = mem[i];
+          if (m.isize == 0) continue;
+          const unsigned char* p = raw.data() + m.off;
+          const size_t xlen = p[10] | (p[11] << 8), hdr = 12 + xlen;
+          z_stream zs;
+          memset(&zs, 0, sizeof(zs));
+          if (inflateInit2(&zs, -15) != Z_OK) { ok = false; continue; }
+          zs.next_in = (Bytef*)(p + hdr); zs.avail_in = (uInt)(m.csize - hdr - 8);
+          zs.next_out = (Bytef*)&out[m.out_off]; zs.avail_out = (uInt)m.isize;
+          const int rc = inflate(&zs, Z_FINISH);
+          if (rc != Z_STREAM_END || zs.avail_out != 0) ok = false;
+          inflateEnd(&zs);
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < inflate_threads && (size_t)t < mem.size(); t++) th.emplace_back(work);
+      work();
+      for (auto& t : th) t.join();
+      return ok.load();
+    }
+  }
+  // ---- ordinary gzip (possibly several members back to back: flate2 MultiGzDecoder semantics)
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, 15 + 16) != Z_OK) return false;
+  zs.next_in = (Bytef*)raw.data(); zs.avail_in = (uInt)std::min<size_t>(raw.size(), 1u << 30);
+  size_t consumed = 0;
+  out.resize(std::max<size_t>(raw.size() * 4, 1 << 16));
+  size_t produced = 0;
+  bool ok = true;
+  for (;;) {
+    if (produced == out.size()) out.resize(out.size() * 2);
+    zs.next_out = (Bytef*)&out[produced];
+    zs.avail_out = (uInt)std::min<size_t>(out.size() - produced, 1u << 30);
+    const uInt in0 = zs.avail_in, out0 = zs.avail_out;
+    const int rc = inflate(&zs, Z_NO_FLUSH);
+    consumed += in0 - zs.avail_in;
+    produced += out0 - zs.avail_out;
+    if (zs.avail_in == 0 && consumed < raw.size()) { zs.next_in = (Bytef*)raw.data() + consumed; zs.avail_in = (uInt)std::min<size_t>(raw.size() - consumed, 1u << 30); }
+    if (rc == Z_STREAM_END) {
+      if (consumed >= raw.size()) break;
+      // another member?  (trailing garbage that is not a gzip header ends the stream, as zlib's gzread does)
+      if (raw.size() - consumed < 2 || raw[consumed] != 0x1f || raw[consumed + 1] != 0x8b) break;
+      if (inflateReset(&zs) != Z_OK) { ok = false; break; }
+      continue;
+    }
+    if (rc != Z_OK && rc != Z_BUF_ERROR) { ok = false; break; }
+    if (rc == Z_BUF_ERROR && zs.avail_in == 0 && consumed >= raw.size()) { ok = false; break; }   // truncated stream
+  }
+  inflateEnd(&zs);
+  out.resize(produced);
+  return ok;
+}
+
+// records of an in-memory FASTA / FASTQ text
+inline bool parse_fastx(const char* data, size_t n, std::vector<Record>& out) {
   enum { START, FA_SEQ, FQ_SEQ, FQ_PLUS, FQ_QUAL } st = START;
   bool ok = true, any = false;
   Record cur;
   size_t fq_len = 0;
-  auto flush_line = [&](std::string& ln) {
-    if (!ln.empty() && ln.back() == '\r') ln.pop_back();
+  auto on_line = [&](const char* p, size_t len) {
+    if (len && p[len - 1] == '\r') len--;
     switch (st) {
       case START:
-        if (ln.empty()) { if (any) return; ok = false; return; }
-        if (ln[0] == '>') { cur = Record(); cur.id = ln.substr(1); st = FA_SEQ; any = true; }
-        else if (ln[0] == '@') { cur = Record(); cur.id = ln.substr(1); st = FQ_SEQ; any = true; }
+        if (len == 0) { if (any) return; ok = false; return; }
+        if (p[0] == '>') { cur = Record(); cur.id.assign(p + 1, len - 1); st = FA_SEQ; any = true; }
+        else if (p[0] == '@') { cur = Record(); cur.id.assign(p + 1, len - 1); st = FQ_SEQ; any = true; }
         else ok = false;
         break;
       case FA_SEQ:
-        if (!ln.empty() && ln[0] == '>') { out.push_back(std::move(cur)); cur = Record(); cur.id = ln.substr(1); }
-        else cur.seq += ln;
+        if (len && p[0] == '>') { out.push_back(std::move(cur)); cur = Record(); cur.id.assign(p + 1, len - 1); }
+        else {
+          if (cur.seq.empty()) {   // reserve up to the next header once per record (one pass of memchr over the record)
+            const char* nx = p;
+            const char* end = data + n;
+            while ((nx = (const char*)memchr(nx, '>', end - nx)) != nullptr && nx[-1] != '\n') nx++;
+            cur.seq.reserve((size_t)((nx ? nx : end) - p));
+          }
+          cur.seq.append(p, len);
+        }
         break;
-      case FQ_SEQ: cur.seq = ln; fq_len = ln.size(); st = FQ_PLUS; break;
-      case FQ_PLUS: if (ln.empty() || ln[0] != '+') ok = false; st = FQ_QUAL; break;
+      case FQ_SEQ: cur.seq.assign(p, len); fq_len = len; st = FQ_PLUS; break;
+      case FQ_PLUS: if (len == 0 || p[0] != '+') ok = false; st = FQ_QUAL; break;
       case FQ_QUAL:
-        if (ln.size() != fq_len) ok = false;
+        if (len != fq_len) ok = false;
         out.push_back(std::move(cur)); cur = Record(); st = START;
         break;
     }
   };
-  while (ok) {
-    int got = gzread(f, buf.data(), (unsigned)buf.size());
-    if (got < 0) { ok = false; break; }
-    if (got == 0) break;
-    size_t b = 0;
-    for (int i = 0; i < got; i++) {
-      if (buf[i] == '\n') {
-        pending.append(buf.data() + b, i - b);
-        flush_line(pending);
-        pending.clear();
-        b = i + 1;
-        if (!ok) break;
-      }
-    }
-    if (ok) pending.append(buf.data() + b, got - b);
+  size_t b = 0;
+  while (ok && b < n) {
+    const char* nl = (const char*)memchr(data + b, '\n', n - b);
+    const size_t e = nl ? (size_t)(nl - data) : n;
+    on_line(data + b, e - b);
+    b = e + 1;
   }
-  gzclose(f);
-  if (ok && !pending.empty()) flush_line(pending);
   if (ok && st == FA_SEQ) out.push_back(std::move(cur));
   if (ok && (st == FQ_SEQ || st == FQ_PLUS || st == FQ_QUAL)) ok = false;
   if (!any) ok = false;  // empty file (needletail: EmptyFile error)
   return ok;
+}
+
+inline bool read_fastx(const std::string& path, std::vector<Record>& out, int inflate_threads = 1) {
+  FileView fv(path);
+  if (!fv.ok) return false;
+  if (fv.n >= 2 && fv.p[0] == 0x1f && fv.p[1] == 0x8b) {
+    std::string text;
+    if (!inflate_gzip(RawSpan{fv.p, fv.n}, text, inflate_threads)) return false;
+    return parse_fastx(text.data(), text.size(), out);
+  }
+  return parse_fastx((const char*)fv.p, fv.n, out);     // plain text: parsed straight from the mapping
 }
 
 }  // namespace fastx

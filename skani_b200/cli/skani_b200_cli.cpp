@@ -19,6 +19,8 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -57,13 +59,20 @@ void load_inputs(std::vector<std::string> files, bool individual, int threads, I
   std::sort(files.begin(), files.end());                      // final order = (file_name, contig_order)
   std::vector<std::vector<Record>> recs(files.size());
   std::vector<int> status(files.size(), 0);
-  std::vector<std::thread> pool;
-  std::vector<size_t> next(1, 0);
-  auto worker = [&](int tid) {
-    for (size_t i = tid; i < files.size(); i += threads) status[i] = read_fastx(files[i], recs[i]) ? 1 : -1;
-  };
-  for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
-  for (auto& t : pool) t.join();
+  threads = std::max(threads, 1);
+  {   // files in parallel (dynamic); threads left over when there are few files go to member-parallel BGZF inflate
+    std::atomic<size_t> next{0};
+    const int per_file = std::max<int>(1, threads / (int)std::max<size_t>(files.size(), 1));
+    auto worker = [&] { for (size_t i; (i = next.fetch_add(1)) < files.size();) status[i] = read_fastx(files[i], recs[i], per_file) ? 1 : -1; };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads && (size_t)t < files.size(); t++) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+  }
+  // record rules + layout (serial, metadata only), then one parallel copy of the sequences into the flat buffer
+  struct Copy { const std::string* seq; uint64_t off; };
+  std::vector<Copy> copies;
+  uint64_t total = in.bases.size();
   for (size_t i = 0; i < files.size(); i++) {
     if (status[i] < 0) { fprintf(stderr, "WARN %s is not a valid fasta/fastq file; skipping.\n", files[i].c_str()); continue; }
     size_t kept = 0;
@@ -72,8 +81,9 @@ void load_inputs(std::vector<std::string> files, bool individual, int threads, I
       for (auto& r : recs[i]) {
         if (r.seq.size() < 500) continue;                     // MIN_LENGTH_CONTIG (src/params.rs:42, src/file_io.rs:176)
         g.contigs.push_back(r.id); g.total_len += r.seq.size();
-        in.bases.insert(in.bases.end(), r.seq.begin(), r.seq.end());
-        in.contig_off.push_back(in.bases.size());
+        copies.push_back(Copy{&r.seq, total});
+        total += r.seq.size();
+        in.contig_off.push_back(total);
         in.genome_of_contig.push_back((uint32_t)in.genomes.size());
         kept++;
       }
@@ -87,13 +97,22 @@ void load_inputs(std::vector<std::string> files, bool individual, int threads, I
           continue;
         }
         Genome g; g.file_name = files[i]; g.contigs.push_back(r.id); g.total_len = r.seq.size(); g.contig_order = kept++;
-        in.bases.insert(in.bases.end(), r.seq.begin(), r.seq.end());
-        in.contig_off.push_back(in.bases.size());
+        copies.push_back(Copy{&r.seq, total});
+        total += r.seq.size();
+        in.contig_off.push_back(total);
         in.genome_of_contig.push_back((uint32_t)in.genomes.size());
         in.genomes.push_back(std::move(g));
       }
     }
-    recs[i].clear(); recs[i].shrink_to_fit();
+  }
+  in.bases.resize(total);
+  {
+    std::atomic<size_t> next{0};
+    auto worker = [&] { for (size_t i; (i = next.fetch_add(1)) < copies.size();) memcpy(in.bases.data() + copies[i].off, copies[i].seq->data(), copies[i].seq->size()); };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads && (size_t)t < copies.size(); t++) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
   }
 }
 
@@ -755,6 +774,22 @@ int run_search(Opts& op) {
   return 0;
 }
 
+// `skani-b200 ingest [-t T] files...`: parse the inputs exactly as triangle / dist / sketch do (no GPU work) and report the
+// ingestion rate -- the host-side bound of an end-to-end run on FASTA(.gz) files
+int run_ingest(Opts& op) {
+  if (op.files.empty()) { fprintf(stderr, "ERROR No inputs.\n"); return 1; }
+  uint64_t file_bytes = 0;
+  for (auto& f : op.files) { struct stat st; if (stat(f.c_str(), &st) == 0) file_bytes += (uint64_t)st.st_size; }
+  const auto t0 = std::chrono::steady_clock::now();
+  Inputs in;
+  load_inputs(op.files, op.individual, std::max(op.threads, 1), in);
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  printf("{\"files\": %zu, \"threads\": %d, \"file_bytes\": %llu, \"bases\": %zu, \"genomes\": %zu, \"seconds\": %.4f, "
+         "\"file_MB_per_s\": %.1f, \"bases_MB_per_s\": %.1f}\n", op.files.size(), std::max(op.threads, 1), (unsigned long long)file_bytes,
+         in.bases.size(), in.genomes.size(), dt, file_bytes / dt / 1e6, in.bases.size() / dt / 1e6);
+  return 0;
+}
+
 void usage() {
   fprintf(stderr,
           "skani-b200 (Blackwell implementation of skani v0.3.0's ANI hot path)\n"
@@ -772,7 +807,7 @@ int main(int argc, char** argv) {
   if (argc < 2) { usage(); return 2; }
   Opts op;
   op.cmd = argv[1];
-  if (op.cmd != "triangle" && op.cmd != "dist" && op.cmd != "sketch" && op.cmd != "search") { usage(); return 2; }
+  if (op.cmd != "triangle" && op.cmd != "dist" && op.cmd != "sketch" && op.cmd != "search" && op.cmd != "ingest") { usage(); return 2; }
   std::vector<std::string> positional;
   enum { NONE, QS, RS } multi = NONE;
   for (int i = 2; i < argc; i++) {
@@ -824,9 +859,9 @@ int main(int argc, char** argv) {
     else if (a == "-v" || a == "--debug" || a == "--trace") {}
     else { fprintf(stderr, "ERROR unknown option %s\n", a.c_str()); usage(); return 2; }
   }
-  if (op.cmd == "triangle" || op.cmd == "sketch") {
+  if (op.cmd == "triangle" || op.cmd == "sketch" || op.cmd == "ingest") {
     op.files.insert(op.files.end(), positional.begin(), positional.end());
-    return op.cmd == "triangle" ? run_triangle(op) : run_sketch(op);
+    return op.cmd == "triangle" ? run_triangle(op) : op.cmd == "sketch" ? run_sketch(op) : run_ingest(op);
   }
   if (op.cmd == "search") {
     op.queries.insert(op.queries.end(), positional.begin(), positional.end());

@@ -69,3 +69,39 @@ def test_edge_cases(tmp_path):
         p.write_bytes(data)
         assert tool(p) is None, name
     assert tool(tmp_path / "missing.fa") is None
+
+
+def bgzf_compress(data, block=65280):
+    """Block-gzip (BGZF, as bgzip / htslib write it): independent members with their compressed size in a 'BC' extra field."""
+    import struct
+    import zlib
+    out = bytearray()
+    chunks = [data[i:i + block] for i in range(0, len(data), block)] + [b""]   # empty EOF member
+    for ch in chunks:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        raw = co.compress(ch) + co.flush()
+        bsize = 12 + 6 + len(raw) + 8 - 1
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + raw
+        out += struct.pack("<II", zlib.crc32(ch) & 0xFFFFFFFF, len(ch))
+    return bytes(out)
+
+
+def test_bgzf_member_parallel_inflate(tmp_path):
+    """Block-gzipped FASTA (many members, records spanning member boundaries) reads like the plain file."""
+    import random
+    rnd = random.Random(5)
+    recs = []
+    for i in range(40):
+        seq = "".join(rnd.choice("ACGTN") for _ in range(rnd.randrange(0, 30000)))
+        recs.append((">c%d some description" % i, seq))
+    text = "".join(h + "\n" + "\n".join(s[j:j + 70] for j in range(0, len(s), 70)) + "\n" for h, s in recs).encode()
+    plain = tmp_path / "x.fa"
+    plain.write_bytes(text)
+    bg = tmp_path / "x.fa.gz"
+    bg.write_bytes(bgzf_compress(text, block=4000))
+    assert gzip.decompress(bg.read_bytes()) == text          # a valid multi-member gzip for every other reader too
+    assert tool(bg) == tool(plain) == expect(plain)
+    # a BGZF prefix followed by an ordinary member falls back to the sequential stream
+    mixed = tmp_path / "m.fa.gz"
+    mixed.write_bytes(bgzf_compress(b">a\nACGT\n")[:-28] + gzip.compress(b"GGGG\n>b\nTT\n"))
+    assert tool(mixed) == [("a", 8, fnv(b"ACGTGGGG")), ("b", 2, fnv(b"TT"))]

@@ -818,7 +818,8 @@ __global__ void __launch_bounds__(CT)
 select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws) {
   __shared__ unsigned long long s_key[SEL_SMEM_MAX];
   __shared__ uint32_t s_idx[SEL_SMEM_MAX];
-  __shared__ AccRec s_acc[SEL_SMEM_MAX];
+  __shared__ AccRec s_cand[SEL_SMEM_MAX];       // candidates in sorted order (the greedy loop then never waits on global memory)
+  __shared__ uint16_t s_accpos[SEL_SMEM_MAX];   // accepted candidates: their sorted positions
   __shared__ uint32_t s_qmap[SEL_MAP_BITS / 32], s_rmap[SEL_MAP_BITS / 32];
   __shared__ uint32_t s_nacc;
   const unsigned FULL = 0xFFFFFFFFu;
@@ -841,21 +842,35 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
   for (uint32_t i = threadIdx.x; i < SEL_MAP_BITS / 32; i += blockDim.x) { s_qmap[i] = 0; s_rmap[i] = 0; }
   __syncthreads();
   block_bitonic_sort_intervals(key, idx, npow2, iv);
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { ws.iv_order[4 * ib + npow2 + i] = idx[i]; }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t ci = idx[i];
+    ws.iv_order[4 * ib + npow2 + i] = ci;
+    if (in_smem) {
+      const IntervalKey c = iv[ci];
+      AccRec x; x.q0 = iv_q0(c); x.q1 = iv_q1(c); x.r0 = iv_r0(c); x.r1 = iv_r1(c); x.qctg = iv_qctg(c); x.rctg = iv_rctg(c);
+      s_cand[i] = x;
+    }
+  }
+  if (threadIdx.x == 0) s_nacc = 0;
   __syncthreads();
   const uint32_t* order = ws.iv_order + 4 * ib + npow2;  // final sorted order lives after the sort scratch
   // greedy selection by warp 0 (inherently ordered, src/chain.rs:1016-1095).  A 16 kb-cell occupancy bitmap per axis
   // answers "cannot overlap anything accepted so far" in O(1); only candidates that touch an occupied cell scan the list.
   uint32_t* acc = ws.acc_list + ib;
-  if (threadIdx.x == 0) s_nacc = 0;
-  __syncthreads();
   if (threadIdx.x < 32) {
     const uint32_t lane = threadIdx.x;
     uint32_t nacc = 0;
     for (uint32_t i = 0; i < n; i++) {
-      const uint32_t ci = order[i];
-      const IntervalKey c = iv[ci];
-      const uint32_t q0 = iv_q0(c), q1 = iv_q1(c), r0 = iv_r0(c), r1 = iv_r1(c), qc = iv_qctg(c), rcg = iv_rctg(c);
+      uint32_t ci, q0, q1, r0, r1, qc, rcg;
+      IntervalKey c;
+      if (in_smem) {
+        const AccRec x = s_cand[i];
+        ci = s_idx[i]; q0 = x.q0; q1 = x.q1; r0 = x.r0; r1 = x.r1; qc = x.qctg; rcg = x.rctg;
+      } else {
+        ci = order[i];
+        c = iv[ci];
+        q0 = iv_q0(c); q1 = iv_q1(c); r0 = iv_r0(c); r1 = iv_r1(c); qc = iv_qctg(c); rcg = iv_rctg(c);
+      }
       const uint32_t cq0 = q0 >> SEL_CELL_SHIFT, ncq = ((q1 - 1) >> SEL_CELL_SHIFT) - cq0 + 1;   // q0 < q1, r0 < r1 always
       const uint32_t cr0 = r0 >> SEL_CELL_SHIFT, ncr = ((r1 - 1) >> SEL_CELL_SHIFT) - cr0 + 1;
       bool need_scan = true;
@@ -869,26 +884,25 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
       if (need_scan) {
         uint32_t sum_r = 0, hit_r = 0, sum_q = 0, hit_q = 0;
         for (uint32_t a = lane; a < nacc; a += 32) {
-          if (a < SEL_SMEM_MAX) {
-            const AccRec x = s_acc[a];
-            if (x.rctg == rcg && x.r0 < r1 && r0 < x.r1) { uint32_t u = r1 - x.r0, v = x.r1 - r0; sum_r += u < v ? u : v; hit_r = 1; }
-            if (x.qctg == qc && x.q0 < q1 && q0 < x.q1) { uint32_t u = q1 - x.q0, v = x.q1 - q0; sum_q += u < v ? u : v; hit_q = 1; }
-          } else {
-            uint32_t hr = 0, hq = 0;
-            overlap_contrib(c, iv[acc[a]], &sum_r, &hr, &sum_q, &hq);
-            hit_r |= hr ? 1u : 0u; hit_q |= hq ? 1u : 0u;
-          }
+          AccRec x;
+          if (in_smem) x = s_cand[s_accpos[a]];
+          else { const IntervalKey y = iv[acc[a]]; x.q0 = iv_q0(y); x.q1 = iv_q1(y); x.r0 = iv_r0(y); x.r1 = iv_r1(y); x.qctg = iv_qctg(y); x.rctg = iv_rctg(y); }
+          // half-open overlap (bio IntervalTree::find), contribution = min(c.end - a.start, a.end - c.start) (src/chain.rs:1023-1086)
+          if (x.rctg == rcg && x.r0 < r1 && r0 < x.r1) { uint32_t u = r1 - x.r0, v = x.r1 - r0; sum_r += u < v ? u : v; hit_r = 1; }
+          if (x.qctg == qc && x.q0 < q1 && q0 < x.q1) { uint32_t u = q1 - x.q0, v = x.q1 - q0; sum_q += u < v ? u : v; hit_q = 1; }
         }
         sum_r = __reduce_add_sync(FULL, sum_r);
         sum_q = __reduce_add_sync(FULL, sum_q);
         hit_r = __any_sync(FULL, hit_r) ? 1u : 0u;
         hit_q = __any_sync(FULL, hit_q) ? 1u : 0u;
-        ok = overlap_accept(c, sum_r, hit_r, sum_q, hit_q);
+        const bool ok_r = (hit_r == 0) || ((float)sum_r < (float)(r1 - r0) * 0.5f);   // OVERLAP_ORTHOLOGOUS_FRACTION (:1042)
+        const bool ok_q = (hit_q == 0) || ((float)sum_q < (float)(q1 - q0) * 0.5f);   // (:1072)
+        ok = ok_r && ok_q;
       }
       if (ok) {
         if (lane == 0) {
           acc[nacc] = ci;
-          if (nacc < SEL_SMEM_MAX) { AccRec x; x.q0 = q0; x.q1 = q1; x.r0 = r0; x.r1 = r1; x.qctg = qc; x.rctg = rcg; s_acc[nacc] = x; }
+          if (in_smem) s_accpos[nacc] = (uint16_t)i;
         }
         for (uint32_t t = lane; t < ncq; t += 32) { uint32_t h = sel_cell_hash(qc, cq0 + t); atomicOr(&s_qmap[h >> 5], 1u << (h & 31)); }
         for (uint32_t t = lane; t < ncr; t += 32) { uint32_t h = sel_cell_hash(rcg, cr0 + t); atomicOr(&s_rmap[h >> 5], 1u << (h & 31)); }
@@ -923,12 +937,19 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K6: per-chunk identity, one thread per chunk
+// K6: per-chunk identity, one WARP per chunk: the lanes stride over the chunk's query seeds (coalesced), the chunk's kept
+// intervals (1-3 as a rule) are read once into shared memory instead of being re-walked through global memory per seed
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int CS_WARPS = 8;        // warps (= chunks) per block
+constexpr int CS_IV_MAX = 32;      // kept intervals of a chunk staged in shared memory; more are walked in global memory
+
+__global__ void __launch_bounds__(CS_WARPS * 32)
 chunkstat_kernel(uint64_t n_chunks, const PairDesc* __restrict__ pairs, SetView s0, SetView s1,
                  const GenomeMeta* __restrict__ m0, const GenomeMeta* __restrict__ m1, ChainParams prm, Workspace ws) {
-  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint32_t s_start[CS_WARPS][CS_IV_MAX], s_stop[CS_WARPS][CS_IV_MAX];
+  const unsigned FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const uint64_t c = (uint64_t)blockIdx.x * CS_WARPS + w;
   if (c >= n_chunks) return;
   const uint32_t p = ws.chunk_pair[c];
   const PairDesc pd = pairs[p];
@@ -937,46 +958,68 @@ chunkstat_kernel(uint64_t n_chunks, const PairDesc* __restrict__ pairs, SetView 
   ChunkAcc acc;
   acc.total_anchors = ws.acc_total[c]; acc.rq0 = ws.acc_rq0[c]; acc.rq1 = ws.acc_rq1[c];
   acc.tbcq = ws.acc_tbcq[c]; acc.n_int = ws.acc_nint[c];
-  ws.chunk_valid[c] = 0;
-  // seeds_in_chunk: counted query records of the chunk's contig with lo < pos <= hi
+  // seeds_in_chunk: counted query records of the chunk's contig with lo < pos <= hi (all lanes run the same searches)
   const uint32_t ctg = ws.chunk_qctg[c];
   const uint32_t* cro = Q.ctg_rec_off + qm.ctg_off + qm.g;
-  uint32_t r0 = cro[ctg], r1 = cro[ctg + 1];
+  const uint32_t r0 = cro[ctg], r1 = cro[ctg + 1];
   const uint32_t* pos = Q.pv_pos + qm.seed_off;
   const int64_t lo = ws.chunk_lo[c], hi = ws.chunk_hi[c];
-  // first record with pos > lo
   uint32_t a = r0, b = r1;
-  while (a < b) { uint32_t m = (a + b) >> 1; if ((int64_t)pos[m] <= lo) a = m + 1; else b = m; }
-  uint32_t first = a;
+  while (a < b) { uint32_t m = (a + b) >> 1; if ((int64_t)pos[m] <= lo) a = m + 1; else b = m; }   // first record with pos > lo
+  const uint32_t first = a;
   b = r1;
   while (a < b) { uint32_t m = (a + b) >> 1; if ((int64_t)pos[m] <= hi) a = m + 1; else b = m; }
-  uint32_t last = a;  // [first, last)
+  const uint32_t last = a;  // [first, last)
   const uint16_t* nhv = ws.rec_nh + pd.rec_off;
   const uint64_t ib = ws.pairIbase[p];
-  uint32_t n_seeds = 0, num_in = 0, upper_lower = 0;
   const bool has_int = acc.n_int > 0;
-  for (uint32_t t = first; t < last; t++) {
+  // the chunk's kept intervals, padded by c on both sides (src/chain.rs:239-240), staged by lane 0
+  uint32_t n_iv = 0, more = 0xFFFFFFFFu;
+  if (has_int) {
+    if (lane == 0) {
+      uint32_t i = ws.chunk_head[c];
+      while (i != 0xFFFFFFFFu && n_iv < CS_IV_MAX) {
+        const IntervalKey x = ws.iv[ib + i];
+        const uint32_t q0 = iv_q0(x), q1 = iv_q1(x);
+        s_start[w][n_iv] = q0 > prm.c ? q0 - prm.c : 0;       // max(q0 - c, 0) in i32
+        s_stop[w][n_iv] = q1 + prm.c;
+        n_iv++;
+        i = ws.iv_next[ib + i];
+      }
+      more = i;                                               // rest of the list (beyond CS_IV_MAX), walked in global memory
+    }
+    n_iv = __shfl_sync(FULL, n_iv, 0);
+    more = __shfl_sync(FULL, more, 0);
+    __syncwarp();
+  }
+  uint32_t n_seeds = 0, num_in = 0, upper_lower = 0;
+  for (uint32_t t = first + lane; t < last; t += 32) {
     if (!(nhv[t] & 0x8000u)) continue;
     n_seeds++;
     if (!has_int) continue;
-    uint32_t ps = pos[t];
+    const uint32_t ps = pos[t];
     bool in = false;
-    for (uint32_t i = ws.chunk_head[c]; i != 0xFFFFFFFFu; i = ws.iv_next[ib + i]) {
+    for (uint32_t i = 0; i < n_iv; i++) if (s_start[w][i] <= ps && ps <= s_stop[w][i]) { in = true; break; }
+    for (uint32_t i = more; !in && i != 0xFFFFFFFFu; i = ws.iv_next[ib + i]) {
       const IntervalKey x = ws.iv[ib + i];
-      uint32_t q0 = iv_q0(x), q1 = iv_q1(x);
-      uint32_t start = q0 > prm.c ? q0 - prm.c : 0;         // max(q0 - c, 0) in i32 (src/chain.rs:239-240)
-      uint32_t stop = q1 + prm.c;
-      if (start <= ps && ps <= stop) { in = true; break; }
+      const uint32_t q0 = iv_q0(x), q1 = iv_q1(x);
+      if ((q0 > prm.c ? q0 - prm.c : 0) <= ps && ps <= q1 + prm.c) in = true;
     }
     if (in) num_in++;
     if (ps >= acc.rq0 && ps <= acc.rq1) upper_lower++;      // :322-328 with both spacing estimates 0
   }
+  n_seeds = __reduce_add_sync(FULL, n_seeds);
+  num_in = __reduce_add_sync(FULL, num_in);
+  upper_lower = __reduce_add_sync(FULL, upper_lower);
+  if (lane != 0) return;
   ws.chunk_nseeds[c] = n_seeds;
-  double est; uint32_t w;
-  if (chunk_estimate(acc, prm.c, prm.k, n_seeds, num_in, upper_lower, &est, &w)) {
-    ws.chunk_est[c] = est; ws.chunk_w[c] = w; ws.chunk_valid[c] = 1;
+  double est; uint32_t wgt;
+  uint8_t valid = 0;
+  if (chunk_estimate(acc, prm.c, prm.k, n_seeds, num_in, upper_lower, &est, &wgt)) {
+    ws.chunk_est[c] = est; ws.chunk_w[c] = wgt; valid = 1;
     if (prm.c >= 200) atomicAdd(&ws.pair_tqb_ns[p], acc.rq1 - acc.rq0 + 2 * prm.c + prm.k);  // !sensitive_af (:261-264)
   }
+  ws.chunk_valid[c] = valid;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -999,6 +1042,10 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
   __shared__ uint64_t s_cum[FIN_SMEM_MAX];
   __shared__ uint32_t s_n;
   __shared__ double s_boot[128];
+  __shared__ double s_ci[2];
+  __shared__ float s_term[200];
+  __shared__ float s_x[5];
+  __shared__ int s_do_reg;
   __shared__ uint32_t s_lower_i, s_upper_i, s_reject;
   __shared__ double s_final, s_std;
   __shared__ uint64_t s_pool;
@@ -1133,11 +1180,19 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
           s_boot[rep] = ssum / (double)n;
         }
       }
-      // sort the 100 replicate means, take [4] and [94]
-      for (int i = 1; i < 100; i++) { double v = s_boot[i]; int j = i - 1; while (j >= 0 && s_boot[j] > v) { s_boot[j + 1] = s_boot[j]; j--; } s_boot[j + 1] = v; }
     }
     __syncthreads();
-    ci_lo = s_boot[4]; ci_hi = s_boot[94];
+    // order statistics [4] and [94] of the 100 replicate means (src/chain.rs:80-85 sorts them): every thread ranks its own
+    // value (ties broken by index, so the ranks are a permutation) instead of one thread sorting serially
+    if (threadIdx.x < 100) {
+      const double v = s_boot[threadIdx.x];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < 100; j++) { const double u = s_boot[j]; rank += (u < v || (u == v && j < threadIdx.x)) ? 1u : 0u; }
+      if (rank == 4) s_ci[0] = v;
+      if (rank == 94) s_ci[1] = v;
+    }
+    __syncthreads();
+    ci_lo = s_ci[0]; ci_hi = s_ci[1];
   }
   if (threadIdx.x == 0) {
     double final_ani = s_final;
@@ -1158,22 +1213,40 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
     r.num_contigs_q = qrym.n_ctg; r.num_contigs_r = refm.n_ctg;
     r.avg_chain_int_len = sumlen / num_chains;            // u32 division (:421)
     r.total_bases_covered = tqb;
-    // learned-ANI regression (src/regression.rs:30-64)
+    // learned-ANI regression (src/regression.rs:30-64): features now, the 195 trees are walked by all threads below
+    s_do_reg = 0;
     if (prm.model >= 0 && r.ani > 0.9f && r.total_bases_covered > REGRESS_CUTOFF) {
-      float x[5];
-      x[0] = r.ani * 100.f; x[1] = r.std;
-      if (r.q50_r > r.q50_q) { x[2] = r.q90_r; x[3] = r.q90_q; } else { x[2] = r.q90_q; x[3] = r.q90_r; }
-      x[4] = (float)r.avg_chain_int_len;
-      float pred = gbdt_eval(c_gbdt_feat[prm.model], c_gbdt_thr[prm.model], c_gbdt_leaf[prm.model], 195,
-                             c_gbdt_shrink[prm.model], c_gbdt_bias[prm.model], x);
+      s_x[0] = r.ani * 100.f; s_x[1] = r.std;
+      if (r.q50_r > r.q50_q) { s_x[2] = r.q90_r; s_x[3] = r.q90_q; } else { s_x[2] = r.q90_q; s_x[3] = r.q90_r; }
+      s_x[4] = (float)r.avg_chain_int_len;
+      s_do_reg = 1;
+    }
+  }
+  __syncthreads();
+  if (s_do_reg) {   // uniform
+    // gbdt 0.1.1 predict: bias + sum_t shrink * leaf_t(x), the sum taken in tree order in f32: the per-tree
+    // terms are independent -> one tree per thread, then thread 0 adds them in order
+    const unsigned char* feat = c_gbdt_feat[prm.model];
+    const float* thr = c_gbdt_thr[prm.model];
+    const float* leaf = c_gbdt_leaf[prm.model];
+    const float shrink = c_gbdt_shrink[prm.model];
+    for (uint32_t t = threadIdx.x; t < 195; t += blockDim.x) {
+      int node = 0;
+      for (int d = 0; d < 3; d++) node = 2 * node + ((s_x[feat[7 * t + node]] < thr[7 * t + node]) ? 1 : 2);
+      s_term[t] = __fmul_rn(shrink, leaf[8 * t + (node - 7)]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float pred = c_gbdt_bias[prm.model];
+      for (int t = 0; t < 195; t++) pred = __fadd_rn(pred, s_term[t]);
       if (pred < 100.f) {
         r.ci_upper = (r.ci_upper - r.ani) + pred / 100.f;
         r.ci_lower = (r.ci_lower - r.ani) + pred / 100.f;
         r.ani = pred / 100.f;
       }
     }
-    out[p] = r;
   }
+  if (threadIdx.x == 0) out[p] = r;
 }
 
 __global__ void chunk_size_kernel(uint64_t n, Workspace ws) {
@@ -1396,7 +1469,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
 #undef DP_LAUNCH
     }
     SK_LAUNCH(ctx, "select_kernel", (select_kernel<<<B, CT, 0, st>>>(S.d_pairs, prm, ws)));
-    SK_LAUNCH(ctx, "chunkstat_kernel", (chunkstat_kernel<<<(uint32_t)((TC + 127) / 128), 128, 0, st>>>(TC, S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+    SK_LAUNCH(ctx, "chunkstat_kernel", (chunkstat_kernel<<<(uint32_t)((TC + CS_WARPS - 1) / CS_WARPS), CS_WARPS * 32, 0, st>>>(TC, S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
   }
   SK_LAUNCH(ctx, "final_kernel", (final_kernel<<<B, FT, 0, st>>>(S.d_pairs, S.d_m0, S.d_m1, prm, ws, S.d_out)));
   SK_CUDA(cudaMemcpyAsync(host_out + b0, S.d_out, B * sizeof(sk_ani_result), cudaMemcpyDeviceToHost, st));

@@ -656,15 +656,19 @@ dp_warp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
 // Lane gl of a group owns the anchors congruent to gl mod 8; register set s holds the anchor of block (current - s).
 // Group-wide arg-max = two 3-step xor-butterflies (max score, then largest j among the maxima).
 // ------------------------------------------------------------------------------------------------------------
-template <bool TAPS>
+template <bool TAPS, int GL>
 __global__ void __launch_bounds__(32)
 dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
-  constexpr int NB = 4;                       // sets: current block + 3 earlier (covers band <= 24)
+  // GL lanes per chunk (8 or 4), 32 / GL chunks per warp.  Lane gl of a group owns the anchors congruent to gl mod GL;
+  // register set s holds the anchor of block (current - s); NB - 1 earlier blocks cover band <= 24.
+  constexpr int NB = 24 / GL + 1;
+  constexpr int LG = (GL == 8) ? 3 : 2;       // log2(GL)
+  constexpr uint32_t GW = 32 / GL;            // chunks per warp
   const unsigned FULL = 0xFFFFFFFFu;
-  const uint32_t lane = threadIdx.x, gl = lane & 7u, gbase = lane & 24u;
-  const uint64_t slot = (uint64_t)blockIdx.x * 4 + (lane >> 3);
+  const uint32_t lane = threadIdx.x, gl = lane & (GL - 1), gbase = lane & ~(uint32_t)(GL - 1);
+  const uint64_t slot = (uint64_t)blockIdx.x * GW + (lane >> LG);
   const bool live = slot < n_chunks;
-  const uint64_t c = live ? (uint64_t)ws.chunk_perm[slot] : 0;   // chunks sorted by size: the 4 chunks of a warp are alike
+  const uint64_t c = live ? (uint64_t)ws.chunk_perm[slot] : 0;   // chunks sorted by size: the chunks of a warp are alike
   uint64_t a0 = 0;
   uint32_t n = 0;
   if (live) { a0 = ws.chunk_first[c]; n = (uint32_t)(ws.chunk_first[c + 1] - a0); }
@@ -675,13 +679,13 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
   // longest chunk of the warp bounds the common loop
   uint32_t nmax = n;
 #pragma unroll
-  for (int o = 16; o >= 8; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+  for (int o = 16; o >= GL; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
   uint32_t q[NB], r[NB], rc[NB], rt[NB], dpth[NB];
   int32_t sc[NB];
   uint32_t my_ptr = 0;
 #pragma unroll
   for (int s = 0; s < NB; s++) { q[s] = r[s] = rc[s] = rt[s] = dpth[s] = 0; sc[s] = 0; }
-  for (uint32_t b0 = 0; b0 < nmax; b0 += 8) {
+  for (uint32_t b0 = 0; b0 < nmax; b0 += GL) {
 #pragma unroll
     for (int s = NB - 1; s > 0; s--) { q[s] = q[s - 1]; r[s] = r[s - 1]; rc[s] = rc[s - 1]; rt[s] = rt[s - 1]; dpth[s] = dpth[s - 1]; sc[s] = sc[s - 1]; }
     const uint32_t idx = b0 + gl;
@@ -693,7 +697,7 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
     }
     __syncwarp();
 #pragma unroll
-    for (uint32_t m = 0; m < 8; m++) {
+    for (uint32_t m = 0; m < (uint32_t)GL; m++) {
       const uint32_t i = b0 + m;
       const uint32_t src = gbase | m;
       AnchorRec cur;
@@ -710,7 +714,7 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
         const uint32_t rs = lo_set ? r[t] : r[t + 1];
         const uint32_t rcs = lo_set ? rc[t] : rc[t + 1];
         const int32_t scs = lo_set ? sc[t] : sc[t + 1];
-        const uint32_t d = m + 8u * (uint32_t)t + (lo_set ? 0u : 8u) - gl; // i - j >= 1
+        const uint32_t d = m + (uint32_t)GL * (uint32_t)t + (lo_set ? 0u : (uint32_t)GL) - gl; // i - j >= 1
         const uint32_t dq = cur.qpos - qs;
         const uint32_t tr = cur.rpos - rs;
         const uint32_t dr = (cur.rc & 1u) ? (0u - tr) : tr;
@@ -726,19 +730,19 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
       // group arg-max: maximal score, then the smallest distance d (= largest j) among the maxima
       int32_t smax = best_ns;
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) smax = max(smax, __shfl_xor_sync(FULL, smax, o));
+      for (int o = GL / 2; o > 0; o >>= 1) smax = max(smax, __shfl_xor_sync(FULL, smax, o));
       uint32_t dkey = (best_ns == smax && smax > 0) ? (64u - best_d) : 0u;   // d <= 31, so 64 - d > 0
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) dkey = max(dkey, __shfl_xor_sync(FULL, dkey, o));
+      for (int o = GL / 2; o > 0; o >>= 1) dkey = max(dkey, __shfl_xor_sync(FULL, dkey, o));
       const bool has = dkey != 0u;
       const uint32_t dwin = 64u - dkey;
       const uint32_t jw = i - dwin;                                          // only meaningful when has
-      // winner's root / depth: owner lane = jw mod 8, set = block distance
-      const int sidx = (int)(b0 >> 3) - (int)(jw >> 3);
+      // winner's root / depth: owner lane = jw mod GL, set = block distance
+      const int sidx = (int)(b0 >> LG) - (int)(jw >> LG);
       uint32_t rsel = rt[0], dsel = dpth[0];
 #pragma unroll
       for (int s = 1; s < NB; s++) if (sidx == s) { rsel = rt[s]; dsel = dpth[s]; }
-      const uint32_t wsrc = gbase | (jw & 7u);
+      const uint32_t wsrc = gbase | (jw & (uint32_t)(GL - 1));
       const uint32_t root_w = __shfl_sync(FULL, rsel, wsrc);
       const uint32_t depth_w = __shfl_sync(FULL, dsel, wsrc);
       const bool mine = has & (gl == m);
@@ -759,7 +763,7 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
   const uint32_t p = ws.chunk_pair[c];
   const uint32_t qctg = ws.chunk_qctg[c];
   const uint32_t chunk_local_id = (uint32_t)(c - ws.pairCbase[p]);
-  for (uint32_t i = gl; i < n; i += 8) {
+  for (uint32_t i = gl; i < n; i += GL) {
     if (((volatile uint32_t*)g_depth)[i] != 1) continue;            // not a root
     const unsigned long long key = ((volatile unsigned long long*)g_key)[i];
     const uint32_t b = (uint32_t)key, score = (uint32_t)(key >> 32);
@@ -769,8 +773,8 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
     const AnchorRec f = a[i], l = a[b];
     uint32_t r0 = f.rpos < l.rpos ? f.rpos : l.rpos, r1 = f.rpos < l.rpos ? l.rpos : f.rpos;
     IntervalKey key5 = make_interval((int32_t)score, num_anchors, f.qpos, l.qpos, r0, r1, f.rc >> 1, qctg, chunk_local_id, f.rc & 1u);
-    uint32_t slot = atomicAdd(&ws.pair_nint[p], 1u);
-    ws.iv[ws.pairIbase[p] + slot] = key5;
+    uint32_t slot2 = atomicAdd(&ws.pair_nint[p], 1u);
+    ws.iv[ws.pairIbase[p] + slot2] = key5;
   }
 }
 
@@ -1453,7 +1457,9 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, true><<<grid, 32, 0, st>>>(TC, prm, ws)));       \
   else SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, false><<<grid, 32, 0, st>>>(TC, prm, ws)));
       if (prm.band <= 24 && getenv("SK_DP_WARP") == nullptr) {   // 4 chunks per warp, 8 lanes each
-        const uint32_t g4 = (uint32_t)((TC + 3) / 4);
+        const int dp_gl = getenv("SK_DP_GL") ? atoi(getenv("SK_DP_GL")) : 8;   // lanes per chunk: 8 (default) or 4 (A/B, profiles/r02_*)
+        const uint32_t gw = dp_gl == 4 ? 8 : 4;
+        const uint32_t g4 = (uint32_t)((TC + gw - 1) / gw);
         // group chunks of similar size: sort chunk ids by descending anchor count (cub radix sort, ~0.1 ms per batch)
         SK_TRY(ensure(ctx, &ws.chunk_size, &S.c_chunk_size, TC)); SK_TRY(ensure(ctx, &ws.chunk_size_sorted, &S.c_chunk_size_sorted, TC));
         SK_TRY(ensure(ctx, &ws.chunk_id, &S.c_chunk_id, TC)); SK_TRY(ensure(ctx, &ws.chunk_perm, &S.c_chunk_perm, TC));
@@ -1462,8 +1468,13 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
         SK_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, (int)TC, 0, 32, st));
         SK_TRY(ensure(ctx, &S.sort_tmp, &S.c_sort_tmp, tb));
         SK_CUDA(cub::DeviceRadixSort::SortPairsDescending(S.sort_tmp, tb, ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, (int)TC, 0, 32, st));
-        if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true><<<g4, 32, 0, st>>>(TC, prm, ws)));
-        else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false><<<g4, 32, 0, st>>>(TC, prm, ws)));
+        if (dp_gl == 4) {
+          if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true, 4><<<g4, 32, 0, st>>>(TC, prm, ws)));
+          else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, 4><<<g4, 32, 0, st>>>(TC, prm, ws)));
+        } else {
+          if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true, 8><<<g4, 32, 0, st>>>(TC, prm, ws)));
+          else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, 8><<<g4, 32, 0, st>>>(TC, prm, ws)));
+        }
       } else if (nb <= 2) { DP_LAUNCH(2) } else if (nb <= 4) { DP_LAUNCH(4) } else if (nb <= 8) { DP_LAUNCH(8) }
       else if (nb <= 16) { DP_LAUNCH(16) } else { ctx->err = "c too small: chain band > 479 anchors is not supported"; return SK_ERR_PARAM; }
 #undef DP_LAUNCH

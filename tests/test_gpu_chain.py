@@ -92,6 +92,18 @@ def test_chain_debug_parity_synthetic(ctx, c, mc, learned):
         assert_debug_equal(gd, od)
 
 
+def test_chain_debug_parity_dp_four_lane_groups(ctx, monkeypatch):
+    """The banded DP with 4 lanes per chunk / 8 chunks per warp (SK_DP_GL=4, the A/B variant of dp_group_kernel) is held to
+    the same bit-exact per-anchor score / pointer / interval parity as the default 8-lane form."""
+    import skani_b200 as sk
+    monkeypatch.setenv("SK_DP_GL", "4")
+    genomes = synth_genomes(8, 700_000, 4)
+    for c in (125, 200):
+        gs, osk = make_sets(ctx, genomes, dict(c=c, k=15, marker_c=1000))
+        for (r, q) in [(0, 1), (1, 3), (5, 6), (4, 7), (3, 3)]:
+            assert_debug_equal(sk.chain_pair_debug(ctx, gs, gs, r, q, sk.map_params()), O.chain_debug(osk[r], osk[q], O.cmd()))
+
+
 def test_triangle_parity_synthetic(ctx):
     import skani_b200 as sk
     n, L, G = 24, 400_000, 6

@@ -105,3 +105,41 @@ def test_gather_variable_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_cross_block_pairs_and_bench_helpers():
+    """cross_block_pairs keeps exactly the pairs whose genomes live in different blocks (the pairs inside a block are chained
+    by the block's own pipelined triangle), for the block layouts sk_triangle_multi and bench.py use; bench.py's result
+    checksum is order independent and sensitive to every compared field; the permuted generator is a permutation."""
+    from skani_b200.multi_gpu import cross_block_pairs, shard_range
+    rng = np.random.default_rng(3)
+    for n, world in ((40, 2), (1000, 8), (17, 3)):
+        ii = rng.integers(0, n - 1, 500); jj = rng.integers(1, n, 500)
+        pl = np.array(sorted({(int(min(a, b)) << 32) | int(max(a, b)) for a, b in zip(ii, jj) if a != b}), np.uint64)
+        bounds = [shard_range(n, world, r)[0] for r in range(world)] + [n]
+        blk = lambda g: max(r for r in range(world) if bounds[r] <= g)
+        want = [int(x) for x in pl if blk(int(x) >> 32) != blk(int(x) & 0xFFFFFFFF)]
+        assert cross_block_pairs(pl, bounds).tolist() == want
+    assert len(cross_block_pairs(np.zeros(0, np.uint64), [0, 5, 10])) == 0
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from skani_b200.host import RESULT_DTYPE
+    res = np.zeros(50, RESULT_DTYPE)
+    res["ref_id"] = rng.integers(0, 1000, 50); res["query_id"] = rng.integers(0, 1000, 50)
+    res["ani"] = rng.random(50).astype(np.float32); res["af_ref"] = rng.random(50).astype(np.float32); res["af_query"] = rng.random(50).astype(np.float32)
+    c0 = bench.result_checksum(res)
+    assert c0 == bench.result_checksum(res[rng.permutation(50)]) and 0 < c0 < 2 ** 64
+    parts = [res[:20], res[20:]]
+    assert (bench.result_checksum(parts[0]) + bench.result_checksum(parts[1])) % 2 ** 64 == c0      # what the all-reduce adds up
+    for f in ("ref_id", "query_id", "ani", "af_ref", "af_query"):
+        r2 = res.copy()
+        r2[f][7] = r2[f][7] + (1 if f.endswith("_id") else np.float32(1e-6))
+        assert bench.result_checksum(r2) != c0, f
+    assert bench.result_checksum(res[:0]) == 0
+    assert bench.expected_pairs(10000, 20) == 95000 and bench.expected_pairs(45, 20) == 2 * 190 + 10
+    from bench_support import synth
+    ids = synth.shuffled_ids(1000, 12345)
+    assert sorted(ids.tolist()) == list(range(1000)) and ids.tolist() != list(range(1000))
+    assert np.array_equal(ids, synth.shuffled_ids(1000, 12345))

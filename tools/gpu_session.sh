@@ -16,6 +16,6 @@ SK_DP_GL=4 timeout 600 python tools/profile_step.py 400 > $O/${TAG}_profile_step
 head -24 $O/${TAG}_profile_step.txt; grep "dp_kernel" $O/${TAG}_profile_step_gl4.txt | head -3
 if [ "$2" != "quick" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/${TAG}_launches.csv python bench.py --config c2 --steps 1 --warmup 1 --no-cpu-baseline --spot-check 0 > $O/${TAG}_bench_under_ncu.log 2>&1
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"pack_kernel|hashpass|expand_kernel|hash_build|probe_kernel|chunk_fast|anchor_kernel|dp_group|select_kernel|chunkstat|final_kernel" --launch-skip 30 -c 14 -f -o $O/${TAG}_full python tools/profile_step.py 200 > $O/${TAG}_ncu_full.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"pack_kernel|hashpass|expand_kernel|hash_build|probe_kernel|chunk_fast|anchor_kernel|dp_group|select_kernel|chunkstat|final_kernel" -c 21 -f -o $O/${TAG}_full python tools/profile_step.py 200 > $O/${TAG}_ncu_full.log 2>&1
   ls -la $O/${TAG}_full.ncu-rep
 fi

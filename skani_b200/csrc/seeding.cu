@@ -87,10 +87,54 @@ pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ coff
 
 constexpr int HASH_THREADS = 128;
 
+// ---- A/B variants of the hash arithmetic (SK_HASHPASS_VARIANT=1|2, profiles/r02_hashpass_variants.md): the kernel is bound
+// by the ALU pipe (LOP3 / SHF / IADD3) while the FMA pipe (IMAD) has headroom, so the right shifts of the three xor-shift
+// steps can be issued as multiplications: x >> s == mul.hi(x, 2^(32-s)).  The multipliers arrive as kernel arguments so
+// that ptxas cannot turn them back into shifts.  V=1: the high word only; V=2: both words (low word = mul.hi(lo, c) + hi * c).
+template <int V>
+__device__ __forceinline__ uint64_t xorshift_var(uint64_t key, uint32_t s, uint32_t c) {
+  const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+  uint32_t hs, ls;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(hs) : "r"(hi), "r"(c));
+  if (V == 1) ls = __funnelshift_r(lo, hi, s);
+  else { uint32_t t; asm("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(lo), "r"(c)); ls = t + hi * c; }
+  return ((uint64_t)(hi ^ hs) << 32) | (uint64_t)(lo ^ ls);
+}
+template <int V>
+__device__ __forceinline__ uint32_t unit_pass_mask_var(uint64_t lo, uint64_t hi, uint32_t nm_lo, uint32_t nm_hi, uint32_t n, uint32_t ul,
+                                                       uint32_t seed_mask32, uint64_t threshold, uint32_t c24, uint32_t c14, uint32_t c28) {
+  const uint32_t valid = unit_valid_mask(n, ul);
+  if (valid == 0) return 0;
+  const uint64_t clo = ~lo, chi = ~hi;
+  const uint64_t tlo = pair_reverse64(hi), thi = pair_reverse64(lo);
+  const uint32_t c[4] = {(uint32_t)clo, (uint32_t)(clo >> 32), (uint32_t)chi, (uint32_t)(chi >> 32)};
+  const uint32_t t[4] = {(uint32_t)tlo, (uint32_t)(tlo >> 32), (uint32_t)thi, (uint32_t)(thi >> 32)};
+  uint32_t pass = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 32; j++) {
+    const uint32_t orv = 24 + 2 * j, ofw = 62 - 2 * j;
+    const uint32_t rs = funnel_r32(c[orv >> 5], c[(orv >> 5) + 1], orv & 31) & seed_mask32;
+    const uint32_t fs = funnel_r32(t[ofw >> 5], t[(ofw >> 5) + 1], ofw & 31) & seed_mask32;
+    const uint32_t seed = fs < rs ? fs : rs;
+    uint64_t key = ~((uint64_t)seed * 0x200001ull);
+    key = xorshift_var<V>(key, 24, c24);
+    key = key * 265ull;
+    key = xorshift_var<V>(key, 14, c14);
+    key = key * 21ull;
+    key = xorshift_var<V>(key, 28, c28);
+    key = key * 0x80000001ull;
+    if (key < threshold) pass |= 1u << j;
+  }
+  pass &= valid;
+  if ((nm_lo | nm_hi) != 0 && pass != 0) pass &= ~unit_n_suppress_mask(n, ul, nm_lo, nm_hi, pass);
+  return pass;
+}
+
+template <int V>
 __global__ void __launch_bounds__(HASH_THREADS)
 hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM, const uint32_t* __restrict__ ucoarse,
                 const uint32_t* __restrict__ cuoff, const uint32_t* __restrict__ clen, uint32_t n_units,
-                uint64_t seed_mask, uint64_t threshold, uint32_t* __restrict__ PM) {
+                uint64_t seed_mask, uint64_t threshold, uint32_t* __restrict__ PM, uint32_t c24, uint32_t c14, uint32_t c28) {
   uint32_t u = blockIdx.x * HASH_THREADS + threadIdx.x;
   if (u >= n_units) return;
   uint32_t ci = contig_of_unit(ucoarse, cuoff, u);
@@ -100,7 +144,8 @@ hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM,
   uint64_t lo = ul ? P[u - 1] : 0ull;
   uint32_t nhi = NM[u];
   uint32_t nlo = ul ? NM[u - 1] : 0u;
-  PM[u] = unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold);
+  if (V == 0) PM[u] = unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold);
+  else PM[u] = unit_pass_mask_var<V>(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold, c24, c14, c28);
 }
 
 // one thread per unit with a non-empty pass mask: regenerate the few passing windows and emit their records
@@ -551,8 +596,14 @@ int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_
     }
     const uint64_t seed_mask = ~0ull >> (64 - 2 * sp->k);
     const uint64_t thr = ~0ull / sp->c, thr_m = ~0ull / sp->marker_c;  // src/avx2_seeding.rs:93-94
-    SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<<<div_up(NU, HASH_THREADS), HASH_THREADS, 0, st>>>(
-        P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p)));
+    {
+      const int hv = getenv("SK_HASHPASS_VARIANT") ? atoi(getenv("SK_HASHPASS_VARIANT")) : 0;
+      const uint32_t c24 = 1u << 8, c14 = 1u << 18, c28 = 1u << 4;     // 2^(32 - s) for the xor-shift distances 24 / 14 / 28
+      const uint32_t grid = div_up(NU, HASH_THREADS);
+      if (hv == 1) SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<1><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28)));
+      else if (hv == 2) SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<2><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28)));
+      else SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<0><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28)));
+    }
     {   // record offset of every unit = exclusive scan of the pass-mask popcounts (no separate count array)
       auto cnt_it = thrust::make_transform_iterator((const uint32_t*)PM.p, PopcOp());
       size_t tb = 0;

@@ -101,3 +101,17 @@ def test_empty_and_tiny_inputs(ctx):
     assert len(gs) == 2 and gs.info(0)["n_records"] == 0 and gs.info(1)["n_contigs"] == 0
     with pytest.raises(Exception):
         sk.sketch_contigs(ctx, np.zeros(600, np.uint8), [0, 600], [0], 1, sk.sketch_params(2000, 15, 1000))  # c > marker_c
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_hashpass_arithmetic_variants_bit_exact(ctx, monkeypatch, variant):
+    """The A/B variants of hashpass_kernel (xor-shift right shifts issued as mul.hi on the FMA pipe, SK_HASHPASS_VARIANT)
+    select exactly the same windows as the default arithmetic."""
+    import skani_b200 as sk
+    monkeypatch.setenv("SK_HASHPASS_VARIANT", variant)
+    rng = np.random.default_rng(99)
+    contigs = parity_set(rng, 30)
+    for c, k, mc in ((125, 15, 1000), (10, 13, 40)):
+        gs = sk.sketch_sequences(ctx, [contigs[:12], contigs[12:30]], sk.sketch_params(c, k, mc))
+        compare(gs, 0, O.sketch_from_contigs("a", contigs[:12], c=c, k=k, marker_c=mc))
+        compare(gs, 1, O.sketch_from_contigs("b", contigs[12:30], c=c, k=k, marker_c=mc))

@@ -115,12 +115,38 @@ constexpr int ITEMS = 4;
 // ------------------------------------------------------------------------------------------------------------
 // K1: probe
 // ------------------------------------------------------------------------------------------------------------
+// 1-D bulk copy (TMA, cp.async.bulk) global -> shared memory, completion signalled on an mbarrier: used to stage the whole
+// k-mer table of a SMALL ref-role genome (<= 2048 entries = 16 KB: viruses, plasmids, single contigs -- BASELINE.json
+// configs[4]) so that its probes hit shared memory instead of L2.  A/B switch SK_PROBE_TMA (profiles/r02_tma_probe.md).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load_to_smem(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+constexpr uint32_t PROBE_STAGE_ENTRIES = 2048;   // 16 KB: fits the (otherwise unused) bucket-index array of the block
+
+// STAGED = the batch is dominated by small ref-role genomes: their tables are bulk-copied to shared memory (generic loads);
+// otherwise every probe is a read-only global load.
+template <bool STAGED>
 __global__ void __launch_bounds__(CT)
 probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const GenomeMeta* __restrict__ m0,
              const GenomeMeta* __restrict__ m1, ChainParams prm, Workspace ws) {
   using Scan = cub::BlockScan<uint64_t, CT>;
   __shared__ typename Scan::TempStorage tmp;
-  __shared__ uint32_t s_bucket[UBUCKETS + 1];
+  __shared__ __align__(16) uint32_t s_bucket[UBUCKETS + 4];
+  __shared__ __align__(8) unsigned long long s_bar;
   const PairDesc pd = pairs[blockIdx.x];
   if (!pd.valid) {
     if (threadIdx.x == 0) { ws.pairA[blockIdx.x] = 0; ws.pairH[blockIdx.x] = 0; }
@@ -134,8 +160,19 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
   const uint32_t* __restrict__ rus = R.ustart + rm.uk_off + rm.g;
   const uint32_t nuk = rm.n_uk;
   const bool use_hash = rm.ht_cap != 0;
-  const unsigned long long* __restrict__ htab = R.htab + rm.ht_off;
+  const unsigned long long* htab = R.htab + rm.ht_off;
   const uint32_t ht_mask = rm.ht_cap - 1;
+  if (STAGED && use_hash && rm.ht_cap <= PROBE_STAGE_ENTRIES) {   // block-uniform
+    unsigned long long* s_tab = (unsigned long long*)s_bucket;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      bulk_load_to_smem(s_tab, htab, rm.ht_cap * 8u, &s_bar);     // table offsets and sizes are multiples of 16 entries
+    }
+    __syncthreads();          // the barrier is initialised before anybody polls it
+    mbar_wait(&s_bar, 0);
+    htab = s_tab;
+  }
   const uint32_t ht_shift = use_hash ? (32u - (uint32_t)__ffs((int)rm.ht_cap) + 1u) : 32u;
   if (!use_hash) {  // fallback (genomes with >= 2^20 records): bucket index (16 KB) staged in shared memory
     const uint32_t* gb = R.ubucket + (size_t)rm.g * (UBUCKETS + 1);
@@ -162,7 +199,7 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
         }
       }
 #pragma unroll
-      for (int it = 0; it < ITEMS; it++) if (live[it]) ent[it] = htab[hpos[it]];
+      for (int it = 0; it < ITEMS; it++) if (live[it]) ent[it] = STAGED ? htab[hpos[it]] : __ldg(htab + hpos[it]);
 #pragma unroll
       for (int it = 0; it < ITEMS; it++) {
         const uint32_t t = t0 + threadIdx.x * ITEMS + it;
@@ -171,7 +208,7 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
         if (live[it]) {
           unsigned long long e = ent[it];
           uint32_t hp = hpos[it];
-          while (e != 0ull && (uint32_t)(e >> 32) != kmer[it]) { hp = (hp + 1) & ht_mask; e = htab[hp]; }
+          while (e != 0ull && (uint32_t)(e >> 32) != kmer[it]) { hp = (hp + 1) & ht_mask; e = STAGED ? htab[hp] : __ldg(htab + hp); }
           if (e != 0ull) {
             const uint32_t cntr = (uint32_t)e & 0xFFFu;        // saturated at 4095 > any band
             if (cntr <= prm.band) { counted = 1; nh[it] = cntr; rst[it] = (uint32_t)(e >> 12) & 0xFFFFFu; }  // else dropped (:695-697)
@@ -1419,7 +1456,19 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   SK_CUDA(cudaMemsetAsync(ws.pair_nchains, 0, B * 4, st));
   SK_CUDA(cudaMemsetAsync(ws.pair_tqb_ns, 0, B * 4, st));
 
-  SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+  {
+    // small ref-role genomes (k-mer table <= 16 KB): TMA-stage the table in shared memory when they dominate the batch
+    size_t n_small = 0;
+    for (size_t i = b0; i < b1; i++) {
+      const PairDesc& d = descs[i];
+      if (!d.valid) continue;
+      const sk_sketch_set* rs_ = d.rset ? qs : refs;
+      if (!rs_->ht_off.empty()) { const uint64_t cap = rs_->ht_off[d.rg + 1] - rs_->ht_off[d.rg]; if (cap && cap <= PROBE_STAGE_ENTRIES) n_small++; }
+    }
+    const bool staged = (getenv("SK_PROBE_TMA") ? atoi(getenv("SK_PROBE_TMA")) != 0 : true) && 2 * n_small >= (size_t)B;
+    if (staged) SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<true><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+    else SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<false><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+  }
   SK_LAUNCH(ctx, "chunk_fast_kernel", (chunk_fast_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
   SK_LAUNCH(ctx, "chunk_kernel", (chunk_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
   std::vector<uint32_t> hA(B), hC(B);

@@ -1,5 +1,7 @@
 """Scaled-down versions of BASELINE.json configs 3 and 5 on the GPU vs the oracle (parity at the configurations'
 parameter settings: search-mode screening, c=30 / m=200 / rescue off on thousands of short contigs)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -50,6 +52,14 @@ def test_config5_small_genomes_triangle(ctx):
     got = {(int(r["ref_id"]), int(r["query_id"])): r for r in res if r["ani"] > 0.1}
     assert set(got) == set(exp)
     assert all(close(got[k], exp[k]) for k in exp)
+    # the probe kernel stages small k-mer tables in shared memory with a TMA bulk copy (cp.async.bulk + mbarrier); the
+    # plain global-memory probe (SK_PROBE_TMA=0, the A/B baseline) must give byte-identical results
+    os.environ["SK_PROBE_TMA"] = "0"
+    try:
+        res0 = sk.chain_pairs(ctx, gs, gs, pairs, mp, as_array=True)
+    finally:
+        del os.environ["SK_PROBE_TMA"]
+    assert res.tobytes() == res0.tobytes()
 
 
 def test_config3_search_queries_vs_db(ctx):

@@ -37,3 +37,23 @@ def test_two_rank_triangle_matches_oracle():
             assert abs(sizes[0] - sizes[1]) <= 1
             for k, e in exp.items():
                 assert abs(got[k][2] - e.ani) <= 1e-4 and abs(got[k][3] - e.af_ref) <= 1e-4 and abs(got[k][4] - e.af_query) <= 1e-4
+
+
+def test_one_process_multi_device_triangle_matches_single():
+    """sk_triangle_multi with one context per PHYSICAL GPU (peer copies over NVLink): same result set as one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import skani_b200 as sk
+    n, L, G = 18, 300_000, 6
+    for ids in (np.arange(n, dtype=np.uint64), synth.shuffled_ids(n, 11)):
+        bases, off, goc = synth.generate_ids(ids, L, G=G)
+        ctxs = [sk.Context(d) for d in range(2)]
+        try:
+            single, _ = sk.triangle(ctxs[0], bases, off, goc, n, as_array=True)
+            multi, _ = sk.triangle_multi(ctxs, bases, off, goc, n)
+            a = np.sort(single, order=["ref_id", "query_id"]); b = np.sort(multi, order=["ref_id", "query_id"])
+            assert len(a) == len(b) == n // G * (G * (G - 1) // 2) and a.tobytes() == b.tobytes()
+        finally:
+            for c in ctxs:
+                c.close()

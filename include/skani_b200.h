@@ -74,6 +74,16 @@ void* sk_ctx_stream(const sk_ctx* ctx);
 int sk_ctx_set_timing(sk_ctx* ctx, int on);
 int sk_ctx_get_timing(sk_ctx* ctx, char* buf, uint64_t cap, int reset);
 
+/* Which of the reference's two seeders the context reproduces.  SK_SEED_AVX2 (default) = avx2_seeding::avx2_fmh_seeds
+ * (src/avx2_seeding.rs:33), what every x86-64 host with AVX2 runs (src/file_io.rs:196-226 dispatch): 4 quarter-lanes, the
+ * last (len - 20) mod 4 windows never examined, only 'N' breaks a window, for 21 bases.  SK_SEED_SCALAR = seeding::fmh_seeds
+ * (src/seeding.rs:225-323), what hosts WITHOUT AVX2 run: one lane, every window, 'N' and 'n' break the next k windows.
+ * Both are bit-exact against the oracle (tests/test_gpu_seeding.py).  With SK_SEED_SCALAR sk_sketch_batch_2bit expects the
+ * caller's N mask to flag 'n' as well. */
+#define SK_SEED_AVX2 0
+#define SK_SEED_SCALAR 1
+int sk_ctx_set_seeding_semantics(sk_ctx* ctx, int semantics);
+
 /* ---- seeding: replaces avx2_seeding::avx2_fmh_seeds (src/avx2_seeding.rs:33, the path x86-64 hosts run;
  *      bit-exact incl. its 4-lane split, dropped tail windows and 'N' rule) and the Sketch assembly of
  *      file_io::fastx_to_sketches / fastx_to_multiple_sketch_rewrite (src/file_io.rs:141-362) ------------

@@ -45,6 +45,7 @@ SYMBOLS = [
     ("sk_device_count", i32, []),
     ("sk_ctx_create", i32, [i32, PP(vp)]),
     ("sk_ctx_destroy", i32, [vp]),
+    ("sk_ctx_set_seeding_semantics", i32, [vp, i32]),
     ("sk_last_error", C.c_char_p, [vp]),
     ("sk_ctx_launch_count", u64, [vp]),
     ("sk_ctx_stream", vp, [vp]),

@@ -305,6 +305,13 @@ int sk_device_count(void) {
   return n;
 }
 
+int sk_ctx_set_seeding_semantics(sk_ctx* ctx, int semantics) {
+  if (!ctx || (semantics != SK_SEED_AVX2 && semantics != SK_SEED_SCALAR)) return SK_ERR_PARAM;
+  ctx->seed_scalar = semantics == SK_SEED_SCALAR;
+  if (ctx->child) ctx->child->seed_scalar = ctx->seed_scalar;
+  return SK_OK;
+}
+
 const char* sk_last_error(const sk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t sk_ctx_launch_count(const sk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* sk_ctx_stream(const sk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -744,6 +751,7 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
   double fixed_share = -1.0;
   if (const char* e = getenv("SK_HOST_PACK")) fixed_share = std::min(1.0, std::max(0.0, atof(e)));
   if (prepacked) fixed_share = 1.0;
+  else if (ctx->seed_scalar) fixed_share = 0.0;   // the scalar seeder also breaks on 'n': only the device packer flags it
   SkPool* pool = ctx_pool(ctx);
   // ---- buffers (grow-only, kept in the context)
   const bool want_ascii = !prepacked && fixed_share < 1.0;

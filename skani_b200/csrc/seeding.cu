@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t contig_of_unit(const uint32_t* __restrict__ 
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ coff, const uint32_t* __restrict__ cuoff,
             const uint32_t* __restrict__ clen, const uint32_t* __restrict__ ucoarse, uint32_t u_begin, uint32_t n_units,
-            uint64_t* __restrict__ P, uint32_t* __restrict__ NM) {
+            uint64_t* __restrict__ P, uint32_t* __restrict__ NM, int small_n) {
   const uint32_t u = u_begin + blockIdx.x * PACK_THREADS + threadIdx.x;
   if (u >= n_units) return;
   const uint32_t ci = contig_of_unit(ucoarse, cuoff, u);
@@ -76,7 +76,7 @@ pack_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ coff
   for (int i = 0; i < 8; i++) {
     const uint32_t r = __funnelshift_r(w[i], w[i + 1], sh);
     uint32_t c8, n4;
-    pack_word(r, c8, n4);
+    pack_word(r, c8, n4, small_n != 0);
     packed |= (uint64_t)c8 << (8 * i);
     nm |= n4 << (4 * i);
   }
@@ -134,7 +134,8 @@ template <int V>
 __global__ void __launch_bounds__(HASH_THREADS)
 hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM, const uint32_t* __restrict__ ucoarse,
                 const uint32_t* __restrict__ cuoff, const uint32_t* __restrict__ clen, uint32_t n_units,
-                uint64_t seed_mask, uint64_t threshold, uint32_t* __restrict__ PM, uint32_t c24, uint32_t c14, uint32_t c28) {
+                uint64_t seed_mask, uint64_t threshold, uint32_t* __restrict__ PM, uint32_t c24, uint32_t c14, uint32_t c28,
+                uint32_t scalar_k) {
   uint32_t u = blockIdx.x * HASH_THREADS + threadIdx.x;
   if (u >= n_units) return;
   uint32_t ci = contig_of_unit(ucoarse, cuoff, u);
@@ -144,7 +145,7 @@ hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM,
   uint64_t lo = ul ? P[u - 1] : 0ull;
   uint32_t nhi = NM[u];
   uint32_t nlo = ul ? NM[u - 1] : 0u;
-  if (V == 0) PM[u] = unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold);
+  if (V == 0) PM[u] = unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold, scalar_k);
   else PM[u] = unit_pass_mask_var<V>(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold, c24, c14, c28);
 }
 
@@ -592,17 +593,18 @@ int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_
     if (u_ascii < NU) {
       if (!src.d_ascii) { ctx->err = "ASCII contigs without a device buffer"; return SK_ERR_PARAM; }
       SK_LAUNCH(ctx, "pack_kernel", (pack_kernel<<<div_up(NU - u_ascii, PACK_THREADS), PACK_THREADS, 0, st>>>(
-          src.d_ascii, d_coff.p, d_cuoff.p, d_clen.p, d_ucoarse.p, u_ascii, NU, P, NM)));
+          src.d_ascii, d_coff.p, d_cuoff.p, d_clen.p, d_ucoarse.p, u_ascii, NU, P, NM, ctx->seed_scalar ? 1 : 0)));
     }
     const uint64_t seed_mask = ~0ull >> (64 - 2 * sp->k);
     const uint64_t thr = ~0ull / sp->c, thr_m = ~0ull / sp->marker_c;  // src/avx2_seeding.rs:93-94
     {
-      const int hv = getenv("SK_HASHPASS_VARIANT") ? atoi(getenv("SK_HASHPASS_VARIANT")) : 0;
+      const uint32_t scalar_k = ctx->seed_scalar ? sp->k : 0;     // scalar fmh_seeds semantics (sk_ctx_set_seeding_semantics)
+      const int hv = (getenv("SK_HASHPASS_VARIANT") && !scalar_k) ? atoi(getenv("SK_HASHPASS_VARIANT")) : 0;
       const uint32_t c24 = 1u << 8, c14 = 1u << 18, c28 = 1u << 4;     // 2^(32 - s) for the xor-shift distances 24 / 14 / 28
       const uint32_t grid = div_up(NU, HASH_THREADS);
-      if (hv == 1) SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<1><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28)));
-      else if (hv == 2) SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<2><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28)));
-      else SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<0><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28)));
+      if (hv == 1) SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<1><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28, scalar_k)));
+      else if (hv == 2) SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<2><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28, scalar_k)));
+      else SK_LAUNCH(ctx, "hashpass_kernel", (hashpass_kernel<0><<<grid, HASH_THREADS, 0, st>>>(P, NM, d_ucoarse.p, d_cuoff.p, d_clen.p, NU, seed_mask, thr, PM.p, c24, c14, c28, scalar_k)));
     }
     {   // record offset of every unit = exclusive scan of the pass-mask popcounts (no separate count array)
       auto cnt_it = thrust::make_transform_iterator((const uint32_t*)PM.p, PopcOp());

@@ -46,11 +46,12 @@ SK_HD uint32_t ascii_code(uint32_t b) {
 // Letters ACGTU in either case: code = ((b >> 1) ^ (b >> 2)) & 3 (A 0, C 1, G 2, T/U 3 = BYTE_TO_SEQ, src/types.rs:40-49).
 // The word takes the arithmetic path only if all four bytes are such letters (checked by rebuilding the expected
 // upper-case byte from the code); anything else (N, IUPAC, table rows 0..3, padding) goes through ascii_code per byte.
-SK_HD void pack_word(uint32_t x, uint32_t& code8, uint32_t& n4) {
+SK_HD void pack_word(uint32_t x, uint32_t& code8, uint32_t& n4, bool small_n = false) {
   const uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
   const uint32_t lo = t & 0x01010101u, hi = (t >> 1) & 0x01010101u, lh = lo & hi;
   const uint32_t expect = 0x41414141u + 2u * lo + 6u * hi + 11u * lh;     // 'A' 'C' 'G' 'T' per byte (no carries: max 0x54)
   const uint32_t u = x & 0xDFDFDFDFu;                                     // fold case
+  // (the scalar seeder also treats 'n' as a break, src/seeding.rs:273: with small_n the N-mask flags it; 'n' is never a valid letter)
   if ((((u ^ expect) & ~lh)) == 0u) {                                     // T/U differ in bit 0 only
     code8 = (t * 0x00041041u) >> 18 & 0xFFu;                              // gather the four 2-bit fields (disjoint partial products)
     n4 = 0;
@@ -59,9 +60,10 @@ SK_HD void pack_word(uint32_t x, uint32_t& code8, uint32_t& n4) {
   uint32_t c = 0, n = 0;
 #pragma unroll
   for (int b = 0; b < 4; b++) {
-    const uint32_t v = ascii_code((x >> (8 * b)) & 0xFFu);
+    const uint32_t byte = (x >> (8 * b)) & 0xFFu;
+    const uint32_t v = ascii_code(byte);
     c |= (v & 3u) << (2 * b);
-    n |= (v >> 2) << b;
+    n |= ((v >> 2) | ((small_n && byte == 110u) ? 1u : 0u)) << b;
   }
   code8 = c; n4 = n;
 }
@@ -152,6 +154,37 @@ SK_HD uint32_t unit_n_suppress_mask(uint32_t n, uint32_t ul, uint32_t nm_lo, uin
   return sup;
 }
 
+// ---- scalar seeding semantics (fmh_seeds, src/seeding.rs:225-323: what the reference runs on hosts WITHOUT AVX2) ----
+// one lane over the whole contig: every window end e with 20 <= e < n exists (no quarter-lane tail drop); n < 42 -> none
+SK_HD uint32_t unit_valid_mask_scalar(uint32_t n, uint32_t ul) {
+  if (n < 2 * MARKER_K) return 0;
+  const uint64_t e_lo = 20, e_hi = n;
+  const uint64_t b = 32ull * ul;
+  uint32_t m = 0xFFFFFFFFu;
+  if (b + 32 <= e_lo || b >= e_hi) return 0;
+  if (b < e_lo) m &= 0xFFFFFFFFu << (uint32_t)(e_lo - b);
+  if (b + 32 > e_hi) m &= 0xFFFFFFFFu >> (uint32_t)(b + 32 - e_hi);
+  return m;
+}
+// 'N' / 'n' at position p >= 20 sets resume_ind = p + k (src/seeding.rs:273-275): window e is suppressed iff such a byte lies in
+// [max(e - k + 1, 20), e].  The mask bits must flag 'N' AND 'n' (pack_word(..., small_n = true)).
+SK_HD uint32_t unit_n_suppress_mask_scalar(uint32_t ul, uint32_t k, uint32_t nm_lo, uint32_t nm_hi, uint32_t cand) {
+  const uint64_t nm = ((uint64_t)nm_hi << 32) | nm_lo;   // relative base r = p - 32*(ul-1), bit r
+  if (nm == 0 || cand == 0) return 0;
+  uint32_t sup = 0;
+  for (uint32_t j = 0; j < 32; j++) {
+    if (!((cand >> j) & 1u)) continue;
+    const int64_t e = 32ll * ul + j;
+    int64_t lb = e - (int64_t)k + 1;
+    if (lb < 20) lb = 20;
+    const int64_t base0 = 32ll * ((int64_t)ul - 1);
+    const uint32_t r_lo = (uint32_t)(lb - base0), r_hi = (uint32_t)(e - base0);   // e >= 20 and k <= 16: 17 <= r_lo <= r_hi <= 63
+    const uint64_t span = (((r_hi - r_lo == 63) ? ~0ull : ((1ull << (r_hi - r_lo + 1)) - 1)) << r_lo);
+    if (nm & span) sup |= 1u << j;
+  }
+  return sup;
+}
+
 }  // namespace sk
 
 namespace sk {
@@ -204,8 +237,9 @@ SK_HD uint64_t mm_hash64_mul(uint64_t key) {
 }
 
 SK_HD uint32_t unit_pass_mask_fast(uint64_t lo, uint64_t hi, uint32_t nm_lo, uint32_t nm_hi, uint32_t n, uint32_t ul,
-                                   uint32_t seed_mask32, uint64_t threshold) {
-  const uint32_t valid = unit_valid_mask(n, ul);
+                                   uint32_t seed_mask32, uint64_t threshold, uint32_t scalar_k = 0) {
+  // scalar_k != 0: scalar fmh_seeds semantics (src/seeding.rs:225-323) with that k; 0 = avx2_fmh_seeds (the default)
+  const uint32_t valid = scalar_k ? unit_valid_mask_scalar(n, ul) : unit_valid_mask(n, ul);
   if (valid == 0) return 0;
   const uint64_t clo = ~lo, chi = ~hi;
   const uint64_t tlo = pair_reverse64(hi), thi = pair_reverse64(lo);
@@ -224,7 +258,8 @@ SK_HD uint32_t unit_pass_mask_fast(uint64_t lo, uint64_t hi, uint32_t nm_lo, uin
     if (mm_hash64_mul((uint64_t)seed) < threshold) pass |= 1u << j;
   }
   pass &= valid;
-  if ((nm_lo | nm_hi) != 0 && pass != 0) pass &= ~unit_n_suppress_mask(n, ul, nm_lo, nm_hi, pass);
+  if ((nm_lo | nm_hi) != 0 && pass != 0)
+    pass &= ~(scalar_k ? unit_n_suppress_mask_scalar(ul, scalar_k, nm_lo, nm_hi, pass) : unit_n_suppress_mask(n, ul, nm_lo, nm_hi, pass));
   return pass;
 }
 

@@ -71,6 +71,7 @@ struct sk_ctx {
   cudaEvent_t x0[2] = {nullptr, nullptr}, x1[2] = {nullptr, nullptr};   // timing events around a sub-batch's H2D copies
   SkPool* pool = nullptr;
   int cpu_share = 1;                      // contexts of one process sharing the host cores (sk_triangle_multi)
+  bool seed_scalar = false;               // seed with the scalar fmh_seeds semantics (src/seeding.rs:225) instead of avx2_fmh_seeds
   double pack_rate = 0, h2d_rate = 0;     // measured: bases/s packed by the pool, bytes/s over PCIe (adapt the host-packed share)
   double last_pack_share = 0;             // share of the bases packed on the host in the last sk_sketch_batch (stats)
   // small host->device parameter uploads go through a pinned, device-mapped ring + a copy kernel on the context's

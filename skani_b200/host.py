@@ -54,6 +54,10 @@ class Context:
     def stream(self):
         return self.L.sk_ctx_stream(self.h)
 
+    def set_seeding_semantics(self, scalar=False):
+        """False = avx2_fmh_seeds (default, src/avx2_seeding.rs:33); True = scalar fmh_seeds (src/seeding.rs:225)."""
+        self.check(self.L.sk_ctx_set_seeding_semantics(self.h, 1 if scalar else 0))
+
     def set_timing(self, on=True):
         self.check(self.L.sk_ctx_set_timing(self.h, int(on)))
 

@@ -14,23 +14,32 @@
 using Rec = std::tuple<uint32_t, uint32_t, uint32_t>;  // kmer, pos, canon
 
 static void emu_seed(const std::vector<uint8_t>& s, uint32_t c, uint32_t k, uint32_t marker_c, std::vector<Rec>& recs,
-                     std::vector<uint64_t>& markers) {
+                     std::vector<uint64_t>& markers, bool scalar = false) {
   uint32_t n = (uint32_t)s.size();
   uint32_t nu = (n + 31) / 32;
   std::vector<uint64_t> P(nu, 0);
   std::vector<uint32_t> NM(nu, 0);
-  for (uint32_t i = 0; i < n; i++) {
-    uint32_t v = sk::ascii_code(s[i]);
-    P[i / 32] |= (uint64_t)(v & 3) << (2 * (i % 32));
-    NM[i / 32] |= (uint32_t)(v >> 2) << (i % 32);
+  for (uint32_t i = 0; i < n; i += 4) {   // through pack_word, as pack_kernel does (4 bytes at a time, zero padded)
+    uint32_t x = 0;
+    for (uint32_t b = 0; b < 4 && i + b < n; b++) x |= (uint32_t)s[i + b] << (8 * b);
+    uint32_t c8, n4;
+    sk::pack_word(x, c8, n4, scalar);
+    for (uint32_t b = 0; b < 4 && i + b < n; b++) {
+      P[(i + b) / 32] |= (uint64_t)((c8 >> (2 * b)) & 3) << (2 * ((i + b) % 32));
+      NM[(i + b) / 32] |= (uint32_t)((n4 >> b) & 1) << ((i + b) % 32);
+    }
   }
   uint64_t seed_mask = ~0ull >> (64 - 2 * k);
   uint64_t thr = ~0ull / c, thr_m = ~0ull / marker_c;
   for (uint32_t ul = 0; ul < nu; ul++) {
     uint64_t lo = ul ? P[ul - 1] : 0, hi = P[ul];
     uint32_t nlo = ul ? NM[ul - 1] : 0, nhi = NM[ul];
-    uint32_t pass = sk::unit_pass_mask(lo, hi, nlo, nhi, n, ul, seed_mask, thr);
-    if (pass != sk::unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, thr)) { fprintf(stderr, "fast/slow pass mask mismatch\n"); exit(2); }
+    uint32_t pass;
+    if (scalar) pass = sk::unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, thr, k);
+    else {
+      pass = sk::unit_pass_mask(lo, hi, nlo, nhi, n, ul, seed_mask, thr);
+      if (pass != sk::unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, thr)) { fprintf(stderr, "fast/slow pass mask mismatch\n"); exit(2); }
+    }
     sk::WindowCtx w = sk::make_window_ctx(lo, hi);
     for (uint32_t j = 0; j < 32; j++) {
       if (!((pass >> j) & 1)) continue;
@@ -46,10 +55,11 @@ static void emu_seed(const std::vector<uint8_t>& s, uint32_t c, uint32_t k, uint
 }
 
 static void oracle_seed(const std::vector<uint8_t>& s, uint32_t c, uint32_t k, uint32_t marker_c, std::vector<Rec>& recs,
-                        std::vector<uint64_t>& markers) {
+                        std::vector<uint64_t>& markers, bool scalar = false) {
   orc::SketchParams sp; sp.c = c; sp.k = k; sp.marker_c = marker_c;
   orc::Sketch sk;
-  orc::fmh_seeds_avx2sem(s.data(), s.size(), sp, 0, sk);
+  if (scalar) orc::fmh_seeds_scalar(s.data(), s.size(), sp, 0, sk);
+  else orc::fmh_seeds_avx2sem(s.data(), s.size(), sp, 0, sk);
   const orc::KmerSeeds& m = sk.kmer_seeds_k;
   orc::SeedPosition tmp;
   for (size_t i = 0; i < m.capacity(); i++) {
@@ -94,6 +104,16 @@ int main() {
       fails++;
       fprintf(stderr, "MISMATCH case %d n=%u c=%u k=%u flavour=%d: recs %zu vs %zu, markers %zu vs %zu\n", t, n, c, k, flavour,
               r1.size(), r2.size(), m1.size(), m2.size());
+    }
+    // scalar fmh_seeds semantics (src/seeding.rs:225-323): one lane, no tail drop, 'N' and 'n' suppress k windows
+    std::vector<Rec> s1, s2;
+    std::vector<uint64_t> n1, n2;
+    emu_seed(s, c, k, mc, s1, n1, true);
+    oracle_seed(s, c, k, mc, s2, n2, true);
+    if (s1 != s2 || n1 != n2) {
+      fails++;
+      fprintf(stderr, "SCALAR MISMATCH case %d n=%u c=%u k=%u flavour=%d: recs %zu vs %zu, markers %zu vs %zu\n", t, n, c, k, flavour,
+              s1.size(), s2.size(), n1.size(), n2.size());
     }
   }
   // table check: ascii_code vs BYTE_TO_SEQ for all 256 bytes

@@ -115,3 +115,27 @@ def test_hashpass_arithmetic_variants_bit_exact(ctx, monkeypatch, variant):
         gs = sk.sketch_sequences(ctx, [contigs[:12], contigs[12:30]], sk.sketch_params(c, k, mc))
         compare(gs, 0, O.sketch_from_contigs("a", contigs[:12], c=c, k=k, marker_c=mc))
         compare(gs, 1, O.sketch_from_contigs("b", contigs[12:30], c=c, k=k, marker_c=mc))
+
+
+def test_scalar_seeder_semantics_bit_exact(ctx):
+    """SK_SEED_SCALAR: the device reproduces seeding::fmh_seeds (src/seeding.rs:225-323, the path of hosts without AVX2):
+    single lane, no dropped tail windows, 'N' AND 'n' suppress the next k windows -- against the oracle's scalar seeder on the
+    edge-case set (which contains lowercase n, N runs, IUPAC codes, lengths 500..131k)."""
+    import skani_b200 as sk
+    rng = np.random.default_rng(4321)
+    contigs = parity_set(rng, 40)
+    contigs[3][100:110] = ord("n"); contigs[5][25:40] = ord("n"); contigs[7][-3:] = ord("n")
+    ctx.set_seeding_semantics(scalar=True)
+    try:
+        for c, k, mc in ((125, 15, 1000), (30, 15, 200), (10, 13, 40), (125, 16, 1000)):
+            genomes = [contigs[0:9], contigs[9:10], contigs[10:40]]
+            gs = sk.sketch_sequences(ctx, genomes, sk.sketch_params(c, k, mc))
+            for g, ctgs in enumerate(genomes):
+                compare(gs, g, O.sketch_from_contigs("g%d" % g, ctgs, c=c, k=k, marker_c=mc, avx2sem=False))
+        # and the two semantics really differ on this set
+        a = sk.sketch_sequences(ctx, [contigs[0:9]], sk.sketch_params()).export(0)
+        ctx.set_seeding_semantics(scalar=False)
+        b = sk.sketch_sequences(ctx, [contigs[0:9]], sk.sketch_params()).export(0)
+        assert len(a["kmer"]) != len(b["kmer"]) or not np.array_equal(a["pos"], b["pos"])
+    finally:
+        ctx.set_seeding_semantics(scalar=False)

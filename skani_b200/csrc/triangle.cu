@@ -87,6 +87,20 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
   // forces it for small inputs in tests).  Two things made it work: the context arena (no driver allocations in steady
   // state) and h2d_small (parameter uploads bypass the H2D copy engine that is saturated by the sequence upload);
   // see profiles/r01_pipeline_trace.txt.
+  // memory guard: the whole sketch set stays resident (records 22 B + k-mer tables <= 32 B per seed, markers 8 B each, plus the
+  // chaining workspace); refuse up front instead of failing half-way through a long run -- more genomes than one GPU holds
+  // go through sk_triangle_multi (blocks per GPU), SURVEY.md section 8 config 4
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const double need = (double)total_bytes / sp->c * 56.0 + (double)total_bytes / sp->marker_c * 24.0 + 6.0e9;
+      if (need > 0.92 * (double)total_b) {
+        ctx->err = "input too large for one GPU: ~" + std::to_string((uint64_t)(need / 1e9)) + " GB of sketches + workspace vs " +
+                   std::to_string((uint64_t)(total_b / 1e9)) + " GB of device memory; use sk_triangle_multi (triangle --gpus N)";
+        return SK_ERR_NOMEM;
+      }
+    }
+  }
   const bool pipelined = ((total_bytes >= (4ull << 30) && n_genomes >= 64) || (getenv("SK_FORCE_PIPELINE") && n_genomes >= 2)) &&
                          getenv("SK_NO_PIPELINE") == nullptr && n_contigs > 0;
   if (!pipelined) {

@@ -1,6 +1,8 @@
 // api.cu -- C ABI glue of libskani_b200.so: context, sketch-set lifecycle, host->device staging.
 #include <sched.h>
 
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -127,6 +129,44 @@ static int host_pack_threads(const sk_ctx* ctx) {
 SkPool* ctx_pool(sk_ctx* ctx) {
   if (!ctx->pool) ctx->pool = new SkPool(host_pack_threads(ctx));
   return ctx->pool;
+}
+
+// ---- sk_sketch_set_import_batch: device-side (contig, pos) ordering of imported records --------------------------------
+__global__ void import_keys_kernel(const uint64_t* __restrict__ rec_off, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ cc,
+                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t g = blockIdx.x;
+  const uint64_t b = rec_off[g], e = rec_off[g + 1];
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
+    keys[i] = ((uint64_t)(cc[i] >> 1) << 32) | pos[i];
+    vals[i] = (uint32_t)(i - b);
+  }
+}
+__global__ void import_gather_kernel(const uint64_t* __restrict__ rec_off, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ k,
+                                     const uint32_t* __restrict__ p, const uint32_t* __restrict__ c, uint32_t* __restrict__ ok,
+                                     uint32_t* __restrict__ op, uint32_t* __restrict__ oc) {
+  const uint32_t g = blockIdx.x;
+  const uint64_t b = rec_off[g], e = rec_off[g + 1];
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
+    const uint64_t src = b + perm[i];
+    ok[i] = k[src]; op[i] = p[src]; oc[i] = c[src];
+  }
+}
+// per contig (+ one sentinel per genome): local index of its first record = lower bound of (contig << 32) in the genome's sorted keys
+__global__ void import_ctab_kernel(const uint64_t* __restrict__ rec_off, const uint64_t* __restrict__ ctg_off, uint32_t G,
+                                   const uint64_t* __restrict__ skeys, uint32_t* __restrict__ ctab, uint32_t* __restrict__ bad) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;      // entry index in [0, C + G)
+  const uint64_t total = ctg_off[G] + G;
+  if (t >= total) return;
+  uint32_t lo = 0, hi = G;                                                 // genome g with ctg_off[g] + g <= t < ctg_off[g + 1] + g + 1
+  while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (ctg_off[m] + m <= t) lo = m; else hi = m; }
+  const uint32_t g = lo;
+  const uint32_t c = (uint32_t)(t - ctg_off[g] - g), nc = (uint32_t)(ctg_off[g + 1] - ctg_off[g]);
+  const uint64_t b = rec_off[g], e = rec_off[g + 1];
+  uint64_t a = b, z = e;
+  const uint64_t want = (uint64_t)c << 32;
+  while (a < z) { const uint64_t m = (a + z) >> 1; if (skeys[m] < want) a = m + 1; else z = m; }
+  ctab[t] = (uint32_t)(a - b);
+  if (c == nc && a != e) atomicExch(bad, 1u);                              // a record names a contig the sketch does not have
 }
 
 __global__ void stage_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n_words) {
@@ -1118,37 +1158,10 @@ int sk_sketch_set_import_batch(sk_ctx* ctx, const sk_sketch_params* sp, uint32_t
   sk_sketch_set* s = new sk_sketch_set();
   s->ctx = ctx; s->sp = *sp; s->G = G;
   struct Guard { sk_sketch_set* s; ~Guard() { if (s) { free_set_device(s); delete s; } } } guard{s};
-  // position view = each genome's records ordered by (contig, pos); per-contig first-record table with one sentinel per genome
-  std::vector<uint32_t> hk(n_records), hp(n_records), hc(n_records);
-  std::vector<uint32_t> crl(n_contigs + G + 1, 0);
-  std::vector<int> bad(G, 0);
-  auto do_genome = [&](uint32_t g) {
-    const uint64_t a = rec_off[g], e = rec_off[g + 1], n = e - a;
-    const uint32_t nc = (uint32_t)(ctg_off[g + 1] - ctg_off[g]);
-    std::vector<uint32_t> order(n);
-    for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
-    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-      const uint32_t cx = cc[a + x] >> 1, cy = cc[a + y] >> 1;
-      if (cx != cy) return cx < cy;
-      return pos[a + x] < pos[a + y];
-    });
-    uint32_t* tab = crl.data() + (ctg_off[g] - c0) + g;          // nc + 1 entries
-    for (uint64_t i = 0; i < n; i++) {
-      const uint64_t src = a + order[i], dst = a - r0 + i;
-      hk[dst] = kmer[src]; hp[dst] = pos[src]; hc[dst] = cc[src];
-      const uint32_t ctg = hc[dst] >> 1;
-      if (ctg >= nc) { bad[g] = 1; return; }
-      if (ctg + 1 < nc + 1) tab[ctg + 1]++;
-    }
-    for (uint32_t c = 0; c < nc; c++) tab[c + 1] += tab[c];
-  };
-  {
-    const unsigned T = std::max(1u, std::min(8u, std::min((unsigned)G, std::thread::hardware_concurrency())));
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < T; t++) pool.emplace_back([&, t] { for (uint32_t g = t; g < G; g += T) do_genome(g); });
-    for (auto& th : pool) th.join();
-  }
-  for (uint32_t g = 0; g < G; g++) if (bad[g]) { ctx->err = "record contig index out of range"; return SK_ERR_PARAM; }
+  // position view = each genome's records ordered by (contig, pos); per-contig first-record table with one sentinel per
+  // genome.  The records arrive in arbitrary (hash-map) order: they are sorted ON THE DEVICE (one segmented radix sort over
+  // all genomes of the batch), so that a database of tens of thousands of sketches imports at PCIe speed (src/search.rs
+  // deserialises and re-hashes per pair; here the host only concatenates)
   s->S = n_records; s->C = n_contigs;
   s->seed_off.resize(G + 1); s->ctg_off.resize(G + 1);
   for (uint32_t g = 0; g <= G; g++) { s->seed_off[g] = rec_off[g] - r0; s->ctg_off[g] = ctg_off[g] - c0; }
@@ -1167,14 +1180,43 @@ int sk_sketch_set_import_batch(sk_ctx* ctx, const sk_sketch_params* sp, uint32_t
   SK_CUDA(ctx->arena.alloc((void**)&s->pv_cc, S1 * 4));
   SK_CUDA(ctx->arena.alloc((void**)&s->d_ctg_len, std::max<size_t>(n_contigs, 1) * 4));
   SK_CUDA(ctx->arena.alloc((void**)&s->ctg_rec_off, (size_t)(n_contigs + G + 1) * 4));
-  SK_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (n_records) {
-    SK_CUDA(cudaMemcpy(s->pv_kmer, hk.data(), n_records * 4, cudaMemcpyHostToDevice));
-    SK_CUDA(cudaMemcpy(s->pv_pos, hp.data(), n_records * 4, cudaMemcpyHostToDevice));
-    SK_CUDA(cudaMemcpy(s->pv_cc, hc.data(), n_records * 4, cudaMemcpyHostToDevice));
+  cudaStream_t st = ctx->stream;
+  SK_CUDA(cudaStreamSynchronize(st));
+  if (n_contigs) SK_CUDA(cudaMemcpyAsync(s->d_ctg_len, contig_lengths + c0, n_contigs * 4, cudaMemcpyHostToDevice, st));
+  {
+    DTmp<uint64_t> d_ro, d_co;
+    SK_CUDA(d_ro.alloc(G + 1, ctx)); SK_CUDA(d_co.alloc(G + 1, ctx));
+    SK_CUDA(h2d_small(ctx, d_ro.p, s->seed_off.data(), (G + 1) * 8));
+    SK_CUDA(h2d_small(ctx, d_co.p, s->ctg_off.data(), (G + 1) * 8));
+    DTmp<uint32_t> d_bad;
+    SK_CUDA(d_bad.alloc(1, ctx));
+    SK_CUDA(cudaMemsetAsync(d_bad.p, 0, 4, st));
+    if (n_records) {
+      DTmp<uint32_t> rk, rp, rc, vals, perm;
+      DTmp<uint64_t> keys, skeys;
+      SK_CUDA(rk.alloc(n_records, ctx)); SK_CUDA(rp.alloc(n_records, ctx)); SK_CUDA(rc.alloc(n_records, ctx));
+      SK_CUDA(vals.alloc(n_records, ctx)); SK_CUDA(perm.alloc(n_records, ctx)); SK_CUDA(keys.alloc(n_records, ctx)); SK_CUDA(skeys.alloc(n_records, ctx));
+      SK_CUDA(cudaMemcpyAsync(rk.p, kmer + r0, n_records * 4, cudaMemcpyHostToDevice, st));
+      SK_CUDA(cudaMemcpyAsync(rp.p, pos + r0, n_records * 4, cudaMemcpyHostToDevice, st));
+      SK_CUDA(cudaMemcpyAsync(rc.p, cc + r0, n_records * 4, cudaMemcpyHostToDevice, st));
+      import_keys_kernel<<<dim3(G, 8), 256, 0, st>>>(d_ro.p, rp.p, rc.p, keys.p, vals.p); count_launch(ctx);
+      size_t tb = 0;
+      SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tb, keys.p, skeys.p, vals.p, perm.p, (int)n_records, (int)G, d_ro.p, d_ro.p + 1, 0, 62, st));
+      DTmp<uint8_t> tmp;
+      SK_CUDA(tmp.alloc(tb, ctx));
+      SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp.p, tb, keys.p, skeys.p, vals.p, perm.p, (int)n_records, (int)G, d_ro.p, d_ro.p + 1, 0, 62, st));
+      count_launch(ctx);
+      import_gather_kernel<<<dim3(G, 8), 256, 0, st>>>(d_ro.p, perm.p, rk.p, rp.p, rc.p, s->pv_kmer, s->pv_pos, s->pv_cc); count_launch(ctx);
+      import_ctab_kernel<<<(unsigned)((n_contigs + G + 255) / 256), 256, 0, st>>>(d_ro.p, d_co.p, G, skeys.p, s->ctg_rec_off, d_bad.p); count_launch(ctx);
+      SK_CUDA(cudaStreamSynchronize(st));
+    } else {
+      SK_CUDA(cudaMemsetAsync(s->ctg_rec_off, 0, (size_t)(n_contigs + G + 1) * 4, st));
+    }
+    uint32_t bad = 0;
+    SK_CUDA(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(cudaStreamSynchronize(st));
+    if (bad) { ctx->err = "record contig index out of range"; return SK_ERR_PARAM; }
   }
-  if (n_contigs) SK_CUDA(cudaMemcpy(s->d_ctg_len, contig_lengths + c0, n_contigs * 4, cudaMemcpyHostToDevice));
-  SK_CUDA(cudaMemcpy(s->ctg_rec_off, crl.data(), (size_t)(n_contigs + G) * 4, cudaMemcpyHostToDevice));
   DTmp<uint64_t> mraw;
   SK_CUDA(mraw.alloc(n_markers, ctx));
   if (n_markers) SK_CUDA(cudaMemcpy(mraw.p, markers + m0, n_markers * 8, cudaMemcpyHostToDevice));

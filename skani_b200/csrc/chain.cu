@@ -855,13 +855,22 @@ struct AccRec { uint32_t q0, q1, r0, r1, qctg, rctg; };
 
 __device__ __forceinline__ uint32_t sel_cell_hash(uint32_t ctg, uint32_t cell) { return (cell + ctg * 0x9E37u) & (SEL_MAP_BITS - 1); }
 
+constexpr uint32_t SEL_DEPS = 4;          // earlier overlapping candidates remembered per candidate (more -> full scan)
+
+// Greedy non-overlap selection (src/chain.rs:1016-1095) is inherently ordered: candidate i is accepted iff its summed overlap
+// with the ALREADY ACCEPTED intervals stays under half its length on both axes.  What is NOT ordered is finding out which
+// earlier candidates can overlap it at all: every thread does that for its own candidates in parallel (n^2 / 2 interval
+// tests per pair, shared-memory broadcasts), leaving a short dependency list per candidate; the ordered pass then only
+// looks at the kept flags of those few predecessors (a candidate with more than SEL_DEPS of them scans the accepted list).
 __global__ void __launch_bounds__(CT)
 select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws) {
-  __shared__ unsigned long long s_key[SEL_SMEM_MAX];
+  __shared__ __align__(8) unsigned long long s_key[SEL_SMEM_MAX];   // sort keys; afterwards the dependency lists (u16 x SEL_DEPS)
   __shared__ uint32_t s_idx[SEL_SMEM_MAX];
-  __shared__ AccRec s_cand[SEL_SMEM_MAX];       // candidates in sorted order (the greedy loop then never waits on global memory)
+  __shared__ AccRec s_cand[SEL_SMEM_MAX];       // candidates in sorted order
   __shared__ uint16_t s_accpos[SEL_SMEM_MAX];   // accepted candidates: their sorted positions
-  __shared__ uint32_t s_qmap[SEL_MAP_BITS / 32], s_rmap[SEL_MAP_BITS / 32];
+  __shared__ uint16_t s_cnt[SEL_SMEM_MAX];      // number of earlier candidates overlapping on either axis
+  __shared__ uint8_t s_kept[SEL_SMEM_MAX];
+  __shared__ uint32_t s_qmap[SEL_MAP_BITS / 32], s_rmap[SEL_MAP_BITS / 32];   // global-memory fallback only
   __shared__ uint32_t s_nacc;
   const unsigned FULL = 0xFFFFFFFFu;
   const uint32_t p = blockIdx.x;
@@ -894,24 +903,76 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
   }
   if (threadIdx.x == 0) s_nacc = 0;
   __syncthreads();
-  const uint32_t* order = ws.iv_order + 4 * ib + npow2;  // final sorted order lives after the sort scratch
-  // greedy selection by warp 0 (inherently ordered, src/chain.rs:1016-1095).  A 16 kb-cell occupancy bitmap per axis
-  // answers "cannot overlap anything accepted so far" in O(1); only candidates that touch an occupied cell scan the list.
   uint32_t* acc = ws.acc_list + ib;
-  if (threadIdx.x < 32) {
+  if (in_smem) {
+    // ---- parallel: which earlier candidates overlap candidate i on the ref or on the query axis
+    uint16_t* s_dep = (uint16_t*)s_key;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const AccRec c = s_cand[i];
+      uint32_t cnt = 0;
+      for (uint32_t j = 0; j < i; j++) {
+        const AccRec x = s_cand[j];
+        const bool ov = (x.rctg == c.rctg && x.r0 < c.r1 && c.r0 < x.r1) || (x.qctg == c.qctg && x.q0 < c.q1 && c.q0 < x.q1);
+        if (ov) { if (cnt < SEL_DEPS) s_dep[i * SEL_DEPS + cnt] = (uint16_t)j; cnt++; }
+      }
+      s_cnt[i] = (uint16_t)min(cnt, 0xFFFFu);
+    }
+    __syncthreads();
+    // ---- ordered pass, warp 0
+    if (threadIdx.x < 32) {
+      const uint32_t lane = threadIdx.x;
+      uint32_t nacc = 0;
+      for (uint32_t i = 0; i < n; i++) {
+        const uint32_t cnt = s_cnt[i];
+        bool ok = true;
+        if (cnt != 0) {   // uniform
+          const AccRec c = s_cand[i];
+          uint32_t sum_r = 0, sum_q = 0;
+          if (cnt <= SEL_DEPS) {
+            if (lane < cnt) {
+              const uint32_t j = s_dep[i * SEL_DEPS + lane];
+              if (s_kept[j]) {
+                const AccRec x = s_cand[j];
+                // half-open overlap (bio IntervalTree::find), contribution = min(c.end - a.start, a.end - c.start) (src/chain.rs:1023-1086)
+                if (x.rctg == c.rctg && x.r0 < c.r1 && c.r0 < x.r1) { const uint32_t u = c.r1 - x.r0, v = x.r1 - c.r0; sum_r = u < v ? u : v; }
+                if (x.qctg == c.qctg && x.q0 < c.q1 && c.q0 < x.q1) { const uint32_t u = c.q1 - x.q0, v = x.q1 - c.q0; sum_q = u < v ? u : v; }
+              }
+            }
+          } else {
+            for (uint32_t a = lane; a < nacc; a += 32) {
+              const AccRec x = s_cand[s_accpos[a]];
+              if (x.rctg == c.rctg && x.r0 < c.r1 && c.r0 < x.r1) { const uint32_t u = c.r1 - x.r0, v = x.r1 - c.r0; sum_r += u < v ? u : v; }
+              if (x.qctg == c.qctg && x.q0 < c.q1 && c.q0 < x.q1) { const uint32_t u = c.q1 - x.q0, v = x.q1 - c.q0; sum_q += u < v ? u : v; }
+            }
+          }
+          sum_r = __reduce_add_sync(FULL, sum_r);
+          sum_q = __reduce_add_sync(FULL, sum_q);
+          // an overlapping interval always contributes > 0, so "no hit" == "sum is 0" (src/chain.rs:1042, 1072: OVERLAP_ORTHOLOGOUS_FRACTION)
+          const bool ok_r = (sum_r == 0) || ((float)sum_r < (float)(c.r1 - c.r0) * 0.5f);
+          const bool ok_q = (sum_q == 0) || ((float)sum_q < (float)(c.q1 - c.q0) * 0.5f);
+          ok = ok_r && ok_q;
+        }
+        if (lane == 0) {
+          const uint32_t ci = s_idx[i];
+          s_kept[i] = ok ? 1 : 0;
+          ws.iv_kept[ib + ci] = ok ? 1 : 0;
+          if (ok) { acc[nacc] = ci; s_accpos[nacc] = (uint16_t)i; }
+        }
+        nacc += ok ? 1u : 0u;
+        __syncwarp();
+      }
+      if (lane == 0) s_nacc = nacc;
+    }
+  } else if (threadIdx.x < 32) {
+    // ---- more than SEL_SMEM_MAX intervals (huge / highly repetitive pairs): everything through global memory.  A 16 kb-cell
+    //      occupancy bitmap per axis answers "cannot overlap anything accepted so far" in O(1) for most candidates.
+    const uint32_t* order = ws.iv_order + 4 * ib + npow2;  // final sorted order lives after the sort scratch
     const uint32_t lane = threadIdx.x;
     uint32_t nacc = 0;
     for (uint32_t i = 0; i < n; i++) {
-      uint32_t ci, q0, q1, r0, r1, qc, rcg;
-      IntervalKey c;
-      if (in_smem) {
-        const AccRec x = s_cand[i];
-        ci = s_idx[i]; q0 = x.q0; q1 = x.q1; r0 = x.r0; r1 = x.r1; qc = x.qctg; rcg = x.rctg;
-      } else {
-        ci = order[i];
-        c = iv[ci];
-        q0 = iv_q0(c); q1 = iv_q1(c); r0 = iv_r0(c); r1 = iv_r1(c); qc = iv_qctg(c); rcg = iv_rctg(c);
-      }
+      const uint32_t ci = order[i];
+      const IntervalKey c = iv[ci];
+      const uint32_t q0 = iv_q0(c), q1 = iv_q1(c), r0 = iv_r0(c), r1 = iv_r1(c), qc = iv_qctg(c), rcg = iv_rctg(c);
       const uint32_t cq0 = q0 >> SEL_CELL_SHIFT, ncq = ((q1 - 1) >> SEL_CELL_SHIFT) - cq0 + 1;   // q0 < q1, r0 < r1 always
       const uint32_t cr0 = r0 >> SEL_CELL_SHIFT, ncr = ((r1 - 1) >> SEL_CELL_SHIFT) - cr0 + 1;
       bool need_scan = true;
@@ -925,26 +986,18 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
       if (need_scan) {
         uint32_t sum_r = 0, hit_r = 0, sum_q = 0, hit_q = 0;
         for (uint32_t a = lane; a < nacc; a += 32) {
-          AccRec x;
-          if (in_smem) x = s_cand[s_accpos[a]];
-          else { const IntervalKey y = iv[acc[a]]; x.q0 = iv_q0(y); x.q1 = iv_q1(y); x.r0 = iv_r0(y); x.r1 = iv_r1(y); x.qctg = iv_qctg(y); x.rctg = iv_rctg(y); }
-          // half-open overlap (bio IntervalTree::find), contribution = min(c.end - a.start, a.end - c.start) (src/chain.rs:1023-1086)
-          if (x.rctg == rcg && x.r0 < r1 && r0 < x.r1) { uint32_t u = r1 - x.r0, v = x.r1 - r0; sum_r += u < v ? u : v; hit_r = 1; }
-          if (x.qctg == qc && x.q0 < q1 && q0 < x.q1) { uint32_t u = q1 - x.q0, v = x.q1 - q0; sum_q += u < v ? u : v; hit_q = 1; }
+          uint32_t hr = 0, hq = 0;
+          overlap_contrib(c, iv[acc[a]], &sum_r, &hr, &sum_q, &hq);
+          hit_r |= hr ? 1u : 0u; hit_q |= hq ? 1u : 0u;
         }
         sum_r = __reduce_add_sync(FULL, sum_r);
         sum_q = __reduce_add_sync(FULL, sum_q);
         hit_r = __any_sync(FULL, hit_r) ? 1u : 0u;
         hit_q = __any_sync(FULL, hit_q) ? 1u : 0u;
-        const bool ok_r = (hit_r == 0) || ((float)sum_r < (float)(r1 - r0) * 0.5f);   // OVERLAP_ORTHOLOGOUS_FRACTION (:1042)
-        const bool ok_q = (hit_q == 0) || ((float)sum_q < (float)(q1 - q0) * 0.5f);   // (:1072)
-        ok = ok_r && ok_q;
+        ok = overlap_accept(c, sum_r, hit_r, sum_q, hit_q);
       }
       if (ok) {
-        if (lane == 0) {
-          acc[nacc] = ci;
-          if (in_smem) s_accpos[nacc] = (uint16_t)i;
-        }
+        if (lane == 0) acc[nacc] = ci;
         for (uint32_t t = lane; t < ncq; t += 32) { uint32_t h = sel_cell_hash(qc, cq0 + t); atomicOr(&s_qmap[h >> 5], 1u << (h & 31)); }
         for (uint32_t t = lane; t < ncr; t += 32) { uint32_t h = sel_cell_hash(rcg, cr0 + t); atomicOr(&s_rmap[h >> 5], 1u << (h & 31)); }
         nacc++;
@@ -981,86 +1034,118 @@ select_kernel(const PairDesc* __restrict__ pairs, ChainParams prm, Workspace ws)
 // K6: per-chunk identity, one WARP per chunk: the lanes stride over the chunk's query seeds (coalesced), the chunk's kept
 // intervals (1-3 as a rule) are read once into shared memory instead of being re-walked through global memory per seed
 // ------------------------------------------------------------------------------------------------------------
-constexpr int CS_WARPS = 8;        // warps (= chunks) per block
+constexpr int CS_WARPS = 8;        // warps per block
+constexpr int CS_PER_WARP = 4;     // chunks handled by one warp, one after the other (32 chunks per block)
 constexpr int CS_IV_MAX = 32;      // kept intervals of a chunk staged in shared memory; more are walked in global memory
+
+// first index in [a, b) with pos[idx] > key (b if none), searched by the whole warp: 32 probes per round instead of one
+__device__ __forceinline__ uint32_t warp_first_greater(const uint32_t* __restrict__ pos, uint32_t a, uint32_t b, int64_t key, uint32_t lane) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  while (b - a > 32) {
+    const uint32_t step = (b - a + 31) / 32;
+    const uint32_t seg_b = min(a + (lane + 1) * step, b);          // this lane's segment is [a + lane * step, seg_b)
+    const bool gt = (a + lane * step < b) && ((int64_t)pos[seg_b - 1] > key);
+    const uint32_t m = __ballot_sync(FULL, gt);
+    if (m == 0) return b;
+    const uint32_t L = __ffs(m) - 1;
+    const uint32_t na = a + L * step, nb = min(a + (L + 1) * step, b);
+    a = na; b = nb;                                                 // the first greater element lies in segment L
+  }
+  const bool gt = (a + lane < b) && ((int64_t)pos[a + lane] > key);
+  const uint32_t m = __ballot_sync(FULL, gt);
+  return m ? a + __ffs(m) - 1 : b;
+}
 
 __global__ void __launch_bounds__(CS_WARPS * 32)
 chunkstat_kernel(uint64_t n_chunks, const PairDesc* __restrict__ pairs, SetView s0, SetView s1,
                  const GenomeMeta* __restrict__ m0, const GenomeMeta* __restrict__ m1, ChainParams prm, Workspace ws) {
   __shared__ uint32_t s_start[CS_WARPS][CS_IV_MAX], s_stop[CS_WARPS][CS_IV_MAX];
+  __shared__ uint32_t s_nseeds[CS_WARPS * CS_PER_WARP], s_numin[CS_WARPS * CS_PER_WARP], s_ul[CS_WARPS * CS_PER_WARP];
   const unsigned FULL = 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  const uint64_t c = (uint64_t)blockIdx.x * CS_WARPS + w;
-  if (c >= n_chunks) return;
-  const uint32_t p = ws.chunk_pair[c];
-  const PairDesc pd = pairs[p];
-  const SetView& Q = pd.qset ? s1 : s0;
-  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
-  ChunkAcc acc;
-  acc.total_anchors = ws.acc_total[c]; acc.rq0 = ws.acc_rq0[c]; acc.rq1 = ws.acc_rq1[c];
-  acc.tbcq = ws.acc_tbcq[c]; acc.n_int = ws.acc_nint[c];
-  // seeds_in_chunk: counted query records of the chunk's contig with lo < pos <= hi (all lanes run the same searches)
-  const uint32_t ctg = ws.chunk_qctg[c];
-  const uint32_t* cro = Q.ctg_rec_off + qm.ctg_off + qm.g;
-  const uint32_t r0 = cro[ctg], r1 = cro[ctg + 1];
-  const uint32_t* pos = Q.pv_pos + qm.seed_off;
-  const int64_t lo = ws.chunk_lo[c], hi = ws.chunk_hi[c];
-  uint32_t a = r0, b = r1;
-  while (a < b) { uint32_t m = (a + b) >> 1; if ((int64_t)pos[m] <= lo) a = m + 1; else b = m; }   // first record with pos > lo
-  const uint32_t first = a;
-  b = r1;
-  while (a < b) { uint32_t m = (a + b) >> 1; if ((int64_t)pos[m] <= hi) a = m + 1; else b = m; }
-  const uint32_t last = a;  // [first, last)
-  const uint16_t* nhv = ws.rec_nh + pd.rec_off;
-  const uint64_t ib = ws.pairIbase[p];
-  const bool has_int = acc.n_int > 0;
-  // the chunk's kept intervals, padded by c on both sides (src/chain.rs:239-240), staged by lane 0
-  uint32_t n_iv = 0, more = 0xFFFFFFFFu;
-  if (has_int) {
-    if (lane == 0) {
-      uint32_t i = ws.chunk_head[c];
-      while (i != 0xFFFFFFFFu && n_iv < CS_IV_MAX) {
+  const uint64_t cblock = (uint64_t)blockIdx.x * (CS_WARPS * CS_PER_WARP);
+  for (int k = 0; k < CS_PER_WARP; k++) {
+    const uint32_t slot = w * CS_PER_WARP + k;
+    const uint64_t c = cblock + slot;
+    if (c >= n_chunks) break;                                  // warp-uniform
+    const uint32_t p = ws.chunk_pair[c];
+    const PairDesc pd = pairs[p];
+    const SetView& Q = pd.qset ? s1 : s0;
+    const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
+    const uint32_t n_int = ws.acc_nint[c], rq0 = ws.acc_rq0[c], rq1 = ws.acc_rq1[c];
+    // seeds_in_chunk: counted query records of the chunk's contig with lo < pos <= hi
+    const uint32_t ctg = ws.chunk_qctg[c];
+    const uint32_t* cro = Q.ctg_rec_off + qm.ctg_off + qm.g;
+    const uint32_t r0 = cro[ctg], r1 = cro[ctg + 1];
+    const uint32_t* pos = Q.pv_pos + qm.seed_off;
+    const int64_t lo = ws.chunk_lo[c], hi = ws.chunk_hi[c];
+    const uint32_t first = warp_first_greater(pos, r0, r1, lo, lane);
+    // a chunk spans <= 20 kb: its last seed is normally within a few hundred records of the first
+    uint32_t cap = min(r1, first + 1024u);
+    if (cap < r1 && (int64_t)pos[cap - 1] <= hi) cap = r1;
+    const uint32_t last = warp_first_greater(pos, first, cap, hi, lane);   // [first, last)
+    const uint16_t* nhv = ws.rec_nh + pd.rec_off;
+    const uint64_t ib = ws.pairIbase[p];
+    const bool has_int = n_int > 0;
+    // the chunk's kept intervals, padded by c on both sides (src/chain.rs:239-240), staged by lane 0
+    uint32_t n_iv = 0, more = 0xFFFFFFFFu;
+    __syncwarp();                                              // the previous chunk's readers of s_start / s_stop are done
+    if (has_int) {
+      if (lane == 0) {
+        uint32_t i = ws.chunk_head[c];
+        while (i != 0xFFFFFFFFu && n_iv < CS_IV_MAX) {
+          const IntervalKey x = ws.iv[ib + i];
+          const uint32_t q0 = iv_q0(x), q1 = iv_q1(x);
+          s_start[w][n_iv] = q0 > prm.c ? q0 - prm.c : 0;       // max(q0 - c, 0) in i32
+          s_stop[w][n_iv] = q1 + prm.c;
+          n_iv++;
+          i = ws.iv_next[ib + i];
+        }
+        more = i;                                               // rest of the list (beyond CS_IV_MAX), walked in global memory
+      }
+      n_iv = __shfl_sync(FULL, n_iv, 0);
+      more = __shfl_sync(FULL, more, 0);
+      __syncwarp();
+    }
+    uint32_t n_seeds = 0, num_in = 0, upper_lower = 0;
+    for (uint32_t t = first + lane; t < last; t += 32) {
+      if (!(nhv[t] & 0x8000u)) continue;
+      n_seeds++;
+      if (!has_int) continue;
+      const uint32_t ps = pos[t];
+      bool in = false;
+      for (uint32_t i = 0; i < n_iv; i++) if (s_start[w][i] <= ps && ps <= s_stop[w][i]) { in = true; break; }
+      for (uint32_t i = more; !in && i != 0xFFFFFFFFu; i = ws.iv_next[ib + i]) {
         const IntervalKey x = ws.iv[ib + i];
         const uint32_t q0 = iv_q0(x), q1 = iv_q1(x);
-        s_start[w][n_iv] = q0 > prm.c ? q0 - prm.c : 0;       // max(q0 - c, 0) in i32
-        s_stop[w][n_iv] = q1 + prm.c;
-        n_iv++;
-        i = ws.iv_next[ib + i];
+        if ((q0 > prm.c ? q0 - prm.c : 0) <= ps && ps <= q1 + prm.c) in = true;
       }
-      more = i;                                               // rest of the list (beyond CS_IV_MAX), walked in global memory
+      if (in) num_in++;
+      if (ps >= rq0 && ps <= rq1) upper_lower++;              // :322-328 with both spacing estimates 0
     }
-    n_iv = __shfl_sync(FULL, n_iv, 0);
-    more = __shfl_sync(FULL, more, 0);
-    __syncwarp();
+    n_seeds = __reduce_add_sync(FULL, n_seeds);
+    num_in = __reduce_add_sync(FULL, num_in);
+    upper_lower = __reduce_add_sync(FULL, upper_lower);
+    if (lane == 0) { s_nseeds[slot] = n_seeds; s_numin[slot] = num_in; s_ul[slot] = upper_lower; }
   }
-  uint32_t n_seeds = 0, num_in = 0, upper_lower = 0;
-  for (uint32_t t = first + lane; t < last; t += 32) {
-    if (!(nhv[t] & 0x8000u)) continue;
-    n_seeds++;
-    if (!has_int) continue;
-    const uint32_t ps = pos[t];
-    bool in = false;
-    for (uint32_t i = 0; i < n_iv; i++) if (s_start[w][i] <= ps && ps <= s_stop[w][i]) { in = true; break; }
-    for (uint32_t i = more; !in && i != 0xFFFFFFFFu; i = ws.iv_next[ib + i]) {
-      const IntervalKey x = ws.iv[ib + i];
-      const uint32_t q0 = iv_q0(x), q1 = iv_q1(x);
-      if ((q0 > prm.c ? q0 - prm.c : 0) <= ps && ps <= q1 + prm.c) in = true;
+  __syncthreads();
+  // the per-chunk identity (two pow() calls) for the block's 32 chunks in parallel lanes
+  if (threadIdx.x < CS_WARPS * CS_PER_WARP) {
+    const uint64_t c = cblock + threadIdx.x;
+    if (c < n_chunks) {
+      ChunkAcc acc;
+      acc.total_anchors = ws.acc_total[c]; acc.rq0 = ws.acc_rq0[c]; acc.rq1 = ws.acc_rq1[c];
+      acc.tbcq = ws.acc_tbcq[c]; acc.n_int = ws.acc_nint[c];
+      ws.chunk_nseeds[c] = s_nseeds[threadIdx.x];
+      double est; uint32_t wgt;
+      uint8_t valid = 0;
+      if (chunk_estimate(acc, prm.c, prm.k, s_nseeds[threadIdx.x], s_numin[threadIdx.x], s_ul[threadIdx.x], &est, &wgt)) {
+        ws.chunk_est[c] = est; ws.chunk_w[c] = wgt; valid = 1;
+        if (prm.c >= 200) atomicAdd(&ws.pair_tqb_ns[ws.chunk_pair[c]], acc.rq1 - acc.rq0 + 2 * prm.c + prm.k);  // !sensitive_af (:261-264)
+      }
+      ws.chunk_valid[c] = valid;
     }
-    if (in) num_in++;
-    if (ps >= acc.rq0 && ps <= acc.rq1) upper_lower++;      // :322-328 with both spacing estimates 0
   }
-  n_seeds = __reduce_add_sync(FULL, n_seeds);
-  num_in = __reduce_add_sync(FULL, num_in);
-  upper_lower = __reduce_add_sync(FULL, upper_lower);
-  if (lane != 0) return;
-  ws.chunk_nseeds[c] = n_seeds;
-  double est; uint32_t wgt;
-  uint8_t valid = 0;
-  if (chunk_estimate(acc, prm.c, prm.k, n_seeds, num_in, upper_lower, &est, &wgt)) {
-    ws.chunk_est[c] = est; ws.chunk_w[c] = wgt; valid = 1;
-    if (prm.c >= 200) atomicAdd(&ws.pair_tqb_ns[p], acc.rq1 - acc.rq0 + 2 * prm.c + prm.k);  // !sensitive_af (:261-264)
-  }
-  ws.chunk_valid[c] = valid;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1084,6 +1169,7 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
   __shared__ uint32_t s_n;
   __shared__ double s_boot[128];
   __shared__ double s_ci[2];
+  __shared__ uint16_t s_guide[260];
   __shared__ float s_term[200];
   __shared__ float s_x[5];
   __shared__ int s_do_reg;
@@ -1184,20 +1270,51 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
       for (uint32_t i = 0; i < n; i++) { run += gw[i]; cum[i] = run; }
     }
     __syncthreads();
-    if (threadIdx.x < 100) {
+    // guide table for the draws: bucket b = idx >> gshift (<= 256 buckets) -> first chunk i with cum[i] > (b << gshift); a draw then
+    // walks forward from there (1-2 steps) instead of a 8-12 step binary search per draw (100 x n draws per pair)
+    uint32_t gshift = 0;
+    while ((pool >> gshift) >= 256) gshift++;
+    const uint32_t nbuck = (uint32_t)(pool >> gshift) + 1;
+    for (uint32_t bk = threadIdx.x; bk < nbuck; bk += blockDim.x) {
+      const uint64_t lo = (uint64_t)bk << gshift;
+      uint32_t a = 0, b = n;
+      while (a < b) { uint32_t m = (a + b) >> 1; if (cum[m] <= lo) a = m + 1; else b = m; }
+      s_guide[bk] = (uint16_t)min(a, 0xFFFFu);
+    }
+    __syncthreads();
+    auto replicate = [&](const uint64_t* cumv, const double* gev) {
       const uint32_t rep = threadIdx.x;
       double ssum = 0.;
       bool rej = false;
       for (uint32_t s = 0; s < n; s++) {
         bool nr;
-        uint64_t idx = lemire_below(wyrand_at(7, (uint64_t)rep * n + s), pool, &nr);
+        const uint64_t idx = lemire_below(wyrand_at(7, (uint64_t)rep * n + s), pool, &nr);
         rej |= nr;
-        uint32_t a = 0, b = n;                           // first i with cum[i] > idx
-        while (a < b) { uint32_t m = (a + b) >> 1; if (cum[m] <= idx) a = m + 1; else b = m; }
-        ssum += ge[a];
+        uint32_t a = s_guide[(uint32_t)(idx >> gshift)];   // first i with cum[i] > idx
+        while (a + 1 < n && cumv[a] <= idx) a++;           // idx < pool = cum[n-1]: ends inside the array (bounded anyway)
+        ssum += gev[a];
       }
       s_boot[rep] = ssum / (double)n;
       if (rej) atomicOr(&s_reject, 1u);
+    };
+    if (threadIdx.x < 100) {
+      if (nc <= FIN_SMEM_MAX && n < 0xFFFFu) replicate(s_cum, s_e);   // shared-memory operands (LDS), the common case
+      else if (n < 0xFFFFu) replicate(cum, ge);
+      else {                                              // more than 65535 chunks: plain binary search
+        const uint32_t rep = threadIdx.x;
+        double ssum = 0.;
+        bool rej = false;
+        for (uint32_t s = 0; s < n; s++) {
+          bool nr;
+          uint64_t idx = lemire_below(wyrand_at(7, (uint64_t)rep * n + s), pool, &nr);
+          rej |= nr;
+          uint32_t a = 0, b = n;
+          while (a < b) { uint32_t m = (a + b) >> 1; if (cum[m] <= idx) a = m + 1; else b = m; }
+          ssum += ge[a];
+        }
+        s_boot[rep] = ssum / (double)n;
+        if (rej) atomicOr(&s_reject, 1u);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1506,7 +1623,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, true><<<grid, 32, 0, st>>>(TC, prm, ws)));       \
   else SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, false><<<grid, 32, 0, st>>>(TC, prm, ws)));
       if (prm.band <= 24 && getenv("SK_DP_WARP") == nullptr) {   // 4 chunks per warp, 8 lanes each
-        const int dp_gl = getenv("SK_DP_GL") ? atoi(getenv("SK_DP_GL")) : 8;   // lanes per chunk: 8 (default) or 4 (A/B, profiles/r02_*)
+        const int dp_gl = getenv("SK_DP_GL") ? atoi(getenv("SK_DP_GL")) : 4;   // lanes per chunk: 4 (default: 1.25x faster, profiles/r02_dp_lanes.md) or 8
         const uint32_t gw = dp_gl == 4 ? 8 : 4;
         const uint32_t g4 = (uint32_t)((TC + gw - 1) / gw);
         // group chunks of similar size: sort chunk ids by descending anchor count (cub radix sort, ~0.1 ms per batch)
@@ -1529,7 +1646,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
 #undef DP_LAUNCH
     }
     SK_LAUNCH(ctx, "select_kernel", (select_kernel<<<B, CT, 0, st>>>(S.d_pairs, prm, ws)));
-    SK_LAUNCH(ctx, "chunkstat_kernel", (chunkstat_kernel<<<(uint32_t)((TC + CS_WARPS - 1) / CS_WARPS), CS_WARPS * 32, 0, st>>>(TC, S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+    SK_LAUNCH(ctx, "chunkstat_kernel", (chunkstat_kernel<<<(uint32_t)((TC + CS_WARPS * CS_PER_WARP - 1) / (CS_WARPS * CS_PER_WARP)), CS_WARPS * 32, 0, st>>>(TC, S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
   }
   SK_LAUNCH(ctx, "final_kernel", (final_kernel<<<B, FT, 0, st>>>(S.d_pairs, S.d_m0, S.d_m1, prm, ws, S.d_out)));
   SK_CUDA(cudaMemcpyAsync(host_out + b0, S.d_out, B * sizeof(sk_ani_result), cudaMemcpyDeviceToHost, st));

@@ -92,11 +92,12 @@ def test_chain_debug_parity_synthetic(ctx, c, mc, learned):
         assert_debug_equal(gd, od)
 
 
-def test_chain_debug_parity_dp_four_lane_groups(ctx, monkeypatch):
-    """The banded DP with 4 lanes per chunk / 8 chunks per warp (SK_DP_GL=4, the A/B variant of dp_group_kernel) is held to
-    the same bit-exact per-anchor score / pointer / interval parity as the default 8-lane form."""
+@pytest.mark.parametrize("lanes", ["4", "8"])
+def test_chain_debug_parity_dp_lane_groups(ctx, monkeypatch, lanes):
+    """The banded DP with 4 lanes per chunk / 8 chunks per warp (the default since the A/B of profiles/r02_dp_lanes.md) and with 8
+    lanes / 4 chunks per warp (SK_DP_GL=8) are both held to bit-exact per-anchor score / pointer / interval parity."""
     import skani_b200 as sk
-    monkeypatch.setenv("SK_DP_GL", "4")
+    monkeypatch.setenv("SK_DP_GL", lanes)
     genomes = synth_genomes(8, 700_000, 4)
     for c in (125, 200):
         gs, osk = make_sets(ctx, genomes, dict(c=c, k=15, marker_c=1000))

@@ -206,8 +206,26 @@ __global__ void iota_local_kernel(const uint64_t* __restrict__ seg_off, uint32_t
   for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) vals[i] = (uint32_t)(i - b);
 }
 
-// after the per-genome sort by k-mer: gather the k-mer view and flag group heads
-__global__ void kview_gather_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ skmer,
+// sort keys of the k-mer view: (genome << kbits | k-mer), value = the record's index inside its genome.  ONE device-wide radix
+// sort of these keys orders every genome of the sub-batch by (kmer, contig, pos) at once (stable), instead of a segmented
+// sort that runs one block per genome and pass (5.5 % + 1.7 % of a step in profiles/r02_launches_bench_c2.md)
+__global__ void kview_keys_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ pv_kmer, uint32_t kbits,
+                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t g = blockIdx.x;
+  const uint64_t b = seg_off[g], e = seg_off[g + 1];
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
+    keys[i] = ((uint64_t)g << kbits) | pv_kmer[i];
+    vals[i] = (uint32_t)(i - b);
+  }
+}
+__global__ void marker_keys_kernel(const uint64_t* __restrict__ seg_off, uint64_t* __restrict__ mk) {   // in place: genome << 42 | marker
+  const uint32_t g = blockIdx.x;
+  const uint64_t b = seg_off[g], e = seg_off[g + 1];
+  for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) mk[i] |= (uint64_t)g << (2 * MARKER_K);
+}
+
+// after the sort by k-mer: gather the k-mer view and flag group heads
+__global__ void kview_gather_kernel(const uint64_t* __restrict__ seg_off, const uint64_t* __restrict__ skmer,
                                     const uint32_t* __restrict__ perm, const uint32_t* __restrict__ pv_pos,
                                     const uint32_t* __restrict__ pv_cc, uint32_t* __restrict__ kv_pos,
                                     uint32_t* __restrict__ kv_cc, uint32_t* __restrict__ head) {
@@ -223,7 +241,7 @@ __global__ void kview_gather_kernel(const uint64_t* __restrict__ seg_off, const 
 
 // hscan = exclusive scan of head flags (global).  Group id of sorted element i = hscan[i] + head[i] - 1 (global);
 // writes distinct k-mers and local group starts (+ one sentinel per genome), then multiplicities per pv record.
-__global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ skmer,
+__global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint64_t* __restrict__ skmer, uint64_t kmask,
                               const uint32_t* __restrict__ head, const uint32_t* __restrict__ hscan, uint32_t total_groups,
                               uint32_t n_genomes, uint32_t* __restrict__ ukmer, uint32_t* __restrict__ ustart) {
   uint32_t g = blockIdx.x;
@@ -231,7 +249,7 @@ __global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint32
   for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
     if (head[i]) {
       uint32_t gid = hscan[i];
-      ukmer[gid] = skmer[i];
+      ukmer[gid] = (uint32_t)(skmer[i] & kmask);
       ustart[gid + g] = (uint32_t)(i - b);
     }
   }
@@ -279,9 +297,9 @@ __global__ void marker_head_kernel(const uint64_t* __restrict__ seg_off, const u
   for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) head[i] = (i == b || mk[i] != mk[i - 1]) ? 1u : 0u;
 }
 __global__ void marker_compact_kernel(const uint64_t* __restrict__ mk, const uint32_t* __restrict__ head,
-                                      const uint32_t* __restrict__ hscan, uint32_t n, uint64_t* __restrict__ out) {
+                                      const uint32_t* __restrict__ hscan, uint32_t n, uint64_t mask, uint64_t* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && head[i]) out[hscan[i]] = mk[i];
+  if (i < n && head[i]) out[hscan[i]] = mk[i] & mask;
 }
 __global__ void gather_scan_at_kernel(const uint32_t* __restrict__ scan, const uint64_t* __restrict__ at, uint32_t n,
                                       uint64_t len, uint32_t total, uint64_t* __restrict__ out) {
@@ -371,7 +389,7 @@ int build_hash(sk_ctx* ctx, sk_sketch_set* set) {
   SK_CUDA(d_uk.alloc(G + 1, ctx)); SK_CUDA(d_ht.alloc(G + 1, ctx));
   SK_CUDA(h2d_small(ctx, d_uk.p, set->uk_off.data(), (G + 1) * 8));
   SK_CUDA(h2d_small(ctx, d_ht.p, set->ht_off.data(), (G + 1) * 8));
-  hash_build_kernel<<<dim3(G, 8), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab, 0); count_launch(ctx);
+  hash_build_kernel<<<dim3(G, 32), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab, 0); count_launch(ctx);
   SK_CUDA(cudaStreamSynchronize(st));
   return SK_OK;
 }
@@ -411,7 +429,7 @@ int build_hash_range(sk_ctx* ctx, sk_sketch_set* set, uint32_t g_begin) {
   SK_CUDA(d_uk.alloc(G + 1, ctx)); SK_CUDA(d_ht.alloc(G + 1, ctx));
   SK_CUDA(h2d_small(ctx, d_uk.p, set->uk_off.data(), (G + 1) * 8));
   SK_CUDA(h2d_small(ctx, d_ht.p, set->ht_off.data(), (G + 1) * 8));
-  hash_build_kernel<<<dim3(G - g_begin, 8), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab, g_begin); count_launch(ctx);
+  hash_build_kernel<<<dim3(G - g_begin, 32), 256, 0, st>>>(d_uk.p, d_ht.p, set->ukmer, set->ustart, set->htab, g_begin); count_launch(ctx);
   SK_CUDA(cudaStreamSynchronize(st));
   return SK_OK;
 }
@@ -431,18 +449,20 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
   set->uk_off.assign(G + 1, 0);
   if (S > 0) {
     if (S >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 seed records"; return SK_ERR_PARAM; }
-    DTmp<uint32_t> vals, skmer, perm, head, hscan;
-    SK_CUDA(vals.alloc(S, ctx)); SK_CUDA(skmer.alloc(S, ctx)); SK_CUDA(perm.alloc(S, ctx));
+    DTmp<uint32_t> vals, perm, head, hscan;
+    DTmp<uint64_t> keys, skmer;
+    SK_CUDA(vals.alloc(S, ctx)); SK_CUDA(keys.alloc(S, ctx)); SK_CUDA(skmer.alloc(S, ctx)); SK_CUDA(perm.alloc(S, ctx));
     SK_CUDA(head.alloc(S + 1, ctx)); SK_CUDA(hscan.alloc(S + 1, ctx));
-    iota_local_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, vals.p); count_launch(ctx);
+    const uint32_t kbits = std::min(32u, 2 * set->sp.k);
+    const uint32_t gbits = G > 1 ? 32 - (uint32_t)__builtin_clz(G - 1) : 0;     // bits of a genome index 0 .. G-1
+    const uint64_t kmask = (kbits >= 64) ? ~0ull : ((1ull << kbits) - 1);
+    kview_keys_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, set->pv_kmer, kbits, keys.p, vals.p); count_launch(ctx);
     size_t tb = 0;
-    int end_bit = std::min(32, (int)(2 * set->sp.k));
-    SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tb, set->pv_kmer, skmer.p, vals.p, perm.p, (int)S, (int)G,
-                                                     d_seed_off.p, d_seed_off.p + 1, 0, end_bit, st));
+    SK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, skmer.p, vals.p, perm.p, (int)S, 0, (int)(kbits + gbits), st));
     DTmp<uint8_t> tmp;
     SK_CUDA(tmp.alloc(tb, ctx));
-    SK_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp.p, tb, set->pv_kmer, skmer.p, vals.p, perm.p, (int)S, (int)G,
-                                                     d_seed_off.p, d_seed_off.p + 1, 0, end_bit, st));
+    SK_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, skmer.p, vals.p, perm.p, (int)S, 0, (int)(kbits + gbits), st));
+    count_launch(ctx);
     kview_gather_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, perm.p, set->pv_pos, set->pv_cc, set->kv_pos,
                                            set->kv_cc, head.p); count_launch(ctx);
     SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, S));
@@ -459,7 +479,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     set->U = U;
     SK_CUDA(ctx->arena.alloc((void**)&set->ukmer, std::max<size_t>(U, 1) * 4));
     SK_CUDA(ctx->arena.alloc((void**)&set->ustart, (size_t)(U + G) * 4));
-    groups_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, head.p, hscan.p, U, G, set->ukmer, set->ustart); count_launch(ctx);
+    groups_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, kmask, head.p, hscan.p, U, G, set->ukmer, set->ustart); count_launch(ctx);
     mult_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult); count_launch(ctx);
     SK_CUDA(cudaStreamSynchronize(st));
   } else {
@@ -478,12 +498,22 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     DTmp<uint64_t> sorted;
     SK_CUDA(sorted.alloc(MR, ctx));
     size_t tb = 0;
-    SK_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, d_marker_raw, sorted.p, (int)MR, (int)G, d_rawmk_off.p,
-                                                    d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
+    const uint32_t mgbits = G > 1 ? 32 - (uint32_t)__builtin_clz(G - 1) : 0;
+    const bool global_sort = 2 * MARKER_K + mgbits <= 64;      // one device-wide sort of (genome << 42 | marker); else per-genome segments
     DTmp<uint8_t> tmp;
-    SK_CUDA(tmp.alloc(tb, ctx));
-    SK_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(tmp.p, tb, d_marker_raw, sorted.p, (int)MR, (int)G, d_rawmk_off.p,
-                                                    d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
+    if (global_sort) {
+      marker_keys_kernel<<<dim3(G, 8), 256, 0, st>>>(d_rawmk_off.p, d_marker_raw); count_launch(ctx);
+      SK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_marker_raw, sorted.p, (int)MR, 0, (int)(2 * MARKER_K + mgbits), st));
+      SK_CUDA(tmp.alloc(tb, ctx));
+      SK_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, d_marker_raw, sorted.p, (int)MR, 0, (int)(2 * MARKER_K + mgbits), st));
+    } else {
+      SK_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, d_marker_raw, sorted.p, (int)MR, (int)G, d_rawmk_off.p,
+                                                      d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
+      SK_CUDA(tmp.alloc(tb, ctx));
+      SK_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(tmp.p, tb, d_marker_raw, sorted.p, (int)MR, (int)G, d_rawmk_off.p,
+                                                      d_rawmk_off.p + 1, 0, 2 * MARKER_K, st));
+    }
+    count_launch(ctx);
     DTmp<uint32_t> head, hscan;
     SK_CUDA(head.alloc(MR, ctx)); SK_CUDA(hscan.alloc(MR, ctx));
     marker_head_kernel<<<dim3(G, 8), 256, 0, st>>>(d_rawmk_off.p, sorted.p, head.p); count_launch(ctx);
@@ -495,7 +525,7 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     uint32_t M = lh + ls;
     set->M = M;
     SK_CUDA(ctx->arena.alloc((void**)&set->markers, std::max<size_t>(M, 1) * 8));
-    marker_compact_kernel<<<div_up(MR, 256), 256, 0, st>>>(sorted.p, head.p, hscan.p, (uint32_t)MR, set->markers); count_launch(ctx);
+    marker_compact_kernel<<<div_up(MR, 256), 256, 0, st>>>(sorted.p, head.p, hscan.p, (uint32_t)MR, global_sort ? ((1ull << (2 * MARKER_K)) - 1) : ~0ull, set->markers); count_launch(ctx);
     DTmp<uint64_t> d_mkoff;
     SK_CUDA(d_mkoff.alloc(G + 1, ctx));
     gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_rawmk_off.p, G + 1, MR, M, d_mkoff.p); count_launch(ctx);

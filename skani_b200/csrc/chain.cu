@@ -161,7 +161,7 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
   const uint32_t nuk = rm.n_uk;
   const bool use_hash = rm.ht_cap != 0;
   const unsigned long long* htab = R.htab + rm.ht_off;
-  const uint32_t ht_mask = rm.ht_cap - 1;
+  const uint32_t ht_mask = (rm.ht_cap >> 2) - 1;        // in 4-entry buckets
   if (STAGED && use_hash && rm.ht_cap <= PROBE_STAGE_ENTRIES) {   // block-uniform
     unsigned long long* s_tab = (unsigned long long*)s_bucket;
     if (threadIdx.x == 0) {
@@ -173,7 +173,7 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
     mbar_wait(&s_bar, 0);
     htab = s_tab;
   }
-  const uint32_t ht_shift = use_hash ? (32u - (uint32_t)__ffs((int)rm.ht_cap) + 1u) : 32u;
+  const uint32_t ht_shift = use_hash ? (32u - (uint32_t)__ffs((int)(rm.ht_cap >> 2)) + 1u) : 32u;   // 32 - log2(buckets); capacity >= 16 entries
   if (!use_hash) {  // fallback (genomes with >= 2^20 records): bucket index (16 KB) staged in shared memory
     const uint32_t* gb = R.ubucket + (size_t)rm.g * (UBUCKETS + 1);
     for (uint32_t b = threadIdx.x; b <= UBUCKETS; b += CT) s_bucket[b] = gb[b];
@@ -184,31 +184,48 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
     uint64_t item[ITEMS];
     uint32_t rst[ITEMS], nh[ITEMS];
     if (use_hash) {
-      // one 8-byte probe (plus rare linear-probing steps) per record; the ITEMS probes of a thread are independent
-      uint32_t kmer[ITEMS], hpos[ITEMS];
-      unsigned long long ent[ITEMS];
+      // one 32-byte BUCKET (4 entries = one memory sector) per record: a probe almost never needs a second access, so the
+      // lanes of a warp finish together (with one entry per step the warp waited for its longest probe chain, 3.4 steps on
+      // average: profiles/r02_ncu_full_r2a.md).  The ITEMS probes of a thread are independent.
+      uint32_t kmer[ITEMS], bidx[ITEMS];
+      ulonglong2 ea[ITEMS], eb[ITEMS];
       bool live[ITEMS];
+      const ulonglong2* __restrict__ tb2 = (const ulonglong2*)htab;
 #pragma unroll
       for (int it = 0; it < ITEMS; it++) {
         const uint32_t t = t0 + threadIdx.x * ITEMS + it;
-        live[it] = false; kmer[it] = 0; hpos[it] = 0; ent[it] = 0;
+        live[it] = false; kmer[it] = 0; bidx[it] = 0;
+        ea[it] = make_ulonglong2(0ull, 0ull); eb[it] = ea[it];
         if (t < qm.n_rec) {
           kmer[it] = Q.pv_kmer[qm.seed_off + t];
           live[it] = Q.pv_mult[qm.seed_off + t] <= prm.band;   // query positions > band: dropped entirely (src/chain.rs:676-678)
-          hpos[it] = (ht_shift >= 32) ? 0u : ((kmer[it] * 0x9E3779B1u) >> ht_shift);
+          bidx[it] = (kmer[it] * 0x9E3779B1u) >> ht_shift;
         }
       }
 #pragma unroll
-      for (int it = 0; it < ITEMS; it++) if (live[it]) ent[it] = STAGED ? htab[hpos[it]] : __ldg(htab + hpos[it]);
+      for (int it = 0; it < ITEMS; it++)
+        if (live[it]) {
+          if (STAGED) { ea[it] = tb2[2 * bidx[it]]; eb[it] = tb2[2 * bidx[it] + 1]; }
+          else { ea[it] = __ldg(tb2 + 2 * bidx[it]); eb[it] = __ldg(tb2 + 2 * bidx[it] + 1); }
+        }
 #pragma unroll
       for (int it = 0; it < ITEMS; it++) {
         const uint32_t t = t0 + threadIdx.x * ITEMS + it;
         nh[it] = 0; rst[it] = 0;
         uint32_t counted = 0;
         if (live[it]) {
-          unsigned long long e = ent[it];
-          uint32_t hp = hpos[it];
-          while (e != 0ull && (uint32_t)(e >> 32) != kmer[it]) { hp = (hp + 1) & ht_mask; e = STAGED ? htab[hp] : __ldg(htab + hp); }
+          unsigned long long e = 0ull;
+          uint32_t b = bidx[it];
+          ulonglong2 x = ea[it], y = eb[it];
+          for (;;) {
+            if ((uint32_t)(x.x >> 32) == kmer[it] && x.x != 0ull) { e = x.x; break; }
+            if ((uint32_t)(x.y >> 32) == kmer[it] && x.y != 0ull) { e = x.y; break; }
+            if ((uint32_t)(y.x >> 32) == kmer[it] && y.x != 0ull) { e = y.x; break; }
+            if ((uint32_t)(y.y >> 32) == kmer[it] && y.y != 0ull) { e = y.y; break; }
+            if (y.y == 0ull) break;                            // buckets fill front to back: an empty last slot ends the chain
+            b = (b + 1) & ht_mask;                             // full bucket without the key: the key may have spilled over
+            if (STAGED) { x = tb2[2 * b]; y = tb2[2 * b + 1]; } else { x = __ldg(tb2 + 2 * b); y = __ldg(tb2 + 2 * b + 1); }
+          }
           if (e != 0ull) {
             const uint32_t cntr = (uint32_t)e & 0xFFFu;        // saturated at 4095 > any band
             if (cntr <= prm.band) { counted = 1; nh[it] = cntr; rst[it] = (uint32_t)(e >> 12) & 0xFFFFFu; }  // else dropped (:695-697)

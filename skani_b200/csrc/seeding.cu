@@ -341,17 +341,25 @@ __global__ void hash_build_kernel(const uint64_t* __restrict__ uk_off, const uin
   const uint32_t g = g_base + blockIdx.x;
   const uint64_t cap = ht_off[g + 1] - ht_off[g];
   if (cap == 0) return;
-  const uint32_t mask = (uint32_t)cap - 1;
-  const uint32_t shift = 32 - (uint32_t)__ffsll((long long)cap) + 1;   // 32 - log2(cap)
+  const uint32_t nb = (uint32_t)(cap >> 2);                              // 4-entry (32-byte) buckets; cap is a power of two >= 16
+  const uint32_t bmask = nb - 1;
+  const uint32_t shift = 32 - (uint32_t)__ffs((int)nb) + 1;              // 32 - log2(nb)
   const uint32_t* uk = ukmer + uk_off[g];
   const uint32_t* us = ustart + uk_off[g] + g;
   unsigned long long* tab = htab + ht_off[g];
   const uint32_t n = (uint32_t)(uk_off[g + 1] - uk_off[g]);
   for (uint32_t u = blockIdx.y * blockDim.x + threadIdx.x; u < n; u += blockDim.x * gridDim.y) {
     const uint32_t key = uk[u], start = us[u], cntv = us[u + 1] - start;
+    // key 0 with start 0 and count 0 cannot occur (count >= 1), so a stored entry is never 0 = "empty"
     const unsigned long long e = ((unsigned long long)key << 32) | ((unsigned long long)start << 12) | (cntv < 4095u ? cntv : 4095u);
-    uint32_t hpos = (shift >= 32) ? 0u : ((key * 0x9E3779B1u) >> shift);
-    while (atomicCAS(&tab[hpos], 0ull, e) != 0ull) hpos = (hpos + 1) & mask;
+    uint32_t b = (key * 0x9E3779B1u) >> shift;
+    for (;;) {                      // first free slot of the bucket, front to back; a full bucket spills into the next one
+      bool done = false;
+#pragma unroll
+      for (int sl = 0; sl < 4 && !done; sl++) done = atomicCAS(&tab[4 * b + sl], 0ull, e) == 0ull;
+      if (done) break;
+      b = (b + 1) & bmask;
+    }
   }
 }
 

@@ -138,13 +138,17 @@ hashpass_kernel(const uint64_t* __restrict__ P, const uint32_t* __restrict__ NM,
                 uint32_t scalar_k) {
   uint32_t u = blockIdx.x * HASH_THREADS + threadIdx.x;
   if (u >= n_units) return;
-  uint32_t ci = contig_of_unit(ucoarse, cuoff, u);
-  uint32_t ul = u - cuoff[ci];
-  uint32_t n = clen[ci];
-  uint64_t hi = P[u];
-  uint64_t lo = ul ? P[u - 1] : 0ull;
-  uint32_t nhi = NM[u];
-  uint32_t nlo = ul ? NM[u - 1] : 0u;
+  // the unit loads do not wait for the contig lookup (ucoarse -> cuoff / clen is a two-level dependent chain): the previous
+  // unit is fetched unconditionally and dropped afterwards if this unit turns out to be the first of its contig
+  const uint64_t hi = P[u];
+  const uint64_t lo_raw = u ? P[u - 1] : 0ull;
+  const uint32_t nhi = NM[u];
+  const uint32_t nlo_raw = u ? NM[u - 1] : 0u;
+  const uint32_t ci = contig_of_unit(ucoarse, cuoff, u);
+  const uint32_t ul = u - cuoff[ci];
+  const uint32_t n = clen[ci];
+  const uint64_t lo = ul ? lo_raw : 0ull;
+  const uint32_t nlo = ul ? nlo_raw : 0u;
   if (V == 0) PM[u] = unit_pass_mask_fast(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold, scalar_k);
   else PM[u] = unit_pass_mask_var<V>(lo, hi, nlo, nhi, n, ul, (uint32_t)seed_mask, threshold, c24, c14, c28);
 }

@@ -70,11 +70,12 @@ struct ChainParams {
 // per-batch workspace (device pointers)
 struct Workspace {
   // per record of the query-role genome
-  uint32_t* rec_rstart;   // local start of the matching k-mer group in the ref-role k-mer view
   uint16_t* rec_nh;       // bits 0..14 = number of anchors, bit 15 = "counted" (enters seeds_in_chunk)
   // per hit record (compact, same slice offsets)
-  uint32_t *hit_rec, *hit_aoff;
-  uint32_t *hit_clfirst, *hit_need, *hit_p0, *hit_cid;  // hit_cid: pair-local chunk id of the first anchor; bit31 of hit_clfirst unused
+  uint4* hitA;            // x = record index t, y = pair-local offset of its first anchor, z = start of the matching group in the
+                          // ref-role k-mer view, w = number of anchors (written by probe_kernel: one 16-byte store per hit)
+  uint4* hitB;            // x = query pos, y = query contig << 1 | canonical, z = need, w = pair-local chunk id of the first anchor
+  uint32_t* hit_clfirst;  // contig-local chunk of the hit's first anchor (= need on the fast path)
   // per pair
   uint32_t *ctab_p0, *ctab_a0;           // per query contig: position / anchor offset of its first hit record
   uint32_t* pair_slow;                   // 1 = the pair needs the general (prefix-min) chunk assignment
@@ -234,7 +235,6 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
           }
         }
         if (t < qm.n_rec) {
-          ws.rec_rstart[pd.rec_off + t] = rst[it];
           ws.rec_nh[pd.rec_off + t] = (uint16_t)(nh[it] | (counted << 15));
         }
         item[it] = (uint64_t)nh[it] | ((uint64_t)(nh[it] ? 1u : 0u) << 32);
@@ -282,7 +282,6 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
         }
       }
       if (t < qm.n_rec) {
-        ws.rec_rstart[pd.rec_off + t] = rst[it];
         ws.rec_nh[pd.rec_off + t] = (uint16_t)(nh[it] | (counted << 15));
       }
       item[it] = (uint64_t)nh[it] | ((uint64_t)(nh[it] ? 1u : 0u) << 32);
@@ -296,8 +295,7 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
       if (nh[it]) {
         uint64_t pre = carry + item[it];
         uint32_t hidx = (uint32_t)(pre >> 32);
-        ws.hit_rec[pd.rec_off + hidx] = t0 + threadIdx.x * ITEMS + it;
-        ws.hit_aoff[pd.rec_off + hidx] = (uint32_t)pre;
+        ws.hitA[pd.rec_off + hidx] = make_uint4(t0 + threadIdx.x * ITEMS + it, (uint32_t)pre, rst[it], nh[it]);
       }
     }
     carry += agg;
@@ -331,27 +329,29 @@ chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, co
   uint32_t* __restrict__ ta0 = ws.ctab_a0 + pd.ctab_off;
   // phase A: the first hit record of every query contig publishes (P0, A0)
   for (uint32_t h = threadIdx.x; h < H; h += CT) {
-    const uint32_t t = ws.hit_rec[pd.rec_off + h];
+    const uint4 ha = ws.hitA[pd.rec_off + h];
+    const uint32_t t = ha.x;
     const uint32_t ctg = Q.pv_cc[qm.seed_off + t] >> 1;
     bool head = (h == 0);
-    if (!head) { const uint32_t tp = ws.hit_rec[pd.rec_off + h - 1]; head = (Q.pv_cc[qm.seed_off + tp] >> 1) != ctg; }
-    if (head) { tp0[ctg] = Q.pv_pos[qm.seed_off + t]; ta0[ctg] = ws.hit_aoff[pd.rec_off + h]; }
+    if (!head) { const uint32_t tp = ws.hitA[pd.rec_off + h - 1].x; head = (Q.pv_cc[qm.seed_off + tp] >> 1) != ctg; }
+    if (head) { tp0[ctg] = Q.pv_pos[qm.seed_off + t]; ta0[ctg] = ha.y; }
   }
   __threadfence_block();
   __syncthreads();
   // phase B: need per hit, chunk starts, chunk ids
   uint32_t carry_ctg = 0xFFFFFFFFu, carry_need = 0, carryC = 0, slow = 0;
   for (uint32_t h0 = 0; h0 < H; h0 += CT * ITEMS) {
-    uint32_t ctg[ITEMS], need[ITEMS], p0[ITEMS];
+    uint32_t ctg[ITEMS], need[ITEMS], qpos[ITEMS], qcc[ITEMS];
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
       const uint32_t h = h0 + threadIdx.x * ITEMS + it;
-      ctg[it] = 0xFFFFFFFFu; need[it] = 0; p0[it] = 0;
+      ctg[it] = 0xFFFFFFFFu; need[it] = 0; qpos[it] = 0; qcc[it] = 0;
       if (h < H) {
-        const uint32_t t = ws.hit_rec[pd.rec_off + h];
-        ctg[it] = Q.pv_cc[qm.seed_off + t] >> 1;
-        p0[it] = tp0[ctg[it]];
-        need[it] = chunk_need(Q.pv_pos[qm.seed_off + t], p0[it]);
+        const uint32_t t = ws.hitA[pd.rec_off + h].x;
+        qcc[it] = Q.pv_cc[qm.seed_off + t];
+        qpos[it] = Q.pv_pos[qm.seed_off + t];
+        ctg[it] = qcc[it] >> 1;
+        need[it] = chunk_need(qpos[it], tp0[ctg[it]]);
       }
     }
     __syncthreads();                       // sh_* of the previous tile fully consumed
@@ -381,9 +381,7 @@ chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, co
       const uint32_t h = h0 + threadIdx.x * ITEMS + it;
       if (h < H) {
         ws.hit_clfirst[pd.rec_off + h] = need[it];
-        ws.hit_need[pd.rec_off + h] = need[it];
-        ws.hit_p0[pd.rec_off + h] = p0[it];
-        ws.hit_cid[pd.rec_off + h] = carryC + ex[it] + st[it] - 1;
+        ws.hitB[pd.rec_off + h] = make_uint4(qpos[it], qcc[it], need[it], carryC + ex[it] + st[it] - 1);
       }
       if (h0 + threadIdx.x * ITEMS + it == h0 + last_h) { sh_ctg[0] = ctg[it]; sh_need[0] = need[it]; }  // written after the reads above (guarded by the next sync)
     }
@@ -421,19 +419,21 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
   uint32_t carry_ctg = 0xFFFFFFFFu, carry_cl = 0;  // contig / last chunk_local of the previous hit record
   uint32_t carryC = 0;                              // chunk starts so far
   for (uint32_t h0 = 0; h0 < H; h0 += CT * ITEMS) {
-    uint32_t ctg[ITEMS], pos[ITEMS], aoff[ITEMS], nh[ITEMS];
+    uint32_t ctg[ITEMS], pos[ITEMS], aoff[ITEMS], nh[ITEMS], qcc[ITEMS];
     FirstState fs[ITEMS];
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
       uint32_t h = h0 + threadIdx.x * ITEMS + it;
       fs[it].valid = 0; fs[it].ctg = 0; fs[it].p0 = 0; fs[it].a0 = 0;
-      ctg[it] = pos[it] = aoff[it] = nh[it] = 0;
+      ctg[it] = pos[it] = aoff[it] = nh[it] = qcc[it] = 0;
       if (h < H) {
-        uint32_t t = ws.hit_rec[pd.rec_off + h];
-        ctg[it] = Q.pv_cc[qm.seed_off + t] >> 1;
+        const uint4 ha = ws.hitA[pd.rec_off + h];
+        const uint32_t t = ha.x;
+        qcc[it] = Q.pv_cc[qm.seed_off + t];
+        ctg[it] = qcc[it] >> 1;
         pos[it] = Q.pv_pos[qm.seed_off + t];
-        aoff[it] = ws.hit_aoff[pd.rec_off + h];
-        nh[it] = ws.rec_nh[pd.rec_off + t] & 0x7FFFu;
+        aoff[it] = ha.y;
+        nh[it] = ha.w;
         fs[it].valid = 1; fs[it].ctg = ctg[it]; fs[it].p0 = pos[it]; fs[it].a0 = aoff[it];
       }
     }
@@ -507,9 +507,7 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
       uint32_t h = h0 + threadIdx.x * ITEMS + it;
       if (h < H) {
         ws.hit_clfirst[pd.rec_off + h] = clf[it];
-        ws.hit_need[pd.rec_off + h] = need[it];
-        ws.hit_p0[pd.rec_off + h] = fs[it].p0;
-        ws.hit_cid[pd.rec_off + h] = carryC + exu[it] + start0[it] - 1;  // chunk id of the hit's first anchor
+        ws.hitB[pd.rec_off + h] = make_uint4(pos[it], qcc[it], need[it], carryC + exu[it] + start0[it] - 1);  // w = chunk id of the hit's first anchor
       }
     }
     carryC += aggU;
@@ -528,29 +526,25 @@ anchor_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const 
   const PairDesc pd = pairs[p];
   const uint32_t H = ws.pairH[p];
   if (!pd.valid || H == 0) return;
-  const SetView& Q = pd.qset ? s1 : s0;
   const SetView& R = pd.rset ? s1 : s0;
-  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
   const GenomeMeta rm = (pd.rset ? m1 : m0)[pd.rg];
   const uint64_t abase = ws.pairAbase[p], cbase = ws.pairCbase[p];
+  const uint32_t* __restrict__ tp0 = ws.ctab_p0 + pd.ctab_off;     // per query contig: position of its first hit record
   for (uint32_t h = threadIdx.x; h < H; h += CT) {
-    uint32_t t = ws.hit_rec[pd.rec_off + h];
-    uint32_t nh = ws.rec_nh[pd.rec_off + t] & 0x7FFFu;
-    uint32_t rs = ws.rec_rstart[pd.rec_off + t];
-    uint32_t qpos = Q.pv_pos[qm.seed_off + t];
-    uint32_t qcc = Q.pv_cc[qm.seed_off + t];
-    uint32_t clf = ws.hit_clfirst[pd.rec_off + h], need = ws.hit_need[pd.rec_off + h], p0 = ws.hit_p0[pd.rec_off + h];
-    uint32_t cid = ws.hit_cid[pd.rec_off + h];
-    uint64_t x = abase + ws.hit_aoff[pd.rec_off + h];
-    // is the first anchor a chunk start?  (cid of the previous anchor differs)  recompute from neighbours' ids:
-    // the hit's first anchor starts a chunk iff h == 0 or hit_cid[h] != chunk id of the previous hit's last anchor
+    // everything about the hit comes from two 16-byte records (+ its contig-local first chunk): no dependent loads
+    const uint4 ha = ws.hitA[pd.rec_off + h], hb = ws.hitB[pd.rec_off + h];
+    const uint32_t nh = ha.w, rs = ha.z;
+    const uint32_t qpos = hb.x, qcc = hb.y, need = hb.z, cid = hb.w;
+    const uint32_t clf = ws.hit_clfirst[pd.rec_off + h];
+    const uint32_t p0 = tp0[qcc >> 1];
+    uint64_t x = abase + ha.y;
+    // the hit's first anchor starts a chunk iff h == 0 or its chunk id differs from that of the previous hit's last anchor
     uint32_t prev_last_cid = 0xFFFFFFFFu;
     if (h > 0) {
-      uint32_t tp = ws.hit_rec[pd.rec_off + h - 1];
-      uint32_t nhp = ws.rec_nh[pd.rec_off + tp] & 0x7FFFu;
-      uint32_t clfp = ws.hit_clfirst[pd.rec_off + h - 1], needp = ws.hit_need[pd.rec_off + h - 1];
-      uint32_t cllp = min(clfp + nhp - 1, needp);
-      prev_last_cid = ws.hit_cid[pd.rec_off + h - 1] + (cllp - clfp);
+      const uint4 pa = ws.hitA[pd.rec_off + h - 1], pb = ws.hitB[pd.rec_off + h - 1];
+      const uint32_t clfp = ws.hit_clfirst[pd.rec_off + h - 1];
+      const uint32_t cllp = min(clfp + pa.w - 1, pb.z);
+      prev_last_cid = pb.w + (cllp - clfp);
     }
     uint32_t prev_cid = prev_last_cid, prev_cl = 0;
     for (uint32_t u = 0; u < nh; u++) {
@@ -579,11 +573,10 @@ anchor_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const 
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t h = H - 1;
-    uint32_t t = ws.hit_rec[pd.rec_off + h];
-    uint32_t nh = ws.rec_nh[pd.rec_off + t] & 0x7FFFu;
-    uint32_t clf = ws.hit_clfirst[pd.rec_off + h], need = ws.hit_need[pd.rec_off + h];
-    uint32_t cll = min(clf + nh - 1, need);
-    ws.chunk_hi[cbase + ws.hit_cid[pd.rec_off + h] + (cll - clf)] = (int64_t)Q.pv_pos[qm.seed_off + t];
+    const uint4 ha = ws.hitA[pd.rec_off + h], hb = ws.hitB[pd.rec_off + h];
+    const uint32_t clf = ws.hit_clfirst[pd.rec_off + h];
+    const uint32_t cll = min(clf + ha.w - 1, hb.z);
+    ws.chunk_hi[cbase + hb.w + (cll - clf)] = (int64_t)hb.x;
   }
 }
 
@@ -1540,7 +1533,7 @@ static int ensure(sk_ctx* ctx, T** p, size_t* cap, size_t need) {
 struct ChainScratch {
   Workspace ws{};
   size_t cap_rec = 0, cap_pair = 0, cap_anc = 0, cap_chunk = 0, cap_iv = 0;
-  size_t c_rec_rstart = 0, c_rec_nh = 0, c_hit_rec = 0, c_hit_aoff = 0, c_hit_clfirst = 0, c_hit_need = 0, c_hit_p0 = 0, c_hit_cid = 0;
+  size_t c_rec_nh = 0, c_hitA = 0, c_hitB = 0, c_hit_clfirst = 0;
   size_t c_ctab_p0 = 0, c_ctab_a0 = 0, c_pair_slow = 0;
   size_t c_pairA = 0, c_pairH = 0, c_pairC = 0, c_pairAbase = 0, c_pairCbase = 0, c_pairIbase = 0, c_pair_nint = 0, c_pair_sumlen = 0,
          c_pair_nchains = 0, c_pair_tqb = 0;
@@ -1555,7 +1548,7 @@ struct ChainScratch {
   GenomeMeta *d_m0 = nullptr, *d_m1 = nullptr;
   size_t c_m0 = 0, c_m1 = 0;
   void free_all() {
-    void* ptrs[] = {ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, sort_tmp, ws.ctab_p0, ws.ctab_a0, ws.pair_slow, ws.rec_rstart, ws.rec_nh, ws.hit_rec, ws.hit_aoff, ws.hit_clfirst, ws.hit_need, ws.hit_p0, ws.hit_cid, ws.pairA, ws.pairH,
+    void* ptrs[] = {ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, sort_tmp, ws.ctab_p0, ws.ctab_a0, ws.pair_slow, ws.rec_nh, ws.hitA, ws.hitB, ws.hit_clfirst, ws.pairA, ws.pairH,
                     ws.pairC, ws.pairAbase, ws.pairCbase, ws.pairIbase, ws.pair_nint, ws.pair_sumlen, ws.pair_nchains, ws.pair_tqb_ns, ws.anc,
                     ws.score, ws.ptr, ws.rootkey, ws.depth, ws.chunk_first, ws.chunk_pair, ws.chunk_qctg, ws.chunk_lo, ws.chunk_hi,
                     ws.acc_total, ws.acc_rq0, ws.acc_rq1, ws.acc_tbcq, ws.acc_nint, ws.chunk_head, ws.chunk_est, ws.chunk_w, ws.chunk_valid,
@@ -1576,8 +1569,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   Workspace& ws = S.ws;
   const size_t NR = std::max<uint64_t>(total_rec, 1);
 #define ENS(field, capf, n) SK_TRY(ensure(ctx, &ws.field, &S.capf, n))
-  ENS(rec_rstart, c_rec_rstart, NR); ENS(rec_nh, c_rec_nh, NR); ENS(hit_rec, c_hit_rec, NR); ENS(hit_aoff, c_hit_aoff, NR);
-  ENS(hit_clfirst, c_hit_clfirst, NR); ENS(hit_need, c_hit_need, NR); ENS(hit_p0, c_hit_p0, NR); ENS(hit_cid, c_hit_cid, NR);
+  ENS(rec_nh, c_rec_nh, NR); ENS(hitA, c_hitA, NR); ENS(hitB, c_hitB, NR); ENS(hit_clfirst, c_hit_clfirst, NR);
   ENS(pairA, c_pairA, B); ENS(pairH, c_pairH, B); ENS(pairC, c_pairC, B); ENS(pairAbase, c_pairAbase, B + 1); ENS(pairCbase, c_pairCbase, B + 1);
   ENS(pairIbase, c_pairIbase, B + 1); ENS(pair_nint, c_pair_nint, B); ENS(pair_sumlen, c_pair_sumlen, B); ENS(pair_nchains, c_pair_nchains, B);
   ENS(pair_tqb_ns, c_pair_tqb, B); ENS(pair_slow, c_pair_slow, B);

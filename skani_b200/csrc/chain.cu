@@ -295,7 +295,11 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
       if (nh[it]) {
         uint64_t pre = carry + item[it];
         uint32_t hidx = (uint32_t)(pre >> 32);
-        ws.hitA[pd.rec_off + hidx] = make_uint4(t0 + threadIdx.x * ITEMS + it, (uint32_t)pre, rst[it], nh[it]);
+        const uint32_t t = t0 + threadIdx.x * ITEMS + it;
+        ws.hitA[pd.rec_off + hidx] = make_uint4(t, (uint32_t)pre, rst[it], nh[it]);
+        // query position / contig of the hit travel with it (z, w are filled by the chunk assignment): later kernels never
+        // gather from the position view again
+        ws.hitB[pd.rec_off + hidx] = make_uint4(Q.pv_pos[qm.seed_off + t], Q.pv_cc[qm.seed_off + t], 0u, 0u);
       }
     }
     carry += agg;
@@ -323,18 +327,15 @@ chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, co
     if (threadIdx.x == 0) ws.pairC[blockIdx.x] = 0;
     return;
   }
-  const SetView& Q = pd.qset ? s1 : s0;
-  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
   uint32_t* __restrict__ tp0 = ws.ctab_p0 + pd.ctab_off;
   uint32_t* __restrict__ ta0 = ws.ctab_a0 + pd.ctab_off;
   // phase A: the first hit record of every query contig publishes (P0, A0)
   for (uint32_t h = threadIdx.x; h < H; h += CT) {
-    const uint4 ha = ws.hitA[pd.rec_off + h];
-    const uint32_t t = ha.x;
-    const uint32_t ctg = Q.pv_cc[qm.seed_off + t] >> 1;
+    const uint4 hb = ws.hitB[pd.rec_off + h];
+    const uint32_t ctg = hb.y >> 1;
     bool head = (h == 0);
-    if (!head) { const uint32_t tp = ws.hitA[pd.rec_off + h - 1].x; head = (Q.pv_cc[qm.seed_off + tp] >> 1) != ctg; }
-    if (head) { tp0[ctg] = Q.pv_pos[qm.seed_off + t]; ta0[ctg] = ha.y; }
+    if (!head) head = (ws.hitB[pd.rec_off + h - 1].y >> 1) != ctg;
+    if (head) { tp0[ctg] = hb.x; ta0[ctg] = ws.hitA[pd.rec_off + h].y; }
   }
   __threadfence_block();
   __syncthreads();
@@ -347,9 +348,9 @@ chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, co
       const uint32_t h = h0 + threadIdx.x * ITEMS + it;
       ctg[it] = 0xFFFFFFFFu; need[it] = 0; qpos[it] = 0; qcc[it] = 0;
       if (h < H) {
-        const uint32_t t = ws.hitA[pd.rec_off + h].x;
-        qcc[it] = Q.pv_cc[qm.seed_off + t];
-        qpos[it] = Q.pv_pos[qm.seed_off + t];
+        const uint4 hb = ws.hitB[pd.rec_off + h];
+        qcc[it] = hb.y;
+        qpos[it] = hb.x;
         ctg[it] = qcc[it] >> 1;
         need[it] = chunk_need(qpos[it], tp0[ctg[it]]);
       }
@@ -412,8 +413,6 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
     if (threadIdx.x == 0) ws.pairC[blockIdx.x] = 0;
     return;
   }
-  const SetView& Q = pd.qset ? s1 : s0;
-  const GenomeMeta qm = (pd.qset ? m1 : m0)[pd.qg];
   FirstState carryF; carryF.valid = 0; carryF.ctg = 0; carryF.p0 = 0; carryF.a0 = 0;
   MinState carryM; carryM.valid = 0; carryM.ctg = 0; carryM.v = 0;
   uint32_t carry_ctg = 0xFFFFFFFFu, carry_cl = 0;  // contig / last chunk_local of the previous hit record
@@ -428,10 +427,10 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
       ctg[it] = pos[it] = aoff[it] = nh[it] = qcc[it] = 0;
       if (h < H) {
         const uint4 ha = ws.hitA[pd.rec_off + h];
-        const uint32_t t = ha.x;
-        qcc[it] = Q.pv_cc[qm.seed_off + t];
+        const uint4 hb = ws.hitB[pd.rec_off + h];
+        qcc[it] = hb.y;
         ctg[it] = qcc[it] >> 1;
-        pos[it] = Q.pv_pos[qm.seed_off + t];
+        pos[it] = hb.x;
         aoff[it] = ha.y;
         nh[it] = ha.w;
         fs[it].valid = 1; fs[it].ctg = ctg[it]; fs[it].p0 = pos[it]; fs[it].a0 = aoff[it];

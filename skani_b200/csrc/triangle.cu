@@ -143,7 +143,12 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
           pending_genomes += w.set->G;
         }
         done = w.last;
-        if (pending.empty() || (!done && pending_genomes < wave_genomes)) continue;
+        // wave size: n/8 while plenty is still to come, then half of what is left (down to n/64), so that the work that
+        // remains after the LAST upload -- one screen + the chains of the last wave -- is small (the pipeline's tail)
+        const uint32_t merged_g = merged ? merged->G : 0;
+        const uint32_t left = n_genomes - std::min(n_genomes, merged_g);          // genomes not merged yet (pending included)
+        const uint32_t threshold = std::max<uint32_t>(std::max<uint32_t>(1, n_genomes / 64), std::min(wave_genomes, left / 2));
+        if (pending.empty() || (!done && pending_genomes < threshold)) continue;
         if (worker_rc == SK_OK) {
           const double ta = now_s();
           // the merged set grows in place: only the new genomes are copied and only their k-mer tables are built

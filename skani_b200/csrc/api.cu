@@ -283,7 +283,10 @@ int concat_sets(sk_ctx* ctx, const std::vector<const sk_sketch_set*>& parts, sk_
 
 extern "C" {
 
-int sk_ctx_create(int device, sk_ctx** out) {
+// low_priority: the worker context of the pipelined sk_triangle.  Its chaining kernels share the GPU with the producer's
+// seeding kernels; the producer is on the critical path (upload -> seed must keep pace with PCIe), the chains only have to be
+// done by the end, so the producer's stream gets the higher hardware priority (its blocks are scheduled first)
+static int ctx_create_impl(int device, sk_ctx** out, bool low_priority) {
   if (!out) return SK_ERR_PARAM;
   *out = nullptr;
   int ndev = 0;
@@ -294,7 +297,9 @@ int sk_ctx_create(int device, sk_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return SK_ERR_CUDA; }
   ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  int prio_least = 0, prio_greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) != cudaSuccess) { prio_least = prio_greatest = 0; cudaGetLastError(); }
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, low_priority ? prio_least : prio_greatest) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SK_ERR_CUDA; }
   for (int i = 0; i < 2; i++) {
     cudaEventCreateWithFlags(&ctx->pinned_free[i], cudaEventDisableTiming);
@@ -309,6 +314,9 @@ int sk_ctx_create(int device, sk_ctx** out) {
   *out = ctx;
   return SK_OK;
 }
+
+int sk_ctx_create(int device, sk_ctx** out) { return ctx_create_impl(device, out, false); }
+int sk_ctx_create_worker(int device, sk_ctx** out) { return ctx_create_impl(device, out, true); }   // internal (triangle.cu)
 
 int sk_ctx_destroy(sk_ctx* ctx) {
   if (!ctx) return SK_OK;
@@ -849,6 +857,7 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
   bool abort_all = false;
   uint64_t bases_packed = 0, bases_total = 0;
   const bool trace = getenv("SK_TRACE") != nullptr;
+  const double t_call = wall_s();
   std::thread stager([&] {
     cudaSetDevice(ctx->device);
     std::vector<uint64_t> cu;           // unit offset of every contig of the part (+ total)
@@ -931,6 +940,7 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
         const double tp = wall_s() - tp0;
         if (tp > 1e-4 && pk_bases > (8u << 20)) ctx->pack_rate = 0.5 * ctx->pack_rate + 0.5 * ((double)pk_bases / tp);
       }
+      const double tp_end = wall_s();
       // staging of an unpinned ASCII tail
       const uint8_t* ascii_src = nullptr;
       const uint64_t ascii_bytes = prepacked ? 0 : (p.b1 - contig_off[p.c0 + np]);
@@ -976,8 +986,10 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
       xbytes[b] = wire;
       if ((e = cudaEventRecord(ctx->x1[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
       if ((e = cudaEventRecord(ctx->h2d_done[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
-      if (trace) fprintf(stderr, "[sk_sketch_batch] part %zu: %.0f%% of %.1f MB packed on the host (%d threads, %.1f GB/s; PCIe %.1f GB/s), %.1f MB on the wire\n",
-                         k, B ? 100.0 * pk_bases / B : 0.0, B / 1e6, pool->size(), ctx->pack_rate / 1e9, ctx->h2d_rate / 1e9, wire / 1e6);
+      if (trace) fprintf(stderr, "[sk_sketch_batch] part %zu: %.0f%% of %.1f MB packed on the host (%d threads, %.1f GB/s; PCIe %.1f GB/s), %.1f MB on the wire;"
+                         " pack %.1f..%.1f ms, copies queued at %.1f ms\n",
+                         k, B ? 100.0 * pk_bases / B : 0.0, B / 1e6, pool->size(), ctx->pack_rate / 1e9, ctx->h2d_rate / 1e9, wire / 1e6,
+                         (tp0 - t_call) * 1e3, (tp_end - t_call) * 1e3, (wall_s() - t_call) * 1e3);
       {
         std::lock_guard<std::mutex> lk(mu);
         enqueued = (long)k; bases_packed += pk_bases; bases_total += B;
@@ -1007,7 +1019,9 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
     SeedSrc src;
     src.d_ascii = ctx->dbuf[b]; src.ascii_base = p.b0; src.d_P = ctx->dP[b]; src.d_NM = ctx->dNM[b]; src.n_packed = n_packed[pi];
     sk_sketch_set* part = nullptr;
+    const double tc0 = wall_s();
     SK_TRY(sketch_batch_device(ctx, src, contig_off + p.c0, p.c1 - p.c0, gl.data(), p.g_end - p.g_begin, sp, &part));   // ends synchronised
+    if (trace) fprintf(stderr, "[sk_sketch_batch] part %zu seeded: %.1f..%.1f ms\n", pi, (tc0 - t_call) * 1e3, (wall_s() - t_call) * 1e3);
     { std::lock_guard<std::mutex> lk(mu); computed = (long)pi; }
     cv.notify_all();
     if (on_part) SK_TRY((*on_part)(part, p.g_begin, p.g_end));   // ownership moves to the callee

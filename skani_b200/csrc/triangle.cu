@@ -21,6 +21,8 @@
 
 #include "sk_internal.h"
 
+extern "C" int sk_ctx_create_worker(int device, sk_ctx** out);   // api.cu: a context whose stream has the LOWEST priority
+
 namespace {
 
 struct Wave { sk_sketch_set* set; uint32_t g_begin; bool last; };
@@ -111,7 +113,8 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
     //      handed to the worker.  Worker: once >= 1/8 of the genomes are pending (or the input is finished) it merges
     //      them into the set sketched so far, screens the merged set and chains the pairs whose larger index is new.
     if (!ctx->child) {
-      if (sk_ctx_create(ctx->device, &ctx->child) != SK_OK) { ctx->err = "cannot create the worker context"; return SK_ERR_CUDA; }
+      if (sk_ctx_create_worker(ctx->device, &ctx->child) != SK_OK) { ctx->err = "cannot create the worker context"; return SK_ERR_CUDA; }
+      ctx->child->seed_scalar = ctx->seed_scalar;
     }
     sk_ctx* wctx = ctx->child;
     const bool trace = getenv("SK_TRACE") != nullptr;

@@ -1178,7 +1178,7 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
   __shared__ uint32_t s_n;
   __shared__ double s_boot[128];
   __shared__ double s_ci[2];
-  __shared__ uint16_t s_guide[260];
+  __shared__ uint16_t s_guide[1028];
   __shared__ float s_term[200];
   __shared__ float s_x[5];
   __shared__ int s_do_reg;
@@ -1279,10 +1279,10 @@ final_kernel(const PairDesc* __restrict__ pairs, const GenomeMeta* __restrict__ 
       for (uint32_t i = 0; i < n; i++) { run += gw[i]; cum[i] = run; }
     }
     __syncthreads();
-    // guide table for the draws: bucket b = idx >> gshift (<= 256 buckets) -> first chunk i with cum[i] > (b << gshift); a draw then
-    // walks forward from there (1-2 steps) instead of a 8-12 step binary search per draw (100 x n draws per pair)
+    // guide table for the draws: bucket b = idx >> gshift (<= 1024 buckets) -> first chunk i with cum[i] > (b << gshift); a draw then
+    // walks forward from there (0-1 steps) instead of a 8-12 step binary search per draw (100 x n draws per pair)
     uint32_t gshift = 0;
-    while ((pool >> gshift) >= 256) gshift++;
+    while ((pool >> gshift) >= 1024) gshift++;
     const uint32_t nbuck = (uint32_t)(pool >> gshift) + 1;
     for (uint32_t bk = threadIdx.x; bk < nbuck; bk += blockDim.x) {
       const uint64_t lo = (uint64_t)bk << gshift;

@@ -226,8 +226,16 @@ SK_HD uint32_t funnel_r32(uint32_t lo, uint32_t hi, uint32_t sh) {  // low 32 bi
 // mm_hash64 with its shift-add steps written as multiplications (x + (x << s) == x * (2^s + 1) mod 2^64): on sm_100a
 // the 64-bit multiplies issue on the FMA pipe (IMAD) and relieve the ALU pipe (LOP3/SHF/IADD3) that bounds the kernel.
 SK_HD uint64_t mm_hash64_mul(uint64_t key) {
-  key = ~(key * 0x200001ull);
-  key = key ^ (key >> 24);
+  // steps 1 + 2, x = ~(key * 0x200001); x ^= x >> 24, with the complement folded into the xors (two LOP3 fewer per window):
+  //   low word : ~a ^ ~f == a ^ f                         (f = the funnel-shifted low word of the un-complemented product)
+  //   high word: ~b ^ ((~b) >> 24) == b ^ (b >> 24) ^ 0xFFFFFF00
+  {
+    const uint64_t k = key * 0x200001ull;
+    const uint32_t a = (uint32_t)k, b = (uint32_t)(k >> 32);
+    const uint32_t lo = a ^ funnel_r32(a, b, 24);
+    const uint32_t hi = b ^ (b >> 24) ^ 0xFFFFFF00u;
+    key = ((uint64_t)hi << 32) | lo;
+  }
   key = key * 265ull;
   key = key ^ (key >> 14);
   key = key * 21ull;

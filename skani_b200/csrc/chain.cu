@@ -702,12 +702,13 @@ dp_warp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
 // Lane gl of a group owns the anchors congruent to gl mod 8; register set s holds the anchor of block (current - s).
 // Group-wide arg-max = two 3-step xor-butterflies (max score, then largest j among the maxima).
 // ------------------------------------------------------------------------------------------------------------
-template <bool TAPS, int GL>
+template <bool TAPS, int GL, int NE>
 __global__ void __launch_bounds__(32)
 dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
   // GL lanes per chunk (8 or 4), 32 / GL chunks per warp.  Lane gl of a group owns the anchors congruent to gl mod GL;
-  // register set s holds the anchor of block (current - s); NB - 1 earlier blocks cover band <= 24.
-  constexpr int NB = 24 / GL + 1;
+  // register set s holds the anchor of block (current - s); a lane evaluates NE candidates per step, which covers every
+  // predecessor distance d <= GL * NE (band = 20 at c = 125: NE = 5 with 4 lanes, 3 with 8).
+  constexpr int NB = NE + 1;
   constexpr int LG = (GL == 8) ? 3 : 2;       // log2(GL)
   constexpr uint32_t GW = 32 / GL;            // chunks per warp
   const unsigned FULL = 0xFFFFFFFFu;
@@ -730,7 +731,9 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
   int32_t sc[NB];
   uint32_t my_ptr = 0;
 #pragma unroll
-  for (int s = 0; s < NB; s++) { q[s] = r[s] = rc[s] = rt[s] = dpth[s] = 0; sc[s] = 0; }
+  // register sets that have not been filled yet hold a contig no anchor can have (and one different from the filler of
+  // slots past the chunk end below), so "same contig and strand" alone rejects them: no `d <= i` / `i < n` tests per candidate
+  for (int s = 0; s < NB; s++) { q[s] = r[s] = rt[s] = dpth[s] = 0; rc[s] = 0xFFFFFFFCu; sc[s] = 0; }
   for (uint32_t b0 = 0; b0 < nmax; b0 += GL) {
 #pragma unroll
     for (int s = NB - 1; s > 0; s--) { q[s] = q[s - 1]; r[s] = r[s - 1]; rc[s] = rc[s - 1]; rt[s] = rt[s - 1]; dpth[s] = dpth[s - 1]; sc[s] = sc[s - 1]; }
@@ -750,7 +753,6 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
       cur.qpos = __shfl_sync(FULL, q[0], src);
       cur.rpos = __shfl_sync(FULL, r[0], src);
       cur.rc = __shfl_sync(FULL, rc[0], src);
-      const bool active = i < n;                                           // uniform inside a group
       int32_t best_ns = 0;
       uint32_t best_d = 0;                                                 // i - j of the lane's best candidate (0 = none)
       const bool lo_set = gl < m;
@@ -765,7 +767,7 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
         const uint32_t tr = cur.rpos - rs;
         const uint32_t dr = (cur.rc & 1u) ? (0u - tr) : tr;
         const uint32_t g = dr - dq;
-        const bool ok = active & (d <= band) & (d <= i) & (rcs == cur.rc) & (dq - 1u < BP_CHAIN_BAND) & (dr - 1u < (uint32_t)MAX_LIN) &
+        const bool ok = (d <= band) & (rcs == cur.rc) & (dq - 1u < BP_CHAIN_BAND) & (dr - 1u < (uint32_t)MAX_LIN) &
                         (g + (uint32_t)MAX_GAP <= 2u * (uint32_t)MAX_GAP);
         const int32_t gi = (int32_t)g;
         const int32_t ns = scs + ANCHOR_SCORE - (gi < 0 ? -gi : gi);
@@ -1642,13 +1644,14 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
         SK_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, (int)TC, 0, 32, st));
         SK_TRY(ensure(ctx, &S.sort_tmp, &S.c_sort_tmp, tb));
         SK_CUDA(cub::DeviceRadixSort::SortPairsDescending(S.sort_tmp, tb, ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, (int)TC, 0, 32, st));
-        if (dp_gl == 4) {
-          if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true, 4><<<g4, 32, 0, st>>>(TC, prm, ws)));
-          else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, 4><<<g4, 32, 0, st>>>(TC, prm, ws)));
-        } else {
-          if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true, 8><<<g4, 32, 0, st>>>(TC, prm, ws)));
-          else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, 8><<<g4, 32, 0, st>>>(TC, prm, ws)));
-        }
+#define DPG(GLV, NEV)                                                                                                   \
+  {                                                                                                                    \
+    if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true, GLV, NEV><<<g4, 32, 0, st>>>(TC, prm, ws)));           \
+    else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, GLV, NEV><<<g4, 32, 0, st>>>(TC, prm, ws)));              \
+  }
+        if (dp_gl == 4) { if (prm.band <= 20) DPG(4, 5) else DPG(4, 6) }
+        else { DPG(8, 3) }
+#undef DPG
       } else if (nb <= 2) { DP_LAUNCH(2) } else if (nb <= 4) { DP_LAUNCH(4) } else if (nb <= 8) { DP_LAUNCH(8) }
       else if (nb <= 16) { DP_LAUNCH(16) } else { ctx->err = "c too small: chain band > 479 anchors is not supported"; return SK_ERR_PARAM; }
 #undef DP_LAUNCH

@@ -99,7 +99,7 @@ def test_chain_debug_parity_dp_lane_groups(ctx, monkeypatch, lanes):
     import skani_b200 as sk
     monkeypatch.setenv("SK_DP_GL", lanes)
     genomes = synth_genomes(8, 700_000, 4)
-    for c in (125, 200):
+    for c in (125, 200, 110):          # band 20 / 12 (5 candidates per lane with 4 lanes), band 22 (6 candidates)
         gs, osk = make_sets(ctx, genomes, dict(c=c, k=15, marker_c=1000))
         for (r, q) in [(0, 1), (1, 3), (5, 6), (4, 7), (3, 3)]:
             assert_debug_equal(sk.chain_pair_debug(ctx, gs, gs, r, q, sk.map_params()), O.chain_debug(osk[r], osk[q], O.cmd()))

@@ -72,10 +72,12 @@ struct Workspace {
   // per record of the query-role genome
   uint16_t* rec_nh;       // bits 0..14 = number of anchors, bit 15 = "counted" (enters seeds_in_chunk)
   // per hit record (compact, same slice offsets)
-  uint4* hitA;            // x = record index t, y = pair-local offset of its first anchor, z = start of the matching group in the
-                          // ref-role k-mer view, w = number of anchors (written by probe_kernel: one 16-byte store per hit)
-  uint4* hitB;            // x = query pos, y = query contig << 1 | canonical, z = need, w = pair-local chunk id of the first anchor
-  uint32_t* hit_clfirst;  // contig-local chunk of the hit's first anchor (= need on the fast path)
+  // (structure of arrays: every kernel reads only the fields it needs, all accesses coalesced over the hit index)
+  uint32_t *h_qpos, *h_qcc;   // query position, query contig << 1 | canonical            (probe_kernel)
+  uint32_t *h_aoff, *h_rs;    // pair-local offset of the hit's first anchor (the anchor count of hit h is h_aoff[h+1] - h_aoff[h],
+                              // pairA - h_aoff[h] for the last one); start of the matching group in the ref-role k-mer view
+  uint32_t *h_need, *h_cid;   // contig-local chunk `need` of the hit's position, pair-local chunk id of its first anchor (chunk kernels)
+  uint32_t* hit_clfirst;      // contig-local chunk of the hit's first anchor: written by the general chunk kernel only (= need on the fast path)
   // per pair
   uint32_t *ctab_p0, *ctab_a0;           // per query contig: position / anchor offset of its first hit record
   uint32_t* pair_slow;                   // 1 = the pair needs the general (prefix-min) chunk assignment
@@ -296,10 +298,11 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
         uint64_t pre = carry + item[it];
         uint32_t hidx = (uint32_t)(pre >> 32);
         const uint32_t t = t0 + threadIdx.x * ITEMS + it;
-        ws.hitA[pd.rec_off + hidx] = make_uint4(t, (uint32_t)pre, rst[it], nh[it]);
-        // query position / contig of the hit travel with it (z, w are filled by the chunk assignment): later kernels never
-        // gather from the position view again
-        ws.hitB[pd.rec_off + hidx] = make_uint4(Q.pv_pos[qm.seed_off + t], Q.pv_cc[qm.seed_off + t], 0u, 0u);
+        // query position / contig of the hit travel with it: later kernels never gather from the position view again
+        ws.h_aoff[pd.rec_off + hidx] = (uint32_t)pre;
+        ws.h_rs[pd.rec_off + hidx] = rst[it];
+        ws.h_qpos[pd.rec_off + hidx] = Q.pv_pos[qm.seed_off + t];
+        ws.h_qcc[pd.rec_off + hidx] = Q.pv_cc[qm.seed_off + t];
       }
     }
     carry += agg;
@@ -331,11 +334,10 @@ chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, co
   uint32_t* __restrict__ ta0 = ws.ctab_a0 + pd.ctab_off;
   // phase A: the first hit record of every query contig publishes (P0, A0)
   for (uint32_t h = threadIdx.x; h < H; h += CT) {
-    const uint4 hb = ws.hitB[pd.rec_off + h];
-    const uint32_t ctg = hb.y >> 1;
+    const uint32_t ctg = ws.h_qcc[pd.rec_off + h] >> 1;
     bool head = (h == 0);
-    if (!head) head = (ws.hitB[pd.rec_off + h - 1].y >> 1) != ctg;
-    if (head) { tp0[ctg] = hb.x; ta0[ctg] = ws.hitA[pd.rec_off + h].y; }
+    if (!head) head = (ws.h_qcc[pd.rec_off + h - 1] >> 1) != ctg;
+    if (head) { tp0[ctg] = ws.h_qpos[pd.rec_off + h]; ta0[ctg] = ws.h_aoff[pd.rec_off + h]; }
   }
   __threadfence_block();
   __syncthreads();
@@ -348,9 +350,8 @@ chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, co
       const uint32_t h = h0 + threadIdx.x * ITEMS + it;
       ctg[it] = 0xFFFFFFFFu; need[it] = 0; qpos[it] = 0; qcc[it] = 0;
       if (h < H) {
-        const uint4 hb = ws.hitB[pd.rec_off + h];
-        qcc[it] = hb.y;
-        qpos[it] = hb.x;
+        qcc[it] = ws.h_qcc[pd.rec_off + h];
+        qpos[it] = ws.h_qpos[pd.rec_off + h];
         ctg[it] = qcc[it] >> 1;
         need[it] = chunk_need(qpos[it], tp0[ctg[it]]);
       }
@@ -381,8 +382,8 @@ chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, co
     for (int it = 0; it < ITEMS; it++) {
       const uint32_t h = h0 + threadIdx.x * ITEMS + it;
       if (h < H) {
-        ws.hit_clfirst[pd.rec_off + h] = need[it];
-        ws.hitB[pd.rec_off + h] = make_uint4(qpos[it], qcc[it], need[it], carryC + ex[it] + st[it] - 1);
+        ws.h_need[pd.rec_off + h] = need[it];
+        ws.h_cid[pd.rec_off + h] = carryC + ex[it] + st[it] - 1;
       }
       if (h0 + threadIdx.x * ITEMS + it == h0 + last_h) { sh_ctg[0] = ctg[it]; sh_need[0] = need[it]; }  // written after the reads above (guarded by the next sync)
     }
@@ -408,6 +409,7 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
   __shared__ uint32_t sh_ctg[CT], sh_cl[CT];
   const PairDesc pd = pairs[blockIdx.x];
   const uint32_t H = ws.pairH[blockIdx.x];
+  const uint32_t A_total = ws.pairA[blockIdx.x];
   if (!ws.pair_slow[blockIdx.x]) return;      // the fast path already produced this pair's chunks
   if (!pd.valid || H == 0) {
     if (threadIdx.x == 0) ws.pairC[blockIdx.x] = 0;
@@ -426,13 +428,11 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
       fs[it].valid = 0; fs[it].ctg = 0; fs[it].p0 = 0; fs[it].a0 = 0;
       ctg[it] = pos[it] = aoff[it] = nh[it] = qcc[it] = 0;
       if (h < H) {
-        const uint4 ha = ws.hitA[pd.rec_off + h];
-        const uint4 hb = ws.hitB[pd.rec_off + h];
-        qcc[it] = hb.y;
+        qcc[it] = ws.h_qcc[pd.rec_off + h];
         ctg[it] = qcc[it] >> 1;
-        pos[it] = hb.x;
-        aoff[it] = ha.y;
-        nh[it] = ha.w;
+        pos[it] = ws.h_qpos[pd.rec_off + h];
+        aoff[it] = ws.h_aoff[pd.rec_off + h];
+        nh[it] = (h + 1 < H ? ws.h_aoff[pd.rec_off + h + 1] : A_total) - aoff[it];
         fs[it].valid = 1; fs[it].ctg = ctg[it]; fs[it].p0 = pos[it]; fs[it].a0 = aoff[it];
       }
     }
@@ -506,7 +506,8 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
       uint32_t h = h0 + threadIdx.x * ITEMS + it;
       if (h < H) {
         ws.hit_clfirst[pd.rec_off + h] = clf[it];
-        ws.hitB[pd.rec_off + h] = make_uint4(pos[it], qcc[it], need[it], carryC + exu[it] + start0[it] - 1);  // w = chunk id of the hit's first anchor
+        ws.h_need[pd.rec_off + h] = need[it];
+        ws.h_cid[pd.rec_off + h] = carryC + exu[it] + start0[it] - 1;   // chunk id of the hit's first anchor
       }
     }
     carryC += aggU;
@@ -528,22 +529,26 @@ anchor_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const 
   const SetView& R = pd.rset ? s1 : s0;
   const GenomeMeta rm = (pd.rset ? m1 : m0)[pd.rg];
   const uint64_t abase = ws.pairAbase[p], cbase = ws.pairCbase[p];
+  const uint32_t A_total = ws.pairA[p];
+  const bool slow = ws.pair_slow[p] != 0;                            // general chunk assignment: the first chunk of a hit may lag behind `need`
   const uint32_t* __restrict__ tp0 = ws.ctab_p0 + pd.ctab_off;     // per query contig: position of its first hit record
+  const uint64_t o = pd.rec_off;
   for (uint32_t h = threadIdx.x; h < H; h += CT) {
-    // everything about the hit comes from two 16-byte records (+ its contig-local first chunk): no dependent loads
-    const uint4 ha = ws.hitA[pd.rec_off + h], hb = ws.hitB[pd.rec_off + h];
-    const uint32_t nh = ha.w, rs = ha.z;
-    const uint32_t qpos = hb.x, qcc = hb.y, need = hb.z, cid = hb.w;
-    const uint32_t clf = ws.hit_clfirst[pd.rec_off + h];
+    // everything about the hit comes from coalesced per-hit arrays: no dependent loads
+    const uint32_t aoff = ws.h_aoff[o + h], rs = ws.h_rs[o + h];
+    const uint32_t nh = (h + 1 < H ? ws.h_aoff[o + h + 1] : A_total) - aoff;
+    const uint32_t qpos = ws.h_qpos[o + h], qcc = ws.h_qcc[o + h], need = ws.h_need[o + h], cid = ws.h_cid[o + h];
+    const uint32_t clf = slow ? ws.hit_clfirst[o + h] : need;
     const uint32_t p0 = tp0[qcc >> 1];
-    uint64_t x = abase + ha.y;
+    uint64_t x = abase + aoff;
     // the hit's first anchor starts a chunk iff h == 0 or its chunk id differs from that of the previous hit's last anchor
     uint32_t prev_last_cid = 0xFFFFFFFFu;
     if (h > 0) {
-      const uint4 pa = ws.hitA[pd.rec_off + h - 1], pb = ws.hitB[pd.rec_off + h - 1];
-      const uint32_t clfp = ws.hit_clfirst[pd.rec_off + h - 1];
-      const uint32_t cllp = min(clfp + pa.w - 1, pb.z);
-      prev_last_cid = pb.w + (cllp - clfp);
+      const uint32_t needp = ws.h_need[o + h - 1];
+      const uint32_t clfp = slow ? ws.hit_clfirst[o + h - 1] : needp;
+      const uint32_t nhp = aoff - ws.h_aoff[o + h - 1];
+      const uint32_t cllp = min(clfp + nhp - 1, needp);
+      prev_last_cid = ws.h_cid[o + h - 1] + (cllp - clfp);
     }
     uint32_t prev_cid = prev_last_cid, prev_cl = 0;
     for (uint32_t u = 0; u < nh; u++) {
@@ -572,10 +577,10 @@ anchor_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const 
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t h = H - 1;
-    const uint4 ha = ws.hitA[pd.rec_off + h], hb = ws.hitB[pd.rec_off + h];
-    const uint32_t clf = ws.hit_clfirst[pd.rec_off + h];
-    const uint32_t cll = min(clf + ha.w - 1, hb.z);
-    ws.chunk_hi[cbase + hb.w + (cll - clf)] = (int64_t)hb.x;
+    const uint32_t need = ws.h_need[o + h];
+    const uint32_t clf = slow ? ws.hit_clfirst[o + h] : need;
+    const uint32_t cll = min(clf + (A_total - ws.h_aoff[o + h]) - 1, need);
+    ws.chunk_hi[cbase + ws.h_cid[o + h] + (cll - clf)] = (int64_t)ws.h_qpos[o + h];
   }
 }
 
@@ -1534,7 +1539,7 @@ static int ensure(sk_ctx* ctx, T** p, size_t* cap, size_t need) {
 struct ChainScratch {
   Workspace ws{};
   size_t cap_rec = 0, cap_pair = 0, cap_anc = 0, cap_chunk = 0, cap_iv = 0;
-  size_t c_rec_nh = 0, c_hitA = 0, c_hitB = 0, c_hit_clfirst = 0;
+  size_t c_rec_nh = 0, c_h_qpos = 0, c_h_qcc = 0, c_h_aoff = 0, c_h_rs = 0, c_h_need = 0, c_h_cid = 0, c_hit_clfirst = 0;
   size_t c_ctab_p0 = 0, c_ctab_a0 = 0, c_pair_slow = 0;
   size_t c_pairA = 0, c_pairH = 0, c_pairC = 0, c_pairAbase = 0, c_pairCbase = 0, c_pairIbase = 0, c_pair_nint = 0, c_pair_sumlen = 0,
          c_pair_nchains = 0, c_pair_tqb = 0;
@@ -1549,7 +1554,7 @@ struct ChainScratch {
   GenomeMeta *d_m0 = nullptr, *d_m1 = nullptr;
   size_t c_m0 = 0, c_m1 = 0;
   void free_all() {
-    void* ptrs[] = {ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, sort_tmp, ws.ctab_p0, ws.ctab_a0, ws.pair_slow, ws.rec_nh, ws.hitA, ws.hitB, ws.hit_clfirst, ws.pairA, ws.pairH,
+    void* ptrs[] = {ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, sort_tmp, ws.ctab_p0, ws.ctab_a0, ws.pair_slow, ws.rec_nh, ws.h_qpos, ws.h_qcc, ws.h_aoff, ws.h_rs, ws.h_need, ws.h_cid, ws.hit_clfirst, ws.pairA, ws.pairH,
                     ws.pairC, ws.pairAbase, ws.pairCbase, ws.pairIbase, ws.pair_nint, ws.pair_sumlen, ws.pair_nchains, ws.pair_tqb_ns, ws.anc,
                     ws.score, ws.ptr, ws.rootkey, ws.depth, ws.chunk_first, ws.chunk_pair, ws.chunk_qctg, ws.chunk_lo, ws.chunk_hi,
                     ws.acc_total, ws.acc_rq0, ws.acc_rq1, ws.acc_tbcq, ws.acc_nint, ws.chunk_head, ws.chunk_est, ws.chunk_w, ws.chunk_valid,
@@ -1570,7 +1575,8 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   Workspace& ws = S.ws;
   const size_t NR = std::max<uint64_t>(total_rec, 1);
 #define ENS(field, capf, n) SK_TRY(ensure(ctx, &ws.field, &S.capf, n))
-  ENS(rec_nh, c_rec_nh, NR); ENS(hitA, c_hitA, NR); ENS(hitB, c_hitB, NR); ENS(hit_clfirst, c_hit_clfirst, NR);
+  ENS(rec_nh, c_rec_nh, NR); ENS(h_qpos, c_h_qpos, NR); ENS(h_qcc, c_h_qcc, NR); ENS(h_aoff, c_h_aoff, NR); ENS(h_rs, c_h_rs, NR); ENS(h_need, c_h_need, NR);
+  ENS(h_cid, c_h_cid, NR); ENS(hit_clfirst, c_hit_clfirst, NR);
   ENS(pairA, c_pairA, B); ENS(pairH, c_pairH, B); ENS(pairC, c_pairC, B); ENS(pairAbase, c_pairAbase, B + 1); ENS(pairCbase, c_pairCbase, B + 1);
   ENS(pairIbase, c_pairIbase, B + 1); ENS(pair_nint, c_pair_nint, B); ENS(pair_sumlen, c_pair_sumlen, B); ENS(pair_nchains, c_pair_nchains, B);
   ENS(pair_tqb_ns, c_pair_tqb, B); ENS(pair_slow, c_pair_slow, B);

@@ -271,6 +271,211 @@ static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_se
   return SK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Incremental triangle screen (the pipelined sk_triangle screens a GROWING set once per wave): the inverted index is
+// kept as ONE sorted array of (marker << 22 | genome).  A wave sorts only its own markers, merges them into the table
+// (one streaming pass) and runs only its own genomes as rows: row j finds each of its markers in the table (lower
+// bound inside a 16-bit prefix bucket) and walks the run's entries with genome < j.  Same predicate, same pairs as the
+// full screen restricted to "larger index in the wave" -- without re-sorting and re-walking everything every wave.
+constexpr uint32_t TS_GBITS = 22;                   // genome index bits of a table key (the caller falls back above 2^22 genomes)
+constexpr uint32_t TS_PREFIX_BITS = 16;
+constexpr uint32_t TS_PREFIX_SHIFT = 2 * MARKER_K + TS_GBITS - TS_PREFIX_BITS;
+
+__global__ void ts_keys_kernel(const uint64_t* __restrict__ markers, const uint64_t* __restrict__ off, uint32_t g_begin,
+                               uint64_t* __restrict__ keys) {
+  const uint32_t g = g_begin + blockIdx.x;
+  const uint64_t base = off[g_begin];
+  for (uint64_t i = off[g] + threadIdx.x; i < off[g + 1]; i += blockDim.x) keys[i - base] = (markers[i] << TS_GBITS) | g;
+}
+// bucket[b] = first table position whose key prefix is >= b; bucket[2^16] = n
+__global__ void ts_bucket_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ bucket) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > (1u << TS_PREFIX_BITS)) return;
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if ((key[mid] >> TS_PREFIX_SHIFT) < b) lo = mid + 1; else hi = mid;
+  }
+  bucket[b] = lo;
+}
+// One block per NEW genome j (the larger index of its pairs); columns are the genomes i < j.
+__global__ void __launch_bounds__(256)
+ts_rows_kernel(const uint64_t* __restrict__ markers, const uint64_t* __restrict__ off, const uint64_t* __restrict__ key,
+               const uint32_t* __restrict__ bucket, uint32_t g_begin, uint32_t n_genomes, int rescue_small, double cutoff,
+               uint32_t tile, uint64_t* __restrict__ pairs, unsigned long long* __restrict__ n_pairs, unsigned long long cap) {
+  extern __shared__ uint32_t counts[];
+  const uint32_t j = g_begin + blockIdx.x;
+  if (j >= n_genomes || j == 0) return;
+  const uint64_t mb = off[j], me = off[j + 1];
+  const uint64_t card_j = me - mb;
+  for (uint32_t t0 = 0; t0 < j; t0 += tile) {
+    const uint32_t t1 = min(j, t0 + tile);
+    for (uint32_t c = threadIdx.x; c < t1 - t0; c += blockDim.x) counts[c] = 0;
+    __syncthreads();
+    for (uint64_t e = mb + threadIdx.x; e < me; e += blockDim.x) {
+      const uint64_t m = markers[e];
+      const uint64_t k0 = m << TS_GBITS;
+      const uint32_t b = (uint32_t)(k0 >> TS_PREFIX_SHIFT);
+      uint32_t lo = bucket[b], hi = bucket[b + 1];
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (key[mid] < k0) lo = mid + 1; else hi = mid;
+      }
+      // the run of marker m starts at lo; its entries are in ascending genome order, row j's own entry ends the walk
+      for (uint32_t t = lo;; t++) {
+        const uint64_t kk = key[t];
+        const uint32_t col = (uint32_t)(kk & ((1u << TS_GBITS) - 1));
+        if ((kk >> TS_GBITS) != m || col >= j) break;
+        if (col >= t0 && col < t1) atomicAdd(&counts[col - t0], 1u);
+      }
+    }
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < t1 - t0; c += blockDim.x) {
+      const uint32_t i = t0 + c;
+      const uint64_t card_i = off[i + 1] - off[i];
+      bool pass;
+      // screen_refs with row i (src/screen.rs:158-160, 177-187): a row with < 20 markers passes every column when rescue is on
+      if (rescue_small && card_i < 20) pass = true;
+      else {
+        const uint64_t mn = card_i < card_j ? card_i : card_j;
+        unsigned long long thr = (unsigned long long)(cutoff * (double)mn);
+        if (thr < 1) thr = 1;
+        pass = counts[c] > thr;
+      }
+      if (pass) {
+        unsigned long long slot = atomicAdd(n_pairs, 1ull);
+        if (slot < cap) pairs[slot] = ((uint64_t)i << 32) | j;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct TriScreen {
+  sk_ctx* ctx = nullptr;
+  uint64_t* key[2] = {nullptr, nullptr};
+  size_t cap = 0, n = 0;
+  int cur = 0;
+  uint32_t G = 0;
+  uint32_t* bucket = nullptr;
+};
+
+int tri_screen_create(sk_ctx* ctx, size_t marker_hint, TriScreen** out) {
+  TriScreen* t = new TriScreen();
+  t->ctx = ctx;
+  t->cap = std::max<size_t>(marker_hint, 1024);
+  for (int i = 0; i < 2; i++)
+    if (ctx->arena.alloc((void**)&t->key[i], t->cap * 8) != cudaSuccess) { tri_screen_free(t); ctx->err = "tri_screen: out of device memory"; return SK_ERR_NOMEM; }
+  if (ctx->arena.alloc((void**)&t->bucket, ((1u << TS_PREFIX_BITS) + 2) * 4) != cudaSuccess) { tri_screen_free(t); ctx->err = "tri_screen: out of device memory"; return SK_ERR_NOMEM; }
+  *out = t;
+  return SK_OK;
+}
+void tri_screen_free(TriScreen* t) {
+  if (!t) return;
+  for (int i = 0; i < 2; i++) if (t->key[i]) t->ctx->arena.release(t->key[i]);
+  if (t->bucket) t->ctx->arena.release(t->bucket);
+  delete t;
+}
+bool tri_screen_supports(uint32_t n_genomes, uint64_t n_markers) { return n_genomes < (1u << TS_GBITS) && n_markers < (1ull << 31); }
+
+// Screens the pairs (i, j), i < j, g_begin <= j < set->G; `set` must hold exactly the genomes added so far plus the new ones.
+int tri_screen_add(TriScreen* ts, const sk_sketch_set* set, uint32_t g_begin, const sk_map_params* mp, uint64_t** out_pairs,
+                   uint64_t* out_n) {
+  sk_ctx* ctx = ts->ctx;
+  cudaStream_t st = ctx->stream;
+  *out_pairs = nullptr; *out_n = 0;
+  const uint32_t G = set->G;
+  if (g_begin != ts->G || G < g_begin || set->mk_off[g_begin] != ts->n || !tri_screen_supports(G, set->M)) {
+    ctx->err = "tri_screen_add: set does not continue the screened prefix";
+    return SK_ERR_PARAM;
+  }
+  const size_t m_new = set->mk_off[G] - set->mk_off[g_begin], n_tot = ts->n + m_new;
+  double screen_val = mp->screen_val == 0. ? 0.80 : mp->screen_val;  // src/triangle.rs:34-42
+  const double cutoff = powi21(screen_val);
+  if (n_tot > ts->cap) {   // estimate was short: grow both halves, keep the current table
+    const size_t ncap = n_tot + n_tot / 2;
+    for (int i = 0; i < 2; i++) {
+      uint64_t* p = nullptr;
+      if (ctx->arena.alloc((void**)&p, ncap * 8) != cudaSuccess) { ctx->err = "tri_screen: out of device memory"; return SK_ERR_NOMEM; }
+      if (i == ts->cur && ts->n) SK_CUDA(cudaMemcpyAsync(p, ts->key[i], ts->n * 8, cudaMemcpyDeviceToDevice, st));
+      SK_CUDA(cudaStreamSynchronize(st));
+      ctx->arena.release(ts->key[i]);
+      ts->key[i] = p;
+    }
+    ts->cap = ncap;
+  }
+  DTmp<uint64_t> d_off;
+  SK_CUDA(d_off.alloc((size_t)G + 1, ctx));
+  SK_CUDA(h2d_small(ctx, d_off.p, set->mk_off.data(), ((size_t)G + 1) * 8));
+  if (m_new > 0) {
+    DTmp<uint64_t> nk, snk;
+    SK_CUDA(nk.alloc(m_new, ctx)); SK_CUDA(snk.alloc(m_new, ctx));
+    ts_keys_kernel<<<G - g_begin, 256, 0, st>>>(set->markers, d_off.p, g_begin, nk.p); count_launch(ctx);
+    // stable sort on the marker bits only: inside a run the genomes stay ascending (they are laid out genome-major)
+    size_t tb = 0;
+    SK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, nk.p, snk.p, (int)m_new, (int)TS_GBITS, (int)(TS_GBITS + 2 * MARKER_K), st));
+    DTmp<uint8_t> tmp;
+    SK_CUDA(tmp.alloc(tb, ctx));
+    SK_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, nk.p, snk.p, (int)m_new, (int)TS_GBITS, (int)(TS_GBITS + 2 * MARKER_K), st));
+    if (ts->n == 0) {
+      SK_CUDA(cudaMemcpyAsync(ts->key[1 - ts->cur], snk.p, m_new * 8, cudaMemcpyDeviceToDevice, st));
+    } else {       // keys are distinct (marker, genome) pairs, so the unstable merge has one possible output
+      size_t mb = 0;
+      SK_CUDA(cub::DeviceMerge::MergeKeys(nullptr, mb, ts->key[ts->cur], (int)ts->n, snk.p, (int)m_new, ts->key[1 - ts->cur], ::cuda::std::less<uint64_t>{}, st));
+      DTmp<uint8_t> tmp2;
+      SK_CUDA(tmp2.alloc(mb, ctx));
+      SK_CUDA(cub::DeviceMerge::MergeKeys(tmp2.p, mb, ts->key[ts->cur], (int)ts->n, snk.p, (int)m_new, ts->key[1 - ts->cur], ::cuda::std::less<uint64_t>{}, st));
+      count_launch(ctx);
+    }
+    ts->cur = 1 - ts->cur;
+    SK_CUDA(cudaStreamSynchronize(st));   // temporaries go back to the arena below
+  }
+  ts->n = n_tot; ts->G = G;
+  uint64_t* host = nullptr;
+  unsigned long long n = 0;
+  if (G > g_begin && G > 1) {
+    // (a row's walk always ends at its own table entry, so it never runs past the end of the table)
+    ts_bucket_kernel<<<((1u << TS_PREFIX_BITS) + 256) / 256, 256, 0, st>>>(ts->key[ts->cur], (uint32_t)n_tot, ts->bucket); count_launch(ctx);
+    const uint32_t tile = std::min<uint32_t>(std::max<uint32_t>(G, 1), 48 * 1024);
+    const size_t smem = (size_t)tile * 4;
+    SK_CUDA(cudaFuncSetAttribute(ts_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned long long cap = std::max<unsigned long long>(1ull << 20, 64ull * (G - g_begin));
+    DTmp<unsigned long long> d_n;
+    SK_CUDA(d_n.alloc(1, ctx));
+    DTmp<uint64_t> d_pairs;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      SK_CUDA(d_pairs.alloc(cap, ctx));
+      SK_CUDA(cudaMemsetAsync(d_n.p, 0, 8, st));
+      SK_LAUNCH(ctx, "screen_rows_kernel", (ts_rows_kernel<<<G - g_begin, 256, smem, st>>>(
+          set->markers, d_off.p, ts->key[ts->cur], ts->bucket, g_begin, G, mp->rescue_small, cutoff, tile, d_pairs.p, d_n.p, cap)));
+      SK_CUDA(cudaMemcpyAsync(&n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+      SK_CUDA(cudaStreamSynchronize(st));
+      SK_CUDA(cudaGetLastError());
+      if (n <= cap) break;
+      cap = n;
+    }
+    host = (uint64_t*)malloc(std::max<size_t>(n, 1) * 8);
+    if (!host) return SK_ERR_NOMEM;
+    if (n > 0) {
+      DTmp<uint64_t> sorted;
+      SK_CUDA(sorted.alloc(n, ctx));
+      size_t tb = 0;
+      SK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_pairs.p, sorted.p, (uint64_t)n, 0, 64, st));
+      DTmp<uint8_t> tmp;
+      SK_CUDA(tmp.alloc(tb, ctx));
+      SK_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, d_pairs.p, sorted.p, (uint64_t)n, 0, 64, st));
+      SK_CUDA(cudaMemcpyAsync(host, sorted.p, n * 8, cudaMemcpyDeviceToHost, st));
+      SK_CUDA(cudaStreamSynchronize(st));
+    }
+  } else {
+    host = (uint64_t*)malloc(8);
+    if (!host) return SK_ERR_NOMEM;
+  }
+  *out_pairs = host;
+  *out_n = n;
+  return SK_OK;
+}
+
 }  // namespace sk
 
 extern "C" {

@@ -204,6 +204,12 @@ struct SetReserve { uint64_t bases = 0, contigs = 0, genomes = 0; };
 int append_sets_inplace(sk_ctx* ctx, sk_sketch_set** dst, const std::vector<sk_sketch_set*>& parts, const SetReserve& hint);
 int build_hash_range(sk_ctx* ctx, sk_sketch_set* set, uint32_t g_begin);   // tables of the genomes [g_begin, G) appended to set->htab
 int merge_sets(sk_ctx* ctx, const sk_sketch_set* base, const std::vector<sk_sketch_set*>& parts, sk_sketch_set** out);  // (re)builds set->htab from ukmer/ustart; call on every finished set
+// screen.cu: incremental triangle screen of a growing set (pipelined sk_triangle)
+struct TriScreen;
+int tri_screen_create(sk_ctx* ctx, size_t marker_hint, TriScreen** out);
+int tri_screen_add(TriScreen* ts, const sk_sketch_set* set, uint32_t g_begin, const sk_map_params* mp, uint64_t** pairs, uint64_t* n);
+void tri_screen_free(TriScreen* ts);
+bool tri_screen_supports(uint32_t n_genomes, uint64_t n_markers);
 // screen.cu / chain.cu
 uint64_t count_launch(sk_ctx* ctx, uint64_t n = 1);
 cudaError_t h2d_small(sk_ctx* ctx, void* dst, const void* src, size_t bytes);  // api.cu

@@ -128,6 +128,11 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
     int worker_rc = SK_OK;
     std::string worker_err;
     sk_sketch_set* merged = nullptr;        // the set sketched so far (owned by the worker context's arena)
+    // incremental screen: the sorted marker table of the merged set is kept and each wave only adds its own markers and
+    // screens its own genomes (SK_FULL_RESCREEN=1: screen the whole merged set every wave and filter, as round 1 did)
+    sk::TriScreen* tscreen = nullptr;
+    const bool inc_screen = getenv("SK_FULL_RESCREEN") == nullptr &&
+                            sk::tri_screen_supports(n_genomes, (uint64_t)((double)total_bytes / sp->marker_c * 1.5) + n_genomes);
     std::thread worker([&] {
       cudaSetDevice(wctx->device);
       std::vector<sk_sketch_set*> pending;
@@ -163,7 +168,10 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
               merged->ranks_user_set = true;
             }
             uint64_t* pairs = nullptr; uint64_t np = 0;
-            rc = sk_screen_triangle(wctx, merged, mp, &pairs, &np);
+            bool inc = inc_screen && sk::tri_screen_supports(merged->G, merged->M);
+            if (inc && !tscreen) rc = sk::tri_screen_create(wctx, (size_t)((double)total_bytes / sp->marker_c * 1.1) + 1024, &tscreen);
+            if (rc == SK_OK) rc = inc ? sk::tri_screen_add(tscreen, merged, pending_begin, mp, &pairs, &np)
+                                      : sk_screen_triangle(wctx, merged, mp, &pairs, &np);
             tc = now_s();
             if (rc == SK_OK) {
               uint64_t m = 0;   // new pairs: larger index j inside the genomes just merged
@@ -184,6 +192,7 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
         pending.clear(); pending_genomes = 0;
       }
       cudaStreamSynchronize(wctx->stream);
+      sk::tri_screen_free(tscreen);
     });
     std::function<int(sk_sketch_set*, uint32_t, uint32_t)> on_part = [&](sk_sketch_set* part, uint32_t g_begin, uint32_t g_end) -> int {
       (void)g_end;

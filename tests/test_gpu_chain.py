@@ -293,6 +293,42 @@ def test_pipelined_triangle_equals_simple(ctx, monkeypatch):
     assert len(k0) == len(k1) and k0.tobytes() == k1.tobytes()
 
 
+@pytest.mark.parametrize("rescreen", [False, True])
+def test_pipelined_triangle_small_marker_sets(ctx, monkeypatch, rescreen):
+    """Incremental screen of the pipelined triangle vs the one-shot screen when some genomes have < 20 markers (screen_refs'
+    rescue rule is decided by the SMALLER index of a pair, src/screen.rs:158-160) or no markers at all, in every wave position."""
+    import skani_b200 as sk
+    L, G = 200_000, 3
+    b0, off0, goc0 = synth.generate(0, 12, L, G=G)
+    rng = np.random.default_rng(11)
+    contigs, goc = [], []
+    tiny_at = {0, 5, 9, 14}        # slots of tiny genomes (6 kb: ~6 markers) among the 12 real ones
+    real = iter(range(12))
+    n = 16
+    for g in range(n):
+        if g in tiny_at:
+            src = b0[int(off0[0]) + 1000 * g: int(off0[0]) + 1000 * g + 6000].copy()     # related to genome 0's cluster
+            contigs.append(src); goc.append(g)
+        else:
+            r = next(real)
+            for i in np.nonzero(goc0 == r)[0]:
+                contigs.append(b0[int(off0[i]):int(off0[i + 1])]); goc.append(g)
+    bases = np.concatenate(contigs)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in contigs])]).astype(np.uint64)
+    goc = np.asarray(goc, dtype=np.uint32)
+    monkeypatch.setenv("SK_NO_PIPELINE", "1")
+    r0, st0 = sk.triangle(ctx, bases, off, goc, n, as_array=True)
+    monkeypatch.delenv("SK_NO_PIPELINE")
+    monkeypatch.setenv("SK_FORCE_PIPELINE", "1")
+    monkeypatch.setenv("SK_SUBBATCH_BYTES", "450000")
+    if rescreen:
+        monkeypatch.setenv("SK_FULL_RESCREEN", "1")
+    r1, st1 = sk.triangle(ctx, bases, off, goc, n, as_array=True)
+    assert st0.n_pairs_screened == st1.n_pairs_screened and st0.n_pairs_screened >= 4 * 8   # rescue rows pass whole columns
+    k0 = np.sort(r0, order=["ref_id", "query_id"]); k1 = np.sort(r1, order=["ref_id", "query_id"])
+    assert len(k0) == len(k1) and k0.tobytes() == k1.tobytes()
+
+
 @pytest.mark.parametrize("subbatch", ["350000", "1300000", "2500000"])
 def test_pipelined_triangle_many_uneven_waves_vs_oracle(ctx, monkeypatch, subbatch):
     """The pipelined path with several waves of uneven size (sub-batches of 1 / 4 / 8 genomes, wave threshold n/8), genomes

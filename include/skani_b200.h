@@ -177,6 +177,11 @@ int sk_screen_triangle(sk_ctx* ctx, const sk_sketch_set* set, const sk_map_param
 /* same, restricted to rows i with i % row_mod == row_rem: the partition of the pair set over ranks (no communication) */
 int sk_screen_triangle_rows(sk_ctx* ctx, const sk_sketch_set* set, const sk_map_params* mp, uint32_t row_mod, uint32_t row_rem,
                             uint64_t** pairs_ij, uint64_t* n_pairs);
+/* one BLOCK of a sharded triangle screen: the pairs (i, j), i < j, g_begin <= j < g_end of sk_screen_triangle(set), computed from
+ * the markers of the genomes [0, g_end) only.  The union over a partition of [0, n) into blocks is sk_screen_triangle's list
+ * (multi-GPU: every GPU screens the rows of its own genome block against everything before them, src/triangle.rs:71-90). */
+int sk_screen_triangle_block(sk_ctx* ctx, const sk_sketch_set* set, uint32_t g_begin, uint32_t g_end, const sk_map_params* mp,
+                             uint64_t** pairs_ij, uint64_t* n_pairs);
 /* dist / search: pairs (ref, query).  mode 0 = check_markers_quickly with rescue_small from mp (dist without index,
  * src/dist.rs:104), mode 1 = check_markers_quickly with rescue_small = false (search, src/search.rs:127),
  * mode 2 = screen_refs via the inverted index (dist with index, src/dist.rs:122), mode 3 = screen_refs_indices

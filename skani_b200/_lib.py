@@ -70,6 +70,7 @@ SYMBOLS = [
     ("sk_sketch_set_pack_subset", i32, [vp, vp, u32, i32, vp, vp]),
     ("sk_screen_triangle", i32, [vp, vp, PP(MapParams), PP(PP(u64)), PP(u64)]),
     ("sk_screen_triangle_rows", i32, [vp, vp, PP(MapParams), u32, u32, PP(PP(u64)), PP(u64)]),
+    ("sk_screen_triangle_block", i32, [vp, vp, u32, u32, PP(MapParams), PP(PP(u64)), PP(u64)]),
     ("sk_screen_query_ref", i32, [vp, vp, vp, PP(MapParams), i32, PP(PP(u64)), PP(u64)]),
     ("sk_free", None, [vp]),
     ("sk_chain_pairs", i32, [vp, vp, vp, vp, u64, PP(MapParams), vp]),

@@ -88,7 +88,6 @@ extern "C" int sk_triangle_multi(sk_ctx* const* ctxs, uint32_t n_ctx, const uint
     for (uint32_t k = 1; k <= W; k++) gb[k] = std::max(gb[k], gb[k - 1]);
   }
   for (uint32_t d = 0; d <= W; d++) cb[d] = (uint32_t)(std::lower_bound(genome_of_contig, genome_of_contig + n_contigs, gb[d]) - genome_of_contig);
-  auto block_of = [&](uint32_t g) { return (uint32_t)(std::upper_bound(gb.begin() + 1, gb.begin() + W + 1, g) - (gb.begin() + 1)); };
   // peer access between distinct devices (ignored when unsupported: the copies then stage through the host)
   for (uint32_t a = 0; a < W; a++)
     for (uint32_t b = 0; b < W; b++)
@@ -104,6 +103,7 @@ extern "C" int sk_triangle_multi(sk_ctx* const* ctxs, uint32_t n_ctx, const uint
   std::vector<std::vector<sk_ani_result>> results(W);
   std::vector<Blob> mk(W);
   std::vector<std::vector<Blob>> sub(W, std::vector<Blob>(W));     // sub[src][dst]
+  std::vector<std::vector<uint64_t>> cross_part(W);                 // cross-block pairs found by each device's share of the screen
   std::vector<int> rcs(W, SK_OK);
   std::vector<uint64_t> screened(W, 0);
   const bool trace = getenv("SK_TRACE") != nullptr;
@@ -156,16 +156,22 @@ extern "C" int sk_triangle_multi(sk_ctx* const* ctxs, uint32_t n_ctx, const uint
     }
     if (!bar.sync(rc == SK_OK)) { if (mkset) sk_sketch_set_free(mkset); return rc; }   // every peer has copied: the marker blobs may go
     c->arena.release(mk[d].d); mk[d].d = nullptr;
-    // ---- screen everything, keep the cross-block pairs, take this device's slice
+    // ---- sharded screen: this device screens the rows of ITS block against every genome before them (one sort of the markers of
+    //      the blocks up to its own, rows of one block) and keeps the pairs that cross a block boundary; the W partial lists are
+    //      exchanged through host memory and merged, so that every device holds the same sorted cross-block pair list
     uint64_t* pairs = nullptr; uint64_t np = 0;
-    rc = sk_screen_triangle(c, mkset, mp, &pairs, &np);
+    rc = sk_screen_triangle_block(c, mkset, gb[d], gb[d + 1], mp, &pairs, &np);
     sk_sketch_set_free(mkset);
-    const double t2 = now_s();
-    std::vector<uint64_t> cross;
     if (rc == SK_OK) {
-      for (uint64_t i = 0; i < np; i++) if (block_of((uint32_t)(pairs[i] >> 32)) != block_of((uint32_t)pairs[i])) cross.push_back(pairs[i]);
+      cross_part[d].clear();
+      for (uint64_t i = 0; i < np; i++) if ((uint32_t)(pairs[i] >> 32) < gb[d]) cross_part[d].push_back(pairs[i]);
       sk_free(pairs);
     }
+    if (!bar.sync(rc == SK_OK)) return rc;
+    std::vector<uint64_t> cross;
+    for (uint32_t r = 0; r < W; r++) cross.insert(cross.end(), cross_part[r].begin(), cross_part[r].end());
+    std::sort(cross.begin(), cross.end());
+    const double t2 = now_s();
     auto slice_of = [&](uint32_t r, uint64_t& lo, uint64_t& hi) { lo = cross.size() * r / W; hi = cross.size() * (r + 1) / W; };
     auto genomes_of_slice = [&](uint32_t r, std::vector<uint32_t>& need) {
       uint64_t lo, hi;

@@ -231,7 +231,8 @@ static int run_screen(sk_ctx* ctx, const sk_sketch_set* rows, const sk_sketch_se
   // ---- row pass with retry on capacity overflow
   const uint32_t tile = std::min<uint32_t>(NC, 48 * 1024);
   const size_t smem = (size_t)tile * 4;
-  SK_CUDA(cudaFuncSetAttribute(screen_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // always the same (maximal) value: the attribute is per device, and several contexts may screen on one device concurrently
+  SK_CUDA(cudaFuncSetAttribute(screen_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 * 4));
   unsigned long long cap = std::max<unsigned long long>(1ull << 20, 64ull * NR);
   DTmp<unsigned long long> d_n;
   SK_CUDA(d_n.alloc(1, ctx));
@@ -378,14 +379,16 @@ void tri_screen_free(TriScreen* t) {
 }
 bool tri_screen_supports(uint32_t n_genomes, uint64_t n_markers) { return n_genomes < (1u << TS_GBITS) && n_markers < (1ull << 31); }
 
-// Screens the pairs (i, j), i < j, g_begin <= j < set->G; `set` must hold exactly the genomes added so far plus the new ones.
-int tri_screen_add(TriScreen* ts, const sk_sketch_set* set, uint32_t g_begin, const sk_map_params* mp, uint64_t** out_pairs,
-                   uint64_t* out_n) {
+// Adds the markers of the genomes [ts->G, g_end) of `set` to the table and screens the pairs (i, j), i < j, row_begin <= j < g_end
+// (`set` must hold the genomes added so far as its prefix).  The pipelined triangle calls it once per wave with row_begin = ts->G;
+// a sharded screen (sk_screen_triangle_block) calls it once on an empty table with the rows of one block.
+int tri_screen_add(TriScreen* ts, const sk_sketch_set* set, uint32_t g_end, uint32_t row_begin, const sk_map_params* mp,
+                   uint64_t** out_pairs, uint64_t* out_n) {
   sk_ctx* ctx = ts->ctx;
   cudaStream_t st = ctx->stream;
   *out_pairs = nullptr; *out_n = 0;
-  const uint32_t G = set->G;
-  if (g_begin != ts->G || G < g_begin || set->mk_off[g_begin] != ts->n || !tri_screen_supports(G, set->M)) {
+  const uint32_t G = g_end, g_begin = ts->G;
+  if (G > set->G || G < g_begin || row_begin < g_begin || row_begin > G || set->mk_off[g_begin] != ts->n || !tri_screen_supports(G, set->mk_off[G])) {
     ctx->err = "tri_screen_add: set does not continue the screened prefix";
     return SK_ERR_PARAM;
   }
@@ -433,21 +436,21 @@ int tri_screen_add(TriScreen* ts, const sk_sketch_set* set, uint32_t g_begin, co
   ts->n = n_tot; ts->G = G;
   uint64_t* host = nullptr;
   unsigned long long n = 0;
-  if (G > g_begin && G > 1) {
+  if (G > row_begin && G > 1) {
     // (a row's walk always ends at its own table entry, so it never runs past the end of the table)
     ts_bucket_kernel<<<((1u << TS_PREFIX_BITS) + 256) / 256, 256, 0, st>>>(ts->key[ts->cur], (uint32_t)n_tot, ts->bucket); count_launch(ctx);
     const uint32_t tile = std::min<uint32_t>(std::max<uint32_t>(G, 1), 48 * 1024);
     const size_t smem = (size_t)tile * 4;
-    SK_CUDA(cudaFuncSetAttribute(ts_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unsigned long long cap = std::max<unsigned long long>(1ull << 20, 64ull * (G - g_begin));
+    SK_CUDA(cudaFuncSetAttribute(ts_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 * 4));   // constant: see run_screen
+    unsigned long long cap = std::max<unsigned long long>(1ull << 20, 64ull * (G - row_begin));
     DTmp<unsigned long long> d_n;
     SK_CUDA(d_n.alloc(1, ctx));
     DTmp<uint64_t> d_pairs;
     for (int attempt = 0; attempt < 2; attempt++) {
       SK_CUDA(d_pairs.alloc(cap, ctx));
       SK_CUDA(cudaMemsetAsync(d_n.p, 0, 8, st));
-      SK_LAUNCH(ctx, "screen_rows_kernel", (ts_rows_kernel<<<G - g_begin, 256, smem, st>>>(
-          set->markers, d_off.p, ts->key[ts->cur], ts->bucket, g_begin, G, mp->rescue_small, cutoff, tile, d_pairs.p, d_n.p, cap)));
+      SK_LAUNCH(ctx, "screen_rows_kernel", (ts_rows_kernel<<<G - row_begin, 256, smem, st>>>(
+          set->markers, d_off.p, ts->key[ts->cur], ts->bucket, row_begin, G, mp->rescue_small, cutoff, tile, d_pairs.p, d_n.p, cap)));
       SK_CUDA(cudaMemcpyAsync(&n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
       SK_CUDA(cudaStreamSynchronize(st));
       SK_CUDA(cudaGetLastError());
@@ -491,6 +494,25 @@ int sk_screen_triangle_rows(sk_ctx* ctx, const sk_sketch_set* set, const sk_map_
   if (!ctx || !set || !mp || !pairs || !n || row_mod == 0 || row_rem >= row_mod) return SK_ERR_PARAM;
   SK_CUDA(cudaSetDevice(ctx->device));
   return sk::run_screen(ctx, set, set, sk::MODE_TRIANGLE, mp, pairs, n, row_mod, row_rem);
+}
+
+int sk_screen_triangle_block(sk_ctx* ctx, const sk_sketch_set* set, uint32_t g_begin, uint32_t g_end, const sk_map_params* mp,
+                             uint64_t** pairs, uint64_t* n) {
+  if (!ctx || !set || !mp || !pairs || !n || g_begin > g_end || g_end > set->G) return SK_ERR_PARAM;
+  SK_CUDA(cudaSetDevice(ctx->device));
+  if (!sk::tri_screen_supports(g_end, set->mk_off[g_end]) || getenv("SK_FULL_RESCREEN")) {   // one-shot screen of everything, then the block's rows
+    uint64_t* all = nullptr; uint64_t na = 0;
+    SK_TRY(sk::run_screen(ctx, set, set, sk::MODE_TRIANGLE, mp, &all, &na));
+    uint64_t m = 0;
+    for (uint64_t i = 0; i < na; i++) { const uint32_t j = (uint32_t)all[i]; if (j >= g_begin && j < g_end) all[m++] = all[i]; }
+    *pairs = all; *n = m;
+    return SK_OK;
+  }
+  sk::TriScreen* ts = nullptr;
+  SK_TRY(sk::tri_screen_create(ctx, set->mk_off[g_end] + 1024, &ts));
+  const int rc = sk::tri_screen_add(ts, set, g_end, g_begin, mp, pairs, n);
+  sk::tri_screen_free(ts);
+  return rc;
 }
 
 int sk_screen_query_ref(sk_ctx* ctx, const sk_sketch_set* refs, const sk_sketch_set* queries, const sk_map_params* mp, int mode,

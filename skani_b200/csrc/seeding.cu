@@ -213,13 +213,18 @@ __global__ void iota_local_kernel(const uint64_t* __restrict__ seg_off, uint32_t
 // sort keys of the k-mer view: (genome << kbits | k-mer), value = the record's index inside its genome.  ONE device-wide radix
 // sort of these keys orders every genome of the sub-batch by (kmer, contig, pos) at once (stable), instead of a segmented
 // sort that runs one block per genome and pass (5.5 % + 1.7 % of a step in profiles/r02_launches_bench_c2.md)
+//
+// When genome, k-mer and the record's index inside its genome fit 64 bits together (ibits > 0: always, short of sub-batches of
+// thousands of multi-Gbp genomes) the index rides in the LOW bits of the key and the sort is keys-only over the bits above it:
+// 16 instead of 24 bytes moved per record and pass, no value arrays.
 __global__ void kview_keys_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ pv_kmer, uint32_t kbits,
-                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                  uint32_t ibits, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint32_t g = blockIdx.x;
   const uint64_t b = seg_off[g], e = seg_off[g + 1];
   for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
-    keys[i] = ((uint64_t)g << kbits) | pv_kmer[i];
-    vals[i] = (uint32_t)(i - b);
+    const uint64_t k = ((uint64_t)g << kbits) | pv_kmer[i];
+    if (ibits) keys[i] = (k << ibits) | (uint64_t)(i - b);
+    else { keys[i] = k; vals[i] = (uint32_t)(i - b); }
   }
 }
 __global__ void marker_keys_kernel(const uint64_t* __restrict__ seg_off, uint64_t* __restrict__ mk) {   // in place: genome << 42 | marker
@@ -232,14 +237,16 @@ __global__ void marker_keys_kernel(const uint64_t* __restrict__ seg_off, uint64_
 __global__ void kview_gather_kernel(const uint64_t* __restrict__ seg_off, const uint64_t* __restrict__ skmer,
                                     const uint32_t* __restrict__ perm, const uint32_t* __restrict__ pv_pos,
                                     const uint32_t* __restrict__ pv_cc, uint32_t* __restrict__ kv_pos,
-                                    uint32_t* __restrict__ kv_cc, uint32_t* __restrict__ head) {
+                                    uint32_t* __restrict__ kv_cc, uint32_t* __restrict__ head, uint32_t ibits) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
+  const uint64_t imask = (1ull << ibits) - 1;
   for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
-    uint32_t r = perm[i];
+    const uint64_t k = skmer[i];
+    uint32_t r = ibits ? (uint32_t)(k & imask) : perm[i];
     kv_pos[i] = pv_pos[b + r];
     kv_cc[i] = pv_cc[b + r];
-    head[i] = (i == b || skmer[i] != skmer[i - 1]) ? 1u : 0u;
+    head[i] = (i == b || (k >> ibits) != (skmer[i - 1] >> ibits)) ? 1u : 0u;
   }
 }
 
@@ -247,13 +254,13 @@ __global__ void kview_gather_kernel(const uint64_t* __restrict__ seg_off, const 
 // writes distinct k-mers and local group starts (+ one sentinel per genome), then multiplicities per pv record.
 __global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint64_t* __restrict__ skmer, uint64_t kmask,
                               const uint32_t* __restrict__ head, const uint32_t* __restrict__ hscan, uint32_t total_groups,
-                              uint32_t n_genomes, uint32_t* __restrict__ ukmer, uint32_t* __restrict__ ustart) {
+                              uint32_t n_genomes, uint32_t* __restrict__ ukmer, uint32_t* __restrict__ ustart, uint32_t ibits) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
   for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
     if (head[i]) {
       uint32_t gid = hscan[i];
-      ukmer[gid] = (uint32_t)(skmer[i] & kmask);
+      ukmer[gid] = (uint32_t)((skmer[i] >> ibits) & kmask);
       ustart[gid + g] = (uint32_t)(i - b);
     }
   }
@@ -267,13 +274,16 @@ __global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint64
 
 __global__ void mult_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ head,
                             const uint32_t* __restrict__ hscan, const uint32_t* __restrict__ perm,
-                            const uint32_t* __restrict__ ustart, uint16_t* __restrict__ pv_mult) {
+                            const uint32_t* __restrict__ ustart, uint16_t* __restrict__ pv_mult,
+                            const uint64_t* __restrict__ skmer, uint32_t ibits) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
+  const uint64_t imask = (1ull << ibits) - 1;
   for (uint64_t i = b + (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (uint64_t)blockDim.x * gridDim.y) {
     uint32_t gid = hscan[i] + head[i] - 1;
     uint32_t cntv = ustart[gid + g + 1] - ustart[gid + g];
-    pv_mult[b + perm[i]] = (uint16_t)min(cntv, 65535u);
+    const uint32_t r = ibits ? (uint32_t)(skmer[i] & imask) : perm[i];
+    pv_mult[b + r] = (uint16_t)min(cntv, 65535u);
   }
 }
 
@@ -463,20 +473,31 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     if (S >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 seed records"; return SK_ERR_PARAM; }
     DTmp<uint32_t> vals, perm, head, hscan;
     DTmp<uint64_t> keys, skmer;
-    SK_CUDA(vals.alloc(S, ctx)); SK_CUDA(keys.alloc(S, ctx)); SK_CUDA(skmer.alloc(S, ctx)); SK_CUDA(perm.alloc(S, ctx));
+    SK_CUDA(keys.alloc(S, ctx)); SK_CUDA(skmer.alloc(S, ctx));
     SK_CUDA(head.alloc(S + 1, ctx)); SK_CUDA(hscan.alloc(S + 1, ctx));
     const uint32_t kbits = std::min(32u, 2 * set->sp.k);
     const uint32_t gbits = G > 1 ? 32 - (uint32_t)__builtin_clz(G - 1) : 0;     // bits of a genome index 0 .. G-1
     const uint64_t kmask = (kbits >= 64) ? ~0ull : ((1ull << kbits) - 1);
-    kview_keys_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, set->pv_kmer, kbits, keys.p, vals.p); count_launch(ctx);
+    uint64_t max_rec = 1;
+    for (uint32_t g = 0; g < G; g++) max_rec = std::max<uint64_t>(max_rec, set->seed_off[g + 1] - set->seed_off[g]);
+    uint32_t ibits = max_rec > 1 ? 64 - (uint32_t)__builtin_clzll(max_rec - 1) : 1;   // bits of a record index inside its genome
+    if (ibits + kbits + gbits > 64 || getenv("SK_KVIEW_SORT_PAIRS")) ibits = 0;                // does not fit: (key, index) pairs
+    if (!ibits) { SK_CUDA(vals.alloc(S, ctx)); SK_CUDA(perm.alloc(S, ctx)); }
+    kview_keys_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, set->pv_kmer, kbits, ibits, keys.p, vals.p); count_launch(ctx);
     size_t tb = 0;
-    SK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, skmer.p, vals.p, perm.p, (int)S, 0, (int)(kbits + gbits), st));
     DTmp<uint8_t> tmp;
-    SK_CUDA(tmp.alloc(tb, ctx));
-    SK_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, skmer.p, vals.p, perm.p, (int)S, 0, (int)(kbits + gbits), st));
+    if (ibits) {
+      SK_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, skmer.p, (int)S, (int)ibits, (int)(ibits + kbits + gbits), st));
+      SK_CUDA(tmp.alloc(tb, ctx));
+      SK_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, keys.p, skmer.p, (int)S, (int)ibits, (int)(ibits + kbits + gbits), st));
+    } else {
+      SK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, skmer.p, vals.p, perm.p, (int)S, 0, (int)(kbits + gbits), st));
+      SK_CUDA(tmp.alloc(tb, ctx));
+      SK_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, skmer.p, vals.p, perm.p, (int)S, 0, (int)(kbits + gbits), st));
+    }
     count_launch(ctx);
     kview_gather_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, perm.p, set->pv_pos, set->pv_cc, set->kv_pos,
-                                           set->kv_cc, head.p); count_launch(ctx);
+                                           set->kv_cc, head.p, ibits); count_launch(ctx);
     SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, S));
     // total groups and per-genome group offsets
     DTmp<uint64_t> d_ukoff;
@@ -491,8 +512,8 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     set->U = U;
     SK_CUDA(ctx->arena.alloc((void**)&set->ukmer, std::max<size_t>(U, 1) * 4));
     SK_CUDA(ctx->arena.alloc((void**)&set->ustart, (size_t)(U + G) * 4));
-    groups_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, kmask, head.p, hscan.p, U, G, set->ukmer, set->ustart); count_launch(ctx);
-    mult_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult); count_launch(ctx);
+    groups_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, kmask, head.p, hscan.p, U, G, set->ukmer, set->ustart, ibits); count_launch(ctx);
+    mult_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult, skmer.p, ibits); count_launch(ctx);
     SK_CUDA(cudaStreamSynchronize(st));
   } else {
     set->U = 0;

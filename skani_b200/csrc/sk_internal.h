@@ -207,7 +207,7 @@ int merge_sets(sk_ctx* ctx, const sk_sketch_set* base, const std::vector<sk_sket
 // screen.cu: incremental triangle screen of a growing set (pipelined sk_triangle)
 struct TriScreen;
 int tri_screen_create(sk_ctx* ctx, size_t marker_hint, TriScreen** out);
-int tri_screen_add(TriScreen* ts, const sk_sketch_set* set, uint32_t g_begin, const sk_map_params* mp, uint64_t** pairs, uint64_t* n);
+int tri_screen_add(TriScreen* ts, const sk_sketch_set* set, uint32_t g_end, uint32_t row_begin, const sk_map_params* mp, uint64_t** pairs, uint64_t* n);
 void tri_screen_free(TriScreen* ts);
 bool tri_screen_supports(uint32_t n_genomes, uint64_t n_markers);
 // screen.cu / chain.cu

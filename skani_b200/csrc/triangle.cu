@@ -170,7 +170,7 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
             uint64_t* pairs = nullptr; uint64_t np = 0;
             bool inc = inc_screen && sk::tri_screen_supports(merged->G, merged->M);
             if (inc && !tscreen) rc = sk::tri_screen_create(wctx, (size_t)((double)total_bytes / sp->marker_c * 1.1) + 1024, &tscreen);
-            if (rc == SK_OK) rc = inc ? sk::tri_screen_add(tscreen, merged, pending_begin, mp, &pairs, &np)
+            if (rc == SK_OK) rc = inc ? sk::tri_screen_add(tscreen, merged, merged->G, pending_begin, mp, &pairs, &np)
                                       : sk_screen_triangle(wctx, merged, mp, &pairs, &np);
             tc = now_s();
             if (rc == SK_OK) {

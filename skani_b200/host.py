@@ -267,6 +267,16 @@ def screen_triangle(ctx, sset, mp=None):
     return _pairs_out(ctx, ctx.L.sk_screen_triangle, ctx.h, sset.h, C.byref(mp))
 
 
+def screen_triangle_block(ctx, sset, g_begin, g_end, mp=None):
+    """Pairs (i, j), i < j, g_begin <= j < g_end of the triangle screen (sharded screen: one block of rows)."""
+    mp = mp or map_params()
+    pp = C.POINTER(C.c_uint64)(); n = C.c_uint64()
+    ctx.check(ctx.L.sk_screen_triangle_block(ctx.h, sset.h, int(g_begin), int(g_end), C.byref(mp), C.byref(pp), C.byref(n)))
+    arr = np.ctypeslib.as_array(pp, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
+    ctx.L.sk_free(pp)
+    return arr
+
+
 def screen_query_ref(ctx, refs, queries, mp=None, mode=0):
     mp = mp or map_params()
     pp = C.POINTER(C.c_uint64)(); n = C.c_uint64()

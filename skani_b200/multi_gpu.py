@@ -77,6 +77,28 @@ def fetch_plan(sorted_pairs, world, rank, bounds):
     return need, send, recv_counts
 
 
+def allgather_sorted_u64(dist, torch, part, world, device):
+    """All ranks contribute a uint64 array of any length; everyone gets the sorted concatenation (two collectives: lengths,
+    then the arrays padded to the longest).  `device` = where the collective's tensors live (cuda for NCCL, cpu for gloo)."""
+    part = np.ascontiguousarray(part, np.uint64)
+    cnt = torch.tensor([len(part)], dtype=torch.int64, device=device)
+    allcnt = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allcnt, cnt)
+    allcnt = allcnt.cpu().numpy()
+    mx = int(allcnt.max()) if world else 0
+    if mx == 0:
+        return np.zeros(0, np.uint64)
+    buf = np.zeros(mx, np.int64)
+    buf[:len(part)] = part.view(np.int64)
+    mine = torch.from_numpy(buf).to(device)
+    allbuf = torch.empty(world * mx, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allbuf, mine)
+    allbuf = allbuf.cpu().numpy().view(np.uint64).reshape(world, mx)
+    out = np.concatenate([allbuf[r, :int(allcnt[r])] for r in range(world)])
+    out.sort()
+    return out
+
+
 def cross_block_pairs(sorted_pairs, bounds):
     """The pairs whose two genomes live in different blocks (bounds[r] .. bounds[r+1] = block of rank r)."""
     p = np.asarray(sorted_pairs, np.uint64)
@@ -241,11 +263,15 @@ class DistTriangle:
         allblk = allblk.cpu().numpy().reshape(self.world, 2)
         bounds = np.concatenate([allblk[:, 0], [allblk[-1, 0] + allblk[-1, 1]]])
         assert bounds[0] == 0 and bounds[-1] == n_total and np.all(np.diff(bounds) == allblk[:, 1]), "ranks must hold consecutive blocks"
-        # markers everywhere -> every rank screens the whole triangle; pairs inside a block are already done
+        # markers everywhere -> SHARDED screen: this rank screens the rows of its own block against every genome before them
+        # (pairs inside the block are already done) and the partial cross-block pair lists are all-gathered and merged, so every
+        # rank holds the same sorted list
         mk = self.exchange(local, PACK_MARKERS_ONLY)
         assert len(mk) == n_total
-        pairs = cross_block_pairs(H.screen_triangle(ctx, mk, self.mp), bounds)
+        part = H.screen_triangle_block(ctx, mk, g0, g0 + nloc, self.mp)
         mk.free()
+        part = part[(part >> np.uint64(32)) < np.uint64(g0)]
+        pairs = allgather_sorted_u64(self.dist, torch, part, self.world, self.device)
         t2 = time.perf_counter()
         need, send, recv_counts = fetch_plan(pairs, self.world, self.rank, bounds)
         mine = pair_slice_of_rank(pairs, self.world, self.rank)

@@ -293,6 +293,46 @@ def test_pipelined_triangle_equals_simple(ctx, monkeypatch):
     assert len(k0) == len(k1) and k0.tobytes() == k1.tobytes()
 
 
+def test_screen_triangle_block_partitions_the_pair_list(ctx):
+    """sk_screen_triangle_block (one GPU's share of the sharded screen): for any cut of the genome range into blocks the union
+    of the blocks' lists is sk_screen_triangle's list, each block holding exactly the pairs whose larger index it owns --
+    including genomes with < 20 markers (rescue rows pass whole columns) and a genome without sequence."""
+    import skani_b200 as sk
+    L, G = 200_000, 3
+    b0, off0, goc0 = synth.generate(0, 12, L, G=G)
+    contigs, goc = [], []
+    real = iter(range(12))
+    n = 16
+    for g in range(n):
+        if g in (0, 6, 13):
+            contigs.append(b0[int(off0[0]) + 1500 * g: int(off0[0]) + 1500 * g + 7000].copy()); goc.append(g)
+        elif g == 9:
+            continue                                                   # no contigs: empty sketch
+        else:
+            r = next(real)
+            for i in np.nonzero(goc0 == r)[0]:
+                contigs.append(b0[int(off0[i]):int(off0[i + 1])]); goc.append(g)
+    bases = np.concatenate(contigs)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in contigs])]).astype(np.uint64)
+    sset = sk.sketch_contigs(ctx, bases, off, np.asarray(goc, np.uint32), n)
+    full = sk.screen_triangle(ctx, sset)
+    assert len(full) > 20
+    for cuts in ([0, n], [0, 5, n], [0, 1, 2, 9, 10, n], [0, 0, 7, 7, n]):
+        parts = [sk.screen_triangle_block(ctx, sset, cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+        for i, p in enumerate(parts):
+            j = (p & np.uint64(0xFFFFFFFF)).astype(np.int64)
+            assert np.all((j >= cuts[i]) & (j < cuts[i + 1])) and np.all(np.diff(p.astype(np.int64)) > 0)
+        assert np.array_equal(np.sort(np.concatenate(parts)), full)
+    import os
+    os.environ["SK_FULL_RESCREEN"] = "1"                               # the fallback (one-shot screen + filter) gives the same blocks
+    try:
+        fb = sk.screen_triangle_block(ctx, sset, 5, n)
+    finally:
+        del os.environ["SK_FULL_RESCREEN"]
+    assert np.array_equal(fb, sk.screen_triangle_block(ctx, sset, 5, n))
+    sset.free()
+
+
 @pytest.mark.parametrize("rescreen", [False, True])
 def test_pipelined_triangle_small_marker_sets(ctx, monkeypatch, rescreen):
     """Incremental screen of the pipelined triangle vs the one-shot screen when some genomes have < 20 markers (screen_refs'

@@ -90,6 +90,14 @@ def _worker(rank, world, port, q):
         views.append(buf[o:o + p_.numel()]); o += p_.numel()
     got2 = alltoall_variable(dist, views, world, "cpu", src=buf)
     ok = ok and all(torch.equal(a, b) for a, b in zip(got, got2))
+    # partial pair lists of the sharded screen -> the same sorted list everywhere (incl. an empty contribution, values >= 2^63)
+    from skani_b200.multi_gpu import allgather_sorted_u64
+    mine_u = np.array([], np.uint64) if rank == 1 else np.array([(5 << 32) | 9, (1 << 63) | 7, 3], np.uint64)
+    allp = allgather_sorted_u64(dist, torch, mine_u, world, "cpu")
+    ok = ok and allp.dtype == np.uint64 and allp.tolist() == [3, (5 << 32) | 9, (1 << 63) | 7]
+    allp = allgather_sorted_u64(dist, torch, np.array([10 * rank + 2, 10 * rank + 1], np.uint64), world, "cpu")
+    ok = ok and allp.tolist() == [1, 2, 11, 12]
+    ok = ok and len(allgather_sorted_u64(dist, torch, np.zeros(0, np.uint64), world, "cpu")) == 0
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

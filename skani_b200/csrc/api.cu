@@ -767,14 +767,19 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
   uint64_t max_bytes = 0, max_units = 0;
   size_t SUBBATCH = subbatch_override ? subbatch_override : subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
   if (const char* e = getenv("SK_SUBBATCH_BYTES")) SUBBATCH = std::max<size_t>(1, (size_t)atoll(e));   // test hook: many small sub-batches
+  // large sub-batches amortise the per-sub-batch launches and host synchronisations (which cost most when the GPU is shared with
+  // the chaining worker: profiles/r02_subbatch_ab.md), but nothing can be seeded before the first one is packed and uploaded:
+  // the first two are a quarter and a half of the size
+  const bool ramp = (n_contigs ? contig_off[n_contigs] - contig_off[0] : 0) >= 4 * (uint64_t)SUBBATCH && getenv("SK_SUBBATCH_NO_RAMP") == nullptr;
   while (c0 < n_contigs) {
     uint32_t c1 = c0;
     uint64_t bytes = 0;
+    const uint64_t limit = !ramp ? SUBBATCH : plan.empty() ? SUBBATCH / 4 : plan.size() == 1 ? SUBBATCH / 2 : SUBBATCH;
     while (c1 < n_contigs) {
       uint32_t g = genome_of_contig[c1], c2 = c1;
       while (c2 < n_contigs && genome_of_contig[c2] == g) c2++;
       uint64_t gb = contig_off[c2] - contig_off[c1];
-      if (c1 > c0 && bytes + gb > SUBBATCH) break;
+      if (c1 > c0 && bytes + gb > limit) break;
       bytes += gb;
       c1 = c2;
     }

@@ -142,8 +142,8 @@ constexpr uint32_t PROBE_STAGE_ENTRIES = 2048;   // 16 KB: fits the (otherwise u
 
 // STAGED = the batch is dominated by small ref-role genomes: their tables are bulk-copied to shared memory (generic loads);
 // otherwise every probe is a read-only global load.
-template <bool STAGED>
-__global__ void __launch_bounds__(CT)
+template <bool STAGED, int MINB>
+__global__ void __launch_bounds__(CT, MINB)
 probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const GenomeMeta* __restrict__ m0,
              const GenomeMeta* __restrict__ m1, ChainParams prm, Workspace ws) {
   using Scan = cub::BlockScan<uint64_t, CT>;
@@ -316,7 +316,8 @@ probe_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
 // need = ceil((pos - P0)/F) - 1 (SURVEY App. A.6 with the prefix minimum attained at the anchor itself), so one u32
 // block scan per tile suffices.  Pairs that violate the condition are flagged and redone by the general kernel below.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CT)
+template <int MINB>
+__global__ void __launch_bounds__(CT, MINB)
 chunk_fast_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const GenomeMeta* __restrict__ m0,
                   const GenomeMeta* __restrict__ m1, Workspace ws) {
   using ScanU = cub::BlockScan<uint32_t, CT>;
@@ -519,7 +520,8 @@ chunk_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const G
 // ------------------------------------------------------------------------------------------------------------
 // K3: anchors + chunk descriptors
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CT)
+template <int MINB>
+__global__ void __launch_bounds__(CT, MINB)
 anchor_kernel(const PairDesc* __restrict__ pairs, SetView s0, SetView s1, const GenomeMeta* __restrict__ m0,
               const GenomeMeta* __restrict__ m1, Workspace ws) {
   const uint32_t p = blockIdx.x;
@@ -707,9 +709,10 @@ dp_warp_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
 // Lane gl of a group owns the anchors congruent to gl mod 8; register set s holds the anchor of block (current - s).
 // Group-wide arg-max = two 3-step xor-butterflies (max score, then largest j among the maxima).
 // ------------------------------------------------------------------------------------------------------------
-template <bool TAPS, int GL, int NE>
-__global__ void __launch_bounds__(32)
+template <bool TAPS, int GL, int NE, bool FULLBAND, int MINB>
+__global__ void __launch_bounds__(32, MINB)
 dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
+  // FULLBAND: band == GL * NE, so every candidate distance the register sets can express is inside the band (no test needed)
   // GL lanes per chunk (8 or 4), 32 / GL chunks per warp.  Lane gl of a group owns the anchors congruent to gl mod GL;
   // register set s holds the anchor of block (current - s); a lane evaluates NE candidates per step, which covers every
   // predecessor distance d <= GL * NE (band = 20 at c = 125: NE = 5 with 4 lanes, 3 with 8).
@@ -746,7 +749,9 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
     {
       AnchorRec x; x.qpos = 0; x.rpos = 0; x.rc = 0xFFFFFFFEu;            // impossible contig: never matches
       if (idx < n) { x = a[idx]; g_key[idx] = (unsigned long long)idx; }
-      q[0] = x.qpos; r[0] = x.rpos; rc[0] = x.rc; sc[0] = 0; rt[0] = idx; dpth[0] = 1;
+      // the ref position is held NEGATED for reverse-strand anchors: two anchors can only chain on the same contig and
+      // strand, and then (r' of the current) - (r' of the candidate) is the reference's strand-corrected ref gap directly
+      q[0] = x.qpos; r[0] = (x.rc & 1u) ? (0u - x.rpos) : x.rpos; rc[0] = x.rc; sc[0] = 0; rt[0] = idx; dpth[0] = 1;
       my_ptr = idx;
     }
     __syncwarp();
@@ -758,37 +763,35 @@ dp_group_kernel(uint64_t n_chunks, ChainParams prm, Workspace ws) {
       cur.qpos = __shfl_sync(FULL, q[0], src);
       cur.rpos = __shfl_sync(FULL, r[0], src);
       cur.rc = __shfl_sync(FULL, rc[0], src);
-      int32_t best_ns = 0;
-      uint32_t best_d = 0;                                                 // i - j of the lane's best candidate (0 = none)
+      // The candidate in register set s is the predecessor at distance d = m - gl + GL * s.  Lanes that own an anchor of the
+      // current block already scored (gl < m) use the sets 0 .. NE-1, the others 1 .. NE: the sets 1 .. NE-1 are common to all
+      // lanes (no selects), only ONE "edge" candidate per lane is picked between set 0 and set NE.  The lane's best candidate
+      // is kept as ONE key, (score - 1) << 5 | (31 - d): its maximum is the maximal score and, among those, the smallest
+      // distance = largest j -- the reference's strict `>` while scanning j downward (src/chain.rs:853-880) -- and the group
+      // arg-max is a single butterfly.  Keys of admissible candidates are > 0 (score >= 1, d <= 24).
+      int32_t best = 0;
       const bool lo_set = gl < m;
-#pragma unroll
-      for (int t = 0; t < NB - 1; t++) {                                   // ascending t = descending j: strict > keeps the largest j
-        const uint32_t qs = lo_set ? q[t] : q[t + 1];
-        const uint32_t rs = lo_set ? r[t] : r[t + 1];
-        const uint32_t rcs = lo_set ? rc[t] : rc[t + 1];
-        const int32_t scs = lo_set ? sc[t] : sc[t + 1];
-        const uint32_t d = m + (uint32_t)GL * (uint32_t)t + (lo_set ? 0u : (uint32_t)GL) - gl; // i - j >= 1
+      auto eval = [&](uint32_t qs, uint32_t rs, uint32_t rcs, int32_t scs, uint32_t d) {
         const uint32_t dq = cur.qpos - qs;
-        const uint32_t tr = cur.rpos - rs;
-        const uint32_t dr = (cur.rc & 1u) ? (0u - tr) : tr;
+        const uint32_t dr = cur.rpos - rs;                                   // strand-corrected (see the load above)
         const uint32_t g = dr - dq;
-        const bool ok = (d <= band) & (rcs == cur.rc) & (dq - 1u < BP_CHAIN_BAND) & (dr - 1u < (uint32_t)MAX_LIN) &
+        const bool ok = (FULLBAND || d <= band) & (rcs == cur.rc) & (dq - 1u < BP_CHAIN_BAND) & (dr - 1u < (uint32_t)MAX_LIN) &
                         (g + (uint32_t)MAX_GAP <= 2u * (uint32_t)MAX_GAP);
         const int32_t gi = (int32_t)g;
-        const int32_t ns = scs + ANCHOR_SCORE - (gi < 0 ? -gi : gi);
-        const bool take = ok & (ns > best_ns);                               // branch-free: keeps the warp converged
-        best_ns = take ? ns : best_ns;
-        best_d = take ? d : best_d;
-      }
-      // group arg-max: maximal score, then the smallest distance d (= largest j) among the maxima
-      int32_t smax = best_ns;
+        const int32_t nsm1 = scs + (ANCHOR_SCORE - 1) - (gi < 0 ? -gi : gi);
+        const int32_t key = (int32_t)(((uint32_t)nsm1 << 5) | (31u - d));
+        best = max(best, ok ? key : 0);
+      };
 #pragma unroll
-      for (int o = GL / 2; o > 0; o >>= 1) smax = max(smax, __shfl_xor_sync(FULL, smax, o));
-      uint32_t dkey = (best_ns == smax && smax > 0) ? (64u - best_d) : 0u;   // d <= 31, so 64 - d > 0
+      for (int s2 = 1; s2 < NE; s2++) eval(q[s2], r[s2], rc[s2], sc[s2], m + (uint32_t)(GL * s2) - gl);
+      eval(lo_set ? q[0] : q[NE], lo_set ? r[0] : r[NE], lo_set ? rc[0] : rc[NE], lo_set ? sc[0] : sc[NE],
+           m - gl + (lo_set ? 0u : (uint32_t)(GL * NE)));
+      int32_t kmax = best;
 #pragma unroll
-      for (int o = GL / 2; o > 0; o >>= 1) dkey = max(dkey, __shfl_xor_sync(FULL, dkey, o));
-      const bool has = dkey != 0u;
-      const uint32_t dwin = 64u - dkey;
+      for (int o = GL / 2; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(FULL, kmax, o));
+      const bool has = kmax > 0;
+      const int32_t smax = (kmax >> 5) + 1;
+      const uint32_t dwin = 31u - ((uint32_t)kmax & 31u);
       const uint32_t jw = i - dwin;                                          // only meaningful when has
       // winner's root / depth: owner lane = jw mod GL, set = block distance
       const int sidx = (int)(b0 >> LG) - (int)(jw >> LG);
@@ -1589,6 +1592,9 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   SK_CUDA(cudaMemsetAsync(ws.pair_nchains, 0, B * 4, st));
   SK_CUDA(cudaMemsetAsync(ws.pair_tqb_ns, 0, B * 4, st));
 
+  // A/B hook: register caps that raise the resident blocks per SM of the latency-bound block-per-pair kernels
+  // (bit 0 probe: 5 blocks, bit 1 chunk_fast: 6, bit 2 anchor: 6); see profiles/r02_occupancy_ab.md
+  const int occ = getenv("SK_OCC") ? atoi(getenv("SK_OCC")) : 0;
   {
     // small ref-role genomes (k-mer table <= 16 KB): TMA-stage the table in shared memory when they dominate the batch
     size_t n_small = 0;
@@ -1599,10 +1605,12 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
       if (!rs_->ht_off.empty()) { const uint64_t cap = rs_->ht_off[d.rg + 1] - rs_->ht_off[d.rg]; if (cap && cap <= PROBE_STAGE_ENTRIES) n_small++; }
     }
     const bool staged = (getenv("SK_PROBE_TMA") ? atoi(getenv("SK_PROBE_TMA")) != 0 : true) && 2 * n_small >= (size_t)B;
-    if (staged) SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<true><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
-    else SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<false><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+    if (staged) SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<true, 1><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+    else if (occ & 1) SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<false, 5><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+    else SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<false, 1><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
   }
-  SK_LAUNCH(ctx, "chunk_fast_kernel", (chunk_fast_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
+  if (occ & 2) SK_LAUNCH(ctx, "chunk_fast_kernel", (chunk_fast_kernel<6><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
+  else SK_LAUNCH(ctx, "chunk_fast_kernel", (chunk_fast_kernel<1><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
   SK_LAUNCH(ctx, "chunk_kernel", (chunk_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
   std::vector<uint32_t> hA(B), hC(B);
   SK_CUDA(cudaMemcpyAsync(hA.data(), ws.pairA, B * 4, cudaMemcpyDeviceToHost, st));
@@ -1631,7 +1639,8 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   if (TC > 0) {
     SK_CUDA(h2d_small(ctx, ws.chunk_first + TC, &TA, 8));
     init_chunk_acc_kernel<<<(uint32_t)((TC + 255) / 256), 256, 0, st>>>(TC, ws); count_launch(ctx);
-    SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
+    if (occ & 4) SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<6><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
+    else SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<1><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
     {
       const uint32_t grid = (uint32_t)TC;
       const uint32_t nb = prm.band / 32 + 2;   // register sets per lane: current block + ceil(band / 32) earlier ones
@@ -1640,6 +1649,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   else SK_LAUNCH(ctx, "dp_kernel", (dp_warp_kernel<NBV, false><<<grid, 32, 0, st>>>(TC, prm, ws)));
       if (prm.band <= 24 && getenv("SK_DP_WARP") == nullptr) {   // 4 chunks per warp, 8 lanes each
         const int dp_gl = getenv("SK_DP_GL") ? atoi(getenv("SK_DP_GL")) : 4;   // lanes per chunk: 4 (default: 1.25x faster, profiles/r02_dp_lanes.md) or 8
+        const int dp_minb = getenv("SK_DP_MINB") ? atoi(getenv("SK_DP_MINB")) : 25;   // register cap: 72 registers = 28 resident warps per SM (A/B: 1 = uncapped)
         const uint32_t gw = dp_gl == 4 ? 8 : 4;
         const uint32_t g4 = (uint32_t)((TC + gw - 1) / gw);
         // group chunks of similar size: sort chunk ids by descending anchor count (cub radix sort, ~0.1 ms per batch)
@@ -1652,8 +1662,10 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
         SK_CUDA(cub::DeviceRadixSort::SortPairsDescending(S.sort_tmp, tb, ws.chunk_size, ws.chunk_size_sorted, ws.chunk_id, ws.chunk_perm, (int)TC, 0, 32, st));
 #define DPG(GLV, NEV)                                                                                                   \
   {                                                                                                                    \
-    if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true, GLV, NEV><<<g4, 32, 0, st>>>(TC, prm, ws)));           \
-    else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, GLV, NEV><<<g4, 32, 0, st>>>(TC, prm, ws)));              \
+    if (dbg) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<true, GLV, NEV, false, 1><<<g4, 32, 0, st>>>(TC, prm, ws)));    \
+    else if (prm.band == GLV * NEV && dp_minb > 1) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, GLV, NEV, true, 25><<<g4, 32, 0, st>>>(TC, prm, ws)));  \
+    else if (prm.band == GLV * NEV) SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, GLV, NEV, true, 1><<<g4, 32, 0, st>>>(TC, prm, ws)));  \
+    else SK_LAUNCH(ctx, "dp_kernel", (dp_group_kernel<false, GLV, NEV, false, 1><<<g4, 32, 0, st>>>(TC, prm, ws)));       \
   }
         if (dp_gl == 4) { if (prm.band <= 20) DPG(4, 5) else DPG(4, 6) }
         else { DPG(8, 3) }

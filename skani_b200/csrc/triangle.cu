@@ -202,7 +202,9 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
       return SK_OK;
     };
     sk::HostSeq seq; seq.ascii = bases;
-    int rc = sk::sketch_batch_host(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, nullptr, &on_part, 1024ull << 20);
+    // sub-batches of 1 .. 2 GiB (about 1/16 of the input): 2 GiB measured 10 % faster end to end than 1 GiB on the 50 GB run
+    const size_t subbatch = (size_t)std::min<uint64_t>(2048ull << 20, std::max<uint64_t>(1024ull << 20, total_bytes / 16));
+    int rc = sk::sketch_batch_host(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, nullptr, &on_part, subbatch);
     { std::lock_guard<std::mutex> lk(mu); q.push_back(Wave{nullptr, 0, true}); }
     cv.notify_one();
     worker.join();

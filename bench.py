@@ -397,8 +397,11 @@ def main():
             t0 = time.perf_counter()
             ev0.record(stream)
             kept = 0
+            per_step = []
             for _ in range(n_steps):
-                kept = step(e2e)
+                ts = time.perf_counter()
+                kept = step(e2e)                      # blocks until the step's results are on the host
+                per_step.append(round((time.perf_counter() - ts) * 1e3, 1))
             ev1.record(stream)
             torch.cuda.synchronize()
             if world > 1:
@@ -410,6 +413,7 @@ def main():
                 t = torch.tensor([ms], device="cuda")
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
                 ms = float(t.item())
+            last["step_ms_e2e" if e2e else "step_ms_value"] = per_step   # rank-local wall clock of each step (spread, not the metric)
             return ms / n_steps, kept, ctx.launches - l0
 
         # value leg first (needs the device-resident copy of the bases), then the roofline probes, then drop the device copy
@@ -443,7 +447,7 @@ def main():
         expected = expected_pairs(N, G)
         return {"order": order, "value": total_pairs / (ms_val * 1e-3), "ms_per_step": ms_val, "launches": int(launches),
                 "e2e_value": total_pairs / (ms_e2e * 1e-3), "e2e_ms_per_step": ms_e2e, "d2h": int(d2h), "host_gen_s": round(t_gen, 2),
-                "host_pack_share": round(pack_share, 3),
+                "host_pack_share": round(pack_share, 3), "step_ms_value": last.get("step_ms_value"), "step_ms_e2e": last.get("step_ms_e2e"),
                 "verify": {"kept_pairs_all_ranks": ck_e2e[0], "kept_pairs_expected": expected, "kept_ok": ck_e2e[0] == expected == ck_val[0],
                            "checksum_e2e": "%016x" % ck_e2e[1], "checksum_value_leg": "%016x" % ck_val[1],
                            "legs_agree": ck_e2e == ck_val, "oracle_spot_check": spot},
@@ -467,7 +471,8 @@ def main():
                 "dtype": "u64", "data": "synthetic",
                 "config": {"workload": workload_name(cfg), "genomes": N, "genome_len": L, "pairs": total_pairs, "order": "contiguous (clusters adjacent)",
                            "host_gen_s": m["host_gen_s"], "verify": m["verify"]},
-                "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms_per_step"],
+                "step_ms_rank0": m["step_ms_value"],
+                "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms_per_step"], "step_ms_rank0": m["step_ms_e2e"],
                         "h2d_bytes_per_step": int(N * L * (1.0 - 0.75 * m["host_pack_share"])), "d2h_bytes_per_step": m["d2h"],
                         "host_bytes_per_step": int(N * L), "host_pack_share": m["host_pack_share"],
                         "note": "inputs = ASCII in pinned host memory; host_pack_share of the bases is converted to 2-bit on the host "

@@ -336,6 +336,7 @@ int sk_ctx_destroy(sk_ctx* ctx) {
   }
   ctx->arena.destroy();
   if (ctx->stage) cudaFreeHost(ctx->stage);
+  for (auto& b : ctx->mbox_blocks) cudaFreeHost(b.first);
   for (int i = 0; i < 2; i++) {
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
     if (ctx->pinned_free[i]) cudaEventDestroy(ctx->pinned_free[i]);
@@ -1241,7 +1242,7 @@ int sk_sketch_set_import_batch(sk_ctx* ctx, const sk_sketch_params* sp, uint32_t
   if (n_markers) SK_CUDA(cudaMemcpy(mraw.p, markers + m0, n_markers * 8, cudaMemcpyHostToDevice));
   std::vector<uint64_t> raw_off(G + 1);
   for (uint32_t g = 0; g <= G; g++) raw_off[g] = mk_off[g] - m0;
-  SK_TRY(build_views(ctx, s, mraw.p, raw_off));
+  SK_TRY(build_views(ctx, s, mraw.p, raw_off.data()));
   SK_TRY(build_hash(ctx, s));
   SK_CUDA(cudaStreamSynchronize(ctx->stream));
   guard.s = nullptr;

@@ -1592,9 +1592,9 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   SK_CUDA(cudaMemsetAsync(ws.pair_nchains, 0, B * 4, st));
   SK_CUDA(cudaMemsetAsync(ws.pair_tqb_ns, 0, B * 4, st));
 
-  // A/B hook: register caps that raise the resident blocks per SM of the latency-bound block-per-pair kernels
-  // (bit 0 probe: 5 blocks, bit 1 chunk_fast: 6, bit 2 anchor: 6); see profiles/r02_occupancy_ab.md
-  const int occ = getenv("SK_OCC") ? atoi(getenv("SK_OCC")) : 0;
+  // resident blocks per SM of the block-per-pair kernels (register caps through __launch_bounds__), measured in
+  // profiles/r02_occupancy_ab.md: probe 4 (5 blocks = 48 registers is 10 % slower, 2 blocks = 93 registers 33 % slower),
+  // anchor 6 (40 registers: 8 % faster than 72), chunk_fast 5 (indifferent)
   {
     // small ref-role genomes (k-mer table <= 16 KB): TMA-stage the table in shared memory when they dominate the batch
     size_t n_small = 0;
@@ -1605,12 +1605,10 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
       if (!rs_->ht_off.empty()) { const uint64_t cap = rs_->ht_off[d.rg + 1] - rs_->ht_off[d.rg]; if (cap && cap <= PROBE_STAGE_ENTRIES) n_small++; }
     }
     const bool staged = (getenv("SK_PROBE_TMA") ? atoi(getenv("SK_PROBE_TMA")) != 0 : true) && 2 * n_small >= (size_t)B;
-    if (staged) SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<true, 1><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
-    else if (occ & 1) SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<false, 5><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
-    else SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<false, 1><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+    if (staged) SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<true, 4><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
+    else SK_LAUNCH(ctx, "probe_kernel", (probe_kernel<false, 4><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, prm, ws)));
   }
-  if (occ & 2) SK_LAUNCH(ctx, "chunk_fast_kernel", (chunk_fast_kernel<6><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
-  else SK_LAUNCH(ctx, "chunk_fast_kernel", (chunk_fast_kernel<1><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
+  SK_LAUNCH(ctx, "chunk_fast_kernel", (chunk_fast_kernel<5><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
   SK_LAUNCH(ctx, "chunk_kernel", (chunk_kernel<<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
   std::vector<uint32_t> hA(B), hC(B);
   SK_CUDA(cudaMemcpyAsync(hA.data(), ws.pairA, B * 4, cudaMemcpyDeviceToHost, st));
@@ -1639,8 +1637,7 @@ static int run_batch(sk_ctx* ctx, ChainScratch& S, const sk_sketch_set* refs, co
   if (TC > 0) {
     SK_CUDA(h2d_small(ctx, ws.chunk_first + TC, &TA, 8));
     init_chunk_acc_kernel<<<(uint32_t)((TC + 255) / 256), 256, 0, st>>>(TC, ws); count_launch(ctx);
-    if (occ & 4) SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<6><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
-    else SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<1><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
+    SK_LAUNCH(ctx, "anchor_kernel", (anchor_kernel<6><<<B, CT, 0, st>>>(S.d_pairs, v0, v1, S.d_m0, S.d_m1, ws)));
     {
       const uint32_t grid = (uint32_t)TC;
       const uint32_t nb = prm.band / 32 + 2;   // register sets per lane: current block + ceil(band / 32) earlier ones

@@ -193,6 +193,18 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32
   dst[i] = (k >= src_len) ? total : src[k];
 }
 
+// same, the value for "one past the end" taken from the device: last element + its own count (the popcount of the last pass
+// mask, or the last flag) -- the host does not have to know the total before this kernel is queued
+__global__ void gather_u32_tail_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n,
+                                       uint32_t src_len, const uint32_t* __restrict__ tail, int tail_is_mask,
+                                       uint32_t* __restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = idx[i];
+  if (k >= src_len) { const uint32_t t = tail[src_len - 1]; dst[i] = src[src_len - 1] + (tail_is_mask ? (uint32_t)__popc(t) : t); }
+  else dst[i] = src[k];
+}
+
 __global__ void marker_flag_kernel(const uint64_t* __restrict__ mkv, uint32_t n, uint32_t* __restrict__ flag) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flag[i] = (mkv[i] != ~0ull) ? 1u : 0u;
@@ -253,7 +265,7 @@ __global__ void kview_gather_kernel(const uint64_t* __restrict__ seg_off, const 
 // hscan = exclusive scan of head flags (global).  Group id of sorted element i = hscan[i] + head[i] - 1 (global);
 // writes distinct k-mers and local group starts (+ one sentinel per genome), then multiplicities per pv record.
 __global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint64_t* __restrict__ skmer, uint64_t kmask,
-                              const uint32_t* __restrict__ head, const uint32_t* __restrict__ hscan, uint32_t total_groups,
+                              const uint32_t* __restrict__ head, const uint32_t* __restrict__ hscan,
                               uint32_t n_genomes, uint32_t* __restrict__ ukmer, uint32_t* __restrict__ ustart, uint32_t ibits) {
   uint32_t g = blockIdx.x;
   uint64_t b = seg_off[g], e = seg_off[g + 1];
@@ -267,7 +279,7 @@ __global__ void groups_kernel(const uint64_t* __restrict__ seg_off, const uint64
   if (threadIdx.x == 0 && blockIdx.y == 0) {
     // sentinel of genome g sits right after its last group: global group index of next genome's first group
     uint64_t total = seg_off[n_genomes];
-    uint32_t next_gid = (e < total) ? hscan[e] : total_groups;  // head[e] is always 1, so hscan[e] = #groups before e
+    uint32_t next_gid = (e < total) ? hscan[e] : hscan[total - 1] + head[total - 1];  // head[e] is always 1, so hscan[e] = #groups before e; past the end: all groups
     ustart[next_gid + g] = (uint32_t)(e - b);
   }
 }
@@ -321,9 +333,33 @@ __global__ void gather_scan_at_kernel(const uint32_t* __restrict__ scan, const u
   if (i < n) out[i] = (at[i] >= len) ? (uint64_t)total : (uint64_t)scan[at[i]];
 }
 
+__global__ void gather_scan_at_tail_kernel(const uint32_t* __restrict__ scan, const uint64_t* __restrict__ at, uint32_t n,
+                                           uint64_t len, const uint32_t* __restrict__ flag, uint64_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (at[i] >= len) ? (uint64_t)(scan[len - 1] + flag[len - 1]) : (uint64_t)scan[at[i]];
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+// pinned landing space for an asynchronous device->host readback (valid until the next mbox_reset)
+static void* mbox_alloc(sk_ctx* ctx, size_t bytes) {
+  bytes = (bytes + 63) & ~(size_t)63;
+  for (;;) {
+    if (ctx->mbox_block < ctx->mbox_blocks.size()) {
+      auto& b = ctx->mbox_blocks[ctx->mbox_block];
+      if (ctx->mbox_pos + bytes <= b.second) { void* p = b.first + ctx->mbox_pos; ctx->mbox_pos += bytes; return p; }
+      ctx->mbox_block++; ctx->mbox_pos = 0;
+      continue;
+    }
+    uint8_t* p = nullptr;
+    const size_t cap = std::max<size_t>(bytes, 1u << 20);
+    if (cudaHostAlloc((void**)&p, cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->mbox_blocks.push_back({p, cap});
+  }
+}
+static void mbox_reset(sk_ctx* ctx) { ctx->mbox_block = 0; ctx->mbox_pos = 0; }
+
 static inline uint32_t div_up(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 template <typename T>
@@ -458,7 +494,10 @@ int build_hash_range(sk_ctx* ctx, sk_sketch_set* set, uint32_t g_begin) {
 
 // Given the position view (pv_kmer/pv_pos/pv_cc filled, set->seed_off known) and the raw (unsorted, possibly
 // duplicated) markers per genome, build the k-mer view, groups, multiplicities and the sorted distinct marker arrays.
-int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const std::vector<uint64_t>& raw_mk_off) {
+int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const uint64_t* raw_mk_off) {
+  // Host synchronisations: ONE in the middle (the raw marker counts are needed to size the marker sort; by then the whole
+  // k-mer view is queued behind it, so the device does not idle) and one at the end.  Everything whose size only the device
+  // knows yet (distinct k-mers, distinct markers) is allocated at its upper bound and the totals are read back at the end.
   const uint32_t G = set->G;
   const size_t S = set->S;
   cudaStream_t st = ctx->stream;
@@ -469,6 +508,9 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
   SK_CUDA(ctx->arena.alloc((void**)&set->kv_cc, std::max<size_t>(S, 1) * 4));
   SK_CUDA(ctx->arena.alloc((void**)&set->pv_mult, std::max<size_t>(S, 1) * 2));
   set->uk_off.assign(G + 1, 0);
+  uint64_t* h_ukoff = (uint64_t*)mbox_alloc(ctx, (size_t)(G + 1) * 8);
+  uint64_t* h_mkoff = (uint64_t*)mbox_alloc(ctx, (size_t)(G + 1) * 8);
+  if (!h_ukoff || !h_mkoff) { ctx->err = "out of pinned host memory"; return SK_ERR_NOMEM; }
   if (S > 0) {
     if (S >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 seed records"; return SK_ERR_PARAM; }
     DTmp<uint32_t> vals, perm, head, hscan;
@@ -499,35 +541,32 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     kview_gather_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, perm.p, set->pv_pos, set->pv_cc, set->kv_pos,
                                            set->kv_cc, head.p, ibits); count_launch(ctx);
     SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, S));
-    // total groups and per-genome group offsets
+    // per-genome group offsets (+ the total in the last slot) -> host, asynchronously
     DTmp<uint64_t> d_ukoff;
     SK_CUDA(d_ukoff.alloc(G + 1, ctx));
-    uint32_t last_head = 0, last_scan = 0;
-    SK_CUDA(cudaMemcpyAsync(&last_head, head.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
-    SK_CUDA(cudaMemcpyAsync(&last_scan, hscan.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
-    SK_CUDA(cudaStreamSynchronize(st));
-    uint32_t U = last_head + last_scan;
-    gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_seed_off.p, G + 1, S, U, d_ukoff.p); count_launch(ctx);
-    SK_CUDA(cudaMemcpyAsync(set->uk_off.data(), d_ukoff.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
-    set->U = U;
-    SK_CUDA(ctx->arena.alloc((void**)&set->ukmer, std::max<size_t>(U, 1) * 4));
-    SK_CUDA(ctx->arena.alloc((void**)&set->ustart, (size_t)(U + G) * 4));
-    groups_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, kmask, head.p, hscan.p, U, G, set->ukmer, set->ustart, ibits); count_launch(ctx);
+    gather_scan_at_tail_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_seed_off.p, G + 1, S, head.p, d_ukoff.p); count_launch(ctx);
+    SK_CUDA(cudaMemcpyAsync(h_ukoff, d_ukoff.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(ctx->arena.alloc((void**)&set->ukmer, S * 4));                       // upper bound: distinct k-mers <= records
+    SK_CUDA(ctx->arena.alloc((void**)&set->ustart, (size_t)(S + G + 1) * 4));
+    groups_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, skmer.p, kmask, head.p, hscan.p, G, set->ukmer, set->ustart, ibits); count_launch(ctx);
     mult_kernel<<<dim3(G, 8), 256, 0, st>>>(d_seed_off.p, head.p, hscan.p, perm.p, set->ustart, set->pv_mult, skmer.p, ibits); count_launch(ctx);
-    SK_CUDA(cudaStreamSynchronize(st));
   } else {
     set->U = 0;
     SK_CUDA(ctx->arena.alloc((void**)&set->ukmer, 4));
     SK_CUDA(ctx->arena.alloc((void**)&set->ustart, (size_t)(G + 1) * 4));
     SK_CUDA(cudaMemsetAsync(set->ustart, 0, (size_t)(G + 1) * 4, st));
+    for (uint32_t g = 0; g <= G; g++) h_ukoff[g] = 0;
   }
+  SK_CUDA(cudaStreamSynchronize(st));      // raw marker offsets (queued by the caller) and group offsets have landed
+  for (uint32_t g = 0; g <= G; g++) set->uk_off[g] = h_ukoff[g];
+  set->U = (size_t)set->uk_off[G];
   // ---- markers: per-genome sort + dedup (HashSet semantics, reference src/types.rs:269)
   const size_t MR = raw_mk_off[G];
   set->mk_off.assign(G + 1, 0);
   if (MR > 0) {
     if (MR >= (1ull << 31)) { ctx->err = "sub-batch has >= 2^31 markers"; return SK_ERR_PARAM; }
     SK_CUDA(d_rawmk_off.alloc(G + 1, ctx));
-    SK_CUDA(h2d_small(ctx, d_rawmk_off.p, raw_mk_off.data(), (G + 1) * 8));
+    SK_CUDA(h2d_small(ctx, d_rawmk_off.p, raw_mk_off, (G + 1) * 8));
     DTmp<uint64_t> sorted;
     SK_CUDA(sorted.alloc(MR, ctx));
     size_t tb = 0;
@@ -551,19 +590,15 @@ int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const s
     SK_CUDA(head.alloc(MR, ctx)); SK_CUDA(hscan.alloc(MR, ctx));
     marker_head_kernel<<<dim3(G, 8), 256, 0, st>>>(d_rawmk_off.p, sorted.p, head.p); count_launch(ctx);
     SK_TRY(scan_exclusive<uint32_t>(ctx, head.p, hscan.p, MR));
-    uint32_t lh = 0, ls = 0;
-    SK_CUDA(cudaMemcpyAsync(&lh, head.p + (MR - 1), 4, cudaMemcpyDeviceToHost, st));
-    SK_CUDA(cudaMemcpyAsync(&ls, hscan.p + (MR - 1), 4, cudaMemcpyDeviceToHost, st));
-    SK_CUDA(cudaStreamSynchronize(st));
-    uint32_t M = lh + ls;
-    set->M = M;
-    SK_CUDA(ctx->arena.alloc((void**)&set->markers, std::max<size_t>(M, 1) * 8));
+    SK_CUDA(ctx->arena.alloc((void**)&set->markers, MR * 8));                 // upper bound: distinct markers <= raw markers
     marker_compact_kernel<<<div_up(MR, 256), 256, 0, st>>>(sorted.p, head.p, hscan.p, (uint32_t)MR, global_sort ? ((1ull << (2 * MARKER_K)) - 1) : ~0ull, set->markers); count_launch(ctx);
     DTmp<uint64_t> d_mkoff;
     SK_CUDA(d_mkoff.alloc(G + 1, ctx));
-    gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_rawmk_off.p, G + 1, MR, M, d_mkoff.p); count_launch(ctx);
-    SK_CUDA(cudaMemcpyAsync(set->mk_off.data(), d_mkoff.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
+    gather_scan_at_tail_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(hscan.p, d_rawmk_off.p, G + 1, MR, head.p, d_mkoff.p); count_launch(ctx);
+    SK_CUDA(cudaMemcpyAsync(h_mkoff, d_mkoff.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t g = 0; g <= G; g++) set->mk_off[g] = h_mkoff[g];
+    set->M = (size_t)set->mk_off[G];
   } else {
     set->M = 0;
     SK_CUDA(ctx->arena.alloc((void**)&set->markers, 8));
@@ -637,7 +672,9 @@ int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_
 
   DTmp<uint64_t> d_coff, Pown;
   DTmp<uint32_t> d_cuoff, d_clen, d_clocal, d_ucoarse, NMown, PM, uoff;
-  std::vector<uint64_t> raw_mk_off(G + 1, 0);
+  mbox_reset(ctx);                           // no readback of an earlier sub-batch is in flight (each one ends synchronised)
+  uint64_t* h_raw_mk_off = (uint64_t*)mbox_alloc(ctx, (size_t)(G + 1) * 8);    // raw markers per genome (prefix offsets), pinned
+  if (h_raw_mk_off) for (uint32_t g = 0; g <= G; g++) h_raw_mk_off[g] = 0;
   DTmp<uint64_t> mkv, mraw;
   if (NU > 0) {
     SK_CUDA(d_coff.alloc(n_contigs + 1, ctx)); SK_CUDA(d_cuoff.alloc(n_contigs + 1, ctx));
@@ -678,17 +715,17 @@ int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_
       SK_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_it, uoff.p, (int)NU, st));
       count_launch(ctx, 2);
     }
-    uint32_t last_pm = 0, last_off = 0;
-    SK_CUDA(cudaMemcpyAsync(&last_pm, PM.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
-    SK_CUDA(cudaMemcpyAsync(&last_off, uoff.p + (NU - 1), 4, cudaMemcpyDeviceToHost, st));
-    // record offset of every contig's first unit (-> per-genome offsets and per-contig record offsets)
+    // record offset of every contig's first unit (-> per-genome offsets and per-contig record offsets); the entry past the last
+    // contig is the total number of records, computed on the device: ONE host synchronisation delivers everything the host
+    // needs to size the record arrays and lay out the set
     DTmp<uint32_t> d_crec;
     SK_CUDA(d_crec.alloc(n_contigs + 1, ctx));
+    gather_u32_tail_kernel<<<div_up(n_contigs + 1, 256), 256, 0, st>>>(uoff.p, d_cuoff.p, n_contigs + 1, NU, PM.p, 1, d_crec.p); count_launch(ctx);
+    uint32_t* crec = (uint32_t*)mbox_alloc(ctx, (size_t)(n_contigs + 1) * 4);
+    if (!crec || !h_raw_mk_off) { ctx->err = "out of pinned host memory"; return SK_ERR_NOMEM; }
+    SK_CUDA(cudaMemcpyAsync(crec, d_crec.p, (size_t)(n_contigs + 1) * 4, cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaStreamSynchronize(st));
-    const uint32_t S = (uint32_t)__builtin_popcount(last_pm) + last_off;
-    gather_u32_kernel<<<div_up(n_contigs + 1, 256), 256, 0, st>>>(uoff.p, d_cuoff.p, n_contigs + 1, NU, S, d_crec.p); count_launch(ctx);
-    std::vector<uint32_t> crec(n_contigs + 1);
-    SK_CUDA(cudaMemcpyAsync(crec.data(), d_crec.p, (n_contigs + 1) * 4, cudaMemcpyDeviceToHost, st));
+    const uint32_t S = crec[n_contigs];      // cuoff[n_contigs] == NU: "past the end"
     set->S = S;
     SK_CUDA(ctx->arena.alloc((void**)&set->pv_kmer, std::max<size_t>(S, 1) * 4));
     SK_CUDA(ctx->arena.alloc((void**)&set->pv_pos, std::max<size_t>(S, 1) * 4));
@@ -696,7 +733,6 @@ int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_
     SK_CUDA(mkv.alloc(S, ctx));
     SK_LAUNCH(ctx, "expand_kernel", (expand_kernel<<<div_up(NU, 256), 256, 0, st>>>(
         P, d_ucoarse.p, d_cuoff.p, d_clocal.p, NU, PM.p, uoff.p, seed_mask, thr_m, set->pv_kmer, set->pv_pos, set->pv_cc, mkv.p)));
-    SK_CUDA(cudaStreamSynchronize(st));
     // per-genome record offsets + per-contig local record offsets (with one sentinel per genome)
     std::vector<uint32_t> crl(n_contigs + G + 1, 0);
     for (uint32_t g = 0; g < G; g++) {
@@ -709,25 +745,21 @@ int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_
     }
     set->seed_off[G] = S;
     SK_CUDA(h2d_small(ctx, set->ctg_rec_off, crl.data(), (size_t)(n_contigs + G) * 4));
-    // raw markers: compact the flagged values (order inside a genome is irrelevant: they are sorted + deduped next)
+    // raw markers: compact the flagged values (order inside a genome is irrelevant: they are sorted + deduped next).  Their
+    // number is not known to the host yet: the buffer takes the upper bound (one per record), the per-genome offsets travel to
+    // the host asynchronously and are read after build_views' first synchronisation.
     if (S > 0) {
       DTmp<uint32_t> mflag, mscan;
       SK_CUDA(mflag.alloc(S, ctx)); SK_CUDA(mscan.alloc(S, ctx));
       marker_flag_kernel<<<div_up(S, 256), 256, 0, st>>>(mkv.p, S, mflag.p); count_launch(ctx);
       SK_TRY(scan_exclusive<uint32_t>(ctx, mflag.p, mscan.p, S));
-      uint32_t lf = 0, ls = 0;
-      SK_CUDA(cudaMemcpyAsync(&lf, mflag.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
-      SK_CUDA(cudaMemcpyAsync(&ls, mscan.p + (S - 1), 4, cudaMemcpyDeviceToHost, st));
       DTmp<uint64_t> d_so, d_mo;
       SK_CUDA(d_so.alloc(G + 1, ctx)); SK_CUDA(d_mo.alloc(G + 1, ctx));
       SK_CUDA(h2d_small(ctx, d_so.p, set->seed_off.data(), (G + 1) * 8));
-      SK_CUDA(cudaStreamSynchronize(st));
-      uint32_t MR = lf + ls;
-      SK_CUDA(mraw.alloc(MR, ctx));
+      SK_CUDA(mraw.alloc(S, ctx));
       marker_scatter_kernel<<<div_up(S, 256), 256, 0, st>>>(mkv.p, mscan.p, S, mraw.p); count_launch(ctx);
-      gather_scan_at_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(mscan.p, d_so.p, G + 1, S, MR, d_mo.p); count_launch(ctx);
-      SK_CUDA(cudaMemcpyAsync(raw_mk_off.data(), d_mo.p, (G + 1) * 8, cudaMemcpyDeviceToHost, st));
-      SK_CUDA(cudaStreamSynchronize(st));
+      gather_scan_at_tail_kernel<<<div_up(G + 1, 256), 256, 0, st>>>(mscan.p, d_so.p, G + 1, S, mflag.p, d_mo.p); count_launch(ctx);
+      SK_CUDA(cudaMemcpyAsync(h_raw_mk_off, d_mo.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
     }
   } else {
     set->S = 0;
@@ -736,7 +768,8 @@ int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_
   }
   // free the big per-base temporaries before the sort temporaries are allocated
   Pown.release(); NMown.release(); PM.release(); uoff.release(); mkv.release();
-  SK_TRY(build_views(ctx, set, mraw.p, raw_mk_off));
+  if (!h_raw_mk_off) { ctx->err = "out of pinned host memory"; return SK_ERR_NOMEM; }
+  SK_TRY(build_views(ctx, set, mraw.p, h_raw_mk_off));
   SK_CUDA(cudaStreamSynchronize(st));
   guard.s = nullptr;
   *out = set;

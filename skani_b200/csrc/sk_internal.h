@@ -78,6 +78,10 @@ struct sk_ctx {
   // stream instead of the H2D copy engine, which may be busy for tens of ms with bulk sequence uploads
   uint8_t* stage = nullptr;
   size_t stage_cap = 0, stage_pos = 0;
+  // pinned landing blocks for small device->host readbacks (a pageable target makes cudaMemcpyAsync block the host):
+  // bump-allocated per seeding sub-batch, reset when the sub-batch is done (seeding.cu)
+  std::vector<std::pair<uint8_t*, size_t>> mbox_blocks;
+  size_t mbox_block = 0, mbox_pos = 0;
   sk_ctx* child = nullptr;               // worker context of the pipelined sk_triangle (second stream + own workspaces)
   // grow-only chaining workspace (chain.cu), kept for the life of the context
   void* chain_scratch = nullptr;
@@ -185,7 +189,7 @@ struct SeedSrc {                 // where a sub-batch's sequence comes from
 };
 int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_off, uint32_t n_contigs,
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out);
-int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const std::vector<uint64_t>& raw_mk_off);
+int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const uint64_t* raw_mk_off);   // raw_mk_off: host, [G+1]; may still be in flight on ctx->stream (read after the function's first synchronisation)
 void free_set_device(sk_sketch_set* s);
 int build_hash(sk_ctx* ctx, sk_sketch_set* set);
 // api.cu

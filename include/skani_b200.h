@@ -107,6 +107,8 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases_ascii, const uint64_t* con
  * HOST memory (pinned or not); 0.25 B/base cross PCIe instead of 1 (+ the mask words of contigs that contain 'N').
  * sk_pack_contig converts one contig's ASCII to this layout on the host (AVX-512 / AVX2 / scalar). */
 int sk_pack_contig(const uint8_t* ascii, uint64_t n_bases, uint64_t* units, uint32_t* nmask);
+/* name of the packing implementation this machine runs ("avx512vbmi", "avx512bw", "avx2", "scalar"); static string */
+const char* sk_pack_impl(void);
 int sk_sketch_batch_2bit(sk_ctx* ctx, const uint64_t* units, const uint32_t* nmask, const uint32_t* contig_len, uint32_t n_contigs,
                          const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* params, sk_sketch_set** out);
 /* share of the bases that the last sk_sketch_batch / sk_triangle on this context converted to 2-bit on the host before the

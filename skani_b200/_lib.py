@@ -53,6 +53,7 @@ SYMBOLS = [
     ("sk_ctx_get_timing", i32, [vp, C.c_char_p, u64, i32]),
     ("sk_sketch_batch", i32, [vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(vp)]),
     ("sk_pack_contig", i32, [vp, u64, vp, vp]),
+    ("sk_pack_impl", C.c_char_p, []),
     ("sk_sketch_batch_2bit", i32, [vp, vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(vp)]),
     ("sk_ctx_last_pack_share", C.c_double, [vp]),
     ("sk_sketch_batch_dev", i32, [vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(vp)]),

@@ -1139,6 +1139,8 @@ int sk_sketch_batch(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
   return sk::sketch_batch_host(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, out, nullptr, 0);
 }
 
+const char* sk_pack_impl(void) { return sk_host::pack_impl_name(); }
+
 int sk_pack_contig(const uint8_t* ascii, uint64_t n_bases, uint64_t* units, uint32_t* nmask) {
   if ((!ascii && n_bases) || !units || !nmask) return SK_ERR_PARAM;
   sk_host::pack_contig(ascii, n_bases, units, nmask);

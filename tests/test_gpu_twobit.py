@@ -103,3 +103,34 @@ def test_2bit_synthetic_and_triangle_hybrid(ctx, monkeypatch):
         ea, eb = gs.export(g), ga.export(g)
         for key in ea:
             assert np.array_equal(ea[key], eb[key])
+
+
+def test_host_packer_implementation_and_bytes():
+    """The GPU boxes' CPUs have AVX-512 VBMI: the table-driven packer must be the one in use there (its self-check passed), and
+    sk_pack_contig must agree with the byte table (oracle ascii semantics, every byte value at every position of a unit)
+    whatever implementation runs.  (Marked gpu only because that is where the AVX-512 paths exist; no kernel is launched.)"""
+    import skani_b200 as sk
+    from skani_b200 import _lib
+    L = _lib.load()
+    impl = L.sk_pack_impl().decode()
+    flags = open("/proc/cpuinfo").read()
+    if "avx512vbmi" in flags and "avx512bw" in flags:
+        assert impl == "avx512vbmi", impl
+    rng = np.random.default_rng(5)
+    parts = [np.arange(256, dtype=np.uint8).repeat(3), rng.integers(0, 256, 100_003).astype(np.uint8),
+             np.frombuffer(bytes(rng.choice(list(b"ACGTNacgtnUuRYKM-*"), 70_001).tolist()), np.uint8)]
+    for shift in (0, 1, 31, 33, 63, 64, 65):
+        seq = np.concatenate([np.frombuffer(b"A" * shift, np.uint8)] + parts)
+        units, nmask, clen = sk.pack_contigs(L, seq, np.array([0, len(seq)], np.uint64))
+        code = np.zeros(256, np.uint8)
+        for ch, v in ((b"C", 1), (b"G", 2), (b"T", 3), (b"U", 3), (b"c", 1), (b"g", 2), (b"t", 3), (b"u", 3)):
+            code[ch[0]] = v
+        code[:4] = np.arange(4)
+        c = code[seq].astype(np.uint64)
+        pad = (-len(seq)) % 32
+        c = np.concatenate([c, np.zeros(pad, np.uint64)]).reshape(-1, 32)
+        want = (c << (2 * np.arange(32, dtype=np.uint64))).sum(axis=1, dtype=np.uint64)      # disjoint bit fields: sum == or
+        isn = np.concatenate([(seq == 78), np.zeros(pad, bool)]).reshape(-1, 32).astype(np.uint64)
+        want_n = (isn << np.arange(32, dtype=np.uint64)).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(units, want), shift
+        assert np.array_equal(nmask, want_n), shift

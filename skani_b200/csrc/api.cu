@@ -936,10 +936,7 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
           const uint64_t nb = std::min<uint64_t>(len - 32 * tk.ub, 32 * (tk.ue - tk.ub));
           uint64_t* P = hP + cu[tk.ci] + tk.ub;
           uint32_t* M = hNM + cu[tk.ci] + tk.ub;
-          sk_host::pack_contig(s0, nb, P, M);
-          uint32_t any = 0;
-          for (uint64_t j = 0, n = tk.ue - tk.ub; j < n; j++) any |= M[j];
-          if (any) flag[tk.ci].store(1, std::memory_order_relaxed);
+          if (sk_host::pack_contig(s0, nb, P, M)) flag[tk.ci].store(1, std::memory_order_relaxed);
         });
         for (uint32_t i = 0; i < np; i++) has_n[i] = flag[i].load(std::memory_order_relaxed);
         src_units = hP; src_nm = hNM;

@@ -97,7 +97,8 @@ __attribute__((target("avx512f,avx512bw,bmi2"))) inline void pack_contig_avx512(
 // by the low six bits of the byte (bytes outside 0x40..0x7F are zeroed by the mask: only letters carry a code), two
 // multiply-adds gather 4 codes into a byte and a down-convert leaves the 128 packed bits -- 11 micro-ops per 64 bases where the
 // compare-based variant above needs ~28 cycles (measured 5 GB/s per thread; this one is bound by memory instead).
-__attribute__((target("avx512f,avx512bw,avx512vbmi,sse4.1"))) inline void pack_contig_avx512vbmi(const uint8_t* s, size_t n, uint64_t* P, uint32_t* NM) {
+__attribute__((target("avx512f,avx512bw,avx512vbmi,sse4.1"))) inline bool pack_contig_avx512vbmi(const uint8_t* s, size_t n, uint64_t* P, uint32_t* NM) {   // returns: any 'N' seen
+  uint64_t any_n = 0;
   alignas(64) static const uint8_t lut[64] = {
       0, 0, 0, 1, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,     // @ A B C D E F G ... T U ...
       0, 0, 0, 1, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};    // ` a b c d e f g ... t u ...
@@ -115,6 +116,7 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi,sse4.1"))) inline void pack_c
     if (__builtin_expect(_mm512_cmplt_epu8_mask(x, four) != 0, 0)) {            // table rows 0..3 (identity): scalar path
       pack_unit_scalar(s + 64 * j, 32, P + 2 * j, NM + 2 * j);
       pack_unit_scalar(s + 64 * j + 32, 32, P + 2 * j + 1, NM + 2 * j + 1);
+      any_n |= NM[2 * j] | NM[2 * j + 1];
       continue;
     }
     const __mmask64 is_letter = _mm512_cmpeq_epi8_mask(_mm512_and_si512(x, hi2), letter);
@@ -126,9 +128,14 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi,sse4.1"))) inline void pack_c
     _mm_stream_si64((long long*)(P + 2 * j + 1), _mm_extract_epi64(r, 1));
     _mm_stream_si32((int*)(NM + 2 * j), (int)(uint32_t)nn);
     _mm_stream_si32((int*)(NM + 2 * j + 1), (int)(uint32_t)(nn >> 32));
+    any_n |= nn;
   }
   _mm_sfence();
-  if (n % 64) pack_contig_avx2(s + 64 * full, n % 64, P + 2 * full, NM + 2 * full);
+  if (n % 64) {
+    pack_contig_avx2(s + 64 * full, n % 64, P + 2 * full, NM + 2 * full);
+    for (size_t u = 2 * full; u < (n + 31) / 32; u++) any_n |= NM[u];
+  }
+  return any_n != 0;
 }
 // the table-driven variant is checked against the scalar definition once per process (every byte value, every position of a
 // unit) before it is used; a mismatch disables it loudly instead of corrupting sequence
@@ -146,18 +153,21 @@ inline bool vbmi_packer_ok() {
 }
 #endif
 
-// P and NM must hold (n + 31) / 32 entries
-inline void pack_contig(const uint8_t* s, size_t n, uint64_t* P, uint32_t* NM) {
+// P and NM must hold (n + 31) / 32 entries; returns whether the sequence contains an 'N' (the mask has a bit set)
+inline bool pack_contig(const uint8_t* s, size_t n, uint64_t* P, uint32_t* NM) {
+  const size_t nu_all = (n + 31) / 32;
+  auto scan = [&]() { uint32_t any = 0; for (size_t j = 0; j < nu_all; j++) any |= NM[j]; return any != 0; };
 #if defined(__x86_64__)
   static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
   static const bool fast512 = fast && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f");
   static const bool vbmi = fast512 && __builtin_cpu_supports("avx512vbmi") && getenv("SK_PACK_NO_VBMI") == nullptr &&
                            (vbmi_packer_ok() || (fprintf(stderr, "skani_b200: AVX-512 VBMI packer failed its self-check, using the compare-based one\n"), false));
-  if (vbmi) { pack_contig_avx512vbmi(s, n, P, NM); return; }
-  if (fast512) { pack_contig_avx512(s, n, P, NM); return; }
-  if (fast) { pack_contig_avx2(s, n, P, NM); return; }
+  if (vbmi) return pack_contig_avx512vbmi(s, n, P, NM);    // streams its output past the caches: the flag comes with it
+  if (fast512) { pack_contig_avx512(s, n, P, NM); return scan(); }
+  if (fast) { pack_contig_avx2(s, n, P, NM); return scan(); }
 #endif
   pack_contig_scalar(s, n, P, NM);
+  return scan();
 }
 
 // which implementation pack_contig uses on this machine (reported by sk_sketch_batch's trace and checked by the GPU-box tests)

@@ -32,8 +32,9 @@ int main() {
     const size_t nu = (n + 31) / 32;
     std::vector<uint64_t> P(nu + 1, 0xDEADBEEFull), Ps(nu + 1, 0), Pr(nu + 1, 0);
     std::vector<uint32_t> M(nu + 1, 0xABCDu), Ms(nu + 1, 0), Mr(nu + 1, 0);
-    sk_host::pack_contig(s, n, P.data(), M.data());
+    const bool any_n = sk_host::pack_contig(s, n, P.data(), M.data());
     sk_host::pack_contig_scalar(s, n, Ps.data(), Ms.data());
+    { uint32_t want = 0; for (size_t j = 0; j < nu; j++) want |= Ms[j]; if (any_n != (want != 0)) { failures++; fprintf(stderr, "case %d: any-N flag\n", t); } }
     for (size_t i = 0; i < n; i++) {
       const uint32_t v = sk::ascii_code(s[i]);
       Pr[i / 32] |= (uint64_t)(v & 3) << (2 * (i % 32));

@@ -775,7 +775,11 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
   while (c0 < n_contigs) {
     uint32_t c1 = c0;
     uint64_t bytes = 0;
-    const uint64_t limit = !ramp ? SUBBATCH : plan.empty() ? SUBBATCH / 4 : plan.size() == 1 ? SUBBATCH / 2 : SUBBATCH;
+    // ... and towards the end every sub-batch takes half of what is left (down to an eighth of the size): what remains to be
+    // seeded and chained after the LAST upload is small (the tail of the pipelined triangle)
+    const uint64_t left_bytes = contig_off[n_contigs] - contig_off[c0];
+    const uint64_t limit = !ramp ? SUBBATCH : plan.empty() ? SUBBATCH / 4 : plan.size() == 1 ? SUBBATCH / 2
+                           : std::min<uint64_t>(SUBBATCH, std::max<uint64_t>(SUBBATCH / 8, left_bytes / 2));
     while (c1 < n_contigs) {
       uint32_t g = genome_of_contig[c1], c2 = c1;
       while (c2 < n_contigs && genome_of_contig[c2] == g) c2++;
@@ -868,7 +872,10 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
     cudaSetDevice(ctx->device);
     std::vector<uint64_t> cu;           // unit offset of every contig of the part (+ total)
     std::vector<uint8_t> has_n;
-    std::vector<uint64_t> xbytes(2, 0);
+    std::vector<uint64_t> xbytes(2, 0), part_bytes(2, 0);
+    std::vector<double> part_pack_s(2, 0.0);
+    int host_sharers = std::max(1, ctx->cpu_share);
+    if (const char* ev = getenv("LOCAL_WORLD_SIZE")) host_sharers *= std::max(1, atoi(ev));
     auto fail = [&](const char* what, cudaError_t e) {
       std::lock_guard<std::mutex> lk(mu);
       stager_rc = SK_ERR_CUDA; stager_err = std::string(what) + ": " + cudaGetErrorString(e); abort_all = true;
@@ -883,15 +890,34 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
       if (k >= 2) {
         if ((e = cudaEventSynchronize(ctx->x1[b])) != cudaSuccess) return fail("cudaEventSynchronize", e);
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, ctx->x0[b], ctx->x1[b]) == cudaSuccess && ms > 0.05f && xbytes[b] > (8u << 20))
+        if (cudaEventElapsedTime(&ms, ctx->x0[b], ctx->x1[b]) == cudaSuccess && ms > 0.05f && xbytes[b] > (8u << 20)) {
           ctx->h2d_rate = 0.5 * ctx->h2d_rate + 0.5 * ((double)xbytes[b] / (ms * 1e-3));
+          // hill climbing on the host-side stage rate of that part: input bytes / max(packing time, copy time).  Both stages
+          // run concurrently and draw on the same host memory bandwidth, so balancing their measured rates (the formula below)
+          // overshoots as soon as DRAM, not PCIe or the cores, is the limit (two or more GPUs per host): every second sample
+          // the share moves by 0.05 in the direction that last raised the rate.
+          if (fixed_share < 0 && part_bytes[b] > (64u << 20)) {
+            ctx->share_acc += (double)part_bytes[b] / std::max((double)ms * 1e-3, part_pack_s[b]);
+            if (++ctx->share_samples == 2) {
+              const double r = ctx->share_acc / 2;
+              if (ctx->share_ref_rate > 0 && r < 1.01 * ctx->share_ref_rate) ctx->share_dir = -ctx->share_dir;
+              ctx->share_ref_rate = r;
+              ctx->share_bias = std::min(0.5, std::max(-0.9, ctx->share_bias + 0.05 * ctx->share_dir));
+              ctx->share_acc = 0; ctx->share_samples = 0;
+            }
+          }
+        }
       }
       // (2) how many leading contigs are packed on the host
       cu.assign(nc + 1, 0);
       for (uint32_t i = 0; i < nc; i++) cu[i + 1] = cu[i] + (contig_off[p.c0 + i + 1] - contig_off[p.c0 + i] + 31) / 32;
       const uint64_t B = p.b1 - p.b0;
-      double share = fixed_share >= 0 ? fixed_share : ctx->pack_rate / (ctx->h2d_rate + 0.75 * ctx->pack_rate);
+      // rate balance (pack time = copy time) scaled by the number of contexts that share this host's memory system as the
+      // starting point, plus the correction found by the hill climber above
+      double share = fixed_share >= 0 ? fixed_share : ctx->pack_rate / (ctx->h2d_rate + 0.75 * ctx->pack_rate) / (double)host_sharers + ctx->share_bias;
       share = std::min(1.0, std::max(0.0, share));
+      if (fixed_share < 0 && share <= 0.0 && ctx->share_bias < 0) ctx->share_bias += 0.05;     // keep the climber inside [0, 1]
+      if (fixed_share < 0 && share >= 1.0 && ctx->share_bias > 0) ctx->share_bias -= 0.05;
       uint32_t np = 0;
       if (share >= 1.0) np = nc;
       else if (share > 0.0) {
@@ -986,7 +1012,7 @@ int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_of
         wire += ascii_bytes;
         if (!pinned_src && (e = cudaEventRecord(ctx->pinned_free[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
       }
-      xbytes[b] = wire;
+      xbytes[b] = wire; part_bytes[b] = B; part_pack_s[b] = tp_end - tp0;
       if ((e = cudaEventRecord(ctx->x1[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
       if ((e = cudaEventRecord(ctx->h2d_done[b], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
       if (trace) fprintf(stderr, "[sk_sketch_batch] part %zu: %.0f%% of %.1f MB packed on the host (%d threads, %.1f GB/s; PCIe %.1f GB/s), %.1f MB on the wire;"

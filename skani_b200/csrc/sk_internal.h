@@ -74,6 +74,11 @@ struct sk_ctx {
   bool seed_scalar = false;               // seed with the scalar fmh_seeds semantics (src/seeding.rs:225) instead of avx2_fmh_seeds
   double pack_rate = 0, h2d_rate = 0;     // measured: bases/s packed by the pool, bytes/s over PCIe (adapt the host-packed share)
   double last_pack_share = 0;             // share of the bases packed on the host in the last sk_sketch_batch (stats)
+  // correction of the packed share found by hill climbing on the measured host-side stage rate (packing threads and DMA engines
+  // share the host's memory bandwidth, which the rate-balancing formula does not know about); persists across calls
+  double share_bias = 0, share_ref_rate = 0;
+  int share_dir = -1, share_samples = 0;
+  double share_acc = 0;
   // small host->device parameter uploads go through a pinned, device-mapped ring + a copy kernel on the context's
   // stream instead of the H2D copy engine, which may be busy for tens of ms with bulk sequence uploads
   uint8_t* stage = nullptr;

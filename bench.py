@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=400, help="genomes in the bounded CPU-baseline sample of the b200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shuffle-order", action="store_true", help="also measure a seeded random permutation of the genome order (always on for N > 1)")
+    ap.add_argument("--no-shuffle", action="store_true", help="skip the permuted-order measurement (A/B sessions)")
     ap.add_argument("--perm-seed", type=int, default=12345)
     ap.add_argument("--spot-check", type=int, default=200, help="kept pairs re-chained by the CPU oracle after the timed legs")
     a = ap.parse_args()
@@ -457,7 +458,7 @@ def main():
         clocks.start()
     m = measure("contiguous")
     shuf = None
-    if world > 1 or args.shuffle_order:
+    if (world > 1 or args.shuffle_order) and not args.no_shuffle:
         shuf = measure("shuffled")
     clk = clocks.stop() if rank == 0 else None
 

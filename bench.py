@@ -537,6 +537,7 @@ def measure_hashpass(ctx, dev_bases, off, goc, nloc, sp, L):
         sm, mhz = 148, 1965.0
         peak_windows = sm * 4 * 32 * mhz * 1e6 / tr["inst_per_window"]
         alu = {"inst_per_window": tr["inst_per_window"], "issue_active_pct": tr.get("issue_active_pct"),
+               "busiest_pipe_pct": tr.get("sm_throughput_pct"),     # ncu sm__throughput: the integer ALU pipe (half-rate LOP3/SHF/IADD3)
                "windows_per_s": genomes_per_launch * L / sec_per_launch, "issue_peak_windows_per_s": peak_windows,
                "frac_of_issue_peak": genomes_per_launch * L / sec_per_launch / peak_windows}
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,

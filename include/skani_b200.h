@@ -243,6 +243,14 @@ int sk_triangle_local(sk_ctx* ctx, const uint8_t* bases_ascii, const uint64_t* c
                       const sk_map_params* mp, const uint64_t* name_ranks, sk_ani_result** out, uint64_t* n_out,
                       sk_triangle_stats* stats, sk_sketch_set** set_out);
 
+/* sk_triangle_local for callers whose genomes are already 2-bit packed on the host (sk_sketch_batch_2bit's layout: units of 32
+ * bases, optional 'N' mask, contig lengths): 0.25 B/base leave host memory instead of 1 -- with several GPUs per host the ASCII
+ * form is bounded by the host's memory bandwidth.  set_out may be NULL. */
+int sk_triangle_2bit(sk_ctx* ctx, const uint64_t* units, const uint32_t* nmask, const uint32_t* contig_len, uint32_t n_contigs,
+                     const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, const sk_map_params* mp,
+                     const uint64_t* name_ranks, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats,
+                     sk_sketch_set** set_out);
+
 /* ---- multi-GPU triangle from ONE host process (north_star: host -> C-ABI shim -> one exchange of the
  *      per-GPU sketch blocks over NVLink).  ctxs[0..n_ctx): one context per GPU (created with sk_ctx_create(device)); a
  *      device may appear more than once (the exchange then stays on that device: how a 1-GPU box tests this path).

@@ -82,6 +82,8 @@ SYMBOLS = [
                           PP(TriangleStats)]),
     ("sk_triangle_local", i32, [vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(MapParams), vp, PP(PP(AniResult)), PP(u64),
                                 PP(TriangleStats), PP(vp)]),
+    ("sk_triangle_2bit", i32, [vp, vp, vp, vp, u32, vp, u32, PP(SketchParams), PP(MapParams), vp, PP(PP(AniResult)), PP(u64),
+                               PP(TriangleStats), PP(vp)]),
     ("sk_triangle_multi", i32, [vp, u32, vp, vp, u32, vp, u32, PP(SketchParams), PP(MapParams), vp, PP(PP(AniResult)), PP(u64),
                                 PP(TriangleStats)]),
 ]

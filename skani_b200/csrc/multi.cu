@@ -50,6 +50,47 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 
 }  // namespace
 
+// Cross-block pairs -> one list per device.  The pairs of one connected component of the pair graph (a cluster of related
+// genomes) stay together, so a device fetches that cluster's sketches once; with a genome order unrelated to relatedness a
+// contiguous slice of the sorted list touches ~5x more genomes (skani_b200/multi_gpu.py partition_pairs is the same rule).
+// Components above half a device's fair share are cut into runs of consecutive pairs; items go to the least loaded device,
+// largest first (ties: first pair).  Deterministic; every list comes out sorted.
+static void partition_pairs(const std::vector<uint64_t>& sorted_pairs, uint32_t W, uint32_t n_genomes, std::vector<std::vector<uint64_t>>& out) {
+  out.assign(W, {});
+  const size_t n = sorted_pairs.size();
+  if (n == 0) return;
+  if (W == 1) { out[0] = sorted_pairs; return; }
+  std::vector<uint32_t> parent(n_genomes);
+  for (uint32_t g = 0; g < n_genomes; g++) parent[g] = g;
+  auto find = [&](uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+  for (uint64_t p : sorted_pairs) {
+    const uint32_t a = find((uint32_t)(p >> 32)), b = find((uint32_t)p);
+    if (a != b) parent[std::max(a, b)] = std::min(a, b);            // root = smallest genome of the component
+  }
+  // pairs grouped by component root (stable: sorted inside a group)
+  std::vector<std::pair<uint32_t, uint64_t>> keyed(n);
+  for (size_t i = 0; i < n; i++) keyed[i] = {find((uint32_t)(sorted_pairs[i] >> 32)), sorted_pairs[i]};
+  std::sort(keyed.begin(), keyed.end());
+  const size_t cap = std::max<size_t>(1, (n + 2 * (size_t)W - 1) / (2 * (size_t)W));
+  struct Item { size_t size, start; };
+  std::vector<Item> items;
+  for (size_t i = 0; i < n;) {
+    size_t j = i;
+    while (j < n && keyed[j].first == keyed[i].first) j++;
+    for (size_t s0 = i; s0 < j; s0 += cap) items.push_back(Item{std::min(cap, j - s0), s0});
+    i = j;
+  }
+  std::sort(items.begin(), items.end(), [&](const Item& a, const Item& b) { return a.size != b.size ? a.size > b.size : keyed[a.start].second < keyed[b.start].second; });
+  std::vector<size_t> load(W, 0);
+  for (const Item& it : items) {
+    uint32_t r = 0;
+    for (uint32_t k = 1; k < W; k++) if (load[k] < load[r]) r = k;
+    for (size_t k = it.start; k < it.start + it.size; k++) out[r].push_back(keyed[k].second);
+    load[r] += it.size;
+  }
+  for (auto& v : out) std::sort(v.begin(), v.end());
+}
+
 extern "C" int sk_triangle_multi(sk_ctx* const* ctxs, uint32_t n_ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
                                  const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                                  const sk_map_params* mp, const uint64_t* name_ranks, sk_ani_result** out, uint64_t* n_out,
@@ -172,12 +213,12 @@ extern "C" int sk_triangle_multi(sk_ctx* const* ctxs, uint32_t n_ctx, const uint
     for (uint32_t r = 0; r < W; r++) cross.insert(cross.end(), cross_part[r].begin(), cross_part[r].end());
     std::sort(cross.begin(), cross.end());
     const double t2 = now_s();
-    auto slice_of = [&](uint32_t r, uint64_t& lo, uint64_t& hi) { lo = cross.size() * r / W; hi = cross.size() * (r + 1) / W; };
+    // split over the devices by connected component of the pair graph (every thread computes the same split)
+    std::vector<std::vector<uint64_t>> share;
+    partition_pairs(cross, W, n_genomes, share);
     auto genomes_of_slice = [&](uint32_t r, std::vector<uint32_t>& need) {
-      uint64_t lo, hi;
-      slice_of(r, lo, hi);
       need.clear();
-      for (uint64_t i = lo; i < hi; i++) { need.push_back((uint32_t)(cross[i] >> 32)); need.push_back((uint32_t)cross[i]); }
+      for (uint64_t pr : share[r]) { need.push_back((uint32_t)(pr >> 32)); need.push_back((uint32_t)pr); }
       std::sort(need.begin(), need.end());
       need.erase(std::unique(need.begin(), need.end()), need.end());
     };
@@ -221,8 +262,8 @@ extern "C" int sk_triangle_multi(sk_ctx* const* ctxs, uint32_t n_ctx, const uint
     sk_sketch_set_free(local[d]); local[d] = nullptr;
     const double t3 = now_s();
     // ---- chain the slice on the working set (ids -> working indices and back)
-    uint64_t lo, hi;
-    slice_of(d, lo, hi);
+    const std::vector<uint64_t>& my_pairs = share[d];
+    const uint64_t lo = 0, hi = my_pairs.size();
     if (rc == SK_OK && hi > lo) {
       if (sk_sketch_set_n_genomes(work) != mine.size()) { c->err = "fetch plan mismatch"; rc = SK_ERR_STATE; }
       std::vector<uint64_t> ranks(mine.size());
@@ -230,8 +271,8 @@ extern "C" int sk_triangle_multi(sk_ctx* const* ctxs, uint32_t n_ctx, const uint
       if (rc == SK_OK) rc = sk_sketch_set_set_name_ranks(work, ranks.data());
       std::vector<uint64_t> lp(hi - lo);
       for (uint64_t i = lo; i < hi; i++) {
-        const uint64_t a = std::lower_bound(mine.begin(), mine.end(), (uint32_t)(cross[i] >> 32)) - mine.begin();
-        const uint64_t b = std::lower_bound(mine.begin(), mine.end(), (uint32_t)cross[i]) - mine.begin();
+        const uint64_t a = std::lower_bound(mine.begin(), mine.end(), (uint32_t)(my_pairs[i] >> 32)) - mine.begin();
+        const uint64_t b = std::lower_bound(mine.begin(), mine.end(), (uint32_t)my_pairs[i]) - mine.begin();
         lp[i - lo] = (a << 32) | b;
       }
       std::vector<sk_ani_result> res(lp.size());

@@ -29,11 +29,12 @@ struct Wave { sk_sketch_set* set; uint32_t g_begin; bool last; };
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-int simple_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs, const uint32_t* genome_of_contig,
+int simple_triangle(sk_ctx* ctx, const sk::HostSeq& seq, const uint64_t* contig_off, uint32_t n_contigs, const uint32_t* genome_of_contig,
                     uint32_t n_genomes, const sk_sketch_params* sp, const sk_map_params* mp, std::vector<sk_ani_result>& kept,
                     uint64_t* n_screened, sk_sketch_set** keep, const uint64_t* name_ranks) {
   sk_sketch_set* set = nullptr;
-  SK_TRY(sk_sketch_batch(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, &set));
+  if (seq.units && n_contigs && contig_off[n_contigs] > contig_off[0]) SK_TRY(sk::sketch_batch_host(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, &set, nullptr, 0));
+  else SK_TRY(sk_sketch_batch(ctx, seq.ascii ? seq.ascii : (const uint8_t*)"", contig_off, n_contigs, genome_of_contig, n_genomes, sp, &set));
   if (name_ranks) sk_sketch_set_set_name_ranks(set, name_ranks);
   struct SG { sk_sketch_set* s; sk_sketch_set** keep; ~SG() { if (keep && s) *keep = s; else sk_sketch_set_free(s); } } sg{set, keep};
   if (keep) *keep = nullptr;
@@ -48,7 +49,7 @@ int simple_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_of
   return SK_OK;
 }
 
-int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+int triangle_impl(sk_ctx* ctx, const sk::HostSeq& seq, const uint64_t* contig_off, uint32_t n_contigs,
                   const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                   const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats, sk_sketch_set** keep,
                   const uint64_t* name_ranks);
@@ -58,7 +59,8 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
 extern "C" int sk_triangle(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
                            const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                            const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats) {
-  return triangle_impl(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, out, n_out, stats, nullptr, nullptr);
+  sk::HostSeq seq; seq.ascii = bases;
+  return triangle_impl(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, out, n_out, stats, nullptr, nullptr);
 }
 
 extern "C" int sk_triangle_local(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
@@ -66,11 +68,24 @@ extern "C" int sk_triangle_local(sk_ctx* ctx, const uint8_t* bases, const uint64
                                  const sk_map_params* mp, const uint64_t* name_ranks, sk_ani_result** out, uint64_t* n_out,
                                  sk_triangle_stats* stats, sk_sketch_set** set_out) {
   if (!set_out) return SK_ERR_PARAM;
-  return triangle_impl(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, out, n_out, stats, set_out, name_ranks);
+  sk::HostSeq seq; seq.ascii = bases;
+  return triangle_impl(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, out, n_out, stats, set_out, name_ranks);
+}
+
+// the same for callers that hold their genomes 2-bit packed (sk_sketch_batch_2bit's layout): 0.25 B/base leave host memory
+extern "C" int sk_triangle_2bit(sk_ctx* ctx, const uint64_t* units, const uint32_t* nmask, const uint32_t* contig_len, uint32_t n_contigs,
+                                const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
+                                const sk_map_params* mp, const uint64_t* name_ranks, sk_ani_result** out, uint64_t* n_out,
+                                sk_triangle_stats* stats, sk_sketch_set** set_out) {
+  if (!ctx || (n_contigs && (!units || !contig_len || !genome_of_contig))) return SK_ERR_PARAM;
+  std::vector<uint64_t> off((size_t)n_contigs + 1, 0);
+  for (uint32_t i = 0; i < n_contigs; i++) off[i + 1] = off[i] + contig_len[i];
+  sk::HostSeq seq; seq.units = units; seq.nmask = nmask;
+  return triangle_impl(ctx, seq, off.data(), n_contigs, genome_of_contig, n_genomes, sp, mp, out, n_out, stats, set_out, name_ranks);
 }
 
 namespace {
-int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, uint32_t n_contigs,
+int triangle_impl(sk_ctx* ctx, const sk::HostSeq& seq, const uint64_t* contig_off, uint32_t n_contigs,
                   const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                   const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats, sk_sketch_set** keep,
                   const uint64_t* name_ranks) {
@@ -106,7 +121,7 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
   const bool pipelined = ((total_bytes >= (4ull << 30) && n_genomes >= 64) || (getenv("SK_FORCE_PIPELINE") && n_genomes >= 2)) &&
                          getenv("SK_NO_PIPELINE") == nullptr && n_contigs > 0;
   if (!pipelined) {
-    int rc = simple_triangle(ctx, bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, kept, &n_screened, keep, name_ranks);
+    int rc = simple_triangle(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, mp, kept, &n_screened, keep, name_ranks);
     if (rc != SK_OK) { if (keep && *keep) { sk_sketch_set_free(*keep); *keep = nullptr; } return rc; }
   } else {
     // ---- producer: ONE continuous upload + seeding pass (the H2D stream never drains); every finished sub-batch is
@@ -201,7 +216,6 @@ int triangle_impl(sk_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
       cv.notify_one();
       return SK_OK;
     };
-    sk::HostSeq seq; seq.ascii = bases;
     // sub-batches of 1 .. 2 GiB (about 1/16 of the input): 2 GiB measured 10 % faster end to end than 1 GiB on the 50 GB run
     const size_t subbatch = (size_t)std::min<uint64_t>(2048ull << 20, std::max<uint64_t>(1024ull << 20, total_bytes / 16));
     int rc = sk::sketch_batch_host(ctx, seq, contig_off, n_contigs, genome_of_contig, n_genomes, sp, nullptr, &on_part, subbatch);

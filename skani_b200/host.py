@@ -358,6 +358,25 @@ def triangle_local(ctx, bases, contig_off, genome_of_contig, n_genomes, sp=None,
     return _take_results(ctx, out, n, as_array), SketchSet(ctx, h), st
 
 
+def triangle_2bit(ctx, units, nmask, contig_len, genome_of_contig, n_genomes, sp=None, mp=None, name_ranks=None, as_array=True, keep_set=False):
+    """sk_triangle_2bit: the triangle of genomes that are already 2-bit packed on the host (units may be an address).  Returns
+    (results, stats) or, with keep_set, (results, SketchSet, stats)."""
+    sp = sp or sketch_params(); mp = mp or map_params()
+    cl = np.ascontiguousarray(contig_len, np.uint32)
+    goc = np.ascontiguousarray(genome_of_contig, np.uint32)
+    ua = None if isinstance(units, int) else np.ascontiguousarray(units, np.uint64)
+    uptr = units if ua is None else ua.ctypes.data
+    na = None if (nmask is None or isinstance(nmask, int)) else np.ascontiguousarray(nmask, np.uint32)
+    nptr = nmask if na is None else na.ctypes.data
+    nr = None if name_ranks is None else np.ascontiguousarray(name_ranks, np.uint64)
+    out = C.POINTER(AniResult)(); n = C.c_uint64(); st = TriangleStats(); h = C.c_void_p()
+    ctx.check(ctx.L.sk_triangle_2bit(ctx.h, uptr, nptr, cl.ctypes.data, len(cl), goc.ctypes.data, n_genomes, C.byref(sp), C.byref(mp),
+                                     None if nr is None else nr.ctypes.data, C.byref(out), C.byref(n), C.byref(st),
+                                     C.byref(h) if keep_set else None))
+    res = _take_results(ctx, out, n, as_array)
+    return (res, SketchSet(ctx, h), st) if keep_set else (res, st)
+
+
 def triangle_multi(ctxs, bases, contig_off, genome_of_contig, n_genomes, sp=None, mp=None, name_ranks=None, as_array=True):
     """sk_triangle_multi: one host process, one context per GPU (a device may repeat: the exchange then stays on it)."""
     sp = sp or sketch_params(); mp = mp or map_params()

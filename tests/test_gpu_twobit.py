@@ -134,3 +134,26 @@ def test_host_packer_implementation_and_bytes():
         want_n = (isn << np.arange(32, dtype=np.uint64)).sum(axis=1, dtype=np.uint64).astype(np.uint32)
         assert np.array_equal(units, want), shift
         assert np.array_equal(nmask, want_n), shift
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_triangle_2bit_equals_ascii_triangle(ctx, monkeypatch, pipelined):
+    """sk_triangle_2bit (genomes already packed on the host, with an N mask) gives the result bytes of sk_triangle on the ASCII
+    form, through the one-shot path and through the upload || seed || chain pipeline with several sub-batches and waves."""
+    import skani_b200 as sk
+    n, L, G = 14, 250_000, 4
+    bases, off, goc = synth.generate(0, n, L, G=G)
+    bases = bases.copy()
+    bases[1000:1040] = ord("N"); bases[3 * L + 77: 3 * L + 79] = ord("n")          # an N run and lower-case n (not an 'N' for the mask)
+    r0, st0 = sk.triangle(ctx, bases, off, goc, n, as_array=True)
+    units, nmask, lens = sk.pack_contigs(ctx.L, bases, off)
+    if pipelined:
+        monkeypatch.setenv("SK_FORCE_PIPELINE", "1")
+        monkeypatch.setenv("SK_SUBBATCH_BYTES", "600000")
+    r1, st1 = sk.triangle_2bit(ctx, units, nmask, lens, goc, n)
+    r2, kept_set, _ = sk.triangle_2bit(ctx, units, nmask, lens, goc, n, keep_set=True)
+    assert len(kept_set) == n
+    kept_set.free()
+    k0 = np.sort(r0, order=["ref_id", "query_id"]).tobytes()
+    assert len(r0) > 0 and k0 == np.sort(r1, order=["ref_id", "query_id"]).tobytes() == np.sort(r2, order=["ref_id", "query_id"]).tobytes()
+    assert st0.n_pairs_screened == st1.n_pairs_screened

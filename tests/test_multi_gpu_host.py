@@ -61,9 +61,11 @@ def test_fetch_plan_is_consistent_across_ranks():
             rp = remap_pairs(mine, need)
             back = (need[(rp >> np.uint64(32)).astype(np.int64)].astype(np.uint64) << np.uint64(32)) | need[(rp & np.uint64(0xFFFFFFFF)).astype(np.int64)].astype(np.uint64)
             assert np.array_equal(back, mine)
-        assert np.array_equal(np.concatenate(covered), pairs)
+        assert np.array_equal(np.sort(np.concatenate(covered)), pairs)              # a partition of the pair list
         sizes = [len(c) for c in covered]
-        assert max(sizes) - min(sizes) <= 1
+        assert all(np.all(np.diff(c.astype(np.int64)) > 0) for c in covered if len(c) > 1)
+        # load balance: whole components stay together, items are at most half a fair share: nobody above 1.5x the mean (+ one item)
+        assert max(sizes) <= 1.5 * len(pairs) / world + max(1, -(-len(pairs) // (2 * world)))
     # no pairs at all
     need, send, rc = fetch_plan(np.zeros(0, np.uint64), 2, 1, [0, 5, 10])
     assert len(need) == 0 and all(len(x) == 0 for x in send) and rc.tolist() == [0, 0]
@@ -151,3 +153,29 @@ def test_cross_block_pairs_and_bench_helpers():
     ids = synth.shuffled_ids(1000, 12345)
     assert sorted(ids.tolist()) == list(range(1000)) and ids.tolist() != list(range(1000))
     assert np.array_equal(ids, synth.shuffled_ids(1000, 12345))
+
+
+def test_partition_pairs_keeps_clusters_together():
+    """Shuffled genome order (relatedness unrelated to the index): the component-wise partition makes a rank fetch about one
+    cluster's genomes per 190 pairs, where contiguous slices of the sorted list touch several times more genomes; a single giant
+    component degrades to slices (no rank above its fair share + one item)."""
+    from skani_b200.multi_gpu import partition_pairs, genomes_of_pairs, shard_range
+    rng = np.random.default_rng(11)
+    n, G, world = 2000, 20, 8
+    perm = rng.permutation(n)                                            # genome g sits at index perm[g]
+    pl = sorted({(int(min(perm[a], perm[b])) << 32) | int(max(perm[a], perm[b]))
+                 for c in range(n // G) for a in range(c * G, (c + 1) * G) for b in range(a + 1, (c + 1) * G)})
+    pairs = np.array(pl, np.uint64)
+    parts = partition_pairs(pairs, world)
+    assert np.array_equal(np.sort(np.concatenate(parts)), pairs)
+    need_comp = [len(genomes_of_pairs(p)) for p in parts]
+    need_slice = [len(genomes_of_pairs(pairs[slice(*shard_range(len(pairs), world, r))])) for r in range(world)]
+    assert max(need_comp) <= 1.2 * n / world and sum(need_slice) > 3 * sum(need_comp), (need_comp, need_slice)
+    sizes = [len(p) for p in parts]
+    assert max(sizes) - min(sizes) <= 190                                # whole clusters: at most one cluster of difference
+    # one giant component (a dense set): cut into runs, balanced
+    dense = np.array([(i << 32) | j for i in range(60) for j in range(i + 1, 60)], np.uint64)
+    dp = partition_pairs(dense, 4)
+    assert np.array_equal(np.sort(np.concatenate(dp)), dense)
+    assert max(len(x) for x in dp) <= len(dense) / 4 + len(dense) / 8 + 1
+    assert [len(x) for x in partition_pairs(dense[:0], 3)] == [0, 0, 0] and len(partition_pairs(dense, 1)[0]) == len(dense)

@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=400, help="genomes in the bounded CPU-baseline sample of the b200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shuffle-order", action="store_true", help="also measure a seeded random permutation of the genome order (always on for N > 1)")
+    ap.add_argument("--no-2bit", action="store_true", help="skip the third leg (genomes already 2-bit packed in host memory)")
     ap.add_argument("--no-shuffle", action="store_true", help="skip the permuted-order measurement (A/B sessions)")
     ap.add_argument("--perm-seed", type=int, default=12345)
     ap.add_argument("--spot-check", type=int, default=200, help="kept pairs re-chained by the CPU oracle after the timed legs")
@@ -371,8 +372,17 @@ def main():
         t_gen = time.perf_counter() - t_gen0
         dev_bases = pinned.to("cuda", non_blocking=False)
         last = {}
+        packed = {}
 
         def step(e2e):
+            if e2e == "2bit":           # genomes already 2-bit packed in (pinned) host memory: SURVEY 8(d)'s other starting point
+                if world == 1:
+                    res, st = sk.triangle_2bit(ctx, packed["units"], None, packed["lens"], goc, nloc, sp, mp)
+                    last["res"] = res
+                    return len(res)
+                kept = tri.step(None, 0, off, goc, nloc, g0, N, packed=(packed["units"], None, packed["lens"]))
+                last["res"] = tri.last_results
+                return kept
             if world == 1:
                 if e2e:
                     res, st = sk.triangle(ctx, host, off, goc, nloc, sp, mp, as_array=True)
@@ -414,7 +424,7 @@ def main():
                 t = torch.tensor([ms], device="cuda")
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
                 ms = float(t.item())
-            last["step_ms_e2e" if e2e else "step_ms_value"] = per_step   # rank-local wall clock of each step (spread, not the metric)
+            last["step_ms_2bit" if e2e == "2bit" else "step_ms_e2e" if e2e else "step_ms_value"] = per_step   # rank-local wall clock of each step (spread, not the metric)
             return ms / n_steps, kept, ctx.launches - l0
 
         # value leg first (needs the device-resident copy of the bases), then the roofline probes, then drop the device copy
@@ -433,6 +443,7 @@ def main():
             step(True)
         ms_e2e, kept, _ = timed(True, args.steps)
         res = last["res"]
+        step_ms_e2e = last.get("step_ms_e2e")
         pack_share = ctx.last_pack_share
         d2h = len(res) * C.sizeof(_lib.AniResult)
         ck_e2e = allreduce_count_checksum(len(res), result_checksum(res), world)
@@ -443,12 +454,39 @@ def main():
         spot = None
         if rank == 0:
             spot = oracle_spot_check(res, ids, cfg, args.spot_check, 99)
+        # third leg: the same call on genomes that are ALREADY 2-bit packed in host memory (sk_triangle_2bit): 0.25 B/base leave
+        # host DRAM instead of 1, which is what bounds the ASCII leg when several GPUs share one host
+        ms_2bit = ck_2bit = None
+        if not args.no_2bit and order == "contiguous":
+            import concurrent.futures
+            lens = np.diff(off).astype(np.uint32)
+            uoff = np.concatenate([[0], np.cumsum((lens.astype(np.uint64) + 31) // 32)]).astype(np.int64)
+            pu = torch.empty(max(int(uoff[-1]), 1), dtype=torch.int64, pin_memory=True)
+            scratch_nm = np.zeros(int(((lens.astype(np.int64) + 31) // 32).max()) if len(lens) else 1, np.uint32)
+            ua = pu.numpy().view(np.uint64)
+            Lh = _lib.load()
+            def pack_range(lo, hi):
+                nm = np.zeros_like(scratch_nm)
+                for i in range(lo, hi):
+                    Lh.sk_pack_contig(host.ctypes.data + int(off[i]), int(lens[i]), ua.ctypes.data + 8 * int(uoff[i]), nm.ctypes.data)
+            nthr = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+            cuts = np.linspace(0, len(lens), nthr + 1).astype(int)
+            with concurrent.futures.ThreadPoolExecutor(nthr) as ex:
+                list(ex.map(lambda k: pack_range(int(cuts[k]), int(cuts[k + 1])), range(nthr)))
+            packed.update(units=ua.ctypes.data, lens=lens, keep=pu)
+            for _ in range(max(args.warmup, 0)):
+                step("2bit")
+            ms_2bit, _, _ = timed("2bit", args.steps)
+            ck_2bit = allreduce_count_checksum(len(last["res"]), result_checksum(last["res"]), world)
+            packed.clear()
         if rank != 0:
             return None
         expected = expected_pairs(N, G)
         return {"order": order, "value": total_pairs / (ms_val * 1e-3), "ms_per_step": ms_val, "launches": int(launches),
                 "e2e_value": total_pairs / (ms_e2e * 1e-3), "e2e_ms_per_step": ms_e2e, "d2h": int(d2h), "host_gen_s": round(t_gen, 2),
-                "host_pack_share": round(pack_share, 3), "step_ms_value": last.get("step_ms_value"), "step_ms_e2e": last.get("step_ms_e2e"),
+                "host_pack_share": round(pack_share, 3), "step_ms_value": last.get("step_ms_value"), "step_ms_e2e": step_ms_e2e,
+                "e2e_2bit_ms_per_step": ms_2bit, "step_ms_2bit": last.get("step_ms_2bit"), "units_bytes": int(((np.diff(off).astype(np.int64) + 31) // 32).sum() * 8),
+                "checksum_2bit": (None if ck_2bit is None else "%016x" % ck_2bit[1]), "kept_2bit": (None if ck_2bit is None else int(ck_2bit[0])),
                 "verify": {"kept_pairs_all_ranks": ck_e2e[0], "kept_pairs_expected": expected, "kept_ok": ck_e2e[0] == expected == ck_val[0],
                            "checksum_e2e": "%016x" % ck_e2e[1], "checksum_value_leg": "%016x" % ck_val[1],
                            "legs_agree": ck_e2e == ck_val, "oracle_spot_check": spot},
@@ -479,6 +517,13 @@ def main():
                         "note": "inputs = ASCII in pinned host memory; host_pack_share of the bases is converted to 2-bit on the host "
                                 "cores inside the timed call (0.25 B/base on the wire), the rest crosses PCIe as ASCII"},
                 "gpu_launches": m["launches"], "clocks": clk, "roofline": m["roof"], "roofline_chain": m["roof_chain"], "cpu_baseline": cpu}
+        if m.get("e2e_2bit_ms_per_step"):
+            line["e2e_2bit"] = {"what": "the same call on genomes that are already 2-bit packed in pinned host memory (sk_triangle_2bit; SURVEY 8(d): "
+                                        "'resident in host memory as ASCII/2-bit'); results on the host; the ASCII leg above stays the headline `e2e`",
+                                "value": total_pairs / (m["e2e_2bit_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": m["e2e_2bit_ms_per_step"],
+                                "step_ms_rank0": m["step_ms_2bit"], "h2d_bytes_per_step": m["units_bytes"] * (world if world > 1 else 1),
+                                "kept_pairs_all_ranks": m["kept_2bit"], "checksum": m["checksum_2bit"],
+                                "same_results_as_e2e": m["checksum_2bit"] == m["verify"]["checksum_e2e"] and m["kept_2bit"] == m["verify"]["kept_pairs_all_ranks"]}
         if shuf:
             line["shuffled"] = {"what": "same genomes, seeded random permutation of the genome order (perm seed %d): input order unrelated "
                                         "to relatedness" % args.perm_seed,

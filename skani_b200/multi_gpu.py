@@ -278,7 +278,7 @@ class DistTriangle:
         work = self._unpack([g.data_ptr() for g in got], [np.ascontiguousarray(m) for m in gmeta])
         return work, sum(int(g.numel()) for r, g in enumerate(got) if r != self.rank)
 
-    def step(self, host_bases, dev_ptr, off, goc, nloc, g0, n_total):
+    def step(self, host_bases, dev_ptr, off, goc, nloc, g0, n_total, packed=None):
         """One whole triangle over all ranks; returns this rank's number of kept pairs (results in self.last_results,
         ref_id / query_id = GLOBAL genome indices)."""
         ctx = self.ctx
@@ -286,7 +286,9 @@ class DistTriangle:
         trace = os.environ.get("SK_TRACE") and self.rank == 0
         t0 = time.perf_counter()
         ranks_local = None if self.name_ranks is None else self.name_ranks[g0:g0 + nloc]
-        if host_bases is not None:      # pipelined: upload || seed || screen || chain inside the block
+        if packed is not None:          # (units, nmask, contig_len): the block's genomes already 2-bit packed on the host
+            res_local, local, _st = H.triangle_2bit(ctx, packed[0], packed[1], packed[2], goc, nloc, self.sp, self.mp, name_ranks=ranks_local, keep_set=True)
+        elif host_bases is not None:    # pipelined: upload || seed || screen || chain inside the block
             res_local, local, _st = H.triangle_local(ctx, host_bases, off, goc, nloc, self.sp, self.mp, name_ranks=ranks_local)
         else:                           # sequences already resident on the device
             local = H.sketch_contigs(ctx, None, off, goc, nloc, self.sp, device_ptr=dev_ptr)

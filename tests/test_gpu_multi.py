@@ -32,9 +32,9 @@ def test_two_rank_triangle_matches_oracle():
             rows = np.concatenate([np.load(os.path.join(d, "rank%d_%d.npy" % (r, use_host))) for r in range(2)])
             got = {(int(x[0]), int(x[1])): x for x in rows}
             assert set(got) == set(exp) and len(rows) == len(exp)
-            # the passing-pair list is split evenly over the ranks
+            # both ranks chain: their own block's pairs plus a share of the cross-block component (items of <= 3 of its 9 pairs)
             sizes = [len(np.load(os.path.join(d, "rank%d_%d.npy" % (r, use_host)))) for r in range(2)]
-            assert abs(sizes[0] - sizes[1]) <= 1
+            assert min(sizes) > 0 and abs(sizes[0] - sizes[1]) <= 3
             for k, e in exp.items():
                 assert abs(got[k][2] - e.ani) <= 1e-4 and abs(got[k][3] - e.af_ref) <= 1e-4 and abs(got[k][4] - e.af_query) <= 1e-4
 

@@ -86,3 +86,33 @@ def test_subset_roundtrip_markers_only_and_working_set(ctx):
     rw["query_id"] = need[rw["query_id"]]
     assert rw.tobytes() == res_full[5:17].tobytes()
     work.free(); full.free()
+
+
+@pytest.mark.parametrize("flags", [0, 2])
+def test_scattered_subset_uses_the_batched_copy(ctx, flags):
+    """More than 8 separate runs of genomes (the cross-block fetch of a genome order unrelated to relatedness) go through one
+    batched device memcpy instead of thousands of cudaMemcpyAsync calls: same sketches (and, with SK_PACK_TABLES, chaining on
+    the unpacked set without rebuilding tables gives the full set's results)."""
+    import torch
+    import skani_b200 as sk
+    n, L, G = 40, 120_000, 4
+    bases, off, goc = synth.generate(0, n, L, G=G)
+    mp = sk.map_params()
+    full = sk.sketch_contigs(ctx, bases, off, goc, n)
+    pick = np.array([0, 2, 3, 5, 8, 9, 11, 14, 16, 17, 20, 23, 25, 26, 27, 30, 33, 35, 38, 39], np.uint32)   # 14 runs
+    sub = unpack(ctx, torch, [(full, pick[:11]), (full, pick[11:])], flags)
+    assert len(sub) == len(pick)
+    for i, g in enumerate(pick):
+        a, b = sub.export(i), full.export(int(g))
+        for key in ("kmer", "pos", "cc", "markers", "contig_lengths"):
+            assert np.array_equal(a[key], b[key]), (key, i, g)
+    pairs_full = sk.screen_triangle(ctx, full, mp)
+    keep = pairs_full[np.isin(pairs_full >> np.uint64(32), pick) & np.isin(pairs_full & np.uint64(0xFFFFFFFF), pick)]
+    assert len(keep) >= 5
+    from skani_b200.multi_gpu import remap_pairs
+    sub.set_name_ranks(pick.astype(np.uint64))
+    rs = sk.chain_pairs(ctx, sub, sub, remap_pairs(keep, pick), mp, as_array=True)
+    rf = sk.chain_pairs(ctx, full, full, keep, mp, as_array=True)
+    rs["ref_id"] = pick[rs["ref_id"]]; rs["query_id"] = pick[rs["query_id"]]
+    assert rs.tobytes() == rf.tobytes()
+    sub.free(); full.free()

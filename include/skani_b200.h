@@ -235,6 +235,8 @@ int sk_triangle(sk_ctx* ctx, const uint8_t* bases_ascii, const uint64_t* contig_
                 const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                 const sk_map_params* mp, sk_ani_result** out, uint64_t* n_out, sk_triangle_stats* stats);
 
+/* (sk_triangle and sk_triangle_local also accept a DEVICE pointer for bases_ascii: genomes already resident in HBM go through the
+ * same seed || screen || chain pipeline without the pack / upload stages.) */
 /* Same, and additionally hands back the device-resident sketch set of all n_genomes genomes (with their k-mer tables), e.g.
  * to chain further pairs against it (the cross-block pairs of a multi-GPU run).  name_ranks: optional file-name order per
  * genome for the switch_qr tie-break (see sk_sketch_set_set_name_ranks), NULL = index order.  Free with sk_sketch_set_free. */

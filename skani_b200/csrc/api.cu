@@ -694,15 +694,29 @@ int sk_sketch_set_unpack(sk_ctx* ctx, uint32_t n_parts, const void* const* d_blo
 int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* contig_off, uint32_t n_contigs,
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp,
                         sk_sketch_set** out) {
-  if (!ctx || !out || !contig_off || (!genome_of_contig && n_contigs)) return SK_ERR_PARAM;
+  if (!out) return SK_ERR_PARAM;
+  return sk::sketch_batch_dev_parts(ctx, d_bases, contig_off, n_contigs, genome_of_contig, n_genomes, sp, out, nullptr, 0);
+}
+
+}  // extern "C"
+
+namespace sk {
+// Sequences already resident on the device: sub-batches of whole genomes through the seeding kernels.  With on_part every
+// finished sub-batch is handed over (the pipelined sk_triangle on device-resident input) instead of being concatenated into *out.
+int sketch_batch_dev_parts(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* contig_off, uint32_t n_contigs,
+                           const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out,
+                           const std::function<int(sk_sketch_set*, uint32_t, uint32_t)>* on_part, size_t subbatch_override) {
+  if (!ctx || (!out && !on_part) || !contig_off || (!genome_of_contig && n_contigs)) return SK_ERR_PARAM;
   SK_CUDA(cudaSetDevice(ctx->device));
   SK_TRY(check_sketch_params(ctx, sp));
   // split into sub-batches of whole genomes (bounds the per-base temporaries)
   std::vector<sk_sketch_set*> parts;
   struct Guard { std::vector<sk_sketch_set*>& v; ~Guard() { for (auto* s : v) sk_sketch_set_free(s); } } guard{parts};
   uint32_t c0 = 0;
+  bool first = true;
   std::vector<uint32_t> gl;
-  const size_t SUBBATCH = subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
+  size_t SUBBATCH = subbatch_override ? subbatch_override : subbatch_bytes(n_contigs ? contig_off[n_contigs] - contig_off[0] : 0);
+  if (const char* e = getenv("SK_SUBBATCH_BYTES")) SUBBATCH = std::max<size_t>(1, (size_t)atoll(e));   // test hook: many small sub-batches
   while (c0 < n_contigs) {
     uint32_t g0 = genome_of_contig[c0];
     uint32_t c1 = c0;
@@ -718,19 +732,20 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
       c1 = c2;
     }
     uint32_t g_next = (c1 < n_contigs) ? genome_of_contig[c1] : n_genomes;
-    // genomes g0 .. g_next-1 belong to this part (empty genomes between are kept as empty sketches)
-    uint32_t g_begin = parts.empty() ? 0 : g0;
-    if (!parts.empty()) {
-      // empty genomes skipped between the previous part and g0 were already attributed to the previous part
-    }
+    // genomes g0 .. g_next-1 belong to this part (empty genomes between are kept as empty sketches; those skipped between
+    // the previous part and g0 were attributed to the previous part)
+    uint32_t g_begin = first ? 0 : g0;
+    first = false;
     gl.resize(c1 - c0);
     for (uint32_t i = c0; i < c1; i++) gl[i - c0] = genome_of_contig[i] - g_begin;
     sk_sketch_set* part = nullptr;
     SeedSrc src; src.d_ascii = d_bases;
     SK_TRY(sketch_batch_device(ctx, src, contig_off + c0, c1 - c0, gl.data(), g_next - g_begin, sp, &part));
-    parts.push_back(part);
+    if (on_part) SK_TRY((*on_part)(part, g_begin, g_next));     // ownership moves to the callee
+    else parts.push_back(part);
     c0 = c1;
   }
+  if (on_part) return SK_OK;
   if (parts.empty()) {  // no contigs at all: n_genomes empty sketches
     sk_sketch_set* part = nullptr;
     uint64_t z = 0;
@@ -752,9 +767,6 @@ int sk_sketch_batch_dev(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* con
   return SK_OK;
 }
 
-}  // extern "C"
-
-namespace sk {
 static double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // Host -> device seeding pipeline behind sk_sketch_batch / sk_sketch_batch_2bit / sk_triangle.

@@ -206,6 +206,9 @@ struct HostSeq {                 // host-resident sequence of a sketch batch: AS
 int sketch_batch_host(sk_ctx* ctx, const HostSeq& seq, const uint64_t* contig_off, uint32_t n_contigs, const uint32_t* genome_of_contig,
                       uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out,
                       const std::function<int(sk_sketch_set*, uint32_t, uint32_t)>* on_part, size_t subbatch_override);
+int sketch_batch_dev_parts(sk_ctx* ctx, const uint8_t* d_bases, const uint64_t* contig_off, uint32_t n_contigs,
+                           const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out,
+                           const std::function<int(sk_sketch_set*, uint32_t, uint32_t)>* on_part, size_t subbatch_override);
 SkPool* ctx_pool(sk_ctx* ctx);
 // grows `*dst` (created on first use, with capacities reserved for the expected totals) by the genomes of `parts` IN PLACE:
 // only the new genomes' arrays are copied and only their k-mer tables are built (the pipelined sk_triangle's merged set)

@@ -333,6 +333,28 @@ def test_screen_triangle_block_partitions_the_pair_list(ctx):
     sset.free()
 
 
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_triangle_on_device_resident_bases(ctx, monkeypatch, pipelined):
+    """sk_triangle / sk_triangle_local on a DEVICE pointer (genomes already in HBM: the bench's `value` leg) give the result
+    bytes of the host-buffer call, through the one-shot path and through the pipeline (several sub-batches and waves)."""
+    import torch
+    import skani_b200 as sk
+    n, L, G = 20, 250_000, 4
+    bases, off, goc = synth.generate(0, n, L, G=G)
+    r0, st0 = sk.triangle(ctx, bases, off, goc, n, as_array=True)
+    dev = torch.from_numpy(bases).cuda()
+    if pipelined:
+        monkeypatch.setenv("SK_FORCE_PIPELINE", "1")
+        monkeypatch.setenv("SK_SUBBATCH_BYTES", "700000")
+    r1, st1 = sk.triangle(ctx, int(dev.data_ptr()), off, goc, n, as_array=True)
+    r2, kept, _ = sk.triangle_local(ctx, int(dev.data_ptr()), off, goc, n)
+    assert len(kept) == n
+    kept.free()
+    k0 = np.sort(r0, order=["ref_id", "query_id"]).tobytes()
+    assert len(r0) > 0 and k0 == np.sort(r1, order=["ref_id", "query_id"]).tobytes() == np.sort(r2, order=["ref_id", "query_id"]).tobytes()
+    assert st0.n_pairs_screened == st1.n_pairs_screened
+
+
 @pytest.mark.parametrize("rescreen", [False, True])
 def test_pipelined_triangle_small_marker_sets(ctx, monkeypatch, rescreen):
     """Incremental screen of the pipelined triangle vs the one-shot screen when some genomes have < 20 markers (screen_refs'

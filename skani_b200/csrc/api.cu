@@ -362,7 +362,7 @@ int sk_ctx_set_seeding_semantics(sk_ctx* ctx, int semantics) {
 }
 
 const char* sk_last_error(const sk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-uint64_t sk_ctx_launch_count(const sk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t sk_ctx_launch_count(const sk_ctx* ctx) { return ctx ? ctx->launches + (ctx->child ? ctx->child->launches : 0) : 0; }   // incl. the pipelined triangle's worker context
 void* sk_ctx_stream(const sk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 void sk_free(void* p) { free(p); }
 

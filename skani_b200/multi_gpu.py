@@ -290,8 +290,13 @@ class DistTriangle:
             res_local, local, _st = H.triangle_2bit(ctx, packed[0], packed[1], packed[2], goc, nloc, self.sp, self.mp, name_ranks=ranks_local, keep_set=True)
         elif host_bases is not None:    # pipelined: upload || seed || screen || chain inside the block
             res_local, local, _st = H.triangle_local(ctx, host_bases, off, goc, nloc, self.sp, self.mp, name_ranks=ranks_local)
-        else:                           # sequences already resident on the device: the same pipelined call on a device pointer
-            res_local, local, _st = H.triangle_local(ctx, int(dev_ptr), off, goc, nloc, self.sp, self.mp, name_ranks=ranks_local)
+        else:                           # sequences already resident on the device: sketch -> screen -> chain on one stream
+            local = H.sketch_contigs(ctx, None, off, goc, nloc, self.sp, device_ptr=dev_ptr)
+            if ranks_local is not None:
+                local.set_name_ranks(ranks_local)
+            lp = H.screen_triangle(ctx, local, self.mp)
+            res_local = H.chain_pairs(ctx, local, local, lp, self.mp, as_array=True)
+            res_local = res_local[res_local["ani"] > 0.1]               # src/triangle.rs:99
         res_local["ref_id"] += np.uint32(g0)
         res_local["query_id"] += np.uint32(g0)
         t1 = time.perf_counter()

@@ -1307,6 +1307,7 @@ int sk_sketch_set_import_batch(sk_ctx* ctx, const sk_sketch_params* sp, uint32_t
   if (n_markers) SK_CUDA(cudaMemcpy(mraw.p, markers + m0, n_markers * 8, cudaMemcpyHostToDevice));
   std::vector<uint64_t> raw_off(G + 1);
   for (uint32_t g = 0; g <= G; g++) raw_off[g] = mk_off[g] - m0;
+  mbox_reset(ctx);                 // build_views takes pinned read-back space from the context's mailbox
   SK_TRY(build_views(ctx, s, mraw.p, raw_off.data()));
   SK_TRY(build_hash(ctx, s));
   SK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -358,7 +358,7 @@ static void* mbox_alloc(sk_ctx* ctx, size_t bytes) {
     ctx->mbox_blocks.push_back({p, cap});
   }
 }
-static void mbox_reset(sk_ctx* ctx) { ctx->mbox_block = 0; ctx->mbox_pos = 0; }
+void mbox_reset(sk_ctx* ctx) { ctx->mbox_block = 0; ctx->mbox_pos = 0; }
 
 static inline uint32_t div_up(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 

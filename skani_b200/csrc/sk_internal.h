@@ -196,6 +196,7 @@ int sketch_batch_device(sk_ctx* ctx, const SeedSrc& src, const uint64_t* contig_
                         const uint32_t* genome_of_contig, uint32_t n_genomes, const sk_sketch_params* sp, sk_sketch_set** out);
 int build_views(sk_ctx* ctx, sk_sketch_set* set, uint64_t* d_marker_raw, const uint64_t* raw_mk_off);   // raw_mk_off: host, [G+1]; may still be in flight on ctx->stream (read after the function's first synchronisation)
 void free_set_device(sk_sketch_set* s);
+void mbox_reset(sk_ctx* ctx);   // forget the pinned read-back blocks handed out so far (no read-back may be in flight)
 int build_hash(sk_ctx* ctx, sk_sketch_set* set);
 // api.cu
 struct HostSeq {                 // host-resident sequence of a sketch batch: ASCII, or 2-bit units (+ optional N mask)

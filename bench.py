@@ -38,6 +38,8 @@ CONFIGS = {   # BASELINE.json configs that are a triangle on one box (c3 = searc
                   metric="genome-pairs/sec, skani triangle 10k x 5 Mbp synthetic"),
     "c2": dict(genomes=1000, genome_len=5_000_000, cluster=20, c=125, marker_c=1000, rescue_small=True,
                metric="genome-pairs/sec, skani triangle 1k x 5 Mbp synthetic (BASELINE.json configs[1])"),
+    "c4": dict(genomes=50000, genome_len=5_000_000, cluster=20, c=125, marker_c=1000, rescue_small=True,
+               metric="genome-pairs/sec, skani triangle 50k x 5 Mbp synthetic (BASELINE.json configs[3]; needs --gpus 8: 31 GB of bases and 14 GB of sketches per GPU; not measured this round)"),
     "dense": dict(genomes=2000, genome_len=5_000_000, cluster=2000, c=125, marker_c=1000, rescue_small=True,
                   metric="genome-pairs/sec, skani triangle 2000 x 5 Mbp synthetic, ONE cluster (every pair is chained)"),
     "c5": dict(genomes=200000, genome_len=30_000, cluster=10, c=30, marker_c=200, rescue_small=False,

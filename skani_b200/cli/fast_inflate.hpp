@@ -1,0 +1,433 @@
+// fast_inflate.hpp -- raw DEFLATE (RFC 1951) decoder for the FASTA/FASTQ ingestion path of the host CLI.
+//
+// Why: reading `.fa.gz` inputs is bounded by inflate (the reference uses flate2 behind
+// needletail, src/file_io.rs:141-362).  zlib's inflate keeps its state machine resumable at every byte, which costs it most
+// of its speed; here the whole compressed file and the whole output buffer are in memory (the file is mmap'ed, the text is
+// parsed in place afterwards), so the decoder can be a tight loop: a 64-bit bit buffer refilled with one unaligned load,
+// one table look-up per literal / length / distance (11-bit and 8-bit first-level tables with sub-tables for longer codes),
+// several literals per refill, and 8-byte-at-a-time match copies.  Anything unusual (a code set that is not complete, a
+// distance beyond the start of the output, a truncated stream) makes the function return false and the caller falls back to
+// zlib, which then reports the error in its own terms.
+//
+// Checked against zlib by tests/emu/emu_inflate.cpp: random and FASTA-like inputs at every compression level and strategy
+// (stored, fixed and dynamic blocks, long matches, distance-1 runs), truncations, multi-member files, the gzip fixtures of
+// tests/golden/.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace sk_inflate {
+
+constexpr int LT_BITS = 11;     // first-level bits of the literal/length table
+constexpr int DT_BITS = 8;      // ... of the distance table
+// table entry: [31:16] payload (literal byte, length / distance base, or sub-table start), [15:12] kind, [11:8] extra bits (or
+// sub-table bits), [7:0] code length in bits (for sub-table pointers: LT_BITS / DT_BITS)
+enum : uint32_t { K_LIT = 1u << 12, K_BASE = 2u << 12, K_EOB = 4u << 12, K_SUB = 8u << 12 };
+
+struct Tables {
+  uint32_t lt[(1 << LT_BITS) + 1024];    // 288 symbols, codes <= 15 bits: sub-tables need < 1024 extra entries
+  uint32_t dt[(1 << DT_BITS) + 512];
+};
+
+static inline uint32_t rev_bits(uint32_t code, int len) {
+  uint32_t r = 0;
+  for (int i = 0; i < len; i++) { r = (r << 1) | (code & 1); code >>= 1; }
+  return r;
+}
+
+// canonical Huffman code lengths -> look-up table; returns false unless the code is complete (Kraft sum exactly 1)
+static inline bool build_table(const uint8_t* lens, int n_sym, int table_bits, uint32_t* table, size_t table_cap,
+                               const uint32_t* sym_entry /* entry without the length field, per symbol */) {
+  int count[16] = {0};
+  for (int s = 0; s < n_sym; s++) count[lens[s]]++;
+  count[0] = 0;
+  uint32_t kraft = 0;
+  for (int l = 1; l <= 15; l++) kraft += (uint32_t)count[l] << (15 - l);
+  if (kraft != (1u << 15)) return false;
+  uint32_t next_code[16];
+  uint32_t code = 0;
+  for (int l = 1; l <= 15; l++) { code = (code + (uint32_t)count[l - 1]) << 1; next_code[l] = code; }
+  // longest code behind every first-level prefix (codes longer than table_bits share their low table_bits bits)
+  const uint32_t prim = 1u << table_bits;
+  std::vector<uint8_t> sub_len(prim, 0);
+  std::vector<uint32_t> codes(n_sym, 0);
+  {
+    uint32_t nc[16];
+    memcpy(nc, next_code, sizeof(nc));
+    for (int s = 0; s < n_sym; s++) {
+      const int l = lens[s];
+      if (!l) continue;
+      const uint32_t r = rev_bits(nc[l]++, l);
+      codes[s] = r;
+      if (l > table_bits) { uint8_t& m = sub_len[r & (prim - 1)]; if (l > m) m = (uint8_t)l; }
+    }
+  }
+  size_t next_free = prim;
+  std::vector<uint32_t> sub_start(prim, 0);
+  for (uint32_t p = 0; p < prim; p++)
+    if (sub_len[p]) {
+      const int sb = sub_len[p] - table_bits;
+      if (next_free + ((size_t)1 << sb) > table_cap) return false;
+      sub_start[p] = (uint32_t)next_free;
+      table[p] = ((uint32_t)next_free << 16) | K_SUB | ((uint32_t)sb << 8) | (uint32_t)table_bits;
+      next_free += (size_t)1 << sb;
+    }
+  for (int s = 0; s < n_sym; s++) {
+    const int l = lens[s];
+    if (!l) continue;
+    const uint32_t e = sym_entry[s] | (uint32_t)l, r = codes[s];
+    if (l <= table_bits) {
+      for (uint32_t i = r; i < prim; i += 1u << l) table[i] = e;
+    } else {
+      const uint32_t p = r & (prim - 1);
+      const int sb = sub_len[p] - table_bits;
+      const uint32_t hi = r >> table_bits, step = 1u << (l - table_bits);
+      // inside the sub-table the entry's length field counts only the bits beyond the first level
+      const uint32_t es = sym_entry[s] | (uint32_t)(l - table_bits);
+      for (uint32_t i = hi; i < (1u << sb); i += step) table[sub_start[p] + i] = es;
+    }
+  }
+  return true;
+}
+
+static const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+static const uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static const uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static const uint8_t DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+
+static inline bool build_litlen(const uint8_t* lens, int n, Tables& t) {
+  uint32_t ent[288];
+  for (int s = 0; s < 288; s++) {
+    if (s < 256) ent[s] = ((uint32_t)s << 16) | K_LIT;
+    else if (s == 256) ent[s] = K_EOB;
+    else if (s < 286) ent[s] = ((uint32_t)LEN_BASE[s - 257] << 16) | K_BASE | ((uint32_t)LEN_EXTRA[s - 257] << 8);
+    else ent[s] = 0;          // 286, 287: never valid in a stream (kind 0 = error)
+  }
+  uint8_t l[288] = {0};
+  memcpy(l, lens, (size_t)n);
+  if (!build_table(l, 288, LT_BITS, t.lt, sizeof(t.lt) / 4, ent)) return false;
+  // Two literals per look-up where both codes fit the first-level index (nucleotide text has 2-3 bit codes for A/C/G/T, and
+  // the chain "look up -> shift -> look up" is what bounds a Huffman decoder): bit 8 of a literal entry says that the payload
+  // holds two bytes and the length field covers both codes.
+  uint32_t first[1 << LT_BITS];
+  memcpy(first, t.lt, sizeof(first));
+  for (uint32_t i = 0; i < (1u << LT_BITS); i++) {
+    const uint32_t e = first[i];
+    if (!(e & K_LIT)) continue;
+    const uint32_t l1 = e & 0xFF;
+    if (l1 >= (uint32_t)LT_BITS) continue;
+    const uint32_t e2 = first[i >> l1];
+    if (!(e2 & K_LIT) || (e2 & 0xFF) > (uint32_t)LT_BITS - l1) continue;
+    t.lt[i] = ((((e >> 16) & 0xFF) | (((e2 >> 16) & 0xFF) << 8)) << 16) | K_LIT | (1u << 8) | (l1 + (e2 & 0xFF));
+  }
+  return true;
+}
+static inline bool build_dist(const uint8_t* lens, int n, Tables& t) {
+  uint32_t ent[32];
+  for (int s = 0; s < 32; s++) ent[s] = s < 30 ? (((uint32_t)DIST_BASE[s] << 16) | K_BASE | ((uint32_t)DIST_EXTRA[s] << 8)) : 0;
+  uint8_t l[32] = {0};
+  memcpy(l, lens, (size_t)n);
+  return build_table(l, 32, DT_BITS, t.dt, sizeof(t.dt) / 4, ent);
+}
+
+static inline uint64_t load64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }   // little-endian hosts only (x86-64)
+
+// Decodes ONE raw deflate stream starting at in[0].  Output is appended to `out` (which also serves as the window: matches may
+// reach back into bytes that were there before, never before out[base]).  On success *in_used = compressed bytes consumed.
+inline bool inflate_raw(const uint8_t* in, size_t in_len, std::string& out, size_t base, size_t* in_used) {
+  const uint8_t* ip = in;
+  const uint8_t* const in_end = in + in_len;
+  uint64_t bb = 0;       // bit buffer, LSB first
+  int bc = 0;            // valid bits in bb
+  size_t pos = out.size();
+  Tables* T = new Tables;
+  struct Del { Tables* t; ~Del() { delete t; } } del{T};
+  auto ensure = [&](size_t extra) {   // room for `extra` more bytes (+ slack for the word-wise match copy)
+    if (pos + extra + 16 > out.size()) out.resize(std::max(out.size() * 2, pos + extra + 65536));
+  };
+  // byte-wise refill (headers, stored blocks, the last bytes of the stream)
+  auto need = [&](int n) -> bool {
+    while (bc < n) {
+      if (ip >= in_end) return false;
+      bb |= (uint64_t)*ip++ << bc;
+      bc += 8;
+    }
+    return true;
+  };
+  for (;;) {
+    if (!need(3)) return false;
+    const uint32_t bfinal = (uint32_t)bb & 1, btype = ((uint32_t)bb >> 1) & 3;
+    bb >>= 3; bc -= 3;
+    if (btype == 0) {                 // stored: to the byte boundary, LEN / NLEN, raw bytes
+      const int drop = bc & 7;
+      bb >>= drop; bc -= drop;
+      if (!need(32)) return false;
+      const uint32_t len = (uint32_t)bb & 0xFFFF, nlen = ((uint32_t)(bb >> 16)) & 0xFFFF;
+      bb >>= 32; bc -= 32;
+      if ((len ^ nlen) != 0xFFFF) return false;
+      ensure(len);
+      uint32_t left = len;
+      while (left && bc >= 8) { out[pos++] = (char)(bb & 0xFF); bb >>= 8; bc -= 8; left--; }
+      if (left) {                       // bc == 0 here; bits above bc may mirror bytes at ip that are skipped now: forget them
+        bb = 0;
+        if ((size_t)(in_end - ip) < left) return false;
+        memcpy(&out[pos], ip, left);
+        pos += left; ip += left;
+      }
+    } else if (btype == 1 || btype == 2) {
+      uint8_t ll[288 + 32];
+      int hlit = 288, hdist = 32;
+      if (btype == 1) {
+        for (int i = 0; i < 144; i++) ll[i] = 8;
+        for (int i = 144; i < 256; i++) ll[i] = 9;
+        for (int i = 256; i < 280; i++) ll[i] = 7;
+        for (int i = 280; i < 288; i++) ll[i] = 8;
+        for (int i = 0; i < 32; i++) ll[288 + i] = 5;
+        // the fixed distance code has 32 codes of 5 bits (30, 31 never occur): complete as it stands
+        uint32_t ent[32];
+        for (int s = 0; s < 32; s++) ent[s] = s < 30 ? (((uint32_t)DIST_BASE[s] << 16) | K_BASE | ((uint32_t)DIST_EXTRA[s] << 8)) : 0;
+        if (!build_litlen(ll, 288, *T) || !build_table(ll + 288, 32, DT_BITS, T->dt, sizeof(T->dt) / 4, ent)) return false;
+      } else {
+        if (!need(14)) return false;
+        hlit = 257 + ((int)bb & 31); hdist = 1 + ((int)(bb >> 5) & 31);
+        const int hclen = 4 + ((int)(bb >> 10) & 15);
+        bb >>= 14; bc -= 14;
+        if (hlit > 286 || hdist > 30) return false;
+        static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        uint8_t cl[19] = {0};
+        for (int i = 0; i < hclen; i++) {
+          if (!need(3)) return false;
+          cl[order[i]] = (uint8_t)(bb & 7);
+          bb >>= 3; bc -= 3;
+        }
+        // code-length code: 7-bit table built directly
+        uint16_t clt[128];
+        {
+          int count[8] = {0};
+          for (int s = 0; s < 19; s++) count[cl[s]]++;
+          count[0] = 0;
+          uint32_t kraft = 0;
+          for (int l = 1; l <= 7; l++) kraft += (uint32_t)count[l] << (7 - l);
+          if (kraft != 128) return false;
+          uint32_t nc[8], code = 0;
+          for (int l = 1; l <= 7; l++) { code = (code + (uint32_t)count[l - 1]) << 1; nc[l] = code; }
+          for (int s = 0; s < 19; s++) {
+            const int l = cl[s];
+            if (!l) continue;
+            const uint32_t r = rev_bits(nc[l]++, l);
+            for (uint32_t i = r; i < 128; i += 1u << l) clt[i] = (uint16_t)((s << 4) | l);
+          }
+        }
+        int n = 0;
+        const int total = hlit + hdist;
+        while (n < total) {
+          while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }   // near the end fewer bits may be left: checked per symbol
+          const uint16_t e = clt[bb & 127];
+          const int l = e & 15, sym = e >> 4;
+          if (l > bc) return false;
+          bb >>= l; bc -= l;
+          if (sym < 16) { ll[n++] = (uint8_t)sym; continue; }
+          int rep, val = 0, eb;
+          if (sym == 16) { if (n == 0) return false; val = ll[n - 1]; eb = 2; rep = 3; }
+          else if (sym == 17) { eb = 3; rep = 3; }
+          else { eb = 7; rep = 11; }
+          if (!need(eb)) return false;
+          rep += (int)(bb & ((1u << eb) - 1));
+          bb >>= eb; bc -= eb;
+          if (n + rep > total) return false;
+          while (rep--) ll[n++] = (uint8_t)val;
+        }
+        if (ll[256] == 0) return false;                          // no end-of-block code
+        if (!build_litlen(ll, hlit, *T)) return false;
+        if (!build_dist(ll + hlit, hdist, *T)) return false;      // incomplete distance codes (a block without matches from some encoders): zlib decides
+      }
+      // ---- symbols
+      const uint32_t* const lt = T->lt;
+      const uint32_t* const dt = T->dt;
+      for (;;) {
+        ensure(4096);
+        const size_t out_lim = out.size() - 16 - 258 - 9;         // a whole iteration (up to 8 literals + scratch byte, or one match + copy slack) fits below this
+        char* const o = &out[0];
+        bool eob = false;
+        // Fast loop.  Invariants at the top: >= 16 input bytes ahead of ip, the bit buffer was just refilled (bc >= 56) and e is
+        // the entry for its low bits.  The look-up for the NEXT symbol is issued before a match is copied, so its latency
+        // overlaps the copy (the serial chain look-up -> shift -> look-up is what bounds a Huffman decoder).
+#define SK_REFILL() do { bb |= load64(ip) << bc; ip += (63 - bc) >> 3; bc |= 56; } while (0)
+#define SK_PUT_LIT(e)                                                                          \
+  do {                                                                                         \
+    const uint16_t two__ = (uint16_t)((e) >> 16);                                              \
+    memcpy(o + pos, &two__, 2);          /* one or two literals: the second byte is scratch if there is one */ \
+    pos += 1 + (((e) >> 8) & 1);                                                               \
+    bb >>= ((e) & 0xFF); bc -= (int)((e) & 0xFF);                                              \
+  } while (0)
+        if (pos < out_lim && (size_t)(in_end - ip) >= 16) {
+          SK_REFILL();
+          uint32_t e = lt[bb & ((1u << LT_BITS) - 1)];
+          for (;;) {
+            if (e & K_LIT) {                     // up to 3 look-ups (<= 11 bits each) after one refill, then refill and go on
+              SK_PUT_LIT(e);
+              e = lt[bb & ((1u << LT_BITS) - 1)];
+              if (e & K_LIT) {
+                SK_PUT_LIT(e);
+                e = lt[bb & ((1u << LT_BITS) - 1)];
+                if (e & K_LIT) {
+                  SK_PUT_LIT(e);
+                  e = lt[bb & ((1u << LT_BITS) - 1)];
+                }
+              }
+              if (!(pos < out_lim && (size_t)(in_end - ip) >= 16)) break;     // e is dropped: the careful loop looks it up again
+              SK_REFILL();                                                     // adds high bits only: e stays the entry of the low bits
+              continue;
+            }
+            if (e & K_SUB) {
+              bb >>= LT_BITS; bc -= LT_BITS;
+              e = lt[(e >> 16) + (bb & ((1u << ((e >> 8) & 15)) - 1))];
+              if (e & K_LIT) {
+                SK_PUT_LIT(e);
+                if (!(pos < out_lim && (size_t)(in_end - ip) >= 16)) break;
+                SK_REFILL();
+                e = lt[bb & ((1u << LT_BITS) - 1)];
+                continue;
+              }
+            }
+            if (e & K_EOB) { bb >>= (e & 0xFF); bc -= (int)(e & 0xFF); eob = true; break; }
+            if (!(e & K_BASE)) return false;
+            bb >>= (e & 0xFF); bc -= (int)(e & 0xFF);
+            const uint32_t xb = (e >> 8) & 15;
+            const uint32_t len = (e >> 16) + ((uint32_t)bb & ((1u << xb) - 1));
+            bb >>= xb; bc -= (int)xb;
+            uint32_t d = dt[bb & ((1u << DT_BITS) - 1)];
+            if (d & K_SUB) {
+              bb >>= DT_BITS; bc -= DT_BITS;
+              d = dt[(d >> 16) + (bb & ((1u << ((d >> 8) & 15)) - 1))];
+            }
+            if (!(d & K_BASE)) return false;
+            bb >>= (d & 0xFF); bc -= (int)(d & 0xFF);
+            const uint32_t db = (d >> 8) & 15;
+            const size_t dist = (d >> 16) + ((uint32_t)bb & ((1u << db) - 1));
+            bb >>= db; bc -= (int)db;
+            if (dist > pos - base) return false;
+            char* dst = o + pos;
+            const char* src = dst - dist;
+            pos += len;
+            const bool more = pos < out_lim && (size_t)(in_end - ip) >= 16;
+            if (more) { SK_REFILL(); e = lt[bb & ((1u << LT_BITS) - 1)]; }       // next symbol's look-up in flight during the copy
+            if (dist >= 8) {
+              memcpy(dst, src, 8); memcpy(dst + 8, src + 8, 8);                    // in order: valid for any distance >= 8
+              if (len > 16) {
+                char* const end = dst + len;
+                dst += 16; src += 16;
+                do { memcpy(dst, src, 8); dst += 8; src += 8; } while (dst < end);
+              }
+            } else if (dist == 1) {
+              memset(dst, (unsigned char)*src, len);
+            } else {
+              for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+            }
+            if (!more) break;
+          }
+        }
+#undef SK_PUT_LIT
+#undef SK_REFILL
+        if (eob) break;
+        // careful loop: one symbol at a time with byte-wise refill (end of input, or the output buffer has to grow)
+        {
+          // (bits above bc in bb always mirror the bytes at ip, so byte-wise refills continue seamlessly after the fast loop)
+          while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }
+          if (bc == 0) return false;
+          uint32_t e = lt[bb & ((1u << LT_BITS) - 1)];
+          int used = 0;
+          if (e & K_SUB) { const uint32_t sb = (e >> 8) & 15; e = lt[(e >> 16) + ((bb >> LT_BITS) & ((1u << sb) - 1))]; used = LT_BITS; }
+          used += (int)(e & 0xFF);
+          if (used > bc) return false;
+          bb >>= used; bc -= used;
+          if (e & K_LIT) { ensure(2); out[pos++] = (char)(e >> 16); if (e & (1u << 8)) out[pos++] = (char)(e >> 24); continue; }
+          if (e & K_EOB) break;
+          if (!(e & K_BASE)) return false;
+          const int xb = (int)((e >> 8) & 15);
+          while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }
+          if (xb > bc) return false;
+          const uint32_t len = (e >> 16) + ((uint32_t)bb & ((1u << xb) - 1));
+          bb >>= xb; bc -= xb;
+          while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }
+          uint32_t d = dt[bb & ((1u << DT_BITS) - 1)];
+          used = 0;
+          if (d & K_SUB) { const uint32_t sb = (d >> 8) & 15; d = dt[(d >> 16) + ((bb >> DT_BITS) & ((1u << sb) - 1))]; used = DT_BITS; }
+          if (!(d & K_BASE)) return false;
+          used += (int)(d & 0xFF);
+          if (used > bc) return false;
+          bb >>= used; bc -= used;
+          const int db = (int)((d >> 8) & 15);
+          while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }
+          if (db > bc) return false;
+          const size_t dist = (d >> 16) + ((uint32_t)bb & ((1u << db) - 1));
+          bb >>= db; bc -= db;
+          if (dist > pos - base) return false;
+          ensure(len);
+          for (uint32_t i = 0; i < len; i++) { out[pos] = out[pos - dist]; pos++; }
+        }
+      }
+    } else {
+      return false;
+    }
+    if (bfinal) break;
+  }
+  // whole bytes still sitting in the bit buffer were not part of the stream
+  const size_t unused = (size_t)(bc >> 3);
+  *in_used = (size_t)(ip - in) - unused;
+  out.resize(pos);
+  return true;
+}
+
+// crc: function computing the CRC-32 of a buffer continuing from a previous value (zlib's crc32 signature), or nullptr to skip
+typedef unsigned long (*crc_fn)(unsigned long, const unsigned char*, unsigned int);
+
+// gzip file (one or several members back to back, flate2 MultiGzDecoder semantics; bytes after the last member that do not
+// start a new one end the stream, as zlib's gzread does) -> text.  Returns false on anything unexpected; `out` is then
+// unspecified and the caller decodes the file with zlib instead.
+inline bool gunzip(const uint8_t* p, size_t n, std::string& out, crc_fn crc) {
+  out.clear();
+  if (n >= 18) {   // size hint: ISIZE of the last member (exact for single-member files below 4 GB)
+    const uint8_t* t = p + n - 4;
+    const size_t isz = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+    if (isz <= n * 1100 + 65536) out.reserve(isz + 65536 + 512);       // deflate cannot expand more than ~1032x
+  }
+  size_t o = 0;
+  size_t members = 0;
+  while (o < n) {
+    if (n - o < 18 || p[o] != 0x1f || p[o + 1] != 0x8b) break;
+    if (p[o + 2] != 8) return false;
+    const uint8_t flg = p[o + 3];
+    if (flg & 0xE0) return false;
+    size_t h = o + 10;
+    if (flg & 4) { if (h + 2 > n) return false; h += 2 + (size_t)(p[h] | (p[h + 1] << 8)); }
+    if (flg & 8) { while (h < n && p[h]) h++; h++; }
+    if (flg & 16) { while (h < n && p[h]) h++; h++; }
+    if (flg & 2) h += 2;
+    if (h + 8 > n) return false;
+    const size_t base = out.size();
+    size_t used = 0;
+    if (!inflate_raw(p + h, n - h, out, base, &used)) return false;
+    const size_t t = h + used;
+    if (t + 8 > n) return false;
+    const uint32_t want_crc = (uint32_t)p[t] | ((uint32_t)p[t + 1] << 8) | ((uint32_t)p[t + 2] << 16) | ((uint32_t)p[t + 3] << 24);
+    const uint32_t want_len = (uint32_t)p[t + 4] | ((uint32_t)p[t + 5] << 8) | ((uint32_t)p[t + 6] << 16) | ((uint32_t)p[t + 7] << 24);
+    const size_t got = out.size() - base;
+    if ((uint32_t)got != want_len) return false;
+    if (crc) {
+      unsigned long c = crc(0, nullptr, 0);
+      for (size_t q = 0; q < got;) { const size_t m = std::min<size_t>(got - q, 1u << 30); c = crc(c, (const unsigned char*)out.data() + base + q, (unsigned int)m); q += m; }
+      if ((uint32_t)c != want_crc) return false;
+    }
+    o = t + 8;
+    members++;
+  }
+  return members > 0;
+}
+
+}  // namespace sk_inflate

@@ -20,6 +20,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <memory>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -153,63 +154,121 @@ inline bool inflate_gzip(const RawSpan raw, std::string& out, int inflate_thread
   return ok;
 }
 
-// records of an in-memory FASTA / FASTQ text
-inline bool parse_fastx(const char* data, size_t n, std::vector<Record>& out) {
+// A record located inside a text buffer, not copied: its sequence is the lines of text[seq_b, seq_e) with the line breaks
+// ("\n" / "\r\n") removed, n_bases bytes in all.  The CLI lays all records out first and then strips the lines straight into
+// the one flat buffer the GPU library takes (one copy per base instead of text -> record string -> flat buffer).
+struct RecordView { std::string id; size_t seq_b = 0, seq_e = 0, n_bases = 0; };
+
+inline bool scan_fastx(const char* data, size_t n, std::vector<RecordView>& out) {
   enum { START, FA_SEQ, FQ_SEQ, FQ_PLUS, FQ_QUAL } st = START;
-  bool ok = true, any = false;
-  Record cur;
+  bool ok = true, any = false, open = false;
+  RecordView cur;
   size_t fq_len = 0;
-  auto on_line = [&](const char* p, size_t len) {
-    if (len && p[len - 1] == '\r') len--;
-    switch (st) {
-      case START:
-        if (len == 0) { if (any) return; ok = false; return; }
-        if (p[0] == '>') { cur = Record(); cur.id.assign(p + 1, len - 1); st = FA_SEQ; any = true; }
-        else if (p[0] == '@') { cur = Record(); cur.id.assign(p + 1, len - 1); st = FQ_SEQ; any = true; }
-        else ok = false;
-        break;
-      case FA_SEQ:
-        if (len && p[0] == '>') { out.push_back(std::move(cur)); cur = Record(); cur.id.assign(p + 1, len - 1); }
-        else {
-          if (cur.seq.empty()) {   // reserve up to the next header once per record (one pass of memchr over the record)
-            const char* nx = p;
-            const char* end = data + n;
-            while ((nx = (const char*)memchr(nx, '>', end - nx)) != nullptr && nx[-1] != '\n') nx++;
-            cur.seq.reserve((size_t)((nx ? nx : end) - p));
-          }
-          cur.seq.append(p, len);
-        }
-        break;
-      case FQ_SEQ: cur.seq.assign(p, len); fq_len = len; st = FQ_PLUS; break;
-      case FQ_PLUS: if (len == 0 || p[0] != '+') ok = false; st = FQ_QUAL; break;
-      case FQ_QUAL:
-        if (len != fq_len) ok = false;
-        out.push_back(std::move(cur)); cur = Record(); st = START;
-        break;
-    }
-  };
   size_t b = 0;
   while (ok && b < n) {
     const char* nl = (const char*)memchr(data + b, '\n', n - b);
     const size_t e = nl ? (size_t)(nl - data) : n;
-    on_line(data + b, e - b);
+    const char* p = data + b;
+    size_t len = e - b;
+    if (len && p[len - 1] == '\r') len--;
+    switch (st) {
+      case START:
+        if (len == 0) { if (!any) ok = false; break; }
+        if (p[0] == '>' || p[0] == '@') {
+          cur = RecordView(); cur.id.assign(p + 1, len - 1); cur.seq_b = cur.seq_e = std::min(e + 1, n);
+          st = p[0] == '>' ? FA_SEQ : FQ_SEQ; any = true; open = true;
+        } else ok = false;
+        break;
+      case FA_SEQ:
+        if (len && p[0] == '>') {
+          out.push_back(std::move(cur));
+          cur = RecordView(); cur.id.assign(p + 1, len - 1); cur.seq_b = cur.seq_e = std::min(e + 1, n);
+        } else { cur.n_bases += len; cur.seq_e = std::min(e + 1, n); }
+        break;
+      case FQ_SEQ: cur.seq_b = b; cur.seq_e = std::min(e + 1, n); cur.n_bases = len; fq_len = len; st = FQ_PLUS; break;
+      case FQ_PLUS: if (len == 0 || p[0] != '+') ok = false; st = FQ_QUAL; break;
+      case FQ_QUAL:
+        if (len != fq_len) ok = false;
+        out.push_back(std::move(cur)); cur = RecordView(); open = false; st = START;
+        break;
+    }
     b = e + 1;
   }
-  if (ok && st == FA_SEQ) out.push_back(std::move(cur));
+  if (ok && st == FA_SEQ && open) out.push_back(std::move(cur));
   if (ok && (st == FQ_SEQ || st == FQ_PLUS || st == FQ_QUAL)) ok = false;
   if (!any) ok = false;  // empty file (needletail: EmptyFile error)
   return ok;
 }
 
-inline bool read_fastx(const std::string& path, std::vector<Record>& out, int inflate_threads = 1) {
-  FileView fv(path);
-  if (!fv.ok) return false;
-  if (fv.n >= 2 && fv.p[0] == 0x1f && fv.p[1] == 0x8b) {
-    std::string text;
-    if (!inflate_gzip(RawSpan{fv.p, fv.n}, text, inflate_threads)) return false;
-    return parse_fastx(text.data(), text.size(), out);
+// the sequence of a located record, line breaks removed; dst must hold r.n_bases bytes
+inline void copy_sequence(const char* data, const RecordView& r, char* dst) {
+  size_t b = r.seq_b;
+  while (b < r.seq_e) {
+    const char* nl = (const char*)memchr(data + b, '\n', r.seq_e - b);
+    const size_t e = nl ? (size_t)(nl - data) : r.seq_e;
+    size_t len = e - b;
+    if (len && data[b + len - 1] == '\r') len--;
+    memcpy(dst, data + b, len);
+    dst += len;
+    b = e + 1;
   }
-  return parse_fastx((const char*)fv.p, fv.n, out);     // plain text: parsed straight from the mapping
 }
+
+// records of an in-memory FASTA / FASTQ text (copies)
+inline bool parse_fastx(const char* data, size_t n, std::vector<Record>& out) {
+  std::vector<RecordView> v;
+  if (!scan_fastx(data, n, v)) return false;
+  out.reserve(out.size() + v.size());
+  for (auto& r : v) {
+    Record rec;
+    rec.id = std::move(r.id);
+    rec.seq.resize(r.n_bases);
+    if (r.n_bases) copy_sequence(data, r, &rec.seq[0]);
+    out.push_back(std::move(rec));
+  }
+  return true;
+}
+
+// a file opened for the two-step read: the text stays alive (the mapping, or the inflated buffer) until the sequences are copied
+struct LoadedFile {
+  std::unique_ptr<FileView> fv;
+  std::string text;
+  const char* data = nullptr;
+  size_t n = 0;
+  std::vector<RecordView> recs;
+};
+inline bool open_fastx(const std::string& path, LoadedFile& f, int inflate_threads = 1) {
+  f.fv.reset(new FileView(path));
+  if (!f.fv->ok) return false;
+  if (f.fv->n >= 2 && f.fv->p[0] == 0x1f && f.fv->p[1] == 0x8b) {
+    if (!inflate_gzip(RawSpan{f.fv->p, f.fv->n}, f.text, inflate_threads)) return false;
+    f.fv.reset();                                               // the compressed bytes are not needed any more
+    f.data = f.text.data(); f.n = f.text.size();
+  } else { f.data = (const char*)f.fv->p; f.n = f.fv->n; }     // plain text: scanned straight from the mapping
+  return scan_fastx(f.data, f.n, f.recs);
+}
+
+inline bool read_fastx(const std::string& path, std::vector<Record>& out, int inflate_threads = 1) {
+  LoadedFile f;
+  if (!open_fastx(path, f, inflate_threads)) return false;
+  out.reserve(out.size() + f.recs.size());
+  for (auto& r : f.recs) {
+    Record rec;
+    rec.id = std::move(r.id);
+    rec.seq.resize(r.n_bases);
+    if (r.n_bases) copy_sequence(f.data, r, &rec.seq[0]);
+    out.push_back(std::move(rec));
+  }
+  return true;
+}
+
+// allocator that leaves trivially constructible elements uninitialised: a std::vector<uint8_t> of tens of GB is not zero-filled
+// by one thread before the parallel copies write (and first-touch) it
+template <class T>
+struct no_init_alloc : std::allocator<T> {
+  template <class U> struct rebind { using other = no_init_alloc<U>; };
+  template <class U> void construct(U* p) noexcept { ::new ((void*)p) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
 
 }  // namespace fastx

@@ -49,7 +49,7 @@ struct Genome {          // one Sketch-to-be (src/types.rs:253-277 metadata kept
 
 struct Inputs {
   std::vector<Genome> genomes;       // sorted by (file_name, contig_order) (src/types.rs:360-364)
-  std::vector<uint8_t> bases;
+  std::vector<uint8_t, fastx::no_init_alloc<uint8_t>> bases;      // filled (and first touched) by the parallel copies of load_inputs
   std::vector<uint64_t> contig_off{0};
   std::vector<uint32_t> genome_of_contig;
 };
@@ -57,20 +57,22 @@ struct Inputs {
 // file_io::fastx_to_sketches / fastx_to_multiple_sketch_rewrite record rules (src/file_io.rs:141-362)
 void load_inputs(std::vector<std::string> files, bool individual, int threads, Inputs& in) {
   std::sort(files.begin(), files.end());                      // final order = (file_name, contig_order)
-  std::vector<std::vector<Record>> recs(files.size());
+  // step 1 (files in parallel): open / inflate and LOCATE the records; the text stays alive.  Step 2 (serial, metadata only):
+  // record rules + layout.  Step 3 (parallel): line breaks are stripped straight into the flat buffer -- one copy per base.
+  std::vector<fastx::LoadedFile> loaded(files.size());
   std::vector<int> status(files.size(), 0);
   threads = std::max(threads, 1);
   {   // files in parallel (dynamic); threads left over when there are few files go to member-parallel BGZF inflate
     std::atomic<size_t> next{0};
     const int per_file = std::max<int>(1, threads / (int)std::max<size_t>(files.size(), 1));
-    auto worker = [&] { for (size_t i; (i = next.fetch_add(1)) < files.size();) status[i] = read_fastx(files[i], recs[i], per_file) ? 1 : -1; };
+    auto worker = [&] { for (size_t i; (i = next.fetch_add(1)) < files.size();) status[i] = fastx::open_fastx(files[i], loaded[i], per_file) ? 1 : -1; };
     std::vector<std::thread> pool;
     for (int t = 1; t < threads && (size_t)t < files.size(); t++) pool.emplace_back(worker);
     worker();
     for (auto& t : pool) t.join();
   }
   // record rules + layout (serial, metadata only), then one parallel copy of the sequences into the flat buffer
-  struct Copy { const std::string* seq; uint64_t off; };
+  struct Copy { size_t file; const fastx::RecordView* rec; uint64_t off; };
   std::vector<Copy> copies;
   uint64_t total = in.bases.size();
   for (size_t i = 0; i < files.size(); i++) {
@@ -78,11 +80,11 @@ void load_inputs(std::vector<std::string> files, bool individual, int threads, I
     size_t kept = 0;
     if (!individual) {
       Genome g; g.file_name = files[i];
-      for (auto& r : recs[i]) {
-        if (r.seq.size() < 500) continue;                     // MIN_LENGTH_CONTIG (src/params.rs:42, src/file_io.rs:176)
-        g.contigs.push_back(r.id); g.total_len += r.seq.size();
-        copies.push_back(Copy{&r.seq, total});
-        total += r.seq.size();
+      for (auto& r : loaded[i].recs) {
+        if (r.n_bases < 500) continue;                        // MIN_LENGTH_CONTIG (src/params.rs:42, src/file_io.rs:176)
+        g.contigs.push_back(r.id); g.total_len += r.n_bases;
+        copies.push_back(Copy{i, &r, total});
+        total += r.n_bases;
         in.contig_off.push_back(total);
         in.genome_of_contig.push_back((uint32_t)in.genomes.size());
         kept++;
@@ -91,14 +93,14 @@ void load_inputs(std::vector<std::string> files, bool individual, int threads, I
       else fprintf(stderr, "WARN File %s consists of only contigs < 500 bp. Skipping this file.\n", files[i].c_str());
     } else {
       bool warned = false;
-      for (auto& r : recs[i]) {
-        if (r.seq.size() < 500) {
+      for (auto& r : loaded[i].recs) {
+        if (r.n_bases < 500) {
           if (!warned) { fprintf(stderr, "WARN At least one sequence in file %s has < 500 bp. These sequences will be skipped.\n", files[i].c_str()); warned = true; }
           continue;
         }
-        Genome g; g.file_name = files[i]; g.contigs.push_back(r.id); g.total_len = r.seq.size(); g.contig_order = kept++;
-        copies.push_back(Copy{&r.seq, total});
-        total += r.seq.size();
+        Genome g; g.file_name = files[i]; g.contigs.push_back(r.id); g.total_len = r.n_bases; g.contig_order = kept++;
+        copies.push_back(Copy{i, &r, total});
+        total += r.n_bases;
         in.contig_off.push_back(total);
         in.genome_of_contig.push_back((uint32_t)in.genomes.size());
         in.genomes.push_back(std::move(g));
@@ -108,7 +110,7 @@ void load_inputs(std::vector<std::string> files, bool individual, int threads, I
   in.bases.resize(total);
   {
     std::atomic<size_t> next{0};
-    auto worker = [&] { for (size_t i; (i = next.fetch_add(1)) < copies.size();) memcpy(in.bases.data() + copies[i].off, copies[i].seq->data(), copies[i].seq->size()); };
+    auto worker = [&] { for (size_t i; (i = next.fetch_add(1)) < copies.size();) fastx::copy_sequence(loaded[copies[i].file].data, *copies[i].rec, (char*)in.bases.data() + copies[i].off); };
     std::vector<std::thread> pool;
     for (int t = 1; t < threads && (size_t)t < copies.size(); t++) pool.emplace_back(worker);
     worker();

@@ -26,7 +26,8 @@ namespace sk_inflate {
 constexpr int LT_BITS = 11;     // first-level bits of the literal/length table
 constexpr int DT_BITS = 8;      // ... of the distance table
 // table entry: [31:16] payload (literal byte, length / distance base, or sub-table start), [15:12] kind, [11:8] extra bits (or
-// sub-table bits), [7:0] code length in bits (for sub-table pointers: LT_BITS / DT_BITS)
+// sub-table bits), [7:0] bits to consume = code length + extra bits (for sub-table pointers: LT_BITS / DT_BITS; inside a
+// sub-table: the bits beyond the first level + extra bits)
 enum : uint32_t { K_LIT = 1u << 12, K_BASE = 2u << 12, K_EOB = 4u << 12, K_SUB = 8u << 12 };
 
 struct Tables {
@@ -80,7 +81,8 @@ static inline bool build_table(const uint8_t* lens, int n_sym, int table_bits, u
   for (int s = 0; s < n_sym; s++) {
     const int l = lens[s];
     if (!l) continue;
-    const uint32_t e = sym_entry[s] | (uint32_t)l, r = codes[s];
+    const uint32_t xb = (sym_entry[s] & K_BASE) ? ((sym_entry[s] >> 8) & 15) : 0;     // extra bits are consumed together with the code
+    const uint32_t e = sym_entry[s] | ((uint32_t)l + xb), r = codes[s];
     if (l <= table_bits) {
       for (uint32_t i = r; i < prim; i += 1u << l) table[i] = e;
     } else {
@@ -88,7 +90,7 @@ static inline bool build_table(const uint8_t* lens, int n_sym, int table_bits, u
       const int sb = sub_len[p] - table_bits;
       const uint32_t hi = r >> table_bits, step = 1u << (l - table_bits);
       // inside the sub-table the entry's length field counts only the bits beyond the first level
-      const uint32_t es = sym_entry[s] | (uint32_t)(l - table_bits);
+      const uint32_t es = sym_entry[s] | ((uint32_t)(l - table_bits) + xb);
       for (uint32_t i = hi; i < (1u << sb); i += step) table[sub_start[p] + i] = es;
     }
   }
@@ -297,20 +299,21 @@ inline bool inflate_raw(const uint8_t* in, size_t in_len, std::string& out, size
             }
             if (e & K_EOB) { bb >>= (e & 0xFF); bc -= (int)(e & 0xFF); eob = true; break; }
             if (!(e & K_BASE)) return false;
-            bb >>= (e & 0xFF); bc -= (int)(e & 0xFF);
-            const uint32_t xb = (e >> 8) & 15;
-            const uint32_t len = (e >> 16) + ((uint32_t)bb & ((1u << xb) - 1));
-            bb >>= xb; bc -= (int)xb;
+            // code + extra bits leave the buffer with ONE shift; the extra bits are read from the saved copy off the critical chain
+            const uint64_t sv = bb;
+            const uint32_t tb = e & 0xFF, xb = (e >> 8) & 15;
+            bb >>= tb; bc -= (int)tb;
+            const uint32_t len = (e >> 16) + ((uint32_t)(sv >> (tb - xb)) & ((1u << xb) - 1));
             uint32_t d = dt[bb & ((1u << DT_BITS) - 1)];
             if (d & K_SUB) {
               bb >>= DT_BITS; bc -= DT_BITS;
               d = dt[(d >> 16) + (bb & ((1u << ((d >> 8) & 15)) - 1))];
             }
             if (!(d & K_BASE)) return false;
-            bb >>= (d & 0xFF); bc -= (int)(d & 0xFF);
-            const uint32_t db = (d >> 8) & 15;
-            const size_t dist = (d >> 16) + ((uint32_t)bb & ((1u << db) - 1));
-            bb >>= db; bc -= (int)db;
+            const uint64_t sd = bb;
+            const uint32_t td = d & 0xFF, db = (d >> 8) & 15;
+            bb >>= td; bc -= (int)td;
+            const size_t dist = (d >> 16) + ((uint32_t)(sd >> (td - db)) & ((1u << db) - 1));
             if (dist > pos - base) return false;
             char* dst = o + pos;
             const char* src = dst - dist;
@@ -343,17 +346,15 @@ inline bool inflate_raw(const uint8_t* in, size_t in_len, std::string& out, size
           uint32_t e = lt[bb & ((1u << LT_BITS) - 1)];
           int used = 0;
           if (e & K_SUB) { const uint32_t sb = (e >> 8) & 15; e = lt[(e >> 16) + ((bb >> LT_BITS) & ((1u << sb) - 1))]; used = LT_BITS; }
-          used += (int)(e & 0xFF);
+          used += (int)(e & 0xFF);                               // code (+ extra bits of a length symbol)
           if (used > bc) return false;
+          const uint64_t sv = bb;
           bb >>= used; bc -= used;
           if (e & K_LIT) { ensure(2); out[pos++] = (char)(e >> 16); if (e & (1u << 8)) out[pos++] = (char)(e >> 24); continue; }
           if (e & K_EOB) break;
           if (!(e & K_BASE)) return false;
           const int xb = (int)((e >> 8) & 15);
-          while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }
-          if (xb > bc) return false;
-          const uint32_t len = (e >> 16) + ((uint32_t)bb & ((1u << xb) - 1));
-          bb >>= xb; bc -= xb;
+          const uint32_t len = (e >> 16) + ((uint32_t)(sv >> (used - xb)) & ((1u << xb) - 1));
           while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }
           uint32_t d = dt[bb & ((1u << DT_BITS) - 1)];
           used = 0;
@@ -361,12 +362,9 @@ inline bool inflate_raw(const uint8_t* in, size_t in_len, std::string& out, size
           if (!(d & K_BASE)) return false;
           used += (int)(d & 0xFF);
           if (used > bc) return false;
-          bb >>= used; bc -= used;
           const int db = (int)((d >> 8) & 15);
-          while (bc < 56 && ip < in_end) { bb |= (uint64_t)*ip++ << bc; bc += 8; }
-          if (db > bc) return false;
-          const size_t dist = (d >> 16) + ((uint32_t)bb & ((1u << db) - 1));
-          bb >>= db; bc -= db;
+          const size_t dist = (d >> 16) + ((uint32_t)(bb >> (used - db)) & ((1u << db) - 1));
+          bb >>= used; bc -= used;
           if (dist > pos - base) return false;
           ensure(len);
           for (uint32_t i = 0; i < len; i++) { out[pos] = out[pos - dist]; pos++; }

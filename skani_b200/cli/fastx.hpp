@@ -92,12 +92,24 @@ inline bool inflate_gzip(const RawSpan raw, std::string& out, int inflate_thread
       out.resize(total);
       std::atomic<size_t> next{0};
       std::atomic<bool> ok{true};
+      const bool use_fast = getenv("SK_ZLIB_INFLATE") == nullptr;
       auto work = [&] {
         for (size_t i; (i = next.fetch_add(1)) < mem.size();) {
           const Mem& m = mem[i];
           if (m.isize == 0) continue;
           const unsigned char* p = raw.data() + m.off;
           const size_t xlen = p[10] | (p[11] << 8), hdr = 12 + xlen;
+          if (hdr + 8 > m.csize) { ok = false; continue; }
+          if (use_fast) {   // whole-buffer decoder into a per-thread scratch string (a member is <= 64 KB), zlib if it declines
+            static thread_local std::string scratch;
+            scratch.clear();
+            size_t used = 0;
+            if (sk_inflate::inflate_raw(p + hdr, raw.size() - (m.off + hdr), scratch, 0, &used) && scratch.size() == m.isize &&
+                used + hdr + 8 <= m.csize) {
+              memcpy(&out[m.out_off], scratch.data(), m.isize);
+              continue;
+            }
+          }
           z_stream zs;
           memset(&zs, 0, sizeof(zs));
           if (inflateInit2(&zs, -15) != Z_OK) { ok = false; continue; }

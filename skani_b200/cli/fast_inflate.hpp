@@ -17,11 +17,56 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <stdlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include <algorithm>
+#include <new>
+#ifdef SK_INFLATE_TRACE
+#include <chrono>
+#include <cstdio>
+#endif
 #include <string>
 #include <vector>
 
 namespace sk_inflate {
+
+// Growable byte buffer that does NOT initialise new space (std::string::resize zero-fills, which for a multi-GB text is a
+// single-threaded pass over memory the decoder is about to overwrite anyway): malloc / realloc, size <= capacity.
+template <class T>
+class RawBuf {
+ public:
+  RawBuf() {}
+  RawBuf(const RawBuf&) = delete;
+  RawBuf& operator=(const RawBuf&) = delete;
+  RawBuf(RawBuf&& o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_) { o.p_ = nullptr; o.n_ = o.cap_ = 0; }
+  RawBuf& operator=(RawBuf&& o) noexcept { if (this != &o) { free(p_); p_ = o.p_; n_ = o.n_; cap_ = o.cap_; o.p_ = nullptr; o.n_ = o.cap_ = 0; } return *this; }
+  ~RawBuf() { free(p_); }
+  size_t size() const { return n_; }
+  size_t capacity() const { return cap_; }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  T& operator[](size_t i) { return p_[i]; }
+  const T& operator[](size_t i) const { return p_[i]; }
+  void clear() { n_ = 0; }
+  void release() { free(p_); p_ = nullptr; n_ = cap_ = 0; }
+  void reserve(size_t c) {
+    if (c <= cap_) return;
+    T* q = (T*)realloc(p_, c * sizeof(T));
+    if (!q) throw std::bad_alloc();
+    p_ = q; cap_ = c;
+  }
+  void resize(size_t n) { if (n > cap_) reserve(std::max(n, cap_ + cap_ / 2)); n_ = n; }     // new elements are uninitialised
+  void push_back(T v) { if (n_ == cap_) reserve(std::max<size_t>(cap_ * 2, 4096)); p_[n_++] = v; }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+};
+typedef RawBuf<char> TextBuf;
+typedef RawBuf<uint16_t> SymBuf;
 
 constexpr int LT_BITS = 11;     // first-level bits of the literal/length table
 constexpr int DT_BITS = 8;      // ... of the distance table
@@ -141,7 +186,7 @@ static inline uint64_t load64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); 
 
 // Decodes ONE raw deflate stream starting at in[0].  Output is appended to `out` (which also serves as the window: matches may
 // reach back into bytes that were there before, never before out[base]).  On success *in_used = compressed bytes consumed.
-inline bool inflate_raw(const uint8_t* in, size_t in_len, std::string& out, size_t base, size_t* in_used) {
+inline bool inflate_raw(const uint8_t* in, size_t in_len, TextBuf& out, size_t base, size_t* in_used) {
   const uint8_t* ip = in;
   const uint8_t* const in_end = in + in_len;
   uint64_t bb = 0;       // bit buffer, LSB first
@@ -388,7 +433,7 @@ typedef unsigned long (*crc_fn)(unsigned long, const unsigned char*, unsigned in
 // gzip file (one or several members back to back, flate2 MultiGzDecoder semantics; bytes after the last member that do not
 // start a new one end the stream, as zlib's gzread does) -> text.  Returns false on anything unexpected; `out` is then
 // unspecified and the caller decodes the file with zlib instead.
-inline bool gunzip(const uint8_t* p, size_t n, std::string& out, crc_fn crc) {
+inline bool gunzip(const uint8_t* p, size_t n, TextBuf& out, crc_fn crc) {
   out.clear();
   if (n >= 18) {   // size hint: ISIZE of the last member (exact for single-member files below 4 GB)
     const uint8_t* t = p + n - 4;
@@ -426,6 +471,430 @@ inline bool gunzip(const uint8_t* p, size_t n, std::string& out, crc_fn crc) {
     members++;
   }
   return members > 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Block-parallel decoding of ONE gzip member (a single large `.fa.gz`, e.g. a multi-FASTA of contigs read with -i).
+//
+// A deflate stream has no index, but its blocks can be found and decoded out of order (the two-pass scheme of pugz /
+// rapidgzip, restated here for nucleotide TEXT):
+//   1. the compressed payload is cut into chunks; every chunk but the first looks for the first bit position at which a
+//      non-final dynamic-Huffman block header parses (complete code sets, an end-of-block code), the whole block decodes,
+//      every literal is a text byte and the next block header is plausible too;
+//   2. every chunk is decoded from its block start to the next chunk's start into 16-bit SYMBOLS: a byte, or 256 + w for a
+//      byte copied from position w of the (still unknown) 32 KB window before the chunk;
+//   3. the windows are resolved front to back (only the last 32 KB of a chunk matter for the next one), then all chunks are
+//      resolved into the output in parallel.
+// A wrong guess in step 1 cannot survive: the chunk before it must arrive at exactly that bit position, and the member's
+// ISIZE and CRC-32 are checked at the end.  On any failure the function returns false and the caller decodes serially.
+// ---------------------------------------------------------------------------------------------------------------------
+struct BitPos {
+  const uint8_t* in; size_t nbytes; size_t pos;       // pos = absolute bit position
+  inline uint64_t peek() const {                      // >= 57 valid bits while >= 8 bytes are left; zeros past the end
+    const size_t by = pos >> 3;
+    uint64_t v = 0;
+    if (by + 8 <= nbytes) memcpy(&v, in + by, 8);
+    else for (size_t i = 0; by + i < nbytes; i++) v |= (uint64_t)in[by + i] << (8 * i);
+    return v >> (pos & 7);
+  }
+  inline bool has(size_t nbits) const { return pos + nbits <= nbytes * 8; }
+};
+
+static inline bool text_byte(uint32_t c) { return c == 9 || c == 10 || c == 13 || (c >= 32 && c < 127); }
+
+// header of a dynamic block at br.pos (after the 3 header bits): code sets -> tables
+static inline bool parse_dynamic(BitPos& br, Tables& T) {
+  if (!br.has(14)) return false;
+  uint64_t v = br.peek();
+  const int hlit = 257 + (int)(v & 31), hdist = 1 + (int)((v >> 5) & 31), hclen = 4 + (int)((v >> 10) & 15);
+  br.pos += 14;
+  if (hlit > 286 || hdist > 30) return false;
+  static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  uint8_t cl[19] = {0};
+  if (!br.has((size_t)hclen * 3)) return false;
+  v = br.peek();                                      // 19 * 3 = 57 bits at most
+  for (int i = 0; i < hclen; i++) cl[order[i]] = (uint8_t)((v >> (3 * i)) & 7);
+  br.pos += (size_t)hclen * 3;
+  uint16_t clt[128];
+  {
+    int count[8] = {0};
+    for (int s2 = 0; s2 < 19; s2++) count[cl[s2]]++;
+    count[0] = 0;
+    uint32_t kraft = 0;
+    for (int l = 1; l <= 7; l++) kraft += (uint32_t)count[l] << (7 - l);
+    if (kraft != 128) return false;
+    uint32_t nc[8], code = 0;
+    for (int l = 1; l <= 7; l++) { code = (code + (uint32_t)count[l - 1]) << 1; nc[l] = code; }
+    for (int s2 = 0; s2 < 19; s2++) {
+      const int l = cl[s2];
+      if (!l) continue;
+      const uint32_t r = rev_bits(nc[l]++, l);
+      for (uint32_t i = r; i < 128; i += 1u << l) clt[i] = (uint16_t)((s2 << 4) | l);
+    }
+  }
+  uint8_t ll[288 + 32];
+  int n = 0;
+  const int total = hlit + hdist;
+  while (n < total) {
+    if (!br.has(1)) return false;
+    v = br.peek();
+    const uint16_t e = clt[v & 127];
+    const int l = e & 15, sym = e >> 4;
+    if (!br.has((size_t)l)) return false;
+    br.pos += (size_t)l; v >>= l;
+    if (sym < 16) { ll[n++] = (uint8_t)sym; continue; }
+    int rep, val = 0, eb;
+    if (sym == 16) { if (n == 0) return false; val = ll[n - 1]; eb = 2; rep = 3; }
+    else if (sym == 17) { eb = 3; rep = 3; }
+    else { eb = 7; rep = 11; }
+    if (!br.has((size_t)eb)) return false;
+    rep += (int)(v & ((1u << eb) - 1));
+    br.pos += (size_t)eb;
+    if (n + rep > total) return false;
+    while (rep--) ll[n++] = (uint8_t)val;
+  }
+  if (ll[256] == 0) return false;
+  return build_litlen(ll, hlit, T) && build_dist(ll + hlit, hdist, T);
+}
+static inline bool build_fixed(Tables& T) {
+  uint8_t ll[288 + 32];
+  for (int i = 0; i < 144; i++) ll[i] = 8;
+  for (int i = 144; i < 256; i++) ll[i] = 9;
+  for (int i = 256; i < 280; i++) ll[i] = 7;
+  for (int i = 280; i < 288; i++) ll[i] = 8;
+  for (int i = 0; i < 32; i++) ll[288 + i] = 5;
+  uint32_t ent[32];
+  for (int s2 = 0; s2 < 32; s2++) ent[s2] = s2 < 30 ? (((uint32_t)DIST_BASE[s2] << 16) | K_BASE | ((uint32_t)DIST_EXTRA[s2] << 8)) : 0;
+  return build_litlen(ll, 288, T) && build_table(ll + 288, 32, DT_BITS, T.dt, sizeof(T.dt) / 4, ent);
+}
+
+// symbols of ONE Huffman-coded block (tables built) appended to out; `text_only` rejects literals that are not text;
+// `limit` bounds the block's output (a trial decode must not run away)
+static inline bool decode_block_symbols(BitPos& br, const Tables& T, SymBuf& out, bool text_only, size_t limit) {
+  const size_t start = out.size();
+  for (;;) {
+    if (!br.has(1)) return false;
+    uint64_t v = br.peek();
+    uint32_t e = T.lt[v & ((1u << LT_BITS) - 1)];
+    uint32_t used = 0;
+    if (e & K_SUB) { const uint32_t sb = (e >> 8) & 15; e = T.lt[(e >> 16) + ((v >> LT_BITS) & ((1u << sb) - 1))]; used = LT_BITS; }
+    used += e & 0xFF;
+    if (!br.has(used)) return false;
+    if (e & K_LIT) {
+      const uint32_t c0 = (e >> 16) & 0xFF;
+      if (text_only && !text_byte(c0)) return false;
+      out.push_back((uint16_t)c0);
+      if (e & (1u << 8)) { const uint32_t c1 = (e >> 24) & 0xFF; if (text_only && !text_byte(c1)) return false; out.push_back((uint16_t)c1); }
+      br.pos += used;
+      if (out.size() - start > limit) return false;
+      continue;
+    }
+    if (e & K_EOB) { br.pos += used; return true; }
+    if (!(e & K_BASE)) return false;
+    const uint32_t xb = (e >> 8) & 15;
+    const uint32_t len = (e >> 16) + ((uint32_t)(v >> (used - xb)) & ((1u << xb) - 1));
+    br.pos += used;
+    v = br.peek();
+    uint32_t d = T.dt[v & ((1u << DT_BITS) - 1)];
+    used = 0;
+    if (d & K_SUB) { const uint32_t sb = (d >> 8) & 15; d = T.dt[(d >> 16) + ((v >> DT_BITS) & ((1u << sb) - 1))]; used = DT_BITS; }
+    if (!(d & K_BASE)) return false;
+    used += d & 0xFF;
+    if (!br.has(used)) return false;
+    const uint32_t db = (d >> 8) & 15;
+    const size_t dist = (d >> 16) + ((uint32_t)(v >> (used - db)) & ((1u << db) - 1));
+    br.pos += used;
+    if (dist > 32768) return false;
+    const size_t q = out.size();
+    if (q - start + len > limit) return false;
+    out.resize(q + len);
+    uint16_t* o = out.data();
+    for (uint32_t i = 0; i < len; i++) {
+      const size_t at = q + i;
+      if (at >= dist) o[at] = o[at - dist];
+      else o[at] = (uint16_t)(256 + (32768 - (dist - at)));        // position in the unknown window before the chunk
+    }
+  }
+}
+
+// The same without the per-literal checks, for the real pass: symbols written through a raw pointer with one capacity check
+// per symbol group, up to three look-ups per 64-bit load, word copies for matches inside the chunk.  The last bytes of the
+// input go through the careful routine above.
+static inline bool decode_block_symbols_fast(BitPos& br, const Tables& T, SymBuf& out) {
+  const uint8_t* const in = br.in;
+  const size_t nbytes = br.nbytes;
+  size_t pos = br.pos;
+  for (;;) {
+    if (out.capacity() < out.size() + 4096) out.reserve(std::max(out.capacity() * 2, out.size() + (1u << 20)));
+    uint16_t* const o = out.data();
+    size_t q = out.size();
+    const size_t q_lim = out.capacity() - 600;
+    bool eob = false;
+    while (q < q_lim && (pos >> 3) + 16 <= nbytes) {
+      uint64_t v = load64(in + (pos >> 3)) >> (pos & 7);             // >= 57 valid bits
+      uint32_t e = T.lt[v & ((1u << LT_BITS) - 1)];
+      if (e & K_LIT) {
+        uint32_t used = 0;
+        for (int k = 0; k < 3 && (e & K_LIT); k++) {                 // 3 x 11 bits of the 57
+          o[q] = (uint16_t)((e >> 16) & 0xFF); o[q + 1] = (uint16_t)(e >> 24);
+          q += 1 + ((e >> 8) & 1);
+          const uint32_t l = e & 0xFF;
+          used += l; v >>= l;
+          e = T.lt[v & ((1u << LT_BITS) - 1)];
+        }
+        pos += used;
+        continue;
+      }
+      uint32_t used = 0;
+      if (e & K_SUB) { const uint32_t sb = (e >> 8) & 15; e = T.lt[(e >> 16) + ((v >> LT_BITS) & ((1u << sb) - 1))]; used = LT_BITS; }
+      used += e & 0xFF;
+      if (e & K_LIT) { o[q++] = (uint16_t)((e >> 16) & 0xFF); pos += used; continue; }       // sub-table literals are single
+      if (e & K_EOB) { pos += used; eob = true; break; }
+      if (!(e & K_BASE)) return false;
+      const uint32_t xb = (e >> 8) & 15;
+      const uint32_t len = (e >> 16) + ((uint32_t)(v >> (used - xb)) & ((1u << xb) - 1));
+      pos += used; v >>= used;                                        // <= 20 bits gone: >= 37 left, a distance needs <= 28
+      uint32_t d = T.dt[v & ((1u << DT_BITS) - 1)];
+      used = 0;
+      if (d & K_SUB) { const uint32_t sb = (d >> 8) & 15; d = T.dt[(d >> 16) + ((v >> DT_BITS) & ((1u << sb) - 1))]; used = DT_BITS; }
+      if (!(d & K_BASE)) return false;
+      used += d & 0xFF;
+      const uint32_t db = (d >> 8) & 15;
+      const size_t dist = (d >> 16) + ((uint32_t)(v >> (used - db)) & ((1u << db) - 1));
+      pos += used;
+      if (dist > 32768) return false;
+      if (q >= dist) {
+        const uint16_t* src = o + q - dist;
+        uint16_t* dst = o + q;
+        if (dist >= 4) {                                              // 8-byte words of 4 symbols, in order
+          uint16_t* const end = dst + len;
+          do { memcpy(dst, src, 8); dst += 4; src += 4; } while (dst < end);
+        } else for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+      } else {
+        for (uint32_t i = 0; i < len; i++) {
+          const size_t at = q + i;
+          o[at] = at >= dist ? o[at - dist] : (uint16_t)(256 + (32768 - (dist - at)));
+        }
+      }
+      q += len;
+    }
+    out.resize(q);
+    br.pos = pos;
+    if (eob) return true;
+    // tail of the input, or the buffer has to grow: one careful step, then back to the fast loop
+    if ((pos >> 3) + 16 > nbytes) return decode_block_symbols(br, T, out, false, (size_t)-1 >> 1);
+  }
+}
+
+// one block (any type) at br.pos -> symbols; *final = BFINAL
+static inline bool decode_any_block(BitPos& br, Tables& T, SymBuf& out, bool* final, bool text_only, size_t limit) {
+  if (!br.has(3)) return false;
+  const uint64_t v = br.peek();
+  *final = (v & 1) != 0;
+  const uint32_t btype = (uint32_t)(v >> 1) & 3;
+  br.pos += 3;
+  if (btype == 0) {
+    br.pos = (br.pos + 7) & ~(size_t)7;
+    if (!br.has(32)) return false;
+    const uint64_t w = br.peek();
+    const uint32_t len = (uint32_t)w & 0xFFFF, nlen = (uint32_t)(w >> 16) & 0xFFFF;
+    if ((len ^ nlen) != 0xFFFF) return false;
+    br.pos += 32;
+    if (!br.has((size_t)len * 8) || len > limit) return false;
+    const uint8_t* src = br.in + (br.pos >> 3);
+    for (uint32_t i = 0; i < len; i++) { if (text_only && !text_byte(src[i])) return false; out.push_back(src[i]); }
+    br.pos += (size_t)len * 8;
+    return true;
+  }
+  if (btype == 1) { if (!build_fixed(T)) return false; }
+  else if (btype == 2) { if (!parse_dynamic(br, T)) return false; }
+  else return false;
+  return text_only ? decode_block_symbols(br, T, out, true, limit) : decode_block_symbols_fast(br, T, out);
+}
+
+// first bit position >= from (and < to) at which a non-final dynamic block of text starts, or SIZE_MAX
+static inline size_t find_block_start(const uint8_t* in, size_t nbytes, size_t from, size_t to, Tables& T, SymBuf& scratch) {
+  for (size_t b = from; b < to; b++) {
+    BitPos br{in, nbytes, b};
+    if (!br.has(3 + 14)) return (size_t)-1;
+    const uint64_t v = br.peek();
+    if ((v & 7) != 4) continue;                                     // BFINAL = 0, BTYPE = 2 (bits: 0, then 01 LSB first = value 4)
+    if (((v >> 3) & 31) > 29 || ((v >> 8) & 31) > 29) continue;     // HLIT <= 286, HDIST <= 30
+    scratch.clear();
+    bool fin = false;
+    if (!decode_any_block(br, T, scratch, &fin, true, 1u << 22)) continue;
+    if (scratch.size() < 1024) continue;                            // real blocks of a large text file are tens of KB
+    // the block that follows must look like a block too
+    BitPos nx = br;
+    if (!nx.has(3)) continue;
+    const uint64_t w = nx.peek();
+    const uint32_t bt = (uint32_t)(w >> 1) & 3;
+    if (bt == 3) continue;
+    if (bt == 2) { nx.pos += 3; Tables* T2 = new Tables; const bool okh = parse_dynamic(nx, *T2); delete T2; if (!okh) continue; }
+    else if (bt == 0) {
+      nx.pos += 3; nx.pos = (nx.pos + 7) & ~(size_t)7;
+      if (!nx.has(32)) continue;
+      const uint64_t x = nx.peek();
+      if ((((uint32_t)x & 0xFFFF) ^ ((uint32_t)(x >> 16) & 0xFFFF)) != 0xFFFF) continue;
+    }
+    return b;
+  }
+  return (size_t)-1;
+}
+
+typedef unsigned long (*crc_combine_fn)(unsigned long, unsigned long, long);
+
+// ONE gzip member decoded by `threads` threads (see above).  run(n, f) must execute f(0) .. f(n-1), possibly concurrently,
+// and return when all are done.  Returns false if the file is not a single member, is too small to bother, is not text, or
+// anything does not add up: the caller then uses the serial decoder.
+template <class ParallelFor>
+inline bool gunzip_parallel(const uint8_t* p, size_t n, TextBuf& out, int threads, crc_fn crc, crc_combine_fn crc_combine,
+                            ParallelFor&& run, size_t min_chunk = 4u << 20) {
+  if (threads < 2 || n < 18 + 2 * min_chunk || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8) return false;
+  const uint8_t flg = p[3];
+  if (flg & 0xE0) return false;
+  size_t h = 10;
+  if (flg & 4) { if (h + 2 > n) return false; h += 2 + (size_t)(p[h] | (p[h + 1] << 8)); }
+  if (flg & 8) { while (h < n && p[h]) h++; h++; }
+  if (flg & 16) { while (h < n && p[h]) h++; h++; }
+  if (flg & 2) h += 2;
+  if (h + 8 >= n) return false;
+  const size_t payload_end = n - 8;                                  // if this is the only member, its trailer is the last 8 bytes
+  const size_t K = std::min<size_t>((size_t)threads * 2, (payload_end - h) / min_chunk);
+  if (K < 3) return false;
+  struct Chunk { size_t start_bit = (size_t)-1, end_bit = 0; SymBuf sym; bool ok = false, final_seen = false; unsigned long crc = 0; size_t out_off = 0; };
+  std::vector<Chunk> ch(K);
+  const size_t span = (payload_end - h) / K;
+  ch[0].start_bit = h * 8;
+#ifdef SK_INFLATE_TRACE
+  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tt0 = tnow();
+#endif
+  // 1. block starts
+  run(K, [&](size_t k) {
+    if (k == 0) return;
+    Tables* T = new Tables;
+    SymBuf scratch;
+    scratch.reserve(1u << 20);
+    const size_t from = (h + k * span) * 8, to = (k + 1 < K ? (h + (k + 1) * span) : payload_end) * 8;
+    ch[k].start_bit = find_block_start(p, payload_end, from, to, *T, scratch);
+    delete T;
+  });
+  // chunks without a block start are merged into their predecessor
+  std::vector<size_t> use;
+  for (size_t k = 0; k < K; k++) if (ch[k].start_bit != (size_t)-1) use.push_back(k);
+  if (use.size() < 2) return false;
+#ifdef SK_INFLATE_TRACE
+  const double tt1 = tnow();
+#endif
+  // 2. symbols
+  run(use.size(), [&](size_t u) {
+    Chunk& c = ch[use[u]];
+    const size_t stop = u + 1 < use.size() ? ch[use[u + 1]].start_bit : (size_t)-1;
+    Tables* T = new Tables;
+    BitPos br{p, payload_end, c.start_bit};
+    c.sym.reserve((size_t)((stop == (size_t)-1 ? payload_end * 8 - c.start_bit : stop - c.start_bit) / 8 * 4));
+    bool good = true, fin = false;
+    while (good) {
+      if (br.pos == stop) break;
+      if (br.pos > stop) { good = false; break; }                    // ran past the next chunk's start: that start was not a block boundary
+      good = decode_any_block(br, *T, c.sym, &fin, false, (size_t)-1 >> 1);
+      if (good && fin) { c.final_seen = true; break; }
+    }
+    if (good && stop != (size_t)-1 && (c.final_seen || br.pos != stop)) good = false;
+    if (good && stop == (size_t)-1 && !c.final_seen) good = false;
+    c.end_bit = br.pos;
+    c.ok = good;
+    delete T;
+  });
+#ifdef SK_INFLATE_TRACE
+  const double tt2 = tnow();
+#endif
+  size_t total = 0;
+  for (size_t u = 0; u < use.size(); u++) { Chunk& c = ch[use[u]]; if (!c.ok) return false; c.out_off = total; total += c.sym.size(); }
+  // the member must end right before its trailer (otherwise: more members, or garbage -- the serial path sorts that out)
+  const Chunk& last = ch[use.back()];
+  if (((last.end_bit + 7) >> 3) != payload_end) return false;
+  const uint32_t want_crc = (uint32_t)p[n - 8] | ((uint32_t)p[n - 7] << 8) | ((uint32_t)p[n - 6] << 16) | ((uint32_t)p[n - 5] << 24);
+  const uint32_t want_len = (uint32_t)p[n - 4] | ((uint32_t)p[n - 3] << 8) | ((uint32_t)p[n - 2] << 16) | ((uint32_t)p[n - 1] << 24);
+  if ((uint32_t)total != want_len) return false;
+  // 3a. windows, front to back: window[u] = the 32 KB of output before chunk u (only tails are resolved here)
+  std::vector<std::vector<uint8_t>> win(use.size());
+  for (size_t u = 0; u + 1 < use.size(); u++) {
+    const Chunk& c = ch[use[u]];
+    const std::vector<uint8_t>& w = win[u];                          // window of THIS chunk (empty for the first)
+    std::vector<uint8_t>& nw = win[u + 1];
+    nw.assign(32768, 0);
+    const size_t m = c.sym.size();
+    const size_t take = std::min<size_t>(m, 32768);
+    // bytes of the next window that come from this chunk's own window (chunk shorter than 32 KB)
+    for (size_t i = 0; i < 32768 - take; i++) nw[i] = w.empty() ? 0 : w[i + take];
+    for (size_t i = 0; i < take; i++) {
+      const uint16_t sy = c.sym[m - take + i];
+      if (sy < 256) nw[32768 - take + i] = (uint8_t)sy;
+      else { if (w.empty()) return false; nw[32768 - take + i] = w[sy - 256]; }   // a reference before the start of the member
+    }
+  }
+#ifdef SK_INFLATE_TRACE
+  const double tt3 = tnow();
+#endif
+  // 3b. all chunks into the output, in parallel; CRC per chunk
+  out.resize(total);
+#ifdef SK_INFLATE_TRACE
+  const double tt4 = tnow();
+#endif
+  std::vector<char> bad(use.size(), 0);
+  run(use.size(), [&](size_t u) {
+    Chunk& c = ch[use[u]];
+    const std::vector<uint8_t>& w = win[u];
+    char* o = &out[c.out_off];
+    const uint16_t* sy = c.sym.data();
+    const size_t m = c.sym.size();
+    size_t i = 0;
+#if defined(__SSE2__)
+    for (; i + 16 <= m; i += 16) {                                    // 16 symbols at a time; groups without window references are packed
+      const __m128i a = _mm_loadu_si128((const __m128i*)(sy + i)), b = _mm_loadu_si128((const __m128i*)(sy + i + 8));
+      if (_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_srli_epi16(_mm_or_si128(a, b), 8), _mm_setzero_si128())) == 0xFFFF) {
+        _mm_storeu_si128((__m128i*)(o + i), _mm_packus_epi16(a, b));
+      } else {
+        for (size_t k = i; k < i + 16; k++) {
+          if (sy[k] < 256) o[k] = (char)sy[k];
+          else if (w.empty()) { bad[u] = 1; o[k] = 0; }
+          else o[k] = (char)w[sy[k] - 256];
+        }
+      }
+    }
+#endif
+    for (; i < m; i++) {
+      if (sy[i] < 256) o[i] = (char)sy[i];
+      else if (w.empty()) { bad[u] = 1; o[i] = 0; }
+      else o[i] = (char)w[sy[i] - 256];
+    }
+    if (crc) {
+      unsigned long cc = crc(0, nullptr, 0);
+      for (size_t q = 0; q < m;) { const size_t mm = std::min<size_t>(m - q, 1u << 30); cc = crc(cc, (const unsigned char*)o + q, (unsigned int)mm); q += mm; }
+      c.crc = cc;
+    }
+    c.sym.release();
+  });
+#ifdef SK_INFLATE_TRACE
+  fprintf(stderr, "[gunzip_parallel] find %.1f ms, symbols %.1f ms, windows %.1f ms, resize %.1f ms, resolve+crc %.1f ms (%zu chunks)\n", (tt1 - tt0) * 1e3, (tt2 - tt1) * 1e3, (tt3 - tt2) * 1e3, (tt4 - tt3) * 1e3, (tnow() - tt4) * 1e3, use.size());
+#endif
+  for (char b : bad) if (b) return false;
+  if (crc && crc_combine) {
+    unsigned long cc = crc(0, nullptr, 0);
+    for (size_t u = 0; u < use.size(); u++) {
+      const Chunk& c = ch[use[u]];
+      const size_t m = (u + 1 < use.size() ? ch[use[u + 1]].out_off : total) - c.out_off;
+      size_t left = m;
+      unsigned long part = c.crc;
+      // crc32_combine takes a (signed) long length: fine for chunks below 2^63
+      cc = crc_combine(cc, part, (long)left);
+    }
+    if ((uint32_t)cc != want_crc) return false;
+  }
+  return true;
 }
 
 }  // namespace sk_inflate

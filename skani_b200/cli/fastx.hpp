@@ -7,8 +7,10 @@
 // Ingestion speed: a file is read whole, inflated into one buffer and split into lines with
 // memchr (no per-byte state machine).  Block-gzipped files (BGZF: bgzip / htslib, every member carries its compressed
 // size in a 'BC' extra field) are inflated member-parallel with `inflate_threads` threads; ordinary single-member gzip has
-// no block index and is inflated by ONE stream (the caller runs files in parallel) -- by the whole-buffer decoder of
-// fast_inflate.hpp (1.6x zlib on nucleotide text, checked against zlib in tests/emu/emu_inflate.cpp), zlib as the fallback.
+// no block index: by the whole-buffer decoder of fast_inflate.hpp (1.7x zlib on nucleotide text), and when threads are to
+// spare (few large files) block-parallel by its two-pass scheme (blocks located by trial decoding, decoded against an unknown
+// window, resolved afterwards; ISIZE + CRC-32 verified); zlib as the fallback.  All of it checked against zlib in
+// tests/emu/emu_inflate.cpp.
 #pragma once
 #include <zlib.h>
 
@@ -24,6 +26,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -71,7 +74,8 @@ inline size_t bgzf_member_size(const unsigned char* p, size_t n) {
 
 // gzip bytes -> decompressed text: multi-member streams via zlib; BGZF member-parallel.
 struct RawSpan { const unsigned char* p; size_t n; const unsigned char* data() const { return p; } size_t size() const { return n; } const unsigned char& operator[](size_t i) const { return p[i]; } };
-inline bool inflate_gzip(const RawSpan raw, std::string& out, int inflate_threads = 1) {
+using TextBuf = sk_inflate::TextBuf;
+inline bool inflate_gzip(const RawSpan raw, TextBuf& out, int inflate_threads = 1) {
   out.clear();
   // ---- BGZF: every member announces its size, so the members can be located without inflating and inflated in parallel
   if (bgzf_member_size(raw.data(), raw.size())) {
@@ -101,7 +105,7 @@ inline bool inflate_gzip(const RawSpan raw, std::string& out, int inflate_thread
           const size_t xlen = p[10] | (p[11] << 8), hdr = 12 + xlen;
           if (hdr + 8 > m.csize) { ok = false; continue; }
           if (use_fast) {   // whole-buffer decoder into a per-thread scratch string (a member is <= 64 KB), zlib if it declines
-            static thread_local std::string scratch;
+            static thread_local TextBuf scratch;
             scratch.clear();
             size_t used = 0;
             if (sk_inflate::inflate_raw(p + hdr, raw.size() - (m.off + hdr), scratch, 0, &used) && scratch.size() == m.isize &&
@@ -131,6 +135,27 @@ inline bool inflate_gzip(const RawSpan raw, std::string& out, int inflate_thread
   //      fast_inflate.hpp first (1.6x zlib on nucleotide text); anything it does not like is decoded again by zlib below, which
   //      then accepts or rejects the file in its own terms.  SK_ZLIB_INFLATE=1 forces the zlib path (A/B, tests).
   if (getenv("SK_ZLIB_INFLATE") == nullptr) {
+    // ONE large member and threads to spare (a multi-FASTA of contigs read with -i): block-parallel two-pass decoding
+    // (fast_inflate.hpp gunzip_parallel); it declines anything that is not a single text member, or that does not verify
+    // (worth its 2 bytes of symbol buffer per output byte from ~30 MB of compressed data and 4 threads on)
+    if (inflate_threads >= (getenv("SK_INFLATE_MIN_CHUNK") ? 2 : 4) && getenv("SK_SERIAL_INFLATE") == nullptr) {
+      auto run = [&](size_t n, const std::function<void(size_t)>& f) {
+        std::atomic<size_t> next{0};
+        auto w = [&] { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); };
+        std::vector<std::thread> th;
+        for (int t = 1; t < inflate_threads && (size_t)t < n; t++) th.emplace_back(w);
+        w();
+        for (auto& t : th) t.join();
+      };
+      const char* mc = getenv("SK_INFLATE_MIN_CHUNK");            // test hook: small chunks on small files
+      if (sk_inflate::gunzip_parallel(raw.data(), raw.size(), out, inflate_threads, (sk_inflate::crc_fn)crc32,
+                                      (sk_inflate::crc_combine_fn)crc32_combine, run, mc ? (size_t)atoll(mc) : (8u << 20))) {
+        if (getenv("SK_TRACE")) fprintf(stderr, "[inflate] block-parallel: %zu -> %zu bytes with %d threads\n", raw.size(), out.size(), inflate_threads);
+        return true;
+      }
+      if (getenv("SK_TRACE")) fprintf(stderr, "[inflate] block-parallel declined, serial\n");
+      out.clear();
+    }
     if (sk_inflate::gunzip(raw.data(), raw.size(), out, (sk_inflate::crc_fn)crc32)) return true;
     out.clear();
   }
@@ -244,7 +269,7 @@ inline bool parse_fastx(const char* data, size_t n, std::vector<Record>& out) {
 // a file opened for the two-step read: the text stays alive (the mapping, or the inflated buffer) until the sequences are copied
 struct LoadedFile {
   std::unique_ptr<FileView> fv;
-  std::string text;
+  TextBuf text;
   const char* data = nullptr;
   size_t n = 0;
   std::vector<RecordView> recs;

@@ -99,7 +99,7 @@ int main(int argc, char** argv) {
     }
     if (argc >= 3 && std::string(argv[1]) == "fastx") {
       std::vector<fastx::Record> recs;
-      if (!fastx::read_fastx(argv[2], recs)) { printf("ERR\n"); return 0; }
+      if (!fastx::read_fastx(argv[2], recs, argc >= 4 ? std::max(1, atoi(argv[3])) : 1)) { printf("ERR\n"); return 0; }    // [threads]
       printf("OK %zu\n", recs.size());
       for (auto& r : recs) {
         uint64_t h = 0xcbf29ce484222325ull;

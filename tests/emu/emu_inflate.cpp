@@ -8,7 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <functional>
 #include <random>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -50,13 +53,15 @@ static bool zlib_gunzip(const std::string& in, std::string& out) {
 }
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+static bool same(const sk_inflate::TextBuf& a, const std::string& b) { return a.size() == b.size() && (b.empty() || memcmp(a.data(), b.data(), b.size()) == 0); }
+
 int main(int argc, char** argv) {
   std::mt19937_64 rng(20260924);
   int cases = 0, failures = 0;
   auto check = [&](const std::string& plain, const std::string& comp, const char* what) {
-    std::string got;
+    sk_inflate::TextBuf got;
     cases++;
-    if (!sk_inflate::gunzip((const uint8_t*)comp.data(), comp.size(), got, (sk_inflate::crc_fn)crc32) || got != plain) {
+    if (!sk_inflate::gunzip((const uint8_t*)comp.data(), comp.size(), got, (sk_inflate::crc_fn)crc32) || !same(got, plain)) {
       failures++;
       fprintf(stderr, "FAIL %s: plain %zu comp %zu got %zu\n", what, plain.size(), comp.size(), got.size());
     }
@@ -101,7 +106,8 @@ int main(int argc, char** argv) {
       check(plain + a + b, comp + std::string("\0\0\0garbage", 10), "trailing bytes");
     }
     if (t % 13 == 0 && n > 50) {                                // truncated / corrupted: false or the right bytes, never garbage
-      std::string comp = gz(plain, 6, Z_DEFAULT_STRATEGY), got;
+      std::string comp = gz(plain, 6, Z_DEFAULT_STRATEGY);
+      sk_inflate::TextBuf got;
       for (int k = 0; k < 6; k++) {
         std::string bad = comp;
         if (k < 3) bad.resize(bad.size() - 1 - rng() % std::min<size_t>(bad.size() - 1, 40));
@@ -110,7 +116,7 @@ int main(int argc, char** argv) {
         const bool ok = sk_inflate::gunzip((const uint8_t*)bad.data(), bad.size(), got, (sk_inflate::crc_fn)crc32);
         std::string ref;
         const bool zok = zlib_gunzip(bad, ref);
-        if (ok && (!zok || got != ref)) { failures++; fprintf(stderr, "FAIL corrupt case accepted: t=%d k=%d\n", t, k); }
+        if (ok && (!zok || !same(got, ref))) { failures++; fprintf(stderr, "FAIL corrupt case accepted: t=%d k=%d\n", t, k); }
       }
     }
   }
@@ -126,20 +132,70 @@ int main(int argc, char** argv) {
     if (!zlib_gunzip(comp, ref)) { fprintf(stderr, "zlib failed on %s\n", argv[a]); failures++; continue; }
     check(ref, comp, argv[a]);
   }
+  // ---- block-parallel decoding of one member (two-pass scheme): must equal the plain text, or decline
+  auto prun = [](size_t n, const std::function<void(size_t)>& f) {
+    std::vector<std::thread> th;
+    std::atomic<size_t> next{0};
+    auto w = [&] { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); };
+    for (int t = 1; t < 6; t++) th.emplace_back(w);
+    w();
+    for (auto& t : th) t.join();
+  };
+  {
+    int declined = 0, decoded = 0;
+    for (int t = 0; t < 36; t++) {
+      const size_t n = (t < 30 ? (1u << 20) : (10u << 20)) + rng() % (1u << 20);
+      std::string plain = fasta(n);
+      if (t % 10 == 9) for (auto& c : plain) c = (char)(rng() & 0xFF);              // binary: no text block will be found
+      const int level = 1 + t % 9;
+      std::string comp = gz(plain, level, (t % 4 == 3) ? Z_FILTERED : Z_DEFAULT_STRATEGY);
+      if (t % 10 == 8) comp += gz(fasta(5000), 6, Z_DEFAULT_STRATEGY);                  // two members: must decline
+      sk_inflate::TextBuf got;
+      cases++;
+      const size_t min_chunk = t < 30 ? (32u << 10) : (512u << 10);
+      const bool ok = sk_inflate::gunzip_parallel((const uint8_t*)comp.data(), comp.size(), got, 6, (sk_inflate::crc_fn)crc32,
+                                                  (sk_inflate::crc_combine_fn)crc32_combine, prun, min_chunk);
+      if (ok) { decoded++; if (!same(got, plain) || t % 10 == 8) { failures++; fprintf(stderr, "FAIL parallel gunzip t=%d\n", t); } }
+      else declined++;
+      if (!ok && t % 10 < 8) { failures++; fprintf(stderr, "FAIL parallel gunzip declined plain text t=%d level %d\n", t, level); }
+      if (t % 10 == 5) {                                                                  // corruption in the middle: decline (CRC) or decode like zlib
+        std::string bad = comp;
+        bad[bad.size() / 2] ^= 0x10;
+        sk_inflate::TextBuf g2;
+        std::string ref;
+        cases++;
+        const bool ok2 = sk_inflate::gunzip_parallel((const uint8_t*)bad.data(), bad.size(), g2, 6, (sk_inflate::crc_fn)crc32,
+                                                     (sk_inflate::crc_combine_fn)crc32_combine, prun, min_chunk);
+        if (ok2 && (!zlib_gunzip(bad, ref) || !same(g2, ref))) { failures++; fprintf(stderr, "FAIL parallel gunzip accepted a corrupt stream t=%d\n", t); }
+      }
+    }
+    printf("parallel gunzip: %d decoded, %d declined\n", decoded, declined);
+  }
   // rates on 64 MB of FASTA at level 6 (best of 3 each)
   {
     const std::string plain = fasta(64u << 20), comp = gz(plain, 6, Z_DEFAULT_STRATEGY);
     double best_f = 1e9, best_n = 1e9, best_z = 1e9;
-    for (int r = 0; r < 3; r++) {
-      std::string o1, o2, o3;
+    for (int r = 0; r < 2; r++) {
+      sk_inflate::TextBuf o1, o3;
+      std::string o2;
       double t0 = now(); const bool a = sk_inflate::gunzip((const uint8_t*)comp.data(), comp.size(), o1, (sk_inflate::crc_fn)crc32); double t1 = now();
       const bool b = zlib_gunzip(comp, o2); double t2 = now();
       sk_inflate::gunzip((const uint8_t*)comp.data(), comp.size(), o3, nullptr); double t3 = now();
-      if (!a || !b || o1 != o2 || o3 != o2) failures++;
+      if (!a || !b || !same(o1, o2) || !same(o3, o2)) failures++;
       best_f = std::min(best_f, t1 - t0); best_z = std::min(best_z, t2 - t1); best_n = std::min(best_n, t3 - t2);
     }
     printf("rates (64 MB FASTA, ratio %.2f): fast_inflate %.0f MB/s (%.0f without CRC), zlib %.0f MB/s\n", (double)plain.size() / comp.size(),
            plain.size() / 1e6 / best_f, plain.size() / 1e6 / best_n, plain.size() / 1e6 / best_z);
+    double best_p = 1e9;
+    for (int r = 0; r < 2; r++) {
+      sk_inflate::TextBuf o4;
+      double t0 = now();
+      const bool okp = sk_inflate::gunzip_parallel((const uint8_t*)comp.data(), comp.size(), o4, 6, (sk_inflate::crc_fn)crc32,
+                                                   (sk_inflate::crc_combine_fn)crc32_combine, prun, 1u << 20);
+      best_p = std::min(best_p, now() - t0);
+      if (!okp || !same(o4, plain)) failures++;
+    }
+    printf("parallel gunzip (6 threads, one member): %.0f MB/s\n", plain.size() / 1e6 / best_p);
   }
   printf("%d cases, %d failures\n", cases, failures);
   return failures ? 1 : 0;

@@ -22,8 +22,9 @@ def fnv(b):
     return h
 
 
-def tool(path):
-    out = subprocess.run([db_tool(), "fastx", str(path)], check=True, capture_output=True).stdout.decode().split("\n")
+def tool(path, threads=1, env=None):
+    out = subprocess.run([db_tool(), "fastx", str(path), str(threads)], check=True, capture_output=True,
+                         env=None if env is None else dict(os.environ, **env)).stdout.decode().split("\n")
     if out[0] == "ERR":
         return None
     n = int(out[0].split()[1])
@@ -105,3 +106,33 @@ def test_bgzf_member_parallel_inflate(tmp_path):
     mixed = tmp_path / "m.fa.gz"
     mixed.write_bytes(bgzf_compress(b">a\nACGT\n")[:-28] + gzip.compress(b"GGGG\n>b\nTT\n"))
     assert tool(mixed) == [("a", 8, fnv(b"ACGTGGGG")), ("b", 2, fnv(b"TT"))]
+
+
+def test_block_parallel_inflate_of_one_member(tmp_path):
+    """ONE ordinary gzip member read with several threads (two-pass block-parallel decoding, here forced onto a small file with
+    32 KB chunks) gives the records of the serial readers; a file that is not text, or has two members, silently takes the
+    serial path."""
+    import random
+    rnd = random.Random(9)
+    recs = []
+    for i in range(30):
+        seq = "".join(rnd.choice("ACGT") for _ in range(rnd.randrange(1000, 120000)))
+        recs.append((">contig_%d len=%d" % (i, len(seq)), seq))
+    text = "".join(h + "\n" + "\n".join(s[j:j + 80] for j in range(0, len(s), 80)) + "\n" for h, s in recs).encode()
+    plain = tmp_path / "big.fa"
+    plain.write_bytes(text)
+    want = expect(plain)
+    for level in (1, 6, 9):
+        gz = tmp_path / ("big%d.fa.gz" % level)
+        gz.write_bytes(gzip.compress(text, level))
+        serial = tool(gz, 1)
+        par = tool(gz, 6, env={"SK_INFLATE_MIN_CHUNK": "32768"})
+        assert serial == par == want
+        err = subprocess.run([db_tool(), "fastx", str(gz), "6"], capture_output=True, env=dict(os.environ, SK_INFLATE_MIN_CHUNK="32768", SK_TRACE="1")).stderr.decode()
+        assert "[inflate] block-parallel:" in err, err                      # the parallel path really ran (it did not decline)
+    two = tmp_path / "two.fa.gz"
+    two.write_bytes(gzip.compress(text, 6) + gzip.compress(b">extra\nACGTACGT\n", 6))
+    got = tool(two, 6, env={"SK_INFLATE_MIN_CHUNK": "32768"})
+    assert got[:-1] == want and got[-1] == ("extra", 8, fnv(b"ACGTACGT"))
+    err = subprocess.run([db_tool(), "fastx", str(two), "6"], capture_output=True, env=dict(os.environ, SK_INFLATE_MIN_CHUNK="32768", SK_TRACE="1")).stderr.decode()
+    assert "declined" in err

@@ -41,4 +41,14 @@ with tempfile.TemporaryDirectory() as d:
     r = json.loads(one.strip().split("\n")[-1]); r["kind"] = "bgzf, ONE file, member-parallel inflate"
     rows.append(r)
     print("%-6s t=%-3d  %8.1f MB/s of file bytes  %8.1f Mbases/s  (one file, member-parallel)" % ("bgzf", ncpu, r["file_MB_per_s"], r["bases_MB_per_s"]))
+    # ONE ordinary gzip member holding many contigs (a metagenome assembly read with -i): block-parallel two-pass inflate
+    k = min(n, 24)
+    big = b"".join(b">c%06d\n" % g + b"\n".join(bases[g * L:(g + 1) * L].tobytes()[i:i + 80] for i in range(0, L, 80)) + b"\n" for g in range(k))
+    bp = os.path.join(d, "big.fa.gz")
+    open(bp, "wb").write(gzip.compress(big, 6))
+    for t, env, label in ((1, {}, "serial"), (ncpu, {"SK_SERIAL_INFLATE": "1"}, "serial decoder, %d threads given" % ncpu), (ncpu, {}, "block-parallel")):
+        one = subprocess.run([BIN, "ingest", "-i", "-t", str(t), bp], capture_output=True, text=True, check=True, env=dict(os.environ, **env)).stdout
+        r = json.loads(one.strip().split("\n")[-1]); r["kind"] = "gzip, ONE file of %d contigs, %s" % (k, label)
+        rows.append(r)
+        print("%-6s t=%-3d  %8.1f MB/s of file bytes  %8.1f Mbases/s  (one file of %d contigs, %s)" % ("gzip", t, r["file_MB_per_s"], r["bases_MB_per_s"], k, label))
     print(json.dumps({"host_cpus": ncpu, "genomes": n, "genome_len": L, "rows": rows}))

@@ -750,8 +750,8 @@ typedef unsigned long (*crc_combine_fn)(unsigned long, unsigned long, long);
 // anything does not add up: the caller then uses the serial decoder.
 template <class ParallelFor>
 inline bool gunzip_parallel(const uint8_t* p, size_t n, TextBuf& out, int threads, crc_fn crc, crc_combine_fn crc_combine,
-                            ParallelFor&& run, size_t min_chunk = 4u << 20) {
-  if (threads < 2 || n < 18 + 2 * min_chunk || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8) return false;
+                            ParallelFor&& run, size_t min_chunk = 8u << 20) {
+  if (threads < 2 || n < 18 + 3 * min_chunk || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8) return false;
   const uint8_t flg = p[3];
   if (flg & 0xE0) return false;
   size_t h = 10;
@@ -761,139 +761,155 @@ inline bool gunzip_parallel(const uint8_t* p, size_t n, TextBuf& out, int thread
   if (flg & 2) h += 2;
   if (h + 8 >= n) return false;
   const size_t payload_end = n - 8;                                  // if this is the only member, its trailer is the last 8 bytes
-  const size_t K = std::min<size_t>((size_t)threads * 2, (payload_end - h) / min_chunk);
-  if (K < 3) return false;
-  struct Chunk { size_t start_bit = (size_t)-1, end_bit = 0; SymBuf sym; bool ok = false, final_seen = false; unsigned long crc = 0; size_t out_off = 0; };
-  std::vector<Chunk> ch(K);
-  const size_t span = (payload_end - h) / K;
-  ch[0].start_bit = h * 8;
-#ifdef SK_INFLATE_TRACE
-  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double tt0 = tnow();
-#endif
-  // 1. block starts
-  run(K, [&](size_t k) {
-    if (k == 0) return;
-    Tables* T = new Tables;
-    SymBuf scratch;
-    scratch.reserve(1u << 20);
-    const size_t from = (h + k * span) * 8, to = (k + 1 < K ? (h + (k + 1) * span) : payload_end) * 8;
-    ch[k].start_bit = find_block_start(p, payload_end, from, to, *T, scratch);
-    delete T;
-  });
-  // chunks without a block start are merged into their predecessor
-  std::vector<size_t> use;
-  for (size_t k = 0; k < K; k++) if (ch[k].start_bit != (size_t)-1) use.push_back(k);
-  if (use.size() < 2) return false;
-#ifdef SK_INFLATE_TRACE
-  const double tt1 = tnow();
-#endif
-  // 2. symbols
-  run(use.size(), [&](size_t u) {
-    Chunk& c = ch[use[u]];
-    const size_t stop = u + 1 < use.size() ? ch[use[u + 1]].start_bit : (size_t)-1;
-    Tables* T = new Tables;
-    BitPos br{p, payload_end, c.start_bit};
-    c.sym.reserve((size_t)((stop == (size_t)-1 ? payload_end * 8 - c.start_bit : stop - c.start_bit) / 8 * 4));
-    bool good = true, fin = false;
-    while (good) {
-      if (br.pos == stop) break;
-      if (br.pos > stop) { good = false; break; }                    // ran past the next chunk's start: that start was not a block boundary
-      good = decode_any_block(br, *T, c.sym, &fin, false, (size_t)-1 >> 1);
-      if (good && fin) { c.final_seen = true; break; }
-    }
-    if (good && stop != (size_t)-1 && (c.final_seen || br.pos != stop)) good = false;
-    if (good && stop == (size_t)-1 && !c.final_seen) good = false;
-    c.end_bit = br.pos;
-    c.ok = good;
-    delete T;
-  });
-#ifdef SK_INFLATE_TRACE
-  const double tt2 = tnow();
-#endif
-  size_t total = 0;
-  for (size_t u = 0; u < use.size(); u++) { Chunk& c = ch[use[u]]; if (!c.ok) return false; c.out_off = total; total += c.sym.size(); }
-  // the member must end right before its trailer (otherwise: more members, or garbage -- the serial path sorts that out)
-  const Chunk& last = ch[use.back()];
-  if (((last.end_bit + 7) >> 3) != payload_end) return false;
+  if ((payload_end - h) / min_chunk < 3) return false;
   const uint32_t want_crc = (uint32_t)p[n - 8] | ((uint32_t)p[n - 7] << 8) | ((uint32_t)p[n - 6] << 16) | ((uint32_t)p[n - 5] << 24);
   const uint32_t want_len = (uint32_t)p[n - 4] | ((uint32_t)p[n - 3] << 8) | ((uint32_t)p[n - 2] << 16) | ((uint32_t)p[n - 1] << 24);
-  if ((uint32_t)total != want_len) return false;
-  // 3a. windows, front to back: window[u] = the 32 KB of output before chunk u (only tails are resolved here)
-  std::vector<std::vector<uint8_t>> win(use.size());
-  for (size_t u = 0; u + 1 < use.size(); u++) {
-    const Chunk& c = ch[use[u]];
-    const std::vector<uint8_t>& w = win[u];                          // window of THIS chunk (empty for the first)
-    std::vector<uint8_t>& nw = win[u + 1];
-    nw.assign(32768, 0);
-    const size_t m = c.sym.size();
-    const size_t take = std::min<size_t>(m, 32768);
-    // bytes of the next window that come from this chunk's own window (chunk shorter than 32 KB)
-    for (size_t i = 0; i < 32768 - take; i++) nw[i] = w.empty() ? 0 : w[i + take];
-    for (size_t i = 0; i < take; i++) {
-      const uint16_t sy = c.sym[m - take + i];
-      if (sy < 256) nw[32768 - take + i] = (uint8_t)sy;
-      else { if (w.empty()) return false; nw[32768 - take + i] = w[sy - 256]; }   // a reference before the start of the member
+  struct Chunk { size_t start_bit = (size_t)-1, end_bit = 0; SymBuf sym; bool ok = false, final_seen = false; unsigned long crc = 0; size_t out_off = 0; };
+  out.clear();
+  { const size_t hint = (size_t)want_len; if (hint <= (payload_end - h) * 1100 + 65536) out.reserve(hint + 64); }
+  // The member is processed in ROUNDS of up to 2 x threads chunks, so that the symbol buffers (2 bytes per output byte) stay
+  // bounded for files of any size: a round starts at an exactly known bit (the end of the previous round) with a known window.
+  size_t round_bit = h * 8;
+  std::vector<uint8_t> round_win;                                    // the 32 KB of output before the round (empty for the first)
+  unsigned long crc_all = crc ? crc(0, nullptr, 0) : 0;
+  bool finished = false;
+#ifdef SK_INFLATE_TRACE
+  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+#endif
+  while (!finished) {
+#ifdef SK_INFLATE_TRACE
+    const double tt0 = tnow();
+#endif
+    const size_t byte0 = round_bit >> 3;
+    if (byte0 >= payload_end) return false;
+    const size_t remaining = payload_end - byte0;
+    const size_t K = std::max<size_t>(1, std::min<size_t>((size_t)threads * 2, (remaining + min_chunk - 1) / min_chunk));
+    const size_t round_end = std::min(payload_end, byte0 + K * min_chunk);
+    bool last_round = round_end == payload_end;
+    std::vector<Chunk> ch(K + 1);                                    // ch[K] = the block start the round's last chunk stops at (next round's first)
+    ch[0].start_bit = round_bit;
+    // 1. block starts (chunk k looks inside its own byte range; the sentinel looks right after the round)
+    run(K + 1, [&](size_t k) {
+      if (k == 0 || (k == K && last_round)) return;
+      const size_t from = std::max(round_bit + 1, (byte0 + k * min_chunk) * 8);
+      const size_t to = std::min(payload_end, byte0 + (k + (k == K ? 4 : 1)) * min_chunk) * 8;   // the sentinel may look further (a block can be longer than a small chunk)
+      if (from >= to) return;
+      Tables* T = new Tables;
+      SymBuf scratch;
+      scratch.reserve(1u << 20);
+      ch[k].start_bit = find_block_start(p, payload_end, from, to, *T, scratch);
+      delete T;
+    });
+    if (!last_round && ch[K].start_bit == (size_t)-1) {
+      // no qualifying block start after the round: fine if the search reached the end of the member (only the final block, or a
+      // few small ones, are left: the round's last chunk decodes them too), otherwise give up (serial decoder)
+      if (byte0 + (K + 4) * min_chunk < payload_end) return false;
+      last_round = true;
     }
-  }
+    std::vector<size_t> use;                                          // chunks without a block start are merged into their predecessor
+    for (size_t k = 0; k < K; k++) if (ch[k].start_bit != (size_t)-1) use.push_back(k);
 #ifdef SK_INFLATE_TRACE
-  const double tt3 = tnow();
+    const double tt1 = tnow();
 #endif
-  // 3b. all chunks into the output, in parallel; CRC per chunk
-  out.resize(total);
-#ifdef SK_INFLATE_TRACE
-  const double tt4 = tnow();
-#endif
-  std::vector<char> bad(use.size(), 0);
-  run(use.size(), [&](size_t u) {
-    Chunk& c = ch[use[u]];
-    const std::vector<uint8_t>& w = win[u];
-    char* o = &out[c.out_off];
-    const uint16_t* sy = c.sym.data();
-    const size_t m = c.sym.size();
-    size_t i = 0;
-#if defined(__SSE2__)
-    for (; i + 16 <= m; i += 16) {                                    // 16 symbols at a time; groups without window references are packed
-      const __m128i a = _mm_loadu_si128((const __m128i*)(sy + i)), b = _mm_loadu_si128((const __m128i*)(sy + i + 8));
-      if (_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_srli_epi16(_mm_or_si128(a, b), 8), _mm_setzero_si128())) == 0xFFFF) {
-        _mm_storeu_si128((__m128i*)(o + i), _mm_packus_epi16(a, b));
-      } else {
-        for (size_t k = i; k < i + 16; k++) {
-          if (sy[k] < 256) o[k] = (char)sy[k];
-          else if (w.empty()) { bad[u] = 1; o[k] = 0; }
-          else o[k] = (char)w[sy[k] - 256];
-        }
+    // 2. symbols
+    run(use.size(), [&](size_t u) {
+      Chunk& c = ch[use[u]];
+      const size_t stop = u + 1 < use.size() ? ch[use[u + 1]].start_bit : (last_round ? (size_t)-1 : ch[K].start_bit);
+      Tables* T = new Tables;
+      BitPos br{p, payload_end, c.start_bit};
+      c.sym.reserve((size_t)((stop == (size_t)-1 ? payload_end * 8 - c.start_bit : stop - c.start_bit) / 8 * 4) + 4096);
+      bool good = true, fin = false;
+      while (good) {
+        if (br.pos == stop) break;
+        if (br.pos > stop) { good = false; break; }                  // ran past the next start: that start was not a block boundary
+        good = decode_any_block(br, *T, c.sym, &fin, false, (size_t)-1 >> 1);
+        if (good && fin) { c.final_seen = true; break; }
       }
-    }
-#endif
-    for (; i < m; i++) {
-      if (sy[i] < 256) o[i] = (char)sy[i];
-      else if (w.empty()) { bad[u] = 1; o[i] = 0; }
-      else o[i] = (char)w[sy[i] - 256];
-    }
-    if (crc) {
-      unsigned long cc = crc(0, nullptr, 0);
-      for (size_t q = 0; q < m;) { const size_t mm = std::min<size_t>(m - q, 1u << 30); cc = crc(cc, (const unsigned char*)o + q, (unsigned int)mm); q += mm; }
-      c.crc = cc;
-    }
-    c.sym.release();
-  });
+      if (good && stop != (size_t)-1 && (c.final_seen || br.pos != stop)) good = false;
+      if (good && stop == (size_t)-1 && !c.final_seen) good = false;
+      c.end_bit = br.pos;
+      c.ok = good;
+      delete T;
+    });
 #ifdef SK_INFLATE_TRACE
-  fprintf(stderr, "[gunzip_parallel] find %.1f ms, symbols %.1f ms, windows %.1f ms, resize %.1f ms, resolve+crc %.1f ms (%zu chunks)\n", (tt1 - tt0) * 1e3, (tt2 - tt1) * 1e3, (tt3 - tt2) * 1e3, (tt4 - tt3) * 1e3, (tnow() - tt4) * 1e3, use.size());
+    const double tt2 = tnow();
 #endif
-  for (char b : bad) if (b) return false;
-  if (crc && crc_combine) {
-    unsigned long cc = crc(0, nullptr, 0);
+    const size_t out0 = out.size();
+    size_t total = 0;
+    for (size_t u = 0; u < use.size(); u++) { Chunk& c = ch[use[u]]; if (!c.ok) return false; c.out_off = out0 + total; total += c.sym.size(); }
+    if (last_round) {
+      // the member must end right before its trailer (otherwise: more members, or garbage -- the serial path sorts that out)
+      if (!ch[use.back()].final_seen || ((ch[use.back()].end_bit + 7) >> 3) != payload_end) return false;
+      finished = true;
+    }
+    // 3a. windows, front to back: win[u] = the 32 KB of output before chunk u (only tails are resolved here)
+    std::vector<std::vector<uint8_t>> win(use.size() + 1);
+    win[0] = round_win;
     for (size_t u = 0; u < use.size(); u++) {
       const Chunk& c = ch[use[u]];
-      const size_t m = (u + 1 < use.size() ? ch[use[u + 1]].out_off : total) - c.out_off;
-      size_t left = m;
-      unsigned long part = c.crc;
-      // crc32_combine takes a (signed) long length: fine for chunks below 2^63
-      cc = crc_combine(cc, part, (long)left);
+      const std::vector<uint8_t>& w = win[u];
+      std::vector<uint8_t>& nw = win[u + 1];
+      nw.assign(32768, 0);
+      const size_t m = c.sym.size();
+      const size_t take = std::min<size_t>(m, 32768);
+      for (size_t i = 0; i < 32768 - take; i++) nw[i] = w.empty() ? 0 : w[i + take];
+      for (size_t i = 0; i < take; i++) {
+        const uint16_t sy = c.sym[m - take + i];
+        if (sy < 256) nw[32768 - take + i] = (uint8_t)sy;
+        else { if (w.empty()) return false; nw[32768 - take + i] = w[sy - 256]; }   // a reference before the start of the member
+      }
     }
-    if ((uint32_t)cc != want_crc) return false;
+    // 3b. all chunks of the round into the output, in parallel; CRC per chunk
+    out.resize(out0 + total);
+    std::vector<char> bad(use.size(), 0);
+    run(use.size(), [&](size_t u) {
+      Chunk& c = ch[use[u]];
+      const std::vector<uint8_t>& w = win[u];
+      char* o = &out[c.out_off];
+      const uint16_t* sy = c.sym.data();
+      const size_t m = c.sym.size();
+      size_t i = 0;
+#if defined(__SSE2__)
+      for (; i + 16 <= m; i += 16) {                                  // 16 symbols at a time; groups without window references are packed
+        const __m128i a = _mm_loadu_si128((const __m128i*)(sy + i)), b = _mm_loadu_si128((const __m128i*)(sy + i + 8));
+        if (_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_srli_epi16(_mm_or_si128(a, b), 8), _mm_setzero_si128())) == 0xFFFF) {
+          _mm_storeu_si128((__m128i*)(o + i), _mm_packus_epi16(a, b));
+        } else {
+          for (size_t k = i; k < i + 16; k++) {
+            if (sy[k] < 256) o[k] = (char)sy[k];
+            else if (w.empty()) { bad[u] = 1; o[k] = 0; }
+            else o[k] = (char)w[sy[k] - 256];
+          }
+        }
+      }
+#endif
+      for (; i < m; i++) {
+        if (sy[i] < 256) o[i] = (char)sy[i];
+        else if (w.empty()) { bad[u] = 1; o[i] = 0; }
+        else o[i] = (char)w[sy[i] - 256];
+      }
+      if (crc) {
+        unsigned long cc = crc(0, nullptr, 0);
+        for (size_t q = 0; q < m;) { const size_t mm = std::min<size_t>(m - q, 1u << 30); cc = crc(cc, (const unsigned char*)o + q, (unsigned int)mm); q += mm; }
+        c.crc = cc;
+      }
+      c.sym.release();
+    });
+    for (char b : bad) if (b) return false;
+    if (crc && crc_combine)
+      for (size_t u = 0; u < use.size(); u++) {
+        const Chunk& c = ch[use[u]];
+        const size_t m = (u + 1 < use.size() ? ch[use[u + 1]].out_off : out0 + total) - c.out_off;
+        crc_all = crc_combine(crc_all, c.crc, (long)m);
+      }
+#ifdef SK_INFLATE_TRACE
+    fprintf(stderr, "[gunzip_parallel] round of %zu chunks: find %.1f ms, symbols %.1f ms, resolve+crc %.1f ms, %zu bytes\n", use.size(),
+            (tt1 - tt0) * 1e3, (tt2 - tt1) * 1e3, (tnow() - tt2) * 1e3, total);
+#endif
+    if (!finished) { round_bit = ch[K].start_bit; round_win = win[use.size()]; }
   }
+  if ((uint32_t)out.size() != want_len) return false;
+  if (crc && crc_combine && (uint32_t)crc_all != want_crc) return false;
   return true;
 }
 

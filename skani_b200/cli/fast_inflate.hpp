@@ -773,6 +773,7 @@ inline bool gunzip_parallel(const uint8_t* p, size_t n, TextBuf& out, int thread
   std::vector<uint8_t> round_win;                                    // the 32 KB of output before the round (empty for the first)
   unsigned long crc_all = crc ? crc(0, nullptr, 0) : 0;
   bool finished = false;
+  std::vector<SymBuf> pool((size_t)threads * 2 + 1);             // symbol buffers live across rounds: their pages are touched once
 #ifdef SK_INFLATE_TRACE
   auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 #endif
@@ -788,6 +789,7 @@ inline bool gunzip_parallel(const uint8_t* p, size_t n, TextBuf& out, int thread
     bool last_round = round_end == payload_end;
     std::vector<Chunk> ch(K + 1);                                    // ch[K] = the block start the round's last chunk stops at (next round's first)
     ch[0].start_bit = round_bit;
+    for (size_t k = 0; k < K; k++) { ch[k].sym = std::move(pool[k]); ch[k].sym.clear(); }
     // 1. block starts (chunk k looks inside its own byte range; the sentinel looks right after the round)
     run(K + 1, [&](size_t k) {
       if (k == 0 || (k == K && last_round)) return;
@@ -893,8 +895,8 @@ inline bool gunzip_parallel(const uint8_t* p, size_t n, TextBuf& out, int thread
         for (size_t q = 0; q < m;) { const size_t mm = std::min<size_t>(m - q, 1u << 30); cc = crc(cc, (const unsigned char*)o + q, (unsigned int)mm); q += mm; }
         c.crc = cc;
       }
-      c.sym.release();
     });
+    for (size_t k = 0; k < K; k++) pool[k] = std::move(ch[k].sym);
     for (char b : bad) if (b) return false;
     if (crc && crc_combine)
       for (size_t u = 0; u < use.size(); u++) {
